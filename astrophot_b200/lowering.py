@@ -1,0 +1,296 @@
+"""Lower a model tree to the flat tables of the C ABI.
+
+The reference evaluates a group by walking Python objects, one torch op at a
+time, and scatters per-model Jacobians into a dense (H, W, P) tensor
+(`group_model_object.py:183-283`).  Here the walk happens once: the tree
+becomes a source table (kind, windows in image pixels, parameter slots,
+sampling knobs), an image table (geometry + data/weight/mask pointers), a PSF
+table and a parameter table (transform + limits).  Everything the kernels need
+about windows — the quirk that a sub-model inside a group is *sampled* over
+the group's window but *differentiated* over its own
+(`group_model_object.py:211-227` vs `_model_methods.py:294-299`) — is encoded
+as three rectangles per source: ``out``, ``fwd`` and ``jac``.
+"""
+import numpy as np
+import torch
+
+from . import AP_config
+from . import scene as sc
+from .errors import SpecificationConflict, InvalidParameter
+from .image import (Image_List, Jacobian_Image, Jacobian_Image_List, Model_Image, Model_Image_List,
+                    PSF_Image, Window, Window_List)
+from .param import Parameter_Node
+
+__all__ = ["lower", "wrap_model_images", "wrap_jacobian_images", "LoweringInfo"]
+
+
+class LoweringInfo:
+    """Host-side bookkeeping that goes with a Scene."""
+
+    def __init__(self):
+        self.windows = []       # Window of each scene image (the evaluated region)
+        self.targets = []       # Target image (full) of each scene image
+        self.is_list = False
+        self.identities = None
+        self.components = []    # component model per source
+
+
+def _resolve_leaf(node):
+    """Follow pointer nodes to the leaf that owns the tensor."""
+    seen = 0
+    while isinstance(node._value, Parameter_Node):
+        node = node._value
+        seen += 1
+        if seen > 64:
+            raise InvalidParameter("pointer chain too long")
+    if callable(node._value) and not isinstance(node._value, torch.Tensor):
+        raise SpecificationConflict(
+            f"parameter '{node.name}' is function-valued; only tensor and pointer values can be lowered to the device")
+    return node
+
+
+def _components(model):
+    from .models import Group_Model
+
+    if isinstance(model, Group_Model):
+        out = []
+        for sub in model.models.values():
+            out.extend(_components(sub))
+        return out
+    return [model]
+
+
+def _rect(region: Window, win: Window):
+    """Pixel rectangle (x0, y0, w, h) of ``win`` inside ``region``."""
+    rows, cols = region.get_self_indices(win)
+    return (cols.start, rows.start, max(cols.stop - cols.start, 0), max(rows.stop - rows.start, 0))
+
+
+_SAMPLING = {"midpoint": sc.SAMPLE_MIDPOINT, "simpsons": sc.SAMPLE_SIMPSONS, "trapezoid": sc.SAMPLE_TRAPEZOID}
+
+
+def _shift_code(name):
+    if name == "none":
+        return sc.SHIFT_NONE
+    if name == "bilinear":
+        return sc.SHIFT_BILINEAR
+    if isinstance(name, str) and name.startswith("lanczos"):
+        raise SpecificationConflict("lanczos sub-pixel shifts are not implemented in astrophot_b200 yet (SURVEY.md §8f)")
+    raise SpecificationConflict(f"unrecognized subpixel shift method: {name}")
+
+
+def lower(model, window=None, for_fit=False):
+    """Build (Scene, LoweringInfo) for ``model`` evaluated on ``window``
+    (default: the model's own window).  ``for_fit`` ORs the model's
+    ``fit_mask()`` into each image mask the way ``LM.__init__`` does
+    (`fit/lm.py:204-222`)."""
+    from .models import Group_Model, PSF_Model, Point_Source, Component_Model
+
+    info = LoweringInfo()
+    target = model.target
+    info.is_list = isinstance(target, Image_List)
+    is_group = isinstance(model, Group_Model)
+
+    # ---- regions (one scene image per target image)
+    mwin = model.window
+    if window is not None:
+        mwin = mwin & window
+    if info.is_list:
+        targets = list(target.image_list)
+        regions = list(mwin.window_list)
+    else:
+        targets = [target]
+        regions = [mwin]
+    images = []
+    fmask = None
+    if for_fit:
+        fmask = model.fit_mask()
+        fmask = list(fmask) if isinstance(fmask, (tuple, list)) else [fmask]
+        if sum(int(torch.sum(f)) for f in fmask) == 0:
+            fmask = None
+    for k, (tar, reg) in enumerate(zip(targets, regions)):
+        sub = tar[reg]
+        w = sub.window
+        mask = sub.mask if getattr(sub, "has_mask", False) else None
+        if fmask is not None:
+            fm = fmask[k]
+            if window is not None:   # fit_mask() is on the model window; cut to the requested region
+                rows, cols = model.window.window_list[k].get_self_indices(w) if info.is_list else model.window.get_self_indices(w)
+                fm = fm[rows, cols]
+            mask = fm if mask is None else (mask | fm)
+        images.append(sc.SceneImage(
+            H=int(w._shape[1]), W=int(w._shape[0]), S=w._S.copy(), rij=w._rij.copy(), rxy=w._rxy.copy(),
+            data=sub.data.contiguous(),
+            weight=sub.weight.contiguous() if getattr(sub, "has_weight", False) else None,
+            mask=None if mask is None else mask.contiguous()))
+        info.windows.append(w)
+        info.targets.append(tar)
+    ident_to_img = {t.identity: i for i, t in enumerate(targets)}
+
+    # ---- parameter table
+    leaves = list(model.parameters.flat(include_locked=False, include_links=False).values())
+    slot_of = {}
+    transform, lo, hi = [], [], []
+    n = 0
+    for leaf in leaves:
+        m = leaf.mask.reshape(-1).numpy()
+        l0, l1 = leaf.limits
+        l0 = None if l0 is None else np.broadcast_to(l0.numpy(), leaf.shape).reshape(-1)
+        l1 = None if l1 is None else np.broadcast_to(l1.numpy(), leaf.shape).reshape(-1)
+        for e in range(leaf.size):
+            if not m[e]:
+                continue
+            slot_of[(leaf.identity, e)] = n
+            a = np.nan if l0 is None else float(l0[e])
+            b = np.nan if l1 is None else float(l1[e])
+            if leaf.cyclic:
+                t = sc.TR_CYCLIC
+            elif l0 is None and l1 is None:
+                t = sc.TR_NONE
+            elif l1 is None:
+                t = sc.TR_LOWER
+            elif l0 is None:
+                t = sc.TR_UPPER
+            else:
+                t = sc.TR_BOTH
+            transform.append(t)
+            lo.append(a)
+            hi.append(b)
+            n += 1
+    info.identities = list(model.parameters.vector_identities())
+
+    # ---- sources
+    psfs, psf_index = [], {}
+    sources = []
+    for comp in _components(model):
+        if not isinstance(comp, Component_Model) or comp._kind is None:
+            raise SpecificationConflict(
+                f"model type '{comp.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §2)")
+        if comp.mask is not None:
+            raise SpecificationConflict("per-model masks are not supported by astrophot_b200 yet")
+        ii = ident_to_img.get(comp.target.identity)
+        if ii is None:
+            raise SpecificationConflict(f"{comp.name}: target not part of the evaluated model's target")
+        region = info.windows[ii]
+        cwin = comp.window
+        out = _rect(region, cwin)
+        if out[2] <= 0 or out[3] <= 0:
+            continue
+        jac = out
+        fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
+
+        # elements
+        names = list(sc.ELEMS[comp._kind])
+        nodes = []
+        if isinstance(comp, PSF_Model):
+            have = set(comp._parameter_order)
+        for nm in names:
+            if nm in ("cx", "cy"):
+                nodes.append((comp.parameters["center"], 0 if nm == "cx" else 1))
+            elif isinstance(comp, PSF_Model) and nm in ("q", "PA") and nm not in have:
+                nodes.append((None, 1.0 if nm == "q" else 0.0))
+            else:
+                nodes.append((comp.parameters[nm], 0))
+        prof = []
+        if comp._kind == sc.KIND_SPLINE:
+            pn = _resolve_leaf(comp.parameters["I(R)"])
+            if pn.prof is None or pn.value is None:
+                raise InvalidParameter(f"{comp.name}: spline model needs I(R) values and prof radii")
+            prof = [float(v) for v in pn.prof.reshape(-1)]
+            if len(prof) > sc.MAX_PROF:
+                raise SpecificationConflict(f"spline with more than {sc.MAX_PROF} nodes")
+            if not getattr(comp, "extend_profile", True):
+                raise SpecificationConflict("extend_profile=False is not supported by astrophot_b200")
+            for k in range(len(prof)):
+                nodes.append((comp.parameters["I(R)"], k))
+        slot, cval = [], []
+        for node, e in nodes:
+            if node is None:
+                slot.append(-1)
+                cval.append(float(e))
+                continue
+            leaf = _resolve_leaf(node)
+            if leaf.value is None:
+                if leaf.name == "center":   # sky models: centre is irrelevant
+                    slot.append(-1)
+                    cval.append(0.0)
+                    continue
+                raise InvalidParameter(f"{comp.name}: parameter '{leaf.name}' has no value")
+            slot.append(slot_of.get((leaf.identity, e), -1))
+            cval.append(float(leaf.value.reshape(-1)[e]))
+
+        # sampling knobs
+        sm = comp.sampling_mode
+        quad_init = 3
+        if sm in _SAMPLING:
+            smode = _SAMPLING[sm]
+        elif isinstance(sm, str) and "quad" in sm:
+            smode = sc.SAMPLE_QUAD
+            quad_init = int(sm[sm.find(":") + 1:])
+        else:
+            raise SpecificationConflict(
+                f"{comp.name} has unknown sampling mode: {sm}. Should be one of: midpoint, simpsons, quad:level, trapezoid")
+        if smode == sc.SAMPLE_TRAPEZOID:
+            raise SpecificationConflict("sampling_mode='trapezoid' is not implemented in astrophot_b200 yet")
+        im = comp.integrate_mode
+        if im == "none":
+            imode = sc.INTEGRATE_NONE
+        elif im == "threshold":
+            imode = sc.INTEGRATE_THRESHOLD
+        else:
+            raise SpecificationConflict(
+                f"{comp.name} has unknown integration mode: {im}. Should be one of: none, threshold")
+        if comp._kind in (sc.KIND_FLAT_SKY, sc.KIND_POINT):
+            imode = sc.INTEGRATE_NONE
+
+        # psf
+        pidx = -1
+        pmode = comp.psf_mode
+        if pmode not in ("none", "full"):
+            raise SpecificationConflict(f"unknown psf_mode: {pmode}")
+        if comp.psf_convolve_mode not in ("fft", "direct"):
+            raise SpecificationConflict(f"unrecognized psf_convolve_mode: {comp.psf_convolve_mode}")
+        if pmode == "full":
+            psf = comp.psf
+            if psf is None:
+                raise SpecificationConflict(f"{comp.name}: psf_mode='full' but no PSF on model or target")
+            if not isinstance(psf, PSF_Image):
+                raise SpecificationConflict(
+                    "PSF *models* as auxiliary PSFs are not lowered yet; sample the PSF model once and pass the PSF_Image")
+            up = int(np.round(float(region.pixel_length) / float(psf.window.pixel_length)))
+            if up != 1:
+                raise SpecificationConflict("super-sampled PSFs (psf_upscale > 1) are not implemented yet (SURVEY.md §8f)")
+            if id(psf) not in psf_index:
+                psf_index[id(psf)] = len(psfs)
+                psfs.append(sc.ScenePSF(data=psf.data.contiguous()))
+            pidx = psf_index[id(psf)]
+        flags = comp._flags
+        if isinstance(comp, PSF_Model) and comp.normalize_psf:
+            flags |= sc.FLAG_NORMALIZE
+        sources.append(sc.SceneSource(
+            kind=comp._kind, image=ii, out=out, fwd=fwd, jac=jac, slot=slot, cval=cval, flags=flags, prof=prof,
+            sampling_mode=smode, quad_init=quad_init, integrate_mode=imode,
+            quad_level=int(comp.integrate_quad_level), gridding=int(comp.integrate_gridding),
+            max_depth=int(comp.integrate_max_depth), tolerance=float(comp.sampling_tolerance),
+            softening=float(comp.softening), ref_mode=comp._ref_mode, psf=pidx,
+            psf_shift=_shift_code(comp.psf_subpixel_shift), name=comp.name))
+        info.components.append(comp)
+
+    scene = sc.Scene(images=images, sources=sources, psfs=psfs,
+                     transform=np.array(transform, dtype=np.int32),
+                     lo=np.array(lo, dtype=np.float64), hi=np.array(hi, dtype=np.float64),
+                     identities=info.identities)
+    return scene, info
+
+
+def wrap_model_images(model, info, outs):
+    ims = [Model_Image(data=o, window=w.copy(), zeropoint=t.zeropoint, target_identity=t.identity)
+           for o, w, t in zip(outs, info.windows, info.targets)]
+    return Model_Image_List(ims) if info.is_list else ims[0]
+
+
+def wrap_jacobian_images(model, info, outs):
+    ims = [Jacobian_Image(parameters=list(info.identities), data=o, window=w.copy(), zeropoint=t.zeropoint,
+                          target_identity=t.identity)
+           for o, w, t in zip(outs, info.windows, info.targets)]
+    return Jacobian_Image_List(ims) if info.is_list else ims[0]

@@ -1,0 +1,744 @@
+"""Model types of the forward-model-and-fit hot path.
+
+Same factory and method surface as the reference (``AstroPhot_Model(model_type=
+"sersic galaxy model", target=..., window=..., parameters={...}, psf_mode=...)``,
+``model()``, ``.sample()``, ``.jacobian()``, ``.fit_mask()``; reference:
+`models/core_model.py:26-502`, `model_object.py:24-444`,
+`group_model_object.py:27-365`, `psf_model_object.py:20-330`,
+`point_source.py:17-189`) but none of its arithmetic: every class here is a
+*description* (kind, parameter DAG, window, sampling knobs).  ``sample`` and
+``jacobian`` lower the description to flat tables (``lowering.py``) and hand
+them to the sm_100a library through the C ABI (``cabi.py``).  There is no
+torch/CPU evaluation path in this package.
+
+In scope: sersic / exponential / gaussian / moffat / spline
+galaxy, point, flat sky, group; sersic / exponential / gaussian / moffat /
+moffat2d / spline psf models.  Parameter initialisation heuristics are out of
+scope: give parameter values explicitly.
+"""
+from collections import OrderedDict
+from copy import deepcopy
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import AP_config
+from . import scene as sc
+from .errors import (InvalidTarget, InvalidWindow, NameNotAllowed, SpecificationConflict,
+                     UnrecognizedModel, InvalidParameter)
+from .image import (Image, Image_List, Model_Image, PSF_Image, Target_Image, Target_Image_List,
+                    Window, Window_List, Jacobian_Image)
+from .param import Parameter_Node, Param_Unlock, Param_SoftLimits
+
+__all__ = [
+    "AstroPhot_Model", "Component_Model", "Galaxy_Model", "Sersic_Galaxy", "Exponential_Galaxy",
+    "Gaussian_Galaxy", "Moffat_Galaxy", "Spline_Galaxy", "Point_Source", "Sky_Model", "Flat_Sky",
+    "Group_Model", "PSF_Model", "Sersic_PSF", "Exponential_PSF", "Gaussian_PSF", "Moffat_PSF",
+    "Moffat2D_PSF", "Spline_PSF",
+]
+
+
+def _all_subclasses(cls):
+    out = []
+    for sub in cls.__subclasses__():
+        out.append(sub)
+        out.extend(_all_subclasses(sub))
+    return out
+
+
+class AstroPhot_Model:
+    """Base of every model; also the factory: ``AstroPhot_Model(model_type=...)``
+    returns an instance of the class whose ``model_type`` string matches."""
+
+    model_type = "model"
+    parameter_specs = {}
+    _parameter_order = ()
+    usable = False
+    model_names = []
+    special_kwargs = ["parameters", "filename", "model_type", "usable", "models", "psf"]
+
+    def __new__(cls, *, filename=None, model_type=None, **kwargs):
+        if filename is not None:
+            raise NotImplementedError("loading models from file is outside the hot-path scope of astrophot_b200")
+        if model_type is not None:
+            for M in _all_subclasses(AstroPhot_Model):
+                if M.model_type == model_type:
+                    return super().__new__(M)
+            raise UnrecognizedModel(f"Unknown AstroPhot model type: {model_type}")
+        return super().__new__(cls)
+
+    def __init__(self, *, name=None, target=None, window=None, locked=False, **kwargs):
+        self._window = None
+        self._target = None
+        self.name = name
+        self.parameters = Parameter_Node(self.name)
+        self.target = target
+        self.window = window
+        self._locked = locked
+        self.mask = kwargs.get("mask", None)
+        for key, val in kwargs.items():
+            if key in self.special_kwargs or key == "mask":
+                continue
+            setattr(self, key, val)
+
+    # -- naming ----------------------------------------------------------
+    @property
+    def name(self):
+        return self._name
+
+    @name.setter
+    def name(self, name):
+        if name is None:
+            i = 0
+            while f"{self.model_type} [{i}]" in AstroPhot_Model.model_names:
+                i += 1
+            name = f"{self.model_type} [{i}]"
+        if ":" in name or "|" in name:
+            raise NameNotAllowed(
+                "characters '|' and ':' are reserved for internal model operations please do not include these in a model name")
+        self._name = name
+        AstroPhot_Model.model_names.append(name)
+
+    def __del__(self):
+        try:
+            AstroPhot_Model.model_names.remove(self._name)
+        except Exception:
+            pass
+
+    # -- parameters ------------------------------------------------------------
+    @classmethod
+    def build_parameter_specs(cls, user_specs=None):
+        specs = {}
+        for base in reversed(cls.__mro__):
+            specs.update(deepcopy(base.__dict__.get("parameter_specs", {})))
+        if isinstance(user_specs, dict):
+            for p, spec in user_specs.items():
+                if isinstance(spec, Parameter_Node):
+                    specs[p] = spec
+                elif isinstance(spec, dict):
+                    specs.setdefault(p, {}).update(spec)
+                else:
+                    specs.setdefault(p, {})["value"] = spec
+        return specs
+
+    def build_parameters(self):
+        for p in self._parameter_order:
+            if p in self.parameters:
+                continue
+            spec = self.parameter_specs[p]
+            if isinstance(spec, Parameter_Node):
+                self.parameters.link(spec)
+            elif isinstance(spec, dict):
+                self.parameters.link(Parameter_Node(p, **spec))
+            else:
+                raise ValueError(f"unrecognized parameter specification for {p}")
+
+    @property
+    def parameter_order(self):
+        return tuple(P.name for P in self.parameters)
+
+    def __getitem__(self, key):
+        return self.parameters[key]
+
+    def __contains__(self, key):
+        return key in self.parameters
+
+    # -- target / window ---------------------------------------------------
+    @property
+    def target(self):
+        return self._target
+
+    @target.setter
+    def target(self, tar):
+        if not (tar is None or isinstance(tar, Target_Image)):
+            raise InvalidTarget("AstroPhot_Model target must be a Target_Image instance.")
+        self._target = tar
+
+    @property
+    def window(self):
+        if self._window is None:
+            if self.target is None:
+                raise ValueError("This model has no target or window, these must be provided by the user")
+            return self.target.window.copy()
+        return self._window
+
+    @window.setter
+    def window(self, window):
+        self.set_window(window)
+
+    def set_window(self, window):
+        if window is None:
+            self._window = None
+        elif isinstance(window, Window):
+            self._window = window
+        elif len(window) == 2:
+            self._window = self.target.window.copy().crop_to_pixel(window)
+        else:
+            raise InvalidWindow(f"Unrecognized window format: {str(window)}")
+
+    @property
+    def locked(self):
+        return self._locked
+
+    @locked.setter
+    def locked(self, val):
+        self._locked = val
+
+    @property
+    def is_initialized(self):
+        return all((not P.leaf) or (P.value is not None) for P in self.parameters)
+
+    def initialize(self, target=None, parameters=None, **kwargs):
+        """Guessing start values from the data is input prep (out of scope);
+        this only checks that values exist."""
+        for P in self.parameters.flat(include_locked=True).values():
+            if P.value is None:
+                raise InvalidParameter(
+                    f"{self.name}: parameter '{P.name}' has no value. astrophot_b200 does not implement the "
+                    "reference's initialisation heuristics; pass explicit parameter values.")
+
+    def make_model_image(self, window=None):
+        window = self.window if window is None else self.window & window
+        return self.target[window].model_image()
+
+    def fit_mask(self):
+        return torch.zeros_like(self.target[self.window].mask)
+
+    # -- evaluation through the native library -------------------------------
+    def _plan(self, window=None):
+        from .lowering import lower
+        from .cabi import Plan
+
+        scene, info = lower(self, window=window)
+        return Plan(scene), scene, info
+
+    def __call__(self, image=None, parameters=None, window=None, as_representation=False, **kwargs):
+        if isinstance(parameters, (torch.Tensor, np.ndarray, list, tuple)):
+            if as_representation:
+                self.parameters.vector_set_representation(parameters)
+            else:
+                self.parameters.vector_set_values(parameters)
+        return self.sample(image=image, window=window, **kwargs)
+
+    def sample(self, image=None, window=None, parameters=None):
+        """Model flux on ``window`` (default: the model's window); added into
+        ``image`` when one is given (reference: `model_object.py:258-375`,
+        `group_model_object.py:183-231`)."""
+        from .lowering import wrap_model_images
+
+        plan, scene, info = self._plan(window)
+        x = torch.as_tensor(self.parameters.vector_values().numpy(), dtype=torch.float64,
+                            device=AP_config.ap_device)
+        outs = plan.sample(x, as_rep=False)
+        result = wrap_model_images(self, info, outs)
+        if image is None:
+            return result
+        image += result
+        return image
+
+    def jacobian(self, parameters=None, as_representation=False, window=None, pass_jacobian=None, **kwargs):
+        """d(model)/d(parameters) as a ``Jacobian_Image`` (columns ordered as
+        ``parameters.vector_identities()``).  Materialising J is for small
+        problems and tests; ``fit.LM`` never does (reference:
+        `_model_methods.py:260-347`, `group_model_object.py:233-283`)."""
+        from .lowering import wrap_jacobian_images
+
+        if parameters is not None:
+            if as_representation:
+                self.parameters.vector_set_representation(parameters)
+            else:
+                self.parameters.vector_set_values(parameters)
+        plan, scene, info = self._plan(window)
+        vec = self.parameters.vector_representation() if as_representation else self.parameters.vector_values()
+        x = torch.as_tensor(vec.numpy(), dtype=torch.float64, device=AP_config.ap_device)
+        outs = plan.jacobian(x, as_rep=as_representation)
+        result = wrap_jacobian_images(self, info, outs)
+        if pass_jacobian is not None:
+            pass_jacobian += result
+            return pass_jacobian
+        return result
+
+    def total_flux(self, parameters=None, window=None):
+        return torch.sum(self.sample(window=window).data)
+
+    def get_state(self, *args, **kwargs):
+        return {"name": self.name, "model_type": self.model_type}
+
+    @classmethod
+    def List_Models(cls, usable=None):
+        models = _all_subclasses(cls)
+        if usable is not None:
+            models = [m for m in models if m.usable is usable]
+        return models
+
+    @classmethod
+    def List_Model_Names(cls, usable=None):
+        return sorted((m.model_type for m in cls.List_Models(usable)), key=lambda n: n[::-1])
+
+    def __eq__(self, other):
+        return self is other
+
+    __hash__ = object.__hash__
+
+    def __str__(self):
+        return str(self.parameters)
+
+
+class Component_Model(AstroPhot_Model):
+    """A single light source (reference: `model_object.py:24-111` for the
+    attribute list and defaults)."""
+
+    model_type = AstroPhot_Model.model_type
+    parameter_specs = {"center": {"units": "arcsec", "uncertainty": [0.1, 0.1]}}
+    _parameter_order = ("center",)
+
+    psf_mode = "none"                 # none, full
+    psf_convolve_mode = "fft"         # fft, direct  (same result; the library picks by PSF size)
+    psf_subpixel_shift = "bilinear"   # bilinear, lanczos:k, none
+    sampling_mode = "midpoint"        # midpoint, simpsons, quad:N, trapezoid
+    sampling_tolerance = 1e-2
+    integrate_mode = "threshold"      # none, threshold
+    integrate_max_depth = 3
+    integrate_gridding = 5
+    integrate_quad_level = 3
+    jacobian_chunksize = 10           # kept for API compatibility; unused (J is never chunked here)
+    image_chunksize = 1000
+    softening = 1e-3
+
+    track_attrs = ["psf_mode", "psf_convolve_mode", "psf_subpixel_shift", "sampling_mode", "sampling_tolerance",
+                   "integrate_mode", "integrate_max_depth", "integrate_gridding", "integrate_quad_level",
+                   "jacobian_chunksize", "image_chunksize", "softening"]
+    _kind = None
+    _ref_mode = sc.REF_MEAN
+    _flags = 0
+
+    def __init__(self, *, name=None, **kwargs):
+        self._psf = None
+        super().__init__(name=name, **kwargs)
+        self.parameter_specs = self.build_parameter_specs(kwargs.get("parameters", None))
+        self.build_parameters()
+        if isinstance(kwargs.get("parameters", None), torch.Tensor):
+            self.parameters.value = kwargs["parameters"]
+        if "psf" in kwargs:
+            self.psf = kwargs["psf"]
+
+    @property
+    def psf(self):
+        if self._psf is None:
+            try:
+                return self.target.psf
+            except AttributeError:
+                return None
+        return self._psf
+
+    @psf.setter
+    def psf(self, val):
+        if val is None:
+            self._psf = None
+        elif isinstance(val, PSF_Image):
+            self._psf = val
+        elif isinstance(val, AstroPhot_Model):
+            self.set_aux_psf(val)
+        else:
+            self._psf = PSF_Image(data=val, pixelscale=self.target.pixelscale)
+            AP_config.ap_logger.warning(
+                "Setting PSF with pixel matrix, assuming target pixelscale is the same as PSF pixelscale. To remove "
+                "this warning, set PSFs as an ap.image.PSF_Image or ap.models.AstroPhot_Model object instead.")
+
+    def set_aux_psf(self, aux_psf, add_parameters=True):
+        self._psf = aux_psf
+        if add_parameters:
+            self.parameters.link(aux_psf.parameters)
+
+    def initialize(self, target=None, parameters=None, **kwargs):
+        c = self.parameters["center"]
+        if c.value is None:
+            with Param_Unlock(c), Param_SoftLimits(c):
+                c.value = self.window.center
+        super().initialize(target=target, parameters=parameters)
+
+    @property
+    def target(self):
+        return self._target
+
+    @target.setter
+    def target(self, tar):
+        if not (tar is None or isinstance(tar, Target_Image)):
+            raise InvalidTarget("AstroPhot_Model target must be a Target_Image instance.")
+        ident = getattr(self, "_target_identity", None)
+        if isinstance(tar, Target_Image_List) and ident is not None:
+            for sub in tar:
+                if sub.identity == ident:
+                    tar = sub
+                    break
+            else:
+                raise InvalidTarget(
+                    f"Could not find target in Target_Image_List with matching identity to {self.name}: {ident}")
+        self._target = tar
+        if tar is not None and not isinstance(tar, Image_List):
+            self._target_identity = tar.identity
+
+
+class Galaxy_Model(Component_Model):
+    """Adds axis ratio ``q`` and position angle ``PA`` (reference:
+    `galaxy_model_object.py:44-53`)."""
+
+    model_type = f"galaxy {Component_Model.model_type}"
+    parameter_specs = {
+        "q": {"units": "b/a", "limits": (0, 1), "uncertainty": 0.03},
+        "PA": {"units": "radians", "limits": (0, np.pi), "cyclic": True, "uncertainty": 0.06},
+    }
+    _parameter_order = Component_Model._parameter_order + ("q", "PA")
+
+
+class Sersic_Galaxy(Galaxy_Model):
+    """I(R) = Ie exp(-b_n ((R/Re)^(1/n) - 1)) (reference: `sersic_model.py:41-91`)."""
+
+    model_type = f"sersic {Galaxy_Model.model_type}"
+    parameter_specs = {
+        "n": {"units": "none", "limits": (0.36, 8), "uncertainty": 0.05},
+        "Re": {"units": "arcsec", "limits": (0, None)},
+        "Ie": {"units": "log10(flux/arcsec^2)"},
+    }
+    _parameter_order = Galaxy_Model._parameter_order + ("n", "Re", "Ie")
+    usable = True
+    _kind = sc.KIND_SERSIC
+    _ref_mode = sc.REF_SERSIC_FLUX    # total_flux / numel, sersic_model.py:87-89
+
+
+class Exponential_Galaxy(Galaxy_Model):
+    model_type = f"exponential {Galaxy_Model.model_type}"
+    parameter_specs = {
+        "Re": {"units": "arcsec", "limits": (0, None)},
+        "Ie": {"units": "log10(flux/arcsec^2)"},
+    }
+    _parameter_order = Galaxy_Model._parameter_order + ("Re", "Ie")
+    usable = True
+    _kind = sc.KIND_EXPONENTIAL
+
+
+class Gaussian_Galaxy(Galaxy_Model):
+    model_type = f"gaussian {Galaxy_Model.model_type}"
+    parameter_specs = {
+        "sigma": {"units": "arcsec", "limits": (0, None)},
+        "flux": {"units": "log10(flux)"},
+    }
+    _parameter_order = Galaxy_Model._parameter_order + ("sigma", "flux")
+    usable = True
+    _kind = sc.KIND_GAUSSIAN
+
+
+class Moffat_Galaxy(Galaxy_Model):
+    model_type = f"moffat {Galaxy_Model.model_type}"
+    parameter_specs = {
+        "n": {"units": "none", "limits": (0.1, 10), "uncertainty": 0.05},
+        "Rd": {"units": "arcsec", "limits": (0, None)},
+        "I0": {"units": "log10(flux/arcsec^2)"},
+    }
+    _parameter_order = Galaxy_Model._parameter_order + ("n", "Rd", "I0")
+    usable = True
+    _kind = sc.KIND_MOFFAT
+
+
+class Spline_Galaxy(Galaxy_Model):
+    """log10 brightness is a cubic spline through ``I(R)`` at radii ``I(R).prof``
+    (reference: `spline_model.py:27-53`)."""
+
+    model_type = f"spline {Galaxy_Model.model_type}"
+    parameter_specs = {"I(R)": {"units": "log10(flux/arcsec^2)"}}
+    _parameter_order = Galaxy_Model._parameter_order + ("I(R)",)
+    usable = True
+    extend_profile = True
+    _kind = sc.KIND_SPLINE
+
+
+class Point_Source(Component_Model):
+    """Delta function times the PSF (reference: `point_source.py:17-189`)."""
+
+    model_type = f"point {Component_Model.model_type}"
+    parameter_specs = {"flux": {"units": "log10(flux)"}}
+    _parameter_order = Component_Model._parameter_order + ("flux",)
+    usable = True
+    _kind = sc.KIND_POINT
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.psf is None:
+            raise ValueError("Point_Source needs psf information")
+
+    @property
+    def psf_mode(self):
+        return "full"
+
+    @psf_mode.setter
+    def psf_mode(self, value):
+        pass
+
+
+class Sky_Model(Component_Model):
+    """Sky is never convolved nor sub-pixel integrated (reference:
+    `sky_model_object.py:21-35`)."""
+
+    model_type = f"sky {Component_Model.model_type}"
+    parameter_specs = {"center": {"units": "arcsec", "locked": True, "uncertainty": 0.0}}
+
+    @property
+    def psf_mode(self):
+        return "none"
+
+    @psf_mode.setter
+    def psf_mode(self, val):
+        pass
+
+    @property
+    def integrate_mode(self):
+        return "none"
+
+    @integrate_mode.setter
+    def integrate_mode(self, val):
+        pass
+
+
+class Flat_Sky(Sky_Model):
+    model_type = f"flat {Sky_Model.model_type}"
+    parameter_specs = {"F": {"units": "log10(flux/arcsec^2)"}}
+    _parameter_order = Sky_Model._parameter_order + ("F",)
+    usable = True
+    _kind = sc.KIND_FLAT_SKY
+
+
+# ---------------------------------------------------------------------------
+# PSF models: target is a PSF_Image, centre locked at (0, 0), normalised
+# ---------------------------------------------------------------------------
+class PSF_Model(Component_Model):
+    model_type = f"psf {AstroPhot_Model.model_type}"
+    parameter_specs = {"center": {"units": "arcsec", "value": (0.0, 0.0), "uncertainty": (0.1, 0.1), "locked": True}}
+    _parameter_order = ("center",)
+    model_integrated = False
+    normalize_psf = True
+    sampling_mode = "simpsons"
+    sampling_tolerance = 1e-3
+    integrate_mode = "threshold"
+    _flags = sc.FLAG_RADIAL
+
+    @property
+    def psf_mode(self):
+        return "none"
+
+    @psf_mode.setter
+    def psf_mode(self, val):
+        pass
+
+    @property
+    def target(self):
+        return self._target
+
+    @target.setter
+    def target(self, tar):
+        if not (tar is None or isinstance(tar, PSF_Image)):
+            raise InvalidTarget("PSF_Model target must be a PSF_Image instance.")
+        self._target = tar
+
+    def make_model_image(self, window=None):
+        window = self.window if window is None else self.window & window
+        return self.target[window].model_image()
+
+    def fit_mask(self):
+        return torch.zeros_like(self.target[self.window].mask)
+
+
+class Sersic_PSF(PSF_Model):
+    model_type = f"sersic {PSF_Model.model_type}"
+    parameter_specs = {
+        "n": {"units": "none", "limits": (0.36, 8), "uncertainty": 0.05},
+        "Re": {"units": "arcsec", "limits": (0, None)},
+        "Ie": {"units": "log10(flux/arcsec^2)", "value": 0.0, "locked": True},
+    }
+    _parameter_order = PSF_Model._parameter_order + ("n", "Re", "Ie")
+    usable = True
+    _kind = sc.KIND_SERSIC
+
+
+class Exponential_PSF(PSF_Model):
+    model_type = f"exponential {PSF_Model.model_type}"
+    parameter_specs = {
+        "Re": {"units": "arcsec", "limits": (0, None)},
+        "Ie": {"units": "log10(flux/arcsec^2)", "value": 0.0, "locked": True},
+    }
+    _parameter_order = PSF_Model._parameter_order + ("Re", "Ie")
+    usable = True
+    _kind = sc.KIND_EXPONENTIAL
+
+
+class Gaussian_PSF(PSF_Model):
+    model_type = f"gaussian {PSF_Model.model_type}"
+    parameter_specs = {
+        "sigma": {"units": "arcsec", "limits": (0, None)},
+        "flux": {"units": "log10(flux)", "value": 0.0, "locked": True},
+    }
+    _parameter_order = PSF_Model._parameter_order + ("sigma", "flux")
+    usable = True
+    _kind = sc.KIND_GAUSSIAN
+
+
+class Moffat_PSF(PSF_Model):
+    model_type = f"moffat {PSF_Model.model_type}"
+    parameter_specs = {
+        "n": {"units": "none", "limits": (0.1, 10), "uncertainty": 0.05},
+        "Rd": {"units": "arcsec", "limits": (0, None)},
+        "I0": {"units": "log10(flux/arcsec^2)", "value": 0.0, "locked": True},
+    }
+    _parameter_order = PSF_Model._parameter_order + ("n", "Rd", "I0")
+    usable = True
+    _kind = sc.KIND_MOFFAT
+
+
+class Moffat2D_PSF(PSF_Model):
+    model_type = f"moffat2d {PSF_Model.model_type}"
+    parameter_specs = {
+        "q": {"units": "b/a", "limits": (0, 1), "uncertainty": 0.03},
+        "PA": {"units": "radians", "limits": (0, np.pi), "cyclic": True, "uncertainty": 0.06},
+        "n": {"units": "none", "limits": (0.1, 10), "uncertainty": 0.05},
+        "Rd": {"units": "arcsec", "limits": (0, None)},
+        "I0": {"units": "log10(flux/arcsec^2)", "value": 0.0, "locked": True},
+    }
+    _parameter_order = PSF_Model._parameter_order + ("q", "PA", "n", "Rd", "I0")
+    usable = True
+    _kind = sc.KIND_MOFFAT
+    _flags = 0
+
+
+class Spline_PSF(PSF_Model):
+    model_type = f"spline {PSF_Model.model_type}"
+    parameter_specs = {"I(R)": {"units": "log10(flux/arcsec^2)"}}
+    _parameter_order = PSF_Model._parameter_order + ("I(R)",)
+    usable = True
+    extend_profile = True
+    _kind = sc.KIND_SPLINE
+
+
+# ---------------------------------------------------------------------------
+# Group
+# ---------------------------------------------------------------------------
+class Group_Model(AstroPhot_Model):
+    """Sum of sub-models (reference: `group_model_object.py:27-365`).  On the
+    device a group is just a longer source table; nothing is evaluated per
+    sub-model in Python."""
+
+    model_type = f"group {AstroPhot_Model.model_type}"
+    usable = True
+
+    def __init__(self, *, name=None, models=None, **kwargs):
+        self.models = OrderedDict()
+        self._psf_mode = "none"
+        super().__init__(name=name, models=models, **kwargs)
+        if models is not None:
+            self.add_model(models)
+        self.update_window()
+        if "psf_mode" in kwargs:
+            self.psf_mode = kwargs["psf_mode"]
+
+    def add_model(self, model):
+        if isinstance(model, (tuple, list)):
+            for mod in model:
+                self.add_model(mod)
+            return
+        if model.name in self.models:
+            if model is self.models[model.name]:
+                return
+            raise KeyError(
+                f"{self.name} already has model with name {model.name}, every model must have a unique name.")
+        self.models[model.name] = model
+        self.parameters.link(model.parameters)
+        # the group's psf_mode and target override the sub-model's (group_model_object.py:85-89)
+        self.psf_mode = self.psf_mode
+        self.target = self.target
+        self.update_window()
+
+    def update_window(self, include_locked=False):
+        if isinstance(self.target, Image_List):
+            wins = [None] * len(self.target.image_list)
+            for model in self.models.values():
+                if model.locked and not include_locked:
+                    continue
+                if isinstance(model.target, Image_List):
+                    pairs = zip(model.target, model.window)
+                else:
+                    pairs = [(model.target, model.window)]
+                for tar, win in pairs:
+                    i = self.target.index(tar)
+                    if wins[i] is None:
+                        wins[i] = win.copy()
+                    else:
+                        wins[i] |= win
+            self._window = Window_List(wins) if all(w is not None for w in wins) and wins else None
+        else:
+            new = None
+            for model in self.models.values():
+                if model.locked and not include_locked:
+                    continue
+                if new is None:
+                    new = model.window.copy()
+                else:
+                    new |= model.window
+            self._window = new
+
+    @property
+    def target(self):
+        return self._target
+
+    @target.setter
+    def target(self, tar):
+        if not (tar is None or isinstance(tar, Target_Image)):
+            raise InvalidTarget("Group_Model target must be a Target_Image instance.")
+        self._target = tar
+        for model in getattr(self, "models", {}).values():
+            model.target = tar
+
+    @property
+    def psf_mode(self):
+        return self._psf_mode
+
+    @psf_mode.setter
+    def psf_mode(self, value):
+        self._psf_mode = value
+        for model in getattr(self, "models", {}).values():
+            model.psf_mode = value
+
+    def initialize(self, target=None, parameters=None, **kwargs):
+        for model in self.models.values():
+            model.initialize(target=target)
+
+    def fit_mask(self):
+        """True where no sub-model has anything to say (reference:
+        `group_model_object.py:152-181`)."""
+        if isinstance(self.target, Image_List):
+            masks = [torch.ones_like(m) for m in self.target[self.window].mask]
+            for model in self.models.values():
+                sub = model.fit_mask()
+                if isinstance(model.target, Image_List):
+                    trip = zip(model.target, model.window, sub)
+                else:
+                    trip = [(model.target, model.window, sub)]
+                for tar, win, sm in trip:
+                    i = self.target.index(tar)
+                    gw = self.window.window_list[i]
+                    masks[i][gw.get_self_indices(win)] &= sm[win.get_self_indices(gw)]
+            return tuple(masks)
+        mask = torch.ones_like(self.target[self.window].mask)
+        for model in self.models.values():
+            mask[self.window.get_self_indices(model.window)] &= model.fit_mask()[model.window.get_self_indices(self.window)]
+        return mask
+
+    def make_model_image(self, window=None):
+        window = self.window if window is None else self.window & window
+        return self.target[window].model_image()
+
+    def __iter__(self):
+        return iter(self.models.values())
+
+    def get_state(self, *args, **kwargs):
+        state = super().get_state()
+        state["models"] = {m.name: m.get_state() for m in self.models.values()}
+        return state

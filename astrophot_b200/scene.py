@@ -1,0 +1,104 @@
+"""Flat "scene" tables: what a lowered model tree looks like at the C-ABI.
+
+These dataclasses are the Python mirror of the structs in
+``include/astrophot_b200.h`` (``apb_image_t``, ``apb_source_t``, ``apb_psf_t``,
+``apb_param_t``).  ``lowering.py`` builds them from the model/parameter/image
+objects; ``cabi.py`` packs them into ctypes structs for the sm_100a library;
+the CPU oracle under ``oracle/`` (test infrastructure only) consumes the very
+same tables, which is what makes oracle-vs-CUDA parity tests meaningful.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+# -- enumerations (values are part of the C ABI) -------------------------------
+KIND_SERSIC, KIND_EXPONENTIAL, KIND_GAUSSIAN, KIND_MOFFAT, KIND_SPLINE, KIND_POINT, KIND_FLAT_SKY = range(7)
+KIND_NAMES = ["sersic", "exponential", "gaussian", "moffat", "spline", "point", "flat_sky"]
+
+FLAG_RADIAL = 1        # no rotation / axis ratio (PSF-model kinds): elements skip q, PA
+FLAG_NORMALIZE = 2     # divide the sampled stamp by its sum (PSF models)
+
+TR_NONE, TR_LOWER, TR_UPPER, TR_BOTH, TR_CYCLIC = range(5)
+
+SAMPLE_MIDPOINT, SAMPLE_SIMPSONS, SAMPLE_QUAD, SAMPLE_TRAPEZOID = range(4)
+INTEGRATE_NONE, INTEGRATE_THRESHOLD = range(2)
+REF_MEAN, REF_SERSIC_FLUX = range(2)
+SHIFT_NONE, SHIFT_BILINEAR = 0, 1   # SHIFT_LANCZOS + order = 10 + order
+SHIFT_LANCZOS = 10
+
+MAX_ELEM = 24
+MAX_PROF = 20
+
+# number of leading elements of each kind (before any spline nodes)
+ELEMS = {
+    KIND_SERSIC: ("cx", "cy", "q", "PA", "n", "Re", "Ie"),
+    KIND_EXPONENTIAL: ("cx", "cy", "q", "PA", "Re", "Ie"),
+    KIND_GAUSSIAN: ("cx", "cy", "q", "PA", "sigma", "flux"),
+    KIND_MOFFAT: ("cx", "cy", "q", "PA", "n", "Rd", "I0"),
+    KIND_SPLINE: ("cx", "cy", "q", "PA"),
+    KIND_POINT: ("cx", "cy", "flux"),
+    KIND_FLAT_SKY: ("cx", "cy", "F"),
+}
+
+
+@dataclass
+class SceneImage:
+    """One target image region (the fit window of one band)."""
+    H: int
+    W: int
+    S: np.ndarray            # (2,2) pixelscale
+    rij: np.ndarray          # (2,) reference pixel
+    rxy: np.ndarray          # (2,) reference plane position
+    data: object = None      # (H,W) tensor/array or None
+    weight: object = None    # (H,W) or None (= ones)
+    mask: object = None      # (H,W) bool/uint8, True = ignore; or None
+
+
+@dataclass
+class ScenePSF:
+    data: object             # (h,w) odd-shaped stamp, un-normalised
+
+
+@dataclass
+class SceneSource:
+    kind: int
+    image: int
+    out: tuple               # (x0, y0, w, h) output window, image pixel indices
+    fwd: tuple               # working window when sampled inside the forward model
+    jac: tuple               # working window when differentiated
+    slot: List[int]          # per element: index into x, or -1 = locked
+    cval: List[float]        # per element: value when locked (natural units)
+    flags: int = 0
+    prof: List[float] = field(default_factory=list)   # spline node radii
+    sampling_mode: int = SAMPLE_MIDPOINT
+    quad_init: int = 3       # N of "quad:N"
+    integrate_mode: int = INTEGRATE_THRESHOLD
+    quad_level: int = 3
+    gridding: int = 5
+    max_depth: int = 3
+    tolerance: float = 1e-2
+    softening: float = 1e-3
+    ref_mode: int = REF_MEAN
+    psf: int = -1
+    psf_shift: int = SHIFT_BILINEAR
+    name: str = ""
+
+    @property
+    def n_elem(self):
+        return len(self.slot)
+
+
+@dataclass
+class Scene:
+    images: List[SceneImage]
+    sources: List[SceneSource]
+    psfs: List[ScenePSF]
+    transform: np.ndarray    # (P,) int32
+    lo: np.ndarray           # (P,) float64 (nan when absent)
+    hi: np.ndarray           # (P,)
+    identities: Optional[list] = None   # (P,) parameter identity strings (host only)
+
+    @property
+    def n_par(self):
+        return int(len(self.transform))

@@ -1,0 +1,809 @@
+"""CPU oracle for the AstroPhot forward-model-and-fit hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``astrophot_b200/`` imports this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may.  It is a plain numpy restatement
+of the reference's algorithm, written from SURVEY.md Appendix B and the
+reference sources cited next to each function, operating on the same flat
+``Scene`` tables (``astrophot_b200/scene.py``) that are handed to the CUDA
+library.
+
+Parity status: PINNED.  ``oracle/make_golden.py`` imports the reference
+itself (``/root/reference/astrophot``, CPU torch) in the build container, runs
+it on seeded synthetic scenes and stores its outputs under ``tests/golden/``;
+``tests/test_oracle_golden.py`` checks this oracle against those fixtures
+(model images, forward-AD Jacobians, LM histories).
+
+Derivatives are analytic (forward-mode by hand); the reference obtains them
+with ``torch.func`` forward-mode AD over the same arithmetic
+(`models/_model_methods.py:325-340`), so the two agree to rounding.
+"""
+import math
+
+import numpy as np
+from numpy.polynomial.legendre import leggauss
+
+from astrophot_b200 import scene as sc
+
+LN10 = math.log(10.0)
+
+
+# ---------------------------------------------------------------------------
+# parameters: representation <-> value  (utils/conversions/optimization.py:6-54)
+# ---------------------------------------------------------------------------
+def rep_to_val(x, transform, lo, hi):
+    """Returns (values, dvalue/drep) for a representation-space vector."""
+    x = np.asarray(x, dtype=np.float64)
+    val = x.copy()
+    dv = np.ones_like(x)
+    for p in range(len(x)):
+        t = transform[p]
+        if t == sc.TR_LOWER:
+            d = x[p] - lo[p]
+            rt = math.sqrt(d * d + 4)
+            val[p] = 0.5 * (x[p] + lo[p] + rt)
+            dv[p] = 0.5 + 0.5 * d / rt
+        elif t == sc.TR_UPPER:
+            d = x[p] - hi[p]
+            rt = math.sqrt(d * d + 4)
+            val[p] = 0.5 * (x[p] + hi[p] - rt)
+            dv[p] = 0.5 - 0.5 * d / rt
+        elif t == sc.TR_BOTH:
+            val[p] = (math.atan(x[p]) + math.pi / 2) * (hi[p] - lo[p]) / math.pi + lo[p]
+            dv[p] = (hi[p] - lo[p]) / (math.pi * (x[p] * x[p] + 1))
+        elif t == sc.TR_CYCLIC:
+            val[p] = lo[p] + np.remainder(x[p] - lo[p], hi[p] - lo[p])
+    return val, dv
+
+
+def val_to_rep(v, transform, lo, hi):
+    v = np.asarray(v, dtype=np.float64)
+    out = v.copy()
+    for p in range(len(v)):
+        t = transform[p]
+        if t == sc.TR_LOWER:
+            out[p] = v[p] - 1.0 / (v[p] - lo[p])
+        elif t == sc.TR_UPPER:
+            out[p] = v[p] - 1.0 / (v[p] - hi[p])
+        elif t == sc.TR_BOTH:
+            out[p] = math.tan((v[p] - lo[p]) * math.pi / (hi[p] - lo[p]) - math.pi / 2)
+        elif t == sc.TR_CYCLIC:
+            out[p] = lo[p] + np.remainder(v[p] - lo[p], hi[p] - lo[p])
+    return out
+
+
+def source_elements(src, vals):
+    """Natural-unit element values of one source from the global value vector."""
+    return np.array([vals[s] if s >= 0 else c for s, c in zip(src.slot, src.cval)], dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------
+# profiles  (utils/parametric_profiles.py:7-100,157-177; conversions/functions.py:7-22)
+# ---------------------------------------------------------------------------
+def sersic_b(n):
+    return (2 * n - 1 / 3 + 4 / (405 * n) + 46 / (25515 * n**2) + 131 / (1148175 * n**3)
+            - 2194697 / (30690717750 * n**4))
+
+
+def sersic_db(n):
+    return (2 - 4 / (405 * n**2) - 92 / (25515 * n**3) - 393 / (1148175 * n**4)
+            + 4 * 2194697 / (30690717750 * n**5))
+
+
+def sersic_total_flux(Ie_lin, n, Re, q):
+    """conversions/functions.py:168-190 (used as integration reference)."""
+    bn = sersic_b(n)
+    return 2 * math.pi * Ie_lin * Re**2 * q * n * (math.exp(bn) * bn ** (-2 * n)) * math.exp(math.lgamma(2 * n))
+
+
+def _spline_eval(R, prof, v, extend=True):
+    """log10 brightness s(R) and its derivatives wrt R and every node value.
+    Hermite cubic, centred-difference slopes (utils/interpolate.py:31-62) with
+    the reference's index arithmetic, linear extension past the last node
+    (utils/parametric_profiles.py:157-177)."""
+    prof = np.asarray(prof, dtype=np.float64)
+    v = np.asarray(v, dtype=np.float64)
+    K = len(prof)
+    h = prof[1:] - prof[:-1]
+    delta = (v[1:] - v[:-1]) / h
+    m = np.concatenate([delta[[0]], (delta[1:] + delta[:-1]) / 2, delta[[-1]]])
+    # dm/dv  (K x K)
+    ddelta = np.zeros((K - 1, K))
+    for k in range(K - 1):
+        ddelta[k, k + 1] = 1 / h[k]
+        ddelta[k, k] = -1 / h[k]
+    dm = np.concatenate([ddelta[[0]], (ddelta[1:] + ddelta[:-1]) / 2, ddelta[[-1]]])
+    Rf = R.reshape(-1)
+    idx = np.searchsorted(prof[:-1], Rf, side="left") - 1   # -1 wraps like torch indexing
+    i0 = np.mod(idx, K)
+    i1 = idx + 1
+    dx = prof[i1] - prof[i0]
+    t = (Rf - prof[i0]) / dx
+    h00 = 1 - 3 * t**2 + 2 * t**3
+    h10 = t - 2 * t**2 + t**3
+    h01 = 3 * t**2 - 2 * t**3
+    h11 = -(t**2) + t**3
+    s = h00 * v[i0] + h10 * m[i0] * dx + h01 * v[i1] + h11 * m[i1] * dx
+    d00 = (-6 * t + 6 * t**2) / dx
+    d10 = (1 - 4 * t + 3 * t**2) / dx
+    d01 = (6 * t - 6 * t**2) / dx
+    d11 = (-2 * t + 3 * t**2) / dx
+    dsdR = d00 * v[i0] + d10 * m[i0] * dx + d01 * v[i1] + d11 * m[i1] * dx
+    dsdv = np.zeros((K, Rf.size))
+    np.add.at(dsdv, (i0, np.arange(Rf.size)), h00)
+    np.add.at(dsdv, (i1, np.arange(Rf.size)), h01)
+    dsdv += dm[i0].T * (h10 * dx) + dm[i1].T * (h11 * dx)
+    beyond = Rf > prof[-1]
+    if np.any(beyond):
+        slope = (v[-1] - v[-2]) / (prof[-1] - prof[-2])
+        s[beyond] = v[-2] + (Rf[beyond] - prof[-2]) * slope
+        dsdR[beyond] = slope
+        dsdv[:, beyond] = 0
+        dsdv[K - 2, beyond] = 1 - (Rf[beyond] - prof[-2]) / (prof[-1] - prof[-2])
+        dsdv[K - 1, beyond] = (Rf[beyond] - prof[-2]) / (prof[-1] - prof[-2])
+    return s.reshape(R.shape), dsdR.reshape(R.shape), dsdv.reshape((K,) + R.shape), beyond.reshape(R.shape)
+
+
+def eval_profile(src, el, X, Y, area, want_grad):
+    """Brightness at plane offsets (X, Y) from the centre, and (optionally)
+    its derivative with respect to every element (natural units).
+
+    Follows `_shared_methods.py:286-307` (rotate by -(PA - pi/2), divide y by
+    q), `_model_methods.py:38-40` (softened radius) and the radial profiles.
+    Returns (I, dI) with dI of shape (n_elem,) + X.shape or None.
+    """
+    kind = src.kind
+    ne = len(el)
+    if kind == sc.KIND_FLAT_SKY:
+        I = np.full(X.shape, area * 10.0 ** el[2])
+        if not want_grad:
+            return I, None
+        dI = np.zeros((ne,) + X.shape)
+        dI[2] = LN10 * I
+        return I, dI
+    if kind == sc.KIND_POINT:
+        raise ValueError("point sources are not profile-evaluated")
+    q, PA = el[2], el[3]
+    if src.flags & sc.FLAG_RADIAL:
+        xp, yp = X, Y
+        c = s = None
+    else:
+        theta = -(PA - math.pi / 2)
+        s, c = math.sin(theta), math.cos(theta)
+        xp = c * X - s * Y
+        yp = (s * X + c * Y) / q
+    R = np.sqrt(xp**2 + yp**2 + src.softening**2)
+    dI = None
+    if kind == sc.KIND_SERSIC:
+        n, Re, Ie = el[4], el[5], el[6]
+        bn = sersic_b(n)
+        u = np.power(R / Re, 1 / n)
+        I = (area * 10.0**Ie) * np.exp(-bn * (u - 1))
+        if want_grad:
+            dIdR = -I * bn * u / (n * R)
+            dI = np.zeros((ne,) + X.shape)
+            dI[4] = I * (-sersic_db(n) * (u - 1) + bn * u * np.log(R / Re) / n**2)
+            dI[5] = I * bn * u / (n * Re)
+            dI[6] = LN10 * I
+    elif kind == sc.KIND_EXPONENTIAL:
+        Re, Ie = el[4], el[5]
+        b1 = sersic_b(1.0)
+        I = (area * 10.0**Ie) * np.exp(-b1 * (R / Re - 1.0))
+        if want_grad:
+            dIdR = -I * b1 / Re
+            dI = np.zeros((ne,) + X.shape)
+            dI[4] = I * b1 * R / Re**2
+            dI[5] = LN10 * I
+    elif kind == sc.KIND_GAUSSIAN:
+        sig, fl = el[4], el[5]
+        I = ((area * 10.0**fl) / math.sqrt(2 * math.pi * sig**2)) * np.exp(-0.5 * (R / sig) ** 2)
+        if want_grad:
+            dIdR = -I * R / sig**2
+            dI = np.zeros((ne,) + X.shape)
+            dI[4] = I * (-1 / sig + R**2 / sig**3)
+            dI[5] = LN10 * I
+    elif kind == sc.KIND_MOFFAT:
+        n, Rd, I0 = el[4], el[5], el[6]
+        t = 1 + (R / Rd) ** 2
+        I = (area * 10.0**I0) / t**n
+        if want_grad:
+            dIdR = -I * n * 2 * R / (Rd**2 * t)
+            dI = np.zeros((ne,) + X.shape)
+            dI[4] = -I * np.log(t)
+            dI[5] = I * n * 2 * R**2 / (Rd**3 * t)
+            dI[6] = LN10 * I
+    elif kind == sc.KIND_SPLINE:
+        sv, dsdR, dsdv, _ = _spline_eval(R, src.prof, el[4:])
+        I = area * 10.0**sv
+        if want_grad:
+            dIdR = LN10 * I * dsdR
+            dI = np.zeros((ne,) + X.shape)
+            dI[4:] = LN10 * I * dsdv
+    else:
+        raise ValueError(f"unknown kind {kind}")
+    if want_grad:
+        if src.flags & sc.FLAG_RADIAL:
+            dRdX, dRdY = xp / R, yp / R
+        else:
+            dRdX = (xp * c + yp * s / q) / R
+            dRdY = (-xp * s + yp * c / q) / R
+            dI[2] = dIdR * (-(yp**2) / (q * R))
+            dI[3] = dIdR * (xp * yp * (q - 1 / q) / R)
+        dI[0] = -dIdR * dRdX
+        dI[1] = -dIdR * dRdY
+    return I, dI
+
+
+# ---------------------------------------------------------------------------
+# quadrature tables (utils/operations.py:94-120)
+# ---------------------------------------------------------------------------
+def quad_nodes(n, S):
+    """Offsets (dx, dy) in the plane and weights of the n x n Gauss-Legendre
+    rule over one pixel with pixelscale matrix S."""
+    a, w = leggauss(n)
+    k = np.arange(n * n)
+    ax, ay = a[k % n], a[k // n]
+    off = S @ (np.stack((ax, ay)) / 2.0)
+    W = (w[k // n] * w[k % n]) / 4.0
+    return off[0], off[1], W
+
+
+def sub_offsets(N, S):
+    d = np.linspace(-(N - 1) / (2 * N), (N - 1) / (2 * N), N)
+    k = np.arange(N * N)
+    off = S @ np.stack((d[k % N], d[k // N]))
+    return off[0], off[1]
+
+
+def _gl(src, el, X, Y, S, area, n, want_grad):
+    """Gauss-Legendre integral of each point's pixel; also the centre-node value."""
+    ox, oy, W = quad_nodes(n, S)
+    Xs = X[..., None] + ox
+    Ys = Y[..., None] + oy
+    I, dI = eval_profile(src, el, Xs, Ys, area, want_grad)
+    ref = I[..., (n * n) // 2]
+    res = (I * W).sum(axis=-1)
+    dres = (dI * W).sum(axis=-1) if want_grad else None
+    return res, ref, dres
+
+
+def grid_integrate(src, el, X, Y, S, area, depth, reference, want_grad):
+    """Adaptive sub-pixel integration (utils/operations.py:150-247).
+    Returns integrated flux (and derivatives) for flat arrays X, Y; also counts
+    the profile evaluations in ``grid_integrate.spe``."""
+    res, ref, dres = _gl(src, el, X, Y, S, area, src.quad_level, want_grad)
+    grid_integrate.spe += X.size * src.quad_level**2
+    grid_integrate.queued[depth] = grid_integrate.queued.get(depth, 0) + X.size
+    if depth >= src.max_depth:
+        return res, dres
+    select = np.abs(res - ref) > reference
+    if not np.any(select):
+        return res, dres
+    N = src.gridding
+    sx, sy = sub_offsets(N, S)
+    subX = (X[select][:, None] + sx).reshape(-1)
+    subY = (Y[select][:, None] + sy).reshape(-1)
+    sres, sdres = grid_integrate(src, el, subX, subY, S / N, area / N**2, depth + 1,
+                                 reference * N**2, want_grad)
+    out = res.copy()
+    out[select] = sres.reshape(-1, N * N).sum(axis=-1)
+    if want_grad:
+        dout = dres.copy()
+        dout[:, select] = sdres.reshape(sdres.shape[0], -1, N * N).sum(axis=-1)
+        return out, dout
+    return out, None
+
+
+grid_integrate.spe = 0
+grid_integrate.queued = {}
+
+
+# ---------------------------------------------------------------------------
+# PSF shift  (_model_methods.py:187-230, utils/interpolate.py:282-329)
+# ---------------------------------------------------------------------------
+def shift_psf_bilinear(psf, shift, keep_pad=True, want_grad=False):
+    """Bilinear resample of the 1-px zero-padded PSF at (i - sx, j - sy).
+    Returns stamp (and d/dsx, d/dsy)."""
+    im = np.pad(np.asarray(psf, dtype=np.float64), 1)
+    h, w = im.shape
+    x = np.arange(w, dtype=np.float64) - shift[0]
+    y = np.arange(h, dtype=np.float64) - shift[1]
+    x0 = np.floor(x).astype(np.int64)
+    y0 = np.floor(y).astype(np.int64)
+    x1 = np.clip(x0 + 1, 1, w - 1)
+    y1 = np.clip(y0 + 1, 1, h - 1)
+    x0 = np.clip(x0, 0, w - 2)
+    y0 = np.clip(y0, 0, h - 2)
+    wx0, wx1 = (x1 - x)[None, :], (x - x0)[None, :]
+    wy0, wy1 = (y1 - y)[:, None], (y - y0)[:, None]
+    fa = im[np.ix_(y0, x0)]
+    fb = im[np.ix_(y1, x0)]
+    fc = im[np.ix_(y0, x1)]
+    fd = im[np.ix_(y1, x1)]
+    out = fa * (wx0 * wy0) + fb * (wx0 * wy1) + fc * (wx1 * wy0) + fd * (wx1 * wy1)
+    grads = None
+    if want_grad:
+        # x = i - sx  =>  d(x1-x)/dsx = +1, d(x-x0)/dsx = -1
+        dsx = fa * wy0 + fb * wy1 - fc * wy0 - fd * wy1
+        dsy = fa * wx0 - fb * wx0 + fc * wx1 - fd * wx1
+        grads = (dsx, dsy)
+    if not keep_pad:
+        out = out[1:-1, 1:-1]
+        if want_grad:
+            grads = (grads[0][1:-1, 1:-1], grads[1][1:-1, 1:-1])
+    return out, grads
+
+
+def normalized_shifted_psf(psf, shift, method, keep_pad, want_grad):
+    """Shifted PSF divided by its sum (_model_methods.py:239-243), with the
+    quotient-rule derivative wrt the shift."""
+    if method == sc.SHIFT_NONE or shift is None:
+        p = np.asarray(psf, dtype=np.float64)
+        return p / p.sum(), None
+    if method != sc.SHIFT_BILINEAR:
+        raise NotImplementedError("only bilinear / none sub-pixel shifts are in the oracle")
+    st, g = shift_psf_bilinear(psf, shift, keep_pad, want_grad)
+    tot = st.sum()
+    out = st / tot
+    if not want_grad:
+        return out, None
+    dout = tuple(gi / tot - st * (gi.sum() / tot**2) for gi in g)
+    return out, dout
+
+
+def conv_same(img, ker):
+    """Linear 'same' convolution, direct sum (what the reference's FFT /
+    conv2d paths compute up to rounding, _model_methods.py:245-255)."""
+    kh, kw = ker.shape
+    ph, pw = (kh - 1) // 2, (kw - 1) // 2
+    H, W = img.shape
+    pad = np.zeros((H + kh - 1, W + kw - 1))
+    pad[ph : ph + H, pw : pw + W] = img
+    out = np.zeros_like(img, dtype=np.float64)
+    for a in range(kh):
+        for b in range(kw):
+            k = ker[a, b]
+            if k != 0.0:
+                out += k * pad[kh - 1 - a : kh - 1 - a + H, kw - 1 - b : kw - 1 - b + W]
+    return out
+
+
+def conv_same_fft(img, ker):
+    """Same result via scipy FFTs (used for the timed CPU baseline, like the
+    reference's default psf_convolve_mode='fft', utils/operations.py:9-36)."""
+    from scipy.signal import fftconvolve
+    return fftconvolve(img, ker, mode="same")
+
+
+# ---------------------------------------------------------------------------
+# one source
+# ---------------------------------------------------------------------------
+def _affine(img, i, j):
+    """Plane coordinates of pixel indices (wcs.py:561-584)."""
+    di = i - img.rij[0]
+    dj = j - img.rij[1]
+    return (img.S[0, 0] * di + img.S[0, 1] * dj + img.rxy[0],
+            img.S[1, 0] * di + img.S[1, 1] * dj + img.rxy[1])
+
+
+def _psf_border(psf):
+    h, w = psf.shape
+    return int(math.ceil((1 + w) / 2)), int(math.ceil((1 + h) / 2))
+
+
+class SourceResult:
+    """Output-window stamps of one source: value (oh, ow) and derivatives
+    (n_elem, oh, ow) in natural units (None when not requested)."""
+
+    def __init__(self, value, grad):
+        self.value = value
+        self.grad = grad
+
+
+def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None):
+    """One component model on its output window.
+
+    mode: "fwd" (working window = group window; group_model_object.py:211-227
+    passes ``window=use_window``) or "jac" (working window = own window,
+    _model_methods.py:294-299).  Pipeline per model_object.py:258-375.
+    """
+    src = scene.sources[si]
+    img = scene.images[src.image]
+    S = np.asarray(img.S, dtype=np.float64)
+    Sinv = np.linalg.inv(S)
+    area = abs(np.linalg.det(S))
+    ox, oy, ow, oh = src.out
+    wx, wy, ww, wh = src.fwd if mode == "fwd" else src.jac
+    ne = src.n_elem
+
+    if src.kind == sc.KIND_FLAT_SKY:
+        X = np.zeros((oh, ow))
+        I, dI = eval_profile(src, el, X, X, area, want_grad)
+        return SourceResult(I, dI)
+
+    if src.kind == sc.KIND_POINT:
+        return _sample_point(scene, src, img, el, want_grad)
+
+    has_psf = src.psf >= 0
+    bx = by = 0
+    if has_psf:
+        psf = np.asarray(scene.psfs[src.psf].data, dtype=np.float64)
+        bx, by = _psf_border(psf)
+    # evaluation region: output window + psf border; working region likewise
+    ex0, ey0, ew, eh = ox - bx, oy - by, ow + 2 * bx, oh + 2 * by
+    rx0, ry0, rw, rh = wx - bx, wy - by, ww + 2 * bx, wh + 2 * by
+    cx, cy = el[0], el[1]
+    shift = None
+    if has_psf and src.psf_shift != sc.SHIFT_NONE:
+        pc = Sinv @ (np.array([cx, cy]) - img.rxy) + img.rij       # pixel coords of the centre
+        rnd = np.round(pc)
+        shift = pc - rnd
+        # grid re-centred on the source (model_object.py:320-323): X = S.(pix - round(pc))
+        def coords(i, j):
+            di, dj = i - rnd[0], j - rnd[1]
+            return S[0, 0] * di + S[0, 1] * dj, S[1, 0] * di + S[1, 1] * dj
+        center_in_grid = False
+    else:
+        def coords(i, j):
+            px, py = _affine(img, i, j)
+            return px - cx, py - cy
+        center_in_grid = True
+
+    # ---- first pass over the evaluation region (+1 px ring for the curvature stencil)
+    mx0, my0 = max(ex0 - 1, rx0), max(ey0 - 1, ry0)
+    mx1, my1 = min(ex0 + ew + 1, rx0 + rw), min(ey0 + eh + 1, ry0 + rh)
+    jj, ii = np.meshgrid(np.arange(my0, my1, dtype=np.float64), np.arange(mx0, mx1, dtype=np.float64), indexing="ij")
+    X, Y = coords(ii, jj)
+    nspe = 0
+    if src.sampling_mode == sc.SAMPLE_MIDPOINT:
+        deep, ddeep = eval_profile(src, el, X, Y, area, want_grad)
+        nspe += X.size
+        # curvature: valid 3x3 Laplacian, replicate-padded *over the working region*
+        # (_model_methods.py:87-98): evaluate the stencil at the index clamped to the interior
+        def lap_at(i, j):   # absolute pixel indices (arrays)
+            ic = np.clip(i, rx0 + 1, rx0 + rw - 2) - mx0
+            jc = np.clip(j, ry0 + 1, ry0 + rh - 2) - my0
+            return (deep[jc - 1, ic] + deep[jc + 1, ic] + deep[jc, ic - 1] + deep[jc, ic + 1] - 4 * deep[jc, ic])
+        EJ, EI = np.meshgrid(np.arange(ey0, ey0 + eh), np.arange(ex0, ex0 + ew), indexing="ij")
+        if rw >= 3 and rh >= 3:
+            err = np.abs(lap_at(EI, EJ))
+        else:
+            err = np.zeros((eh, ew))
+        sl = (slice(ey0 - my0, ey0 - my0 + eh), slice(ex0 - mx0, ex0 - mx0 + ew))
+        deep_e = deep[sl].copy()
+        ddeep_e = ddeep[(slice(None),) + sl].copy() if want_grad else None
+        Xe, Ye = X[sl], Y[sl]
+        mean_src = deep
+    elif src.sampling_mode == sc.SAMPLE_QUAD:
+        sl = (slice(ey0 - my0, ey0 - my0 + eh), slice(ex0 - mx0, ex0 - mx0 + ew))
+        Xe, Ye = X[sl], Y[sl]
+        deep_e, refc, ddeep_e = _gl(src, el, Xe, Ye, S, area, src.quad_init, want_grad)
+        nspe += Xe.size * src.quad_init**2
+        err = np.abs(deep_e - refc)
+        mean_src = deep_e
+    elif src.sampling_mode == sc.SAMPLE_SIMPSONS:
+        sl = (slice(ey0 - my0, ey0 - my0 + eh), slice(ex0 - mx0, ex0 - mx0 + ew))
+        Xe, Ye = X[sl], Y[sl]
+        # (2h+1) x (2w+1) half-pixel lattice, 3x3 Simpson weights stride 2 (_model_methods.py:99-109)
+        wts = np.array([[1, 4, 1], [4, 16, 4], [1, 4, 1]], dtype=np.float64) / 36.0
+        deep_e = np.zeros((eh, ew))
+        ddeep_e = np.zeros((ne, eh, ew)) if want_grad else None
+        mid = None
+        for a in (-1, 0, 1):
+            for b in (-1, 0, 1):
+                dxp = S[0, 0] * (0.5 * b) + S[0, 1] * (0.5 * a)
+                dyp = S[1, 0] * (0.5 * b) + S[1, 1] * (0.5 * a)
+                I, dI = eval_profile(src, el, Xe + dxp, Ye + dyp, area, want_grad)
+                deep_e += wts[a + 1, b + 1] * I
+                if want_grad:
+                    ddeep_e += wts[a + 1, b + 1] * dI
+                if a == 0 and b == 0:
+                    mid = I
+        nspe += 9 * Xe.size
+        err = np.abs(deep_e - mid)
+        mean_src = deep_e
+    else:
+        raise NotImplementedError("sampling mode not in oracle")
+
+    # ---- threshold integration (_model_methods.py:155-184)
+    if src.integrate_mode == sc.INTEGRATE_THRESHOLD:
+        if src.ref_mode == sc.REF_SERSIC_FLUX:
+            ref = sersic_total_flux(10.0 ** el[6], el[4], el[5], el[2]) / (rw * rh)
+        else:
+            if (mx0, my0, mx1, my1) == (rx0, ry0, rx0 + rw, ry0 + rh) or src.sampling_mode != sc.SAMPLE_MIDPOINT and (ex0, ey0, ew, eh) == (rx0, ry0, rw, rh):
+                ref = mean_src.sum() / (rw * rh)
+            else:
+                ref = _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh)
+        thr = src.tolerance * ref
+        select = err > thr
+        if np.any(select):
+            grid_integrate.spe = 0
+            grid_integrate.queued = {}
+            ires, idres = grid_integrate(src, el, Xe[select], Ye[select], S, area, 1, thr, want_grad)
+            nspe += grid_integrate.spe
+            deep_e[select] = ires
+            if want_grad:
+                ddeep_e[:, select] = idres
+            if stats is not None:
+                for d, c in grid_integrate.queued.items():
+                    stats.setdefault("queued", {}).setdefault(d, 0)
+                    stats["queued"][d] += c
+    if stats is not None:
+        stats["spe"] = stats.get("spe", 0) + nspe
+
+    if src.flags & sc.FLAG_NORMALIZE:
+        tot = deep_e.sum()
+        if want_grad:
+            ddeep_e = ddeep_e / tot - deep_e[None] * (ddeep_e.sum(axis=(1, 2), keepdims=True) / tot**2)
+        deep_e = deep_e / tot
+
+    if not has_psf:
+        return SourceResult(deep_e, ddeep_e)
+
+    # ---- PSF convolution on the padded region, then crop the border (model_object.py:342-349)
+    cfn = conv_same if conv == "direct" else conv_same_fft
+    P, dP = normalized_shifted_psf(psf, shift, src.psf_shift, True, want_grad and shift is not None)
+    crop = (slice(by, by + oh), slice(bx, bx + ow))
+    val = cfn(deep_e, P)[crop]
+    grad = None
+    if want_grad:
+        grad = np.zeros((ne, oh, ow))
+        first = 0 if center_in_grid else 2
+        for e in range(first, ne):
+            if src.slot[e] >= 0:
+                grad[e] = cfn(ddeep_e[e], P)[crop]
+        if not center_in_grid:
+            # centre enters only through the PSF shift: d shift / d centre = S^-1
+            gsx = cfn(deep_e, dP[0])[crop]
+            gsy = cfn(deep_e, dP[1])[crop]
+            grad[0] = Sinv[0, 0] * gsx + Sinv[1, 0] * gsy
+            grad[1] = Sinv[0, 1] * gsx + Sinv[1, 1] * gsy
+    return SourceResult(val, grad)
+
+
+def _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh):
+    """Mean of the first-pass image over the whole working region (the default
+    ``_integrate_reference``, _model_methods.py:151-152), in row blocks."""
+    tot = 0.0
+    for j0 in range(ry0, ry0 + rh, 256):
+        j1 = min(j0 + 256, ry0 + rh)
+        jj, ii = np.meshgrid(np.arange(j0, j1, dtype=np.float64), np.arange(rx0, rx0 + rw, dtype=np.float64), indexing="ij")
+        X, Y = coords(ii, jj)
+        if src.sampling_mode == sc.SAMPLE_MIDPOINT:
+            I, _ = eval_profile(src, el, X, Y, area, False)
+        elif src.sampling_mode == sc.SAMPLE_QUAD:
+            I, _, _ = _gl(src, el, X, Y, S, area, src.quad_init, False)
+        else:
+            raise NotImplementedError
+        tot += I.sum()
+    return tot / (rw * rh)
+
+
+def _sample_point(scene, src, img, el, want_grad):
+    """Point source with a PSF image (models/point_source.py:145-175): the PSF,
+    sub-pixel shifted and normalised, times 10^flux, dropped at the rounded
+    pixel of the centre and clipped to the output window."""
+    S = np.asarray(img.S, dtype=np.float64)
+    Sinv = np.linalg.inv(S)
+    psf = np.asarray(scene.psfs[src.psf].data, dtype=np.float64)
+    ph, pw = psf.shape
+    ox, oy, ow, oh = src.out
+    pc = Sinv @ (np.array([el[0], el[1]]) - img.rxy) + img.rij
+    rnd = np.round(pc)
+    shift = pc - rnd
+    P, dP = normalized_shifted_psf(psf, shift, src.psf_shift, False, want_grad)
+    F = 10.0 ** el[2]
+    val = np.zeros((oh, ow))
+    ne = src.n_elem
+    grad = np.zeros((ne, oh, ow)) if want_grad else None
+    # psf pixel (a, b) lands on image pixel (rnd_x - (pw-1)/2 + b, rnd_y - (ph-1)/2 + a)
+    x_lo = int(rnd[0]) - (pw - 1) // 2
+    y_lo = int(rnd[1]) - (ph - 1) // 2
+    ix0, ix1 = max(ox, x_lo), min(ox + ow, x_lo + pw)
+    iy0, iy1 = max(oy, y_lo), min(oy + oh, y_lo + ph)
+    if ix1 > ix0 and iy1 > iy0:
+        ps = (slice(iy0 - y_lo, iy1 - y_lo), slice(ix0 - x_lo, ix1 - x_lo))
+        os_ = (slice(iy0 - oy, iy1 - oy), slice(ix0 - ox, ix1 - ox))
+        val[os_] = F * P[ps]
+        if want_grad:
+            if dP is not None:
+                gsx, gsy = F * dP[0][ps], F * dP[1][ps]
+                grad[0][os_] = Sinv[0, 0] * gsx + Sinv[1, 0] * gsy
+                grad[1][os_] = Sinv[0, 1] * gsx + Sinv[1, 1] * gsy
+            grad[2][os_] = LN10 * F * P[ps]
+    return SourceResult(val, grad)
+
+
+# ---------------------------------------------------------------------------
+# whole scene
+# ---------------------------------------------------------------------------
+def _values(scene, x, as_rep):
+    if as_rep:
+        return rep_to_val(x, scene.transform, scene.lo, scene.hi)
+    x = np.asarray(x, dtype=np.float64)
+    return x.copy(), np.ones_like(x)
+
+
+def sample(scene, x, as_rep=True, mode="fwd", conv="direct", stats=None):
+    """Model image per scene image: sum of all sources (group_model_object.py:183-231)."""
+    vals, _ = _values(scene, x, as_rep)
+    out = [np.zeros((im.H, im.W)) for im in scene.images]
+    for si, src in enumerate(scene.sources):
+        el = source_elements(src, vals)
+        r = sample_source(scene, si, el, mode, False, conv, stats)
+        ox, oy, ow, oh = src.out
+        out[src.image][oy : oy + oh, ox : ox + ow] += r.value
+    return out
+
+
+def jacobian(scene, x, as_rep=True, conv="direct", stats=None):
+    """Dense (H, W, P) Jacobian per image (group_model_object.py:233-283).
+    Only for small scenes."""
+    vals, dv = _values(scene, x, as_rep)
+    P = scene.n_par
+    out = [np.zeros((im.H, im.W, P)) for im in scene.images]
+    for si, src in enumerate(scene.sources):
+        if all(s < 0 for s in src.slot):
+            continue
+        el = source_elements(src, vals)
+        r = sample_source(scene, si, el, "jac", True, conv, stats)
+        ox, oy, ow, oh = src.out
+        for e, s in enumerate(src.slot):
+            if s >= 0:
+                out[src.image][oy : oy + oh, ox : ox + ow, s] += r.grad[e] * dv[s]
+    return out
+
+
+def flat_targets(scene):
+    """Y, W, keep-mask as flat vectors over all images (lm.py:191-222)."""
+    Y = np.concatenate([np.asarray(im.data, dtype=np.float64).reshape(-1) for im in scene.images])
+    W = np.concatenate([(np.ones(im.H * im.W) if im.weight is None else np.asarray(im.weight, dtype=np.float64).reshape(-1))
+                        for im in scene.images])
+    keep = np.concatenate([(np.ones(im.H * im.W, dtype=bool) if im.mask is None else ~np.asarray(im.mask).astype(bool).reshape(-1))
+                           for im in scene.images])
+    return Y, W, keep
+
+
+def normal_eq(scene, x, conv="direct", same_geometry=False, stats=None):
+    """J^T W J, J^T W (Y - Y0), sum W (Y - Y0)^2 over unmasked pixels
+    (lm.py:256-260,373-399)."""
+    Y, W, keep = flat_targets(scene)
+    Y0 = np.concatenate([m.reshape(-1) for m in sample(scene, x, True, "fwd", conv, stats)])
+    J = np.concatenate([j.reshape(-1, scene.n_par) for j in jacobian(scene, x, True, conv, stats)])
+    Jk, Wk = J[keep], W[keep]
+    H = Jk.T @ (Wk[:, None] * Jk)
+    g = Jk.T @ (Wk * (Y[keep] - Y0[keep]))
+    chi2 = np.sum(Wk * (Y[keep] - Y0[keep]) ** 2)
+    return H, g, chi2, (J, Y0)
+
+
+def chi2(scene, x, conv="direct"):
+    Y, W, keep = flat_targets(scene)
+    Y1 = np.concatenate([m.reshape(-1) for m in sample(scene, x, True, "fwd", conv)])
+    return np.sum((W * (Y - Y1) ** 2)[keep])
+
+
+def lm_solve(H, g, L):
+    """Damped step (lm.py:359-371)."""
+    P = len(g)
+    I = np.eye(P)
+    D = np.ones_like(H) - I
+    return np.linalg.solve(H * (I + D / (1 + L)) + L * I * (1 + np.diag(H)), g)
+
+
+class OptimizeStop(Exception):
+    pass
+
+
+def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_iter=10,
+           curvature_limit=1.0, Lup=11.0, Ldn=9.0, L0=1.0, acceleration=0.0, conv="direct", verbose=0):
+    """Levenberg-Marquardt loop, control flow of fit/lm.py:248-357,428-493."""
+    x = np.asarray(x0, dtype=np.float64).copy()
+    Y, W, keep = flat_targets(scene)
+    if ndf is None:
+        ndf = max(1.0, float(keep.sum()) - len(x))
+    L = L0
+
+    def up(L):
+        return min(1e9, L * Lup)
+
+    def dn(L):
+        return max(1e-9, L / Ldn)
+
+    def fwd(xx):
+        return np.concatenate([m.reshape(-1) for m in sample(scene, xx, True, "fwd", conv)])
+
+    def c2(Yp):
+        return float(np.sum((W * (Y - Yp) ** 2)[keep]) / ndf)
+
+    loss = [c2(fwd(x))]
+    L_hist = [L]
+    x_hist = [x.copy()]
+    trials_hist = []
+    message = ""
+    for it in range(max_iter):
+        # ---- step (lm.py:248-357)
+        Y0 = fwd(x)
+        J = np.concatenate([j.reshape(-1, scene.n_par) for j in jacobian(scene, x, True, conv)])
+        Jk, Wk = J[keep], W[keep]
+        r = Wk * (Y0[keep] - Y[keep])
+        H = Jk.T @ (Wk[:, None] * Jk)
+        g = -Jk.T @ r
+        init = loss[-1]
+        nostep = True
+        best = (np.zeros_like(x), init, L)
+        scary = (None, init, L)
+        direction = "none"
+        d = 0.1
+        ntr = 0
+        for k in range(max_step_iter):
+            ntr += 1
+            if k > max_step_iter / 2 and L < 1e-3:
+                L = 1.0
+            h = lm_solve(H, g, L)
+            Y1 = fwd(x + d * h)
+            rh = Wk * (Y1[keep] - Y[keep])
+            rpp = Jk.T @ ((2 / d) * ((rh - r) / d - Wk * (Jk @ h)))
+            a = -lm_solve(H, rpp, L) / 2 if L > 1e-4 else np.zeros_like(h)
+            ha = h + a * acceleration
+            chi = c2(fwd(x + ha))
+            if verbose > 1:
+                print(f"  sub step L: {L}, Chi^2/DoF: {chi}")
+            if not np.isfinite(chi):
+                L = up(L)
+                if direction == "better":
+                    break
+                direction = "worse"
+                continue
+            if chi <= scary[1]:
+                scary = (ha, chi, L)
+            rho = np.linalg.norm(a) / np.linalg.norm(h)
+            if rho > curvature_limit:
+                L = up(L)
+                if direction == "better":
+                    break
+                direction = "worse"
+                continue
+            if chi < best[1]:
+                best = (ha, chi, L)
+                nostep = False
+                L = dn(L)
+                if L <= 1e-8 or direction == "worse":
+                    break
+                direction = "better"
+            elif chi > best[1] and direction in ("none", "worse"):
+                L = up(L)
+                if L == 1e9:
+                    break
+                direction = "worse"
+            else:
+                break
+            if (best[1] - init) / init < -0.1:
+                break
+        trials_hist.append(ntr)
+        if nostep:
+            if scary[0] is not None:
+                res = scary
+            else:
+                message += "fail. Could not find step to improve Chi^2"
+                break
+        else:
+            res = best
+        L = res[2]
+        x = x + res[0]
+        L_hist.append(L)
+        loss.append(res[1])
+        x_hist.append(x.copy())
+        L = dn(L)
+        if verbose:
+            print(f"Chi^2/DoF: {loss[-1]}, L: {L}")
+        if len(loss) >= 3 and (loss[-3] - loss[-1]) / loss[-1] < relative_tolerance and L < 0.1:
+            message += "success"
+            break
+        if len(loss) > 10 and (loss[-10] - loss[-1]) / loss[-1] < relative_tolerance:
+            message += "success by immobility. Convergence not guaranteed"
+            break
+    else:
+        message += "fail. Maximum iterations"
+    return {"x": x, "loss_history": loss, "L_history": L_hist, "lambda_history": x_hist,
+            "message": message, "trials": trials_hist}

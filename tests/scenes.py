@@ -1,0 +1,185 @@
+"""Seeded synthetic scenes shared by the golden generator (which builds them with
+the *reference* package) and the tests (which build them with astrophot_b200).
+
+``build(ap, name, data=None)`` only uses API common to both packages, so the
+same code constructs the reference model and ours.  ``data`` maps image index
+-> dict(data=, variance=) arrays (from the golden fixture); when absent the
+targets are zero images (enough for sample()/jacobian() parity).
+"""
+import numpy as np
+
+
+def _psf_moffat(n, Rd, width):
+    x = np.arange(width) - (width - 1) / 2
+    X, Y = np.meshgrid(x, x, indexing="xy")
+    # 5x5 sub-sampled moffat, normalised
+    sub = (np.arange(5) - 2) / 5.0
+    z = np.zeros((width, width))
+    for a in sub:
+        for b in sub:
+            z += 1.0 / (1.0 + ((X + b) ** 2 + (Y + a) ** 2) / Rd**2) ** n
+    return z / z.sum()
+
+
+def _psf_gauss(sigma, width):
+    x = np.arange(width) - (width - 1) / 2
+    X, Y = np.meshgrid(x, x, indexing="xy")
+    z = np.exp(-0.5 * (X**2 + Y**2) / sigma**2)
+    return z / z.sum()
+
+
+def _target(ap, shape, data, idx=0, pixelscale=1.0, psf=None, origin=None, mask=None, **kw):
+    d = None if data is None else data.get(idx)
+    arr = np.zeros(shape) if d is None else d["data"]
+    var = None if d is None else d.get("variance")
+    kwargs = dict(data=arr, pixelscale=pixelscale, zeropoint=22.5)
+    if var is not None:
+        kwargs["variance"] = var
+    if psf is not None:
+        kwargs["psf"] = psf
+    if origin is not None:
+        kwargs["origin"] = origin
+    if mask is not None:
+        kwargs["mask"] = mask
+    kwargs.update(kw)
+    return ap.image.Target_Image(**kwargs)
+
+
+def build(ap, name, data=None):
+    """Returns (model, meta) for scene ``name``."""
+    M = ap.models.AstroPhot_Model
+    if name == "c1_sersic":
+        tar = _target(ap, (100, 100), data)
+        m = M(name="c1", model_type="sersic galaxy model", target=tar,
+              parameters={"center": [50.3, 49.6], "q": 0.6, "PA": 1.0, "n": 2.0, "Re": 10.0, "Ie": 1.0})
+        return m, {}
+    if name == "sersic_sheared":
+        S = np.array([[0.8, 0.1], [-0.05, 0.9]])
+        tar = _target(ap, (72, 80), data, pixelscale=S, origin=[3.0, -2.0])
+        m = M(name="shr", model_type="sersic galaxy model", target=tar,
+              parameters={"center": [33.1, 24.7], "q": 0.45, "PA": 2.1, "n": 3.1, "Re": 7.0, "Ie": 0.7})
+        return m, {}
+    if name == "sersic_nointegrate":
+        tar = _target(ap, (64, 64), data)
+        m = M(name="noint", model_type="sersic galaxy model", target=tar, integrate_mode="none",
+              parameters={"center": [31.2, 33.9], "q": 0.7, "PA": 0.4, "n": 1.5, "Re": 8.0, "Ie": 0.5})
+        return m, {}
+    if name == "sersic_quad5":
+        tar = _target(ap, (50, 50), data, pixelscale=0.8)
+        m = M(name="q5", model_type="sersic galaxy model", target=tar, sampling_mode="quad:5",
+              parameters={"center": [20.1, 19.3], "q": 0.5, "PA": 0.9, "n": 1.0, "Re": 8.0, "Ie": 1.0})
+        return m, {}
+    if name in ("exponential", "gaussian", "moffat", "spline"):
+        tar = _target(ap, (64, 60), data, pixelscale=0.9)
+        common = {"center": [26.3, 30.2], "q": 0.65, "PA": 1.9}
+        if name == "exponential":
+            pars = dict(common, Re=6.0, Ie=0.8)
+        elif name == "gaussian":
+            pars = dict(common, sigma=5.0, flux=3.0)
+        elif name == "moffat":
+            pars = dict(common, n=2.2, Rd=4.0, I0=1.2)
+        else:
+            prof = [0.0, 1.5, 3.0, 5.0, 8.0, 12.0, 18.0, 26.0]
+            val = [1.6, 1.45, 1.25, 0.95, 0.5, 0.0, -0.7, -1.6]
+            pars = dict(common)
+            pars["I(R)"] = {"value": val, "prof": prof}
+        m = M(name=f"k_{name}", model_type=f"{name} galaxy model", target=tar, parameters=pars)
+        return m, {}
+    if name in ("psf_sersic", "psf_sersic_noshift"):
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 11), pixelscale=1.0)
+        tar = _target(ap, (64, 64), data, psf=psf)
+        m = M(name=name, model_type="sersic galaxy model", target=tar, psf_mode="full",
+              psf_subpixel_shift="bilinear" if name == "psf_sersic" else "none",
+              parameters={"center": [30.8, 33.3], "q": 0.55, "PA": 2.4, "n": 2.5, "Re": 6.0, "Ie": 1.0})
+        return m, {}
+    if name == "point":
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 15), pixelscale=1.0)
+        tar = _target(ap, (40, 44), data, psf=psf)
+        m = M(name="pt", model_type="point model", target=tar,
+              parameters={"center": [20.7, 18.4], "flux": 1.0})
+        return m, {}
+    if name == "point_edge":
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 15), pixelscale=1.0)
+        tar = _target(ap, (40, 44), data, psf=psf)
+        m = M(name="pte", model_type="point model", target=tar, window=[[0, 12], [25, 40]],
+              parameters={"center": [3.49, 37.51], "flux": 1.3})
+        return m, {}
+    if name == "group":
+        rng = np.random.default_rng(7)
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 1.8, 9), pixelscale=1.0)
+        tar = _target(ap, (96, 96), data, psf=psf)
+        models = []
+        cen = [(28.3, 30.6), (60.2, 40.1), (45.7, 70.4)]
+        for k, (cx, cy) in enumerate(cen):
+            models.append(M(name=f"gal{k}", model_type="sersic galaxy model", target=tar, psf_mode="full",
+                            window=[[int(cx) - 16, int(cx) + 16], [int(cy) - 16, int(cy) + 16]],
+                            parameters={"center": [cx, cy], "q": 0.5 + 0.1 * k, "PA": 0.7 * (k + 1),
+                                        "n": 1.5 + 0.8 * k, "Re": 4.0 + k, "Ie": 0.6 + 0.1 * k}))
+        for k in range(4):
+            cx, cy = rng.uniform(15, 80, size=2)
+            models.append(M(name=f"star{k}", model_type="point model", target=tar,
+                            window=[[int(cx) - 7, int(cx) + 8], [int(cy) - 7, int(cy) + 8]],
+                            parameters={"center": [cx, cy], "flux": 1.0 + 0.2 * k}))
+        sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": -1.0})
+        sky.initialize()
+        models.append(sky)
+        g = M(name="grp", model_type="group model", models=models, target=tar, psf_mode="full")
+        return g, {}
+    if name == "group_nosky":
+        # windows do not tile the image -> fit_mask matters
+        psf = ap.image.PSF_Image(data=_psf_gauss(1.3, 7), pixelscale=1.0)
+        tar = _target(ap, (70, 80), data, psf=psf)
+        m1 = M(name="ga", model_type="sersic galaxy model", target=tar, psf_mode="full",
+               window=[[5, 45], [8, 44]],
+               parameters={"center": [25.4, 26.3], "q": 0.6, "PA": 1.1, "n": 2.0, "Re": 5.0, "Ie": 0.9})
+        m2 = M(name="gb", model_type="exponential galaxy model", target=tar,
+               window=[[35, 75], [30, 66]],
+               parameters={"center": [55.2, 47.9], "q": 0.8, "PA": 2.5, "Re": 6.0, "Ie": 0.5})
+        g = M(name="grp2", model_type="group model", models=[m1, m2], target=tar, psf_mode="full")
+        return g, {}
+    if name == "joint":
+        tars, models = [], []
+        for b in range(3):
+            psf = ap.image.PSF_Image(data=_psf_gauss(1.2 + 0.1 * b, 9), pixelscale=1.0)
+            tars.append(_target(ap, (48, 48), data, idx=b, psf=psf))
+        tlist = ap.image.Target_Image_List(tars)
+        for b in range(3):
+            pars = {"center": [23.6, 24.3], "q": 0.6, "PA": 1.0, "n": 2.0, "Re": 6.0, "Ie": 0.3 + 0.1 * b}
+            m = M(name=f"band{b}", model_type="sersic galaxy model", target=tars[b], psf_mode="full", parameters=pars)
+            if b > 0:
+                for p in ("center", "q", "PA", "n", "Re"):
+                    m[p].value = models[0][p]
+            models.append(m)
+        g = M(name="joint", model_type="group model", models=models, target=tlist, psf_mode="full")
+        return g, {}
+    if name == "moffat_psf_model":
+        ptar = ap.image.PSF_Image(data=np.zeros((25, 25)), pixelscale=1.0)
+        m = M(name="mpsf", model_type="moffat psf model", target=ptar, parameters={"n": 2.5, "Rd": 3.0})
+        return m, {}
+    if name == "gaussian_psf_model":
+        ptar = ap.image.PSF_Image(data=np.zeros((21, 21)), pixelscale=1.0)
+        m = M(name="gpsf", model_type="gaussian psf model", target=ptar, parameters={"sigma": 1.5})
+        return m, {}
+    raise KeyError(name)
+
+
+SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
+                 "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
+                 "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model"]
+# scenes with an LM golden (noise seed, start perturbation)
+LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8}
+
+
+def make_data(truth_images, seed):
+    """Noisy data + variance from noiseless truth (tests/utils.py:73 recipe)."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for i, t in enumerate(truth_images):
+        var = 0.1**2 + t / 100.0
+        out[i] = {"data": t + rng.normal(size=t.shape) * np.sqrt(var), "variance": var}
+    return out
+
+
+def perturb(x_rep, seed, scale=0.05):
+    rng = np.random.default_rng(1000 + seed)
+    return np.asarray(x_rep, dtype=np.float64) + scale * rng.normal(size=len(x_rep))
