@@ -1,0 +1,268 @@
+"""ctypes binding of ``libastrophot_b200.so`` (C ABI in include/astrophot_b200.h).
+
+This is the only door between the Python host code and the sm_100a kernels.
+torch is used for device memory and the current stream, nothing else.  If the
+library is missing or no CUDA device is present the product path raises
+``NativeLibraryError`` — there is no CPU fallback by design.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import scene as sc
+from .errors import NativeLibraryError
+
+__all__ = ["lib", "load_library", "Plan", "lm_solve", "LIB_PATH"]
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libastrophot_b200.so")
+
+MAX_ELEM, MAX_PROF, MAX_DEPTH = sc.MAX_ELEM, sc.MAX_PROF, 4
+
+
+class apb_param_t(C.Structure):
+    _fields_ = [("transform", C.c_int32), ("_pad", C.c_int32), ("lo", C.c_double), ("hi", C.c_double)]
+
+
+class apb_image_t(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("S", C.c_double * 4), ("rij", C.c_double * 2),
+                ("rxy", C.c_double * 2), ("data", C.c_void_p), ("weight", C.c_void_p), ("mask", C.c_void_p)]
+
+
+class apb_psf_t(C.Structure):
+    _fields_ = [("h", C.c_int32), ("w", C.c_int32), ("data", C.c_void_p)]
+
+
+class apb_source_t(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("image", C.c_int32),
+                ("out", C.c_int32 * 4), ("fwd", C.c_int32 * 4), ("jac", C.c_int32 * 4),
+                ("n_elem", C.c_int32), ("slot", C.c_int32 * MAX_ELEM), ("cval", C.c_double * MAX_ELEM),
+                ("n_prof", C.c_int32), ("prof", C.c_double * MAX_PROF),
+                ("sampling_mode", C.c_int32), ("quad_init", C.c_int32), ("integrate_mode", C.c_int32),
+                ("quad_level", C.c_int32), ("gridding", C.c_int32), ("max_depth", C.c_int32),
+                ("ref_mode", C.c_int32), ("psf", C.c_int32), ("psf_shift", C.c_int32), ("_pad", C.c_int32),
+                ("tolerance", C.c_double), ("softening", C.c_double)]
+
+
+class apb_opts_t(C.Structure):
+    _fields_ = [("queue_capacity", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32)]
+
+
+class apb_stats_t(C.Structure):
+    _fields_ = [("first_pass_evals", C.c_int64), ("queued", C.c_int64 * (MAX_DEPTH + 1)),
+                ("launches", C.c_int64), ("overflow", C.c_int64)]
+
+
+EXPORTS = ["apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+           "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the native library and declare its prototypes.  Loading does not
+    need a GPU (the CPU test-suite checks the exports this way)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise NativeLibraryError(
+            f"{path} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). astrophot_b200 has no CPU fallback.")
+    try:
+        L = C.CDLL(path)
+    except OSError as e:
+        raise NativeLibraryError(f"could not load {path}: {e}") from e
+    vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p
+    L.apb_plan_create.argtypes = [C.POINTER(apb_source_t), C.c_int, C.POINTER(apb_image_t), C.c_int,
+                                  C.POINTER(apb_psf_t), C.c_int, C.POINTER(apb_param_t), C.c_int,
+                                  C.POINTER(apb_opts_t), C.POINTER(C.c_void_p)]
+    L.apb_plan_destroy.argtypes = [vp]
+    L.apb_sample.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_void_p), vp]
+    L.apb_jacobian.argtypes = [vp, dp, C.c_int, C.POINTER(C.c_void_p), vp]
+    L.apb_normal_eq.argtypes = [vp, dp, C.c_int, dp, dp, dp, vp]
+    L.apb_geodesic.argtypes = [vp, dp, dp, C.c_double, dp, vp]
+    L.apb_chi2.argtypes = [vp, dp, dp, vp]
+    L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
+    L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
+    L.apb_last_error.restype = C.c_char_p
+    L.apb_version.restype = C.c_int
+    for name in EXPORTS:
+        if name not in ("apb_last_error",):
+            getattr(L, name).restype = C.c_int if name != "apb_last_error" else C.c_char_p
+    L.apb_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().apb_last_error()
+        raise NativeLibraryError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise NativeLibraryError(
+            "astrophot_b200 evaluates models only on a CUDA device (B200, sm_100a); no CUDA device is visible "
+            "and there is no CPU fallback.")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f64(x):
+    t = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x)
+    return t.to(device="cuda", dtype=torch.float64).contiguous()
+
+
+class Plan:
+    """A lowered model tree resident on the device (``apb_plan_t``)."""
+
+    def __init__(self, scene, queue_capacity=0):
+        _require_cuda()
+        L = lib()
+        self.scene = scene
+        self.n_par = scene.n_par
+        self._keep = []          # tensors whose storage the plan points into
+        n_img, n_src, n_psf = len(scene.images), len(scene.sources), len(scene.psfs)
+        imgs = (apb_image_t * max(n_img, 1))()
+        self.shapes = []
+        for i, im in enumerate(scene.images):
+            imgs[i].H, imgs[i].W = im.H, im.W
+            imgs[i].S[:] = [float(v) for v in np.asarray(im.S).reshape(4)]
+            imgs[i].rij[:] = [float(v) for v in im.rij]
+            imgs[i].rxy[:] = [float(v) for v in im.rxy]
+            for name in ("data", "weight"):
+                arr = getattr(im, name)
+                if arr is not None:
+                    t = _dev_f64(arr)
+                    self._keep.append(t)
+                    setattr(imgs[i], name, t.data_ptr())
+            if im.mask is not None:
+                m = torch.as_tensor(im.mask).to(device="cuda", dtype=torch.uint8).contiguous()
+                self._keep.append(m)
+                imgs[i].mask = m.data_ptr()
+            self.shapes.append((im.H, im.W))
+        psfs = (apb_psf_t * max(n_psf, 1))()
+        for i, ps in enumerate(scene.psfs):
+            t = _dev_f64(ps.data)
+            self._keep.append(t)
+            psfs[i].h, psfs[i].w, psfs[i].data = t.shape[0], t.shape[1], t.data_ptr()
+        pars = (apb_param_t * max(self.n_par, 1))()
+        for k in range(self.n_par):
+            pars[k].transform = int(scene.transform[k])
+            pars[k].lo = 0.0 if np.isnan(scene.lo[k]) else float(scene.lo[k])
+            pars[k].hi = 0.0 if np.isnan(scene.hi[k]) else float(scene.hi[k])
+        srcs = (apb_source_t * max(n_src, 1))()
+        for i, s in enumerate(scene.sources):
+            c = srcs[i]
+            c.kind, c.flags, c.image = s.kind, s.flags, s.image
+            c.out[:], c.fwd[:], c.jac[:] = list(s.out), list(s.fwd), list(s.jac)
+            c.n_elem = s.n_elem
+            for e in range(s.n_elem):
+                c.slot[e] = int(s.slot[e])
+                c.cval[e] = float(s.cval[e])
+            c.n_prof = len(s.prof)
+            for k, v in enumerate(s.prof):
+                c.prof[k] = float(v)
+            c.sampling_mode, c.quad_init, c.integrate_mode = s.sampling_mode, s.quad_init, s.integrate_mode
+            c.quad_level, c.gridding, c.max_depth = s.quad_level, s.gridding, s.max_depth
+            c.ref_mode, c.psf, c.psf_shift = s.ref_mode, s.psf, s.psf_shift
+            c.tolerance, c.softening = s.tolerance, s.softening
+        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags=0)
+        handle = C.c_void_p()
+        _check(L.apb_plan_create(srcs, n_src, imgs, n_img, psfs, n_psf, pars, self.n_par, C.byref(opts),
+                                 C.byref(handle)), "apb_plan_create")
+        self._h = handle
+        self._L = L
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._L.apb_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- helpers -------------------------------------------------------------
+    def _x(self, x):
+        t = _dev_f64(x).reshape(-1)
+        if t.numel() != self.n_par:
+            raise NativeLibraryError(f"parameter vector has {t.numel()} elements, plan expects {self.n_par}")
+        return t
+
+    def _ptrs(self, tensors):
+        arr = (C.c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            arr[i] = t.data_ptr()
+        return arr
+
+    # -- entry points ------------------------------------------------------------
+    def sample(self, x, as_rep=False):
+        x = self._x(x)
+        outs = [torch.empty(h, w, dtype=torch.float64, device="cuda") for h, w in self.shapes]
+        _check(self._L.apb_sample(self._h, x.data_ptr(), int(as_rep), self._ptrs(outs), _stream()), "apb_sample")
+        return outs
+
+    def jacobian(self, x, as_rep=False):
+        x = self._x(x)
+        outs = [torch.empty(h, w, self.n_par, dtype=torch.float64, device="cuda") for h, w in self.shapes]
+        _check(self._L.apb_jacobian(self._h, x.data_ptr(), int(as_rep), self._ptrs(outs), _stream()), "apb_jacobian")
+        return outs
+
+    def normal_eq(self, x, as_rep=True, out=None):
+        """Returns (JtWJ (P,P), JtWr (P,), chi2 (1,)) device tensors."""
+        x = self._x(x)
+        P = self.n_par
+        if out is None:
+            out = (torch.empty(P, P, dtype=torch.float64, device="cuda"),
+                   torch.empty(P, dtype=torch.float64, device="cuda"),
+                   torch.empty(2, dtype=torch.float64, device="cuda"))
+        H, g, c2 = out
+        _check(self._L.apb_normal_eq(self._h, x.data_ptr(), int(as_rep), H.data_ptr(), g.data_ptr(), c2.data_ptr(),
+                                     _stream()), "apb_normal_eq")
+        return H, g, c2
+
+    def geodesic(self, xdh, h, d, out=None):
+        xdh, h = self._x(xdh), self._x(h)
+        if out is None:
+            out = torch.empty(self.n_par, dtype=torch.float64, device="cuda")
+        _check(self._L.apb_geodesic(self._h, xdh.data_ptr(), h.data_ptr(), float(d), out.data_ptr(), _stream()),
+               "apb_geodesic")
+        return out
+
+    def chi2(self, x, out=None):
+        """(sum W (Y - model)^2, finite flag) as a 2-element device tensor."""
+        x = self._x(x)
+        if out is None:
+            out = torch.empty(2, dtype=torch.float64, device="cuda")
+        _check(self._L.apb_chi2(self._h, x.data_ptr(), out.data_ptr(), _stream()), "apb_chi2")
+        return out
+
+    def stats(self):
+        st = apb_stats_t()
+        _check(self._L.apb_plan_stats(self._h, C.byref(st)), "apb_plan_stats")
+        return {"first_pass_evals": st.first_pass_evals, "queued": list(st.queued)[1:], "launches": st.launches,
+                "overflow": st.overflow}
+
+
+def lm_solve(H, g, L, out=None, info=None):
+    """Damped LM step on the device (fit/lm.py:359-371)."""
+    _require_cuda()
+    P = g.numel()
+    if out is None:
+        out = torch.empty(P, dtype=torch.float64, device="cuda")
+    if info is None:
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _check(lib().apb_lm_solve(H.data_ptr(), g.data_ptr(), float(L), int(P), out.data_ptr(), info.data_ptr(),
+                              _stream()), "apb_lm_solve")
+    return out

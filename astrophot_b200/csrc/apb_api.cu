@@ -1,0 +1,693 @@
+// libastrophot_b200: host side of the C ABI (include/astrophot_b200.h).
+// Builds the device tables once per plan, then every call is a fixed sequence of
+// kernel launches on the caller's stream with no host synchronisation.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "apb_internal.cuh"
+#include "apb_sample.cuh"
+#include "apb_image.cuh"
+
+
+static thread_local std::string g_err;
+#define APB_FAIL(msg)                      \
+  do {                                     \
+    g_err = std::string(msg);              \
+    return -1;                             \
+  } while (0)
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +     \
+              std::to_string(__LINE__) + ")";                                                  \
+      return -2;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+template <typename T>
+static int upload(const std::vector<T>& v, T** out) {
+  *out = nullptr;
+  const size_t n = std::max<size_t>(v.size(), 1);
+  CU(cudaMalloc((void**)out, n * sizeof(T)));
+  if (!v.empty()) CU(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+struct ModeTables {
+  int4* tiles = nullptr;       // first-pass tiles {src, tx, ty, 0}
+  int n_tiles = 0;
+  int4* chunks = nullptr;      // mean-reference chunks {src, first, n, slot}
+  int n_chunks = 0;
+  int* mean_list = nullptr;    // sources with REF_MEAN + threshold
+  int n_mean = 0;
+  int4* conv_jobs[2] = {nullptr, nullptr};   // [grad]
+  int4* conv_tiles[2] = {nullptr, nullptr};
+  int n_conv_tiles[2] = {0, 0};
+  size_t conv_smem = 0;
+};
+
+struct apb_plan {
+  int n_src = 0, n_img = 0, n_par = 0, n_psf = 0;
+  std::vector<DevSrc> h_src;
+  std::vector<apb_image_t> h_img;
+  DevSrc* d_src = nullptr;
+  DevDyn* d_dyn = nullptr;
+  apb_image_t* d_img = nullptr;
+  apb_param_t* d_par = nullptr;
+  apb_psf_t* d_psf = nullptr;
+  ModeTables mt[2];
+  int* psf_list = nullptr; int n_psf_list = 0;      // sources needing a shifted PSF stamp
+  int* point_list = nullptr; int n_point = 0;
+  int* norm_list = nullptr; int n_norm = 0;
+  bool any_threshold = false, all_same_geo = true;
+  int max_depth = 1;
+  int NVp_grad = 1;
+  // arenas
+  double *d_stamp = nullptr, *d_out = nullptr, *d_psfst = nullptr, *d_meanpart = nullptr, *d_skyJ = nullptr;
+  // queues
+  Queues q{};
+  std::vector<void*> owned;
+  // image tiles + bins
+  int4* img_tiles = nullptr; int n_img_tiles = 0;
+  int *bin_ptr = nullptr, *bin_src = nullptr;
+  double* d_chipart = nullptr;
+  // per-image buffers
+  std::vector<double*> h_model, h_resid, h_resid2;
+  double **d_model = nullptr, **d_resid = nullptr, **d_resid2 = nullptr, **d_userptr = nullptr;
+  // normal equations
+  BlockItem* d_items = nullptr; int n_items = 0;
+  BlockDesc* d_blocks = nullptr; int n_blocks = 0;
+  BlockItem* d_vitems = nullptr; int n_vitems = 0;   // diagonal items only (J^T v)
+  BlockDesc* d_vblocks = nullptr; int n_vblocks = 0;
+  int *d_act_slot = nullptr, *d_act_off = nullptr;
+  double* d_part = nullptr;
+  double* d_xtmp = nullptr;
+  apb_stats_t stats{};
+  long long launches = 0;
+  cudaStream_t last_stream = nullptr;
+  int first_evals[2] = {0, 0};
+};
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+extern "C" const char* apb_last_error(void) { return g_err.c_str(); }
+extern "C" int apb_version(void) { return 100; }
+
+static void gauss_legendre(int n, double* x, double* w) {
+  // Newton iteration on P_n (same nodes as scipy.special.roots_legendre to rounding)
+  for (int i = 0; i < n; ++i) {
+    double z = cos(APB_PI * (i + 0.75) / (n + 0.5));
+    double pp = 0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1);
+      }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double z1 = z;
+      z = z1 - p1 / pp;
+      if (fabs(z - z1) < 1e-16) break;
+    }
+    x[n - 1 - i] = z;
+    w[n - 1 - i] = 2.0 / ((1.0 - z * z) * pp * pp);
+  }
+  if (n % 2 == 1) x[n / 2] = 0.0;
+}
+
+static void set_geo(Geo& g, const int* out, const int* work, int bx, int by, bool ring) {
+  g.ex0 = out[0] - bx; g.ey0 = out[1] - by; g.ew = out[2] + 2 * bx; g.eh = out[3] + 2 * by;
+  g.rx0 = work[0] - bx; g.ry0 = work[1] - by; g.rw = work[2] + 2 * bx; g.rh = work[3] + 2 * by;
+  const int r = ring ? 1 : 0;
+  const int x0 = std::max(g.ex0 - r, g.rx0), y0 = std::max(g.ey0 - r, g.ry0);
+  const int x1 = std::min(g.ex0 + g.ew + r, g.rx0 + g.rw), y1 = std::min(g.ey0 + g.eh + r, g.ry0 + g.rh);
+  g.mx0 = x0; g.my0 = y0; g.mw = x1 - x0; g.mh = y1 - y0;
+  g.tile0 = g.ntile = g.chunk0 = g.nchunk = 0;
+}
+
+extern "C" int apb_plan_destroy(apb_plan_t* p) {
+  if (!p) return 0;
+  for (void* q : p->owned) cudaFree(q);
+  delete p;
+  return 0;
+}
+
+template <typename T>
+static int own_upload(apb_plan* p, const std::vector<T>& v, T** out) {
+  int rc = upload(v, out);
+  if (rc == 0) p->owned.push_back(*out);
+  return rc;
+}
+static int own_alloc(apb_plan* p, void** out, size_t bytes) {
+  CU(cudaMalloc(out, std::max<size_t>(bytes, 8)));
+  p->owned.push_back(*out);
+  return 0;
+}
+
+extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_image_t* img, int n_img,
+                               const apb_psf_t* psf, int n_psf, const apb_param_t* par, int n_par,
+                               const apb_opts_t* opts, apb_plan_t** out) {
+  if (!out) APB_FAIL("apb_plan_create: out is NULL");
+  *out = nullptr;
+  if (n_src < 0 || n_img <= 0 || n_par < 0) APB_FAIL("apb_plan_create: bad counts");
+  int dev_count = 0;
+  CU(cudaGetDeviceCount(&dev_count));
+  apb_plan* p = new apb_plan();
+  p->n_src = n_src; p->n_img = n_img; p->n_par = n_par; p->n_psf = n_psf;
+  p->h_img.assign(img, img + n_img);
+#define PFAIL(msg) do { apb_plan_destroy(p); APB_FAIL(msg); } while (0)
+#define PCU(call) do { int rc_ = [&]() -> int { CU(call); return 0; }(); if (rc_) { apb_plan_destroy(p); return rc_; } } while (0)
+#define PRC(call) do { int rc_ = (call); if (rc_) { apb_plan_destroy(p); return rc_; } } while (0)
+
+  // quadrature tables
+  {
+    QuadTab qt;
+    memset(&qt, 0, sizeof(qt));
+    for (int n = 1; n <= APB_MAX_QUAD; ++n) {
+      double x[APB_MAX_QUAD], w[APB_MAX_QUAD];
+      gauss_legendre(n, x, w);
+      for (int i = 0; i < n; ++i) { qt.a[n][i] = x[i] / 2.0; qt.w[n][i] = w[i] / 2.0; }
+    }
+    PCU(cudaMemcpyToSymbol(c_quad, &qt, sizeof(qt)));
+  }
+
+  // ---- sources
+  std::vector<DevSrc>& S = p->h_src;
+  S.resize(n_src);
+  long long stamp_total = 0, out_total = 0, psfst_total = 0;
+  std::vector<int> psf_list, point_list, norm_list, act_slot, act_off(n_src + 1, 0);
+  int max_nact = 0;
+  for (int i = 0; i < n_src; ++i) {
+    const apb_source_t& a = src[i];
+    DevSrc& s = S[i];
+    memset(&s, 0, sizeof(s));
+    if (a.kind < 0 || a.kind > APB_FLAT_SKY) PFAIL("unknown source kind");
+    if (a.image < 0 || a.image >= n_img) PFAIL("source image index out of range");
+    if (a.n_elem < 3 || a.n_elem > APB_MAX_ELEM) PFAIL("bad n_elem");
+    if (a.sampling_mode == APB_SAMPLE_TRAPEZOID) PFAIL("sampling_mode trapezoid is not implemented");
+    if (a.max_depth < 1 || a.max_depth > APB_MAX_DEPTH) PFAIL("integrate_max_depth out of range (1..4)");
+    if (a.quad_level < 1 || a.quad_level > APB_MAX_QUAD || a.quad_init < 1 || a.quad_init > APB_MAX_QUAD)
+      PFAIL("quadrature level out of range (1..9)");
+    if (a.gridding < 1 || a.gridding > 16) PFAIL("integrate_gridding out of range (1..16)");
+    const apb_image_t& im = img[a.image];
+    s.kind = a.kind; s.flags = a.flags; s.image = a.image; s.n_elem = a.n_elem;
+    s.ox = a.out[0]; s.oy = a.out[1]; s.ow = a.out[2]; s.oh = a.out[3];
+    if (s.ow <= 0 || s.oh <= 0 || s.ox < 0 || s.oy < 0 || s.ox + s.ow > im.W || s.oy + s.oh > im.H)
+      PFAIL("source output window outside its image");
+    s.n_act = 0;
+    for (int e = 0; e < a.n_elem; ++e) {
+      s.slot[e] = a.slot[e]; s.cval[e] = a.cval[e];
+      if (a.slot[e] >= n_par) PFAIL("parameter slot out of range");
+      if (a.slot[e] >= 0) { s.plane[e] = ++s.n_act; act_slot.push_back(a.slot[e]); } else s.plane[e] = 0;
+    }
+    act_off[i + 1] = (int)act_slot.size();
+    max_nact = std::max(max_nact, s.n_act);
+    s.n_prof = a.n_prof;
+    if (a.kind == APB_SPLINE && (a.n_prof < 2 || a.n_prof > APB_MAX_PROF || a.n_elem != 4 + a.n_prof))
+      PFAIL("spline source needs 2..20 nodes and n_elem = 4 + n_prof");
+    for (int k = 0; k < a.n_prof && k < APB_MAX_PROF; ++k) s.prof[k] = a.prof[k];
+    s.sampling_mode = a.sampling_mode; s.quad_init = a.quad_init; s.integrate_mode = a.integrate_mode;
+    s.quad_level = a.quad_level; s.gridding = a.gridding; s.max_depth = a.max_depth; s.ref_mode = a.ref_mode;
+    s.tol = a.tolerance; s.soft2 = a.softening * a.softening;
+    s.psf = a.psf; s.psf_shift = a.psf_shift;
+    for (int k = 0; k < 4; ++k) s.S[k] = im.S[k];
+    const double det = im.S[0] * im.S[3] - im.S[1] * im.S[2];
+    if (det == 0.0) PFAIL("singular pixelscale");
+    s.Sinv[0] = im.S[3] / det; s.Sinv[1] = -im.S[1] / det; s.Sinv[2] = -im.S[2] / det; s.Sinv[3] = im.S[0] / det;
+    s.area = fabs(det);
+    s.rij[0] = im.rij[0]; s.rij[1] = im.rij[1]; s.rxy[0] = im.rxy[0]; s.rxy[1] = im.rxy[1];
+    s.bx = s.by = 0; s.out_off = -1; s.psf_off = -1;
+    if (a.kind == APB_FLAT_SKY || a.kind == APB_POINT) s.integrate_mode = APB_INTEGRATE_NONE;
+    if (a.kind == APB_POINT && a.psf < 0) PFAIL("point source without a PSF");
+    if (a.kind == APB_FLAT_SKY) s.psf = -1;
+    if (s.psf >= 0) {
+      if (s.psf >= n_psf) PFAIL("psf index out of range");
+      if (a.psf_shift != APB_SHIFT_NONE && a.psf_shift != APB_SHIFT_BILINEAR) PFAIL("unsupported psf_subpixel_shift");
+      s.pw = psf[s.psf].w; s.ph = psf[s.psf].h;
+      if (s.pw % 2 != 1 || s.ph % 2 != 1) PFAIL("psf must have odd shape");
+      const bool pad = (a.psf_shift != APB_SHIFT_NONE) && a.kind != APB_POINT;
+      s.spw = s.pw + (pad ? 2 : 0); s.sph = s.ph + (pad ? 2 : 0);
+      if (a.kind != APB_POINT) { s.bx = (s.pw + 2) / 2; s.by = (s.ph + 2) / 2; }  // ceil((1+P)/2), psf_image.py:71-93
+      s.psf_off = psfst_total; psfst_total += 3LL * s.spw * s.sph;
+      s.out_off = out_total; out_total += (long long)(1 + s.n_act) * s.ow * s.oh;
+      psf_list.push_back(i);
+      if (a.kind == APB_POINT) point_list.push_back(i);
+    }
+    const bool ring = (a.kind != APB_FLAT_SKY && a.kind != APB_POINT && s.sampling_mode == APB_SAMPLE_MIDPOINT &&
+                       s.integrate_mode == APB_INTEGRATE_THRESHOLD);
+    set_geo(s.geo[0], a.out, a.fwd, s.bx, s.by, ring);
+    set_geo(s.geo[1], a.out, a.jac, s.bx, s.by, ring);
+    for (int m = 0; m < 2; ++m) {
+      const Geo& g = s.geo[m];
+      if (g.ex0 < g.rx0 || g.ey0 < g.ry0 || g.ex0 + g.ew > g.rx0 + g.rw || g.ey0 + g.eh > g.ry0 + g.rh)
+        PFAIL("working window must contain the output window");
+    }
+    s.same_geo = memcmp(&s.geo[0], &s.geo[1], sizeof(Geo)) == 0;
+    if (!s.same_geo && a.kind != APB_FLAT_SKY && a.kind != APB_POINT) p->all_same_geo = false;
+    if (a.kind != APB_FLAT_SKY && a.kind != APB_POINT) {
+      s.plane_stride = std::max((long long)s.geo[0].mw * s.geo[0].mh, (long long)s.geo[1].mw * s.geo[1].mh);
+      s.stamp_off = stamp_total;
+      stamp_total += s.plane_stride * (s.n_act + 2);   // value + derivatives + first-pass error
+      if (s.integrate_mode == APB_INTEGRATE_THRESHOLD) { p->any_threshold = true; p->max_depth = std::max(p->max_depth, s.max_depth); }
+      if (s.flags & APB_F_NORMALIZE) norm_list.push_back(i);
+    }
+  }
+  p->NVp_grad = 1 + max_nact;
+
+  // ---- per-mode tile / chunk / conv lists
+  for (int m = 0; m < 2; ++m) {
+    ModeTables& T = p->mt[m];
+    std::vector<int4> tiles, chunks;
+    std::vector<int> mean_list;
+    for (int i = 0; i < n_src; ++i) {
+      DevSrc& s = S[i];
+      if (s.kind == APB_FLAT_SKY || s.kind == APB_POINT) continue;
+      Geo& g = s.geo[m];
+      g.tile0 = (int)tiles.size();
+      for (int ty = 0; ty < g.mh; ty += 8)
+        for (int tx = 0; tx < g.mw; tx += 32) tiles.push_back(make_int4(i, tx, ty, 0));
+      g.ntile = (int)tiles.size() - g.tile0;
+      p->first_evals[m] += g.mw * g.mh;
+      if (s.integrate_mode == APB_INTEGRATE_THRESHOLD && s.ref_mode == APB_REF_MEAN) {
+        mean_list.push_back(i);
+        g.chunk0 = (int)chunks.size();
+        const long long npx = (long long)g.rw * g.rh;
+        const int CH = 8192;
+        for (long long f = 0; f < npx; f += CH)
+          chunks.push_back(make_int4(i, (int)f, (int)std::min<long long>(CH, npx - f), (int)chunks.size()));
+        g.nchunk = (int)chunks.size() - g.chunk0;
+      }
+    }
+    T.n_tiles = (int)tiles.size(); T.n_chunks = (int)chunks.size(); T.n_mean = (int)mean_list.size();
+    PRC(own_upload(p, tiles, &T.tiles));
+    PRC(own_upload(p, chunks, &T.chunks));
+    PRC(own_upload(p, mean_list, &T.mean_list));
+    for (int gr = 0; gr < 2; ++gr) {
+      std::vector<int4> jobs, ctiles;
+      size_t smem = 0;
+      for (int i = 0; i < n_src; ++i) {
+        const DevSrc& s = S[i];
+        if (s.psf < 0 || s.kind == APB_POINT) continue;
+        const int cw = (s.spw - 1) / 2, chh = (s.sph - 1) / 2;
+        if (cw > s.bx || chh > s.by) PFAIL("internal: psf stamp wider than the border");
+        auto add_job = [&](int in_plane, int kern, int out_plane) {
+          const int j = (int)jobs.size();
+          jobs.push_back(make_int4(i, in_plane, kern, out_plane));
+          for (int ty = 0; ty < s.oh; ty += CONV_TH)
+            for (int tx = 0; tx < s.ow; tx += CONV_TW) ctiles.push_back(make_int4(j, tx, ty, 0));
+        };
+        add_job(0, 0, 0);
+        if (gr) {
+          const bool shifted = s.psf_shift != APB_SHIFT_NONE;
+          for (int e = 0; e < s.n_elem; ++e) {
+            if (s.plane[e] <= 0) continue;
+            if (e < 2 && shifted) add_job(0, 1 + e, s.plane[e]);   // centre: through the PSF shift
+            else add_job(s.plane[e], 0, s.plane[e]);
+          }
+        }
+        const size_t need = ((size_t)s.spw * s.sph + (size_t)(CONV_TH + s.sph - 1) * ((CONV_TW + s.spw - 1) | 1)) * sizeof(double);
+        smem = std::max(smem, need);
+      }
+      if (smem > 227 * 1024) PFAIL("PSF too large for the direct convolution tile (max ~91x91)");
+      T.conv_smem = std::max(T.conv_smem, smem);
+      T.n_conv_tiles[gr] = (int)ctiles.size();
+      PRC(own_upload(p, jobs, &T.conv_jobs[gr]));
+      PRC(own_upload(p, ctiles, &T.conv_tiles[gr]));
+    }
+  }
+  if (p->mt[0].conv_smem > 48 * 1024 || p->mt[1].conv_smem > 48 * 1024)
+    PCU(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)std::max(p->mt[0].conv_smem, p->mt[1].conv_smem)));
+
+  // ---- image tiles and source bins (32x32 pixels)
+  {
+    std::vector<int4> itiles;
+    std::vector<int> bptr(1, 0), bsrc;
+    for (int ii = 0; ii < n_img; ++ii) {
+      const int ntx = ceil_div(img[ii].W, 32), nty = ceil_div(img[ii].H, 32);
+      std::vector<std::vector<int>> bins((size_t)ntx * nty);
+      for (int i = 0; i < n_src; ++i) {
+        const DevSrc& s = S[i];
+        if (s.image != ii) continue;
+        for (int ty = s.oy / 32; ty <= (s.oy + s.oh - 1) / 32; ++ty)
+          for (int tx = s.ox / 32; tx <= (s.ox + s.ow - 1) / 32; ++tx) bins[(size_t)ty * ntx + tx].push_back(i);
+      }
+      for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx; ++tx) {
+          itiles.push_back(make_int4(ii, tx * 32, ty * 32, (int)bptr.size() - 1));
+          const auto& b = bins[(size_t)ty * ntx + tx];
+          bsrc.insert(bsrc.end(), b.begin(), b.end());
+          bptr.push_back((int)bsrc.size());
+        }
+    }
+    p->n_img_tiles = (int)itiles.size();
+    PRC(own_upload(p, itiles, &p->img_tiles));
+    PRC(own_upload(p, bptr, &p->bin_ptr));
+    PRC(own_upload(p, bsrc, &p->bin_src));
+    PRC(own_alloc(p, (void**)&p->d_chipart, sizeof(double) * 2 * itiles.size()));
+  }
+
+  // ---- normal-equation work lists: diagonal blocks + overlapping pairs, split in <=8-plane
+  //      sub-blocks and <=4096-pixel rectangles
+  {
+    std::vector<BlockItem> items, vitems;
+    std::vector<BlockDesc> blocks, vblocks;
+    auto add_block = [&](int a, int b, int pa0, int na, int pb0, int nb, int diag, int x0, int y0, int w, int h,
+                         std::vector<BlockItem>& it, std::vector<BlockDesc>& bl) {
+      BlockDesc bd{a, b, pa0, na, pb0, nb, diag, (int)it.size(), 0};
+      const int rows = std::max(1, 4096 / std::max(w, 1));
+      for (int r = 0; r < h; r += rows) {
+        BlockItem bi{a, b, pa0, na, pb0, nb, x0, y0 + r, w, std::min(rows, h - r), diag, (int)bl.size()};
+        it.push_back(bi);
+      }
+      bd.nitem = (int)it.size() - bd.item0;
+      bl.push_back(bd);
+    };
+    // spatial hash of sources per image to find overlapping pairs
+    for (int ii = 0; ii < n_img; ++ii) {
+      std::vector<int> ids;
+      for (int i = 0; i < n_src; ++i)
+        if (S[i].image == ii && S[i].n_act > 0) ids.push_back(i);
+      for (int a : ids) {
+        const DevSrc& A = S[a];
+        for (int pa0 = 0; pa0 < A.n_act; pa0 += NB_MAX) {
+          const int na = std::min(NB_MAX, A.n_act - pa0);
+          add_block(a, a, pa0, na, pa0, na, 1, A.ox, A.oy, A.ow, A.oh, vitems, vblocks);
+          for (int pb0 = pa0; pb0 < A.n_act; pb0 += NB_MAX) {
+            const int nb = std::min(NB_MAX, A.n_act - pb0);
+            add_block(a, a, pa0, na, pb0, nb, pa0 == pb0, A.ox, A.oy, A.ow, A.oh, items, blocks);
+          }
+        }
+      }
+      // pairs via a coarse grid
+      const int CELL = 64;
+      const int ncx = ceil_div(img[ii].W, CELL), ncy = ceil_div(img[ii].H, CELL);
+      std::vector<std::vector<int>> cells((size_t)ncx * ncy);
+      std::vector<int> big;   // sources covering many cells (sky): pair with everything directly
+      for (int a : ids) {
+        const DevSrc& A = S[a];
+        const int c0x = A.ox / CELL, c1x = (A.ox + A.ow - 1) / CELL, c0y = A.oy / CELL, c1y = (A.oy + A.oh - 1) / CELL;
+        if ((long long)(c1x - c0x + 1) * (c1y - c0y + 1) > 64) { big.push_back(a); continue; }
+        for (int cy = c0y; cy <= c1y; ++cy)
+          for (int cx = c0x; cx <= c1x; ++cx) cells[(size_t)cy * ncx + cx].push_back(a);
+      }
+      std::vector<std::pair<int, int>> pairs;
+      for (auto& c : cells)
+        for (size_t u = 0; u < c.size(); ++u)
+          for (size_t v = u + 1; v < c.size(); ++v) pairs.emplace_back(std::min(c[u], c[v]), std::max(c[u], c[v]));
+      for (int a : big)
+        for (int b : ids)
+          if (b != a && !(std::find(big.begin(), big.end(), b) != big.end() && b < a))
+            pairs.emplace_back(std::min(a, b), std::max(a, b));
+      std::sort(pairs.begin(), pairs.end());
+      pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+      for (auto& pr : pairs) {
+        const DevSrc& A = S[pr.first];
+        const DevSrc& B = S[pr.second];
+        const int x0 = std::max(A.ox, B.ox), y0 = std::max(A.oy, B.oy);
+        const int x1 = std::min(A.ox + A.ow, B.ox + B.ow), y1 = std::min(A.oy + A.oh, B.oy + B.oh);
+        if (x1 <= x0 || y1 <= y0) continue;
+        for (int pa0 = 0; pa0 < A.n_act; pa0 += NB_MAX)
+          for (int pb0 = 0; pb0 < B.n_act; pb0 += NB_MAX)
+            add_block(pr.first, pr.second, pa0, std::min(NB_MAX, A.n_act - pa0), pb0, std::min(NB_MAX, B.n_act - pb0), 0,
+                      x0, y0, x1 - x0, y1 - y0, items, blocks);
+      }
+    }
+    p->n_items = (int)items.size(); p->n_blocks = (int)blocks.size();
+    p->n_vitems = (int)vitems.size(); p->n_vblocks = (int)vblocks.size();
+    PRC(own_upload(p, items, &p->d_items));
+    PRC(own_upload(p, blocks, &p->d_blocks));
+    PRC(own_upload(p, vitems, &p->d_vitems));
+    PRC(own_upload(p, vblocks, &p->d_vblocks));
+    PRC(own_upload(p, act_slot, &p->d_act_slot));
+    PRC(own_upload(p, act_off, &p->d_act_off));
+    PRC(own_alloc(p, (void**)&p->d_part, sizeof(double) * BLK_VALS * (size_t)std::max(items.size(), vitems.size())));
+  }
+
+  // ---- tables and arenas
+  PRC(own_upload(p, S, &p->d_src));
+  PRC(own_alloc(p, (void**)&p->d_dyn, sizeof(DevDyn) * (size_t)std::max(n_src, 1)));
+  PRC(own_upload(p, p->h_img, &p->d_img));
+  { std::vector<apb_param_t> pv(par, par + n_par); PRC(own_upload(p, pv, &p->d_par)); }
+  { std::vector<apb_psf_t> pv(psf, psf + n_psf); PRC(own_upload(p, pv, &p->d_psf)); }
+  PRC(own_upload(p, psf_list, &p->psf_list)); p->n_psf_list = (int)psf_list.size();
+  PRC(own_upload(p, point_list, &p->point_list)); p->n_point = (int)point_list.size();
+  PRC(own_upload(p, norm_list, &p->norm_list)); p->n_norm = (int)norm_list.size();
+  PRC(own_alloc(p, (void**)&p->d_stamp, sizeof(double) * (size_t)stamp_total));
+  PRC(own_alloc(p, (void**)&p->d_out, sizeof(double) * (size_t)out_total));
+  PRC(own_alloc(p, (void**)&p->d_psfst, sizeof(double) * (size_t)psfst_total));
+  PRC(own_alloc(p, (void**)&p->d_meanpart, sizeof(double) * (size_t)std::max(p->mt[0].n_chunks, p->mt[1].n_chunks)));
+  PRC(own_alloc(p, (void**)&p->d_skyJ, sizeof(double) * (size_t)std::max(n_src, 1)));
+  PRC(own_alloc(p, (void**)&p->d_xtmp, sizeof(double) * (size_t)std::max(n_par, 1)));
+  PCU(cudaMemset(p->d_stamp, 0, sizeof(double) * (size_t)std::max<long long>(stamp_total, 1)));
+
+  // ---- queues
+  {
+    long long cap = opts ? opts->queue_capacity : 0;
+    if (cap <= 0) {
+      long long px = std::max(p->first_evals[0], p->first_evals[1]);
+      cap = std::min<long long>(std::max<long long>(px, 1 << 16), 1LL << 24);
+    }
+    p->q.cap = (int)cap;
+    p->q.NVp = 1;
+    PRC(own_alloc(p, (void**)&p->q.count, sizeof(int) * (APB_MAX_DEPTH + 2)));
+    PRC(own_alloc(p, (void**)&p->q.overflow, sizeof(int)));
+    PCU(cudaMemset(p->q.overflow, 0, sizeof(int)));
+    PCU(cudaMemset(p->q.count, 0, sizeof(int) * (APB_MAX_DEPTH + 2)));
+    if (p->any_threshold) {
+      for (int d = 1; d <= p->max_depth; ++d) {
+        Level& L = p->q.lv[d];
+        PRC(own_alloc(p, (void**)&L.src, sizeof(int) * cap));
+        PRC(own_alloc(p, (void**)&L.x, sizeof(double) * cap));
+        PRC(own_alloc(p, (void**)&L.y, sizeof(double) * cap));
+        PRC(own_alloc(p, (void**)&L.parent, sizeof(int) * cap));
+        PRC(own_alloc(p, (void**)&L.child, sizeof(int) * cap));
+        PRC(own_alloc(p, (void**)&L.res, sizeof(double) * cap * p->NVp_grad));
+      }
+    }
+  }
+
+  // ---- per-image internal buffers
+  p->h_model.resize(n_img); p->h_resid.resize(n_img); p->h_resid2.resize(n_img);
+  for (int ii = 0; ii < n_img; ++ii) {
+    const size_t n = (size_t)img[ii].H * img[ii].W;
+    PRC(own_alloc(p, (void**)&p->h_model[ii], sizeof(double) * n));
+    PRC(own_alloc(p, (void**)&p->h_resid[ii], sizeof(double) * n));
+    PRC(own_alloc(p, (void**)&p->h_resid2[ii], sizeof(double) * n));
+  }
+  PRC(own_upload(p, p->h_model, &p->d_model));
+  PRC(own_upload(p, p->h_resid, &p->d_resid));
+  PRC(own_upload(p, p->h_resid2, &p->d_resid2));
+  PRC(own_alloc(p, (void**)&p->d_userptr, sizeof(double*) * n_img));
+  *out = p;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// one sampling pass: prep -> psf stamps -> first pass -> reference -> select -> refine -> scatter ->
+// normalise -> point sources -> convolution.  Leaves the out-planes of every source ready.
+// ----------------------------------------------------------------------------
+#define LAUNCH_CHECK() do { p->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { g_err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " line " + std::to_string(__LINE__); return -3; } } while (0)
+
+static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int grad, cudaStream_t st) {
+  const int n_src = p->n_src;
+  if (n_src == 0) return 0;
+  ModeTables& T = p->mt[mode];
+  k_prep<<<ceil_div(n_src, 128), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad);
+  LAUNCH_CHECK();
+  if (p->n_psf_list) {
+    k_psf_stamp<<<p->n_psf_list, 256, 0, st>>>(p->d_src, p->d_dyn, p->psf_list, p->d_psf, p->d_psfst, grad);
+    LAUNCH_CHECK();
+  }
+  if (T.n_tiles) {
+    if (grad) k_first<true><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
+    else k_first<false><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
+    LAUNCH_CHECK();
+    if (p->any_threshold) {
+      if (T.n_mean) {
+        k_mean_partial<<<T.n_chunks, 256, 0, st>>>(p->d_src, p->d_dyn, T.chunks, mode, p->d_stamp, p->d_meanpart);
+        LAUNCH_CHECK();
+        k_mean_final<<<ceil_div(T.n_mean, 128), 128, 0, st>>>(p->d_src, p->d_dyn, T.mean_list, T.n_mean, mode, p->d_meanpart);
+        LAUNCH_CHECK();
+      }
+      Queues q = p->q;
+      q.NVp = grad ? p->NVp_grad : 1;
+      k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
+      LAUNCH_CHECK();
+      const int grid = 148 * 8;
+      for (int d = 1; d <= p->max_depth; ++d) {
+        if (grad) k_refine<true><<<grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, d, q);
+        else k_refine<false><<<grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, d, q);
+        LAUNCH_CHECK();
+      }
+      for (int d = p->max_depth - 1; d >= 1; --d) {
+        k_reduce_level<<<grid, 128, 0, st>>>(p->d_src, d, q);
+        LAUNCH_CHECK();
+      }
+      k_scatter<<<grid, 128, 0, st>>>(p->d_src, q, p->d_stamp, grad);
+      LAUNCH_CHECK();
+    }
+    if (p->n_norm) {
+      k_normalize<<<p->n_norm, 256, 0, st>>>(p->d_src, p->norm_list, mode, p->d_stamp, grad);
+      LAUNCH_CHECK();
+    }
+  }
+  if (p->n_point) {
+    k_point<<<p->n_point, 256, 0, st>>>(p->d_src, p->d_dyn, p->point_list, p->d_psfst, p->d_out, grad);
+    LAUNCH_CHECK();
+  }
+  if (T.n_conv_tiles[grad]) {
+    k_conv<<<T.n_conv_tiles[grad], 256, T.conv_smem, st>>>(p->d_src, T.conv_jobs[grad], T.conv_tiles[grad], mode,
+                                                           p->d_stamp, p->d_psfst, p->d_out);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int assemble(apb_plan* p, int mode, double** model_out_dev, double** resid_out_dev, double* chi_out2,
+                    int write_flag, cudaStream_t st) {
+  k_assemble<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, mode,
+                                             p->d_stamp, p->d_out, model_out_dev, resid_out_dev,
+                                             chi_out2 ? p->d_chipart : nullptr);
+  LAUNCH_CHECK();
+  if (chi_out2) {
+    k_chi_final<<<1, 256, 0, st>>>(p->d_chipart, p->n_img_tiles, chi_out2, write_flag);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+static int begin_call(apb_plan* p, cudaStream_t st) {
+  if (!p) APB_FAIL("plan is NULL");
+  p->launches = 0;
+  p->last_stream = st;
+  return 0;
+}
+
+extern "C" int apb_sample(apb_plan_t* p, const double* x, int as_rep, double* const* model_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  if (!model_out) APB_FAIL("apb_sample: model_out is NULL");
+  if (p->n_par > 0 && !x) APB_FAIL("apb_sample: x is NULL");
+  CU(cudaMemcpyAsync(p->d_userptr, model_out, sizeof(double*) * p->n_img, cudaMemcpyHostToDevice, st));
+  int rc = sample_pass(p, x, as_rep, 0, 0, st);
+  if (rc) return rc;
+  rc = assemble(p, 0, p->d_userptr, nullptr, nullptr, 0, st);
+  p->stats.launches = p->launches;
+  return rc;
+}
+
+extern "C" int apb_jacobian(apb_plan_t* p, const double* x, int as_rep, double* const* jac_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  if (!jac_out) APB_FAIL("apb_jacobian: jac_out is NULL");
+  for (int ii = 0; ii < p->n_img; ++ii)
+    CU(cudaMemsetAsync(jac_out[ii], 0, sizeof(double) * (size_t)p->h_img[ii].H * p->h_img[ii].W * p->n_par, st));
+  if (p->n_par == 0) return 0;
+  CU(cudaMemcpyAsync(p->d_userptr, jac_out, sizeof(double*) * p->n_img, cudaMemcpyHostToDevice, st));
+  int rc = sample_pass(p, x, as_rep, 1, 1, st);
+  if (rc) return rc;
+  k_jac_dense<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, p->d_stamp,
+                                              p->d_out, p->d_skyJ, p->d_userptr, p->n_par);
+  LAUNCH_CHECK();
+  p->stats.launches = p->launches;
+  return 0;
+}
+
+extern "C" int apb_chi2(apb_plan_t* p, const double* x_rep, double* out2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  for (int ii = 0; ii < p->n_img; ++ii)
+    if (!p->h_img[ii].data) APB_FAIL("apb_chi2: image without data");
+  int rc = sample_pass(p, x_rep, 1, 0, 0, st);
+  if (rc) return rc;
+  rc = assemble(p, 0, nullptr, nullptr, out2, 1, st);
+  p->stats.launches = p->launches;
+  return rc;
+}
+
+extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double* JtWJ, double* JtWr, double* chi2,
+                             void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  for (int ii = 0; ii < p->n_img; ++ii)
+    if (!p->h_img[ii].data) APB_FAIL("apb_normal_eq: image without data");
+  const int P = p->n_par;
+  int rc;
+  if (!p->all_same_geo) {
+    // forward model in group geometry for the residual, then derivatives in own-window geometry
+    if ((rc = sample_pass(p, x, as_rep, 0, 0, st))) return rc;
+    if ((rc = assemble(p, 0, nullptr, p->d_resid, chi2, 0, st))) return rc;
+    if ((rc = sample_pass(p, x, as_rep, 1, 1, st))) return rc;
+  } else {
+    if ((rc = sample_pass(p, x, as_rep, 1, 1, st))) return rc;
+    if ((rc = assemble(p, 1, nullptr, p->d_resid, chi2, 0, st))) return rc;
+  }
+  CU(cudaMemsetAsync(JtWJ, 0, sizeof(double) * (size_t)P * P, st));
+  CU(cudaMemsetAsync(JtWr, 0, sizeof(double) * (size_t)P, st));
+  if (p->n_items) {
+    k_blocks<<<p->n_items, 256, 0, st>>>(p->d_src, p->d_img, p->d_items, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid,
+                                         -1.0, 0, p->d_part);
+    LAUNCH_CHECK();
+    k_block_final<<<ceil_div(p->n_blocks, 4), 128, 0, st>>>(p->d_src, p->d_blocks, p->n_blocks, p->d_act_slot,
+                                                            p->d_act_off, p->d_part, JtWJ, JtWr, P, -1.0, 0);
+    LAUNCH_CHECK();
+  }
+  p->stats.launches = p->launches;
+  return 0;
+}
+
+extern "C" int apb_geodesic(apb_plan_t* p, const double* xdh, const double* h, double d, double* rpp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  const int P = p->n_par;
+  int rc;
+  // rh = W (Y(x + d h) - Y): forward pass only touches plane 0, the cached derivative planes stay valid
+  if ((rc = sample_pass(p, xdh, 1, 0, 0, st))) return rc;
+  if ((rc = assemble(p, 0, nullptr, p->d_resid2, nullptr, 0, st))) return rc;
+  k_geo_v<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, p->d_stamp, p->d_out,
+                                          p->d_skyJ, h, d, p->d_resid, p->d_resid2);
+  LAUNCH_CHECK();
+  CU(cudaMemsetAsync(rpp, 0, sizeof(double) * (size_t)P, st));
+  if (p->n_vitems) {
+    k_blocks<<<p->n_vitems, 256, 0, st>>>(p->d_src, p->d_img, p->d_vitems, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid2,
+                                          1.0, 1, p->d_part);
+    LAUNCH_CHECK();
+    k_block_final<<<ceil_div(p->n_vblocks, 4), 128, 0, st>>>(p->d_src, p->d_vblocks, p->n_vblocks, p->d_act_slot,
+                                                             p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1);
+    LAUNCH_CHECK();
+  }
+  p->stats.launches = p->launches;
+  return 0;
+}
+
+extern "C" int apb_lm_solve(const double* H, const double* g, double L, int P, double* h, int* info, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (P <= 0) return 0;
+  const size_t smem = sizeof(double) * (size_t)P * (P + 1);
+  if (smem > 200 * 1024) APB_FAIL("apb_lm_solve: P too large for the single-CTA solver (max 159); use a library solver");
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_lm_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_lm_solve_small<<<1, 256, smem, st>>>(H, g, L, P, h, info);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) APB_FAIL(std::string("apb_lm_solve launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int apb_plan_stats(apb_plan_t* p, apb_stats_t* out) {
+  if (!p || !out) APB_FAIL("apb_plan_stats: NULL");
+  CU(cudaStreamSynchronize(p->last_stream));
+  int cnt[APB_MAX_DEPTH + 2], ovf = 0;
+  CU(cudaMemcpy(cnt, p->q.count, sizeof(cnt), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&ovf, p->q.overflow, sizeof(int), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  out->first_pass_evals = p->first_evals[0];
+  for (int d = 1; d <= APB_MAX_DEPTH; ++d) out->queued[d] = cnt[d];
+  out->launches = p->stats.launches;
+  out->overflow = ovf;
+  return 0;
+}

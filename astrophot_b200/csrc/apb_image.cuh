@@ -1,0 +1,497 @@
+// PSF handling (sub-pixel shifted stamps, tiled direct convolution, point sources),
+// image assembly / residuals, and the fused normal-equation accumulation.
+#pragma once
+#include "apb_internal.cuh"
+
+// ----------------------------------------------------------------------------
+// shifted, normalised PSF stamp per source + derivative wrt the centre
+// (_model_methods.py:187-243, utils/interpolate.py:282-329).  One CTA per source.
+// Output planes at psfst + s.psf_off: K0, Kcx, Kcy, each sph x spw; Kcx/Kcy already contain
+// d shift / d centre = S^-1 and the chain factor, so conv(value, Kcx) is the J column.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                   const int* __restrict__ list, const apb_psf_t* __restrict__ psfs,
+                                                   double* __restrict__ psfst, int grad) {
+  __shared__ double sh[8];
+  __shared__ double tot_s[3];
+  const int si = list[blockIdx.x];
+  const DevSrc& s = src[si];
+  const DevDyn& d = dyn[si];
+  const apb_psf_t P = psfs[s.psf];
+  const int pw = P.w, ph = P.h;
+  const int spw = s.spw, sph = s.sph, n = spw * sph;
+  double* K0 = psfst + s.psf_off;
+  double* K1 = K0 + n;
+  double* K2 = K1 + n;
+  const bool shifted = s.psf_shift != APB_SHIFT_NONE;
+  // padded image is (ph+2) x (pw+2); stamps either keep the pad (galaxies) or crop it (points)
+  const int crop = (s.kind == APB_POINT && shifted) ? 1 : 0;
+  const int W2 = pw + 2, H2 = ph + 2;
+  double v0 = 0, v1 = 0, v2 = 0;
+  for (int q = threadIdx.x; q < n; q += 256) {
+    const int a = q / spw, b = q % spw;
+    double val, gx = 0, gy = 0;
+    if (!shifted) {
+      val = P.data[a * pw + b];
+    } else {
+      const int i = b + crop, j = a + crop;  // index in the padded image
+      const double x = (double)i - d.sx, y = (double)j - d.sy;
+      int x0 = (int)floor(x), y0 = (int)floor(y);
+      int x1 = min(max(x0 + 1, 1), W2 - 1), y1 = min(max(y0 + 1, 1), H2 - 1);
+      x0 = min(max(x0, 0), W2 - 2);
+      y0 = min(max(y0, 0), H2 - 2);
+      auto pad = [&](int yy, int xx) -> double {
+        return (yy >= 1 && yy <= ph && xx >= 1 && xx <= pw) ? P.data[(yy - 1) * pw + (xx - 1)] : 0.0;
+      };
+      const double fa = pad(y0, x0), fb = pad(y1, x0), fc = pad(y0, x1), fd = pad(y1, x1);
+      const double wx0 = (double)x1 - x, wx1 = x - (double)x0, wy0 = (double)y1 - y, wy1 = y - (double)y0;
+      val = fa * (wx0 * wy0) + fb * (wx0 * wy1) + fc * (wx1 * wy0) + fd * (wx1 * wy1);
+      gx = fa * wy0 + fb * wy1 - fc * wy0 - fd * wy1;  // d/dsx
+      gy = fa * wx0 - fb * wx0 + fc * wx1 - fd * wx1;  // d/dsy
+    }
+    K0[q] = val;
+    v0 += val;
+    if (grad && shifted) {
+      K1[q] = gx;
+      K2[q] = gy;
+      v1 += gx;
+      v2 += gy;
+    }
+  }
+  double t = block_sum<256>(v0, sh);
+  if (threadIdx.x == 0) tot_s[0] = t;
+  t = block_sum<256>(v1, sh);
+  if (threadIdx.x == 0) tot_s[1] = t;
+  t = block_sum<256>(v2, sh);
+  if (threadIdx.x == 0) tot_s[2] = t;
+  __syncthreads();
+  const double tot = tot_s[0], tx = tot_s[1], ty = tot_s[2];
+  for (int q = threadIdx.x; q < n; q += 256) {
+    const double st = K0[q];
+    if (grad && shifted) {
+      const double gx = K1[q] / tot - st * (tx / (tot * tot));
+      const double gy = K2[q] / tot - st * (ty / (tot * tot));
+      K1[q] = (s.Sinv[0] * gx + s.Sinv[2] * gy) * d.chain[0];
+      K2[q] = (s.Sinv[1] * gx + s.Sinv[3] * gy) * d.chain[1];
+    }
+    K0[q] = st / tot;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// point sources (point_source.py:145-175): PSF stamp x 10^flux placed at the rounded centre
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_point(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                               const int* __restrict__ list, const double* __restrict__ psfst,
+                                               double* __restrict__ outar, int grad) {
+  const int si = list[blockIdx.x];
+  const DevSrc& s = src[si];
+  const DevDyn& d = dyn[si];
+  const int n = s.ow * s.oh;
+  const int spw = s.spw, sph = s.sph, ns = spw * sph;
+  const double* K0 = psfst + s.psf_off;
+  const double F = d.k[0];
+  double* o = outar + s.out_off;
+  const int x_lo = d.rx - (spw - 1) / 2, y_lo = d.ry - (sph - 1) / 2;
+  for (int q = threadIdx.x; q < n; q += 256) {
+    const int x = s.ox + q % s.ow, y = s.oy + q / s.ow;
+    const int b = x - x_lo, a = y - y_lo;
+    const bool in = a >= 0 && a < sph && b >= 0 && b < spw;
+    const int k = a * spw + b;
+    o[q] = in ? F * K0[k] : 0.0;
+    if (grad) {
+      if (s.plane[0] > 0) o[(long long)s.plane[0] * n + q] = (in && s.psf_shift != APB_SHIFT_NONE) ? F * K0[ns + k] : 0.0;
+      if (s.plane[1] > 0) o[(long long)s.plane[1] * n + q] = (in && s.psf_shift != APB_SHIFT_NONE) ? F * K0[2 * ns + k] : 0.0;
+      if (s.plane[2] > 0) o[(long long)s.plane[2] * n + q] = in ? APB_LN10 * F * K0[k] * d.chain[2] : 0.0;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// tiled direct convolution, fp64.  One CTA = 32 rows x 64 columns of output; warp w owns an
+// 8-column strip, lane = row; the input tile and the kernel are staged in shared memory; each
+// thread slides an 8-wide register window along the kernel row (1 LDS per 8 DFMA).
+// job: {src, in_plane, kernel index (0..2), out_plane};  tile: {job, tx0, ty0}
+// ----------------------------------------------------------------------------
+#define CONV_TW 64
+#define CONV_TH 32
+__global__ void __launch_bounds__(256) k_conv(const DevSrc* __restrict__ src, const int4* __restrict__ jobs,
+                                              const int4* __restrict__ tiles, int mode,
+                                              const double* __restrict__ stamp, const double* __restrict__ psfst,
+                                              double* __restrict__ outar) {
+  extern __shared__ double smem[];
+  const int4 tl = tiles[blockIdx.x];
+  const int4 jb = jobs[tl.x];
+  const DevSrc& s = src[jb.x];
+  const Geo& g = s.geo[mode];
+  const int spw = s.spw, sph = s.sph;
+  const int cw = (spw - 1) / 2, chh = (sph - 1) / 2;
+  const int iw = CONV_TW + spw - 1, ih = CONV_TH + sph - 1;
+  const int istr = iw | 1;  // odd row stride: conflict-free when lanes walk down rows
+  double* sK = smem;                 // sph*spw, stored flipped so the inner loop walks forward
+  double* sI = smem + sph * spw;     // ih * istr
+  const double* K = psfst + s.psf_off + (long long)jb.z * spw * sph;
+  for (int q = threadIdx.x; q < spw * sph; q += 256) sK[q] = K[spw * sph - 1 - q];
+  // input tile origin in evaluation-region coordinates
+  const int ex = tl.y + s.bx - cw, ey = tl.z + s.by - chh;
+  const double* in = stamp + s.stamp_off + (long long)jb.y * s.plane_stride +
+                     (long long)(g.ey0 - g.my0) * g.mw + (g.ex0 - g.mx0);
+  for (int q = threadIdx.x; q < iw * ih; q += 256) {
+    const int r = q / iw, c = q % iw;
+    const int yy = ey + r, xx = ex + c;
+    sI[r * istr + c] = (yy >= 0 && yy < g.eh && xx >= 0 && xx < g.ew) ? in[(long long)yy * g.mw + xx] : 0.0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  // out[y][x] = sum_{a,b} Kflip[a][b] * tile[y + a][x + b]
+  for (int a = 0; a < sph; ++a) {
+    const double* row = sI + (lane + a) * istr + w * 8;
+    const double* kr = sK + a * spw;
+    double win[8];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) win[k + 1] = row[k];
+    for (int b = 0; b < spw; ++b) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) win[k] = win[k + 1];
+      win[7] = row[b + 7];
+      const double kv = kr[b];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fma(kv, win[k], acc[k]);
+    }
+  }
+  const int oy = tl.z + lane;
+  if (oy < s.oh) {
+    double* o = outar + s.out_off + (long long)jb.w * s.ow * s.oh + (long long)oy * s.ow;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ox = tl.y + w * 8 + k;
+      if (ox < s.ow) o[ox] = acc[k];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// assemble the model image from the per-source stamps (gather by 32x32 image tile, sources in
+// model order => deterministic), fused with residual / chi^2 / finiteness.
+// tile: {image, tx0, ty0, bin};  bins CSR: bin_ptr, bin_src
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                  const apb_image_t* __restrict__ imgs, const int4* __restrict__ tiles,
+                                                  const int* __restrict__ bin_ptr, const int* __restrict__ bin_src,
+                                                  int mode, const double* __restrict__ stamp,
+                                                  const double* __restrict__ outar, double* const* __restrict__ model_out,
+                                                  double* const* __restrict__ resid_out, double* __restrict__ chipart) {
+  __shared__ double sh[8];
+  const int4 t = tiles[blockIdx.x];
+  const apb_image_t im = imgs[t.x];
+  const int b0 = bin_ptr[t.w], b1 = bin_ptr[t.w + 1];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  double chi = 0.0, bad = 0.0;
+  for (int r = 0; r < 4; ++r) {
+    const int x = t.y + lx, y = t.z + ly + 8 * r;
+    if (x >= im.W || y >= im.H) continue;
+    double m = 0.0;
+    for (int b = b0; b < b1; ++b) {
+      const int si = bin_src[b];
+      const DevSrc& s = src[si];
+      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
+      if (s.kind == APB_FLAT_SKY) {
+        m += dyn[si].k[0];
+      } else {
+        const PlaneView v = out_plane(s, mode, 0, stamp, outar);
+        m += v.p[(long long)(y - s.oy) * v.stride + (x - s.ox)];
+      }
+    }
+    const long long p = (long long)y * im.W + x;
+    if (model_out) model_out[t.x][p] = m;
+    if (im.data) {
+      const bool keep = !(im.mask && im.mask[p]);
+      const double w = im.weight ? im.weight[p] : 1.0;
+      const double df = m - im.data[p];
+      const double rr = keep ? w * df : 0.0;   // r = W (Y0 - Y) on unmasked pixels (lm.py:381-385)
+      if (resid_out) resid_out[t.x][p] = rr;
+      if (keep) {
+        chi += w * df * df;
+        if (!isfinite(m)) bad = 1.0;
+      }
+    }
+  }
+  const double c = block_sum<256>(chi, sh);
+  const double bsum = block_sum<256>(bad, sh);
+  if (threadIdx.x == 0 && chipart) {
+    chipart[2 * blockIdx.x] = c;
+    chipart[2 * blockIdx.x + 1] = bsum;
+  }
+}
+
+__global__ void k_chi_final(const double* __restrict__ part, int n, double* __restrict__ out2, int write_flag) {
+  __shared__ double sh[8];
+  double c = 0, b = 0;
+  for (int q = threadIdx.x; q < n; q += 256) {
+    c += part[2 * q];
+    b += part[2 * q + 1];
+  }
+  c = block_sum<256>(c, sh);
+  b = block_sum<256>(b, sh);
+  if (threadIdx.x == 0) {
+    out2[0] = c;
+    if (write_flag) out2[1] = (b == 0.0 && isfinite(c)) ? 1.0 : 0.0;
+  }
+}
+
+// dense Jacobian for small problems (seam 2): J[pix * P + slot] += plane
+__global__ void __launch_bounds__(256) k_jac_dense(const DevSrc* __restrict__ src, const apb_image_t* __restrict__ imgs,
+                                                   const int4* __restrict__ tiles, const int* __restrict__ bin_ptr,
+                                                   const int* __restrict__ bin_src, const double* __restrict__ stamp,
+                                                   const double* __restrict__ outar, const double* __restrict__ skyJ,
+                                                   double* const* __restrict__ jac_out, int P) {
+  const int4 t = tiles[blockIdx.x];
+  const apb_image_t im = imgs[t.x];
+  const int b0 = bin_ptr[t.w], b1 = bin_ptr[t.w + 1];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int r = 0; r < 4; ++r) {
+    const int x = t.y + lx, y = t.z + ly + 8 * r;
+    if (x >= im.W || y >= im.H) continue;
+    double* J = jac_out[t.x] + ((long long)y * im.W + x) * P;
+    for (int b = b0; b < b1; ++b) {
+      const int si = bin_src[b];
+      const DevSrc& s = src[si];
+      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
+      for (int e = 0; e < s.n_elem; ++e) {
+        const int p = s.plane[e];
+        if (p <= 0) continue;
+        double v;
+        if (s.kind == APB_FLAT_SKY) {
+          v = skyJ[si];
+        } else {
+          const PlaneView pv = out_plane(s, 1, p, stamp, outar);
+          v = pv.p[(long long)(y - s.oy) * pv.stride + (x - s.ox)];
+        }
+        J[s.slot[e]] += v;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// normal equations.  work item: source a (planes pa0.., na), source b (planes pb0.., nb), a rectangle
+// of image pixels (rows y0..y0+nrow of the overlap).  Each CTA accumulates the na x nb block of
+// J^T W J (and, for diagonal items, J^T r) over its rectangle in registers, reduces in a fixed
+// order and writes one partial; k_block_final sums the partials of a block in order and adds
+// them into H / g.  The Jacobian exists only as the per-source stamp planes.
+// ----------------------------------------------------------------------------
+struct BlockItem {
+  int a, b;            // sources
+  int pa0, na, pb0, nb;  // 0-based offsets into the active-plane lists
+  int x0, y0, w, h;    // rectangle in image pixels
+  int diag;            // 1: a == b and pa0 == pb0 (symmetric; also accumulates J^T r)
+  int block;           // block id
+};
+
+__device__ __forceinline__ double plane_at(const DevSrc& s, int plane, int x, int y, const double* stamp,
+                                           const double* outar, const double* skyJ, int si) {
+  if (s.kind == APB_FLAT_SKY) return skyJ[si];
+  const PlaneView pv = out_plane(s, 1, plane, stamp, outar);
+  return pv.p[(long long)(y - s.oy) * pv.stride + (x - s.ox)];
+}
+
+#define NB_MAX 8
+#define BLK_VALS (NB_MAX * NB_MAX + NB_MAX)
+__global__ void __launch_bounds__(256) k_blocks(const DevSrc* __restrict__ src, const apb_image_t* __restrict__ imgs,
+                                                const BlockItem* __restrict__ items, const double* __restrict__ stamp,
+                                                const double* __restrict__ outar, const double* __restrict__ skyJ,
+                                                double* const* __restrict__ resid, double gsign, int vec_only,
+                                                double* __restrict__ part) {
+  __shared__ double sh[8][BLK_VALS];
+  const BlockItem it = items[blockIdx.x];
+  const DevSrc& A = src[it.a];
+  const DevSrc& B = src[it.b];
+  const apb_image_t im = imgs[A.image];
+  const double* rimg = resid[A.image];
+  double acc[NB_MAX][NB_MAX];
+  double gv[NB_MAX];
+#pragma unroll
+  for (int i = 0; i < NB_MAX; ++i) {
+    gv[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NB_MAX; ++j) acc[i][j] = 0.0;
+  }
+  const int n = it.w * it.h;
+  for (int q = threadIdx.x; q < n; q += 256) {
+    const int x = it.x0 + q % it.w, y = it.y0 + q / it.w;
+    const long long p = (long long)y * im.W + x;
+    if (im.mask && im.mask[p]) continue;
+    const double w = im.weight ? im.weight[p] : 1.0;
+    double ja[NB_MAX], jb[NB_MAX];
+#pragma unroll
+    for (int i = 0; i < NB_MAX; ++i) ja[i] = i < it.na ? plane_at(A, it.pa0 + i + 1, x, y, stamp, outar, skyJ, it.a) : 0.0;
+    if (it.diag || vec_only) {
+      const double r = rimg[p];
+#pragma unroll
+      for (int i = 0; i < NB_MAX; ++i) gv[i] = fma(r, ja[i], gv[i]);
+    }
+    if (vec_only) continue;
+    if (it.diag) {
+#pragma unroll
+      for (int i = 0; i < NB_MAX; ++i) jb[i] = ja[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NB_MAX; ++i) jb[i] = i < it.nb ? plane_at(B, it.pb0 + i + 1, x, y, stamp, outar, skyJ, it.b) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NB_MAX; ++i) {
+      const double wa = w * ja[i];
+#pragma unroll
+      for (int j = 0; j < NB_MAX; ++j) acc[i][j] = fma(wa, jb[j], acc[i][j]);
+    }
+  }
+  // fixed-order reduction: lanes by shuffle, then the 8 warps through shared memory
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NB_MAX; ++i) {
+#pragma unroll
+    for (int j = 0; j < NB_MAX; ++j) {
+      double v = acc[i][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) sh[wid][i * NB_MAX + j] = v;
+    }
+    double v = gv[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[wid][NB_MAX * NB_MAX + i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < BLK_VALS) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += sh[k][threadIdx.x];
+    part[(long long)blockIdx.x * BLK_VALS + threadIdx.x] = v;
+  }
+}
+
+// block descriptor: its items are contiguous [item0, item0+nitem)
+struct BlockDesc {
+  int a, b, pa0, na, pb0, nb, diag, item0, nitem;
+};
+
+// one warp-sized group of threads per block: sum partials in item order, add into H and g.
+// Entries that belong to a single block are exact; entries shared by several blocks (linked
+// parameters of joint fits) are combined with fp64 atomics.
+__global__ void k_block_final(const DevSrc* __restrict__ src, const BlockDesc* __restrict__ blocks, int nblocks,
+                              const int* __restrict__ act_slot, const int* __restrict__ act_off,
+                              const double* __restrict__ part, double* __restrict__ H, double* __restrict__ g, int P,
+                              double gsign, int vec_only) {
+  const int bi = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (bi >= nblocks) return;
+  const BlockDesc bd = blocks[bi];
+  const int lane = threadIdx.x & 31;
+  const int* sa = act_slot + act_off[bd.a] + bd.pa0;
+  const int* sb = act_slot + act_off[bd.b] + bd.pb0;
+  for (int v = lane; v < BLK_VALS; v += 32) {
+    const int i = v < NB_MAX * NB_MAX ? v / NB_MAX : v - NB_MAX * NB_MAX;
+    const int j = v < NB_MAX * NB_MAX ? v % NB_MAX : -1;
+    if (i >= bd.na) continue;
+    if (j >= 0 && (j >= bd.nb || vec_only)) continue;
+    if (j < 0 && !(bd.diag || vec_only)) continue;
+    double tot = 0.0;
+    for (int k = 0; k < bd.nitem; ++k) tot += part[(long long)(bd.item0 + k) * BLK_VALS + v];
+    if (j < 0) {
+      atomicAdd(&g[sa[i]], gsign * tot);
+    } else {
+      atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
+      if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
+    }
+  }
+}
+
+// J h per pixel and v = (2/d) ((rh - r)/d - W J h)   (lm.py:401-406); gather by image tile
+__global__ void __launch_bounds__(256) k_geo_v(const DevSrc* __restrict__ src, const apb_image_t* __restrict__ imgs,
+                                               const int4* __restrict__ tiles, const int* __restrict__ bin_ptr,
+                                               const int* __restrict__ bin_src, const double* __restrict__ stamp,
+                                               const double* __restrict__ outar, const double* __restrict__ skyJ,
+                                               const double* __restrict__ h, double dstep,
+                                               double* const* __restrict__ r0, double* const* __restrict__ rh_inout) {
+  const int4 t = tiles[blockIdx.x];
+  const apb_image_t im = imgs[t.x];
+  const int b0 = bin_ptr[t.w], b1 = bin_ptr[t.w + 1];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int r = 0; r < 4; ++r) {
+    const int x = t.y + lx, y = t.z + ly + 8 * r;
+    if (x >= im.W || y >= im.H) continue;
+    const long long p = (long long)y * im.W + x;
+    double jh = 0.0;
+    for (int b = b0; b < b1; ++b) {
+      const int si = bin_src[b];
+      const DevSrc& s = src[si];
+      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
+      for (int e = 0; e < s.n_elem; ++e) {
+        const int pl = s.plane[e];
+        if (pl <= 0) continue;
+        jh += plane_at(s, pl, x, y, stamp, outar, skyJ, si) * h[s.slot[e]];
+      }
+    }
+    const bool keep = !(im.mask && im.mask[p]);
+    const double w = im.weight ? im.weight[p] : 1.0;
+    const double v = keep ? (2.0 / dstep) * ((rh_inout[t.x][p] - r0[t.x][p]) / dstep - w * jh) : 0.0;
+    rh_inout[t.x][p] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// damped solve for small P: one CTA, Gaussian elimination with partial pivoting in shared memory
+// (lm.py:359-371)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict__ H, const double* __restrict__ g,
+                                                        double L, int P, double* __restrict__ h, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double* A = sm;          // P x (P+1) augmented
+  __shared__ int piv_s;
+  const int ld = P + 1;
+  for (int q = threadIdx.x; q < P * P; q += blockDim.x) {
+    const int i = q / P, j = q % P;
+    const double hij = H[q];
+    A[i * ld + j] = (i == j) ? hij + L * (1.0 + hij) : hij / (1.0 + L);
+  }
+  for (int q = threadIdx.x; q < P; q += blockDim.x) A[q * ld + P] = g[q];
+  __syncthreads();
+  int bad = 0;
+  for (int k = 0; k < P; ++k) {
+    if (threadIdx.x == 0) {
+      int pv = k;
+      double best = fabs(A[k * ld + k]);
+      for (int i = k + 1; i < P; ++i) {
+        const double v = fabs(A[i * ld + k]);
+        if (v > best) { best = v; pv = i; }
+      }
+      piv_s = pv;
+      if (!(best > 0.0)) bad = 1;
+    }
+    __syncthreads();
+    const int pv = piv_s;
+    if (pv != k)
+      for (int j = threadIdx.x; j <= P; j += blockDim.x) {
+        const double tmp = A[k * ld + j];
+        A[k * ld + j] = A[pv * ld + j];
+        A[pv * ld + j] = tmp;
+      }
+    __syncthreads();
+    const double inv = 1.0 / A[k * ld + k];
+    for (int q = threadIdx.x; q < (P - k - 1) * (P - k); q += blockDim.x) {
+      const int i = k + 1 + q / (P - k), j = k + 1 + q % (P - k);
+      A[i * ld + j] -= A[i * ld + k] * inv * A[k * ld + j];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = P - 1; i >= 0; --i) {
+      double v = A[i * ld + P];
+      for (int j = i + 1; j < P; ++j) v -= A[i * ld + j] * h[j];
+      h[i] = v / A[i * ld + i];
+    }
+    if (info) *info = bad;
+  }
+}

@@ -1,0 +1,259 @@
+// Internal device structures and the per-point profile evaluation shared by the
+// kernels of libastrophot_b200.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/astrophot_b200.h"
+
+#define APB_LN10 2.302585092994045684
+#define APB_PI 3.141592653589793238
+
+// -----------------------------------------------------------------------------
+// static per-source table (built once per plan)
+// -----------------------------------------------------------------------------
+struct Geo {
+  int ex0, ey0, ew, eh;  // evaluation region: out window +- psf border (image pixels)
+  int rx0, ry0, rw, rh;  // working region: working window +- psf border
+  int mx0, my0, mw, mh;  // stamp region: evaluation region + 1 px ring, clipped to working region
+  int tile0, ntile;      // this source's tiles in the mode's tile list
+  int chunk0, nchunk;    // mean-reference partial sums (REF_MEAN only)
+};
+
+struct DevSrc {
+  int kind, flags, image, n_elem;
+  int ox, oy, ow, oh;
+  Geo geo[2];  // 0 = forward sampling, 1 = jacobian
+  int slot[APB_MAX_ELEM];
+  double cval[APB_MAX_ELEM];
+  int plane[APB_MAX_ELEM];  // derivative plane (1..n_act) of each element, 0 = none
+  int n_act;
+  int n_prof;
+  double prof[APB_MAX_PROF];
+  int sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth, ref_mode;
+  double tol, soft2;
+  int psf, psf_shift, bx, by, pw, ph;  // pw, ph: raw PSF size
+  long long stamp_off;     // doubles, into the stamp arena; plane p at stamp_off + p*plane_stride
+  long long plane_stride;  // >= mw*mh of both modes
+  long long out_off;       // PSF sources: offset of cropped planes (ow*oh each) in the out arena; else -1
+  long long psf_off;       // offset of this source's shifted PSF stamps (3 x spw*sph) or -1
+  int spw, sph;            // shifted stamp size
+  double S[4], Sinv[4], rij[2], rxy[2], area;
+  int same_geo;            // forward and jacobian geometry identical
+};
+
+// per-call, per-source values
+struct DevDyn {
+  double el[APB_MAX_ELEM];
+  double chain[APB_MAX_ELEM];  // d value / d x  (0 for locked)
+  double c, s, qinv;           // rotation by -(PA - pi/2), 1/q
+  double k[8];                 // per-kind constants (see prep kernel)
+  double sx, sy;               // sub-pixel shift of the centre (PSF sources)
+  int rx, ry;                  // rounded centre pixel
+  double thr[2];               // tolerance * reference per mode
+  double spl_m[APB_MAX_PROF];  // spline slopes
+};
+
+// view of one output plane of a source, in the output window
+struct PlaneView {
+  const double* p;
+  int stride;
+};
+
+__device__ __forceinline__ PlaneView out_plane(const DevSrc& s, int mode, int plane, const double* stamp,
+                                               const double* outar) {
+  PlaneView v;
+  if (s.out_off >= 0) {
+    v.p = outar + s.out_off + (long long)plane * s.ow * s.oh;
+    v.stride = s.ow;
+  } else {
+    const Geo& g = s.geo[mode];
+    v.p = stamp + s.stamp_off + plane * s.plane_stride + (long long)(s.oy - g.my0) * g.mw + (s.ox - g.mx0);
+    v.stride = g.mw;
+  }
+  return v;
+}
+
+// -----------------------------------------------------------------------------
+// quadrature tables
+// -----------------------------------------------------------------------------
+struct QuadTab {
+  double a[APB_MAX_QUAD + 1][APB_MAX_QUAD];  // abscissae / 2  (unit pixel offsets)
+  double w[APB_MAX_QUAD + 1][APB_MAX_QUAD];  // weights / 2
+};
+__constant__ QuadTab c_quad;
+
+// -----------------------------------------------------------------------------
+// profile evaluation
+// -----------------------------------------------------------------------------
+__device__ __forceinline__ double sersic_b(double n) {
+  double i = 1.0 / n;
+  return 2 * n - 1.0 / 3 + i * (4.0 / 405 + i * (46.0 / 25515 + i * (131.0 / 1148175 - i * (2194697.0 / 30690717750.0))));
+}
+__device__ __forceinline__ double sersic_db(double n) {
+  double i = 1.0 / n;
+  double i2 = i * i;
+  return 2 - i2 * (4.0 / 405 + i * (92.0 / 25515 + i * (393.0 / 1148175 - i * (4 * 2194697.0 / 30690717750.0))));
+}
+
+// Evaluate brightness I at plane offset (X, Y) from the centre, scaled by `ascale`
+// (sub-pixel area factor), and optionally dI/d(element) for every element.
+// NE = compile-time element bound for the kind.  dI must hold n_elem doubles.
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, double X, double Y, double ascale,
+                                             double* __restrict__ dI) {
+  double xp, yp;
+  const bool radial = (s.flags & APB_F_RADIAL) != 0;
+  if (radial) {
+    xp = X;
+    yp = Y;
+  } else {
+    xp = d.c * X - d.s * Y;
+    yp = (d.s * X + d.c * Y) * d.qinv;
+  }
+  const double R2 = xp * xp + yp * yp + s.soft2;
+  double I, dIdR_over_R;  // (dI/dR)/R : multiply by xp, yp pieces to get dI/dX
+  if (KIND == APB_SERSIC) {
+    // k0 = area*10^Ie, k1 = 1/Re^2, k2 = 1/(2n), k3 = b_n, k4 = b'_n, k5 = 1/n, k6 = 1/Re
+    const double L2 = log(R2 * d.k[1]);  // 2 ln(R/Re)
+    const double u = exp(L2 * d.k[2]);
+    I = ascale * d.k[0] * exp(-d.k[3] * (u - 1.0));
+    if (GRAD) {
+      const double bu = d.k[3] * u;
+      dIdR_over_R = -I * bu * d.k[5] / R2;
+      dI[4] = I * (-d.k[4] * (u - 1.0) + bu * (0.5 * L2) * d.k[5] * d.k[5]);
+      dI[5] = I * bu * d.k[5] * d.k[6];
+      dI[6] = APB_LN10 * I;
+    }
+  } else if (KIND == APB_EXPONENTIAL) {
+    // k0 = area*10^Ie, k1 = 1/Re, k2 = b_1
+    const double R = sqrt(R2);
+    I = ascale * d.k[0] * exp(-d.k[2] * (R * d.k[1] - 1.0));
+    if (GRAD) {
+      dIdR_over_R = -I * d.k[2] * d.k[1] / R;
+      dI[4] = I * d.k[2] * R * d.k[1] * d.k[1];
+      dI[5] = APB_LN10 * I;
+    }
+  } else if (KIND == APB_GAUSSIAN) {
+    // k0 = area*10^flux/sqrt(2 pi sigma^2), k1 = 1/sigma^2, k2 = 1/sigma
+    I = ascale * d.k[0] * exp(-0.5 * R2 * d.k[1]);
+    if (GRAD) {
+      dIdR_over_R = -I * d.k[1];
+      dI[4] = I * (-d.k[2] + R2 * d.k[1] * d.k[2]);
+      dI[5] = APB_LN10 * I;
+    }
+  } else if (KIND == APB_MOFFAT) {
+    // k0 = area*10^I0, k1 = 1/Rd^2, k2 = n, k3 = 1/Rd
+    const double t = 1.0 + R2 * d.k[1];
+    const double lt = log(t);
+    I = ascale * d.k[0] * exp(-d.k[2] * lt);
+    if (GRAD) {
+      dIdR_over_R = -I * d.k[2] * 2.0 * d.k[1] / t;
+      dI[4] = -I * lt;
+      dI[5] = I * d.k[2] * 2.0 * R2 * d.k[1] * d.k[3] / t;
+      dI[6] = APB_LN10 * I;
+    }
+  } else {  // APB_SPLINE: k0 = area
+    const double R = sqrt(R2);
+    const int K = s.n_prof;
+    // idx = searchsorted(prof[:-1], R, left) - 1, wrapping -1 -> K-1 (utils/interpolate.py:53)
+    int idx = -1;
+    for (int k = 0; k < K - 1; ++k)
+      if (s.prof[k] < R) idx = k;
+    const double* v = d.el + 4;
+    double sv, dsdR;
+    if (GRAD)
+      for (int k = 0; k < K; ++k) dI[4 + k] = 0.0;
+    if (R > s.prof[K - 1]) {
+      const double h = s.prof[K - 1] - s.prof[K - 2];
+      const double f = (R - s.prof[K - 2]) / h;
+      sv = v[K - 2] + (R - s.prof[K - 2]) * ((v[K - 1] - v[K - 2]) / h);
+      dsdR = (v[K - 1] - v[K - 2]) / h;
+      I = ascale * d.k[0] * exp(APB_LN10 * sv);
+      if (GRAD) {
+        dI[4 + K - 2] = APB_LN10 * I * (1.0 - f);
+        dI[4 + K - 1] = APB_LN10 * I * f;
+      }
+    } else {
+      const int i0 = idx < 0 ? K - 1 : idx;
+      const int i1 = idx + 1;
+      const double dx = s.prof[i1] - s.prof[i0];
+      const double t = (R - s.prof[i0]) / dx;
+      const double t2 = t * t, t3 = t2 * t;
+      const double h00 = 1 - 3 * t2 + 2 * t3, h10 = t - 2 * t2 + t3, h01 = 3 * t2 - 2 * t3, h11 = t3 - t2;
+      sv = h00 * v[i0] + h10 * d.spl_m[i0] * dx + h01 * v[i1] + h11 * d.spl_m[i1] * dx;
+      I = ascale * d.k[0] * exp(APB_LN10 * sv);
+      if (GRAD) {
+        dsdR = ((-6 * t + 6 * t2) * v[i0] + (1 - 4 * t + 3 * t2) * d.spl_m[i0] * dx + (6 * t - 6 * t2) * v[i1] +
+                (-2 * t + 3 * t2) * d.spl_m[i1] * dx) / dx;
+        const double g = APB_LN10 * I;
+        dI[4 + i0] += g * h00;
+        dI[4 + i1] += g * h01;
+        // slopes: m_0 = D_0, m_k = (D_{k-1}+D_k)/2, m_{K-1} = D_{K-2},  D_k = (v_{k+1}-v_k)/h_k
+        const int ms[2] = {i0, i1};
+        const double mw_[2] = {g * h10 * dx, g * h11 * dx};
+        for (int q = 0; q < 2; ++q) {
+          const int m = ms[q];
+          const double w = mw_[q];
+          if (m == 0) {
+            const double ih = 1.0 / (s.prof[1] - s.prof[0]);
+            dI[4 + 1] += w * ih;
+            dI[4 + 0] -= w * ih;
+          } else if (m == K - 1) {
+            const double ih = 1.0 / (s.prof[K - 1] - s.prof[K - 2]);
+            dI[4 + K - 1] += w * ih;
+            dI[4 + K - 2] -= w * ih;
+          } else {
+            const double ia = 0.5 / (s.prof[m] - s.prof[m - 1]);
+            const double ib = 0.5 / (s.prof[m + 1] - s.prof[m]);
+            dI[4 + m] += w * (ia - ib);
+            dI[4 + m - 1] -= w * ia;
+            dI[4 + m + 1] += w * ib;
+          }
+        }
+      }
+    }
+    if (GRAD) dIdR_over_R = APB_LN10 * I * dsdR / R;
+  }
+  if (GRAD) {
+    // dR/dX * R = xp*c + yp*s/q ; dR/dY * R = -xp*s + yp*c/q
+    if (radial) {
+      dI[0] = -dIdR_over_R * xp;
+      dI[1] = -dIdR_over_R * yp;
+      dI[2] = 0.0;
+      dI[3] = 0.0;
+    } else {
+      dI[0] = -dIdR_over_R * (xp * d.c + yp * d.s * d.qinv);
+      dI[1] = -dIdR_over_R * (-xp * d.s + yp * d.c * d.qinv);
+      dI[2] = dIdR_over_R * (-(yp * yp) * d.qinv);
+      dI[3] = dIdR_over_R * (xp * yp * (d.el[2] - d.qinv));
+    }
+  }
+  return I;
+}
+
+template <int KIND>
+struct KindInfo {};
+template <> struct KindInfo<APB_SERSIC> { static constexpr int NE = 7; };
+template <> struct KindInfo<APB_EXPONENTIAL> { static constexpr int NE = 6; };
+template <> struct KindInfo<APB_GAUSSIAN> { static constexpr int NE = 6; };
+template <> struct KindInfo<APB_MOFFAT> { static constexpr int NE = 7; };
+template <> struct KindInfo<APB_SPLINE> { static constexpr int NE = APB_MAX_ELEM; };
+
+// deterministic block reduction (fixed tree), result valid in thread 0
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (wid == 0) {
+    r = lane < NT / 32 ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+  }
+  __syncthreads();
+  return r;
+}

@@ -1,0 +1,543 @@
+// Sampling kernels: parameter prep, first pass, curvature select + ballot compaction,
+// work-queue refinement, reduction, scatter, PSF-model normalisation.
+#pragma once
+#include "apb_internal.cuh"
+
+// work queues of the adaptive integration (one set per refinement depth)
+struct Level {
+  int* src;      // source of each entry
+  double* x;     // plane offset from the centre
+  double* y;
+  int* parent;   // depth 1: pixel index in the stamp; deeper: entry index one level up
+  int* child;    // first child entry one level down, or -1
+  double* res;   // [entry * NVp + plane]
+};
+
+struct Queues {
+  Level lv[APB_MAX_DEPTH + 1];  // index by depth (1-based)
+  int* count;                   // [APB_MAX_DEPTH + 2] entries per depth, device
+  int* overflow;                // device flag
+  int cap;
+  int NVp;                      // planes carried per entry in this pass
+};
+
+// ----------------------------------------------------------------------------
+// prep: x -> per-source natural values, chain factors, constants
+// ----------------------------------------------------------------------------
+__global__ void k_prep(const DevSrc* __restrict__ src, DevDyn* __restrict__ dyn, int n_src,
+                       const apb_param_t* __restrict__ par, const double* __restrict__ x, int as_rep,
+                       int* qcount, double* skyJ, int write_skyJ) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  if (si == 0 && qcount) {
+    for (int k = 0; k < APB_MAX_DEPTH + 2; ++k) qcount[k] = 0;
+  }
+  if (si >= n_src) return;
+  const DevSrc& s = src[si];
+  DevDyn& d = dyn[si];
+  for (int e = 0; e < s.n_elem; ++e) {
+    const int sl = s.slot[e];
+    double v = s.cval[e], ch = 0.0;
+    if (sl >= 0) {
+      const double r = x[sl];
+      v = r;
+      ch = 1.0;
+      if (as_rep) {
+        const apb_param_t p = par[sl];
+        if (p.transform == APB_TR_LOWER) {
+          const double dd = r - p.lo, rt = sqrt(dd * dd + 4.0);
+          v = 0.5 * (r + p.lo + rt);
+          ch = 0.5 + 0.5 * dd / rt;
+        } else if (p.transform == APB_TR_UPPER) {
+          const double dd = r - p.hi, rt = sqrt(dd * dd + 4.0);
+          v = 0.5 * (r + p.hi - rt);
+          ch = 0.5 - 0.5 * dd / rt;
+        } else if (p.transform == APB_TR_BOTH) {
+          v = (atan(r) + APB_PI / 2) * (p.hi - p.lo) / APB_PI + p.lo;
+          ch = (p.hi - p.lo) / (APB_PI * (r * r + 1.0));
+        } else if (p.transform == APB_TR_CYCLIC) {
+          const double per = p.hi - p.lo;
+          double m = fmod(r - p.lo, per);
+          if (m < 0) m += per;
+          v = p.lo + m;
+        }
+      }
+    }
+    d.el[e] = v;
+    d.chain[e] = ch;
+  }
+  const double cx = d.el[0], cy = d.el[1];
+  // pixel position of the centre, sub-pixel shift (model_object.py:320-323, point_source.py:149-150)
+  const double pcx = s.Sinv[0] * (cx - s.rxy[0]) + s.Sinv[1] * (cy - s.rxy[1]) + s.rij[0];
+  const double pcy = s.Sinv[2] * (cx - s.rxy[0]) + s.Sinv[3] * (cy - s.rxy[1]) + s.rij[1];
+  const double rx = rint(pcx), ry = rint(pcy);
+  d.rx = (int)rx;
+  d.ry = (int)ry;
+  d.sx = pcx - rx;
+  d.sy = pcy - ry;
+  for (int k = 0; k < 8; ++k) d.k[k] = 0.0;
+  d.thr[0] = d.thr[1] = 0.0;
+  d.c = 1.0;
+  d.s = 0.0;
+  d.qinv = 1.0;
+  if (s.kind == APB_FLAT_SKY) {
+    d.k[0] = s.area * exp10(d.el[2]);
+    if (write_skyJ) skyJ[si] = APB_LN10 * d.k[0] * d.chain[2];
+    return;
+  }
+  if (s.kind == APB_POINT) {
+    d.k[0] = exp10(d.el[2]);
+    return;
+  }
+  if (!(s.flags & APB_F_RADIAL)) {
+    const double th = -(d.el[3] - APB_PI / 2);
+    sincos(th, &d.s, &d.c);
+    d.qinv = 1.0 / d.el[2];
+  }
+  if (s.kind == APB_SERSIC) {
+    const double n = d.el[4], Re = d.el[5];
+    const double bn = sersic_b(n);
+    d.k[0] = s.area * exp10(d.el[6]);
+    d.k[1] = 1.0 / (Re * Re);
+    d.k[2] = 0.5 / n;
+    d.k[3] = bn;
+    d.k[4] = sersic_db(n);
+    d.k[5] = 1.0 / n;
+    d.k[6] = 1.0 / Re;
+    if (s.ref_mode == APB_REF_SERSIC_FLUX) {
+      // total flux / numel of the working image (sersic_model.py:87-89, conversions/functions.py:168-190)
+      const double flux = 2 * APB_PI * exp10(d.el[6]) * Re * Re * d.el[2] * n * (exp(bn) * pow(bn, -2 * n)) * exp(lgamma(2 * n));
+      for (int m = 0; m < 2; ++m)
+        d.thr[m] = s.tol * (flux / ((double)s.geo[m].rw * (double)s.geo[m].rh));
+    }
+  } else if (s.kind == APB_EXPONENTIAL) {
+    d.k[0] = s.area * exp10(d.el[5]);
+    d.k[1] = 1.0 / d.el[4];
+    d.k[2] = sersic_b(1.0);
+  } else if (s.kind == APB_GAUSSIAN) {
+    const double sg = d.el[4];
+    d.k[0] = s.area * exp10(d.el[5]) / sqrt(2 * APB_PI * sg * sg);
+    d.k[1] = 1.0 / (sg * sg);
+    d.k[2] = 1.0 / sg;
+  } else if (s.kind == APB_MOFFAT) {
+    d.k[0] = s.area * exp10(d.el[6]);
+    d.k[1] = 1.0 / (d.el[5] * d.el[5]);
+    d.k[2] = d.el[4];
+    d.k[3] = 1.0 / d.el[5];
+  } else if (s.kind == APB_SPLINE) {
+    d.k[0] = s.area;
+    const int K = s.n_prof;
+    const double* v = d.el + 4;
+    for (int k = 0; k < K; ++k) {
+      double m;
+      if (k == 0) m = (v[1] - v[0]) / (s.prof[1] - s.prof[0]);
+      else if (k == K - 1) m = (v[K - 1] - v[K - 2]) / (s.prof[K - 1] - s.prof[K - 2]);
+      else m = ((v[k] - v[k - 1]) / (s.prof[k] - s.prof[k - 1]) + (v[k + 1] - v[k]) / (s.prof[k + 1] - s.prof[k])) / 2;
+      d.spl_m[k] = m;
+    }
+  }
+}
+
+// plane coordinates (relative to the centre) of image pixel (pi, pj)
+__device__ __forceinline__ void pix_coords(const DevSrc& s, const DevDyn& d, double pi, double pj, double& X,
+                                           double& Y) {
+  if (s.psf >= 0 && s.psf_shift != APB_SHIFT_NONE) {
+    // grid re-centred on the source: X = S.(pix - round(pc))   (model_object.py:320-323)
+    const double di = pi - d.rx, dj = pj - d.ry;
+    X = s.S[0] * di + s.S[1] * dj;
+    Y = s.S[2] * di + s.S[3] * dj;
+  } else {
+    const double di = pi - s.rij[0], dj = pj - s.rij[1];
+    X = (s.S[0] * di + s.S[1] * dj + s.rxy[0]) - d.el[0];
+    Y = (s.S[2] * di + s.S[3] * dj + s.rxy[1]) - d.el[1];
+  }
+}
+
+// Gauss-Legendre n x n over one (sub)pixel whose edge vectors are S*scale.
+// acc[0] = integral, acc[1+e] = derivative wrt element e (natural units); returns the centre node.
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double gl_integrate(const DevSrc& s, const DevDyn& d, double X, double Y, int n,
+                                               double scale, double ascale, double* __restrict__ acc) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  double dI[GRAD ? NE : 1];
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  acc[0] = 0.0;
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) acc[1 + e] = 0.0;
+  double centre = 0.0;
+  const int mid = (n * n) / 2;
+  for (int k = 0; k < n * n; ++k) {
+    const int kx = k % n, ky = k / n;
+    const double ax = c_quad.a[n][kx] * scale, ay = c_quad.a[n][ky] * scale;
+    const double w = c_quad.w[n][kx] * c_quad.w[n][ky];
+    const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ax + s.S[1] * ay), Y + (s.S[2] * ax + s.S[3] * ay),
+                                            ascale, dI);
+    if (k == mid) centre = I;
+    acc[0] += I * w;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc[1 + e] += dI[e] * w;
+  }
+  return centre;
+}
+
+// ----------------------------------------------------------------------------
+// first pass over the stamp region (one 32x8 tile per CTA)
+// ----------------------------------------------------------------------------
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& d, const Geo& g, int i, int j,
+                                                 double* __restrict__ stamp, int err_plane) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  const int pi = g.mx0 + i, pj = g.my0 + j;
+  double X, Y;
+  pix_coords(s, d, (double)pi, (double)pj, X, Y);
+  double* base = stamp + s.stamp_off + (long long)j * g.mw + i;
+  const bool in_e = pi >= g.ex0 && pi < g.ex0 + g.ew && pj >= g.ey0 && pj < g.ey0 + g.eh;
+  double acc[(GRAD ? NE : 0) + 1];
+  if (s.sampling_mode == APB_SAMPLE_MIDPOINT) {
+    acc[0] = eval_point<KIND, GRAD>(s, d, X, Y, 1.0, acc + 1);
+  } else if (s.sampling_mode == APB_SAMPLE_QUAD) {
+    const double centre = gl_integrate<KIND, GRAD>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
+    base[(long long)err_plane * s.plane_stride] = fabs(acc[0] - centre);
+  } else {  // simpsons: 3x3 half-pixel lattice, weights [1 4 1; 4 16 4; 1 4 1]/36 (_model_methods.py:99-109)
+    double dI[GRAD ? NE : 1];
+    acc[0] = 0.0;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc[1 + e] = 0.0;
+    double midv = 0.0;
+    for (int a = -1; a <= 1; ++a)
+      for (int b = -1; b <= 1; ++b) {
+        const double w = ((a == 0 ? 4.0 : 1.0) * (b == 0 ? 4.0 : 1.0)) / 36.0;
+        const double ox = 0.5 * b, oy = 0.5 * a;
+        const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy),
+                                                1.0, dI);
+        if (a == 0 && b == 0) midv = I;
+        acc[0] += w * I;
+        if (GRAD)
+          for (int e = 0; e < ne; ++e) acc[1 + e] += w * dI[e];
+      }
+    base[(long long)err_plane * s.plane_stride] = fabs(acc[0] - midv);
+  }
+  base[0] = acc[0];
+  if (GRAD && in_e) {
+    for (int e = 0; e < ne; ++e) {
+      const int p = s.plane[e];
+      if (p > 0) base[(long long)p * s.plane_stride] = acc[1 + e] * d.chain[e];
+    }
+  }
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(256) k_first(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                               const int4* __restrict__ tiles, int mode, double* __restrict__ stamp,
+                                               int err_plane_unused) {
+  const int4 t = tiles[blockIdx.x];
+  const DevSrc& s = src[t.x];
+  const DevDyn& d = dyn[t.x];
+  const Geo& g = s.geo[mode];
+  const int i = t.y + (threadIdx.x & 31), j = t.z + (threadIdx.x >> 5);
+  if (i >= g.mw || j >= g.mh) return;
+  const int errp = s.n_act + 1;
+  switch (s.kind) {
+    case APB_SERSIC: first_pass_pixel<APB_SERSIC, GRAD>(s, d, g, i, j, stamp, errp); break;
+    case APB_EXPONENTIAL: first_pass_pixel<APB_EXPONENTIAL, GRAD>(s, d, g, i, j, stamp, errp); break;
+    case APB_GAUSSIAN: first_pass_pixel<APB_GAUSSIAN, GRAD>(s, d, g, i, j, stamp, errp); break;
+    case APB_MOFFAT: first_pass_pixel<APB_MOFFAT, GRAD>(s, d, g, i, j, stamp, errp); break;
+    case APB_SPLINE: first_pass_pixel<APB_SPLINE, GRAD>(s, d, g, i, j, stamp, errp); break;
+    default: break;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// mean reference (default _integrate_reference = mean of the first-pass image over the
+// WORKING region, _model_methods.py:151-152).  Two stages, fixed order => deterministic.
+// chunk list: {src, first pixel, n pixels, slot}
+// ----------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double first_value(const DevSrc& s, const DevDyn& d, double X, double Y) {
+  double acc[1];
+  if (s.sampling_mode == APB_SAMPLE_MIDPOINT) return eval_point<KIND, false>(s, d, X, Y, 1.0, acc);
+  if (s.sampling_mode == APB_SAMPLE_QUAD) {
+    gl_integrate<KIND, false>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
+    return acc[0];
+  }
+  double tot = 0.0;
+  for (int a = -1; a <= 1; ++a)
+    for (int b = -1; b <= 1; ++b) {
+      const double w = ((a == 0 ? 4.0 : 1.0) * (b == 0 ? 4.0 : 1.0)) / 36.0;
+      const double ox = 0.5 * b, oy = 0.5 * a;
+      tot += w * eval_point<KIND, false>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy), 1.0, acc);
+    }
+  return tot;
+}
+
+__global__ void __launch_bounds__(256) k_mean_partial(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                      const int4* __restrict__ chunks, int mode,
+                                                      const double* __restrict__ stamp, double* __restrict__ part) {
+  __shared__ double sh[8];
+  const int4 c = chunks[blockIdx.x];
+  const DevSrc& s = src[c.x];
+  const DevDyn& d = dyn[c.x];
+  const Geo& g = s.geo[mode];
+  const bool from_stamp = (g.mx0 == g.rx0 && g.my0 == g.ry0 && g.mw == g.rw && g.mh == g.rh);
+  double v = 0.0;
+  for (int q = threadIdx.x; q < c.z; q += 256) {
+    const int p = c.y + q;
+    if (from_stamp) {
+      v += stamp[s.stamp_off + p];
+    } else {
+      const int i = p % g.rw, j = p / g.rw;
+      double X, Y;
+      pix_coords(s, d, (double)(g.rx0 + i), (double)(g.ry0 + j), X, Y);
+      switch (s.kind) {
+        case APB_SERSIC: v += first_value<APB_SERSIC>(s, d, X, Y); break;
+        case APB_EXPONENTIAL: v += first_value<APB_EXPONENTIAL>(s, d, X, Y); break;
+        case APB_GAUSSIAN: v += first_value<APB_GAUSSIAN>(s, d, X, Y); break;
+        case APB_MOFFAT: v += first_value<APB_MOFFAT>(s, d, X, Y); break;
+        case APB_SPLINE: v += first_value<APB_SPLINE>(s, d, X, Y); break;
+        default: break;
+      }
+    }
+  }
+  const double tot = block_sum<256>(v, sh);
+  if (threadIdx.x == 0) part[c.w] = tot;
+}
+
+__global__ void k_mean_final(const DevSrc* __restrict__ src, DevDyn* __restrict__ dyn, const int* __restrict__ list,
+                             int n, int mode, const double* __restrict__ part) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int si = list[q];
+  const DevSrc& s = src[si];
+  const Geo& g = s.geo[mode];
+  double tot = 0.0;
+  for (int k = 0; k < g.nchunk; ++k) tot += part[g.chunk0 + k];
+  dyn[si].thr[mode] = s.tol * (tot / ((double)g.rw * (double)g.rh));
+}
+
+// ----------------------------------------------------------------------------
+// select: curvature test + warp-ballot compaction into the depth-1 queue
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_select(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                const int4* __restrict__ tiles, int mode,
+                                                const double* __restrict__ stamp, Queues q) {
+  const int4 t = tiles[blockIdx.x];
+  const DevSrc& s = src[t.x];
+  if (s.integrate_mode != APB_INTEGRATE_THRESHOLD) return;
+  const DevDyn& d = dyn[t.x];
+  const Geo& g = s.geo[mode];
+  const int i = t.y + (threadIdx.x & 31), j = t.z + (threadIdx.x >> 5);
+  bool sel = false;
+  double X = 0, Y = 0;
+  if (i < g.mw && j < g.mh) {
+    const int pi = g.mx0 + i, pj = g.my0 + j;
+    if (pi >= g.ex0 && pi < g.ex0 + g.ew && pj >= g.ey0 && pj < g.ey0 + g.eh) {
+      const double* m = stamp + s.stamp_off;
+      double err;
+      if (s.sampling_mode == APB_SAMPLE_MIDPOINT) {
+        if (g.rw >= 3 && g.rh >= 3) {
+          // 3x3 Laplacian, replicate-padded over the working region (_model_methods.py:87-98)
+          int ic = min(max(pi, g.rx0 + 1), g.rx0 + g.rw - 2) - g.mx0;
+          int jc = min(max(pj, g.ry0 + 1), g.ry0 + g.rh - 2) - g.my0;
+          ic = min(max(ic, 1), g.mw - 2);
+          jc = min(max(jc, 1), g.mh - 2);
+          const double* c = m + (long long)jc * g.mw + ic;
+          err = fabs(c[-g.mw] + c[-1] + c[1] + c[g.mw] - 4.0 * c[0]);
+        } else {
+          err = 0.0;
+        }
+      } else {
+        err = m[(long long)(s.n_act + 1) * s.plane_stride + (long long)j * g.mw + i];
+      }
+      sel = err > d.thr[mode];
+      if (sel) pix_coords(s, d, (double)pi, (double)pj, X, Y);
+    }
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, sel);
+  if (bal == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&q.count[1], __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (sel) {
+    const int e = base + __popc(bal & ((1u << lane) - 1));
+    if (e < q.cap) {
+      Level& L = q.lv[1];
+      L.src[e] = t.x;
+      L.x[e] = X;
+      L.y[e] = Y;
+      L.parent[e] = j * g.mw + i;
+      L.child[e] = -1;
+    } else {
+      *q.overflow = 1;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// refinement: one thread per queued (sub)pixel, Gauss-Legendre, ballot-compacted re-queue
+// (utils/operations.py:123-247)
+// ----------------------------------------------------------------------------
+template <int KIND, bool GRAD>
+__device__ __forceinline__ bool refine_entry(const DevSrc& s, const DevDyn& d, int mode, int depth, double X, double Y,
+                                             double* __restrict__ res, int NVp) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  double acc[(GRAD ? NE : 0) + 1];
+  double scale = 1.0, ascale = 1.0, thr = d.thr[mode];
+  const double G = (double)s.gridding;
+  for (int k = 1; k < depth; ++k) {
+    scale /= G;
+    ascale /= G * G;
+    thr *= G * G;
+  }
+  const double centre = gl_integrate<KIND, GRAD>(s, d, X, Y, s.quad_level, scale, ascale, acc);
+  if (depth < s.max_depth && fabs(acc[0] - centre) > thr) return true;
+  res[0] = acc[0];
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) {
+      const int p = s.plane[e];
+      if (p > 0) res[p] = acc[1 + e] * d.chain[e];
+    }
+  return false;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                int mode, int depth, Queues q) {
+  const int n = min(q.count[depth], q.cap);
+  const Level& L = q.lv[depth];
+  const int lane = threadIdx.x & 31;
+  // whole warps iterate together so the ballot below is well defined
+  for (int base_t = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base_t < n; base_t += gridDim.x * blockDim.x) {
+    const int t = base_t + lane;
+    bool split = false;
+    int si = 0;
+    double X = 0, Y = 0;
+    if (t < n) {
+      si = L.src[t];
+      X = L.x[t];
+      Y = L.y[t];
+      const DevSrc& s = src[si];
+      const DevDyn& d = dyn[si];
+      double* res = L.res + (long long)t * q.NVp;
+      switch (s.kind) {
+        case APB_SERSIC: split = refine_entry<APB_SERSIC, GRAD>(s, d, mode, depth, X, Y, res, q.NVp); break;
+        case APB_EXPONENTIAL: split = refine_entry<APB_EXPONENTIAL, GRAD>(s, d, mode, depth, X, Y, res, q.NVp); break;
+        case APB_GAUSSIAN: split = refine_entry<APB_GAUSSIAN, GRAD>(s, d, mode, depth, X, Y, res, q.NVp); break;
+        case APB_MOFFAT: split = refine_entry<APB_MOFFAT, GRAD>(s, d, mode, depth, X, Y, res, q.NVp); break;
+        case APB_SPLINE: split = refine_entry<APB_SPLINE, GRAD>(s, d, mode, depth, X, Y, res, q.NVp); break;
+        default: break;
+      }
+    }
+    // re-queue only the pixels that failed the test: gridding^2 children each
+    const int nchild = split ? src[si].gridding * src[si].gridding : 0;
+    int pre = nchild;  // inclusive warp scan of child counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    if (total == 0) continue;
+    int wbase = 0;
+    if (lane == 31) wbase = atomicAdd(&q.count[depth + 1], total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    if (split) {
+      const DevSrc& s = src[si];
+      const int first = wbase + pre - nchild;
+      if (first + nchild <= q.cap) {
+        L.child[t] = first;
+        const Level& C = q.lv[depth + 1];
+        const int G = s.gridding;
+        double scale = 1.0;
+        for (int k = 1; k < depth; ++k) scale /= (double)G;
+        for (int k = 0; k < nchild; ++k) {
+          // displacement_grid: linspace(-(G-1)/(2G), (G-1)/(2G), G)  (utils/operations.py:94-102)
+          const double dx = (-(G - 1) / (2.0 * G) + (double)(k % G) / G) * scale;
+          const double dy = (-(G - 1) / (2.0 * G) + (double)(k / G) / G) * scale;
+          const int c = first + k;
+          C.src[c] = si;
+          C.x[c] = X + (s.S[0] * dx + s.S[1] * dy);
+          C.y[c] = Y + (s.S[2] * dx + s.S[3] * dy);
+          C.parent[c] = t;
+          C.child[c] = -1;
+        }
+      } else {
+        *q.overflow = 1;
+        L.child[t] = -1;
+        double* res = L.res + (long long)t * q.NVp;
+        for (int p = 0; p < q.NVp; ++p) res[p] = 0.0;
+      }
+    }
+  }
+}
+
+// children -> parent sums, in child order (operations.py:245), deepest level first
+__global__ void k_reduce_level(const DevSrc* __restrict__ src, int depth, Queues q) {
+  const int n = min(q.count[depth], q.cap);
+  const Level& L = q.lv[depth];
+  const Level& C = q.lv[depth + 1];
+  const long long total = (long long)n * q.NVp;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(w / q.NVp), p = (int)(w % q.NVp);
+    const int first = L.child[t];
+    if (first < 0) continue;
+    const int G = src[L.src[t]].gridding;
+    double acc = 0.0;
+    for (int k = 0; k < G * G; ++k) acc += C.res[(long long)(first + k) * q.NVp + p];
+    L.res[w] = acc;
+  }
+}
+
+// depth-1 results -> stamp planes
+__global__ void k_scatter(const DevSrc* __restrict__ src, Queues q, double* __restrict__ stamp, int grad) {
+  const int n = min(q.count[1], q.cap);
+  const Level& L = q.lv[1];
+  const long long total = (long long)n * q.NVp;
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(w / q.NVp), p = (int)(w % q.NVp);
+    const DevSrc& s = src[L.src[t]];
+    if (p > (grad ? s.n_act : 0)) continue;
+    stamp[s.stamp_off + (long long)p * s.plane_stride + L.parent[t]] = L.res[w];
+  }
+}
+
+// ----------------------------------------------------------------------------
+// PSF models: divide by the sum over the evaluation region (psf_model_object.py:255-256),
+// quotient rule for the derivative planes.  One CTA per source.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_normalize(const DevSrc* __restrict__ src, const int* __restrict__ list,
+                                                   int mode, double* __restrict__ stamp, int grad) {
+  __shared__ double sh[8];
+  __shared__ double tot_s, dtot_s;
+  const DevSrc& s = src[list[blockIdx.x]];
+  const Geo& g = s.geo[mode];
+  const int n = g.ew * g.eh;
+  const long long off0 = (long long)(g.ey0 - g.my0) * g.mw + (g.ex0 - g.mx0);
+  double* p0 = stamp + s.stamp_off + off0;
+  double v = 0.0;
+  for (int q = threadIdx.x; q < n; q += 256) v += p0[(long long)(q / g.ew) * g.mw + (q % g.ew)];
+  double t = block_sum<256>(v, sh);
+  if (threadIdx.x == 0) tot_s = t;
+  __syncthreads();
+  const double tot = tot_s;
+  const int np = grad ? s.n_act : 0;
+  for (int p = 1; p <= np; ++p) {
+    double* pp = p0 + (long long)p * s.plane_stride;
+    v = 0.0;
+    for (int q = threadIdx.x; q < n; q += 256) v += pp[(long long)(q / g.ew) * g.mw + (q % g.ew)];
+    t = block_sum<256>(v, sh);
+    if (threadIdx.x == 0) dtot_s = t;
+    __syncthreads();
+    const double dtot = dtot_s;
+    for (int q = threadIdx.x; q < n; q += 256) {
+      const long long o = (long long)(q / g.ew) * g.mw + (q % g.ew);
+      pp[o] = pp[o] / tot - p0[o] * (dtot / (tot * tot));
+    }
+    __syncthreads();
+  }
+  for (int q = threadIdx.x; q < n; q += 256) {
+    const long long o = (long long)(q / g.ew) * g.mw + (q % g.ew);
+    p0[o] = p0[o] / tot;
+  }
+}

@@ -1,0 +1,158 @@
+/*
+ * astrophot_b200 — C ABI of the B200-native forward-model-and-fit hot path.
+ *
+ * The reference (Autostronomy/AstroPhot) has no FFI seam: its hot path is the
+ * Python method surface `model.sample()` / `model.jacobian()` / `fit.LM.step()`.
+ * This header is the seam a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md).  Every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - plain C structs, pointers and sizes; no torch types.
+ *  - every `double*` / `uint8_t*` that is documented "device" is a CUDA device
+ *    pointer owned by the caller (torch allocates it); the library never frees
+ *    caller memory.  Internal workspace is owned by the plan.
+ *  - every function returns 0 on success, <0 on error; apb_last_error() gives
+ *    the message of the last failure on the calling thread.
+ *  - `stream` is a CUstream / cudaStream_t passed as void* (NULL = default).
+ *    Calls are asynchronous with respect to the host unless stated.
+ *  - a plan is thread-compatible (one thread at a time), like the reference's
+ *    model objects (core_model.py:484-502 mutates model.parameters).
+ *  - image data are row-major [y][x] (astrophot: data[j, i]); pixel (i, j) has
+ *    plane coordinates  S . ((i, j) - rij) + rxy   (image/wcs.py:561-584).
+ */
+#ifndef ASTROPHOT_B200_H
+#define ASTROPHOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APB_MAX_ELEM 24 /* elements (scalar parameters) per source            */
+#define APB_MAX_PROF 20 /* spline nodes                                       */
+#define APB_MAX_DEPTH 4 /* integrate_max_depth                                */
+#define APB_MAX_QUAD 9  /* Gauss-Legendre order per axis                      */
+
+/* source kinds; element order = column order of the reference's Jacobian
+ *  */
+enum {
+  APB_SERSIC = 0,      /* cx cy q PA n Re Ie      models/sersic_model.py:41       */
+  APB_EXPONENTIAL = 1, /* cx cy q PA Re Ie        models/exponential_model.py:40  */
+  APB_GAUSSIAN = 2,    /* cx cy q PA sigma flux   models/gaussian_model.py:37     */
+  APB_MOFFAT = 3,      /* cx cy q PA n Rd I0      models/moffat_model.py:23       */
+  APB_SPLINE = 4,      /* cx cy q PA v[0..K-1]    models/spline_model.py:27       */
+  APB_POINT = 5,       /* cx cy flux              models/point_source.py:17       */
+  APB_FLAT_SKY = 6     /* cx cy F                 models/flatsky_model.py:13      */
+};
+enum { APB_F_RADIAL = 1, APB_F_NORMALIZE = 2 }; /* psf_model_object.py:36-57,255 */
+enum { APB_TR_NONE = 0, APB_TR_LOWER, APB_TR_UPPER, APB_TR_BOTH, APB_TR_CYCLIC }; /* utils/conversions/optimization.py:6-54 */
+enum { APB_SAMPLE_MIDPOINT = 0, APB_SAMPLE_SIMPSONS, APB_SAMPLE_QUAD, APB_SAMPLE_TRAPEZOID }; /* _model_methods.py:82-148 */
+enum { APB_INTEGRATE_NONE = 0, APB_INTEGRATE_THRESHOLD };                                  /* _model_methods.py:155-184 */
+enum { APB_REF_MEAN = 0, APB_REF_SERSIC_FLUX }; /* _model_methods.py:151-152, sersic_model.py:87-89 */
+enum { APB_SHIFT_NONE = 0, APB_SHIFT_BILINEAR = 1 }; /* _model_methods.py:187-230 */
+
+typedef struct apb_plan apb_plan_t;
+
+/* one free parameter of the flat vector x (param/parameter.py:330-420) */
+typedef struct {
+  int32_t transform; /* APB_TR_*  */
+  int32_t _pad;
+  double lo, hi;     /* limits (ignored where absent) */
+} apb_param_t;
+
+/* one target image region: target[fit_window] (fit/lm.py:191-222) */
+typedef struct {
+  int32_t H, W;
+  double S[4];           /* pixelscale, row-major 2x2                       */
+  double rij[2], rxy[2]; /* reference pixel / plane position                */
+  const double *data;    /* device, H*W; may be NULL when only sampling     */
+  const double *weight;  /* device, H*W; NULL = ones (target_image.py:182)  */
+  const uint8_t *mask;   /* device, H*W; 1 = ignore pixel; NULL = none      */
+} apb_image_t;
+
+/* a PSF stamp (image/psf_image.py:17-93): odd h, w; un-normalised is fine */
+typedef struct {
+  int32_t h, w;
+  const double *data; /* device, h*w */
+} apb_psf_t;
+
+/* one component model, lowered (models/model_object.py:64-95 for the knobs) */
+typedef struct {
+  int32_t kind, flags, image;
+  int32_t out[4]; /* x0 y0 w h : where the source adds flux (image pixels)            */
+  int32_t fwd[4]; /* working window when sampled in the forward model
+                     (group_model_object.py:211-227 hands sub-models the group window) */
+  int32_t jac[4]; /* working window when differentiated (_model_methods.py:294-299)   */
+  int32_t n_elem;
+  int32_t slot[APB_MAX_ELEM]; /* index into x, or -1 = locked                         */
+  double cval[APB_MAX_ELEM];  /* natural value of locked elements                     */
+  int32_t n_prof;
+  double prof[APB_MAX_PROF];  /* spline node radii                                    */
+  int32_t sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth;
+  int32_t ref_mode, psf, psf_shift, _pad;
+  double tolerance, softening;
+} apb_source_t;
+
+typedef struct {
+  int64_t queue_capacity; /* entries per refinement level; 0 = automatic  */
+  int32_t flags;          /* reserved                                      */
+  int32_t _pad;
+} apb_opts_t;
+
+/* counters of the last call, for benchmarks (SURVEY.md §8d "SPE") */
+typedef struct {
+  int64_t first_pass_evals;           /* profile evaluations of the first pass       */
+  int64_t queued[APB_MAX_DEPTH + 1];  /* entries processed per refinement depth 1..  */
+  int64_t launches;                   /* kernels launched by the last call           */
+  int64_t overflow;                   /* !=0: a queue overflowed, results invalid    */
+} apb_stats_t;
+
+/* Build the device tables and workspace for a lowered model tree.
+ * Replaces the per-call Python walk of Group_Model.sample / .jacobian
+ * (group_model_object.py:183-283).  Synchronous. */
+int apb_plan_create(const apb_source_t *src, int n_src, const apb_image_t *img, int n_img,
+                    const apb_psf_t *psf, int n_psf, const apb_param_t *par, int n_par,
+                    const apb_opts_t *opts, apb_plan_t **out);
+int apb_plan_destroy(apb_plan_t *plan);
+
+/* seam 1 — model(parameters=x, as_representation=as_rep) -> model image(s)
+ * (core_model.py:484-502, model_object.py:258-375, group_model_object.py:183-231).
+ * x: device, n_par doubles.  model_out[i]: device, H_i*W_i doubles, OVERWRITTEN. */
+int apb_sample(apb_plan_t *plan, const double *x, int as_rep, double *const *model_out, void *stream);
+
+/* seam 2 — model.jacobian(parameters=x, as_representation=as_rep)
+ * (_model_methods.py:260-347, group_model_object.py:233-283).
+ * jac_out[i]: device, H_i*W_i*n_par doubles (pixel-major, parameter fastest), OVERWRITTEN.
+ * For small problems and tests only; LM never materialises this. */
+int apb_jacobian(apb_plan_t *plan, const double *x, int as_rep, double *const *jac_out, void *stream);
+
+/* seam 3 — the inside of LM.step (fit/lm.py:256-260):  Y0 = forward(x); J = jacobian(x);
+ * JtWJ = J^T W J (n_par x n_par, row-major), JtWr = J^T W (Y - Y0), chi2 = sum W (Y - Y0)^2,
+ * all over unmasked pixels.  The per-source stamp Jacobian stays cached in the plan for
+ * apb_geodesic.  All outputs device pointers. */
+int apb_normal_eq(apb_plan_t *plan, const double *x_rep, int as_rep, double *JtWJ, double *JtWr,
+                  double *chi2, void *stream);
+
+/* fit/lm.py:277-281,401-406:  rpp = J^T [ (2/d) ( (W (Y(x + d h) - Y) - r)/d - W (J h) ) ]
+ * with J, r from the last apb_normal_eq.  xdh = x + d*h (device, n_par), h device. */
+int apb_geodesic(apb_plan_t *plan, const double *xdh_rep, const double *h, double d, double *rpp,
+                 void *stream);
+
+/* fit/lm.py:289-293,373-378: out[0] = sum W (Y - model(x))^2 over unmasked pixels,
+ * out[1] = 1.0 if every model pixel is finite else 0.0.  (Caller divides by ndf.) */
+int apb_chi2(apb_plan_t *plan, const double *x_rep, double *out2, void *stream);
+
+/* fit/lm.py:359-371:  solve (H o (I + (1-I)/(1+L)) + L I (1 + diag H)) h = g.
+ * H: device P*P (not modified), g, h: device P.  info: device int, 0 ok. */
+int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, int *info, void *stream);
+
+int apb_plan_stats(apb_plan_t *plan, apb_stats_t *out); /* synchronises the plan's last stream */
+const char *apb_last_error(void);
+int apb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASTROPHOT_B200_H */

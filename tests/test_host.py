@@ -1,0 +1,115 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header
+declares (no compute without a GPU), host classes behave like the reference's
+(window arithmetic, parameter representation round trips), and the product
+path refuses to run without the native library / a CUDA device."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import astrophot_b200 as ap
+from astrophot_b200 import cabi
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "astrophot_b200.h")).read()
+    declared = set(re.findall(r"\b(apb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"apb_plan"}
+    assert declared == set(cabi.EXPORTS)
+    L = cabi.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.apb_version() >= 100
+
+
+def test_struct_sizes_match_header():
+    import ctypes as C
+    assert C.sizeof(cabi.apb_param_t) == 24
+    assert C.sizeof(cabi.apb_image_t) == 8 + 8 * 8 + 3 * 8
+    assert C.sizeof(cabi.apb_psf_t) == 16
+    assert C.sizeof(cabi.apb_source_t) == 4 * 40 + 8 * 24 + 8 + 8 * 20 + 4 * 10 + 16
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    tar = ap.image.Target_Image(data=np.zeros((16, 16)), pixelscale=1.0)
+    m = ap.models.AstroPhot_Model(name="nofb", model_type="sersic galaxy model", target=tar,
+                                  parameters={"center": [8, 8], "q": 0.5, "PA": 0.1, "n": 1, "Re": 2, "Ie": 0})
+    with pytest.raises(ap.errors.NativeLibraryError):
+        m()
+
+
+def test_missing_library_is_loud(tmp_path):
+    with pytest.raises(ap.errors.NativeLibraryError):
+        cabi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_window_arithmetic():
+    W = ap.image.Window
+    a = W(origin=(0, 0), pixel_shape=(100, 80), pixelscale=0.5)
+    b = W(origin=(10, 5), pixel_shape=(100, 100), pixelscale=0.5)
+    u, i = a | b, a & b
+    np.testing.assert_allclose(u.origin.numpy(), [0, 0])
+    np.testing.assert_allclose(u.pixel_shape.numpy(), [120, 110])
+    np.testing.assert_allclose(i.origin.numpy(), [10, 5])
+    np.testing.assert_allclose(i.pixel_shape.numpy(), [80, 70])
+    rows, cols = a.get_self_indices(i)
+    assert (rows.start, rows.stop, cols.start, cols.stop) == (10, 80, 20, 100)
+    np.testing.assert_allclose(a.pixel_to_plane(torch.tensor([0.0, 0.0])).numpy(), [0.25, 0.25])
+    np.testing.assert_allclose(a.plane_to_pixel(a.pixel_to_plane(torch.tensor([3.0, 7.0]))).numpy(), [3.0, 7.0])
+    c = a.copy().pad_pixel((3,))
+    np.testing.assert_allclose(c.pixel_shape.numpy(), [106, 86])
+    np.testing.assert_allclose(c.origin.numpy(), [-1.5, -1.5])
+    assert a.copy() == a and (a != b)
+
+
+def test_parameter_representation_round_trip():
+    P = ap.param.Parameter_Node
+    for kw, val in [({"limits": (0, 1)}, 0.6), ({"limits": (0, None)}, 10.0), ({"limits": (None, 4.0)}, -3.0),
+                    ({"limits": (0, np.pi), "cyclic": True}, 1.0), ({}, 5.0)]:
+        p = P("p", value=val, **kw)
+        r = p.vector_representation()
+        np.testing.assert_allclose(p.vector_transform_rep_to_val(r).numpy(), [val], rtol=1e-13)
+    with pytest.raises(ap.errors.InvalidParameter):
+        P("q", value=2.0, limits=(0, 1))
+    c = P("c", value=4.0, limits=(0, np.pi), cyclic=True)
+    np.testing.assert_allclose(c.value.numpy(), 4.0 - np.pi)
+
+
+def test_linked_parameters_share_a_slot():
+    import scenes
+    from astrophot_b200.lowering import lower
+
+    model, _ = scenes.build(ap, "joint")
+    assert len(model.parameters.vector_values()) == 9
+    scene, info = lower(model)
+    assert scene.n_par == 9 and len(scene.images) == 3
+    for e in range(6):   # cx cy q PA n Re shared by the three bands
+        assert len({s.slot[e] for s in scene.sources}) == 1
+    assert len({s.slot[6] for s in scene.sources}) == 3
+
+
+def test_group_overrides_psf_mode_like_reference():
+    import scenes
+
+    model, _ = scenes.build(ap, "group")
+    assert all(m.psf_mode in ("full", "none") for m in model.models.values())
+    assert model.models["gal0"].psf_mode == "full" and model.models["sky"].psf_mode == "none"
+    tar = model.target
+    g2 = ap.models.AstroPhot_Model(name="g2", model_type="group model", target=tar,
+                                   models=[ap.models.AstroPhot_Model(name="x1", model_type="sersic galaxy model",
+                                                                     target=tar, psf_mode="full",
+                                                                     parameters={"center": [8, 8], "q": 0.5, "PA": 0.1,
+                                                                                 "n": 1, "Re": 2, "Ie": 0})])
+    assert g2.models["x1"].psf_mode == "none"   # group default wins (group_model_object.py:85-89)
+
+
+def test_fit_mask_of_group():
+    import scenes
+
+    model, _ = scenes.build(ap, "group_nosky")
+    fm = model.fit_mask()
+    assert fm.shape == (58, 70) and 0 < int(fm.sum()) < fm.numel()
