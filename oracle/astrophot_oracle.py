@@ -28,6 +28,13 @@ from astrophot_b200 import scene as sc
 LN10 = math.log(10.0)
 
 
+def _host(a, dtype=np.float64):
+    """numpy view of an array or (possibly CUDA) torch tensor."""
+    if hasattr(a, "detach"):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a, dtype=dtype)
+
+
 # ---------------------------------------------------------------------------
 # parameters: representation <-> value  (utils/conversions/optimization.py:6-54)
 # ---------------------------------------------------------------------------
@@ -427,7 +434,7 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None):
     has_psf = src.psf >= 0
     bx = by = 0
     if has_psf:
-        psf = np.asarray(scene.psfs[src.psf].data, dtype=np.float64)
+        psf = _host(scene.psfs[src.psf].data)
         bx, by = _psf_border(psf)
     # evaluation region: output window + psf border; working region likewise
     ex0, ey0, ew, eh = ox - bx, oy - by, ow + 2 * bx, oh + 2 * by
@@ -585,7 +592,7 @@ def _sample_point(scene, src, img, el, want_grad):
     pixel of the centre and clipped to the output window."""
     S = np.asarray(img.S, dtype=np.float64)
     Sinv = np.linalg.inv(S)
-    psf = np.asarray(scene.psfs[src.psf].data, dtype=np.float64)
+    psf = _host(scene.psfs[src.psf].data)
     ph, pw = psf.shape
     ox, oy, ow, oh = src.out
     pc = Sinv @ (np.array([el[0], el[1]]) - img.rxy) + img.rij
@@ -656,10 +663,10 @@ def jacobian(scene, x, as_rep=True, conv="direct", stats=None):
 
 def flat_targets(scene):
     """Y, W, keep-mask as flat vectors over all images (lm.py:191-222)."""
-    Y = np.concatenate([np.asarray(im.data, dtype=np.float64).reshape(-1) for im in scene.images])
-    W = np.concatenate([(np.ones(im.H * im.W) if im.weight is None else np.asarray(im.weight, dtype=np.float64).reshape(-1))
+    Y = np.concatenate([_host(im.data).reshape(-1) for im in scene.images])
+    W = np.concatenate([(np.ones(im.H * im.W) if im.weight is None else _host(im.weight).reshape(-1))
                         for im in scene.images])
-    keep = np.concatenate([(np.ones(im.H * im.W, dtype=bool) if im.mask is None else ~np.asarray(im.mask).astype(bool).reshape(-1))
+    keep = np.concatenate([(np.ones(im.H * im.W, dtype=bool) if im.mask is None else ~_host(im.mask, bool).reshape(-1))
                            for im in scene.images])
     return Y, W, keep
 
