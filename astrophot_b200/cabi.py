@@ -54,7 +54,11 @@ class apb_stats_t(C.Structure):
                 ("launches", C.c_int64), ("overflow", C.c_int64)]
 
 
-EXPORTS = ["apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+class apb_kernel_time_t(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
+
+
+EXPORTS = ["apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -87,12 +91,16 @@ def load_library(path=None):
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
     L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
+    L.apb_profile.argtypes = [vp, C.c_int]
+    L.apb_profile_read.argtypes = [vp, C.POINTER(apb_kernel_time_t), C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.apb_bench_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.apb_last_error.restype = C.c_char_p
     L.apb_version.restype = C.c_int
     for name in EXPORTS:
         if name not in ("apb_last_error",):
             getattr(L, name).restype = C.c_int if name != "apb_last_error" else C.c_char_p
     L.apb_last_error.restype = C.c_char_p
+    L.apb_launch_count.restype = C.c_longlong
     _lib = L
     return L
 
@@ -135,17 +143,21 @@ class Plan:
         n_img, n_src, n_psf = len(scene.images), len(scene.sources), len(scene.psfs)
         imgs = (apb_image_t * max(n_img, 1))()
         self.shapes = []
+        self.image_buffers = []   # per image: device tensors the plan reads (refill in place to stream new data)
         for i, im in enumerate(scene.images):
             imgs[i].H, imgs[i].W = im.H, im.W
             imgs[i].S[:] = [float(v) for v in np.asarray(im.S).reshape(4)]
             imgs[i].rij[:] = [float(v) for v in im.rij]
             imgs[i].rxy[:] = [float(v) for v in im.rxy]
+            bufs = {}
             for name in ("data", "weight"):
                 arr = getattr(im, name)
                 if arr is not None:
                     t = _dev_f64(arr)
                     self._keep.append(t)
+                    bufs[name] = t
                     setattr(imgs[i], name, t.data_ptr())
+            self.image_buffers.append(bufs)
             if im.mask is not None:
                 m = torch.as_tensor(im.mask).to(device="cuda", dtype=torch.uint8).contiguous()
                 self._keep.append(m)
@@ -248,6 +260,16 @@ class Plan:
         _check(self._L.apb_chi2(self._h, x.data_ptr(), out.data_ptr(), _stream()), "apb_chi2")
         return out
 
+    def profile(self, enable=True):
+        _check(self._L.apb_profile(self._h, int(enable)), "apb_profile")
+
+    def profile_read(self, reset=True):
+        """{kernel name: (launches, total ms)} from CUDA events on the launching stream."""
+        arr = (apb_kernel_time_t * 32)()
+        n = C.c_int(0)
+        _check(self._L.apb_profile_read(self._h, arr, 32, C.byref(n), int(reset)), "apb_profile_read")
+        return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(n.value)}
+
     def stats(self):
         st = apb_stats_t()
         _check(self._L.apb_plan_stats(self._h, C.byref(st)), "apb_plan_stats")
@@ -266,3 +288,15 @@ def lm_solve(H, g, L, out=None, info=None):
     _check(lib().apb_lm_solve(H.data_ptr(), g.data_ptr(), float(L), int(P), out.data_ptr(), info.data_ptr(),
                               _stream()), "apb_lm_solve")
     return out
+
+
+def launch_count():
+    return int(lib().apb_launch_count())
+
+
+def bench_peaks():
+    """(fp64 DFMA TFLOP/s, fp64 copy GB/s) measured now on the current device."""
+    _require_cuda()
+    a, b = C.c_double(0), C.c_double(0)
+    _check(lib().apb_bench_peaks(C.byref(a), C.byref(b)), "apb_bench_peaks")
+    return a.value, b.value

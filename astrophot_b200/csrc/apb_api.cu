@@ -37,6 +37,16 @@ static int upload(const std::vector<T>& v, T** out) {
   return 0;
 }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
+enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_COUNT };
+static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
+                                             "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
+                                             "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
+                                             "k_geo_v"};
+static long long g_launches = 0;
+struct ProfRec { int id; cudaEvent_t a, b; };
+
 struct ModeTables {
   int4* tiles = nullptr;       // first-pass tiles {src, tx, ty, 0}
   int n_tiles = 0;
@@ -89,10 +99,30 @@ struct apb_plan {
   apb_stats_t stats{};
   long long launches = 0;
   cudaStream_t last_stream = nullptr;
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[K_COUNT] = {0};
+  long long prof_n[K_COUNT] = {0};
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void pbegin(int id, cudaStream_t st) {
+    if (!profiling) return;
+    ProfRec r{id, get_event(), get_event()};
+    cudaEventRecord(r.a, st);
+    prof.push_back(r);
+  }
+  void pend(cudaStream_t st) {
+    if (!profiling) return;
+    cudaEventRecord(prof.back().b, st);
+  }
   int first_evals[2] = {0, 0};
 };
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
 
 extern "C" const char* apb_last_error(void) { return g_err.c_str(); }
 extern "C" int apb_version(void) { return 100; }
@@ -492,56 +522,69 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
 // one sampling pass: prep -> psf stamps -> first pass -> reference -> select -> refine -> scatter ->
 // normalise -> point sources -> convolution.  Leaves the out-planes of every source ready.
 // ----------------------------------------------------------------------------
-#define LAUNCH_CHECK() do { p->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { g_err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " line " + std::to_string(__LINE__); return -3; } } while (0)
+#define PB(id) p->pbegin(id, st)
+#define LAUNCH_CHECK() do { p->pend(st); p->launches++; g_launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { g_err = std::string("kernel launch: ") + cudaGetErrorString(e_) + " line " + std::to_string(__LINE__); return -3; } } while (0)
 
 static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int grad, cudaStream_t st) {
   const int n_src = p->n_src;
   if (n_src == 0) return 0;
   ModeTables& T = p->mt[mode];
+  PB(K_PREP);
   k_prep<<<ceil_div(n_src, 128), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad);
   LAUNCH_CHECK();
   if (p->n_psf_list) {
+    PB(K_PSF);
     k_psf_stamp<<<p->n_psf_list, 256, 0, st>>>(p->d_src, p->d_dyn, p->psf_list, p->d_psf, p->d_psfst, grad);
     LAUNCH_CHECK();
   }
   if (T.n_tiles) {
+    PB(K_FIRST);
     if (grad) k_first<true><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
     else k_first<false><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
     LAUNCH_CHECK();
     if (p->any_threshold) {
       if (T.n_mean) {
+        PB(K_MEAN);
         k_mean_partial<<<T.n_chunks, 256, 0, st>>>(p->d_src, p->d_dyn, T.chunks, mode, p->d_stamp, p->d_meanpart);
         LAUNCH_CHECK();
+        PB(K_MEAN);
         k_mean_final<<<ceil_div(T.n_mean, 128), 128, 0, st>>>(p->d_src, p->d_dyn, T.mean_list, T.n_mean, mode, p->d_meanpart);
         LAUNCH_CHECK();
       }
       Queues q = p->q;
       q.NVp = grad ? p->NVp_grad : 1;
+      PB(K_SELECT);
       k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
       LAUNCH_CHECK();
       const int grid = 148 * 8;
       for (int d = 1; d <= p->max_depth; ++d) {
+        PB(K_REFINE);
         if (grad) k_refine<true><<<grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, d, q);
         else k_refine<false><<<grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, d, q);
         LAUNCH_CHECK();
       }
       for (int d = p->max_depth - 1; d >= 1; --d) {
+        PB(K_REDUCE);
         k_reduce_level<<<grid, 128, 0, st>>>(p->d_src, d, q);
         LAUNCH_CHECK();
       }
+      PB(K_SCATTER);
       k_scatter<<<grid, 128, 0, st>>>(p->d_src, q, p->d_stamp, grad);
       LAUNCH_CHECK();
     }
     if (p->n_norm) {
+      PB(K_NORM);
       k_normalize<<<p->n_norm, 256, 0, st>>>(p->d_src, p->norm_list, mode, p->d_stamp, grad);
       LAUNCH_CHECK();
     }
   }
   if (p->n_point) {
+    PB(K_POINT);
     k_point<<<p->n_point, 256, 0, st>>>(p->d_src, p->d_dyn, p->point_list, p->d_psfst, p->d_out, grad);
     LAUNCH_CHECK();
   }
   if (T.n_conv_tiles[grad]) {
+    PB(K_CONV);
     k_conv<<<T.n_conv_tiles[grad], 256, T.conv_smem, st>>>(p->d_src, T.conv_jobs[grad], T.conv_tiles[grad], mode,
                                                            p->d_stamp, p->d_psfst, p->d_out);
     LAUNCH_CHECK();
@@ -551,11 +594,13 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
 
 static int assemble(apb_plan* p, int mode, double** model_out_dev, double** resid_out_dev, double* chi_out2,
                     int write_flag, cudaStream_t st) {
+  PB(K_ASSEMBLE);
   k_assemble<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, mode,
                                              p->d_stamp, p->d_out, model_out_dev, resid_out_dev,
                                              chi_out2 ? p->d_chipart : nullptr);
   LAUNCH_CHECK();
   if (chi_out2) {
+    PB(K_CHI);
     k_chi_final<<<1, 256, 0, st>>>(p->d_chipart, p->n_img_tiles, chi_out2, write_flag);
     LAUNCH_CHECK();
   }
@@ -592,6 +637,7 @@ extern "C" int apb_jacobian(apb_plan_t* p, const double* x, int as_rep, double* 
   CU(cudaMemcpyAsync(p->d_userptr, jac_out, sizeof(double*) * p->n_img, cudaMemcpyHostToDevice, st));
   int rc = sample_pass(p, x, as_rep, 1, 1, st);
   if (rc) return rc;
+  PB(K_JAC);
   k_jac_dense<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, p->d_stamp,
                                               p->d_out, p->d_skyJ, p->d_userptr, p->n_par);
   LAUNCH_CHECK();
@@ -631,9 +677,11 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
   CU(cudaMemsetAsync(JtWJ, 0, sizeof(double) * (size_t)P * P, st));
   CU(cudaMemsetAsync(JtWr, 0, sizeof(double) * (size_t)P, st));
   if (p->n_items) {
+    PB(K_BLOCKS);
     k_blocks<<<p->n_items, 256, 0, st>>>(p->d_src, p->d_img, p->d_items, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid,
                                          -1.0, 0, p->d_part);
     LAUNCH_CHECK();
+    PB(K_BLOCKFIN);
     k_block_final<<<ceil_div(p->n_blocks, 4), 128, 0, st>>>(p->d_src, p->d_blocks, p->n_blocks, p->d_act_slot,
                                                             p->d_act_off, p->d_part, JtWJ, JtWr, P, -1.0, 0);
     LAUNCH_CHECK();
@@ -650,14 +698,17 @@ extern "C" int apb_geodesic(apb_plan_t* p, const double* xdh, const double* h, d
   // rh = W (Y(x + d h) - Y): forward pass only touches plane 0, the cached derivative planes stay valid
   if ((rc = sample_pass(p, xdh, 1, 0, 0, st))) return rc;
   if ((rc = assemble(p, 0, nullptr, p->d_resid2, nullptr, 0, st))) return rc;
+  PB(K_GEOV);
   k_geo_v<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, p->d_stamp, p->d_out,
                                           p->d_skyJ, h, d, p->d_resid, p->d_resid2);
   LAUNCH_CHECK();
   CU(cudaMemsetAsync(rpp, 0, sizeof(double) * (size_t)P, st));
   if (p->n_vitems) {
+    PB(K_BLOCKS);
     k_blocks<<<p->n_vitems, 256, 0, st>>>(p->d_src, p->d_img, p->d_vitems, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid2,
                                           1.0, 1, p->d_part);
     LAUNCH_CHECK();
+    PB(K_BLOCKFIN);
     k_block_final<<<ceil_div(p->n_vblocks, 4), 128, 0, st>>>(p->d_src, p->d_vblocks, p->n_vblocks, p->d_act_slot,
                                                              p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1);
     LAUNCH_CHECK();
@@ -689,5 +740,92 @@ extern "C" int apb_plan_stats(apb_plan_t* p, apb_stats_t* out) {
   for (int d = 1; d <= APB_MAX_DEPTH; ++d) out->queued[d] = cnt[d];
   out->launches = p->stats.launches;
   out->overflow = ovf;
+  return 0;
+}
+
+// ---- measurement helpers ---------------------------------------------------------------------
+extern "C" long long apb_launch_count(void) { return g_launches; }
+
+extern "C" int apb_profile(apb_plan_t* p, int enable) {
+  if (!p) APB_FAIL("apb_profile: NULL plan");
+  p->profiling = enable != 0;
+  return 0;
+}
+
+extern "C" int apb_profile_read(apb_plan_t* p, apb_kernel_time_t* out, int max_out, int* n_out, int reset) {
+  if (!p || !out || !n_out) APB_FAIL("apb_profile_read: NULL");
+  CU(cudaStreamSynchronize(p->last_stream));
+  for (auto& r : p->prof) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { p->prof_ms[r.id] += ms; p->prof_n[r.id]++; }
+    p->ev_pool.push_back(r.a);
+    p->ev_pool.push_back(r.b);
+  }
+  p->prof.clear();
+  int n = 0;
+  for (int k = 0; k < K_COUNT && n < max_out; ++k) {
+    if (!p->prof_n[k]) continue;
+    memset(&out[n], 0, sizeof(out[n]));
+    strncpy(out[n].name, kKNames[k], sizeof(out[n].name) - 1);
+    out[n].launches = p->prof_n[k];
+    out[n].total_ms = p->prof_ms[k];
+    ++n;
+  }
+  *n_out = n;
+  if (reset) for (int k = 0; k < K_COUNT; ++k) { p->prof_ms[k] = 0; p->prof_n[k] = 0; }
+  return 0;
+}
+
+// DFMA-stream and copy microbenchmarks: the FP64 ceiling is not in MEASURED_PEAKS.json
+__global__ void __launch_bounds__(256) k_bench_dfma(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void __launch_bounds__(256) k_bench_copy(const double2* __restrict__ a, double2* __restrict__ b, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+
+extern "C" int apb_bench_peaks(double* dfma_tflops, double* copy_gbs) {
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  const int blocks = 148 * 8, iters = 1 << 15;
+  double* buf = nullptr;
+  CU(cudaMalloc((void**)&buf, sizeof(double) * blocks * 256));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0));
+    k_bench_dfma<<<blocks, 256>>>(buf, iters);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  if (dfma_tflops) *dfma_tflops = 2.0 * 8.0 * iters * (double)blocks * 256 / (best * 1e-3) / 1e12;
+  CU(cudaFree(buf));
+  const size_t n = (size_t)1 << 26;   // 2 x 1 GiB
+  double2 *a = nullptr, *b = nullptr;
+  CU(cudaMalloc((void**)&a, n * sizeof(double2)));
+  CU(cudaMalloc((void**)&b, n * sizeof(double2)));
+  CU(cudaMemset(a, 0, n * sizeof(double2)));
+  best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0));
+    k_bench_copy<<<148 * 16, 256>>>(a, b, n);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  if (copy_gbs) *copy_gbs = 2.0 * n * sizeof(double2) / (best * 1e-3) / 1e9;
+  CU(cudaFree(a));
+  CU(cudaFree(b));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }

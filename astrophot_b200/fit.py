@@ -26,7 +26,7 @@ import torch
 
 from . import AP_config
 from .errors import OptimizeStop
-from .lowering import lower
+from .lowering import lower, shard_scene
 
 __all__ = ["BaseOptimizer", "LM"]
 
@@ -101,6 +101,8 @@ class LM(BaseOptimizer):
             for im in scene.images:
                 im.weight = W[at : at + im.H * im.W].reshape(im.H, im.W)
                 at += im.H * im.W
+        if self.distributed and kwargs.get("shard_images", True):
+            scene = shard_scene(scene, torch.distributed.get_rank(self.group), torch.distributed.get_world_size(self.group))
         self.scene, self.info = scene, info
         n_keep = 0
         for im in scene.images:

@@ -21,7 +21,7 @@ from .image import (Image_List, Jacobian_Image, Jacobian_Image_List, Model_Image
                     PSF_Image, Window, Window_List)
 from .param import Parameter_Node
 
-__all__ = ["lower", "wrap_model_images", "wrap_jacobian_images", "LoweringInfo"]
+__all__ = ["lower", "shard_scene", "wrap_model_images", "wrap_jacobian_images", "LoweringInfo"]
 
 
 class LoweringInfo:
@@ -294,3 +294,21 @@ def wrap_jacobian_images(model, info, outs):
                           target_identity=t.identity)
            for o, w, t in zip(outs, info.windows, info.targets)]
     return Jacobian_Image_List(ims) if info.is_list else ims[0]
+
+
+def shard_scene(scene, rank, world):
+    """Keep the images (bands / tiles) owned by ``rank`` (round robin) and the
+    sources on them; the parameter table stays global so that every rank's
+    J^T W J lands in the same (P, P) layout and a plain sum all-reduce merges
+    them."""
+    keep = [i for i in range(len(scene.images)) if i % world == rank]
+    remap = {old: new for new, old in enumerate(keep)}
+    srcs = []
+    psf_used = {}
+    for s in scene.sources:
+        if s.image in remap:
+            s2 = sc.SceneSource(**{**s.__dict__})
+            s2.image = remap[s.image]
+            srcs.append(s2)
+    return sc.Scene(images=[scene.images[i] for i in keep], sources=srcs, psfs=scene.psfs,
+                    transform=scene.transform, lo=scene.lo, hi=scene.hi, identities=scene.identities)

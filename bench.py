@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the AstroPhot forward-model-and-fit hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+Metric (BASELINE.json): LM iterations/s (model + PSF + J^T J), fp64.  A *step*
+is one Levenberg-Marquardt iteration (fit/lm.py:450-467): one fused
+sample+Jacobian+normal-equation build and k lambda-trials, each with a damped
+solve, a geodesic pass and a chi^2 pass.  The fit restarts from the perturbed
+start whenever it converges, so K steps are K real iterations drawn from the
+fit trajectory.
+
+Workload at N GPUs: an N-band joint fit (Target_Image_List; shared centre / q /
+PA / n / Re, per-band Ie), one band per GPU, every band being BASELINE config[1]
+— a PSF-convolved Sersic on 1024x1024 with a 51x51 Moffat PSF and threshold
+sub-pixel integration.  At N=1 that is exactly config[1].  `value` counts
+band-iterations per second (= LM iterations/s at N=1), weak scaling; the only
+collective is the all-reduce of J^T W J / J^T W r / chi^2 (P^2+P+2 doubles).
+
+`--impl reference` times the CPU oracle port of the reference algorithm
+(oracle/astrophot_oracle.py, numpy + scipy FFT convolution like the reference's
+default psf_convolve_mode) on the host cores, same config, one LM iteration
+per step.  /root/reference is not needed at run time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "lm_iters_per_sec"
+UNIT = "LM iterations/s (x bands)"
+SIZE = 1024
+PSF_W = 51
+
+
+# ---------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------
+def band_truth(b):
+    return {"center": [SIZE / 2 + 0.3, SIZE / 2 - 0.4], "q": 0.6, "PA": 1.0, "n": 2.5, "Re": 60.0, "Ie": 1.0 + 0.1 * b}
+
+
+def build_joint(ap, n_bands, datas, size=SIZE):
+    """n_bands PSF-convolved Sersic models sharing shape parameters
+    (docs/source/tutorials/JointModels.ipynb recipe).  datas[b] = dict(data, variance) or None."""
+    psf_np = ap.utils.moffat_psf(2.5, 3.0, PSF_W, 1.0)
+    tars, models = [], []
+    for b in range(n_bands):
+        d = datas[b] if datas is not None else None
+        kw = {} if d is None else {"variance": d["variance"]}
+        tars.append(ap.image.Target_Image(data=np.zeros((size, size)) if d is None else d["data"], pixelscale=1.0,
+                                          zeropoint=22.5, psf=ap.image.PSF_Image(data=psf_np, pixelscale=1.0), **kw))
+    for b in range(n_bands):
+        pars = band_truth(b)
+        pars["center"] = [size / 2 + 0.3, size / 2 - 0.4]
+        m = ap.models.AstroPhot_Model(name=f"band{b}", model_type="sersic galaxy model", target=tars[b],
+                                      psf_mode="full", parameters=pars)
+        if b > 0:
+            for p in ("center", "q", "PA", "n", "Re"):
+                m[p].value = models[0][p]
+        models.append(m)
+    if n_bands == 1:
+        return models[0]
+    return ap.models.AstroPhot_Model(name="joint", model_type="group model", models=models,
+                                     target=ap.image.Target_Image_List(tars), psf_mode="full")
+
+
+def make_data(truth, seed):
+    rng = np.random.default_rng(seed)
+    var = 0.1**2 + truth / 100.0
+    return {"data": truth + rng.normal(size=truth.shape) * np.sqrt(var), "variance": var}
+
+
+def start_state(x_rep, seed=2):
+    rng = np.random.default_rng(1000 + seed)
+    return np.asarray(x_rep, dtype=np.float64) + 0.05 * rng.normal(size=len(x_rep))
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm: CPU oracle port
+# ---------------------------------------------------------------------------
+def cpu_lm_iteration_seconds(scene, x0, n_iter=1):
+    import astrophot_oracle as orc
+
+    t0 = time.perf_counter()
+    res = orc.lm_fit(scene, x0, max_iter=n_iter, relative_tolerance=0.0, conv="fft")
+    dt = time.perf_counter() - t0
+    its = max(1, len(res["loss_history"]) - 1)
+    return dt / its, res
+
+
+def cpu_scene(n_bands=1, size=SIZE):
+    """Scene tables for the CPU arm (host numpy only, no GPU needed)."""
+    import astrophot_b200 as ap
+    import astrophot_oracle as orc
+    from astrophot_b200.lowering import lower
+
+    ap.AP_config.ap_device = "cpu"
+    model = build_joint(ap, n_bands, None, size)
+    scene, _ = lower(model)
+    xv = model.parameters.vector_values().numpy()
+    truth = orc.sample(scene, xv, as_rep=False, conv="fft")
+    datas = [make_data(t, 10 + b) for b, t in enumerate(truth)]
+    model = build_joint(ap, n_bands, datas, size)
+    scene, _ = lower(model, for_fit=True)
+    x0 = start_state(model.parameters.vector_representation().numpy())
+    return scene, x0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    scene, x0 = cpu_scene(1)
+    times = []
+    for k in range(args.warmup + args.steps):
+        dt, res = cpu_lm_iteration_seconds(scene, x0, 1)
+        if k >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = 1e3 / ms
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"c2: 1 PSF-convolved Sersic, {SIZE}x{SIZE}, {PSF_W}x{PSF_W} Moffat PSF, threshold integration, LM fp64",
+                   "note": "CPU oracle port of the reference algorithm (numpy + scipy FFT conv); one LM iteration from the perturbed start per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "1 full-size LM iteration (1 normal-equation build + lambda trials) per step"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import astrophot_b200 as ap
+    from astrophot_b200 import cabi
+
+    ap.AP_config.ap_device = f"cuda:{local}"
+    n_bands = world
+    dev = torch.device("cuda", local)
+
+    # truth + noisy data for the band(s); every rank builds all bands' descriptions, data only for its own
+    truth_model = build_joint(ap, 1, None)
+    datas = []
+    for b in range(n_bands):
+        if b % world == rank:
+            pars = band_truth(b)
+            truth_model["Ie"].value = pars["Ie"]
+            t = truth_model().data.cpu().numpy()
+            datas.append(make_data(t, 10 + b))
+        else:
+            datas.append(None)
+    model = build_joint(ap, n_bands, datas)
+    x_true = model.parameters.vector_representation().numpy()
+    x0 = start_state(x_true)
+    lm = ap.fit.LM(model, initial_state=x0, max_iter=10**6, relative_tolerance=0.0, distributed=(world > 1))
+    plan = lm.plan
+    n_pix_local = sum(h * w for h, w in plan.shapes)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
+
+    state = {"fresh": True, "iters_in_fit": 0, "restarts": 0}
+
+    def reset():
+        lm.current_state = torch.as_tensor(x0, dtype=torch.float64, device=dev)
+        lm.L = 1.0
+        lm.loss_history = [lm._chi2_record(lm.current_state)]
+        lm.L_history, lm.lambda_history = [lm.L], [x0.copy()]
+        state["iters_in_fit"] = 0
+
+    def one_iteration():
+        """One pass of the `for iteration in range(max_iter)` loop of LM.fit."""
+        from astrophot_b200.errors import OptimizeStop
+        try:
+            res = lm.step(chi2=lm.loss_history[-1])
+        except OptimizeStop:
+            state["restarts"] += 1
+            reset()
+            res = lm.step(chi2=lm.loss_history[-1])
+        lm.L = res[2]
+        lm.current_state = (lm.current_state + res[0]).detach()
+        lm.L_history.append(lm.L)
+        lm.loss_history.append(res[1])
+        lm.Ldn()
+        state["iters_in_fit"] += 1
+        if len(lm.loss_history) >= 3 and abs(lm.loss_history[-3] - lm.loss_history[-1]) / lm.loss_history[-1] < 1e-9:
+            state["restarts"] += 1
+            reset()     # converged: start the next fit (outside the next step's timing)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    reset()
+    for _ in range(args.warmup):
+        one_iteration()
+    barrier()
+
+    # ---- timed region (device-resident inputs): K iterations, L2 flushed between them
+    plan.profile(True)
+    plan.profile_read(reset=True)
+    launches0 = cabi.launch_count()
+    trials0, fwd0 = lm.n_trials, lm.n_forward
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()
+            barrier()
+            ev[k][0].record()
+            one_iteration()
+            ev[k][1].record()
+        barrier()
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(ms_steps))
+    kern = plan.profile_read(reset=True)
+    plan.profile(False)
+    launches = cabi.launch_count() - launches0
+    trials = lm.n_trials - trials0
+    forwards = lm.n_forward - fwd0
+    st = plan.stats()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_bands * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: every step streams the band's data + weight from pinned host memory and reads the result back
+    pin = {k: v.cpu().pin_memory() for k, v in plan.image_buffers[0].items()}
+    h2d = sum(v.numel() * 8 for v in pin.values())
+    out_pin = torch.empty(len(x0) + 1, dtype=torch.float64).pin_memory()
+    reset()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_ms = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        barrier()
+        e0.record()
+        for name, buf in plan.image_buffers[0].items():
+            buf.copy_(pin[name], non_blocking=True)
+        one_iteration()
+        out_pin[:-1].copy_(lm.current_state, non_blocking=True)
+        out_pin[-1] = lm.loss_history[-1]
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms += e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_bands * args.steps / (float(t.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    dfma_tflops, copy_gbs = cabi.bench_peaks()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    top = max(kern.items(), key=lambda kv: kv[1][1]) if kern else ("none", (0, 0.0))
+    name, (n_launch, k_ms) = top
+    spw = PSF_W + 2
+    src0 = plan.scene.sources[0]
+    roof = {"kernel": name, "launches": n_launch, "avg_ms": k_ms / max(n_launch, 1),
+            "share_of_step": k_ms / max(sum(v[1] for v in kern.values()), 1e-9)}
+    if name == "k_conv":
+        # direct convolution = 2 P^2 flop per output pixel per image (P = shifted stamp, 53);
+        # launches alternate between 1-image (forward) and (1 + n_act)-image (Jacobian) batches
+        px = src0.out[2] * src0.out[3]
+        n_jac = lm.n_jacobian
+        imgs_total = forwards + 7 * args.steps    # every forward convolves 1 plane; each Jacobian build 7 more
+        flops = 2.0 * spw * spw * px * imgs_total
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roof.update({"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
+                     "traffic": None, "peak_source": "apb_bench_peaks DFMA stream measured in this run "
+                     "(MEASURED_PEAKS.json has no fp64 figure; nominal 37.2)",
+                     "algorithmic": f"2*{spw}^2 flop x {px} px x {imgs_total} planes"})
+    else:
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        roof.update({"bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None})
+
+    # ---- CPU baseline (bounded sample: one full-size LM iteration of the oracle port)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        scene_c, x0_c = cpu_scene(1)
+        dt, _ = cpu_lm_iteration_seconds(scene_c, x0_c, 1)
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "1 full-size LM iteration of the numpy/scipy oracle port (FFT convolution), same workload"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"c2 x {n_bands} band(s): PSF-convolved Sersic, {SIZE}x{SIZE} per band, {PSF_W}x{PSF_W} Moffat PSF, "
+                               "threshold sub-pixel integration, LM fp64, joint fit sharded 1 band/GPU",
+                   "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
+                   "params": len(x0), "lambda_trials_per_iter": trials / args.steps, "forwards_per_iter": forwards / args.steps,
+                   "fit_restarts": state["restarts"]},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_pin.numel() * 8},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "mpix_per_s_sampled": n_bands * forwards * (n_pix_local / 1e6) / (total_ms * 1e-3),
+        "kernel_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])},
+        "refine_queue_last": st["queued"], "peaks_now": {"dfma_tflops": dfma_tflops, "copy_gbs": copy_gbs},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap_ = argparse.ArgumentParser()
+    ap_.add_argument("--gpus", type=int, default=1)
+    ap_.add_argument("--steps", type=int, default=20)
+    ap_.add_argument("--warmup", type=int, default=3)
+    ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap_.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,17 @@ int apb_chi2(apb_plan_t *plan, const double *x_rep, double *out2, void *stream);
 int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, int *info, void *stream);
 
 int apb_plan_stats(apb_plan_t *plan, apb_stats_t *out); /* synchronises the plan's last stream */
+
+/* ---- measurement (bench.py; no reference counterpart) ---------------------------------- */
+typedef struct {
+  char name[32];
+  int64_t launches;
+  double total_ms; /* sum of CUDA-event durations on the launching stream */
+} apb_kernel_time_t;
+int apb_profile(apb_plan_t *plan, int enable); /* bracket every kernel launch with CUDA events */
+int apb_profile_read(apb_plan_t *plan, apb_kernel_time_t *out, int max_out, int *n_out, int reset);
+long long apb_launch_count(void);               /* kernels launched by this library since load */
+int apb_bench_peaks(double *dfma_tflops, double *copy_gbs); /* DFMA-stream and fp64 copy ceilings, synchronous */
 const char *apb_last_error(void);
 int apb_version(void);
 
