@@ -152,6 +152,29 @@ def build(ap, name, data=None):
             models.append(m)
         g = M(name="joint", model_type="group model", models=models, target=tlist, psf_mode="full")
         return g, {}
+    if name == "crowded":
+        # scale model of BASELINE config[2]: overlapping PSF-convolved Sersics + point sources + sky
+        rng = np.random.default_rng(3)
+        size = 192
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 15), pixelscale=1.0)
+        tar = _target(ap, (size, size), data, psf=psf)
+        models = []
+        for k in range(8):
+            cx, cy = rng.uniform(30, size - 30, size=2)
+            models.append(M(name=f"g{k}", model_type="sersic galaxy model", target=tar, psf_mode="full",
+                            window=[[int(cx) - 24, int(cx) + 24], [int(cy) - 24, int(cy) + 24]],
+                            parameters={"center": [cx, cy], "q": rng.uniform(0.4, 0.9), "PA": rng.uniform(0, np.pi),
+                                        "n": rng.uniform(1, 4), "Re": rng.uniform(3, 8), "Ie": rng.uniform(0, 1)}))
+        for k in range(14):
+            cx, cy = rng.uniform(12, size - 12, size=2)
+            models.append(M(name=f"p{k}", model_type="point model", target=tar,
+                            window=[[int(cx) - 8, int(cx) + 9], [int(cy) - 8, int(cy) + 9]],
+                            parameters={"center": [cx, cy], "flux": rng.uniform(1, 2)}))
+        sky = M(name="csky", model_type="flat sky model", target=tar, parameters={"F": -2.0})
+        sky.initialize()
+        models.append(sky)
+        g = M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
+        return g, {}
     if name == "moffat_psf_model":
         ptar = ap.image.PSF_Image(data=np.zeros((25, 25)), pixelscale=1.0)
         m = M(name="mpsf", model_type="moffat psf model", target=ptar, parameters={"n": 2.5, "Rd": 3.0})
@@ -165,9 +188,9 @@ def build(ap, name, data=None):
 
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
-                 "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model"]
+                 "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded"]
 # scenes with an LM golden (noise seed, start perturbation)
-LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8}
+LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9}
 
 
 def make_data(truth_images, seed):

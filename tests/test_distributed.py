@@ -1,0 +1,64 @@
+"""N>1 path on CPU: two gloo ranks each take their share of the bands of a joint
+fit (lowering.shard_scene), build local normal equations (CPU oracle standing in
+for the kernels), all-reduce them, and must reproduce the unsharded result — the
+same reduction LM(distributed=True) performs over NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden, golden_data
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import astrophot_b200 as ap
+    import astrophot_oracle as orc
+    import scenes
+    from astrophot_b200.lowering import lower, shard_scene
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ap.AP_config.ap_device = "cpu"
+    fix = load_golden("joint")
+    model, _ = scenes.build(ap, "joint", data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    local = shard_scene(scene, rank, world)
+    assert len(local.images) == len([i for i in range(3) if i % world == rank])
+    assert local.n_par == scene.n_par
+    H, g, chi2, _ = orc.normal_eq(local, fix["x0"])
+    buf = torch.cat([torch.as_tensor(H).reshape(-1), torch.as_tensor(g), torch.tensor([chi2])])
+    dist.all_reduce(buf)
+    n_keep = torch.tensor([float(sum(im.H * im.W for im in local.images))], dtype=torch.float64)
+    dist.all_reduce(n_keep)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "reduced.npy"), np.concatenate([buf.numpy(), n_keep.numpy()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_band_sharded_normal_equations_allreduce(tmp_path):
+    import astrophot_b200 as ap
+    import astrophot_oracle as orc
+    import scenes
+    from astrophot_b200.lowering import lower
+
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    red = np.load(tmp_path / "reduced.npy")
+    fix = load_golden("joint")
+    P = len(fix["x0"])
+    H, g, chi2, npix = red[: P * P].reshape(P, P), red[P * P : P * P + P], red[P * P + P], red[-1]
+    d = np.sqrt(np.diag(fix["hess0"]))
+    assert np.max(np.abs(H - fix["hess0"]) / np.outer(d, d)) < 1e-9      # reference's own J^T W J
+    assert np.max(np.abs(g - fix["grad0"])) / np.abs(fix["grad0"]).max() < 1e-9
+    assert npix == 3 * 48 * 48
+    assert abs(chi2 / (npix - P) - fix["loss_history"][0]) / fix["loss_history"][0] < 1e-10
