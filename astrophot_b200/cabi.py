@@ -41,7 +41,7 @@ class apb_source_t(C.Structure):
                 ("n_prof", C.c_int32), ("prof", C.c_double * MAX_PROF),
                 ("sampling_mode", C.c_int32), ("quad_init", C.c_int32), ("integrate_mode", C.c_int32),
                 ("quad_level", C.c_int32), ("gridding", C.c_int32), ("max_depth", C.c_int32),
-                ("ref_mode", C.c_int32), ("psf", C.c_int32), ("psf_shift", C.c_int32), ("_pad", C.c_int32),
+                ("ref_mode", C.c_int32), ("psf", C.c_int32), ("psf_shift", C.c_int32), ("conv_mode", C.c_int32),
                 ("tolerance", C.c_double), ("softening", C.c_double)]
 
 
@@ -58,7 +58,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -91,6 +91,7 @@ def load_library(path=None):
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
     L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
+    L.apb_plan_reserve.argtypes = [vp, C.POINTER(C.c_int64)]
     L.apb_profile.argtypes = [vp, C.c_int]
     L.apb_profile_read.argtypes = [vp, C.POINTER(apb_kernel_time_t), C.c_int, C.POINTER(C.c_int), C.c_int]
     L.apb_bench_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -134,7 +135,9 @@ def _dev_f64(x):
 class Plan:
     """A lowered model tree resident on the device (``apb_plan_t``)."""
 
-    def __init__(self, scene, queue_capacity=0):
+    def __init__(self, scene, queue_capacity=0, conv=None):
+        """``conv``: None (per-source psf_convolve_mode), "direct" or "fft" to force one
+        convolution kernel family for every source (tests, benchmarks)."""
         _require_cuda()
         L = lib()
         self.scene = scene
@@ -188,8 +191,9 @@ class Plan:
             c.sampling_mode, c.quad_init, c.integrate_mode = s.sampling_mode, s.quad_init, s.integrate_mode
             c.quad_level, c.gridding, c.max_depth = s.quad_level, s.gridding, s.max_depth
             c.ref_mode, c.psf, c.psf_shift = s.ref_mode, s.psf, s.psf_shift
+            c.conv_mode = int(getattr(s, "conv_mode", 0))
             c.tolerance, c.softening = s.tolerance, s.softening
-        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags=0)
+        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv])
         handle = C.c_void_p()
         _check(L.apb_plan_create(srcs, n_src, imgs, n_img, psfs, n_psf, pars, self.n_par, C.byref(opts),
                                  C.byref(handle)), "apb_plan_create")
@@ -218,21 +222,45 @@ class Plan:
             arr[i] = t.data_ptr()
         return arr
 
+    # -- refinement-queue capacity ------------------------------------------------
+    def reserve(self, caps=None):
+        """Grow the sub-pixel refinement queues (after an overflow) and clear the flag."""
+        arr = None
+        if caps is not None:
+            arr = (C.c_int64 * (MAX_DEPTH + 1))(*([0] + [int(c) for c in caps] + [0] * MAX_DEPTH)[: MAX_DEPTH + 1])
+        _check(self._L.apb_plan_reserve(self._h, arr), "apb_plan_reserve")
+
+    def _retry_on_overflow(self, call):
+        """Run ``call`` (which launches on the device), synchronise, and if a refinement queue
+        overflowed grow the queues from the observed counts and repeat."""
+        for _ in range(12):
+            out = call()
+            if not self.stats()["overflow"]:
+                return out
+            self.reserve()
+        raise NativeLibraryError("sub-pixel refinement queues keep overflowing; pass queue_capacity= explicitly")
+
     # -- entry points ------------------------------------------------------------
     def sample(self, x, as_rep=False):
         x = self._x(x)
         outs = [torch.empty(h, w, dtype=torch.float64, device="cuda") for h, w in self.shapes]
-        _check(self._L.apb_sample(self._h, x.data_ptr(), int(as_rep), self._ptrs(outs), _stream()), "apb_sample")
+        self._retry_on_overflow(lambda: _check(
+            self._L.apb_sample(self._h, x.data_ptr(), int(as_rep), self._ptrs(outs), _stream()), "apb_sample"))
         return outs
 
     def jacobian(self, x, as_rep=False):
         x = self._x(x)
         outs = [torch.empty(h, w, self.n_par, dtype=torch.float64, device="cuda") for h, w in self.shapes]
-        _check(self._L.apb_jacobian(self._h, x.data_ptr(), int(as_rep), self._ptrs(outs), _stream()), "apb_jacobian")
+        self._retry_on_overflow(lambda: _check(
+            self._L.apb_jacobian(self._h, x.data_ptr(), int(as_rep), self._ptrs(outs), _stream()), "apb_jacobian"))
         return outs
 
-    def normal_eq(self, x, as_rep=True, out=None):
-        """Returns (JtWJ (P,P), JtWr (P,), chi2 (1,)) device tensors."""
+    def normal_eq(self, x, as_rep=True, out=None, check=False):
+        """Returns (JtWJ (P,P), JtWr (P,), chi2 (2,): chi^2 and status flag) device tensors.
+        Asynchronous; ``check=True`` synchronises and transparently repeats after a queue overflow
+        (LM instead watches the sticky flag that comes back with every chi^2 record)."""
+        if check:
+            return self._retry_on_overflow(lambda: self.normal_eq(x, as_rep, out))
         x = self._x(x)
         P = self.n_par
         if out is None:

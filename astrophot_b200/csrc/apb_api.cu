@@ -10,6 +10,7 @@
 #include "apb_internal.cuh"
 #include "apb_sample.cuh"
 #include "apb_image.cuh"
+#include "apb_fft.cuh"
 
 
 static thread_local std::string g_err;
@@ -39,11 +40,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -60,6 +61,15 @@ struct ModeTables {
   size_t conv_smem = 0;
 };
 
+// FFT-convolution work lists; independent of the sampling mode (the evaluation region is)
+struct FftTables {
+  int4* rows = nullptr; int n_rows = 0;          // {src, plane | -1-k, row0, nrows}
+  int4* jobs = nullptr;                          // {src, in_plane | -1-k, kernel, out_plane}
+  int4* cols_psf = nullptr; int n_cols_psf = 0;  // {job, kx0, ncols, 0}
+  int4* cols_img = nullptr; int n_cols_img = 0;
+  int4* rows_inv = nullptr; int n_rows_inv = 0;  // {src, out_plane, row0, nrows}
+};
+
 struct apb_plan {
   int n_src = 0, n_img = 0, n_par = 0, n_psf = 0;
   std::vector<DevSrc> h_src;
@@ -70,6 +80,11 @@ struct apb_plan {
   apb_param_t* d_par = nullptr;
   apb_psf_t* d_psf = nullptr;
   ModeTables mt[2];
+  FftTables ft[2];               // [grad]
+  FftDesc* d_fftdesc = nullptr;
+  cpx *d_twid = nullptr, *d_spec = nullptr;
+  size_t fft_smem_rows = 0, fft_smem_cols = 0;
+  int n_fft_src = 0;
   int* psf_list = nullptr; int n_psf_list = 0;      // sources needing a shifted PSF stamp
   int* point_list = nullptr; int n_point = 0;
   int* norm_list = nullptr; int n_norm = 0;
@@ -160,9 +175,39 @@ static void set_geo(Geo& g, const int* out, const int* work, int bx, int by, boo
   g.tile0 = g.ntile = g.chunk0 = g.nchunk = 0;
 }
 
+// smallest 2^a 3^b 5^c >= n (b <= 3, c <= 1: keeps the odd-radix stages few)
+static int fft_len(int n) {
+  for (int m = std::max(n, 2);; ++m) {
+    int r = m, b = 0, c = 0;
+    while (r % 2 == 0) r /= 2;
+    while (r % 3 == 0 && b < 3) { r /= 3; ++b; }
+    while (r % 5 == 0 && c < 1) { r /= 5; ++c; }
+    if (r == 1) return m;
+  }
+}
+
+static FftDesc fft_desc(int N) {
+  FftDesc D;
+  memset(&D, 0, sizeof(D));
+  D.N = N;
+  int n = N;
+  // power-of-two stages first: their index arithmetic is shifts and masks
+  while (n % 4 == 0) { D.radix[D.nstage++] = 4; n /= 4; }
+  while (n % 2 == 0) { D.radix[D.nstage++] = 2; n /= 2; }
+  while (n % 3 == 0) { D.radix[D.nstage++] = 3; n /= 3; }
+  while (n % 5 == 0) { D.radix[D.nstage++] = 5; n /= 5; }
+  return D;
+}
+
 extern "C" int apb_plan_destroy(apb_plan_t* p) {
   if (!p) return 0;
   for (void* q : p->owned) cudaFree(q);
+  for (int d = 1; d <= APB_MAX_DEPTH; ++d) {
+    Level& L = p->q.lv[d];
+    void* olds[6] = {L.src, L.x, L.y, L.parent, L.child, L.res};
+    for (void* o : olds)
+      if (o) cudaFree(o);
+  }
   delete p;
   return 0;
 }
@@ -176,6 +221,55 @@ static int own_upload(apb_plan* p, const std::vector<T>& v, T** out) {
 static int own_alloc(apb_plan* p, void** out, size_t bytes) {
   CU(cudaMalloc(out, std::max<size_t>(bytes, 8)));
   p->owned.push_back(*out);
+  return 0;
+}
+
+// (re)allocate the refinement queues with caps[d] entries at depth d (0 = keep)
+static int alloc_queues(apb_plan* p, const long long* caps) {
+  for (int d = 1; d <= p->max_depth; ++d) {
+    const long long cap = std::min<long long>(caps[d], 1LL << 28);
+    if (cap <= 0 || cap == p->q.cap[d]) continue;
+    Level& L = p->q.lv[d];
+    void* olds[6] = {L.src, L.x, L.y, L.parent, L.child, L.res};
+    for (void* o : olds)
+      if (o) cudaFree(o);
+    memset(&L, 0, sizeof(L));
+    p->q.cap[d] = 0;
+    CU(cudaMalloc((void**)&L.src, sizeof(int) * cap));
+    CU(cudaMalloc((void**)&L.x, sizeof(double) * cap));
+    CU(cudaMalloc((void**)&L.y, sizeof(double) * cap));
+    CU(cudaMalloc((void**)&L.parent, sizeof(int) * cap));
+    CU(cudaMalloc((void**)&L.child, sizeof(int) * cap));
+    CU(cudaMalloc((void**)&L.res, sizeof(double) * cap * p->NVp_grad));
+    p->q.cap[d] = (int)cap;
+  }
+  return 0;
+}
+
+// Grow the refinement queues after an overflow.  caps[d] (d = 1..APB_MAX_DEPTH) = entries wanted
+// at depth d; NULL = size every level from the counts of the last call (x1.5).  Clears the
+// overflow flag.  Synchronous.
+extern "C" int apb_plan_reserve(apb_plan_t* p, const int64_t* caps) {
+  if (!p) APB_FAIL("apb_plan_reserve: NULL plan");
+  CU(cudaDeviceSynchronize());
+  long long want[APB_MAX_DEPTH + 1] = {0};
+  if (caps) {
+    for (int d = 1; d <= APB_MAX_DEPTH; ++d) want[d] = caps[d];
+  } else {
+    int cnt[APB_MAX_DEPTH + 2];
+    CU(cudaMemcpy(cnt, p->q.count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    for (int d = 1; d <= p->max_depth; ++d) {
+      // a level fed by a truncated parent has not seen all its entries yet: leave it head-room
+      const long long need = (long long)cnt[d] + cnt[d] / 2;
+      want[d] = std::max<long long>(p->q.cap[d], need);
+      if (d > 1 && cnt[d - 1] > p->q.cap[d - 1]) want[d] = std::max<long long>(want[d], 2LL * p->q.cap[d]);
+    }
+  }
+  if (p->any_threshold) {
+    int rc = alloc_queues(p, want);
+    if (rc) return rc;
+  }
+  CU(cudaMemset(p->q.overflow, 0, sizeof(int)));
   return 0;
 }
 
@@ -209,9 +303,24 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   // ---- sources
   std::vector<DevSrc>& S = p->h_src;
   S.resize(n_src);
-  long long stamp_total = 0, out_total = 0, psfst_total = 0;
+  long long stamp_total = 0, out_total = 0, psfst_total = 0, spec_total = 0;
   std::vector<int> psf_list, point_list, norm_list, act_slot, act_off(n_src + 1, 0);
   int max_nact = 0;
+  std::vector<FftDesc> fdescs;
+  std::vector<cpx> twid;
+  auto get_desc = [&](int N) -> int {
+    for (size_t k = 0; k < fdescs.size(); ++k)
+      if (fdescs[k].N == N) return (int)k;
+    FftDesc D = fft_desc(N);
+    D.tw_off = (long long)twid.size();
+    for (int k = 0; k < N; ++k) {
+      const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)N;
+      twid.push_back(cpx{(double)cosl(a), (double)sinl(a)});
+    }
+    fdescs.push_back(D);
+    return (int)fdescs.size() - 1;
+  };
+  const int conv_force = opts ? (opts->flags & 3) : 0;   // 1: direct everywhere, 2: FFT everywhere
   for (int i = 0; i < n_src; ++i) {
     const apb_source_t& a = src[i];
     DevSrc& s = S[i];
@@ -277,6 +386,37 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       if (g.ex0 < g.rx0 || g.ey0 < g.ry0 || g.ex0 + g.ew > g.rx0 + g.rw || g.ey0 + g.eh > g.ry0 + g.rh)
         PFAIL("working window must contain the output window");
     }
+    // ---- convolution method.  The reference convolves by FFT unless psf_convolve_mode="direct"
+    //      (_model_methods.py:245-255); both give the same valid region, so "fft" here means
+    //      "whichever is faster": direct tiles for small stamps, FFT above ~17x17.
+    if (s.psf >= 0 && a.kind != APB_POINT) {
+      int want = conv_force ? conv_force : a.conv_mode;
+      if (want == 0) want = (s.spw * s.sph > 17 * 17) ? 2 : 1;
+      if (want == 2) {
+        const Geo& g = s.geo[0];
+        const int Nx = fft_len(g.ew), Ny = fft_len(g.eh);
+        int nc = 8;
+        auto col_bytes = [&](int c) { return (size_t)(Ny + 2 * c * (Ny + 8 / c)) * sizeof(cpx); };
+        while (nc > 1 && col_bytes(nc) > 110 * 1024) nc /= 2;
+        const int nf = std::max(1, std::min(8, 1024 / Nx));
+        const size_t row_bytes = (size_t)(Nx + 2 * nf * Nx) * sizeof(cpx);
+        if (col_bytes(nc) <= 227 * 1024 && row_bytes <= 227 * 1024) {
+          s.conv_fft = 1;
+          s.fftx = get_desc(Nx); s.ffty = get_desc(Ny);
+          s.fft_nx = Nx; s.nxh = Nx / 2 + 1; s.nxp = (s.nxh + 3) & ~3;
+          s.fft_nf = nf; s.fft_nc = nc;
+          s.specA_off = spec_total; spec_total += (long long)(1 + s.n_act) * g.eh * s.nxp;
+          s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.oh * s.nxp;
+          s.specK_off = spec_total; spec_total += 3LL * s.sph * s.nxp;
+          s.specKT_off = spec_total; spec_total += 3LL * s.nxh * Ny;
+          p->fft_smem_rows = std::max(p->fft_smem_rows, row_bytes);
+          p->fft_smem_cols = std::max(p->fft_smem_cols, col_bytes(nc));
+          p->n_fft_src++;
+        } else if (conv_force == 2 || a.conv_mode == 2) {
+          PFAIL("stamp too large for the shared-memory FFT convolution");
+        }
+      }
+    }
     s.same_geo = memcmp(&s.geo[0], &s.geo[1], sizeof(Geo)) == 0;
     if (!s.same_geo && a.kind != APB_FLAT_SKY && a.kind != APB_POINT) p->all_same_geo = false;
     if (a.kind != APB_FLAT_SKY && a.kind != APB_POINT) {
@@ -322,7 +462,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       size_t smem = 0;
       for (int i = 0; i < n_src; ++i) {
         const DevSrc& s = S[i];
-        if (s.psf < 0 || s.kind == APB_POINT) continue;
+        if (s.psf < 0 || s.kind == APB_POINT || s.conv_fft) continue;
         const int cw = (s.spw - 1) / 2, chh = (s.sph - 1) / 2;
         if (cw > s.bx || chh > s.by) PFAIL("internal: psf stamp wider than the border");
         auto add_job = [&](int in_plane, int kern, int out_plane) {
@@ -354,6 +494,63 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PCU(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)std::max(p->mt[0].conv_smem, p->mt[1].conv_smem)));
 
+  // ---- FFT convolution work lists
+  for (int gr = 0; gr < 2 && p->n_fft_src; ++gr) {
+    FftTables& F = p->ft[gr];
+    std::vector<int4> rows, jobs, cpsf, cimg, rinv;
+    for (int i = 0; i < n_src; ++i) {
+      const DevSrc& s = S[i];
+      if (!s.conv_fft) continue;
+      const Geo& g = s.geo[0];
+      const bool shifted = s.psf_shift != APB_SHIFT_NONE;
+      auto add_rows = [&](std::vector<int4>& v, int code, int nrows) {
+        for (int r = 0; r < nrows; r += 2 * s.fft_nf) v.push_back(make_int4(i, code, r, std::min(2 * s.fft_nf, nrows - r)));
+      };
+      auto add_cols = [&](std::vector<int4>& v, int job) {
+        for (int k = 0; k < s.nxh; k += s.fft_nc) v.push_back(make_int4(job, k, std::min(s.fft_nc, s.nxh - k), 0));
+      };
+      bool need_k[3] = {true, false, false};
+      std::vector<int> in_planes(1, 0);
+      std::vector<int4> conv;   // {in_plane, kernel, out_plane}
+      conv.push_back(make_int4(0, 0, 0, 0));
+      if (gr)
+        for (int e = 0; e < s.n_elem; ++e) {
+          if (s.plane[e] <= 0) continue;
+          if (e < 2 && shifted) { need_k[1 + e] = true; conv.push_back(make_int4(0, 1 + e, s.plane[e], 0)); }
+          else { in_planes.push_back(s.plane[e]); conv.push_back(make_int4(s.plane[e], 0, s.plane[e], 0)); }
+        }
+      for (int k = 0; k < 3; ++k)
+        if (need_k[k]) {
+          add_rows(rows, -1 - k, s.sph);
+          jobs.push_back(make_int4(i, -1 - k, 0, 0));
+          add_cols(cpsf, (int)jobs.size() - 1);
+        }
+      for (int pl : in_planes) add_rows(rows, pl, g.eh);
+      for (const int4& c : conv) {
+        jobs.push_back(make_int4(i, c.x, c.y, c.z));
+        add_cols(cimg, (int)jobs.size() - 1);
+        add_rows(rinv, c.z, s.oh);
+      }
+    }
+    F.n_rows = (int)rows.size(); F.n_cols_psf = (int)cpsf.size(); F.n_cols_img = (int)cimg.size(); F.n_rows_inv = (int)rinv.size();
+    PRC(own_upload(p, rows, &F.rows));
+    PRC(own_upload(p, jobs, &F.jobs));
+    PRC(own_upload(p, cpsf, &F.cols_psf));
+    PRC(own_upload(p, cimg, &F.cols_img));
+    PRC(own_upload(p, rinv, &F.rows_inv));
+  }
+  if (p->n_fft_src) {
+    PRC(own_upload(p, fdescs, &p->d_fftdesc));
+    PRC(own_upload(p, twid, &p->d_twid));
+    PRC(own_alloc(p, (void**)&p->d_spec, sizeof(cpx) * (size_t)spec_total));
+    if (p->fft_smem_rows > 48 * 1024) {
+      PCU(cudaFuncSetAttribute(k_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fft_smem_rows));
+      PCU(cudaFuncSetAttribute(k_fft_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fft_smem_rows));
+    }
+    if (p->fft_smem_cols > 48 * 1024)
+      PCU(cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fft_smem_cols));
+  }
+
   // ---- image tiles and source bins (32x32 pixels)
   {
     std::vector<int4> itiles;
@@ -383,14 +580,14 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   }
 
   // ---- normal-equation work lists: diagonal blocks + overlapping pairs, split in <=8-plane
-  //      sub-blocks and <=4096-pixel rectangles
+  //      sub-blocks and <=2048-pixel rectangles (one CTA each)
   {
     std::vector<BlockItem> items, vitems;
     std::vector<BlockDesc> blocks, vblocks;
     auto add_block = [&](int a, int b, int pa0, int na, int pb0, int nb, int diag, int x0, int y0, int w, int h,
                          std::vector<BlockItem>& it, std::vector<BlockDesc>& bl) {
       BlockDesc bd{a, b, pa0, na, pb0, nb, diag, (int)it.size(), 0};
-      const int rows = std::max(1, 4096 / std::max(w, 1));
+      const int rows = std::max(1, 2048 / std::max(w, 1));
       for (int r = 0; r < h; r += rows) {
         BlockItem bi{a, b, pa0, na, pb0, nb, x0, y0 + r, w, std::min(rows, h - r), diag, (int)bl.size()};
         it.push_back(bi);
@@ -476,29 +673,21 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   PRC(own_alloc(p, (void**)&p->d_xtmp, sizeof(double) * (size_t)std::max(n_par, 1)));
   PCU(cudaMemset(p->d_stamp, 0, sizeof(double) * (size_t)std::max<long long>(stamp_total, 1)));
 
-  // ---- queues
+  // ---- queues: depth 1 can never hold more than the first-pass pixels; deeper levels start at a
+  //      heuristic size and grow on demand (apb_plan_reserve) when the sticky overflow flag is raised
   {
     long long cap = opts ? opts->queue_capacity : 0;
-    if (cap <= 0) {
-      long long px = std::max(p->first_evals[0], p->first_evals[1]);
-      cap = std::min<long long>(std::max<long long>(px, 1 << 16), 1LL << 24);
-    }
-    p->q.cap = (int)cap;
-    p->q.NVp = 1;
+    const long long px = std::max(p->first_evals[0], p->first_evals[1]);
     PRC(own_alloc(p, (void**)&p->q.count, sizeof(int) * (APB_MAX_DEPTH + 2)));
     PRC(own_alloc(p, (void**)&p->q.overflow, sizeof(int)));
     PCU(cudaMemset(p->q.overflow, 0, sizeof(int)));
     PCU(cudaMemset(p->q.count, 0, sizeof(int) * (APB_MAX_DEPTH + 2)));
+    p->q.NVp = 1;
     if (p->any_threshold) {
-      for (int d = 1; d <= p->max_depth; ++d) {
-        Level& L = p->q.lv[d];
-        PRC(own_alloc(p, (void**)&L.src, sizeof(int) * cap));
-        PRC(own_alloc(p, (void**)&L.x, sizeof(double) * cap));
-        PRC(own_alloc(p, (void**)&L.y, sizeof(double) * cap));
-        PRC(own_alloc(p, (void**)&L.parent, sizeof(int) * cap));
-        PRC(own_alloc(p, (void**)&L.child, sizeof(int) * cap));
-        PRC(own_alloc(p, (void**)&L.res, sizeof(double) * cap * p->NVp_grad));
-      }
+      long long caps[APB_MAX_DEPTH + 1] = {0};
+      for (int d = 1; d <= p->max_depth; ++d)
+        caps[d] = cap > 0 ? cap : (d == 1 ? std::max<long long>(px, 1024) : std::max<long long>(px, 1 << 18));
+      PRC(alloc_queues(p, caps));
     }
   }
 
@@ -589,6 +778,25 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
                                                            p->d_stamp, p->d_psfst, p->d_out);
     LAUNCH_CHECK();
   }
+  if (p->n_fft_src) {
+    const FftTables& F = p->ft[grad];
+    PB(K_FFTROWS);
+    k_fft_rows<<<F.n_rows, 256, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows, mode, p->d_stamp,
+                                                        p->d_psfst, p->d_spec);
+    LAUNCH_CHECK();
+    PB(K_FFTCOLS);
+    k_fft_cols<<<F.n_cols_psf, 256, p->fft_smem_cols, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.jobs, F.cols_psf, mode,
+                                                            p->d_spec);
+    LAUNCH_CHECK();
+    PB(K_FFTCOLS);
+    k_fft_cols<<<F.n_cols_img, 256, p->fft_smem_cols, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.jobs, F.cols_img, mode,
+                                                            p->d_spec);
+    LAUNCH_CHECK();
+    PB(K_FFTINV);
+    k_fft_rows_inv<<<F.n_rows_inv, 256, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows_inv, p->d_spec,
+                                                                p->d_out);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -601,7 +809,7 @@ static int assemble(apb_plan* p, int mode, double** model_out_dev, double** resi
   LAUNCH_CHECK();
   if (chi_out2) {
     PB(K_CHI);
-    k_chi_final<<<1, 256, 0, st>>>(p->d_chipart, p->n_img_tiles, chi_out2, write_flag);
+    k_chi_final<<<1, 256, 0, st>>>(p->d_chipart, p->n_img_tiles, chi_out2, write_flag, p->q.overflow);
     LAUNCH_CHECK();
   }
   return 0;
@@ -668,11 +876,11 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
   if (!p->all_same_geo) {
     // forward model in group geometry for the residual, then derivatives in own-window geometry
     if ((rc = sample_pass(p, x, as_rep, 0, 0, st))) return rc;
-    if ((rc = assemble(p, 0, nullptr, p->d_resid, chi2, 0, st))) return rc;
+    if ((rc = assemble(p, 0, nullptr, p->d_resid, chi2, 1, st))) return rc;
     if ((rc = sample_pass(p, x, as_rep, 1, 1, st))) return rc;
   } else {
     if ((rc = sample_pass(p, x, as_rep, 1, 1, st))) return rc;
-    if ((rc = assemble(p, 1, nullptr, p->d_resid, chi2, 0, st))) return rc;
+    if ((rc = assemble(p, 1, nullptr, p->d_resid, chi2, 1, st))) return rc;
   }
   CU(cudaMemsetAsync(JtWJ, 0, sizeof(double) * (size_t)P * P, st));
   CU(cudaMemsetAsync(JtWr, 0, sizeof(double) * (size_t)P, st));
@@ -682,7 +890,7 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
                                          -1.0, 0, p->d_part);
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
-    k_block_final<<<ceil_div(p->n_blocks, 4), 128, 0, st>>>(p->d_src, p->d_blocks, p->n_blocks, p->d_act_slot,
+    k_block_final<<<dim3(p->n_blocks, BLK_VALS / 8), 256, 0, st>>>(p->d_src, p->d_blocks, p->n_blocks, p->d_act_slot,
                                                             p->d_act_off, p->d_part, JtWJ, JtWr, P, -1.0, 0);
     LAUNCH_CHECK();
   }
@@ -709,7 +917,7 @@ extern "C" int apb_geodesic(apb_plan_t* p, const double* xdh, const double* h, d
                                           1.0, 1, p->d_part);
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
-    k_block_final<<<ceil_div(p->n_vblocks, 4), 128, 0, st>>>(p->d_src, p->d_vblocks, p->n_vblocks, p->d_act_slot,
+    k_block_final<<<dim3(p->n_vblocks, BLK_VALS / 8), 256, 0, st>>>(p->d_src, p->d_vblocks, p->n_vblocks, p->d_act_slot,
                                                              p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1);
     LAUNCH_CHECK();
   }

@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(256) k_assemble(const DevSrc* __restrict__ src
   }
 }
 
-__global__ void k_chi_final(const double* __restrict__ part, int n, double* __restrict__ out2, int write_flag) {
+// out2[0] = chi^2; out2[1] = 1 finite, 0 non-finite pixels, -1 a refinement queue overflowed
+// (results invalid: apb_plan_reserve, then repeat the call)
+__global__ void k_chi_final(const double* __restrict__ part, int n, double* __restrict__ out2, int write_flag,
+                            const int* __restrict__ overflow) {
   __shared__ double sh[8];
   double c = 0, b = 0;
   for (int q = threadIdx.x; q < n; q += 256) {
@@ -238,7 +241,7 @@ __global__ void k_chi_final(const double* __restrict__ part, int n, double* __re
   b = block_sum<256>(b, sh);
   if (threadIdx.x == 0) {
     out2[0] = c;
-    if (write_flag) out2[1] = (b == 0.0 && isfinite(c)) ? 1.0 : 0.0;
+    if (write_flag) out2[1] = *overflow ? -1.0 : ((b == 0.0 && isfinite(c)) ? 1.0 : 0.0);
   }
 }
 
@@ -300,6 +303,20 @@ __device__ __forceinline__ double plane_at(const DevSrc& s, int plane, int x, in
 
 #define NB_MAX 8
 #define BLK_VALS (NB_MAX * NB_MAX + NB_MAX)
+
+// D(8x8) += A(8x4) . B(4x8) on the FP64 tensor pipe.  Fragments (PTX ISA, mma.m8n8k4.f64):
+// lane l holds A[l>>2][l&3], B[l&3][l>>2] and D[l>>2][2*(l&3) + {0,1}].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// The contraction over pixels is a tall-skinny GEMM (8 x Npix) . (Npix x 8): four pixels per DMMA.
+// Lane l reads ONE Jacobian value per 4-pixel group -- plane (l>>2) at pixel (l&3) -- which is at the
+// same time its A fragment (times the weight) and, for diagonal blocks, its B fragment.  Two
+// accumulator registers per lane instead of 64: occupancy is no longer register-bound and the
+// kernel streams the derivative planes at HBM speed.  J^T r rides along on the FP64 pipe.
 __global__ void __launch_bounds__(256) k_blocks(const DevSrc* __restrict__ src, const apb_image_t* __restrict__ imgs,
                                                 const BlockItem* __restrict__ items, const double* __restrict__ stamp,
                                                 const double* __restrict__ outar, const double* __restrict__ skyJ,
@@ -311,59 +328,45 @@ __global__ void __launch_bounds__(256) k_blocks(const DevSrc* __restrict__ src, 
   const DevSrc& B = src[it.b];
   const apb_image_t im = imgs[A.image];
   const double* rimg = resid[A.image];
-  double acc[NB_MAX][NB_MAX];
-  double gv[NB_MAX];
-#pragma unroll
-  for (int i = 0; i < NB_MAX; ++i) {
-    gv[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < NB_MAX; ++j) acc[i][j] = 0.0;
-  }
-  const int n = it.w * it.h;
-  for (int q = threadIdx.x; q < n; q += 256) {
-    const int x = it.x0 + q % it.w, y = it.y0 + q / it.w;
-    const long long p = (long long)y * im.W + x;
-    if (im.mask && im.mask[p]) continue;
-    const double w = im.weight ? im.weight[p] : 1.0;
-    double ja[NB_MAX], jb[NB_MAX];
-#pragma unroll
-    for (int i = 0; i < NB_MAX; ++i) ja[i] = i < it.na ? plane_at(A, it.pa0 + i + 1, x, y, stamp, outar, skyJ, it.a) : 0.0;
-    if (it.diag || vec_only) {
-      const double r = rimg[p];
-#pragma unroll
-      for (int i = 0; i < NB_MAX; ++i) gv[i] = fma(r, ja[i], gv[i]);
-    }
-    if (vec_only) continue;
-    if (it.diag) {
-#pragma unroll
-      for (int i = 0; i < NB_MAX; ++i) jb[i] = ja[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < NB_MAX; ++i) jb[i] = i < it.nb ? plane_at(B, it.pb0 + i + 1, x, y, stamp, outar, skyJ, it.b) : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < NB_MAX; ++i) {
-      const double wa = w * ja[i];
-#pragma unroll
-      for (int j = 0; j < NB_MAX; ++j) acc[i][j] = fma(wa, jb[j], acc[i][j]);
-    }
-  }
-  // fixed-order reduction: lanes by shuffle, then the 8 warps through shared memory
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < NB_MAX; ++i) {
-#pragma unroll
-    for (int j = 0; j < NB_MAX; ++j) {
-      double v = acc[i][j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) sh[wid][i * NB_MAX + j] = v;
+  const int pl = lane >> 2, pq = lane & 3;     // plane and pixel-in-group of this lane
+  const bool has_a = pl < it.na, has_b = pl < it.nb;
+  const bool need_r = it.diag || vec_only;
+  // per-lane plane pointers (sky planes are a constant)
+  const bool a_sky = A.kind == APB_FLAT_SKY, b_sky = B.kind == APB_FLAT_SKY;
+  PlaneView va{nullptr, 0}, vb{nullptr, 0};
+  if (has_a && !a_sky) va = out_plane(A, 1, it.pa0 + pl + 1, stamp, outar);
+  if (has_b && !b_sky) vb = out_plane(B, 1, it.pb0 + pl + 1, stamp, outar);
+  const double ca = a_sky ? skyJ[it.a] : 0.0, cb = b_sky ? skyJ[it.b] : 0.0;
+  double d0 = 0.0, d1 = 0.0, gv = 0.0;
+  const int n = it.w * it.h;
+  const int ngroups = (n + 3) >> 2;
+#pragma unroll 4
+  for (int gq = wid; gq < ngroups; gq += 8) {
+    const int q = 4 * gq + pq;
+    double ja = 0.0, jb = 0.0, w = 0.0, r = 0.0;
+    if (q < n) {
+      const int yy = q / it.w, xx = q - yy * it.w;
+      const int x = it.x0 + xx, y = it.y0 + yy;
+      const long long p = (long long)y * im.W + x;
+      const bool masked = im.mask && im.mask[p];
+      if (!masked) {
+        w = im.weight ? im.weight[p] : 1.0;
+        if (need_r) r = rimg[p];
+        if (has_a) ja = a_sky ? ca : va.p[(long long)(y - A.oy) * va.stride + (x - A.ox)];
+        if (it.diag) jb = ja;
+        else if (has_b && !vec_only) jb = b_sky ? cb : vb.p[(long long)(y - B.oy) * vb.stride + (x - B.ox)];
+      }
     }
-    double v = gv[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[wid][NB_MAX * NB_MAX + i] = v;
+    gv = fma(r, ja, gv);
+    if (!vec_only) dmma_8x8x4(d0, d1, w * ja, jb);
   }
+  // J^T r: the four lanes of a plane hold partial sums
+  gv += __shfl_xor_sync(0xffffffffu, gv, 1);
+  gv += __shfl_xor_sync(0xffffffffu, gv, 2);
+  sh[wid][pl * NB_MAX + 2 * pq] = d0;
+  sh[wid][pl * NB_MAX + 2 * pq + 1] = d1;
+  if (pq == 0) sh[wid][NB_MAX * NB_MAX + pl] = gv;
   __syncthreads();
   if (threadIdx.x < BLK_VALS) {
     double v = 0.0;
@@ -378,33 +381,45 @@ struct BlockDesc {
   int a, b, pa0, na, pb0, nb, diag, item0, nitem;
 };
 
-// one warp-sized group of threads per block: sum partials in item order, add into H and g.
-// Entries that belong to a single block are exact; entries shared by several blocks (linked
-// parameters of joint fits) are combined with fp64 atomics.
-__global__ void k_block_final(const DevSrc* __restrict__ src, const BlockDesc* __restrict__ blocks, int nblocks,
-                              const int* __restrict__ act_slot, const int* __restrict__ act_off,
-                              const double* __restrict__ part, double* __restrict__ H, double* __restrict__ g, int P,
-                              double gsign, int vec_only) {
-  const int bi = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  if (bi >= nblocks) return;
+// grid (blocks, BLK_VALS/8): one warp per value of a block; its lanes stride over the block's partials
+// (independent loads, 4 in flight per lane) and combine with a fixed shuffle tree (deterministic),
+// then lane 0 adds into H and g.  Entries that belong to a single block are exact; entries shared
+// by several blocks (linked parameters of joint fits) are combined with fp64 atomics.
+__global__ void __launch_bounds__(256) k_block_final(const DevSrc* __restrict__ src, const BlockDesc* __restrict__ blocks,
+                                                     int nblocks, const int* __restrict__ act_slot,
+                                                     const int* __restrict__ act_off, const double* __restrict__ part,
+                                                     double* __restrict__ H, double* __restrict__ g, int P, double gsign,
+                                                     int vec_only) {
+  const int bi = blockIdx.x;
   const BlockDesc bd = blocks[bi];
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int v = blockIdx.y * 8 + wid;
+  const int i = v < NB_MAX * NB_MAX ? v / NB_MAX : v - NB_MAX * NB_MAX;
+  const int j = v < NB_MAX * NB_MAX ? v % NB_MAX : -1;
+  if (i >= bd.na) return;
+  if (j >= 0 && (j >= bd.nb || vec_only)) return;
+  if (j < 0 && !(bd.diag || vec_only)) return;
+  const double* pp = part + (long long)bd.item0 * BLK_VALS + v;
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+  int k = lane;
+  for (; k + 96 < bd.nitem; k += 128) {
+    t0 += pp[(long long)k * BLK_VALS];
+    t1 += pp[(long long)(k + 32) * BLK_VALS];
+    t2 += pp[(long long)(k + 64) * BLK_VALS];
+    t3 += pp[(long long)(k + 96) * BLK_VALS];
+  }
+  for (; k < bd.nitem; k += 32) t0 += pp[(long long)k * BLK_VALS];
+  double tot = (t0 + t1) + (t2 + t3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+  if (lane != 0) return;
   const int* sa = act_slot + act_off[bd.a] + bd.pa0;
   const int* sb = act_slot + act_off[bd.b] + bd.pb0;
-  for (int v = lane; v < BLK_VALS; v += 32) {
-    const int i = v < NB_MAX * NB_MAX ? v / NB_MAX : v - NB_MAX * NB_MAX;
-    const int j = v < NB_MAX * NB_MAX ? v % NB_MAX : -1;
-    if (i >= bd.na) continue;
-    if (j >= 0 && (j >= bd.nb || vec_only)) continue;
-    if (j < 0 && !(bd.diag || vec_only)) continue;
-    double tot = 0.0;
-    for (int k = 0; k < bd.nitem; ++k) tot += part[(long long)(bd.item0 + k) * BLK_VALS + v];
-    if (j < 0) {
-      atomicAdd(&g[sa[i]], gsign * tot);
-    } else {
-      atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
-      if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
-    }
+  if (j < 0) {
+    atomicAdd(&g[sa[i]], gsign * tot);
+  } else {
+    atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
+    if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
   }
 }
 

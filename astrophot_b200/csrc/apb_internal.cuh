@@ -40,6 +40,12 @@ struct DevSrc {
   int spw, sph;            // shifted stamp size
   double S[4], Sinv[4], rij[2], rxy[2], area;
   int same_geo;            // forward and jacobian geometry identical
+  // FFT convolution (apb_fft.cuh); conv_fft = 0: tiled direct convolution
+  int conv_fft;
+  int fftx, ffty;          // FftDesc index of the row / column transform
+  int fft_nx, nxh, nxp;    // row length, nx/2+1, padded spectrum row stride (cpx)
+  int fft_nf, fft_nc;      // complex row FFTs per CTA, columns per CTA
+  long long specA_off, specB_off, specK_off, specKT_off;  // cpx offsets into the spectrum arena
 };
 
 // per-call, per-source values

@@ -17,7 +17,7 @@ struct Queues {
   Level lv[APB_MAX_DEPTH + 1];  // index by depth (1-based)
   int* count;                   // [APB_MAX_DEPTH + 2] entries per depth, device
   int* overflow;                // device flag
-  int cap;
+  int cap[APB_MAX_DEPTH + 2];   // entries allocated per depth
   int NVp;                      // planes carried per entry in this pass
 };
 
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_select(const DevSrc* __restrict__ src, 
   base = __shfl_sync(0xffffffffu, base, 0);
   if (sel) {
     const int e = base + __popc(bal & ((1u << lane) - 1));
-    if (e < q.cap) {
+    if (e < q.cap[1]) {
       Level& L = q.lv[1];
       L.src[e] = t.x;
       L.x[e] = X;
@@ -404,7 +404,7 @@ __device__ __forceinline__ bool refine_entry(const DevSrc& s, const DevDyn& d, i
 template <bool GRAD>
 __global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                 int mode, int depth, Queues q) {
-  const int n = min(q.count[depth], q.cap);
+  const int n = min(q.count[depth], q.cap[depth]);
   const Level& L = q.lv[depth];
   const int lane = threadIdx.x & 31;
   // whole warps iterate together so the ballot below is well defined
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, 
     if (split) {
       const DevSrc& s = src[si];
       const int first = wbase + pre - nchild;
-      if (first + nchild <= q.cap) {
+      if (first + nchild <= q.cap[depth + 1]) {
         L.child[t] = first;
         const Level& C = q.lv[depth + 1];
         const int G = s.gridding;
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, 
 
 // children -> parent sums, in child order (operations.py:245), deepest level first
 __global__ void k_reduce_level(const DevSrc* __restrict__ src, int depth, Queues q) {
-  const int n = min(q.count[depth], q.cap);
+  const int n = min(q.count[depth], q.cap[depth]);
   const Level& L = q.lv[depth];
   const Level& C = q.lv[depth + 1];
   const long long total = (long long)n * q.NVp;
@@ -491,7 +491,7 @@ __global__ void k_reduce_level(const DevSrc* __restrict__ src, int depth, Queues
 
 // depth-1 results -> stamp planes
 __global__ void k_scatter(const DevSrc* __restrict__ src, Queues q, double* __restrict__ stamp, int grad) {
-  const int n = min(q.count[1], q.cap);
+  const int n = min(q.count[1], q.cap[1]);
   const Level& L = q.lv[1];
   const long long total = (long long)n * q.NVp;
   for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total; w += (long long)gridDim.x * blockDim.x) {

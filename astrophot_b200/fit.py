@@ -76,6 +76,10 @@ class BaseOptimizer:
         return np.min(np.array(self.loss_history)[ok])
 
 
+class _QueueOverflow(Exception):
+    """A sub-pixel refinement queue overflowed on the device: grow it and redo the work."""
+
+
 class LM(BaseOptimizer):
     """Levenberg-Marquardt with geodesic-acceleration curvature control."""
 
@@ -113,7 +117,7 @@ class LM(BaseOptimizer):
             t = torch.tensor([float(n_keep)], dtype=torch.float64, device=AP_config.ap_device)
             torch.distributed.all_reduce(t, group=self.group)
             n_keep = int(t.item())
-        self.plan = Plan(scene)
+        self.plan = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0))   # conv: force "direct"/"fft" (tests, benchmarks)
         self._covariance_matrix = None
         P = len(self.current_state)
         self.ndf = max(1.0, n_keep - P) if ndf is None else ndf
@@ -142,15 +146,21 @@ class LM(BaseOptimizer):
     def _chi2_record(self, x):
         """chi^2/ndf (host float) of the model at x."""
         self.n_forward += 1
-        out = self._allreduce_chi(self.plan.chi2(x, out=self._c2))
-        c, ok = out.tolist()
-        return c / self.ndf if ok >= 1.0 else float("nan")
+        for _ in range(12):
+            out = self._allreduce_chi(self.plan.chi2(x, out=self._c2))
+            c, ok = out.tolist()
+            if ok >= 0.0:
+                return c / self.ndf if ok >= 1.0 else float("nan")
+            self.plan.reserve()
+        raise OptimizeStop("sub-pixel refinement queues keep overflowing")
 
     def _allreduce_chi(self, c2):
         if self.distributed:
-            c2[1] = 1.0 - c2[1]          # count of ranks with non-finite pixels
-            torch.distributed.all_reduce(c2, group=self.group)
-            c2[1] = (c2[1] == 0).to(c2.dtype)
+            # per-rank flag: 1 ok, 0 non-finite, -1 queue overflow -> summed as (bad, overflow) counts
+            rec = torch.stack([c2[0], (c2[1] == 0).to(c2.dtype), (c2[1] < 0).to(c2.dtype)])
+            torch.distributed.all_reduce(rec, group=self.group)
+            c2[0] = rec[0]
+            c2[1] = torch.where(rec[2] > 0, -1.0, (rec[1] == 0).to(c2.dtype))
         return c2
 
     def _solve(self, L, rhs):
@@ -167,8 +177,20 @@ class LM(BaseOptimizer):
 
     @torch.no_grad()
     def step(self, chi2):
-        """One LM iteration: normal equations once, then search over the damping
-        parameter (reference: `fit/lm.py:248-357`)."""
+        """One LM iteration (reference: `fit/lm.py:248-357`).  If the device reports a
+        refinement-queue overflow the queues are grown and the iteration is redone from its
+        (unchanged) starting state."""
+        L0 = self.L
+        for _ in range(12):
+            try:
+                return self._step(chi2)
+            except _QueueOverflow:
+                self.plan.reserve()
+                self.L = L0
+        raise OptimizeStop("sub-pixel refinement queues keep overflowing")
+
+    def _step(self, chi2):
+        """Normal equations once, then search over the damping parameter."""
         x = self.current_state
         self.plan.normal_eq(x, as_rep=True, out=(self._H, self._g, self._c2))
         self.n_forward += 1
@@ -199,6 +221,8 @@ class LM(BaseOptimizer):
             self._rec[2] = torch.linalg.norm(a)
             self._rec[3] = torch.linalg.norm(h)
             csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
+            if ok < 0.0:
+                raise _QueueOverflow()
             chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
             if self.verbose > 1:
                 AP_config.ap_logger.info(f"sub step L: {self.L}, Chi^2/DoF: {chi2}")
@@ -301,9 +325,9 @@ class LM(BaseOptimizer):
     def update_hess_grad(self, natural=False):
         if natural:
             xv = self.model.parameters.vector_transform_rep_to_val(self.current_state.detach().cpu())
-            H, g, _ = self.plan.normal_eq(xv, as_rep=False)
+            H, g, _ = self.plan.normal_eq(xv, as_rep=False, check=True)
         else:
-            H, g, _ = self.plan.normal_eq(self.current_state, as_rep=True)
+            H, g, _ = self.plan.normal_eq(self.current_state, as_rep=True, check=True)
         if self.distributed:
             self._allreduce(H)
             self._allreduce(g)

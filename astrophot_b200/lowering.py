@@ -273,7 +273,8 @@ def lower(model, window=None, for_fit=False):
             quad_level=int(comp.integrate_quad_level), gridding=int(comp.integrate_gridding),
             max_depth=int(comp.integrate_max_depth), tolerance=float(comp.sampling_tolerance),
             softening=float(comp.softening), ref_mode=comp._ref_mode, psf=pidx,
-            psf_shift=_shift_code(comp.psf_subpixel_shift), name=comp.name))
+            psf_shift=_shift_code(comp.psf_subpixel_shift),
+            conv_mode=sc.CONV_DIRECT if comp.psf_convolve_mode == "direct" else sc.CONV_AUTO, name=comp.name))
         info.components.append(comp)
 
     scene = sc.Scene(images=images, sources=sources, psfs=psfs,

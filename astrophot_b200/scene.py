@@ -26,6 +26,7 @@ INTEGRATE_NONE, INTEGRATE_THRESHOLD = range(2)
 REF_MEAN, REF_SERSIC_FLUX = range(2)
 SHIFT_NONE, SHIFT_BILINEAR = 0, 1   # SHIFT_LANCZOS + order = 10 + order
 SHIFT_LANCZOS = 10
+CONV_AUTO, CONV_DIRECT, CONV_FFT = range(3)   # psf_convolve_mode: "fft" -> AUTO (fastest), "direct" -> DIRECT
 
 MAX_ELEM = 24
 MAX_PROF = 20
@@ -82,6 +83,7 @@ class SceneSource:
     ref_mode: int = REF_MEAN
     psf: int = -1
     psf_shift: int = SHIFT_BILINEAR
+    conv_mode: int = CONV_AUTO
     name: str = ""
 
     @property

@@ -100,12 +100,19 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 10.0:     # nvidia-smi needs ~1 s to print its first row
+                time.sleep(0.05)
         except Exception:
             self.proc = None
         return self
+
+    def mark(self):
+        """Index of the next sample: samples[mark0:mark1] were taken inside a region."""
+        return len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -119,9 +126,12 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    def summary(self):
+    def summary(self, lo=0, hi=None):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[lo:hi]
+        if not rows:                       # region shorter than one sampling period: nearest samples
+            rows = self.rows[max(0, lo - 1):(hi or len(self.rows)) + 1]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -198,6 +208,61 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------
+# algorithmic work of the kernels on config[1] (one PSF-convolved Sersic), summed over the timed
+# region: n_fwd value-only sampling passes and n_jac value+derivative passes
+# ---------------------------------------------------------------------------
+def _fft_len(n):
+    m = max(n, 2)
+    while True:
+        r, b, c = m, 0, 0
+        while r % 2 == 0:
+            r //= 2
+        while r % 3 == 0 and b < 3:
+            r //= 3
+            b += 1
+        while r % 5 == 0 and c < 1:
+            r //= 5
+            c += 1
+        if r == 1:
+            return m
+        m += 1
+
+
+def algorithmic_work(src, n_fwd, n_jac, n_geo=0):
+    ow, oh = src.out[2], src.out[3]
+    spw = PSF_W + 2                       # bilinear-shifted stamp keeps its 1-px pad
+    b = (PSF_W + 2) // 2                  # psf_border_int = ceil((P+1)/2)
+    ew, eh = ow + 2 * b, oh + 2 * b
+    n_act = sum(1 for sl in src.slot if sl >= 0)
+    nx, ny = _fft_len(ew), _fft_len(eh)
+    nxh = nx // 2 + 1
+    px = ow * oh
+    # planes per pass: value-only: 1 image plane, 1 PSF plane, 1 product; derivative pass: value + (n_act-2)
+    # non-centre planes in, 3 PSF planes (K, dK/dcx, dK/dcy), 1 + n_act products out
+    in_f, k_f, j_f = 1, 1, 1
+    in_j, k_j, j_j = 1 + (n_act - 2), 3, 1 + n_act
+    tot = lambda f, j: n_fwd * f + n_jac * j
+    rows = lambda n_in, n_k: n_in * (eh * ew * 8 + eh * nxh * 16) + n_k * (spw * spw * 8 + spw * nxh * 16)
+    cols = lambda n_k, n_j: n_k * (spw * nxh * 16 + nxh * ny * 16) + n_j * (eh * nxh * 16 + nxh * ny * 16 + oh * nxh * 16)
+    inv = lambda n_j: n_j * (oh * nxh * 16 + px * 8)
+    planes = tot(j_f, j_j)
+    return {
+        "k_conv": {"bound": "fp64", "flops": 2.0 * spw * spw * px * planes,
+                   "what": f"2*{spw}^2 flop x {px} px x {planes} planes"},
+        "k_fft_rows": {"bound": "hbm", "bytes": float(tot(rows(in_f, k_f), rows(in_j, k_j))),
+                       "what": f"real rows in (8 B/px) + half spectra out (16 B x {nxh}/row), {nx}-point rows"},
+        "k_fft_cols": {"bound": "hbm", "bytes": float(tot(cols(k_f, j_f), cols(k_j, j_j))),
+                       "what": f"per product: read {eh}x{nxh} spectrum + {nxh}x{ny} PSF spectrum, write {oh}x{nxh}; 16 B each"},
+        "k_fft_rows_inv": {"bound": "hbm", "bytes": float(tot(inv(j_f), inv(j_j))),
+                           "what": f"half spectra in (16 B x {nxh}/row) + real rows out (8 B/px)"},
+        # normal equations: (n_act planes + weight + residual) x 8 B + mask per pixel, once per build
+        "k_blocks": {"bound": "hbm", "bytes": float(n_jac * px * ((n_act + 2) * 8 + 1) + n_geo * px * ((n_act + 1) * 8 + 1)),
+                     "what": f"J^T W J build: {n_act} derivative planes + weight + residual (8 B) + mask per pixel; "
+                             f"geodesic J^T v: {n_act} planes + v + mask per pixel"},
+    }
+
+
+# ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
 def run_ours(args):
@@ -232,7 +297,8 @@ def run_ours(args):
     model = build_joint(ap, n_bands, datas)
     x_true = model.parameters.vector_representation().numpy()
     x0 = start_state(x_true)
-    lm = ap.fit.LM(model, initial_state=x0, max_iter=10**6, relative_tolerance=0.0, distributed=(world > 1))
+    lm = ap.fit.LM(model, initial_state=x0, max_iter=10**6, relative_tolerance=0.0, distributed=(world > 1),
+                   conv=args.conv)
     plan = lm.plan
     n_pix_local = sum(h * w for h, w in plan.shapes)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
@@ -270,7 +336,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.__enter__()          # sampling spans warm-up, the timed region and the e2e region (all under load)
     reset()
+    m0 = clocks.mark()
     for _ in range(args.warmup):
         one_iteration()
     barrier()
@@ -279,17 +348,16 @@ def run_ours(args):
     plan.profile(True)
     plan.profile_read(reset=True)
     launches0 = cabi.launch_count()
-    trials0, fwd0 = lm.n_trials, lm.n_forward
+    trials0, fwd0, jac0 = lm.n_trials, lm.n_forward, lm.n_jacobian
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
         barrier()
-        for k in range(args.steps):
-            flush.zero_()
-            barrier()
-            ev[k][0].record()
-            one_iteration()
-            ev[k][1].record()
-        barrier()
+        ev[k][0].record()
+        one_iteration()
+        ev[k][1].record()
+    barrier()
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms_steps))
     kern = plan.profile_read(reset=True)
@@ -297,6 +365,7 @@ def run_ours(args):
     launches = cabi.launch_count() - launches0
     trials = lm.n_trials - trials0
     forwards = lm.n_forward - fwd0
+    jacobians = lm.n_jacobian - jac0
     st = plan.stats()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,6 +394,9 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         e2e_ms += e0.elapsed_time(e1)
+    m1 = clocks.mark()
+    clocks.__exit__()
+    clock_summary = clocks.summary(m0, m1)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -336,34 +408,52 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (algorithmic work per DESIGN.md §4 / SURVEY.md §8d)
     dfma_tflops, copy_gbs = cabi.bench_peaks()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    hbm_peak = None
+    for key in ("hbm_gbs", "hbm_copy_gbs", "hbm_gbs_burst", "hbm_burst_gbs"):
+        if isinstance(peaks.get(key), (int, float)):
+            hbm_peak = float(peaks[key])
+            break
+    hbm_src = "MEASURED_PEAKS.json" if hbm_peak else "apb_bench_peaks fp64 copy measured in this run (MEASURED_PEAKS.json absent)"
+    hbm_peak = hbm_peak or copy_gbs
     top = max(kern.items(), key=lambda kv: kv[1][1]) if kern else ("none", (0, 0.0))
     name, (n_launch, k_ms) = top
-    spw = PSF_W + 2
-    src0 = plan.scene.sources[0]
+    work = algorithmic_work(plan.scene.sources[0], n_fwd=forwards - jacobians, n_jac=jacobians, n_geo=trials)
     roof = {"kernel": name, "launches": n_launch, "avg_ms": k_ms / max(n_launch, 1),
             "share_of_step": k_ms / max(sum(v[1] for v in kern.values()), 1e-9)}
-    if name == "k_conv":
-        # direct convolution = 2 P^2 flop per output pixel per image (P = shifted stamp, 53);
-        # launches alternate between 1-image (forward) and (1 + n_act)-image (Jacobian) batches
-        px = src0.out[2] * src0.out[3]
-        n_jac = lm.n_jacobian
-        imgs_total = forwards + 7 * args.steps    # every forward convolves 1 plane; each Jacobian build 7 more
-        flops = 2.0 * spw * spw * px * imgs_total
-        ach = flops / (k_ms * 1e-3) / 1e12
+    w = work.get(name)
+    traffic = None
+    try:   # dram bytes per launch from the committed ncu --set full capture of this command
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+    except Exception:
+        pass
+    if w is None:
+        roof.update({"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": traffic})
+    elif w["bound"] == "fp64":
+        ach = w["flops"] / (k_ms * 1e-3) / 1e12
         roof.update({"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
-                     "traffic": None, "peak_source": "apb_bench_peaks DFMA stream measured in this run "
-                     "(MEASURED_PEAKS.json has no fp64 figure; nominal 37.2)",
-                     "algorithmic": f"2*{spw}^2 flop x {px} px x {imgs_total} planes"})
+                     "traffic": traffic, "peak_source": "apb_bench_peaks DFMA stream measured in this run "
+                     "(MEASURED_PEAKS.json has no fp64 figure; nominal 37.2)", "algorithmic": w["what"]})
     else:
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        roof.update({"bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None})
+        ach = w["bytes"] / (k_ms * 1e-3) / 1e9
+        roof.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                     "traffic": traffic, "peak_source": hbm_src, "algorithmic": w["what"],
+                     "algorithmic_bytes_per_launch": w["bytes"] / max(n_launch, 1)})
+    roof_all = {}
+    for kname, (nl, ms) in kern.items():
+        ww = work.get(kname)
+        if ww is None or ms <= 0:
+            continue
+        if ww["bound"] == "fp64":
+            roof_all[kname] = {"frac": ww["flops"] / (ms * 1e-3) / 1e12 / dfma_tflops, "bound": "fp64"}
+        else:
+            roof_all[kname] = {"frac": ww["bytes"] / (ms * 1e-3) / 1e9 / hbm_peak, "bound": "hbm"}
 
     # ---- CPU baseline (bounded sample: one full-size LM iteration of the oracle port)
     cpu = None
@@ -382,10 +472,11 @@ def run_ours(args):
                    "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
                    "params": len(x0), "lambda_trials_per_iter": trials / args.steps, "forwards_per_iter": forwards / args.steps,
                    "fit_restarts": state["restarts"]},
-        "clocks": clocks.summary(),
+        "clocks": clock_summary,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_pin.numel() * 8},
         "gpu_launches": launches,
         "roofline": roof,
+        "roofline_all": {k: {"bound": v["bound"], "frac": round(v["frac"], 4)} for k, v in roof_all.items()},
         "cpu_baseline": cpu,
         "mpix_per_s_sampled": n_bands * forwards * (n_pix_local / 1e6) / (total_ms * 1e-3),
         "kernel_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])},
@@ -400,10 +491,12 @@ def run_ours(args):
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
-    ap_.add_argument("--steps", type=int, default=20)
-    ap_.add_argument("--warmup", type=int, default=3)
+    ap_.add_argument("--steps", type=int, default=100)
+    ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap_.add_argument("--conv", default=None, choices=["direct", "fft"],
+                     help="force one PSF-convolution kernel family (default: automatic, FFT for the 51x51 PSF)")
     args = ap_.parse_args()
     if args.impl == "reference":
         run_reference(args)

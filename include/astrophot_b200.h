@@ -52,6 +52,9 @@ enum { APB_SAMPLE_MIDPOINT = 0, APB_SAMPLE_SIMPSONS, APB_SAMPLE_QUAD, APB_SAMPLE
 enum { APB_INTEGRATE_NONE = 0, APB_INTEGRATE_THRESHOLD };                                  /* _model_methods.py:155-184 */
 enum { APB_REF_MEAN = 0, APB_REF_SERSIC_FLUX }; /* _model_methods.py:151-152, sersic_model.py:87-89 */
 enum { APB_SHIFT_NONE = 0, APB_SHIFT_BILINEAR = 1 }; /* _model_methods.py:187-230 */
+/* "fft" in the reference = APB_CONV_AUTO here (tiled direct convolution for small stamps, FFT for
+ * large ones: same valid region, utils/operations.py:9-36); "direct" = APB_CONV_DIRECT */
+enum { APB_CONV_AUTO = 0, APB_CONV_DIRECT = 1, APB_CONV_FFT = 2 };
 
 typedef struct apb_plan apb_plan_t;
 
@@ -91,13 +94,14 @@ typedef struct {
   int32_t n_prof;
   double prof[APB_MAX_PROF];  /* spline node radii                                    */
   int32_t sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth;
-  int32_t ref_mode, psf, psf_shift, _pad;
+  int32_t ref_mode, psf, psf_shift;
+  int32_t conv_mode; /* APB_CONV_*: psf_convolve_mode (_model_methods.py:245-255) */
   double tolerance, softening;
 } apb_source_t;
 
 typedef struct {
-  int64_t queue_capacity; /* entries per refinement level; 0 = automatic  */
-  int32_t flags;          /* reserved                                      */
+  int64_t queue_capacity; /* entries per refinement level; 0 = automatic (grown by apb_plan_reserve) */
+  int32_t flags;          /* bits 0-1: APB_CONV_* override for every source */
   int32_t _pad;
 } apb_opts_t;
 
@@ -133,7 +137,7 @@ int apb_jacobian(apb_plan_t *plan, const double *x, int as_rep, double *const *j
  * all over unmasked pixels.  The per-source stamp Jacobian stays cached in the plan for
  * apb_geodesic.  All outputs device pointers. */
 int apb_normal_eq(apb_plan_t *plan, const double *x_rep, int as_rep, double *JtWJ, double *JtWr,
-                  double *chi2, void *stream);
+                  double *chi2 /* 2 doubles: chi^2, status flag as in apb_chi2 */, void *stream);
 
 /* fit/lm.py:277-281,401-406:  rpp = J^T [ (2/d) ( (W (Y(x + d h) - Y) - r)/d - W (J h) ) ]
  * with J, r from the last apb_normal_eq.  xdh = x + d*h (device, n_par), h device. */
@@ -141,8 +145,16 @@ int apb_geodesic(apb_plan_t *plan, const double *xdh_rep, const double *h, doubl
                  void *stream);
 
 /* fit/lm.py:289-293,373-378: out[0] = sum W (Y - model(x))^2 over unmasked pixels,
- * out[1] = 1.0 if every model pixel is finite else 0.0.  (Caller divides by ndf.) */
+ * out[1] = 1.0 if every model pixel is finite, 0.0 if not, -1.0 if a sub-pixel refinement queue
+ * overflowed in this or an earlier call (sticky; results invalid: call apb_plan_reserve and repeat).
+ * (Caller divides by ndf.) */
 int apb_chi2(apb_plan_t *plan, const double *x_rep, double *out2, void *stream);
+
+/* The adaptive integration (utils/operations.py:150-247) queues re-gridded sub-pixels per depth;
+ * depth 1 is bounded by the pixel count, deeper levels are sized heuristically.  After an
+ * overflow, grow the queues: caps[d], d = 1..APB_MAX_DEPTH, entries wanted at depth d (0 = keep),
+ * or NULL to size from the counts of the last call.  Clears the overflow flag.  Synchronous. */
+int apb_plan_reserve(apb_plan_t *plan, const int64_t *caps);
 
 /* fit/lm.py:359-371:  solve (H o (I + (1-I)/(1+L)) + L I (1 + diag H)) h = g.
  * H: device P*P (not modified), g, h: device P.  info: device int, 0 ok. */

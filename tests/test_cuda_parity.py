@@ -14,9 +14,87 @@ from conftest import load_golden, golden_data, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _plan(scene):
+def _plan(scene, conv=None):
     from astrophot_b200.cabi import Plan
-    return Plan(scene)
+    return Plan(scene, conv=conv)
+
+
+PSF_SCENES = ["psf_sersic", "psf_sersic_noshift", "group", "group_nosky", "joint", "crowded"]
+
+
+@pytest.mark.parametrize("name", PSF_SCENES)
+def test_fft_convolution_path(name):
+    """Force the shared-memory FFT convolution (the goldens' PSFs are small enough that the
+    automatic choice is the direct tile kernel) and hold it to the same bars."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name)
+    scene, info = lower(model)
+    plan = _plan(scene, conv="fft")
+    got = [t.cpu().numpy() for t in plan.sample(fix["x_val"], as_rep=False)]
+    want = orc.sample(scene, fix["x_val"], as_rep=False)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert rel_err(g, w) < 1e-10, (name, "oracle")
+        assert rel_err(g, fix[f"img{i}"]) < 1e-10, (name, "reference golden")
+    J = [t.cpu().numpy() for t in plan.jacobian(fix["x_rep"], as_rep=True)]
+    Jf = np.concatenate([j.reshape(-1, j.shape[-1]) for j in J])
+    ref = fix["jac_rep"]
+    rs = np.maximum(np.abs(ref).max(axis=0), 1e-300)
+    assert np.max(np.abs(Jf[fix["jac_idx"]] - ref) / rs) < 1e-9, (name, "reference golden")
+    Jd = [t.cpu().numpy() for t in _plan(scene, conv="direct").jacobian(fix["x_rep"], as_rep=True)]
+    Jdf = np.concatenate([j.reshape(-1, j.shape[-1]) for j in Jd])
+    scale = np.maximum(np.abs(Jdf).max(axis=0), 1e-300)
+    assert np.max(np.abs(Jf - Jdf) / scale) < 1e-12, (name, "fft vs direct")
+
+
+def test_fft_convolution_large_psf_and_lm():
+    """51x51 PSF on a 200x180 image (padded stamp 252 x 232 -> transform lengths 256 = 2^8 and
+    240 = 2^4.3.5): automatic choice is FFT; the LM trajectory must equal the direct-convolution one."""
+    rng = np.random.default_rng(5)
+    psf = ap.image.PSF_Image(data=ap.utils.moffat_psf(2.5, 3.0, 51, 1.0), pixelscale=1.0)
+    pars = {"center": [101.3, 88.6], "q": 0.6, "PA": 1.0, "n": 2.5, "Re": 14.0, "Ie": 1.0}
+
+    def build(data=None, var=None):
+        kw = {} if var is None else {"variance": var}
+        tar = ap.image.Target_Image(data=np.zeros((180, 200)) if data is None else data, pixelscale=1.0,
+                                    zeropoint=22.5, psf=psf, **kw)
+        return ap.models.AstroPhot_Model(name="big", model_type="sersic galaxy model", target=tar, psf_mode="full",
+                                         parameters=dict(pars))
+
+    m = build()
+    scene, _ = lower(m)
+    xv = m.parameters.vector_values().numpy()
+    a = _plan(scene).sample(xv)[0].cpu().numpy()            # auto -> FFT
+    b = _plan(scene, conv="direct").sample(xv)[0].cpu().numpy()
+    w = orc.sample(scene, xv, as_rep=False)[0]
+    assert rel_err(a, w) < 1e-10 and rel_err(b, w) < 1e-10
+    assert rel_err(a, b) < 1e-13
+    var = 0.01 + w / 100
+    data = w + rng.normal(size=w.shape) * np.sqrt(var)
+    x0 = build().parameters.vector_representation().numpy() + 0.05 * rng.normal(size=7)
+    r1 = ap.fit.LM(build(data, var), initial_state=x0, max_iter=5, relative_tolerance=0.0).fit()
+    r2 = ap.fit.LM(build(data, var), initial_state=x0, max_iter=5, relative_tolerance=0.0, conv="direct").fit()
+    np.testing.assert_allclose(r1.loss_history[:4], r2.loss_history[:4], rtol=1e-10)
+    np.testing.assert_allclose(r1.lambda_history[3], r2.lambda_history[3], rtol=1e-9, atol=1e-10)
+
+
+def test_refinement_queue_grows_on_overflow():
+    """Start with absurdly small refinement queues: sample / jacobian / LM must notice the sticky
+    overflow flag, grow the queues (apb_plan_reserve) and still reproduce the reference."""
+    from astrophot_b200.cabi import Plan
+    fix = load_golden("c1_sersic")
+    model, _ = scenes.build(ap, "c1_sersic")
+    scene, _ = lower(model)
+    plan = Plan(scene, queue_capacity=64)
+    got = plan.sample(fix["x_val"], as_rep=False)[0].cpu().numpy()
+    assert rel_err(got, fix["img0"]) < 1e-10
+    assert plan.stats()["overflow"] == 0
+    J = plan.jacobian(fix["x_rep"], as_rep=True)[0].cpu().numpy().reshape(-1, 7)
+    ref = fix["jac_rep"]
+    rs = np.maximum(np.abs(ref).max(axis=0), 1e-300)
+    assert np.max(np.abs(J[fix["jac_idx"]] - ref) / rs) < 1e-9
+    model, _ = scenes.build(ap, "c1_sersic", data=golden_data(fix))
+    res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=4, relative_tolerance=0.0, queue_capacity=64).fit()
+    np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-8)
 
 
 @pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
