@@ -58,7 +58,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_lm_trial", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -90,6 +90,7 @@ def load_library(path=None):
     L.apb_geodesic.argtypes = [vp, dp, dp, C.c_double, dp, vp]
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
+    L.apb_lm_trial.argtypes = [vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
     L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
     L.apb_plan_reserve.argtypes = [vp, C.POINTER(C.c_int64)]
     L.apb_profile.argtypes = [vp, C.c_int]
@@ -135,7 +136,7 @@ def _dev_f64(x):
 class Plan:
     """A lowered model tree resident on the device (``apb_plan_t``)."""
 
-    def __init__(self, scene, queue_capacity=0, conv=None):
+    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True):
         """``conv``: None (per-source psf_convolve_mode), "direct" or "fft" to force one
         convolution kernel family for every source (tests, benchmarks)."""
         _require_cuda()
@@ -193,7 +194,7 @@ class Plan:
             c.ref_mode, c.psf, c.psf_shift = s.ref_mode, s.psf, s.psf_shift
             c.conv_mode = int(getattr(s, "conv_mode", 0))
             c.tolerance, c.softening = s.tolerance, s.softening
-        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv])
+        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4))
         handle = C.c_void_p()
         _check(L.apb_plan_create(srcs, n_src, imgs, n_img, psfs, n_psf, pars, self.n_par, C.byref(opts),
                                  C.byref(handle)), "apb_plan_create")
@@ -280,6 +281,13 @@ class Plan:
                "apb_geodesic")
         return out
 
+    def lm_trial(self, H, g, L, x, d, acceleration, h_out, ha_out, rec):
+        """One lambda-trial on the device (fit/lm.py:274-293); rec <- [chi2, flag, |a|, |h|]."""
+        _check(self._L.apb_lm_trial(self._h, H.data_ptr(), g.data_ptr(), float(L), x.data_ptr(), float(d),
+                                    float(acceleration), h_out.data_ptr(), ha_out.data_ptr(), rec.data_ptr(), _stream()),
+               "apb_lm_trial")
+        return rec
+
     def chi2(self, x, out=None):
         """(sum W (Y - model)^2, finite flag) as a 2-element device tensor."""
         x = self._x(x)
@@ -316,6 +324,11 @@ def lm_solve(H, g, L, out=None, info=None):
     _check(lib().apb_lm_solve(H.data_ptr(), g.data_ptr(), float(L), int(P), out.data_ptr(), info.data_ptr(),
                               _stream()), "apb_lm_solve")
     return out
+
+
+def fft_length(n):
+    """Transform length the FFT convolution picks for a padded stamp of n pixels."""
+    return int(lib().apb_fft_length(int(n)))
 
 
 def launch_count():

@@ -40,11 +40,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -63,7 +63,8 @@ struct ModeTables {
 
 // FFT-convolution work lists; independent of the sampling mode (the evaluation region is)
 struct FftTables {
-  int4* rows = nullptr; int n_rows = 0;          // {src, plane | -1-k, row0, nrows}
+  int4* rows = nullptr; int n_rows = 0;          // image rows {src, plane, row0, nrows}
+  int4* rows_psf = nullptr; int n_rows_psf = 0;  // PSF rows {src, -1-k, row0, nrows}
   int4* jobs = nullptr;                          // {src, in_plane | -1-k, kernel, out_plane}
   int4* cols_psf = nullptr; int n_cols_psf = 0;  // {job, kx0, ncols, 0}
   int4* cols_img = nullptr; int n_cols_img = 0;
@@ -84,13 +85,19 @@ struct apb_plan {
   FftDesc* d_fftdesc = nullptr;
   cpx *d_twid = nullptr, *d_spec = nullptr;
   size_t fft_smem_rows = 0, fft_smem_cols = 0;
+  int fft_nt_rows = 256, fft_nt_cols = 256;   // threads per CTA of the row / column kernels
   int n_fft_src = 0;
+  cudaStream_t side = nullptr;        // PSF branch (stamp + spectrum) runs here, concurrent with the profile sampling
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int* psf_list = nullptr; int n_psf_list = 0;      // sources needing a shifted PSF stamp
   int* point_list = nullptr; int n_point = 0;
   int* norm_list = nullptr; int n_norm = 0;
   bool any_threshold = false, all_same_geo = true;
   int max_depth = 1;
   int NVp_grad = 1;
+  bool use_coop = false;           // fused integration kernel (k_integrate) instead of per-depth launches
+  int refine_lanes = 16;           // lanes sharing one queue entry
+  int integrate_grid = 148 * 4;    // persistent CTAs of k_integrate (one resident wave)
   // arenas
   double *d_stamp = nullptr, *d_out = nullptr, *d_psfst = nullptr, *d_meanpart = nullptr, *d_skyJ = nullptr;
   // queues
@@ -110,7 +117,7 @@ struct apb_plan {
   BlockDesc* d_vblocks = nullptr; int n_vblocks = 0;
   int *d_act_slot = nullptr, *d_act_off = nullptr;
   double* d_part = nullptr;
-  double* d_xtmp = nullptr;
+  double *d_xtmp = nullptr, *d_xtmp2 = nullptr, *d_rpp = nullptr, *d_atmp = nullptr;
   apb_stats_t stats{};
   long long launches = 0;
   cudaStream_t last_stream = nullptr;
@@ -140,6 +147,8 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 
 extern "C" const char* apb_last_error(void) { return g_err.c_str(); }
+static int fft_len(int n);
+extern "C" int apb_fft_length(int n) { return n > 0 ? fft_len(n) : 0; }
 extern "C" int apb_version(void) { return 100; }
 
 static void gauss_legendre(int n, double* x, double* w) {
@@ -175,33 +184,44 @@ static void set_geo(Geo& g, const int* out, const int* work, int bx, int by, boo
   g.tile0 = g.ntile = g.chunk0 = g.nchunk = 0;
 }
 
-// smallest 2^a 3^b 5^c >= n (b <= 3, c <= 1: keeps the odd-radix stages few)
-static int fft_len(int n) {
-  for (int m = std::max(n, 2);; ++m) {
-    int r = m, b = 0, c = 0;
-    while (r % 2 == 0) r /= 2;
-    while (r % 3 == 0 && b < 3) { r /= 3; ++b; }
-    while (r % 5 == 0 && c < 1) { r /= 5; ++c; }
-    if (r == 1) return m;
-  }
-}
-
+// Stage radices of a length-N transform: 16s first (their index arithmetic is shifts and masks),
+// then the remaining power of two, then 9/3/5.
 static FftDesc fft_desc(int N) {
   FftDesc D;
   memset(&D, 0, sizeof(D));
   D.N = N;
   int n = N;
-  // power-of-two stages first: their index arithmetic is shifts and masks
-  while (n % 4 == 0) { D.radix[D.nstage++] = 4; n /= 4; }
-  while (n % 2 == 0) { D.radix[D.nstage++] = 2; n /= 2; }
+  while (n % 16 == 0) { D.radix[D.nstage++] = 16; n /= 16; }
+  if (n % 8 == 0) { D.radix[D.nstage++] = 8; n /= 8; }
+  if (n % 4 == 0) { D.radix[D.nstage++] = 4; n /= 4; }
+  if (n % 2 == 0) { D.radix[D.nstage++] = 2; n /= 2; }
+  while (n % 9 == 0) { D.radix[D.nstage++] = 9; n /= 9; }
   while (n % 3 == 0) { D.radix[D.nstage++] = 3; n /= 3; }
   while (n % 5 == 0) { D.radix[D.nstage++] = 5; n /= 5; }
+  if (n != 1) D.nstage = 0;   // not 2-3-5 smooth
   return D;
+}
+
+// transform length for a padded stamp of n pixels: the 5-smooth m in [n, 1.3 n] with the lowest
+// m * (stages + 1.5) (every stage is one shared-memory exchange of the whole sequence)
+static int fft_len(int n) {
+  int best = 0;
+  double best_cost = 0.0;
+  for (int m = std::max(n, 2); m <= std::max(n, 2) * 13 / 10 + 16; ++m) {
+    const FftDesc D = fft_desc(m);
+    if (D.nstage == 0 || D.nstage > APB_FFT_MAX_STAGE) continue;
+    const double cost = (double)m * (D.nstage + 1.5);
+    if (!best || cost < best_cost) { best = m; best_cost = cost; }
+  }
+  return best;
 }
 
 extern "C" int apb_plan_destroy(apb_plan_t* p) {
   if (!p) return 0;
   for (void* q : p->owned) cudaFree(q);
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   for (int d = 1; d <= APB_MAX_DEPTH; ++d) {
     Level& L = p->q.lv[d];
     void* olds[6] = {L.src, L.x, L.y, L.parent, L.child, L.res};
@@ -395,25 +415,39 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       if (want == 2) {
         const Geo& g = s.geo[0];
         const int Nx = fft_len(g.ew), Ny = fft_len(g.eh);
+        // shared-memory sequences are skewed (FPAD): i -> i + i/16
+        const int ldx = Nx + Nx / 16 + 1, ldy0 = Ny + Ny / 16 + 1;
+        // columns per CTA: as many as keep two CTAs per SM resident (<= 110 KB), at least one
         int nc = 8;
-        auto col_bytes = [&](int c) { return (size_t)(Ny + 2 * c * (Ny + 8 / c)) * sizeof(cpx); };
-        while (nc > 1 && col_bytes(nc) > 110 * 1024) nc /= 2;
-        const int nf = std::max(1, std::min(8, 1024 / Nx));
-        const size_t row_bytes = (size_t)(Nx + 2 * nf * Nx) * sizeof(cpx);
-        if (col_bytes(nc) <= 227 * 1024 && row_bytes <= 227 * 1024) {
+        while (nc > 1 && (size_t)(2 * nc * (ldy0 + 8)) * sizeof(cpx) > 110 * 1024) nc /= 2;
+        // row transforms per CTA (each carries two real rows)
+        int nf = std::max(1, std::min(16, 4096 / Nx));
+        while (nf > 1 && (size_t)(2 * nf * ldx) * sizeof(cpx) > 110 * 1024) --nf;
+        // pad the column tile so that a quarter-warp of the transposing load hits 8 distinct 16-byte banks
+        int pad = 0, best_conf = 1 << 30;
+        for (int pd = 0; pd < 8; ++pd) {
+          int cnt[8] = {0}, conf = 0;
+          for (int l = 0; l < 8; ++l) cnt[((l % nc) * (ldy0 + pd) + l / nc) & 7]++;
+          for (int k = 0; k < 8; ++k) conf = std::max(conf, cnt[k]);
+          if (conf < best_conf) { best_conf = conf; pad = pd; }
+        }
+        const size_t col_bytes = (size_t)(2 * nc * (ldy0 + pad)) * sizeof(cpx);
+        const size_t row_bytes = (size_t)(2 * nf * ldx) * sizeof(cpx);
+        const bool fits = col_bytes <= 227 * 1024 && row_bytes <= 227 * 1024;
+        if (fits) {
           s.conv_fft = 1;
           s.fftx = get_desc(Nx); s.ffty = get_desc(Ny);
           s.fft_nx = Nx; s.nxh = Nx / 2 + 1; s.nxp = (s.nxh + 3) & ~3;
-          s.fft_nf = nf; s.fft_nc = nc;
+          s.fft_nf = nf; s.fft_nc = nc; s.fft_ld = ldy0 + pad;
           s.specA_off = spec_total; spec_total += (long long)(1 + s.n_act) * g.eh * s.nxp;
           s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.oh * s.nxp;
           s.specK_off = spec_total; spec_total += 3LL * s.sph * s.nxp;
           s.specKT_off = spec_total; spec_total += 3LL * s.nxh * Ny;
           p->fft_smem_rows = std::max(p->fft_smem_rows, row_bytes);
-          p->fft_smem_cols = std::max(p->fft_smem_cols, col_bytes(nc));
+          p->fft_smem_cols = std::max(p->fft_smem_cols, col_bytes);
           p->n_fft_src++;
         } else if (conv_force == 2 || a.conv_mode == 2) {
-          PFAIL("stamp too large for the shared-memory FFT convolution");
+          PFAIL("stamp too large for the shared-memory FFT convolution (transform length > ~7000)");
         }
       }
     }
@@ -497,7 +531,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   // ---- FFT convolution work lists
   for (int gr = 0; gr < 2 && p->n_fft_src; ++gr) {
     FftTables& F = p->ft[gr];
-    std::vector<int4> rows, jobs, cpsf, cimg, rinv;
+    std::vector<int4> rows, rpsf, jobs, cpsf, cimg, rinv;
     for (int i = 0; i < n_src; ++i) {
       const DevSrc& s = S[i];
       if (!s.conv_fft) continue;
@@ -521,7 +555,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         }
       for (int k = 0; k < 3; ++k)
         if (need_k[k]) {
-          add_rows(rows, -1 - k, s.sph);
+          add_rows(rpsf, -1 - k, s.sph);
           jobs.push_back(make_int4(i, -1 - k, 0, 0));
           add_cols(cpsf, (int)jobs.size() - 1);
         }
@@ -532,8 +566,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         add_rows(rinv, c.z, s.oh);
       }
     }
-    F.n_rows = (int)rows.size(); F.n_cols_psf = (int)cpsf.size(); F.n_cols_img = (int)cimg.size(); F.n_rows_inv = (int)rinv.size();
+    F.n_rows = (int)rows.size(); F.n_rows_psf = (int)rpsf.size(); F.n_cols_psf = (int)cpsf.size(); F.n_cols_img = (int)cimg.size(); F.n_rows_inv = (int)rinv.size();
     PRC(own_upload(p, rows, &F.rows));
+    PRC(own_upload(p, rpsf, &F.rows_psf));
     PRC(own_upload(p, jobs, &F.jobs));
     PRC(own_upload(p, cpsf, &F.cols_psf));
     PRC(own_upload(p, cimg, &F.cols_img));
@@ -671,6 +706,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   PRC(own_alloc(p, (void**)&p->d_meanpart, sizeof(double) * (size_t)std::max(p->mt[0].n_chunks, p->mt[1].n_chunks)));
   PRC(own_alloc(p, (void**)&p->d_skyJ, sizeof(double) * (size_t)std::max(n_src, 1)));
   PRC(own_alloc(p, (void**)&p->d_xtmp, sizeof(double) * (size_t)std::max(n_par, 1)));
+  PRC(own_alloc(p, (void**)&p->d_xtmp2, sizeof(double) * (size_t)std::max(n_par, 1)));
+  PRC(own_alloc(p, (void**)&p->d_rpp, sizeof(double) * (size_t)std::max(n_par, 1)));
+  PRC(own_alloc(p, (void**)&p->d_atmp, sizeof(double) * (size_t)std::max(n_par, 1)));
   PCU(cudaMemset(p->d_stamp, 0, sizeof(double) * (size_t)std::max<long long>(stamp_total, 1)));
 
   // ---- queues: depth 1 can never hold more than the first-pass pixels; deeper levels start at a
@@ -690,6 +728,27 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       PRC(alloc_queues(p, caps));
     }
   }
+
+  // ---- fused integration kernel (k_integrate): lanes sharing one depth-1 queue entry
+  if (p->any_threshold && !(opts && (opts->flags & 4))) {
+    p->use_coop = true;
+    int qmax = 1;
+    for (int i = 0; i < n_src; ++i)
+      if (S[i].integrate_mode == APB_INTEGRATE_THRESHOLD) qmax = std::max(qmax, S[i].quad_level);
+    int L = 1;
+    while (L < qmax * qmax && L < 32) L <<= 1;
+    p->refine_lanes = L;
+    int dev = 0, sms = 148, b0 = 4, b1 = 4;
+    PCU(cudaGetDevice(&dev));
+    PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate<false>, 128, 0));
+    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate<true>, 128, 0));
+    p->integrate_grid = sms * std::max(1, std::min(b0, b1));
+  }
+
+  PCU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  PCU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  PCU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
 
   // ---- per-image internal buffers
   p->h_model.resize(n_img); p->h_resid.resize(n_img); p->h_resid2.resize(n_img);
@@ -721,10 +780,29 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   PB(K_PREP);
   k_prep<<<ceil_div(n_src, 128), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad);
   LAUNCH_CHECK();
+  // PSF branch on the side stream: shifted stamps and (FFT sources) their spectra depend only on
+  // k_prep, so they overlap the first pass and the adaptive integration of the profiles
+  const FftTables& F = p->ft[grad];
   if (p->n_psf_list) {
+    cudaStream_t main_st = st;
+    if (cudaEventRecord(p->ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev_fork, 0) != cudaSuccess)
+      APB_FAIL("fork to the PSF stream failed");
+    st = p->side;
     PB(K_PSF);
     k_psf_stamp<<<p->n_psf_list, 256, 0, st>>>(p->d_src, p->d_dyn, p->psf_list, p->d_psf, p->d_psfst, grad);
     LAUNCH_CHECK();
+    if (p->n_fft_src) {
+      PB(K_FFTROWS);
+      k_fft_rows<<<F.n_rows_psf, p->fft_nt_rows, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows_psf, mode,
+                                                                          p->d_stamp, p->d_psfst, p->d_spec);
+      LAUNCH_CHECK();
+      PB(K_FFTCOLS);
+      k_fft_cols<<<F.n_cols_psf, p->fft_nt_cols, p->fft_smem_cols, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.jobs, F.cols_psf,
+                                                                          mode, p->d_spec);
+      LAUNCH_CHECK();
+    }
+    if (cudaEventRecord(p->ev_join, st) != cudaSuccess) APB_FAIL("PSF stream event failed");
+    st = main_st;
   }
   if (T.n_tiles) {
     PB(K_FIRST);
@@ -742,6 +820,15 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
       }
       Queues q = p->q;
       q.NVp = grad ? p->NVp_grad : 1;
+      if (p->use_coop) {
+        PB(K_SELECT);
+        k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
+        LAUNCH_CHECK();
+        PB(K_INTEGRATE);
+        if (grad) k_integrate<true><<<p->integrate_grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
+        else k_integrate<false><<<p->integrate_grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
+        LAUNCH_CHECK();
+      } else {
       PB(K_SELECT);
       k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
       LAUNCH_CHECK();
@@ -760,6 +847,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
       PB(K_SCATTER);
       k_scatter<<<grid, 128, 0, st>>>(p->d_src, q, p->d_stamp, grad);
       LAUNCH_CHECK();
+      }
     }
     if (p->n_norm) {
       PB(K_NORM);
@@ -767,6 +855,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
       LAUNCH_CHECK();
     }
   }
+  if (p->n_psf_list && cudaStreamWaitEvent(st, p->ev_join, 0) != cudaSuccess) APB_FAIL("join of the PSF stream failed");
   if (p->n_point) {
     PB(K_POINT);
     k_point<<<p->n_point, 256, 0, st>>>(p->d_src, p->d_dyn, p->point_list, p->d_psfst, p->d_out, grad);
@@ -779,21 +868,16 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
     LAUNCH_CHECK();
   }
   if (p->n_fft_src) {
-    const FftTables& F = p->ft[grad];
     PB(K_FFTROWS);
-    k_fft_rows<<<F.n_rows, 256, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows, mode, p->d_stamp,
-                                                        p->d_psfst, p->d_spec);
+    k_fft_rows<<<F.n_rows, p->fft_nt_rows, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows, mode, p->d_stamp,
+                                                                    p->d_psfst, p->d_spec);
     LAUNCH_CHECK();
     PB(K_FFTCOLS);
-    k_fft_cols<<<F.n_cols_psf, 256, p->fft_smem_cols, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.jobs, F.cols_psf, mode,
-                                                            p->d_spec);
-    LAUNCH_CHECK();
-    PB(K_FFTCOLS);
-    k_fft_cols<<<F.n_cols_img, 256, p->fft_smem_cols, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.jobs, F.cols_img, mode,
+    k_fft_cols<<<F.n_cols_img, p->fft_nt_cols, p->fft_smem_cols, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.jobs, F.cols_img, mode,
                                                             p->d_spec);
     LAUNCH_CHECK();
     PB(K_FFTINV);
-    k_fft_rows_inv<<<F.n_rows_inv, 256, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows_inv, p->d_spec,
+    k_fft_rows_inv<<<F.n_rows_inv, p->fft_nt_rows, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows_inv, p->d_spec,
                                                                 p->d_out);
     LAUNCH_CHECK();
   }
@@ -853,14 +937,18 @@ extern "C" int apb_jacobian(apb_plan_t* p, const double* x, int as_rep, double* 
   return 0;
 }
 
-extern "C" int apb_chi2(apb_plan_t* p, const double* x_rep, double* out2, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (begin_call(p, st)) return -1;
+static int chi2_core(apb_plan* p, const double* x_rep, double* out2, cudaStream_t st) {
   for (int ii = 0; ii < p->n_img; ++ii)
     if (!p->h_img[ii].data) APB_FAIL("apb_chi2: image without data");
   int rc = sample_pass(p, x_rep, 1, 0, 0, st);
   if (rc) return rc;
-  rc = assemble(p, 0, nullptr, nullptr, out2, 1, st);
+  return assemble(p, 0, nullptr, nullptr, out2, 1, st);
+}
+
+extern "C" int apb_chi2(apb_plan_t* p, const double* x_rep, double* out2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  int rc = chi2_core(p, x_rep, out2, st);
   p->stats.launches = p->launches;
   return rc;
 }
@@ -898,9 +986,16 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
   return 0;
 }
 
+static int geodesic_core(apb_plan* p, const double* xdh, const double* h, double d, double* rpp, cudaStream_t st);
 extern "C" int apb_geodesic(apb_plan_t* p, const double* xdh, const double* h, double d, double* rpp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (begin_call(p, st)) return -1;
+  int rc = geodesic_core(p, xdh, h, d, rpp, st);
+  p->stats.launches = p->launches;
+  return rc;
+}
+
+static int geodesic_core(apb_plan* p, const double* xdh, const double* h, double d, double* rpp, cudaStream_t st) {
   const int P = p->n_par;
   int rc;
   // rh = W (Y(x + d h) - Y): forward pass only touches plane 0, the cached derivative planes stay valid
@@ -921,20 +1016,47 @@ extern "C" int apb_geodesic(apb_plan_t* p, const double* xdh, const double* h, d
                                                              p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1);
     LAUNCH_CHECK();
   }
-  p->stats.launches = p->launches;
+  return 0;
+}
+
+static int lm_solve_launch(const double* H, const double* g, double L, int P, double* h, int* info, const LmEpi& epi,
+                           cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)P * (P + 1);
+  if (smem > 200 * 1024) APB_FAIL("apb_lm_solve: P too large for the single-CTA solver (max 159); use a library solver");
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_lm_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_lm_solve_small<<<1, 256, smem, st>>>(H, g, L, P, h, info, epi);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) APB_FAIL(std::string("apb_lm_solve launch: ") + cudaGetErrorString(e));
+  g_launches++;
+  return 0;
+}
+
+// One lambda-trial of LM.step (fit/lm.py:274-293) without leaving the device:
+//   h = solve(L, g);  rpp = geodesic(x + d h, h);  a = -solve(L, rpp)/2 (0 if L <= 1e-4);
+//   ha = h + acceleration a;  rec = [chi2(x + ha), status flag, |a|, |h|]
+// H, g: the normal equations of the last apb_normal_eq.  h_out, ha_out: device, P doubles.
+// rec: device, 4 doubles -- the single record the host reads back per trial.  P <= 159.
+extern "C" int apb_lm_trial(apb_plan_t* p, const double* H, const double* g, double L, const double* x_rep, double d,
+                            double acceleration, double* h_out, double* ha_out, double* rec, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  const int P = p->n_par;
+  if (P <= 0) APB_FAIL("apb_lm_trial: no parameters");
+  int rc;
+  LmEpi e1{1, x_rep, nullptr, d, 0.0, p->d_xtmp, nullptr, nullptr};
+  if ((rc = lm_solve_launch(H, g, L, P, h_out, nullptr, e1, st))) return rc;
+  if ((rc = geodesic_core(p, p->d_xtmp, h_out, d, p->d_rpp, st))) return rc;
+  LmEpi e2{2, x_rep, h_out, d, acceleration, p->d_xtmp2, ha_out, rec};
+  if ((rc = lm_solve_launch(H, p->d_rpp, L, P, p->d_atmp, nullptr, e2, st))) return rc;
+  if ((rc = chi2_core(p, p->d_xtmp2, rec, st))) return rc;
+  p->stats.launches = p->launches + 2;
   return 0;
 }
 
 extern "C" int apb_lm_solve(const double* H, const double* g, double L, int P, double* h, int* info, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
   if (P <= 0) return 0;
-  const size_t smem = sizeof(double) * (size_t)P * (P + 1);
-  if (smem > 200 * 1024) APB_FAIL("apb_lm_solve: P too large for the single-CTA solver (max 159); use a library solver");
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_lm_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_lm_solve_small<<<1, 256, smem, st>>>(H, g, L, P, h, info);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) APB_FAIL(std::string("apb_lm_solve launch: ") + cudaGetErrorString(e));
-  return 0;
+  LmEpi e0{0, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, nullptr};
+  return lm_solve_launch(H, g, L, P, h, info, e0, (cudaStream_t)stream);
 }
 
 extern "C" int apb_plan_stats(apb_plan_t* p, apb_stats_t* out) {

@@ -1,11 +1,13 @@
 // FFT convolution for large PSFs (utils/operations.py:9-36 `fft_convolve_torch`, called from
-// models/_model_methods.py:233-257).  Hand-written fp64 mixed-radix (2/3/4/5) Stockham FFTs in
-// shared memory, three passes per plane:
+// models/_model_methods.py:233-257).  Hand-written fp64 FFTs, three passes per plane:
 //   k_fft_rows     real rows -> half spectra           (two real rows share one complex FFT)
 //   k_fft_cols     column FFT . PSF spectrum . inverse column FFT, all in shared memory: the
 //                  pointwise multiply never touches HBM and the full 2-D spectrum is never stored
 //   k_fft_rows_inv half spectra -> real rows, cropped to the output window
-// The transform lengths are the next 2^a 3^b 5^c >= the padded stamp, not the reference's exact
+// Each transform is a Stockham autosort FFT whose stages are large-radix (16, 9, 8, 5, 4, 3, 2)
+// butterflies held in registers; shared memory is only the exchange between stages (ping-pong, one
+// barrier per stage), so a 1152-point transform is three stages (16.8.9) and three exchanges.
+// The transform lengths are a cheap 2^a 3^b 5^c >= the padded stamp, not the reference's exact
 // image size: the valid region of the circular convolution equals the linear one either way
 // (the reference relies on the same fact, model_object.py:313-349).
 #pragma once
@@ -32,18 +34,170 @@ APB_HD cpx c_sub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
 // multiply by -i (forward) or +i (inverse)
 template <bool INV>
 APB_HD cpx c_rot(cpx a) { return INV ? cpx{-a.y, a.x} : cpx{a.y, -a.x}; }
-template <bool INV>
-APB_HD cpx c_tw(const cpx* __restrict__ tw, int idx) {
-  cpx w = tw[idx];
-  if (INV) w.y = -w.y;
-  return w;
+
+// cos, sin of 2 pi m / R for the composite radices (first octant entries, 25 digits)
+template <int R>
+APB_HD constexpr double root_cos(int m) {
+  if (R == 16) {
+    constexpr double t[16] = {1.0, 0.9238795325112867561281832, 0.7071067811865475244008444, 0.38268343236508977172846,
+                              0.0, -0.38268343236508977172846, -0.7071067811865475244008444, -0.9238795325112867561281832,
+                              -1.0, -0.9238795325112867561281832, -0.7071067811865475244008444, -0.38268343236508977172846,
+                              0.0, 0.38268343236508977172846, 0.7071067811865475244008444, 0.9238795325112867561281832};
+    return t[m];
+  } else if (R == 9) {
+    constexpr double t[9] = {1.0, 0.7660444431189780352023927, 0.1736481776669303488517166, -0.5,
+                             -0.9396926207859083840541093, -0.9396926207859083840541093, -0.5,
+                             0.1736481776669303488517166, 0.7660444431189780352023927};
+    return t[m];
+  } else {
+    constexpr double t[8] = {1.0, 0.7071067811865475244008444, 0.0, -0.7071067811865475244008444,
+                             -1.0, -0.7071067811865475244008444, 0.0, 0.7071067811865475244008444};
+    return t[m];
+  }
+}
+template <int R>
+APB_HD constexpr double root_sin(int m) {
+  if (R == 16) {
+    constexpr double t[16] = {0.0, 0.38268343236508977172846, 0.7071067811865475244008444, 0.9238795325112867561281832,
+                              1.0, 0.9238795325112867561281832, 0.7071067811865475244008444, 0.38268343236508977172846,
+                              0.0, -0.38268343236508977172846, -0.7071067811865475244008444, -0.9238795325112867561281832,
+                              -1.0, -0.9238795325112867561281832, -0.7071067811865475244008444, -0.38268343236508977172846};
+    return t[m];
+  } else if (R == 9) {
+    constexpr double t[9] = {0.0, 0.6427876096865393263226434, 0.984807753012208059366743, 0.8660254037844386467637232,
+                             0.3420201433256687330440996, -0.3420201433256687330440996, -0.8660254037844386467637232,
+                             -0.984807753012208059366743, -0.6427876096865393263226434};
+    return t[m];
+  } else {
+    constexpr double t[8] = {0.0, 0.7071067811865475244008444, 1.0, 0.7071067811865475244008444,
+                             0.0, -0.7071067811865475244008444, -1.0, -0.7071067811865475244008444};
+    return t[m];
+  }
 }
 
-// One radix-R butterfly of a Stockham autosort stage.  `in`/`out` hold one length-N sequence,
-// Ns = product of the radices of the stages already done, j in [0, N/R).
+// a * exp(-+ 2 pi i m / R) with m a compile-time constant after unrolling
+template <int R, bool INV>
+APB_HD cpx mul_root(cpx a, int m) {
+  m %= R;
+  if (m == 0) return a;
+  if (2 * m == R) return cpx{-a.x, -a.y};
+  if (4 * m == R) return c_rot<INV>(a);
+  if (4 * m == 3 * R) return c_rot<!INV>(a);
+  const double c = root_cos<R>(m), s = root_sin<R>(m);
+  return INV ? cpx{a.x * c - a.y * s, a.x * s + a.y * c} : cpx{a.x * c + a.y * s, a.y * c - a.x * s};
+}
+
+// in-register DFT of R values: v[k] <- sum_r v[r] exp(-+ 2 pi i r k / R)
+template <int R, bool INV>
+struct FftReg;
 template <bool INV>
-APB_HD void fft_butterfly(const cpx* __restrict__ in, cpx* __restrict__ out, int N, int R, int Ns, int j,
-                          const cpx* __restrict__ tw) {
+struct FftReg<2, INV> {
+  static APB_HD void run(cpx* v) {
+    const cpx a = v[0], b = v[1];
+    v[0] = c_add(a, b);
+    v[1] = c_sub(a, b);
+  }
+};
+template <bool INV>
+struct FftReg<4, INV> {
+  static APB_HD void run(cpx* v) {
+    const cpx t0 = c_add(v[0], v[2]), t1 = c_sub(v[0], v[2]), t2 = c_add(v[1], v[3]), t3 = c_rot<INV>(c_sub(v[1], v[3]));
+    v[0] = c_add(t0, t2);
+    v[1] = c_add(t1, t3);
+    v[2] = c_sub(t0, t2);
+    v[3] = c_sub(t1, t3);
+  }
+};
+template <bool INV>
+struct FftReg<3, INV> {
+  static APB_HD void run(cpx* v) {
+    const double s3 = 0.86602540378443864676;
+    const cpx t1 = c_add(v[1], v[2]);
+    const cpx m = cpx{v[0].x - 0.5 * t1.x, v[0].y - 0.5 * t1.y};
+    const cpx dd = c_sub(v[1], v[2]);
+    const cpx d = c_rot<INV>(cpx{s3 * dd.x, s3 * dd.y});
+    v[0] = c_add(v[0], t1);
+    v[1] = c_add(m, d);
+    v[2] = c_sub(m, d);
+  }
+};
+template <bool INV>
+struct FftReg<5, INV> {
+  static APB_HD void run(cpx* v) {
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    const cpx v0 = v[0];
+    const cpx a1 = c_add(v[1], v[4]), a2 = c_add(v[2], v[3]), b1 = c_sub(v[1], v[4]), b2 = c_sub(v[2], v[3]);
+    const cpx p1 = cpx{v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y};
+    const cpx p2 = cpx{v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y};
+    const cpx q1 = c_rot<INV>(cpx{s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y});
+    const cpx q2 = c_rot<INV>(cpx{s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y});
+    v[0] = c_add(v0, c_add(a1, a2));
+    v[1] = c_add(p1, q1);
+    v[2] = c_add(p2, q2);
+    v[3] = c_sub(p2, q2);
+    v[4] = c_sub(p1, q1);
+  }
+};
+// R = R1 * R2 (Cooley-Tukey in registers): r = R2 a + b, k = c + R1 d
+template <int R, int R1, int R2, bool INV>
+APB_HD void fft_reg_composite(cpx* v) {
+  cpx t[R2][R1];
+#pragma unroll
+  for (int b = 0; b < R2; ++b) {
+#pragma unroll
+    for (int a = 0; a < R1; ++a) t[b][a] = v[R2 * a + b];
+    FftReg<R1, INV>::run(t[b]);
+#pragma unroll
+    for (int c = 1; c < R1; ++c) t[b][c] = mul_root<R, INV>(t[b][c], b * c);
+  }
+#pragma unroll
+  for (int c = 0; c < R1; ++c) {
+    cpx u[R2];
+#pragma unroll
+    for (int b = 0; b < R2; ++b) u[b] = t[b][c];
+    FftReg<R2, INV>::run(u);
+#pragma unroll
+    for (int d = 0; d < R2; ++d) v[c + R1 * d] = u[d];
+  }
+}
+template <bool INV>
+struct FftReg<8, INV> {
+  static APB_HD void run(cpx* v) { fft_reg_composite<8, 4, 2, INV>(v); }
+};
+template <bool INV>
+struct FftReg<9, INV> {
+  static APB_HD void run(cpx* v) { fft_reg_composite<9, 3, 3, INV>(v); }
+};
+template <bool INV>
+struct FftReg<16, INV> {
+  static APB_HD void run(cpx* v) { fft_reg_composite<16, 4, 4, INV>(v); }
+};
+
+// Shared-memory sequences are skewed by one element every 16 (index i lives at i + i/16): the
+// first stage of a radix-16 transform writes with stride 16 elements, which without the skew puts
+// every lane of a quarter-warp on the same 16-byte bank (8-way conflict).
+#define FPAD(i) ((i) + ((i) >> 4))
+
+// powers w^1 .. w^(R-1) of the stage twiddle from ONE table read: products arranged as a tree of
+// depth <= 4 (error <= ~5 ulp), which trades the 15 strided, bank-conflicting table reads of a
+// radix-16 butterfly for ~80 flops on an FP64 pipe that is otherwise mostly idle
+template <int R>
+APB_HD void twiddle_powers(cpx w1, cpx* w) {
+  w[1] = w1;
+#pragma unroll
+  for (int r = 2; r < R; ++r) {
+    const int h = (r & (r - 1)) == 0 ? r / 2 : (r & -r);   // power of two: square; else split off the low bit
+    w[r] = c_mul(w[r - h], w[h]);
+  }
+}
+
+// One radix-R butterfly of a Stockham autosort stage: loads its R inputs of the length-N sequence
+// `in`, applies the stage twiddles and the in-register DFT.  Ns = product of the radices of the
+// stages already done, j in [0, N/R).  Returns the index of output 0; output r goes to o + r*Ns
+// (both through FPAD).  tw = exp(-2 pi i k / N) table (global memory, read through L1).
+template <int R, bool INV>
+APB_HD int fft_bfly(const cpx* __restrict__ in, int N, int Ns, int j, const cpx* __restrict__ tw, cpx* v) {
   const int nb = N / R;
   int k, jq;
   if ((Ns & (Ns - 1)) == 0) {
@@ -53,78 +207,57 @@ APB_HD void fft_butterfly(const cpx* __restrict__ in, cpx* __restrict__ out, int
     jq = (j / Ns) * Ns;
     k = j - jq;
   }
-  const int o = jq * R + k;
-  const int step = k * (N / (Ns * R));  // twiddle index of w^(k) for this stage
-  if (R == 4) {
-    cpx v0 = in[j], v1 = in[j + nb], v2 = in[j + 2 * nb], v3 = in[j + 3 * nb];
-    if (k) {
-      v1 = c_mul(v1, c_tw<INV>(tw, step));
-      v2 = c_mul(v2, c_tw<INV>(tw, 2 * step));
-      v3 = c_mul(v3, c_tw<INV>(tw, 3 * step));
-    }
-    const cpx t0 = c_add(v0, v2), t1 = c_sub(v0, v2), t2 = c_add(v1, v3), t3 = c_rot<INV>(c_sub(v1, v3));
-    out[o] = c_add(t0, t2);
-    out[o + Ns] = c_add(t1, t3);
-    out[o + 2 * Ns] = c_sub(t0, t2);
-    out[o + 3 * Ns] = c_sub(t1, t3);
-  } else if (R == 2) {
-    cpx v0 = in[j], v1 = in[j + nb];
-    if (k) v1 = c_mul(v1, c_tw<INV>(tw, step));
-    out[o] = c_add(v0, v1);
-    out[o + Ns] = c_sub(v0, v1);
-  } else if (R == 3) {
-    cpx v0 = in[j], v1 = in[j + nb], v2 = in[j + 2 * nb];
-    if (k) {
-      v1 = c_mul(v1, c_tw<INV>(tw, step));
-      v2 = c_mul(v2, c_tw<INV>(tw, 2 * step));
-    }
-    const double s3 = 0.86602540378443864676;
-    const cpx t1 = c_add(v1, v2);
-    const cpx m = cpx{v0.x - 0.5 * t1.x, v0.y - 0.5 * t1.y};
-    const cpx dd = c_sub(v1, v2);
-    const cpx d = c_rot<INV>(cpx{s3 * dd.x, s3 * dd.y});
-    out[o] = c_add(v0, t1);
-    out[o + Ns] = c_add(m, d);
-    out[o + 2 * Ns] = c_sub(m, d);
-  } else {  // R == 5
-    cpx v0 = in[j], v1 = in[j + nb], v2 = in[j + 2 * nb], v3 = in[j + 3 * nb], v4 = in[j + 4 * nb];
-    if (k) {
-      v1 = c_mul(v1, c_tw<INV>(tw, step));
-      v2 = c_mul(v2, c_tw<INV>(tw, 2 * step));
-      v3 = c_mul(v3, c_tw<INV>(tw, 3 * step));
-      v4 = c_mul(v4, c_tw<INV>(tw, 4 * step));
-    }
-    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
-    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
-    const cpx a1 = c_add(v1, v4), a2 = c_add(v2, v3), b1 = c_sub(v1, v4), b2 = c_sub(v2, v3);
-    const cpx p1 = cpx{v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y};
-    const cpx p2 = cpx{v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y};
-    const cpx q1 = c_rot<INV>(cpx{s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y});
-    const cpx q2 = c_rot<INV>(cpx{s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y});
-    out[o] = c_add(v0, c_add(a1, a2));
-    out[o + Ns] = c_add(p1, q1);
-    out[o + 2 * Ns] = c_add(p2, q2);
-    out[o + 3 * Ns] = c_sub(p2, q2);
-    out[o + 4 * Ns] = c_sub(p1, q1);
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = in[FPAD(j + r * nb)];
+  if (k) {
+    cpx w1 = tw[k * (N / (Ns * R))];
+    if (INV) w1.y = -w1.y;
+    cpx w[R];
+    twiddle_powers<R>(w1, w);
+#pragma unroll
+    for (int r = 1; r < R; ++r) v[r] = c_mul(v[r], w[r]);
   }
+  FftReg<R, INV>::run(v);
+  return jq * R + k;
 }
 
 #if defined(__CUDACC__)
-// nf FFTs of length D.N living at a + f*ld (ping-pong partner b).  All threads of the CTA
-// take part; returns the buffer that holds the (unnormalised) result.
+// One stage for nf sequences: in + f*ld -> out + f*ld, one barrier.  A thread keeps one butterfly
+// (R complex values) in registers at a time.  noinline on purpose: inlined into the stage loop the
+// compiler hoists every radix's fp64 constants out of the loop and spills ~1 KB per thread; as
+// separate functions each radix gets its own allocation (<= 112 registers, no spills).
+template <int R, bool INV>
+__device__ __noinline__ void fft_stage(const cpx* __restrict__ in, cpx* __restrict__ out, int nf, int ld, int N, int Ns,
+                                       const cpx* __restrict__ tw) {
+  const int nb = N / R, total = nf * nb;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int f = idx / nb, j = idx - f * nb;
+    cpx v[R];
+    const int o = fft_bfly<R, INV>(in + f * ld, N, Ns, j, tw, v);
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[f * ld + FPAD(o + r * Ns)] = v[r];
+  }
+  __syncthreads();
+}
+
+// nf FFTs of length D.N at a + f*ld (ping-pong partner b), unnormalised.  All threads of the CTA
+// take part; returns the buffer that holds the result.
 template <bool INV>
 __device__ __forceinline__ cpx* fft_run(cpx* a, cpx* b, int nf, int ld, const FftDesc& D, const cpx* __restrict__ tw) {
   int Ns = 1;
   const int N = D.N;
+#pragma unroll 1
   for (int st = 0; st < D.nstage; ++st) {
     const int R = D.radix[st];
-    const int nb = N / R;
-    const int total = nf * nb;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-      const int f = idx / nb, j = idx - f * nb;
-      fft_butterfly<INV>(a + f * ld, b + f * ld, N, R, Ns, j, tw);
+    switch (R) {
+      case 16: fft_stage<16, INV>(a, b, nf, ld, N, Ns, tw); break;
+      case 9: fft_stage<9, INV>(a, b, nf, ld, N, Ns, tw); break;
+      case 8: fft_stage<8, INV>(a, b, nf, ld, N, Ns, tw); break;
+      case 5: fft_stage<5, INV>(a, b, nf, ld, N, Ns, tw); break;
+      case 4: fft_stage<4, INV>(a, b, nf, ld, N, Ns, tw); break;
+      case 3: fft_stage<3, INV>(a, b, nf, ld, N, Ns, tw); break;
+      default: fft_stage<2, INV>(a, b, nf, ld, N, Ns, tw); break;
     }
-    __syncthreads();
     cpx* t = a;
     a = b;
     b = t;
@@ -140,7 +273,7 @@ __device__ __forceinline__ cpx* fft_run(cpx* a, cpx* b, int nf, int ld, const Ff
 // spectra layout (cpx): image planes  specA + ((plane*eh + row) * nxp + kx)
 //                       PSF planes    specK + ((k*sph + a) * nxp + kx)
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fft_rows(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
+__global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
                                                   const cpx* __restrict__ twid, const int4* __restrict__ work, int mode,
                                                   const double* __restrict__ stamp, const double* __restrict__ psfst,
                                                   cpx* __restrict__ spec) {
@@ -153,10 +286,10 @@ __global__ void __launch_bounds__(256) k_fft_rows(const DevSrc* __restrict__ src
   __syncthreads();
   const int N = D.N, nxh = N / 2 + 1, nxp = s.nxp;
   const int nf = (wk.w + 1) / 2;
-  cpx* tw = fsm;
-  cpx* a = tw + N;
-  cpx* b = a + nf * N;
-  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = twid[D.tw_off + q];
+  const int ld = FPAD(N) + 1;
+  const cpx* tw = twid + D.tw_off;
+  cpx* a = fsm;
+  cpx* b = a + nf * ld;
   const bool is_psf = wk.y < 0;
   const double* base;
   int rstride, valid_w, xoff;
@@ -185,13 +318,14 @@ __global__ void __launch_bounds__(256) k_fft_rows(const DevSrc* __restrict__ src
       re = base[(long long)r0 * rstride + sx];
       if (2 * f + 1 < wk.w) im = base[(long long)(r0 + 1) * rstride + sx];
     }
-    a[idx] = cpx{re, im};
+    a[f * ld + FPAD(x)] = cpx{re, im};
   }
   __syncthreads();
-  const cpx* r = fft_run<false>(a, b, nf, N, D, tw);
+  const cpx* r = fft_run<false>(a, b, nf, ld, D, tw);
   for (int idx = threadIdx.x; idx < nf * nxh; idx += blockDim.x) {
     const int f = idx / nxh, k = idx - f * nxh;
-    const cpx zk = r[f * N + k], zn = r[f * N + (k ? N - k : 0)];
+    const int kn = k ? N - k : 0;
+    const cpx zk = r[f * ld + FPAD(k)], zn = r[f * ld + FPAD(kn)];
     const int r0 = wk.z + 2 * f;
     dst[(long long)r0 * nxp + k] = cpx{0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y)};
     if (2 * f + 1 < wk.w) dst[(long long)(r0 + 1) * nxp + k] = cpx{0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x)};
@@ -205,7 +339,7 @@ __global__ void __launch_bounds__(256) k_fft_rows(const DevSrc* __restrict__ src
 //     specB + ((out_plane*oh + y) * nxp + kx)
 // PSF job: forward column FFT only, stored column-major:  specKT + ((k*nxh + kx) * Ny + ky)
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fft_cols(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
+__global__ void __launch_bounds__(256, 2) k_fft_cols(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
                                                   const cpx* __restrict__ twid, const int4* __restrict__ jobs,
                                                   const int4* __restrict__ work, int mode, cpx* __restrict__ spec) {
   extern __shared__ cpx fsm[];
@@ -218,11 +352,10 @@ __global__ void __launch_bounds__(256) k_fft_cols(const DevSrc* __restrict__ src
   __syncthreads();
   const int N = D.N, nxp = s.nxp, nxh = s.nxh;
   const int nc = wk.z, kx0 = wk.y;
-  const int ld = N + 8 / s.fft_nc;  // pad: the transposing tile load/store is bank-conflict free
-  cpx* tw = fsm;
-  cpx* a = tw + N;
+  const int ld = s.fft_ld;  // skewed length + pad: the transposing tile load/store is bank-conflict free
+  const cpx* tw = twid + D.tw_off;
+  cpx* a = fsm;
   cpx* b = a + s.fft_nc * ld;
-  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = twid[D.tw_off + q];
   const bool is_psf = jb.y < 0;
   const cpx* in;
   int rows_valid, yoff;
@@ -239,7 +372,7 @@ __global__ void __launch_bounds__(256) k_fft_cols(const DevSrc* __restrict__ src
     const int y = idx / nc, c = idx - y * nc;
     int sy = y + yoff;
     if (sy >= N) sy -= N;
-    a[c * ld + y] = sy < rows_valid ? in[(long long)sy * nxp + c] : cpx{0.0, 0.0};
+    a[c * ld + FPAD(y)] = sy < rows_valid ? in[(long long)sy * nxp + c] : cpx{0.0, 0.0};
   }
   __syncthreads();
   cpx* r = fft_run<false>(a, b, nc, ld, D, tw);
@@ -247,7 +380,7 @@ __global__ void __launch_bounds__(256) k_fft_cols(const DevSrc* __restrict__ src
     cpx* kt = spec + s.specKT_off + ((long long)(-1 - jb.y) * nxh + kx0) * N;
     for (int idx = threadIdx.x; idx < nc * N; idx += blockDim.x) {
       const int c = idx / N, y = idx - c * N;
-      kt[(long long)c * N + y] = r[c * ld + y];
+      kt[(long long)c * N + y] = r[c * ld + FPAD(y)];
     }
     return;
   }
@@ -255,23 +388,22 @@ __global__ void __launch_bounds__(256) k_fft_cols(const DevSrc* __restrict__ src
   const double scale = 1.0 / ((double)N * (double)s.fft_nx);
   for (int idx = threadIdx.x; idx < nc * N; idx += blockDim.x) {
     const int c = idx / N, y = idx - c * N;
-    const cpx v = c_mul(r[c * ld + y], kt[(long long)c * N + y]);
-    r[c * ld + y] = cpx{v.x * scale, v.y * scale};
+    const cpx v = c_mul(r[c * ld + FPAD(y)], kt[(long long)c * N + y]);
+    r[c * ld + FPAD(y)] = cpx{v.x * scale, v.y * scale};
   }
   __syncthreads();
-  cpx* other = (r == a) ? b : a;
-  const cpx* z = fft_run<true>(r, other, nc, ld, D, tw);
+  const cpx* z = fft_run<true>(r, r == a ? b : a, nc, ld, D, tw);
   cpx* out = spec + s.specB_off + ((long long)jb.w * s.oh) * nxp + kx0;
   for (int idx = threadIdx.x; idx < nc * s.oh; idx += blockDim.x) {
     const int y = idx / nc, c = idx - y * nc;
-    out[(long long)y * nxp + c] = z[c * ld + y + s.by];
+    out[(long long)y * nxp + c] = z[c * ld + FPAD(y + s.by)];
   }
 }
 
 // ----------------------------------------------------------------------------
 // pass C: half spectra -> real rows of the output window.  work: {src, out_plane, row0, nrows}
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fft_rows_inv(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
+__global__ void __launch_bounds__(256, 2) k_fft_rows_inv(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
                                                       const cpx* __restrict__ twid, const int4* __restrict__ work,
                                                       const cpx* __restrict__ spec, double* __restrict__ outar) {
   extern __shared__ cpx fsm[];
@@ -282,10 +414,10 @@ __global__ void __launch_bounds__(256) k_fft_rows_inv(const DevSrc* __restrict__
   __syncthreads();
   const int N = D.N, nxp = s.nxp;
   const int nf = (wk.w + 1) / 2;
-  cpx* tw = fsm;
-  cpx* a = tw + N;
-  cpx* b = a + nf * N;
-  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = twid[D.tw_off + q];
+  const int ld = FPAD(N) + 1;
+  const cpx* tw = twid + D.tw_off;
+  cpx* a = fsm;
+  cpx* b = a + nf * ld;
   const cpx* in = spec + s.specB_off + ((long long)wk.y * s.oh) * nxp;
   for (int idx = threadIdx.x; idx < nf * N; idx += blockDim.x) {
     const int f = idx / N, k = idx - f * N;
@@ -295,15 +427,15 @@ __global__ void __launch_bounds__(256) k_fft_rows_inv(const DevSrc* __restrict__
     const int kk = lo ? k : N - k;
     const cpx x1 = in[(long long)r0 * nxp + kk];
     const cpx x2 = second ? in[(long long)(r0 + 1) * nxp + kk] : cpx{0.0, 0.0};
-    a[idx] = lo ? cpx{x1.x - x2.y, x1.y + x2.x} : cpx{x1.x + x2.y, -x1.y + x2.x};
+    a[f * ld + FPAD(k)] = lo ? cpx{x1.x - x2.y, x1.y + x2.x} : cpx{x1.x + x2.y, -x1.y + x2.x};
   }
   __syncthreads();
-  const cpx* z = fft_run<true>(a, b, nf, N, D, tw);
+  const cpx* z = fft_run<true>(a, b, nf, ld, D, tw);
   double* o = outar + s.out_off + (long long)wk.y * s.ow * s.oh;
   for (int idx = threadIdx.x; idx < nf * s.ow; idx += blockDim.x) {
     const int f = idx / s.ow, x = idx - f * s.ow;
     const int r0 = wk.z + 2 * f;
-    const cpx v = z[f * N + x + s.bx];
+    const cpx v = z[f * ld + FPAD(x + s.bx)];
     o[(long long)r0 * s.ow + x] = v.x;
     if (2 * f + 1 < wk.w) o[(long long)(r0 + 1) * s.ow + x] = v.y;
   }

@@ -458,10 +458,25 @@ __global__ void __launch_bounds__(256) k_geo_v(const DevSrc* __restrict__ src, c
 
 // ----------------------------------------------------------------------------
 // damped solve for small P: one CTA, Gaussian elimination with partial pivoting in shared memory
-// (lm.py:359-371)
+// (lm.py:359-371), with the vector algebra of one lambda-trial (lm.py:274-290) as epilogues so that
+// a trial is kernels only, no host-side tensor arithmetic:
+//   mode 1: h = solve(H, g);            xout = x + d h                      (point of the geodesic probe)
+//   mode 2: s = solve(H, rhs = rpp);    a = L > 1e-4 ? -s/2 : 0;  ha = hin + acc a;  xout = x + ha;
+//           rec[2] = |a|, rec[3] = |hin|                                     (curvature test rho = |a|/|h|)
 // ----------------------------------------------------------------------------
+struct LmEpi {
+  int mode;
+  const double* x;
+  const double* hin;
+  double d, acc;
+  double* xout;
+  double* ha;
+  double* rec;
+};
+
 __global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict__ H, const double* __restrict__ g,
-                                                        double L, int P, double* __restrict__ h, int* __restrict__ info) {
+                                                        double L, int P, double* __restrict__ h, int* __restrict__ info,
+                                                        LmEpi epi) {
   extern __shared__ double sm[];
   double* A = sm;          // P x (P+1) augmented
   __shared__ int piv_s;
@@ -508,5 +523,21 @@ __global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict
       h[i] = v / A[i * ld + i];
     }
     if (info) *info = bad;
+    if (epi.mode == 1) {
+      for (int i = 0; i < P; ++i) epi.xout[i] = epi.x[i] + epi.d * h[i];
+    } else if (epi.mode == 2) {
+      double na = 0.0, nh = 0.0;
+      for (int i = 0; i < P; ++i) {
+        const double a = L > 1e-4 ? -h[i] / 2 : 0.0;
+        const double hh = epi.hin[i];
+        const double ha = hh + a * epi.acc;
+        na += a * a;
+        nh += hh * hh;
+        epi.ha[i] = ha;
+        epi.xout[i] = epi.x[i] + ha;
+      }
+      epi.rec[2] = sqrt(na);
+      epi.rec[3] = sqrt(nh);
+    }
   }
 }

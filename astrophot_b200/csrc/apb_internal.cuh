@@ -45,6 +45,7 @@ struct DevSrc {
   int fftx, ffty;          // FftDesc index of the row / column transform
   int fft_nx, nxh, nxp;    // row length, nx/2+1, padded spectrum row stride (cpx)
   int fft_nf, fft_nc;      // complex row FFTs per CTA, columns per CTA
+  int fft_ld;              // column tile leading dimension in shared memory (Ny + pad)
   long long specA_off, specB_off, specK_off, specKT_off;  // cpx offsets into the spectrum arena
 };
 

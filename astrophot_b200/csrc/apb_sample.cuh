@@ -1,6 +1,7 @@
 // Sampling kernels: parameter prep, first pass, curvature select + ballot compaction,
 // work-queue refinement, reduction, scatter, PSF-model normalisation.
 #pragma once
+#include <cooperative_groups.h>
 #include "apb_internal.cuh"
 
 // work queues of the adaptive integration (one set per refinement depth)
@@ -317,10 +318,8 @@ __global__ void k_mean_final(const DevSrc* __restrict__ src, DevDyn* __restrict_
 // ----------------------------------------------------------------------------
 // select: curvature test + warp-ballot compaction into the depth-1 queue
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_select(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
-                                                const int4* __restrict__ tiles, int mode,
-                                                const double* __restrict__ stamp, Queues q) {
-  const int4 t = tiles[blockIdx.x];
+__device__ __forceinline__ void select_tile(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn, const int4 t, int mode,
+                                            const double* __restrict__ stamp, const Queues& q) {
   const DevSrc& s = src[t.x];
   if (s.integrate_mode != APB_INTEGRATE_THRESHOLD) return;
   const DevDyn& d = dyn[t.x];
@@ -361,7 +360,7 @@ __global__ void __launch_bounds__(256) k_select(const DevSrc* __restrict__ src, 
   if (sel) {
     const int e = base + __popc(bal & ((1u << lane) - 1));
     if (e < q.cap[1]) {
-      Level& L = q.lv[1];
+      const Level& L = q.lv[1];
       L.src[e] = t.x;
       L.x[e] = X;
       L.y[e] = Y;
@@ -371,6 +370,12 @@ __global__ void __launch_bounds__(256) k_select(const DevSrc* __restrict__ src, 
       *q.overflow = 1;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_select(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                const int4* __restrict__ tiles, int mode,
+                                                const double* __restrict__ stamp, Queues q) {
+  select_tile(src, dyn, tiles[blockIdx.x], mode, stamp, q);
 }
 
 // ----------------------------------------------------------------------------
@@ -499,6 +504,239 @@ __global__ void k_scatter(const DevSrc* __restrict__ src, Queues q, double* __re
     const DevSrc& s = src[L.src[t]];
     if (p > (grad ? s.n_act : 0)) continue;
     stamp[s.stamp_off + (long long)p * s.plane_stride + L.parent[t]] = L.res[w];
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Fused adaptive integration (utils/operations.py:123-247) in ONE launch after the ballot-compacted
+// depth-1 queue is built: no per-depth launches, no deeper queues, nothing that can overflow.
+//  * depth 1: L lanes (power of two >= quad_level^2, <= 32) share one queue entry, one Gauss-Legendre
+//    node each; partial sums are combined with an xor-shuffle tree (fixed order => deterministic).
+//  * an entry that fails |GL - centre| > thr is subdivided on the spot by the whole warp, depth
+//    first: lane c integrates child c (gridding^2 children, 32 per sweep) with its own GL rule and
+//    error test; children that fail again are taken one at a time (ballot + ffs), broadcast to the
+//    warp and subdivided the same way; child sums are combined with the same shuffle tree.
+// Queue entries are dealt round-robin to the warps of the grid so that the expensive entries, which
+// cluster at the source centre, spread over all SMs.
+// ----------------------------------------------------------------------------
+template <bool GRAD, int NE>
+struct Acc {
+  double v[(GRAD ? NE : 0) + 1];
+};
+
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double gl_nodes(const DevSrc& s, const DevDyn& d, double X, double Y, double scale, double ascale,
+                                           int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  double dI[GRAD ? NE : 1];
+  acc.v[0] = 0.0;
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) acc.v[1 + e] = 0.0;
+  double centre = 0.0;
+  const int n = s.quad_level, nn = n * n, mid = nn / 2;
+  for (int k = k0; k < nn; k += kstep) {
+    const int kx = k % n, ky = k / n;
+    const double ax = c_quad.a[n][kx] * scale, ay = c_quad.a[n][ky] * scale;
+    const double w = c_quad.w[n][kx] * c_quad.w[n][ky];
+    const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ax + s.S[1] * ay), Y + (s.S[2] * ax + s.S[3] * ay), ascale, dI);
+    if (k == mid) centre = I;
+    acc.v[0] += I * w;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc.v[1 + e] += dI[e] * w;
+  }
+  return centre;
+}
+
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void acc_shuffle_sum(const DevSrc& s, Acc<GRAD, KindInfo<KIND>::NE>& acc, unsigned mask, int width) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  for (int o = width >> 1; o > 0; o >>= 1) {
+    acc.v[0] += __shfl_xor_sync(mask, acc.v[0], o);
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc.v[1 + e] += __shfl_xor_sync(mask, acc.v[1 + e], o);
+  }
+}
+
+// Whole warp: integral of the cell centred (X, Y) at `depth` (already known to need subdivision)
+// as the sum of its gridding^2 children at depth+1.  Arguments are warp-uniform.  Result in every lane.
+template <int KIND, bool GRAD, int LEVELS_LEFT>
+__device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int mode, int depth, double X, double Y,
+                                           Acc<GRAD, KindInfo<KIND>::NE>& out, int* __restrict__ qcount) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  const int lane = threadIdx.x & 31;
+  const int G = s.gridding, nchild = G * G, cd = depth + 1;
+  double scale = 1.0, ascale = 1.0, thr = d.thr[mode], pscale = 1.0;
+  for (int k = 1; k < cd; ++k) {
+    pscale = scale;
+    scale /= (double)G;
+    ascale /= (double)(G * G);
+    thr *= (double)(G * G);
+  }
+  if (lane == 0) atomicAdd(&qcount[cd], nchild);
+  out.v[0] = 0.0;
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) out.v[1 + e] = 0.0;
+  for (int c0 = 0; c0 < nchild; c0 += 32) {
+    const int c = c0 + lane;
+    const bool have = c < nchild;
+    Acc<GRAD, NE> ca;
+    ca.v[0] = 0.0;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) ca.v[1 + e] = 0.0;
+    double cx = 0.0, cy = 0.0;
+    bool again = false;
+    if (have) {
+      // displacement_grid: linspace(-(G-1)/(2G), (G-1)/(2G), G) of the parent cell (utils/operations.py:94-102)
+      const double dx = (-(G - 1) / (2.0 * G) + (double)(c % G) / G) * pscale;
+      const double dy = (-(G - 1) / (2.0 * G) + (double)(c / G) / G) * pscale;
+      cx = X + (s.S[0] * dx + s.S[1] * dy);
+      cy = Y + (s.S[2] * dx + s.S[3] * dy);
+      const double centre = gl_nodes<KIND, GRAD>(s, d, cx, cy, scale, ascale, 0, 1, ca);
+      again = cd < s.max_depth && fabs(ca.v[0] - centre) > thr;
+    }
+    if constexpr (LEVELS_LEFT > 0) {
+      unsigned bal = __ballot_sync(0xffffffffu, again);
+      while (bal) {
+        const int b = __ffs(bal) - 1;
+        bal &= bal - 1;
+        const double bx = __shfl_sync(0xffffffffu, cx, b), by = __shfl_sync(0xffffffffu, cy, b);
+        Acc<GRAD, NE> sub;
+        split_cell<KIND, GRAD, LEVELS_LEFT - 1>(s, d, mode, cd, bx, by, sub, qcount);
+        if (lane == b) ca = sub;
+      }
+    }
+    acc_shuffle_sum<KIND, GRAD>(s, ca, 0xffffffffu, 32);
+    out.v[0] += ca.v[0];
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) out.v[1 + e] += ca.v[1 + e];
+  }
+}
+
+// depth 1 of one queue entry by the L lanes of a group.  Stores the result unless the entry must be
+// subdivided; returns that decision (same in every lane of the group).
+template <int KIND, bool GRAD>
+__device__ __forceinline__ bool depth1_entry(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
+                                             double* __restrict__ stamp, int L, int gl, unsigned gmask, bool valid) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  Acc<GRAD, NE> acc;
+  double centre = 0.0;
+  if (valid) {
+    centre = gl_nodes<KIND, GRAD>(s, d, X, Y, 1.0, 1.0, gl, L, acc);
+  } else {
+    acc.v[0] = 0.0;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc.v[1 + e] = 0.0;
+  }
+  for (int o = L >> 1; o > 0; o >>= 1) centre += __shfl_xor_sync(gmask, centre, o);
+  acc_shuffle_sum<KIND, GRAD>(s, acc, gmask, L);
+  if (!valid) return false;
+  if (1 < s.max_depth && fabs(acc.v[0] - centre) > d.thr[mode]) return true;
+  if (gl == 0) {
+    double* base = stamp + s.stamp_off + parent;
+    base[0] = acc.v[0];
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) {
+        const int p = s.plane[e];
+        if (p > 0) base[(long long)p * s.plane_stride] = acc.v[1 + e] * d.chain[e];
+      }
+  }
+  return false;
+}
+
+// whole warp: subdivide one depth-1 entry and store its integral
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void split_and_store(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
+                                                double* __restrict__ stamp, int* __restrict__ qcount) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  Acc<GRAD, NE> out;
+  split_cell<KIND, GRAD, APB_MAX_DEPTH - 2>(s, d, mode, 1, X, Y, out, qcount);
+  if ((threadIdx.x & 31) == 0) {
+    double* base = stamp + s.stamp_off + parent;
+    base[0] = out.v[0];
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) {
+        const int p = s.plane[e];
+        if (p > 0) base[(long long)p * s.plane_stride] = out.v[1 + e] * d.chain[e];
+      }
+  }
+}
+
+// spline sources carry up to 24 elements per accumulator: kept out of line so that their local
+// arrays do not inflate the register allocation of the analytic profiles
+template <bool GRAD>
+__device__ __noinline__ bool depth1_entry_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
+                                                 double* __restrict__ stamp, int L, int gl, unsigned gmask, bool valid) {
+  return depth1_entry<APB_SPLINE, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid);
+}
+template <bool GRAD>
+__device__ __noinline__ void split_and_store_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
+                                                    double* __restrict__ stamp, int* __restrict__ qcount) {
+  split_and_store<APB_SPLINE, GRAD>(s, d, mode, X, Y, parent, stamp, qcount);
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(128, 4) k_integrate(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn, int mode,
+                                                      double* __restrict__ stamp, Queues q, int L) {
+  const int n = min(q.count[1], q.cap[1]);
+  const Level& Lv = q.lv[1];
+  const int lane = threadIdx.x & 31;
+  const int epw = 32 / L, g = lane / L, gl = lane - g * L;
+  const unsigned gmask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << (g * L));
+  // persistent warps draw tasks (32/L queue entries) from a global counter: a warp that lands on
+  // entries needing subdivision simply draws fewer tasks (q.count[0] is zeroed by k_prep)
+  for (;;) {
+    int task = 0;
+    if (lane == 0) task = atomicAdd(&q.count[0], 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    const int base = task * epw;
+    if (base >= n) break;
+    const int t = base + g;
+    const bool valid = t < n;
+    int si = 0, parent = 0;
+    double X = 0, Y = 0;
+    if (valid) {
+      si = Lv.src[t];
+      X = Lv.x[t];
+      Y = Lv.y[t];
+      parent = Lv.parent[t];
+    }
+    bool split = false;
+    {
+      const DevSrc& s = src[si];
+      const DevDyn& d = dyn[si];
+      switch (s.kind) {
+        case APB_SERSIC: split = depth1_entry<APB_SERSIC, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_EXPONENTIAL: split = depth1_entry<APB_EXPONENTIAL, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_GAUSSIAN: split = depth1_entry<APB_GAUSSIAN, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_MOFFAT: split = depth1_entry<APB_MOFFAT, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_SPLINE: split = depth1_entry_spline<GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        default: break;
+      }
+    }
+    __syncwarp();
+    // entries that failed the error test: the whole warp subdivides them one after the other
+    unsigned need = __ballot_sync(0xffffffffu, split && gl == 0);
+    while (need) {
+      const int b = __ffs(need) - 1;
+      need &= need - 1;
+      const int sb = __shfl_sync(0xffffffffu, si, b), pb = __shfl_sync(0xffffffffu, parent, b);
+      const double Xb = __shfl_sync(0xffffffffu, X, b), Yb = __shfl_sync(0xffffffffu, Y, b);
+      const DevSrc& s = src[sb];
+      const DevDyn& d = dyn[sb];
+      switch (s.kind) {
+        case APB_SERSIC: split_and_store<APB_SERSIC, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_EXPONENTIAL: split_and_store<APB_EXPONENTIAL, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_GAUSSIAN: split_and_store<APB_GAUSSIAN, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_MOFFAT: split_and_store<APB_MOFFAT, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_SPLINE: split_and_store_spline<GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        default: break;
+      }
+    }
   }
 }
 

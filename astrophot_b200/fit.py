@@ -127,6 +127,11 @@ class LM(BaseOptimizer):
         self._c2 = torch.empty(2, dtype=torch.float64, device=dev)
         self._rpp = torch.empty(P, dtype=torch.float64, device=dev)
         self._rec = torch.empty(4, dtype=torch.float64, device=dev)
+        self._h = torch.empty(P, dtype=torch.float64, device=dev)
+        self._ha = torch.empty(P, dtype=torch.float64, device=dev)
+        # one C-ABI call per lambda-trial when the system fits the single-CTA solver and no
+        # collective sits between the pieces of a trial
+        self._fused_trial = kwargs.get("fused_trial", True) and (not self.distributed) and 0 < P <= 159
         self.hess = self.grad = None
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
@@ -209,21 +214,16 @@ class LM(BaseOptimizer):
             self.n_trials += 1
             if it > self.max_step_iter / 2 and self.L < 1e-3:
                 self.L = 1.0
-            h = self._solve(self.L, self.grad)
-            # geodesic acceleration (second directional derivative along h)
-            self.n_forward += 1
-            rpp = self._allreduce(self.plan.geodesic(x + d * h, h, d, out=self._rpp))
-            a = -self._solve(self.L, rpp) / 2 if self.L > 1e-4 else torch.zeros_like(h)
-            ha = h + a * self.acceleration
-            self.n_forward += 1
-            c2 = self._allreduce_chi(self.plan.chi2(x + ha, out=self._c2))
-            self._rec[0:2] = c2
-            self._rec[2] = torch.linalg.norm(a)
-            self._rec[3] = torch.linalg.norm(h)
-            csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
-            if ok < 0.0:
-                raise _QueueOverflow()
-            chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
+            if self._fused_trial:
+                self.n_forward += 2
+                self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha, self._rec)
+                csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
+                if ok < 0.0:
+                    raise _QueueOverflow()
+                ha = self._ha.clone()
+                chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
+            else:
+                ha, chi2, na, nh = self._trial_pieces(x, d)
             if self.verbose > 1:
                 AP_config.ap_logger.info(f"sub step L: {self.L}, Chi^2/DoF: {chi2}")
             if not np.isfinite(chi2):
@@ -274,6 +274,26 @@ class LM(BaseOptimizer):
                 return scary
             raise OptimizeStop("Could not find step to improve chi^2")
         return best
+
+    def _trial_pieces(self, x, d):
+        """One lambda-trial from separate calls (distributed fits need an all-reduce between the
+        pieces; large systems use the library solver).  Returns (ha, chi2/ndf, |a|, |h|)."""
+        h = self._solve(self.L, self.grad)
+        # geodesic acceleration (second directional derivative along h)
+        self.n_forward += 1
+        rpp = self._allreduce(self.plan.geodesic(x + d * h, h, d, out=self._rpp))
+        a = -self._solve(self.L, rpp) / 2 if self.L > 1e-4 else torch.zeros_like(h)
+        ha = h + a * self.acceleration
+        self.n_forward += 1
+        c2 = self._allreduce_chi(self.plan.chi2(x + ha, out=self._c2))
+        self._rec[0:2] = c2
+        self._rec[2] = torch.linalg.norm(a)
+        self._rec[3] = torch.linalg.norm(h)
+        csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
+        if ok < 0.0:
+            raise _QueueOverflow()
+        chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
+        return ha, chi2, na, nh
 
     @torch.no_grad()
     def fit(self):

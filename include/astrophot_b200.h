@@ -101,7 +101,8 @@ typedef struct {
 
 typedef struct {
   int64_t queue_capacity; /* entries per refinement level; 0 = automatic (grown by apb_plan_reserve) */
-  int32_t flags;          /* bits 0-1: APB_CONV_* override for every source */
+  int32_t flags;          /* bits 0-1: APB_CONV_* override for every source; bit 2: per-depth
+                             refinement launches instead of the fused k_integrate */
   int32_t _pad;
 } apb_opts_t;
 
@@ -160,6 +161,14 @@ int apb_plan_reserve(apb_plan_t *plan, const int64_t *caps);
  * H: device P*P (not modified), g, h: device P.  info: device int, 0 ok. */
 int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, int *info, void *stream);
 
+/* fit/lm.py:268-293, one pass of the lambda search with every tensor operation on the device:
+ *   h = solve(L, g);  rpp = geodesic(x + d h, h, d);  a = -solve(L, rpp)/2 (zeros when L <= 1e-4);
+ *   ha = h + acceleration a;  rec = { chi2(x + ha), status flag (see apb_chi2), |a|, |h| }.
+ * H, g from the last apb_normal_eq; h_out, ha_out: device, n_par doubles; rec: device, 4 doubles,
+ * the one record the host reads back per trial.  n_par <= 159 (single-CTA solver). */
+int apb_lm_trial(apb_plan_t *plan, const double *H, const double *g, double L, const double *x_rep, double d,
+                 double acceleration, double *h_out, double *ha_out, double *rec, void *stream);
+
 int apb_plan_stats(apb_plan_t *plan, apb_stats_t *out); /* synchronises the plan's last stream */
 
 /* ---- measurement (bench.py; no reference counterpart) ---------------------------------- */
@@ -172,6 +181,7 @@ int apb_profile(apb_plan_t *plan, int enable); /* bracket every kernel launch wi
 int apb_profile_read(apb_plan_t *plan, apb_kernel_time_t *out, int max_out, int *n_out, int reset);
 long long apb_launch_count(void);               /* kernels launched by this library since load */
 int apb_bench_peaks(double *dfma_tflops, double *copy_gbs); /* DFMA-stream and fp64 copy ceilings, synchronous */
+int apb_fft_length(int n); /* transform length the FFT convolution uses for a padded stamp of n pixels */
 const char *apb_last_error(void);
 int apb_version(void);
 

@@ -97,6 +97,27 @@ def test_refinement_queue_grows_on_overflow():
     np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-8)
 
 
+@pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat_psf_model", "crowded"])
+def test_fused_integration_equals_per_depth_launches(name):
+    """k_integrate (one cooperative launch, lane-parallel Gauss-Legendre nodes) against the
+    per-depth k_select / k_refine / k_reduce_level / k_scatter launches: same queues, same
+    decisions, sums differ only in association order."""
+    from astrophot_b200.cabi import Plan
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name)
+    scene, _ = lower(model)
+    pa, pb = Plan(scene), Plan(scene, fused_integration=False)
+    a = pa.sample(fix["x_val"])
+    b = pb.sample(fix["x_val"])
+    for u, v in zip(a, b):
+        assert rel_err(u.cpu().numpy(), v.cpu().numpy()) < 1e-13
+    assert pa.stats()["queued"] == pb.stats()["queued"]
+    Ja = np.concatenate([j.cpu().numpy().reshape(-1, scene.n_par) for j in pa.jacobian(fix["x_rep"], as_rep=True)])
+    Jb = np.concatenate([j.cpu().numpy().reshape(-1, scene.n_par) for j in pb.jacobian(fix["x_rep"], as_rep=True)])
+    scale = np.maximum(np.abs(Jb).max(axis=0), 1e-300)
+    assert np.max(np.abs(Ja - Jb) / scale) < 1e-12
+
+
 @pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
 def test_sample_vs_oracle_and_reference(name):
     fix = load_golden(name)
@@ -186,6 +207,21 @@ def test_lm_fit_matches_reference(name):
     assert abs(min(res.loss_history) - ref_loss.min()) / ref_loss.min() < 1e-8
     # fitted parameters were written back to the model (lm.py:491)
     np.testing.assert_allclose(model.parameters.vector_representation().numpy(), res.res(), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["psf_sersic", "group"])
+def test_lm_trial_pieces_equal_fused_trial(name):
+    """apb_lm_trial (solve, geodesic, solve, chi^2 in one call) against the same trial made of
+    separate calls with torch vector algebra in between (the path distributed fits use)."""
+    fix = load_golden(name)
+    m1, _ = scenes.build(ap, name, data=golden_data(fix))
+    m2, _ = scenes.build(ap, name, data=golden_data(fix))
+    r1 = ap.fit.LM(m1, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0).fit()
+    r2 = ap.fit.LM(m2, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0, fused_trial=False).fit()
+    assert r1._fused_trial and not r2._fused_trial
+    np.testing.assert_allclose(r1.loss_history, r2.loss_history, rtol=1e-11)
+    np.testing.assert_allclose(r1.L_history, r2.L_history, rtol=1e-12)
+    np.testing.assert_allclose(r1.lambda_history[-1], r2.lambda_history[-1], rtol=1e-9, atol=1e-10)
 
 
 def test_public_api_sample_and_jacobian():
