@@ -90,7 +90,7 @@ def load_library(path=None):
     L.apb_geodesic.argtypes = [vp, dp, dp, C.c_double, dp, vp]
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
-    L.apb_lm_trial.argtypes = [vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
+    L.apb_lm_trial.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
     L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
     L.apb_plan_reserve.argtypes = [vp, C.POINTER(C.c_int64)]
     L.apb_profile.argtypes = [vp, C.c_int]
@@ -136,14 +136,17 @@ def _dev_f64(x):
 class Plan:
     """A lowered model tree resident on the device (``apb_plan_t``)."""
 
-    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True):
+    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True, share=None):
         """``conv``: None (per-source psf_convolve_mode), "direct" or "fft" to force one
-        convolution kernel family for every source (tests, benchmarks)."""
+        convolution kernel family for every source (tests, benchmarks).
+        ``share``: another Plan of the same scene whose device copies of data / weight / mask / PSFs
+        are reused (the forward-only twin LM uses for the concurrent chi^2 pass)."""
         _require_cuda()
         L = lib()
         self.scene = scene
         self.n_par = scene.n_par
         self._keep = []          # tensors whose storage the plan points into
+        self._masks = {}
         n_img, n_src, n_psf = len(scene.images), len(scene.sources), len(scene.psfs)
         imgs = (apb_image_t * max(n_img, 1))()
         self.shapes = []
@@ -157,20 +160,24 @@ class Plan:
             for name in ("data", "weight"):
                 arr = getattr(im, name)
                 if arr is not None:
-                    t = _dev_f64(arr)
+                    t = share.image_buffers[i][name] if share is not None else _dev_f64(arr)
                     self._keep.append(t)
                     bufs[name] = t
                     setattr(imgs[i], name, t.data_ptr())
             self.image_buffers.append(bufs)
             if im.mask is not None:
-                m = torch.as_tensor(im.mask).to(device="cuda", dtype=torch.uint8).contiguous()
+                m = share._masks[i] if share is not None else \
+                    torch.as_tensor(im.mask).to(device="cuda", dtype=torch.uint8).contiguous()
                 self._keep.append(m)
                 imgs[i].mask = m.data_ptr()
+                self._masks[i] = m
             self.shapes.append((im.H, im.W))
         psfs = (apb_psf_t * max(n_psf, 1))()
+        self._psfs = []
         for i, ps in enumerate(scene.psfs):
-            t = _dev_f64(ps.data)
+            t = share._psfs[i] if share is not None else _dev_f64(ps.data)
             self._keep.append(t)
+            self._psfs.append(t)
             psfs[i].h, psfs[i].w, psfs[i].data = t.shape[0], t.shape[1], t.data_ptr()
         pars = (apb_param_t * max(self.n_par, 1))()
         for k in range(self.n_par):
@@ -281,9 +288,11 @@ class Plan:
                "apb_geodesic")
         return out
 
-    def lm_trial(self, H, g, L, x, d, acceleration, h_out, ha_out, rec):
-        """One lambda-trial on the device (fit/lm.py:274-293); rec <- [chi2, flag, |a|, |h|]."""
-        _check(self._L.apb_lm_trial(self._h, H.data_ptr(), g.data_ptr(), float(L), x.data_ptr(), float(d),
+    def lm_trial(self, H, g, L, x, d, acceleration, h_out, ha_out, rec, twin=None):
+        """One lambda-trial on the device (fit/lm.py:274-293); rec <- [chi2, flag, |a|, |h|].
+        ``twin``: second Plan of the same scene for the concurrent chi^2 pass (acceleration == 0)."""
+        _check(self._L.apb_lm_trial(self._h, twin._h if twin is not None else None, H.data_ptr(), g.data_ptr(),
+                                    float(L), x.data_ptr(), float(d),
                                     float(acceleration), h_out.data_ptr(), ha_out.data_ptr(), rec.data_ptr(), _stream()),
                "apb_lm_trial")
         return rec

@@ -40,11 +40,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -117,7 +117,9 @@ struct apb_plan {
   BlockDesc* d_vblocks = nullptr; int n_vblocks = 0;
   int *d_act_slot = nullptr, *d_act_off = nullptr;
   double* d_part = nullptr;
-  double *d_xtmp = nullptr, *d_xtmp2 = nullptr, *d_rpp = nullptr, *d_atmp = nullptr;
+  double *d_xtmp = nullptr, *d_xtmp2 = nullptr, *d_rpp = nullptr, *d_atmp = nullptr, *d_atmp2 = nullptr, *d_rec2 = nullptr;
+  cudaStream_t trial_stream = nullptr;   // concurrent chi^2 pass of apb_lm_trial (on the second plan)
+  cudaEvent_t ev_trial_fork = nullptr, ev_trial_join = nullptr;
   apb_stats_t stats{};
   long long launches = 0;
   cudaStream_t last_stream = nullptr;
@@ -220,6 +222,9 @@ extern "C" int apb_plan_destroy(apb_plan_t* p) {
   if (!p) return 0;
   for (void* q : p->owned) cudaFree(q);
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->trial_stream) cudaStreamDestroy(p->trial_stream);
+  if (p->ev_trial_fork) cudaEventDestroy(p->ev_trial_fork);
+  if (p->ev_trial_join) cudaEventDestroy(p->ev_trial_join);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
   for (int d = 1; d <= APB_MAX_DEPTH; ++d) {
@@ -709,6 +714,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   PRC(own_alloc(p, (void**)&p->d_xtmp2, sizeof(double) * (size_t)std::max(n_par, 1)));
   PRC(own_alloc(p, (void**)&p->d_rpp, sizeof(double) * (size_t)std::max(n_par, 1)));
   PRC(own_alloc(p, (void**)&p->d_atmp, sizeof(double) * (size_t)std::max(n_par, 1)));
+  PRC(own_alloc(p, (void**)&p->d_atmp2, sizeof(double) * (size_t)std::max(n_par, 1)));
+  PRC(own_alloc(p, (void**)&p->d_rec2, sizeof(double) * 4));
   PCU(cudaMemset(p->d_stamp, 0, sizeof(double) * (size_t)std::max<long long>(stamp_total, 1)));
 
   // ---- queues: depth 1 can never hold more than the first-pass pixels; deeper levels start at a
@@ -747,6 +754,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   }
 
   PCU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+  PCU(cudaStreamCreateWithFlags(&p->trial_stream, cudaStreamNonBlocking));
+  PCU(cudaEventCreateWithFlags(&p->ev_trial_fork, cudaEventDisableTiming));
+  PCU(cudaEventCreateWithFlags(&p->ev_trial_join, cudaEventDisableTiming));
   PCU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   PCU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
 
@@ -805,7 +815,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
     st = main_st;
   }
   if (T.n_tiles) {
-    PB(K_FIRST);
+    PB(grad ? K_FIRST_G : K_FIRST);
     if (grad) k_first<true><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
     else k_first<false><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
     LAUNCH_CHECK();
@@ -824,7 +834,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
         PB(K_SELECT);
         k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
         LAUNCH_CHECK();
-        PB(K_INTEGRATE);
+        PB(grad ? K_INTEGRATE_G : K_INTEGRATE);
         if (grad) k_integrate<true><<<p->integrate_grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
         else k_integrate<false><<<p->integrate_grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
         LAUNCH_CHECK();
@@ -1036,19 +1046,42 @@ static int lm_solve_launch(const double* H, const double* g, double L, int P, do
 //   ha = h + acceleration a;  rec = [chi2(x + ha), status flag, |a|, |h|]
 // H, g: the normal equations of the last apb_normal_eq.  h_out, ha_out: device, P doubles.
 // rec: device, 4 doubles -- the single record the host reads back per trial.  P <= 159.
-extern "C" int apb_lm_trial(apb_plan_t* p, const double* H, const double* g, double L, const double* x_rep, double d,
-                            double acceleration, double* h_out, double* ha_out, double* rec, void* stream) {
+// With acceleration == 0 (the reference's default) x + ha = x + h does not depend on the geodesic
+// term, so when a second, forward-only plan of the same scene is supplied the chi^2 pass runs on
+// it concurrently (own stream, own workspace) with the geodesic pass: both are chains of small
+// latency-bound launches, and side by side they take about the time of one.
+extern "C" int apb_lm_trial(apb_plan_t* p, apb_plan_t* p2, const double* H, const double* g, double L,
+                            const double* x_rep, double d, double acceleration, double* h_out, double* ha_out,
+                            double* rec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (begin_call(p, st)) return -1;
   const int P = p->n_par;
   if (P <= 0) APB_FAIL("apb_lm_trial: no parameters");
+  const bool overlap = p2 != nullptr && acceleration == 0.0;
+  if (overlap && (p2->n_par != P || p2->n_img != p->n_img || p2->n_src != p->n_src))
+    APB_FAIL("apb_lm_trial: the second plan does not describe the same scene");
   int rc;
-  LmEpi e1{1, x_rep, nullptr, d, 0.0, p->d_xtmp, nullptr, nullptr};
+  LmEpi e1{1, x_rep, nullptr, d, 0.0, p->d_xtmp, overlap ? p->d_xtmp2 : nullptr, nullptr};
   if ((rc = lm_solve_launch(H, g, L, P, h_out, nullptr, e1, st))) return rc;
+  if (overlap) {
+    CU(cudaEventRecord(p->ev_trial_fork, st));
+    CU(cudaStreamWaitEvent(p->trial_stream, p->ev_trial_fork, 0));
+    p2->launches = 0;
+    p2->last_stream = p->trial_stream;
+    if ((rc = chi2_core(p2, p->d_xtmp2, p->d_rec2, p->trial_stream))) return rc;
+    CU(cudaEventRecord(p->ev_trial_join, p->trial_stream));
+  }
   if ((rc = geodesic_core(p, p->d_xtmp, h_out, d, p->d_rpp, st))) return rc;
-  LmEpi e2{2, x_rep, h_out, d, acceleration, p->d_xtmp2, ha_out, rec};
-  if ((rc = lm_solve_launch(H, p->d_rpp, L, P, p->d_atmp, nullptr, e2, st))) return rc;
-  if ((rc = chi2_core(p, p->d_xtmp2, rec, st))) return rc;
+  LmEpi e2{2, x_rep, h_out, d, acceleration, overlap ? p->d_atmp : p->d_xtmp2, ha_out, rec};
+  if ((rc = lm_solve_launch(H, p->d_rpp, L, P, p->d_atmp2, nullptr, e2, st))) return rc;
+  if (overlap) {
+    CU(cudaStreamWaitEvent(st, p->ev_trial_join, 0));
+    k_trial_join<<<1, 1, 0, st>>>(p->d_rec2, p->q.overflow, p2->q.overflow, rec);
+    p->launches += p2->launches + 1;
+    g_launches++;
+  } else {
+    if ((rc = chi2_core(p, p->d_xtmp2, rec, st))) return rc;
+  }
   p->stats.launches = p->launches + 2;
   return 0;
 }

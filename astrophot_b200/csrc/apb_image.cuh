@@ -470,9 +470,16 @@ struct LmEpi {
   const double* hin;
   double d, acc;
   double* xout;
-  double* ha;
+  double* ha;     // mode 1: x + h (or NULL);  mode 2: ha
   double* rec;
 };
+
+// joins the concurrent chi^2 pass of a trial into the record the host reads
+__global__ void k_trial_join(const double* __restrict__ c2, const int* __restrict__ ovf_a, const int* __restrict__ ovf_b,
+                             double* __restrict__ rec) {
+  rec[0] = c2[0];
+  rec[1] = (*ovf_a || *ovf_b) ? -1.0 : c2[1];
+}
 
 __global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict__ H, const double* __restrict__ g,
                                                         double L, int P, double* __restrict__ h, int* __restrict__ info,
@@ -524,7 +531,10 @@ __global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict
     }
     if (info) *info = bad;
     if (epi.mode == 1) {
-      for (int i = 0; i < P; ++i) epi.xout[i] = epi.x[i] + epi.d * h[i];
+      for (int i = 0; i < P; ++i) {
+        epi.xout[i] = epi.x[i] + epi.d * h[i];
+        if (epi.ha) epi.ha[i] = epi.x[i] + h[i];
+      }
     } else if (epi.mode == 2) {
       double na = 0.0, nh = 0.0;
       for (int i = 0; i < P; ++i) {

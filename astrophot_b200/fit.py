@@ -132,6 +132,12 @@ class LM(BaseOptimizer):
         # one C-ABI call per lambda-trial when the system fits the single-CTA solver and no
         # collective sits between the pieces of a trial
         self._fused_trial = kwargs.get("fused_trial", True) and (not self.distributed) and 0 < P <= 159
+        # acceleration == 0 (default): chi2(x + h) is independent of the geodesic term; a forward-only twin
+        # plan lets apb_lm_trial evaluate it concurrently with the geodesic pass
+        self.plan2 = None
+        if self._fused_trial and self.acceleration == 0 and kwargs.get("overlap_trial", True):
+            self.plan2 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
+                              share=self.plan)
         self.hess = self.grad = None
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
@@ -157,6 +163,8 @@ class LM(BaseOptimizer):
             if ok >= 0.0:
                 return c / self.ndf if ok >= 1.0 else float("nan")
             self.plan.reserve()
+            if self.plan2 is not None:
+                self.plan2.reserve()
         raise OptimizeStop("sub-pixel refinement queues keep overflowing")
 
     def _allreduce_chi(self, c2):
@@ -191,6 +199,8 @@ class LM(BaseOptimizer):
                 return self._step(chi2)
             except _QueueOverflow:
                 self.plan.reserve()
+                if self.plan2 is not None:
+                    self.plan2.reserve()
                 self.L = L0
         raise OptimizeStop("sub-pixel refinement queues keep overflowing")
 
@@ -216,7 +226,8 @@ class LM(BaseOptimizer):
                 self.L = 1.0
             if self._fused_trial:
                 self.n_forward += 2
-                self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha, self._rec)
+                self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha, self._rec,
+                                   twin=self.plan2)
                 csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
                 if ok < 0.0:
                     raise _QueueOverflow()

@@ -165,9 +165,13 @@ int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, i
  *   h = solve(L, g);  rpp = geodesic(x + d h, h, d);  a = -solve(L, rpp)/2 (zeros when L <= 1e-4);
  *   ha = h + acceleration a;  rec = { chi2(x + ha), status flag (see apb_chi2), |a|, |h| }.
  * H, g from the last apb_normal_eq; h_out, ha_out: device, n_par doubles; rec: device, 4 doubles,
- * the one record the host reads back per trial.  n_par <= 159 (single-CTA solver). */
-int apb_lm_trial(apb_plan_t *plan, const double *H, const double *g, double L, const double *x_rep, double d,
-                 double acceleration, double *h_out, double *ha_out, double *rec, void *stream);
+ * the one record the host reads back per trial.  n_par <= 159 (single-CTA solver).
+ * plan2: NULL, or a second plan created from the same scene: when acceleration == 0 (the reference's
+ * default, lm.py:187) chi2(x + h) does not depend on the geodesic term and is evaluated on plan2,
+ * concurrently with the geodesic pass on plan. */
+int apb_lm_trial(apb_plan_t *plan, apb_plan_t *plan2, const double *H, const double *g, double L,
+                 const double *x_rep, double d, double acceleration, double *h_out, double *ha_out, double *rec,
+                 void *stream);
 
 int apb_plan_stats(apb_plan_t *plan, apb_stats_t *out); /* synchronises the plan's last stream */
 

@@ -95,6 +95,15 @@ def test_refinement_queue_grows_on_overflow():
     model, _ = scenes.build(ap, "c1_sersic", data=golden_data(fix))
     res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=4, relative_tolerance=0.0, queue_capacity=64).fit()
     np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-8)
+    model, _ = scenes.build(ap, "c1_sersic", data=golden_data(fix))
+    from astrophot_b200 import cabi
+    orig = cabi.Plan.__init__
+    try:   # per-depth launches (the only path whose deeper queues can overflow), inside LM
+        cabi.Plan.__init__ = lambda self, *a, **k: orig(self, *a, **{**k, "fused_integration": False})
+        res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=4, relative_tolerance=0.0, queue_capacity=64).fit()
+    finally:
+        cabi.Plan.__init__ = orig
+    np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-8)
 
 
 @pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat_psf_model", "crowded"])
@@ -218,7 +227,11 @@ def test_lm_trial_pieces_equal_fused_trial(name):
     m2, _ = scenes.build(ap, name, data=golden_data(fix))
     r1 = ap.fit.LM(m1, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0).fit()
     r2 = ap.fit.LM(m2, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0, fused_trial=False).fit()
-    assert r1._fused_trial and not r2._fused_trial
+    assert r1._fused_trial and r1.plan2 is not None and not r2._fused_trial
+    m3, _ = scenes.build(ap, name, data=golden_data(fix))
+    r3 = ap.fit.LM(m3, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0, overlap_trial=False).fit()
+    assert r3._fused_trial and r3.plan2 is None
+    np.testing.assert_allclose(r1.loss_history, r3.loss_history, rtol=1e-13)
     np.testing.assert_allclose(r1.loss_history, r2.loss_history, rtol=1e-11)
     np.testing.assert_allclose(r1.L_history, r2.L_history, rtol=1e-12)
     np.testing.assert_allclose(r1.lambda_history[-1], r2.lambda_history[-1], rtol=1e-9, atol=1e-10)
