@@ -58,7 +58,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_lm_trial", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -91,6 +91,8 @@ def load_library(path=None):
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
     L.apb_lm_trial.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
+    L.apb_lm_trial_begin.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, dp, dp, vp]
+    L.apb_lm_trial_end.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp, vp]
     L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
     L.apb_plan_reserve.argtypes = [vp, C.POINTER(C.c_int64)]
     L.apb_profile.argtypes = [vp, C.c_int]
@@ -295,6 +297,18 @@ class Plan:
                                     float(L), x.data_ptr(), float(d),
                                     float(acceleration), h_out.data_ptr(), ha_out.data_ptr(), rec.data_ptr(), _stream()),
                "apb_lm_trial")
+        return rec
+
+    def lm_trial_begin(self, H, g, L, x, d, h_out, buf, twin=None):
+        """First half of a sharded trial: buf <- [local rpp (P), local chi2, #non-finite, #overflow]."""
+        _check(self._L.apb_lm_trial_begin(self._h, twin._h if twin is not None else None, H.data_ptr(), g.data_ptr(),
+                                          float(L), x.data_ptr(), float(d), h_out.data_ptr(), buf.data_ptr(), _stream()),
+               "apb_lm_trial_begin")
+
+    def lm_trial_end(self, H, L, x, h, buf, ha_out, rec):
+        """Second half (after the all-reduce of buf): rec <- [chi2, flag, |a|, |h|], ha_out <- h."""
+        _check(self._L.apb_lm_trial_end(self._h, H.data_ptr(), float(L), x.data_ptr(), h.data_ptr(), buf.data_ptr(),
+                                        ha_out.data_ptr(), rec.data_ptr(), _stream()), "apb_lm_trial_end")
         return rec
 
     def chi2(self, x, out=None):

@@ -1061,7 +1061,7 @@ extern "C" int apb_lm_trial(apb_plan_t* p, apb_plan_t* p2, const double* H, cons
   if (overlap && (p2->n_par != P || p2->n_img != p->n_img || p2->n_src != p->n_src))
     APB_FAIL("apb_lm_trial: the second plan does not describe the same scene");
   int rc;
-  LmEpi e1{1, x_rep, nullptr, d, 0.0, p->d_xtmp, overlap ? p->d_xtmp2 : nullptr, nullptr};
+  LmEpi e1{1, x_rep, nullptr, d, 0.0, p->d_xtmp, overlap ? p->d_xtmp2 : nullptr, nullptr, nullptr};
   if ((rc = lm_solve_launch(H, g, L, P, h_out, nullptr, e1, st))) return rc;
   if (overlap) {
     CU(cudaEventRecord(p->ev_trial_fork, st));
@@ -1072,7 +1072,7 @@ extern "C" int apb_lm_trial(apb_plan_t* p, apb_plan_t* p2, const double* H, cons
     CU(cudaEventRecord(p->ev_trial_join, p->trial_stream));
   }
   if ((rc = geodesic_core(p, p->d_xtmp, h_out, d, p->d_rpp, st))) return rc;
-  LmEpi e2{2, x_rep, h_out, d, acceleration, overlap ? p->d_atmp : p->d_xtmp2, ha_out, rec};
+  LmEpi e2{2, x_rep, h_out, d, acceleration, overlap ? p->d_atmp : p->d_xtmp2, ha_out, rec, nullptr};
   if ((rc = lm_solve_launch(H, p->d_rpp, L, P, p->d_atmp2, nullptr, e2, st))) return rc;
   if (overlap) {
     CU(cudaStreamWaitEvent(st, p->ev_trial_join, 0));
@@ -1086,9 +1086,55 @@ extern "C" int apb_lm_trial(apb_plan_t* p, apb_plan_t* p2, const double* H, cons
   return 0;
 }
 
+// The same trial in two halves, for fits whose pixels are spread over several GPUs (acceleration == 0):
+//   begin: h = solve(L, g); local rpp and local chi2(x + h) -> buf = { rpp[P], chi2, #non-finite, #overflow }
+//   (caller: sum all-reduce of buf over the ranks)
+//   end:   a = -solve(L, rpp)/2, rec = { chi2, status flag, |a|, |h| }, ha = h
+// On one GPU the two are simply called back to back.
+extern "C" int apb_lm_trial_begin(apb_plan_t* p, apb_plan_t* p2, const double* H, const double* g, double L,
+                                  const double* x_rep, double d, double* h_out, double* buf, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (begin_call(p, st)) return -1;
+  const int P = p->n_par;
+  if (P <= 0) APB_FAIL("apb_lm_trial_begin: no parameters");
+  if (p2 && (p2->n_par != P || p2->n_img != p->n_img || p2->n_src != p->n_src))
+    APB_FAIL("apb_lm_trial_begin: the second plan does not describe the same scene");
+  int rc;
+  LmEpi e1{1, x_rep, nullptr, d, 0.0, p->d_xtmp, p->d_xtmp2, nullptr, nullptr};
+  if ((rc = lm_solve_launch(H, g, L, P, h_out, nullptr, e1, st))) return rc;
+  if (p2) {
+    CU(cudaEventRecord(p->ev_trial_fork, st));
+    CU(cudaStreamWaitEvent(p->trial_stream, p->ev_trial_fork, 0));
+    p2->launches = 0;
+    p2->last_stream = p->trial_stream;
+    if ((rc = chi2_core(p2, p->d_xtmp2, p->d_rec2, p->trial_stream))) return rc;
+    CU(cudaEventRecord(p->ev_trial_join, p->trial_stream));
+  }
+  if ((rc = geodesic_core(p, p->d_xtmp, h_out, d, buf, st))) return rc;
+  if (p2) {
+    CU(cudaStreamWaitEvent(st, p->ev_trial_join, 0));
+    p->launches += p2->launches;
+  } else {
+    if ((rc = chi2_core(p, p->d_xtmp2, p->d_rec2, st))) return rc;
+  }
+  k_trial_tail<<<1, 1, 0, st>>>(p->d_rec2, p->q.overflow, p2 ? p2->q.overflow : nullptr, buf + P);
+  g_launches++;
+  p->stats.launches = p->launches + 2;
+  return 0;
+}
+
+extern "C" int apb_lm_trial_end(apb_plan_t* p, const double* H, double L, const double* x_rep, const double* h,
+                                const double* buf, double* ha_out, double* rec, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p) APB_FAIL("plan is NULL");
+  const int P = p->n_par;
+  LmEpi e2{2, x_rep, h, 0.0, 0.0, p->d_atmp, ha_out, rec, buf + P};
+  return lm_solve_launch(H, buf, L, P, p->d_atmp2, nullptr, e2, st);
+}
+
 extern "C" int apb_lm_solve(const double* H, const double* g, double L, int P, double* h, int* info, void* stream) {
   if (P <= 0) return 0;
-  LmEpi e0{0, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, nullptr};
+  LmEpi e0{0, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr};
   return lm_solve_launch(H, g, L, P, h, info, e0, (cudaStream_t)stream);
 }
 

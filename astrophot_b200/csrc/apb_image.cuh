@@ -472,6 +472,7 @@ struct LmEpi {
   double* xout;
   double* ha;     // mode 1: x + h (or NULL);  mode 2: ha
   double* rec;
+  const double* tail;  // mode 2: {chi^2, non-finite count, overflow count} to fold into rec, or NULL
 };
 
 // joins the concurrent chi^2 pass of a trial into the record the host reads
@@ -479,6 +480,15 @@ __global__ void k_trial_join(const double* __restrict__ c2, const int* __restric
                              double* __restrict__ rec) {
   rec[0] = c2[0];
   rec[1] = (*ovf_a || *ovf_b) ? -1.0 : c2[1];
+}
+// same, as summable counts for a cross-rank all-reduce: tail = {chi^2, ranks with non-finite pixels,
+// ranks whose refinement queues overflowed}
+__global__ void k_trial_tail(const double* __restrict__ c2, const int* __restrict__ ovf_a, const int* __restrict__ ovf_b,
+                             double* __restrict__ tail) {
+  const bool ovf = *ovf_a || (ovf_b && *ovf_b) || c2[1] < 0.0;
+  tail[0] = c2[0];
+  tail[1] = (!ovf && c2[1] == 0.0) ? 1.0 : 0.0;
+  tail[2] = ovf ? 1.0 : 0.0;
 }
 
 __global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict__ H, const double* __restrict__ g,
@@ -548,6 +558,10 @@ __global__ void __launch_bounds__(256) k_lm_solve_small(const double* __restrict
       }
       epi.rec[2] = sqrt(na);
       epi.rec[3] = sqrt(nh);
+      if (epi.tail) {   // (summed) tail of apb_lm_trial_begin -> chi^2 and status flag
+        epi.rec[0] = epi.tail[0];
+        epi.rec[1] = epi.tail[2] > 0.0 ? -1.0 : (epi.tail[1] > 0.0 ? 0.0 : 1.0);
+      }
     }
   }
 }

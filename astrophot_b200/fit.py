@@ -131,7 +131,10 @@ class LM(BaseOptimizer):
         self._ha = torch.empty(P, dtype=torch.float64, device=dev)
         # one C-ABI call per lambda-trial when the system fits the single-CTA solver and no
         # collective sits between the pieces of a trial
-        self._fused_trial = kwargs.get("fused_trial", True) and (not self.distributed) and 0 < P <= 159
+        self._fused_trial = kwargs.get("fused_trial", True) and 0 < P <= 159 and \
+            (not self.distributed or self.acceleration == 0)
+        self._tbuf = torch.empty(P + 3, dtype=torch.float64, device=dev)
+        self._split_trial = bool(kwargs.get("split_trial", False)) and self.acceleration == 0
         # acceleration == 0 (default): chi2(x + h) is independent of the geodesic term; a forward-only twin
         # plan lets apb_lm_trial evaluate it concurrently with the geodesic pass
         self.plan2 = None
@@ -226,8 +229,14 @@ class LM(BaseOptimizer):
                 self.L = 1.0
             if self._fused_trial:
                 self.n_forward += 2
-                self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha, self._rec,
-                                   twin=self.plan2)
+                if self.distributed or self._split_trial:
+                    # sharded pixels: local rpp / chi2, one all-reduce of P + 3 doubles, then the second solve
+                    self.plan.lm_trial_begin(self.hess, self.grad, self.L, x, d, self._h, self._tbuf, twin=self.plan2)
+                    self._allreduce(self._tbuf)
+                    self.plan.lm_trial_end(self.hess, self.L, x, self._h, self._tbuf, self._ha, self._rec)
+                else:
+                    self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha,
+                                       self._rec, twin=self.plan2)
                 csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
                 if ok < 0.0:
                     raise _QueueOverflow()

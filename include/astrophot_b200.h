@@ -173,6 +173,15 @@ int apb_lm_trial(apb_plan_t *plan, apb_plan_t *plan2, const double *H, const dou
                  const double *x_rep, double d, double acceleration, double *h_out, double *ha_out, double *rec,
                  void *stream);
 
+/* The same trial in two halves for fits sharded over several GPUs (acceleration == 0 only):
+ *   begin: h = solve(L, g); buf = { local rpp[n_par], local chi2(x + h), #non-finite, #overflow }
+ *   -- the caller sums buf over the ranks (n_par + 3 doubles, one all-reduce per trial) --
+ *   end:   a = -solve(L, rpp)/2;  rec = { chi2, status flag, |a|, |h| };  ha = h. */
+int apb_lm_trial_begin(apb_plan_t *plan, apb_plan_t *plan2, const double *H, const double *g, double L,
+                       const double *x_rep, double d, double *h_out, double *buf, void *stream);
+int apb_lm_trial_end(apb_plan_t *plan, const double *H, double L, const double *x_rep, const double *h,
+                     const double *buf, double *ha_out, double *rec, void *stream);
+
 int apb_plan_stats(apb_plan_t *plan, apb_stats_t *out); /* synchronises the plan's last stream */
 
 /* ---- measurement (bench.py; no reference counterpart) ---------------------------------- */

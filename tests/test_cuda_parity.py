@@ -232,6 +232,11 @@ def test_lm_trial_pieces_equal_fused_trial(name):
     r3 = ap.fit.LM(m3, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0, overlap_trial=False).fit()
     assert r3._fused_trial and r3.plan2 is None
     np.testing.assert_allclose(r1.loss_history, r3.loss_history, rtol=1e-13)
+    # the two-halves form sharded fits use (all-reduce between them), here on one GPU
+    m4, _ = scenes.build(ap, name, data=golden_data(fix))
+    r4 = ap.fit.LM(m4, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0, split_trial=True).fit()
+    np.testing.assert_allclose(r1.loss_history, r4.loss_history, rtol=1e-13)
+    np.testing.assert_allclose(r1.L_history, r4.L_history, rtol=1e-12)
     np.testing.assert_allclose(r1.loss_history, r2.loss_history, rtol=1e-11)
     np.testing.assert_allclose(r1.L_history, r2.L_history, rtol=1e-12)
     np.testing.assert_allclose(r1.lambda_history[-1], r2.lambda_history[-1], rtol=1e-9, atol=1e-10)
