@@ -97,7 +97,7 @@ struct apb_plan {
   int NVp_grad = 1;
   bool use_coop = false;           // fused integration kernel (k_integrate) instead of per-depth launches
   int refine_lanes = 16;           // lanes sharing one queue entry
-  int integrate_grid = 148 * 4;    // persistent CTAs of k_integrate (one resident wave)
+  int integrate_grid[2] = {148 * 4, 148 * 3};   // [grad] persistent CTAs of k_integrate (one resident wave)
   // arenas
   double *d_stamp = nullptr, *d_out = nullptr, *d_psfst = nullptr, *d_meanpart = nullptr, *d_skyJ = nullptr;
   // queues
@@ -107,6 +107,7 @@ struct apb_plan {
   int4* img_tiles = nullptr; int n_img_tiles = 0;
   int *bin_ptr = nullptr, *bin_src = nullptr;
   double* d_chipart = nullptr;
+  unsigned int* d_done = nullptr;   // CTA completion counter of k_assemble (last CTA sums the partials)
   // per-image buffers
   std::vector<double*> h_model, h_resid, h_resid2;
   double **d_model = nullptr, **d_resid = nullptr, **d_resid2 = nullptr, **d_userptr = nullptr;
@@ -617,6 +618,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PRC(own_upload(p, bptr, &p->bin_ptr));
     PRC(own_upload(p, bsrc, &p->bin_src));
     PRC(own_alloc(p, (void**)&p->d_chipart, sizeof(double) * 2 * itiles.size()));
+    PRC(own_alloc(p, (void**)&p->d_done, sizeof(unsigned int)));
+    PCU(cudaMemset(p->d_done, 0, sizeof(unsigned int)));
   }
 
   // ---- normal-equation work lists: diagonal blocks + overlapping pairs, split in <=8-plane
@@ -750,7 +753,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate<false>, 128, 0));
     PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate<true>, 128, 0));
-    p->integrate_grid = sms * std::max(1, std::min(b0, b1));
+    p->integrate_grid[0] = sms * std::max(1, b0);
+    p->integrate_grid[1] = sms * std::max(1, b1);
   }
 
   PCU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
@@ -788,7 +792,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   if (n_src == 0) return 0;
   ModeTables& T = p->mt[mode];
   PB(K_PREP);
-  k_prep<<<ceil_div(n_src, 128), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad);
+  k_prep<<<ceil_div(n_src, 4), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad);
   LAUNCH_CHECK();
   // PSF branch on the side stream: shifted stamps and (FFT sources) their spectra depend only on
   // k_prep, so they overlap the first pass and the adaptive integration of the profiles
@@ -835,8 +839,8 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
         k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
         LAUNCH_CHECK();
         PB(grad ? K_INTEGRATE_G : K_INTEGRATE);
-        if (grad) k_integrate<true><<<p->integrate_grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
-        else k_integrate<false><<<p->integrate_grid, 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
+        if (grad) k_integrate<true><<<p->integrate_grid[1], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
+        else k_integrate<false><<<p->integrate_grid[0], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
         LAUNCH_CHECK();
       } else {
       PB(K_SELECT);
@@ -899,13 +903,9 @@ static int assemble(apb_plan* p, int mode, double** model_out_dev, double** resi
   PB(K_ASSEMBLE);
   k_assemble<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, mode,
                                              p->d_stamp, p->d_out, model_out_dev, resid_out_dev,
-                                             chi_out2 ? p->d_chipart : nullptr);
+                                             chi_out2 ? p->d_chipart : nullptr, p->d_done, chi_out2, write_flag,
+                                             p->q.overflow);
   LAUNCH_CHECK();
-  if (chi_out2) {
-    PB(K_CHI);
-    k_chi_final<<<1, 256, 0, st>>>(p->d_chipart, p->n_img_tiles, chi_out2, write_flag, p->q.overflow);
-    LAUNCH_CHECK();
-  }
   return 0;
 }
 

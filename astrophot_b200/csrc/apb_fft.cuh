@@ -222,6 +222,20 @@ APB_HD int fft_bfly(const cpx* __restrict__ in, int N, int Ns, int j, const cpx*
 }
 
 #if defined(__CUDACC__)
+// asynchronous global -> shared copies (LDGSTS): the tile loads of a CTA are all issued before any
+// is waited for, instead of one dependent load per loop trip; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // One stage for nf sequences: in + f*ld -> out + f*ld, one barrier.  A thread keeps one butterfly
 // (R complex values) in registers at a time.  noinline on purpose: inlined into the stage loop the
 // compiler hoists every radix's fp64 constants out of the loop and spills ~1 KB per thread; as
@@ -313,13 +327,12 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ 
     int sx = x + xoff;
     if (sx >= N) sx -= N;
     const int r0 = wk.z + 2 * f;
-    double re = 0.0, im = 0.0;
-    if (sx < valid_w) {
-      re = base[(long long)r0 * rstride + sx];
-      if (2 * f + 1 < wk.w) im = base[(long long)(r0 + 1) * rstride + sx];
-    }
-    a[f * ld + FPAD(x)] = cpx{re, im};
+    const bool v0 = sx < valid_w, v1 = v0 && (2 * f + 1 < wk.w);
+    cpx* dst = &a[f * ld + FPAD(x)];
+    cp_async8(&dst->x, v0 ? base + (long long)r0 * rstride + sx : base, v0 ? 8 : 0);
+    cp_async8(&dst->y, v1 ? base + (long long)(r0 + 1) * rstride + sx : base, v1 ? 8 : 0);
   }
+  cp_async_wait_all();
   __syncthreads();
   const cpx* r = fft_run<false>(a, b, nf, ld, D, tw);
   for (int idx = threadIdx.x; idx < nf * nxh; idx += blockDim.x) {
@@ -372,8 +385,10 @@ __global__ void __launch_bounds__(256, 2) k_fft_cols(const DevSrc* __restrict__ 
     const int y = idx / nc, c = idx - y * nc;
     int sy = y + yoff;
     if (sy >= N) sy -= N;
-    a[c * ld + FPAD(y)] = sy < rows_valid ? in[(long long)sy * nxp + c] : cpx{0.0, 0.0};
+    const bool v = sy < rows_valid;
+    cp_async16(&a[c * ld + FPAD(y)], v ? in + (long long)sy * nxp + c : in, v ? 16 : 0);
   }
+  cp_async_wait_all();
   __syncthreads();
   cpx* r = fft_run<false>(a, b, nc, ld, D, tw);
   if (is_psf) {
@@ -386,6 +401,7 @@ __global__ void __launch_bounds__(256, 2) k_fft_cols(const DevSrc* __restrict__ 
   }
   const cpx* kt = spec + s.specKT_off + ((long long)jb.z * nxh + kx0) * N;
   const double scale = 1.0 / ((double)N * (double)s.fft_nx);
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < nc * N; idx += blockDim.x) {
     const int c = idx / N, y = idx - c * N;
     const cpx v = c_mul(r[c * ld + FPAD(y)], kt[(long long)c * N + y]);
@@ -419,6 +435,7 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows_inv(const DevSrc* __restric
   cpx* a = fsm;
   cpx* b = a + nf * ld;
   const cpx* in = spec + s.specB_off + ((long long)wk.y * s.oh) * nxp;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < nf * N; idx += blockDim.x) {
     const int f = idx / N, k = idx - f * N;
     const int r0 = wk.z + 2 * f;

@@ -183,65 +183,92 @@ __global__ void __launch_bounds__(256) k_assemble(const DevSrc* __restrict__ src
                                                   const int* __restrict__ bin_ptr, const int* __restrict__ bin_src,
                                                   int mode, const double* __restrict__ stamp,
                                                   const double* __restrict__ outar, double* const* __restrict__ model_out,
-                                                  double* const* __restrict__ resid_out, double* __restrict__ chipart) {
+                                                  double* const* __restrict__ resid_out, double* __restrict__ chipart,
+                                                  unsigned int* __restrict__ done, double* __restrict__ out2, int write_flag,
+                                                  const int* __restrict__ overflow) {
   __shared__ double sh[8];
+  __shared__ bool last_s;
   const int4 t = tiles[blockIdx.x];
   const apb_image_t im = imgs[t.x];
   const int b0 = bin_ptr[t.w], b1 = bin_ptr[t.w + 1];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  double chi = 0.0, bad = 0.0;
-  for (int r = 0; r < 4; ++r) {
-    const int x = t.y + lx, y = t.z + ly + 8 * r;
-    if (x >= im.W || y >= im.H) continue;
-    double m = 0.0;
-    for (int b = b0; b < b1; ++b) {
-      const int si = bin_src[b];
-      const DevSrc& s = src[si];
-      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
-      if (s.kind == APB_FLAT_SKY) {
-        m += dyn[si].k[0];
-      } else {
-        const PlaneView v = out_plane(s, mode, 0, stamp, outar);
-        m += v.p[(long long)(y - s.oy) * v.stride + (x - s.ox)];
+  const int x = t.y + lx;
+  // the four rows of this thread side by side: their loads are independent and all in flight together
+  double m[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = b0; b < b1; ++b) {
+    const int si = bin_src[b];
+    const DevSrc& s = src[si];
+    if (x < s.ox || x >= s.ox + s.ow) continue;
+    if (s.kind == APB_FLAT_SKY) {
+      const double v = dyn[si].k[0];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int y = t.z + ly + 8 * r;
+        if (y >= s.oy && y < s.oy + s.oh) m[r] += v;
       }
-    }
-    const long long p = (long long)y * im.W + x;
-    if (model_out) model_out[t.x][p] = m;
-    if (im.data) {
-      const bool keep = !(im.mask && im.mask[p]);
-      const double w = im.weight ? im.weight[p] : 1.0;
-      const double df = m - im.data[p];
-      const double rr = keep ? w * df : 0.0;   // r = W (Y0 - Y) on unmasked pixels (lm.py:381-385)
-      if (resid_out) resid_out[t.x][p] = rr;
-      if (keep) {
-        chi += w * df * df;
-        if (!isfinite(m)) bad = 1.0;
+    } else {
+      const PlaneView v = out_plane(s, mode, 0, stamp, outar);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int y = t.z + ly + 8 * r;
+        if (y >= s.oy && y < s.oy + s.oh) m[r] += v.p[(long long)(y - s.oy) * v.stride + (x - s.ox)];
       }
     }
   }
+  double chi = 0.0, bad = 0.0;
+  double dat[4], wgt[4];
+  bool keep[4], in[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int y = t.z + ly + 8 * r;
+    in[r] = x < im.W && y < im.H;
+    const long long p = (long long)y * im.W + x;
+    keep[r] = in[r] && !(im.mask && im.mask[p]);
+    dat[r] = (in[r] && im.data) ? im.data[p] : 0.0;
+    wgt[r] = (in[r] && im.weight) ? im.weight[p] : 1.0;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (!in[r]) continue;
+    const int y = t.z + ly + 8 * r;
+    const long long p = (long long)y * im.W + x;
+    if (model_out) model_out[t.x][p] = m[r];
+    if (im.data) {
+      const double df = m[r] - dat[r];
+      const double rr = keep[r] ? wgt[r] * df : 0.0;   // r = W (Y0 - Y) on unmasked pixels (lm.py:381-385)
+      if (resid_out) resid_out[t.x][p] = rr;
+      if (keep[r]) {
+        chi += wgt[r] * df * df;
+        if (!isfinite(m[r])) bad = 1.0;
+      }
+    }
+  }
+  if (!chipart) return;
   const double c = block_sum<256>(chi, sh);
   const double bsum = block_sum<256>(bad, sh);
-  if (threadIdx.x == 0 && chipart) {
+  // chi^2 record: out2[0] = chi^2; out2[1] = 1 finite, 0 non-finite pixels, -1 a refinement queue
+  // overflowed (results invalid: apb_plan_reserve, then repeat the call).  The CTA that finishes
+  // last adds the per-tile partials in tile order: one launch, fixed summation order.
+  if (threadIdx.x == 0) {
     chipart[2 * blockIdx.x] = c;
     chipart[2 * blockIdx.x + 1] = bsum;
+    __threadfence();
+    last_s = atomicAdd(done, 1u) == gridDim.x - 1;
   }
-}
-
-// out2[0] = chi^2; out2[1] = 1 finite, 0 non-finite pixels, -1 a refinement queue overflowed
-// (results invalid: apb_plan_reserve, then repeat the call)
-__global__ void k_chi_final(const double* __restrict__ part, int n, double* __restrict__ out2, int write_flag,
-                            const int* __restrict__ overflow) {
-  __shared__ double sh[8];
-  double c = 0, b = 0;
-  for (int q = threadIdx.x; q < n; q += 256) {
-    c += part[2 * q];
-    b += part[2 * q + 1];
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  double cs = 0.0, bs = 0.0;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += 256) {
+    cs += __ldcg(&chipart[2 * q]);
+    bs += __ldcg(&chipart[2 * q + 1]);
   }
-  c = block_sum<256>(c, sh);
-  b = block_sum<256>(b, sh);
+  cs = block_sum<256>(cs, sh);
+  bs = block_sum<256>(bs, sh);
   if (threadIdx.x == 0) {
-    out2[0] = c;
-    if (write_flag) out2[1] = *overflow ? -1.0 : ((b == 0.0 && isfinite(c)) ? 1.0 : 0.0);
+    out2[0] = cs;
+    if (write_flag) out2[1] = *overflow ? -1.0 : ((bs == 0.0 && isfinite(cs)) ? 1.0 : 0.0);
+    *done = 0u;
   }
 }
 

@@ -25,17 +25,19 @@ struct Queues {
 // ----------------------------------------------------------------------------
 // prep: x -> per-source natural values, chain factors, constants
 // ----------------------------------------------------------------------------
-__global__ void k_prep(const DevSrc* __restrict__ src, DevDyn* __restrict__ dyn, int n_src,
-                       const apb_param_t* __restrict__ par, const double* __restrict__ x, int as_rep,
-                       int* qcount, double* skyJ, int write_skyJ) {
-  const int si = blockIdx.x * blockDim.x + threadIdx.x;
-  if (si == 0 && qcount) {
-    for (int k = 0; k < APB_MAX_DEPTH + 2; ++k) qcount[k] = 0;
-  }
+// One warp per source: lanes transform the elements in parallel, then five lanes compute the
+// independent groups of constants (each a serial chain of fp64 transcendentals) side by side.
+// Every sampling pass waits on this kernel, so its latency, not its throughput, is what counts.
+__global__ void __launch_bounds__(128) k_prep(const DevSrc* __restrict__ src, DevDyn* __restrict__ dyn, int n_src,
+                                              const apb_param_t* __restrict__ par, const double* __restrict__ x, int as_rep,
+                                              int* qcount, double* skyJ, int write_skyJ) {
+  const int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (si == 0 && lane < APB_MAX_DEPTH + 2 && qcount) qcount[lane] = 0;
   if (si >= n_src) return;
   const DevSrc& s = src[si];
   DevDyn& d = dyn[si];
-  for (int e = 0; e < s.n_elem; ++e) {
+  for (int e = lane; e < s.n_elem; e += 32) {
     const int sl = s.slot[e];
     double v = s.cval[e], ch = 0.0;
     if (sl >= 0) {
@@ -66,74 +68,87 @@ __global__ void k_prep(const DevSrc* __restrict__ src, DevDyn* __restrict__ dyn,
     d.el[e] = v;
     d.chain[e] = ch;
   }
-  const double cx = d.el[0], cy = d.el[1];
-  // pixel position of the centre, sub-pixel shift (model_object.py:320-323, point_source.py:149-150)
-  const double pcx = s.Sinv[0] * (cx - s.rxy[0]) + s.Sinv[1] * (cy - s.rxy[1]) + s.rij[0];
-  const double pcy = s.Sinv[2] * (cx - s.rxy[0]) + s.Sinv[3] * (cy - s.rxy[1]) + s.rij[1];
-  const double rx = rint(pcx), ry = rint(pcy);
-  d.rx = (int)rx;
-  d.ry = (int)ry;
-  d.sx = pcx - rx;
-  d.sy = pcy - ry;
-  for (int k = 0; k < 8; ++k) d.k[k] = 0.0;
-  d.thr[0] = d.thr[1] = 0.0;
-  d.c = 1.0;
-  d.s = 0.0;
-  d.qinv = 1.0;
-  if (s.kind == APB_FLAT_SKY) {
-    d.k[0] = s.area * exp10(d.el[2]);
-    if (write_skyJ) skyJ[si] = APB_LN10 * d.k[0] * d.chain[2];
-    return;
-  }
-  if (s.kind == APB_POINT) {
-    d.k[0] = exp10(d.el[2]);
-    return;
-  }
-  if (!(s.flags & APB_F_RADIAL)) {
-    const double th = -(d.el[3] - APB_PI / 2);
-    sincos(th, &d.s, &d.c);
-    d.qinv = 1.0 / d.el[2];
-  }
-  if (s.kind == APB_SERSIC) {
-    const double n = d.el[4], Re = d.el[5];
-    const double bn = sersic_b(n);
-    d.k[0] = s.area * exp10(d.el[6]);
-    d.k[1] = 1.0 / (Re * Re);
-    d.k[2] = 0.5 / n;
-    d.k[3] = bn;
-    d.k[4] = sersic_db(n);
-    d.k[5] = 1.0 / n;
-    d.k[6] = 1.0 / Re;
-    if (s.ref_mode == APB_REF_SERSIC_FLUX) {
-      // total flux / numel of the working image (sersic_model.py:87-89, conversions/functions.py:168-190)
-      const double flux = 2 * APB_PI * exp10(d.el[6]) * Re * Re * d.el[2] * n * (exp(bn) * pow(bn, -2 * n)) * exp(lgamma(2 * n));
-      for (int m = 0; m < 2; ++m)
-        d.thr[m] = s.tol * (flux / ((double)s.geo[m].rw * (double)s.geo[m].rh));
+  __syncwarp();
+  const int kind = s.kind;
+  const bool profile = kind != APB_FLAT_SKY && kind != APB_POINT;
+  if (lane == 0) {
+    // pixel position of the centre, sub-pixel shift (model_object.py:320-323, point_source.py:149-150)
+    const double cx = d.el[0], cy = d.el[1];
+    const double pcx = s.Sinv[0] * (cx - s.rxy[0]) + s.Sinv[1] * (cy - s.rxy[1]) + s.rij[0];
+    const double pcy = s.Sinv[2] * (cx - s.rxy[0]) + s.Sinv[3] * (cy - s.rxy[1]) + s.rij[1];
+    const double rx = rint(pcx), ry = rint(pcy);
+    d.rx = (int)rx;
+    d.ry = (int)ry;
+    d.sx = pcx - rx;
+    d.sy = pcy - ry;
+  } else if (lane == 1) {
+    double sn = 0.0, cs = 1.0, qi = 1.0;
+    if (profile && !(s.flags & APB_F_RADIAL)) {
+      sincos(-(d.el[3] - APB_PI / 2), &sn, &cs);
+      qi = 1.0 / d.el[2];
     }
-  } else if (s.kind == APB_EXPONENTIAL) {
-    d.k[0] = s.area * exp10(d.el[5]);
-    d.k[1] = 1.0 / d.el[4];
-    d.k[2] = sersic_b(1.0);
-  } else if (s.kind == APB_GAUSSIAN) {
-    const double sg = d.el[4];
-    d.k[0] = s.area * exp10(d.el[5]) / sqrt(2 * APB_PI * sg * sg);
-    d.k[1] = 1.0 / (sg * sg);
-    d.k[2] = 1.0 / sg;
-  } else if (s.kind == APB_MOFFAT) {
-    d.k[0] = s.area * exp10(d.el[6]);
-    d.k[1] = 1.0 / (d.el[5] * d.el[5]);
-    d.k[2] = d.el[4];
-    d.k[3] = 1.0 / d.el[5];
-  } else if (s.kind == APB_SPLINE) {
-    d.k[0] = s.area;
-    const int K = s.n_prof;
-    const double* v = d.el + 4;
-    for (int k = 0; k < K; ++k) {
-      double m;
-      if (k == 0) m = (v[1] - v[0]) / (s.prof[1] - s.prof[0]);
-      else if (k == K - 1) m = (v[K - 1] - v[K - 2]) / (s.prof[K - 1] - s.prof[K - 2]);
-      else m = ((v[k] - v[k - 1]) / (s.prof[k] - s.prof[k - 1]) + (v[k + 1] - v[k]) / (s.prof[k + 1] - s.prof[k])) / 2;
-      d.spl_m[k] = m;
+    d.c = cs;
+    d.s = sn;
+    d.qinv = qi;
+  } else if (lane == 2) {
+    // amplitude
+    if (kind == APB_FLAT_SKY) {
+      const double a = s.area * exp10(d.el[2]);
+      d.k[0] = a;
+      if (write_skyJ) skyJ[si] = APB_LN10 * a * d.chain[2];
+    } else if (kind == APB_POINT) {
+      d.k[0] = exp10(d.el[2]);
+    } else if (kind == APB_SERSIC || kind == APB_MOFFAT) {
+      d.k[0] = s.area * exp10(d.el[6]);
+    } else if (kind == APB_EXPONENTIAL) {
+      d.k[0] = s.area * exp10(d.el[5]);
+    } else if (kind == APB_GAUSSIAN) {
+      const double sg = d.el[4];
+      d.k[0] = s.area * exp10(d.el[5]) / sqrt(2 * APB_PI * sg * sg);
+    } else {
+      d.k[0] = s.area;
+    }
+  } else if (lane == 3) {
+    double t0 = 0.0, t1 = 0.0;
+    if (kind == APB_SERSIC && s.ref_mode == APB_REF_SERSIC_FLUX) {
+      // total flux / numel of the working image (sersic_model.py:87-89, conversions/functions.py:168-190)
+      const double n = d.el[4], Re = d.el[5], bn = sersic_b(n);
+      const double flux = 2 * APB_PI * exp10(d.el[6]) * Re * Re * d.el[2] * n * (exp(bn) * pow(bn, -2 * n)) * exp(lgamma(2 * n));
+      t0 = s.tol * (flux / ((double)s.geo[0].rw * (double)s.geo[0].rh));
+      t1 = s.tol * (flux / ((double)s.geo[1].rw * (double)s.geo[1].rh));
+    }
+    d.thr[0] = t0;
+    d.thr[1] = t1;
+  } else if (lane == 4) {
+    if (kind == APB_SERSIC) {
+      const double n = d.el[4], Re = d.el[5];
+      d.k[1] = 1.0 / (Re * Re);
+      d.k[2] = 0.5 / n;
+      d.k[3] = sersic_b(n);
+      d.k[4] = sersic_db(n);
+      d.k[5] = 1.0 / n;
+      d.k[6] = 1.0 / Re;
+    } else if (kind == APB_EXPONENTIAL) {
+      d.k[1] = 1.0 / d.el[4];
+      d.k[2] = sersic_b(1.0);
+    } else if (kind == APB_GAUSSIAN) {
+      const double sg = d.el[4];
+      d.k[1] = 1.0 / (sg * sg);
+      d.k[2] = 1.0 / sg;
+    } else if (kind == APB_MOFFAT) {
+      d.k[1] = 1.0 / (d.el[5] * d.el[5]);
+      d.k[2] = d.el[4];
+      d.k[3] = 1.0 / d.el[5];
+    } else if (kind == APB_SPLINE) {
+      const int K = s.n_prof;
+      const double* v = d.el + 4;
+      for (int k = 0; k < K; ++k) {
+        double m;
+        if (k == 0) m = (v[1] - v[0]) / (s.prof[1] - s.prof[0]);
+        else if (k == K - 1) m = (v[K - 1] - v[K - 2]) / (s.prof[K - 1] - s.prof[K - 2]);
+        else m = ((v[k] - v[k - 1]) / (s.prof[k] - s.prof[k - 1]) + (v[k + 1] - v[k]) / (s.prof[k + 1] - s.prof[k])) / 2;
+        d.spl_m[k] = m;
+      }
     }
   }
 }
@@ -529,12 +544,34 @@ __device__ __forceinline__ double gl_nodes(const DevSrc& s, const DevDyn& d, dou
                                            int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
-  double dI[GRAD ? NE : 1];
   acc.v[0] = 0.0;
   if (GRAD)
     for (int e = 0; e < ne; ++e) acc.v[1 + e] = 0.0;
   double centre = 0.0;
   const int n = s.quad_level, nn = n * n, mid = nn / 2;
+  if (!GRAD && n == 3 && kstep == 1 && KIND != APB_SPLINE) {
+    // the default 3x3 rule, all nodes on one lane: a row of three nodes at a time, so that three
+    // independent log/exp chains are in flight (these launches are latency-bound, not pipe-bound)
+    for (int ky = 0; ky < 3; ++ky) {
+      double I3[3], dI3[3][GRAD ? NE : 1];
+      const double ay = c_quad.a[3][ky] * scale;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const double ax = c_quad.a[3][kx] * scale;
+        I3[kx] = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ax + s.S[1] * ay), Y + (s.S[2] * ax + s.S[3] * ay), ascale, dI3[kx]);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const double w = c_quad.w[3][kx] * c_quad.w[3][ky];
+        if (ky == 1 && kx == 1) centre = I3[kx];
+        acc.v[0] += I3[kx] * w;
+        if (GRAD)
+          for (int e = 0; e < NE; ++e) acc.v[1 + e] += dI3[kx][e] * w;
+      }
+    }
+    return centre;
+  }
+  double dI[GRAD ? NE : 1];
   for (int k = k0; k < nn; k += kstep) {
     const int kx = k % n, ky = k / n;
     const double ax = c_quad.a[n][kx] * scale, ay = c_quad.a[n][ky] * scale;
@@ -680,7 +717,7 @@ __device__ __noinline__ void split_and_store_spline(const DevSrc& s, const DevDy
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(128, 4) k_integrate(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn, int mode,
+__global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn, int mode,
                                                       double* __restrict__ stamp, Queues q, int L) {
   const int n = min(q.count[1], q.cap[1]);
   const Level& Lv = q.lv[1];
