@@ -797,11 +797,16 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   // PSF branch on the side stream: shifted stamps and (FFT sources) their spectra depend only on
   // k_prep, so they overlap the first pass and the adaptive integration of the profiles
   const FftTables& F = p->ft[grad];
+  // (while per-kernel timing is on, everything stays on one stream: an event pair around a side-stream
+  //  kernel would also measure its wait for SMs held by the main stream's kernels)
+  const bool fork = p->n_psf_list && !p->profiling;
   if (p->n_psf_list) {
     cudaStream_t main_st = st;
-    if (cudaEventRecord(p->ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev_fork, 0) != cudaSuccess)
-      APB_FAIL("fork to the PSF stream failed");
-    st = p->side;
+    if (fork) {
+      if (cudaEventRecord(p->ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev_fork, 0) != cudaSuccess)
+        APB_FAIL("fork to the PSF stream failed");
+      st = p->side;
+    }
     PB(K_PSF);
     k_psf_stamp<<<p->n_psf_list, 256, 0, st>>>(p->d_src, p->d_dyn, p->psf_list, p->d_psf, p->d_psfst, grad);
     LAUNCH_CHECK();
@@ -815,7 +820,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
                                                                           mode, p->d_spec);
       LAUNCH_CHECK();
     }
-    if (cudaEventRecord(p->ev_join, st) != cudaSuccess) APB_FAIL("PSF stream event failed");
+    if (fork && cudaEventRecord(p->ev_join, st) != cudaSuccess) APB_FAIL("PSF stream event failed");
     st = main_st;
   }
   if (T.n_tiles) {
@@ -869,7 +874,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
       LAUNCH_CHECK();
     }
   }
-  if (p->n_psf_list && cudaStreamWaitEvent(st, p->ev_join, 0) != cudaSuccess) APB_FAIL("join of the PSF stream failed");
+  if (fork && cudaStreamWaitEvent(st, p->ev_join, 0) != cudaSuccess) APB_FAIL("join of the PSF stream failed");
   if (p->n_point) {
     PB(K_POINT);
     k_point<<<p->n_point, 256, 0, st>>>(p->d_src, p->d_dyn, p->point_list, p->d_psfst, p->d_out, grad);

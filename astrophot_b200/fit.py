@@ -131,7 +131,7 @@ class LM(BaseOptimizer):
         self._ha = torch.empty(P, dtype=torch.float64, device=dev)
         # one C-ABI call per lambda-trial when the system fits the single-CTA solver and no
         # collective sits between the pieces of a trial
-        self._fused_trial = kwargs.get("fused_trial", True) and 0 < P <= 159 and \
+        self._fused_trial = kwargs.get("fused_trial", True) and 0 < P <= min(159, kwargs.get("small_solver_max", 159)) and \
             (not self.distributed or self.acceleration == 0)
         self._tbuf = torch.empty(P + 3, dtype=torch.float64, device=dev)
         self._split_trial = bool(kwargs.get("split_trial", False)) and self.acceleration == 0
@@ -142,6 +142,8 @@ class LM(BaseOptimizer):
             self.plan2 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
                               share=self.plan)
         self.hess = self.grad = None
+        self._small_solver_max = kwargs.get("small_solver_max", 159)   # single-CTA device solver up to this P
+        self._hess_version, self._factor_key, self._factor = 0, None, None
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
     # -- damping -------------------------------------------------------------
@@ -183,13 +185,26 @@ class LM(BaseOptimizer):
         from .cabi import lm_solve
 
         P = rhs.numel()
-        if P <= 159:
+        if P <= self._small_solver_max:
             return lm_solve(self.hess, rhs, L)
-        # large systems: same damped matrix, library dense solver on the device
-        A = self.hess / (1.0 + L)
-        d = torch.diagonal(self.hess)
-        A.diagonal().copy_(d + L * (1.0 + d))
-        return torch.linalg.solve(A, rhs)
+        # large systems: same damped matrix (lm.py:359-371), library dense solver on the device.  The matrix is
+        # symmetric positive definite for L > 0, so it is Cholesky-factored once per (H, L) and the factor serves
+        # both solves of a lambda-trial (h and the geodesic correction); LU is the fallback.
+        key = (self._hess_version, float(L))
+        if self._factor_key != key:
+            A = self.hess / (1.0 + L)
+            d = torch.diagonal(self.hess)
+            A.diagonal().copy_(d + L * (1.0 + d))
+            chol, info = torch.linalg.cholesky_ex(A)
+            if int(info.item()) == 0:
+                self._factor = ("chol", chol)
+            else:
+                self._factor = ("lu",) + tuple(torch.linalg.lu_factor(A))
+            self._factor_key = key
+            del A
+        if self._factor[0] == "chol":
+            return torch.cholesky_solve(rhs.reshape(-1, 1), self._factor[1]).reshape(-1)
+        return torch.linalg.lu_solve(self._factor[1], self._factor[2], rhs.reshape(-1, 1)).reshape(-1)
 
     @torch.no_grad()
     def step(self, chi2):
@@ -217,6 +232,7 @@ class LM(BaseOptimizer):
             self._allreduce(self._H)
             self._allreduce(self._g)
         self.hess, self.grad = self._H, self._g
+        self._hess_version += 1
         init_chi2 = chi2
         nostep = True
         best = (torch.zeros_like(x), init_chi2, self.L)
@@ -372,6 +388,7 @@ class LM(BaseOptimizer):
             self._allreduce(H)
             self._allreduce(g)
         self.hess, self.grad = H, g
+        self._hess_version += 1
 
     @property
     @torch.no_grad()

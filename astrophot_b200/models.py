@@ -639,10 +639,13 @@ class Group_Model(AstroPhot_Model):
         if "psf_mode" in kwargs:
             self.psf_mode = kwargs["psf_mode"]
 
-    def add_model(self, model):
+    def add_model(self, model, _update=True):
         if isinstance(model, (tuple, list)):
+            # one window update for the whole list: the reference re-unions every window per added
+            # model (group_model_object.py:70-90), which is quadratic in the number of sources
             for mod in model:
-                self.add_model(mod)
+                self.add_model(mod, _update=False)
+            self.update_window()
             return
         if model.name in self.models:
             if model is self.models[model.name]:
@@ -652,9 +655,10 @@ class Group_Model(AstroPhot_Model):
         self.models[model.name] = model
         self.parameters.link(model.parameters)
         # the group's psf_mode and target override the sub-model's (group_model_object.py:85-89)
-        self.psf_mode = self.psf_mode
-        self.target = self.target
-        self.update_window()
+        model.psf_mode = self.psf_mode
+        model.target = self.target
+        if _update:
+            self.update_window()
 
     def update_window(self, include_locked=False):
         if isinstance(self.target, Image_List):

@@ -75,15 +75,69 @@ def build_joint(ap, n_bands, datas, size=SIZE):
                                      target=ap.image.Target_Image_List(tars), psf_mode="full")
 
 
+C3 = {"c3": (4096, 1000, 5000), "c3s": (1024, 62, 312)}     # size, Sersic sources, point sources
+
+
+def build_crowded(ap, workload, data=None):
+    """BASELINE config[2]: crowded field, PSF-convolved Sersic sources (128^2 windows) + point sources
+    (53^2 windows) + flat sky on one image with a 51x51 Moffat PSF.  `c3s` is the 1024^2 scale model
+    with the same source densities (the largest the reference's dense Jacobian fits in host memory)."""
+    size, n_gal, n_pt = C3[workload]
+    rng = np.random.default_rng(3)
+    psf_np = ap.utils.moffat_psf(2.5, 2.0, PSF_W, 1.0)
+    kw = {} if data is None else {"variance": data["variance"]}
+    tar = ap.image.Target_Image(data=np.zeros((size, size)) if data is None else data["data"], pixelscale=1.0,
+                                zeropoint=22.5, psf=ap.image.PSF_Image(data=psf_np, pixelscale=1.0), **kw)
+    M = ap.models.AstroPhot_Model
+    models = []
+
+    def box(c, lo, hi):
+        return [max(0, int(c) - lo), min(size, int(c) + hi)]
+
+    for k in range(n_gal):
+        cx, cy = rng.uniform(40, size - 40, size=2)
+        models.append(M(name=f"g{k}", model_type="sersic galaxy model", target=tar, psf_mode="full",
+                        window=[box(cx, 64, 64), box(cy, 64, 64)],
+                        parameters={"center": [cx, cy], "q": rng.uniform(0.4, 0.9), "PA": rng.uniform(0, np.pi),
+                                    "n": rng.uniform(1, 4), "Re": rng.uniform(3, 12), "Ie": rng.uniform(0, 1)}))
+    for k in range(n_pt):
+        cx, cy = rng.uniform(40, size - 40, size=2)
+        models.append(M(name=f"p{k}", model_type="point model", target=tar, window=[box(cx, 26, 27), box(cy, 26, 27)],
+                        parameters={"center": [cx, cy], "flux": rng.uniform(1, 2)}))
+    sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": -2.0})
+    sky.initialize()
+    models.append(sky)
+    return M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
+
+
+def build_workload(ap, workload, n_bands, datas):
+    if workload == "c2":
+        return build_joint(ap, n_bands, datas)
+    return build_crowded(ap, workload, None if datas is None else datas[0])
+
+
+def workload_text(workload, n_bands):
+    if workload == "c2":
+        return (f"c2 x {n_bands} band(s): PSF-convolved Sersic, {SIZE}x{SIZE} per band, {PSF_W}x{PSF_W} Moffat PSF, "
+                "threshold sub-pixel integration, LM fp64, joint fit sharded 1 band/GPU")
+    size, n_gal, n_pt = C3[workload]
+    return (f"{workload}: crowded field, {n_gal} PSF-convolved Sersic (128^2 windows) + {n_pt} point sources (53^2 windows) "
+            f"+ flat sky on {size}x{size}, {PSF_W}x{PSF_W} Moffat PSF, threshold sub-pixel integration, LM fp64")
+
+
 def make_data(truth, seed):
     rng = np.random.default_rng(seed)
     var = 0.1**2 + truth / 100.0
     return {"data": truth + rng.normal(size=truth.shape) * np.sqrt(var), "variance": var}
 
 
-def start_state(x_rep, seed=2):
+def start_state(x_rep, seed=2, scale=0.05):
     rng = np.random.default_rng(1000 + seed)
-    return np.asarray(x_rep, dtype=np.float64) + 0.05 * rng.normal(size=len(x_rep))
+    return np.asarray(x_rep, dtype=np.float64) + scale * rng.normal(size=len(x_rep))
+
+
+def start_scale(workload):
+    return 0.05 if workload == "c2" else 0.02
 
 
 # ---------------------------------------------------------------------------
@@ -159,22 +213,37 @@ def cpu_lm_iteration_seconds(scene, x0, n_iter=1):
     return dt / its, res
 
 
-def cpu_scene(n_bands=1, size=SIZE):
-    """Scene tables for the CPU arm (host numpy only, no GPU needed)."""
+def cpu_scene(workload="c2"):
+    """Scene tables for the CPU arm (host numpy only, no GPU needed).  The crowded field is timed on its
+    scale model c3s: the reference's (and the port's) dense Jacobian of c3 itself would need 2.9 TB."""
     import astrophot_b200 as ap
     import astrophot_oracle as orc
     from astrophot_b200.lowering import lower
 
+    if workload == "c3":
+        workload = "c3s"
+    dev = ap.AP_config.ap_device
     ap.AP_config.ap_device = "cpu"
-    model = build_joint(ap, n_bands, None, size)
-    scene, _ = lower(model)
-    xv = model.parameters.vector_values().numpy()
-    truth = orc.sample(scene, xv, as_rep=False, conv="fft")
-    datas = [make_data(t, 10 + b) for b, t in enumerate(truth)]
-    model = build_joint(ap, n_bands, datas, size)
-    scene, _ = lower(model, for_fit=True)
-    x0 = start_state(model.parameters.vector_representation().numpy())
+    try:
+        model = build_workload(ap, workload, 1, None)
+        scene, _ = lower(model)
+        xv = model.parameters.vector_values().numpy()
+        truth = orc.sample(scene, xv, as_rep=False, conv="fft")
+        datas = [make_data(t, 10 + b) for b, t in enumerate(truth)]
+        model = build_workload(ap, workload, 1, datas)
+        scene, _ = lower(model, for_fit=True)
+        x0 = start_state(model.parameters.vector_representation().numpy(), scale=start_scale(workload))
+    finally:
+        ap.AP_config.ap_device = dev
     return scene, x0
+
+
+def cpu_scale(workload):
+    """(factor, note): c3 is 16 x c3s in sources and pixels; the CPU cost per LM iteration is taken as
+    linear in that (it is super-linear for the dense J^T W J, so this flatters the CPU)."""
+    if workload == "c3":
+        return 1.0 / 16.0, " on the scale model c3s (1024^2, 62 Sersic + 312 points + sky, P = 1371), divided by 16 (linear extrapolation to c3: EXTRAPOLATED)"
+    return 1.0, ""
 
 
 def run_reference(args):
@@ -185,22 +254,23 @@ def run_reference(args):
 
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    scene, x0 = cpu_scene(1)
+    scene, x0 = cpu_scene(args.workload)
+    fac, note = cpu_scale(args.workload)
     times = []
     for k in range(args.warmup + args.steps):
         dt, res = cpu_lm_iteration_seconds(scene, x0, 1)
         if k >= args.warmup:
             times.append(dt)
-    ms = 1e3 * float(np.mean(times))
+    ms = 1e3 * float(np.mean(times)) / fac
     val = 1e3 / ms
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"c2: 1 PSF-convolved Sersic, {SIZE}x{SIZE}, {PSF_W}x{PSF_W} Moffat PSF, threshold integration, LM fp64",
-                   "note": "CPU oracle port of the reference algorithm (numpy + scipy FFT conv); one LM iteration from the perturbed start per step"},
+        "config": {"workload": workload_text(args.workload, 1),
+                   "note": "CPU oracle port of the reference algorithm (numpy + scipy FFT conv); one LM iteration from the perturbed start per step" + note},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "1 full-size LM iteration (1 normal-equation build + lambda trials) per step"},
+                         "sample": "1 full-size LM iteration (1 normal-equation build + lambda trials) per step" + note},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,38 +286,76 @@ def _fft_len(n):
     return cabi.fft_length(n)
 
 
-def algorithmic_work(src, n_fwd, n_jac, n_geo=0):
-    ow, oh = src.out[2], src.out[3]
-    spw = PSF_W + 2                       # bilinear-shifted stamp keeps its 1-px pad
-    b = (PSF_W + 2) // 2                  # psf_border_int = ceil((P+1)/2)
-    ew, eh = ow + 2 * b, oh + 2 * b
-    n_act = sum(1 for sl in src.slot if sl >= 0)
-    nx, ny = _fft_len(ew), _fft_len(eh)
-    nxh = nx // 2 + 1
-    px = ow * oh
-    # planes per pass: value-only: 1 image plane, 1 PSF plane, 1 product; derivative pass: value + (n_act-2)
-    # non-centre planes in, 3 PSF planes (K, dK/dcx, dK/dcy), 1 + n_act products out
-    in_f, k_f, j_f = 1, 1, 1
-    in_j, k_j, j_j = 1 + (n_act - 2), 3, 1 + n_act
+def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
+    """Algorithmic bytes / FP64 work of each kernel over the profiled region,
+    summed over the sources of the scene.  n_fwd value-only sampling passes, n_jac value+derivative
+    passes, n_geo geodesic J^T v passes."""
+    from astrophot_b200 import scene as sc
+
     tot = lambda f, j: n_fwd * f + n_jac * j
-    rows = lambda n_in, n_k: n_in * (eh * ew * 8 + eh * nxh * 16) + n_k * (spw * spw * 8 + spw * nxh * 16)
-    cols = lambda n_k, n_j: n_k * (spw * nxh * 16 + nxh * ny * 16) + n_j * (eh * nxh * 16 + nxh * ny * 16 + oh * nxh * 16)
-    inv = lambda n_j: n_j * (oh * nxh * 16 + px * 8)
-    planes = tot(j_f, j_j)
-    return {
-        "k_conv": {"bound": "fp64", "flops": 2.0 * spw * spw * px * planes,
-                   "what": f"2*{spw}^2 flop x {px} px x {planes} planes"},
-        "k_fft_rows": {"bound": "hbm", "bytes": float(tot(rows(in_f, k_f), rows(in_j, k_j))),
-                       "what": f"real rows in (8 B/px) + half spectra out (16 B x {nxh}/row), {nx}-point rows"},
-        "k_fft_cols": {"bound": "hbm", "bytes": float(tot(cols(k_f, j_f), cols(k_j, j_j))),
-                       "what": f"per product: read {eh}x{nxh} spectrum + {nxh}x{ny} PSF spectrum, write {oh}x{nxh}; 16 B each"},
-        "k_fft_rows_inv": {"bound": "hbm", "bytes": float(tot(inv(j_f), inv(j_j))),
-                           "what": f"half spectra in (16 B x {nxh}/row) + real rows out (8 B/px)"},
-        # normal equations: (n_act planes + weight + residual) x 8 B + mask per pixel, once per build
-        "k_blocks": {"bound": "hbm", "bytes": float(n_jac * px * ((n_act + 2) * 8 + 1) + n_geo * px * ((n_act + 1) * 8 + 1)),
-                     "what": f"J^T W J build: {n_act} derivative planes + weight + residual (8 B) + mask per pixel; "
-                             f"geodesic J^T v: {n_act} planes + v + mask per pixel"},
+    fft_rows = fft_cols = fft_inv = conv_flops = blocks = 0.0
+    first_px = 0
+    n_fft = n_dir = 0
+    for src in scene.sources:
+        n_act = sum(1 for sl in src.slot if sl >= 0)
+        ow, oh = src.out[2], src.out[3]
+        px = ow * oh
+        if src.kind not in (sc.KIND_POINT, sc.KIND_FLAT_SKY):
+            # (n_act derivative planes + weight + residual) x 8 B + mask per pixel per build; J^T v: planes + v + mask
+            blocks += n_jac * px * ((n_act + 2) * 8 + 1) + n_geo * px * ((n_act + 1) * 8 + 1)
+        if src.psf < 0 or src.kind in (sc.KIND_POINT, sc.KIND_FLAT_SKY):
+            if src.kind not in (sc.KIND_POINT, sc.KIND_FLAT_SKY):
+                first_px += (ow + 2) * (oh + 2)
+            continue
+        ps = scene.psfs[src.psf]
+        pw = int(ps.data.shape[1])
+        shifted = src.psf_shift != 0
+        spw = pw + (2 if shifted else 0)      # bilinear-shifted stamp keeps its 1-px pad
+        b = (pw + 2) // 2                     # psf_border_int = ceil((P+1)/2)
+        ew, eh = ow + 2 * b, oh + 2 * b
+        first_px += (ew + 2) * (eh + 2)
+        # planes per pass: value-only: 1 image plane, 1 PSF plane, 1 product; derivative pass: value + (n_act-2)
+        # non-centre planes in, 3 PSF planes (K, dK/dcx, dK/dcy), 1 + n_act products out
+        in_j, k_j, j_j = 1 + max(n_act - 2, 0), 3, 1 + n_act
+        if spw * spw > 17 * 17:
+            n_fft += 1
+            nx, ny = _fft_len(ew), _fft_len(eh)
+            nxh = nx // 2 + 1
+            rows = lambda n_in, n_k: n_in * (eh * ew * 8 + eh * nxh * 16) + n_k * (spw * spw * 8 + spw * nxh * 16)
+            cols = lambda n_k, n_j: n_k * (spw * nxh * 16 + nxh * ny * 16) + n_j * (eh * nxh * 16 + nxh * ny * 16 + oh * nxh * 16)
+            inv = lambda n_j: n_j * (oh * nxh * 16 + px * 8)
+            fft_rows += tot(rows(1, 1), rows(in_j, k_j))
+            fft_cols += tot(cols(1, 1), cols(k_j, j_j))
+            fft_inv += tot(inv(1), inv(j_j))
+        else:
+            n_dir += 1
+            conv_flops += 2.0 * spw * spw * px * tot(1, j_j)
+    # profile evaluations: nominal FP64-pipe instructions per Sersic evaluation (SURVEY.md §8d): 138 value-only,
+    # 230 value + 7 derivatives (reference-faithful pow form; the kernels use a cheaper log/exp form)
+    I_V, I_G = 138.0, 230.0
+    spe_int = 9.0 * sum(st["queued"])      # Gauss-Legendre 3x3 nodes per queue entry of the last call (approximate for the sum)
+    n_int = kern.get("k_integrate", (0, 0))[0]
+    n_int_g = kern.get("k_integrate_grad", (0, 0))[0]
+    work = {
+        "k_conv": {"bound": "fp64", "flops": conv_flops, "what": f"2*P_s^2 flop per output pixel and plane, {n_dir} direct-convolved sources"},
+        "k_fft_rows": {"bound": "hbm", "bytes": float(fft_rows),
+                       "what": f"real rows in (8 B/px) + half spectra out (16 B x nxh/row), {n_fft} FFT-convolved sources"},
+        "k_fft_cols": {"bound": "hbm", "bytes": float(fft_cols),
+                       "what": "per product: read eh x nxh spectrum + nxh x Ny PSF spectrum, write oh x nxh; 16 B each"},
+        "k_fft_rows_inv": {"bound": "hbm", "bytes": float(fft_inv), "what": "half spectra in (16 B x nxh/row) + real rows out (8 B/px)"},
+        "k_blocks": {"bound": "hbm", "bytes": float(blocks),
+                     "what": "J^T W J build: n_act derivative planes + weight + residual (8 B) + mask per pixel of every source window; "
+                             "geodesic J^T v: n_act planes + v + mask per pixel (pair blocks not counted)"},
+        "k_first": {"bound": "fp64", "flops": 2.0 * I_V * first_px * kern.get("k_first", (0, 0))[0],
+                    "what": f"{first_px} first-pass evaluations/launch x {I_V:.0f} nominal FP64 instr (x2 flop)"},
+        "k_first_grad": {"bound": "fp64", "flops": 2.0 * I_G * first_px * kern.get("k_first_grad", (0, 0))[0],
+                         "what": f"{first_px} first-pass evaluations/launch x {I_G:.0f} nominal FP64 instr (value + derivatives)"},
+        "k_integrate": {"bound": "fp64", "flops": 2.0 * I_V * spe_int * n_int,
+                        "what": f"~{spe_int:.0f} sub-pixel evaluations/launch (last call's queue) x {I_V:.0f} nominal FP64 instr"},
+        "k_integrate_grad": {"bound": "fp64", "flops": 2.0 * I_G * spe_int * n_int_g,
+                             "what": f"~{spe_int:.0f} sub-pixel evaluations/launch x {I_G:.0f} nominal FP64 instr"},
     }
+    return {k: v for k, v in work.items() if v.get("flops", 0) or v.get("bytes", 0)}
 
 
 # ---------------------------------------------------------------------------
@@ -270,21 +378,25 @@ def run_ours(args):
     ap.AP_config.ap_device = f"cuda:{local}"
     n_bands = world
     dev = torch.device("cuda", local)
+    wl = args.workload
+    if wl != "c2" and world > 1:
+        raise SystemExit("the crowded-field workloads run on one GPU (tile sharding of one image is not built yet)")
 
     # truth + noisy data for the band(s); every rank builds all bands' descriptions, data only for its own
-    truth_model = build_joint(ap, 1, None)
+    truth_model = build_workload(ap, wl, 1, None)
     datas = []
     for b in range(n_bands):
         if b % world == rank:
-            pars = band_truth(b)
-            truth_model["Ie"].value = pars["Ie"]
+            if wl == "c2":
+                truth_model["Ie"].value = band_truth(b)["Ie"]
             t = truth_model().data.cpu().numpy()
             datas.append(make_data(t, 10 + b))
         else:
             datas.append(None)
-    model = build_joint(ap, n_bands, datas)
+    del truth_model
+    model = build_workload(ap, wl, n_bands, datas)
     x_true = model.parameters.vector_representation().numpy()
-    x0 = start_state(x_true)
+    x0 = start_state(x_true, scale=start_scale(wl))
     lm = ap.fit.LM(model, initial_state=x0, max_iter=10**6, relative_tolerance=0.0, distributed=(world > 1),
                    conv=args.conv)
     plan = lm.plan
@@ -358,12 +470,18 @@ def run_ours(args):
     # ---- the same K iterations again with every kernel launch bracketed by CUDA events on its stream
     #      (per-kernel durations for the roofline; kept out of `value` because the event records cost time)
     reset()
-    plan.profile(True)
-    plan.profile_read(reset=True)
+    plans = [plan] + ([lm.plan2] if lm.plan2 is not None else [])   # the twin plan runs the concurrent chi^2 passes
+    for pl in plans:
+        pl.profile(True)
+        pl.profile_read(reset=True)
     trials0, fwd0, jac0 = lm.n_trials, lm.n_forward, lm.n_jacobian
     profiled_ms = timed_steps()
-    kern = plan.profile_read(reset=True)
-    plan.profile(False)
+    kern = {}
+    for pl in plans:
+        for kname, (nl, ms) in pl.profile_read(reset=True).items():
+            a = kern.get(kname, (0, 0.0))
+            kern[kname] = (a[0] + nl, a[1] + ms)
+        pl.profile(False)
     trials = lm.n_trials - trials0
     forwards = lm.n_forward - fwd0
     jacobians = lm.n_jacobian - jac0
@@ -419,7 +537,7 @@ def run_ours(args):
     hbm_peak = hbm_peak or copy_gbs
     top = max(kern.items(), key=lambda kv: kv[1][1]) if kern else ("none", (0, 0.0))
     name, (n_launch, k_ms) = top
-    work = algorithmic_work(plan.scene.sources[0], n_fwd=forwards - jacobians, n_jac=jacobians, n_geo=trials)
+    work = algorithmic_work(plan.scene, st, kern, dfma_tflops, n_fwd=forwards - jacobians, n_jac=jacobians, n_geo=trials)
     roof = {"kernel": name, "launches": n_launch, "avg_ms": k_ms / max(n_launch, 1),
             "share_of_step": k_ms / max(sum(v[1] for v in kern.values()), 1e-9)}
     w = work.get(name)
@@ -453,17 +571,17 @@ def run_ours(args):
     # ---- CPU baseline (bounded sample: one full-size LM iteration of the oracle port)
     cpu = None
     if world == 1 and not args.no_cpu:
-        scene_c, x0_c = cpu_scene(1)
+        scene_c, x0_c = cpu_scene(wl)
         dt, _ = cpu_lm_iteration_seconds(scene_c, x0_c, 1)
-        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "1 full-size LM iteration of the numpy/scipy oracle port (FFT convolution), same workload"}
+        fac, note = cpu_scale(wl)
+        cpu = {"value": fac / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": "1 full-size LM iteration of the numpy/scipy oracle port (FFT convolution), same workload" + note}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"c2 x {n_bands} band(s): PSF-convolved Sersic, {SIZE}x{SIZE} per band, {PSF_W}x{PSF_W} Moffat PSF, "
-                               "threshold sub-pixel integration, LM fp64, joint fit sharded 1 band/GPU",
+        "config": {"workload": workload_text(wl, n_bands),
                    "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
                    "kernel_timing": "second pass of the same K iterations with CUDA events around every launch "
                                     f"({profiled_ms / args.steps:.3f} ms/step with the event records)",
@@ -491,6 +609,9 @@ def main():
     ap_.add_argument("--steps", type=int, default=100)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap_.add_argument("--workload", default="c2", choices=["c2", "c3s", "c3"],
+                     help="c2 = BASELINE config[1] (default, the metric's configuration); c3 = config[2] crowded field, "
+                          "c3s = its 1024^2 scale model")
     ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap_.add_argument("--conv", default=None, choices=["direct", "fft"],
                      help="force one PSF-convolution kernel family (default: automatic, FFT for the 51x51 PSF)")

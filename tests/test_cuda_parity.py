@@ -242,6 +242,23 @@ def test_lm_trial_pieces_equal_fused_trial(name):
     np.testing.assert_allclose(r1.lambda_history[-1], r2.lambda_history[-1], rtol=1e-9, atol=1e-10)
 
 
+def test_lm_library_solver_path_matches_reference():
+    """Large systems (P > 159: crowded fields) factor the damped matrix with the library Cholesky once per
+    (H, L) instead of the single-CTA solver; forced here on the crowded golden (P = 99)."""
+    fix = load_golden("crowded")
+    m, _ = scenes.build(ap, "crowded", data=golden_data(fix))
+    r = ap.fit.LM(m, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, small_solver_max=0).fit()
+    assert not r._fused_trial and r._factor is not None
+    ref_loss = fix["loss_history"]
+    n = min(len(ref_loss), len(r.loss_history))
+    moving = 1
+    while moving < n and abs(ref_loss[moving] - ref_loss[moving - 1]) / ref_loss[moving] > 1e-12:
+        moving += 1
+    assert moving >= 3
+    np.testing.assert_allclose(r.loss_history[:moving], ref_loss[:moving], rtol=1e-8)
+    np.testing.assert_allclose(r.L_history[:moving], fix["L_history"][:moving], rtol=1e-12)
+
+
 def test_public_api_sample_and_jacobian():
     model, _ = scenes.build(ap, "group")
     img = model()
