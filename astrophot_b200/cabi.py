@@ -58,7 +58,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -90,6 +90,7 @@ def load_library(path=None):
     L.apb_geodesic.argtypes = [vp, dp, dp, C.c_double, dp, vp]
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
+    L.apb_lm_solve_sparse.argtypes = [vp, dp, C.c_double, dp, dp, C.c_double, C.c_int, vp]
     L.apb_lm_trial.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
     L.apb_lm_trial_begin.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, dp, dp, vp]
     L.apb_lm_trial_end.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp, vp]
@@ -310,6 +311,20 @@ class Plan:
         _check(self._L.apb_lm_trial_end(self._h, H.data_ptr(), float(L), x.data_ptr(), h.data_ptr(), buf.data_ptr(),
                                         ha_out.data_ptr(), rec.data_ptr(), _stream()), "apb_lm_trial_end")
         return rec
+
+    def solve_sparse(self, g, L, out=None, info=None, tol=0.0, max_iter=0):
+        """Damped LM solve by block-sparse PCG on the blocks of the last normal_eq (apb_lm_solve_sparse).
+        Returns (h, info) device tensors, info = [iterations, |r|/|b|]; None if the plan cannot use it."""
+        if out is None:
+            out = torch.empty(self.n_par, dtype=torch.float64, device="cuda")
+        if info is None:
+            info = torch.zeros(2, dtype=torch.float64, device="cuda")
+        rc = self._L.apb_lm_solve_sparse(self._h, g.data_ptr(), float(L), out.data_ptr(), info.data_ptr(), float(tol),
+                                         int(max_iter), _stream())
+        if rc == 1:
+            return None
+        _check(rc, "apb_lm_solve_sparse")
+        return out, info
 
     def chi2(self, x, out=None):
         """(sum W (Y - model)^2, finite flag) as a 2-element device tensor."""

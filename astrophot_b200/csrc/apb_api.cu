@@ -11,6 +11,7 @@
 #include "apb_sample.cuh"
 #include "apb_image.cuh"
 #include "apb_fft.cuh"
+#include "apb_solve.cuh"
 
 
 static thread_local std::string g_err;
@@ -118,6 +119,13 @@ struct apb_plan {
   BlockDesc* d_vblocks = nullptr; int n_vblocks = 0;
   int *d_act_slot = nullptr, *d_act_off = nullptr;
   double* d_part = nullptr;
+  // block-sparse PCG solver (apb_solve.cuh): usable when no parameter is shared between sources
+  bool sparse_ok = false;
+  PcgRow* d_prows = nullptr; int n_prows = 0;
+  PcgEntry* d_pentries = nullptr;
+  PcgItem* d_pitems = nullptr; int n_pitems = 0;
+  double *d_bvals = nullptr, *d_diagH = nullptr, *d_pfac = nullptr, *d_pvec = nullptr;
+  int pcg_grid = 0;
   double *d_xtmp = nullptr, *d_xtmp2 = nullptr, *d_rpp = nullptr, *d_atmp = nullptr, *d_atmp2 = nullptr, *d_rec2 = nullptr;
   cudaStream_t trial_stream = nullptr;   // concurrent chi^2 pass of apb_lm_trial (on the second plan)
   cudaEvent_t ev_trial_fork = nullptr, ev_trial_join = nullptr;
@@ -697,6 +705,66 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PRC(own_upload(p, act_slot, &p->d_act_slot));
     PRC(own_upload(p, act_off, &p->d_act_off));
     PRC(own_alloc(p, (void**)&p->d_part, sizeof(double) * BLK_VALS * (size_t)std::max(items.size(), vitems.size())));
+
+    // ---- block-sparse structure of J^T W J for the PCG solver: row blocks = (source, plane chunk),
+    //      every block feeds the row block of its a side and (off-diagonal blocks) of its b side
+    {
+      std::vector<int> uses(std::max(n_par, 1), 0);
+      bool unique = n_par > 0;
+      for (int sl : act_slot)
+        if (++uses[sl] > 1) unique = false;
+      for (int k = 0; k < n_par; ++k)
+        if (uses[k] == 0) unique = false;   // a free parameter no source depends on: singular block, leave it to the dense path
+      if (unique) {
+        std::vector<PcgRow> prows;
+        std::vector<std::vector<PcgEntry>> ents;
+        std::vector<int> row_of((size_t)n_src * (APB_MAX_ELEM / NB_MAX + 1), -1);
+        const int RPS = APB_MAX_ELEM / NB_MAX + 1;
+        for (size_t k = 0; k < blocks.size(); ++k) {
+          const BlockDesc& bd = blocks[k];
+          if (!bd.diag) continue;
+          row_of[(size_t)bd.a * RPS + bd.pa0 / NB_MAX] = (int)prows.size();
+          prows.push_back(PcgRow{bd.a, bd.pa0, bd.na, (int)k});
+          ents.emplace_back();
+        }
+        for (size_t k = 0; k < blocks.size(); ++k) {
+          const BlockDesc& bd = blocks[k];
+          const int ra = row_of[(size_t)bd.a * RPS + bd.pa0 / NB_MAX], rb = row_of[(size_t)bd.b * RPS + bd.pb0 / NB_MAX];
+          if (ra < 0 || rb < 0) { unique = false; break; }
+          ents[ra].push_back(PcgEntry{(int)k, 0, act_off[bd.b] + bd.pb0, bd.nb});
+          if (!bd.diag) ents[rb].push_back(PcgEntry{(int)k, 1, act_off[bd.a] + bd.pa0, bd.na});
+        }
+        if (unique) {
+          std::vector<PcgEntry> flat;
+          std::vector<PcgItem> pitems;
+          const int CH = 32;
+          for (size_t r = 0; r < prows.size(); ++r) {
+            const int e0 = (int)flat.size();
+            flat.insert(flat.end(), ents[r].begin(), ents[r].end());
+            const int e1 = (int)flat.size();
+            const bool multi = e1 - e0 > CH;
+            for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), multi ? (e == e0 ? 1 : 2) : 0});
+          }
+          p->n_prows = (int)prows.size(); p->n_pitems = (int)pitems.size();
+          PRC(own_upload(p, prows, &p->d_prows));
+          PRC(own_upload(p, flat, &p->d_pentries));
+          PRC(own_upload(p, pitems, &p->d_pitems));
+          PRC(own_alloc(p, (void**)&p->d_bvals, sizeof(double) * 64 * std::max<size_t>(blocks.size(), 1)));
+          PRC(own_alloc(p, (void**)&p->d_diagH, sizeof(double) * (size_t)n_par));
+          PRC(own_alloc(p, (void**)&p->d_pfac, sizeof(double) * 64 * std::max<size_t>(prows.size(), 1)));
+          PRC(own_alloc(p, (void**)&p->d_pvec, sizeof(double) * 5 * (size_t)n_par));
+          PCU(cudaMemset(p->d_bvals, 0, sizeof(double) * 64 * std::max<size_t>(blocks.size(), 1)));
+          int dev = 0, sms = 148, per_sm = 1;
+          PCU(cudaGetDevice(&dev));
+          PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+          PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
+          // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
+          const int want = std::max(1, std::min(sms * std::min(per_sm, 2), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
+          p->pcg_grid = want;
+          p->sparse_ok = true;
+        }
+      }
+    }
   }
 
   // ---- tables and arenas
@@ -994,7 +1062,8 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
     k_block_final<<<dim3(p->n_blocks, BLK_VALS / 8), 256, 0, st>>>(p->d_src, p->d_blocks, p->n_blocks, p->d_act_slot,
-                                                            p->d_act_off, p->d_part, JtWJ, JtWr, P, -1.0, 0);
+                                                            p->d_act_off, p->d_part, JtWJ, JtWr, P, -1.0, 0,
+                                                            p->sparse_ok ? p->d_bvals : nullptr, p->d_diagH);
     LAUNCH_CHECK();
   }
   p->stats.launches = p->launches;
@@ -1028,7 +1097,7 @@ static int geodesic_core(apb_plan* p, const double* xdh, const double* h, double
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
     k_block_final<<<dim3(p->n_vblocks, BLK_VALS / 8), 256, 0, st>>>(p->d_src, p->d_vblocks, p->n_vblocks, p->d_act_slot,
-                                                             p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1);
+                                                             p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1, nullptr, nullptr);
     LAUNCH_CHECK();
   }
   return 0;
@@ -1141,6 +1210,24 @@ extern "C" int apb_lm_solve(const double* H, const double* g, double L, int P, d
   if (P <= 0) return 0;
   LmEpi e0{0, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr};
   return lm_solve_launch(H, g, L, P, h, info, e0, (cudaStream_t)stream);
+}
+
+// Damped solve of the system of the last apb_normal_eq by block-sparse PCG (apb_solve.cuh).
+//   g: device, n_par;  h: device, n_par (out);  info: device, 2 doubles {iterations, |r|/|b|}.
+// Returns 1 (not an error) when the plan cannot use it (parameters shared between sources).
+extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, double* h, double* info, double tol,
+                                   int max_iter, void* stream) {
+  if (!p) APB_FAIL("plan is NULL");
+  if (!p->sparse_ok) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P = (size_t)p->n_par;
+  PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_act_slot, p->d_act_off,
+            p->d_bvals, p->d_diagH, p->d_pfac, g, h, p->d_pvec, p->d_pvec + P, p->d_pvec + 2 * P, p->d_pvec + 3 * P,
+            info, p->n_par, max_iter > 0 ? max_iter : 2000, L, tol > 0.0 ? tol : 1e-14};
+  void* args[] = {&A};
+  CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(256), args, 0, st));
+  g_launches++;
+  return 0;
 }
 
 extern "C" int apb_plan_stats(apb_plan_t* p, apb_stats_t* out) {

@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) k_block_final(const DevSrc* __restrict__ 
                                                      int nblocks, const int* __restrict__ act_slot,
                                                      const int* __restrict__ act_off, const double* __restrict__ part,
                                                      double* __restrict__ H, double* __restrict__ g, int P, double gsign,
-                                                     int vec_only) {
+                                                     int vec_only, double* __restrict__ bvals, double* __restrict__ diagH) {
   const int bi = blockIdx.x;
   const BlockDesc bd = blocks[bi];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -445,8 +445,14 @@ __global__ void __launch_bounds__(256) k_block_final(const DevSrc* __restrict__ 
   if (j < 0) {
     atomicAdd(&g[sa[i]], gsign * tot);
   } else {
-    atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
-    if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
+    if (H) {
+      atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
+      if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
+    }
+    if (bvals) {   // block-sparse copy for the PCG solver (apb_solve.cuh); single writer per value
+      bvals[(long long)bi * (NB_MAX * NB_MAX) + i * NB_MAX + j] = tot;
+      if (bd.diag && i == j) diagH[sa[i]] = tot;
+    }
   }
 }
 

@@ -144,6 +144,9 @@ class LM(BaseOptimizer):
         self.hess = self.grad = None
         self._small_solver_max = kwargs.get("small_solver_max", 159)   # single-CTA device solver up to this P
         self._hess_version, self._factor_key, self._factor = 0, None, None
+        self._sparse_solver = bool(kwargs.get("sparse_solver", True))
+        self._blocks_version = -1       # _hess_version whose blocks the plan holds (set by _step, not by natural-units builds)
+        self.pcg_iterations = []
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
     # -- damping -------------------------------------------------------------
@@ -187,7 +190,19 @@ class LM(BaseOptimizer):
         P = rhs.numel()
         if P <= self._small_solver_max:
             return lm_solve(self.hess, rhs, L)
-        # large systems: same damped matrix (lm.py:359-371), library dense solver on the device.  The matrix is
+        # large systems, no parameter shared between sources: block-sparse PCG on the <= 8x8 source-pair blocks the
+        # normal-equation kernels produced (one cooperative launch); checked by its final relative residual
+        if self._sparse_solver and not self.distributed and self._blocks_version == self._hess_version:
+            res = self.plan.solve_sparse(rhs.contiguous(), L)
+            if res is None:
+                self._sparse_solver = False
+            else:
+                h, info = res
+                its, rel = info.tolist()
+                self.pcg_iterations.append(int(its))
+                if rel <= 1e-10:
+                    return h
+        # otherwise: same damped matrix (lm.py:359-371), library dense solver on the device.  The matrix is
         # symmetric positive definite for L > 0, so it is Cholesky-factored once per (H, L) and the factor serves
         # both solves of a lambda-trial (h and the geodesic correction); LU is the fallback.
         key = (self._hess_version, float(L))
@@ -233,6 +248,7 @@ class LM(BaseOptimizer):
             self._allreduce(self._g)
         self.hess, self.grad = self._H, self._g
         self._hess_version += 1
+        self._blocks_version = self._hess_version
         init_chi2 = chi2
         nostep = True
         best = (torch.zeros_like(x), init_chi2, self.L)

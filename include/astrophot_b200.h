@@ -161,6 +161,15 @@ int apb_plan_reserve(apb_plan_t *plan, const int64_t *caps);
  * H: device P*P (not modified), g, h: device P.  info: device int, 0 ok. */
 int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, int *info, void *stream);
 
+/* The same damped system for large parameter counts (crowded fields, fit/lm.py:359-371 with P ~ 1e4):
+ * J^T W J of the last apb_normal_eq is kept inside the plan as its list of <= 8x8 source-pair blocks, and the
+ * system is solved by block-Jacobi preconditioned conjugate gradients in one persistent cooperative kernel.
+ * g, h: device, n_par.  info: device, 2 doubles {iterations, final |r|/|b|}.  tol <= 0: 1e-14; max_iter <= 0: 2000.
+ * Returns 1 (no error set) if the plan cannot use it (a parameter shared between sources, as in joint fits):
+ * use apb_lm_solve or a dense library solver on the JtWJ of apb_normal_eq instead. */
+int apb_lm_solve_sparse(apb_plan_t *plan, const double *g, double L, double *h, double *info, double tol,
+                        int max_iter, void *stream);
+
 /* fit/lm.py:268-293, one pass of the lambda search with every tensor operation on the device:
  *   h = solve(L, g);  rpp = geodesic(x + d h, h, d);  a = -solve(L, rpp)/2 (zeros when L <= 1e-4);
  *   ha = h + acceleration a;  rec = { chi2(x + ha), status flag (see apb_chi2), |a|, |h| }.

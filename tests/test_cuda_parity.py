@@ -242,13 +242,20 @@ def test_lm_trial_pieces_equal_fused_trial(name):
     np.testing.assert_allclose(r1.lambda_history[-1], r2.lambda_history[-1], rtol=1e-9, atol=1e-10)
 
 
-def test_lm_library_solver_path_matches_reference():
-    """Large systems (P > 159: crowded fields) factor the damped matrix with the library Cholesky once per
-    (H, L) instead of the single-CTA solver; forced here on the crowded golden (P = 99)."""
+@pytest.mark.parametrize("sparse", [True, False])
+def test_lm_large_system_solvers_match_reference(sparse):
+    """Large systems (P > 159: crowded fields) solve the damped system by block-sparse PCG on the source-pair
+    blocks (apb_lm_solve_sparse) or, as fallback, a library Cholesky factored once per (H, L); both forced
+    here on the crowded golden (P = 99) and held to the reference's LM history."""
     fix = load_golden("crowded")
     m, _ = scenes.build(ap, "crowded", data=golden_data(fix))
-    r = ap.fit.LM(m, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, small_solver_max=0).fit()
-    assert not r._fused_trial and r._factor is not None
+    r = ap.fit.LM(m, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, small_solver_max=0,
+                  sparse_solver=sparse).fit()
+    assert not r._fused_trial
+    if sparse:
+        assert r._factor is None and len(r.pcg_iterations) > 0 and max(r.pcg_iterations) < 500
+    else:
+        assert r._factor is not None and not r.pcg_iterations
     ref_loss = fix["loss_history"]
     n = min(len(ref_loss), len(r.loss_history))
     moving = 1
@@ -257,6 +264,39 @@ def test_lm_library_solver_path_matches_reference():
     assert moving >= 3
     np.testing.assert_allclose(r.loss_history[:moving], ref_loss[:moving], rtol=1e-8)
     np.testing.assert_allclose(r.L_history[:moving], fix["L_history"][:moving], rtol=1e-12)
+    for k in range(moving):
+        np.testing.assert_allclose(r.lambda_history[k], fix["lambda_history"][k], rtol=1e-8, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["crowded", "group", "c1_sersic"])
+def test_sparse_pcg_solve_vs_dense(name):
+    """apb_lm_solve_sparse against numpy's dense solve of the damped matrix (lm.py:359-371) built from the
+    J^T W J of the same apb_normal_eq call."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    plan = _plan(scene)
+    H, g, _ = plan.normal_eq(fix["x0"], as_rep=True, check=True)
+    Hn, gn = H.cpu().numpy(), g.cpu().numpy()
+    rng = np.random.default_rng(5)
+    for L in (1e-6, 1e-2, 1.0, 50.0):
+        for rhs in (gn, rng.normal(size=len(gn))):
+            res = plan.solve_sparse(torch.as_tensor(rhs, device="cuda"), L)
+            assert res is not None
+            h, info = res
+            its, rel = info.tolist()
+            want = orc.lm_solve(Hn, rhs, L)
+            assert rel <= 1e-12 and its < 1000, (L, its, rel)
+            np.testing.assert_allclose(h.cpu().numpy(), want, rtol=1e-8, atol=1e-11 * np.abs(want).max())
+
+
+def test_sparse_pcg_refuses_shared_parameters():
+    fix = load_golden("joint")
+    model, _ = scenes.build(ap, "joint", data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    plan = _plan(scene)
+    H, g, _ = plan.normal_eq(fix["x0"], as_rep=True, check=True)
+    assert plan.solve_sparse(g, 1.0) is None
 
 
 def test_public_api_sample_and_jacobian():
