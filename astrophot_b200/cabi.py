@@ -16,7 +16,7 @@ from .errors import NativeLibraryError
 
 __all__ = ["lib", "load_library", "Plan", "lm_solve", "LIB_PATH"]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libastrophot_b200.so")
+LIB_PATH = os.environ.get("APB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libastrophot_b200.so")
 
 MAX_ELEM, MAX_PROF, MAX_DEPTH = sc.MAX_ELEM, sc.MAX_PROF, 4
 
@@ -139,7 +139,7 @@ def _dev_f64(x):
 class Plan:
     """A lowered model tree resident on the device (``apb_plan_t``)."""
 
-    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True, share=None):
+    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True, share=None, pooled_integration=False):
         """``conv``: None (per-source psf_convolve_mode), "direct" or "fft" to force one
         convolution kernel family for every source (tests, benchmarks).
         ``share``: another Plan of the same scene whose device copies of data / weight / mask / PSFs
@@ -204,7 +204,7 @@ class Plan:
             c.ref_mode, c.psf, c.psf_shift = s.ref_mode, s.psf, s.psf_shift
             c.conv_mode = int(getattr(s, "conv_mode", 0))
             c.tolerance, c.softening = s.tolerance, s.softening
-        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4))
+        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4) | (8 if pooled_integration else 0))
         handle = C.c_void_p()
         _check(L.apb_plan_create(srcs, n_src, imgs, n_img, psfs, n_psf, pars, self.n_par, C.byref(opts),
                                  C.byref(handle)), "apb_plan_create")

@@ -2,6 +2,8 @@
 // Builds the device tables once per plan, then every call is a fixed sequence of
 // kernel launches on the caller's stream with no host synchronisation.
 #include <algorithm>
+#include <climits>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -41,11 +43,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -99,6 +101,10 @@ struct apb_plan {
   bool use_coop = false;           // fused integration kernel (k_integrate) instead of per-depth launches
   int refine_lanes = 16;           // lanes sharing one queue entry
   int integrate_grid[2] = {148 * 4, 148 * 3};   // [grad] persistent CTAs of k_integrate (one resident wave)
+  int pool_grid[2] = {148 * 4, 148 * 3};        // [grad] persistent CTAs of k_integrate_pool
+  int pool_min = 150000;                        // depth-1 queue length from which the pooled kernel takes over
+  int pool_g2 = 25, pool_nv = 8;                // largest gridding^2 / values per child of the plan
+  bool pool_ok = false;
   // arenas
   double *d_stamp = nullptr, *d_out = nullptr, *d_psfst = nullptr, *d_meanpart = nullptr, *d_skyJ = nullptr;
   // queues
@@ -354,6 +360,12 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     fdescs.push_back(D);
     return (int)fdescs.size() - 1;
   };
+  apb_opts_t opts_env{};   // APB_PLAN_FLAGS ORs bits into opts.flags (experiments: kernel-family switches without a rebuild)
+  if (const char* e = getenv("APB_PLAN_FLAGS")) {
+    if (opts) opts_env = *opts;
+    opts_env.flags |= atoi(e);
+    opts = &opts_env;
+  }
   const int conv_force = opts ? (opts->flags & 3) : 0;   // 1: direct everywhere, 2: FFT everywhere
   for (int i = 0; i < n_src; ++i) {
     const apb_source_t& a = src[i];
@@ -823,6 +835,21 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate<true>, 128, 0));
     p->integrate_grid[0] = sms * std::max(1, b0);
     p->integrate_grid[1] = sms * std::max(1, b1);
+    // throughput form (k_integrate_pool) for long queues
+    int g2 = 1, nv = 1;
+    for (int i = 0; i < n_src; ++i)
+      if (S[i].integrate_mode == APB_INTEGRATE_THRESHOLD) {
+        g2 = std::max(g2, S[i].gridding * S[i].gridding);
+        nv = std::max(nv, 1 + S[i].n_elem);
+      }
+    p->pool_g2 = g2; p->pool_nv = nv;
+    p->pool_ok = g2 * nv <= POOL_CSUM;
+    if (const char* e = getenv("APB_POOL_MIN")) p->pool_min = atoi(e);
+    if (opts && (opts->flags & 8)) p->pool_min = 0;
+    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate_pool<false>, POOL_B, 0));
+    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate_pool<true>, POOL_B, 0));
+    p->pool_grid[0] = sms * std::max(1, b0);
+    p->pool_grid[1] = sms * std::max(1, b1);
   }
 
   PCU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
@@ -911,10 +938,23 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
         PB(K_SELECT);
         k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);
         LAUNCH_CHECK();
-        PB(grad ? K_INTEGRATE_G : K_INTEGRATE);
-        if (grad) k_integrate<true><<<p->integrate_grid[1], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
-        else k_integrate<false><<<p->integrate_grid[0], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes);
-        LAUNCH_CHECK();
+        // the queue length is known only on the device: short queues are integrated by k_integrate (lanes share an
+        // entry: lowest latency), long ones by k_integrate_pool (a lane per cell: full lanes); each kernel returns at
+        // once when the queue is not its kind.  A queue cannot be longer than the first pass has pixels.
+        const bool may_pool = p->pool_ok && p->first_evals[mode] >= p->pool_min;
+        const int n_max = may_pool ? p->pool_min : INT_MAX;
+        if (n_max > 0) {
+          PB(grad ? K_INTEGRATE_G : K_INTEGRATE);
+          if (grad) k_integrate<true><<<p->integrate_grid[1], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
+          else k_integrate<false><<<p->integrate_grid[0], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
+          LAUNCH_CHECK();
+        }
+        if (may_pool) {
+          PB(grad ? K_POOL_G : K_POOL);
+          if (grad) k_integrate_pool<true><<<p->pool_grid[1], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->pool_min, p->pool_g2, p->pool_nv);
+          else k_integrate_pool<false><<<p->pool_grid[0], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->pool_min, p->pool_g2, 1);
+          LAUNCH_CHECK();
+        }
       } else {
       PB(K_SELECT);
       k_select<<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, q);

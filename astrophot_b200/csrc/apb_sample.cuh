@@ -718,8 +718,9 @@ __device__ __noinline__ void split_and_store_spline(const DevSrc& s, const DevDy
 
 template <bool GRAD>
 __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn, int mode,
-                                                      double* __restrict__ stamp, Queues q, int L) {
+                                                      double* __restrict__ stamp, Queues q, int L, int n_max) {
   const int n = min(q.count[1], q.cap[1]);
+  if (n >= n_max) return;   // long queues belong to k_integrate_pool
   const Level& Lv = q.lv[1];
   const int lane = threadIdx.x & 31;
   const int epw = 32 / L, g = lane / L, gl = lane - g * L;
@@ -773,6 +774,201 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
         case APB_SPLINE: split_and_store_spline<GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
         default: break;
       }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Throughput form of the same integration, for queues far larger than the grid (crowded fields:
+// 10^5..10^8 entries).  k_integrate spends 16 lanes on the 9 nodes of a depth-1 entry and 32 lanes on
+// the 25 children of a subdivided one; here a CTA draws 128 entries at a time and keeps every lane on
+// its own cell:
+//   phase 1  one thread per depth-1 entry (all its nodes); entries that pass are stored, the others
+//            are listed in shared memory;
+//   phase 2  the children of all listed entries are pooled: thread c takes child c % G^2 of listed
+//            entry c / G^2 (full lanes whatever the number of failing entries); child integrals go
+//            to shared memory, children that fail again are listed;
+//   phase 3  each listed child is subdivided by a whole warp, depth first (split_cell, as above);
+//   phase 4  one thread per (entry, plane) adds the child integrals in child order and stores.
+// Same nodes, same decisions, same child values as k_integrate; only the order in which the
+// children of an entry are added differs (sequential instead of a shuffle tree).  k_integrate and
+// k_integrate_pool are launched back to back and pick by the queue length, which only the device knows.
+// ----------------------------------------------------------------------------
+#define POOL_B 128        // depth-1 entries per CTA batch (= CTA size)
+#ifndef POOL_MINB
+#define POOL_MINB 5       // resident CTAs per SM the value-only kernel is compiled for (register budget)
+#endif
+#define POOL_CSUM 3200    // child integrals held per CTA (doubles)
+
+template <int KIND, bool GRAD>
+__device__ __forceinline__ bool pool_child(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
+                                           double* __restrict__ out, int nv) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  const int G = s.gridding;
+  double scale = 1.0, ascale = 1.0, thr = d.thr[mode];
+  scale /= (double)G;
+  ascale /= (double)(G * G);
+  thr *= (double)(G * G);
+  const double dx = (-(G - 1) / (2.0 * G) + (double)(ch % G) / G);
+  const double dy = (-(G - 1) / (2.0 * G) + (double)(ch / G) / G);
+  const double cx = X + (s.S[0] * dx + s.S[1] * dy);
+  const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
+  Acc<GRAD, NE> ca;
+  const double centre = gl_nodes<KIND, GRAD>(s, d, cx, cy, scale, ascale, 0, 1, ca);
+  out[0] = ca.v[0];
+  if (GRAD)
+    for (int e = 0; e < ne && 1 + e < nv; ++e) out[1 + e] = ca.v[1 + e];
+  return 2 < s.max_depth && fabs(ca.v[0] - centre) > thr;
+}
+
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void pool_split_child(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
+                                                 double* __restrict__ out, int nv, int* __restrict__ qcount) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  const int G = s.gridding;
+  const double dx = (-(G - 1) / (2.0 * G) + (double)(ch % G) / G);
+  const double dy = (-(G - 1) / (2.0 * G) + (double)(ch / G) / G);
+  const double cx = X + (s.S[0] * dx + s.S[1] * dy);
+  const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
+  Acc<GRAD, NE> sub;
+  split_cell<KIND, GRAD, APB_MAX_DEPTH - 3>(s, d, mode, 2, cx, cy, sub, qcount);
+  if ((threadIdx.x & 31) == 0) {
+    out[0] = sub.v[0];
+    if (GRAD)
+      for (int e = 0; e < ne && 1 + e < nv; ++e) out[1 + e] = sub.v[1 + e];
+  }
+}
+template <bool GRAD>
+__device__ __noinline__ bool pool_child_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
+                                               double* __restrict__ out, int nv) {
+  return pool_child<APB_SPLINE, GRAD>(s, d, mode, X, Y, ch, out, nv);
+}
+template <bool GRAD>
+__device__ __noinline__ void pool_split_child_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
+                                                     double* __restrict__ out, int nv, int* __restrict__ qcount) {
+  pool_split_child<APB_SPLINE, GRAD>(s, d, mode, X, Y, ch, out, nv, qcount);
+}
+
+// g2 = largest gridding^2 of the plan, nv = values per child (1, or 1 + largest element count)
+template <bool GRAD>
+__global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                                                          int mode, double* __restrict__ stamp, Queues q,
+                                                                          int n_min, int g2, int nv) {
+  __shared__ double csum[POOL_CSUM];
+  __shared__ double eX[POOL_B], eY[POOL_B];
+  __shared__ int eS[POOL_B], eP[POOL_B], list1[POOL_B];
+  __shared__ unsigned short list2[POOL_CSUM];   // child index < POOL_CSUM
+  __shared__ int s_base, s_nf1, s_nf2;
+  const int n = min(q.count[1], q.cap[1]);
+  if (n < n_min) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per_chunk = max(1, POOL_CSUM / (g2 * nv));   // listed entries whose children fit in csum
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_base = atomicAdd(&q.count[0], POOL_B);
+      s_nf1 = 0;
+      s_nf2 = 0;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (base >= n) break;
+    // ---- phase 1
+    {
+      const int t = base + tid;
+      const bool valid = t < n;
+      int si = 0, parent = 0;
+      double X = 0, Y = 0;
+      if (valid) {
+        si = q.lv[1].src[t];
+        X = q.lv[1].x[t];
+        Y = q.lv[1].y[t];
+        parent = q.lv[1].parent[t];
+      }
+      eS[tid] = si; eP[tid] = parent; eX[tid] = X; eY[tid] = Y;
+      const DevSrc& s = src[si];
+      const DevDyn& d = dyn[si];
+      bool split = false;
+      const unsigned me = 1u << lane;
+      switch (s.kind) {
+        case APB_SERSIC: split = depth1_entry<APB_SERSIC, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_EXPONENTIAL: split = depth1_entry<APB_EXPONENTIAL, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_GAUSSIAN: split = depth1_entry<APB_GAUSSIAN, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_MOFFAT: split = depth1_entry<APB_MOFFAT, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_SPLINE: split = depth1_entry_spline<GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        default: break;
+      }
+      if (split) list1[atomicAdd(&s_nf1, 1)] = tid;
+    }
+    __syncthreads();
+    const int nf1 = s_nf1;
+    for (int c0 = 0; c0 < nf1; c0 += per_chunk) {
+      const int nb = min(per_chunk, nf1 - c0);
+      if (tid == 0) s_nf2 = 0;
+      __syncthreads();
+      // ---- phase 2
+      int nchild_sum = 0;
+      for (int c = tid; c < nb * g2; c += POOL_B) {
+        const int pi = c / g2, ch = c - pi * g2;
+        const int e = list1[c0 + pi];
+        const DevSrc& s = src[eS[e]];
+        if (ch >= s.gridding * s.gridding) continue;
+        const DevDyn& d = dyn[eS[e]];
+        ++nchild_sum;
+        double* out = csum + (long long)c * nv;
+        bool again = false;
+        switch (s.kind) {
+          case APB_SERSIC: again = pool_child<APB_SERSIC, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_EXPONENTIAL: again = pool_child<APB_EXPONENTIAL, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_GAUSSIAN: again = pool_child<APB_GAUSSIAN, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_MOFFAT: again = pool_child<APB_MOFFAT, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_SPLINE: again = pool_child_spline<GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          default: break;
+        }
+        if (again) list2[atomicAdd(&s_nf2, 1)] = (unsigned short)c;
+      }
+      if (nchild_sum) atomicAdd(&q.count[2], nchild_sum);
+      __syncthreads();
+      // ---- phase 3
+      const int nf2 = s_nf2;
+      for (int k = wid; k < nf2; k += POOL_B / 32) {
+        const int c = list2[k];
+        const int pi = c / g2, ch = c - pi * g2;
+        const int e = list1[c0 + pi];
+        const DevSrc& s = src[eS[e]];
+        const DevDyn& d = dyn[eS[e]];
+        double* out = csum + (long long)c * nv;
+        switch (s.kind) {
+          case APB_SERSIC: pool_split_child<APB_SERSIC, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_EXPONENTIAL: pool_split_child<APB_EXPONENTIAL, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_GAUSSIAN: pool_split_child<APB_GAUSSIAN, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_MOFFAT: pool_split_child<APB_MOFFAT, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_SPLINE: pool_split_child_spline<GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          default: break;
+        }
+      }
+      __syncthreads();
+      // ---- phase 4
+      const int nvals = GRAD ? nv : 1;
+      for (int idx = tid; idx < nb * nvals; idx += POOL_B) {
+        const int pi = idx / nvals, v = idx - pi * nvals;
+        const int e = list1[c0 + pi];
+        const DevSrc& s = src[eS[e]];
+        const int nchild = s.gridding * s.gridding;
+        const double* in = csum + (long long)pi * g2 * nv + v;
+        double tot = 0.0;
+        for (int ch = 0; ch < nchild; ++ch) tot += in[(long long)ch * nv];
+        double* basep = stamp + s.stamp_off + eP[e];
+        if (v == 0) {
+          basep[0] = tot;
+        } else if (v - 1 < s.n_elem) {
+          const int p = s.plane[v - 1];
+          if (p > 0) basep[(long long)p * s.plane_stride] = tot * dyn[eS[e]].chain[v - 1];
+        }
+      }
+      __syncthreads();
     }
   }
 }

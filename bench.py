@@ -334,8 +334,11 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
     # 230 value + 7 derivatives (reference-faithful pow form; the kernels use a cheaper log/exp form)
     I_V, I_G = 138.0, 230.0
     spe_int = 9.0 * sum(st["queued"])      # Gauss-Legendre 3x3 nodes per queue entry of the last call (approximate for the sum)
-    n_int = kern.get("k_integrate", (0, 0))[0]
-    n_int_g = kern.get("k_integrate_grad", (0, 0))[0]
+    # k_integrate and k_integrate_pool are launched back to back; the one whose kind of queue it is not returns at once
+    pooled = kern.get("k_integrate_pool", (0, 0.0))[1] > kern.get("k_integrate", (0, 0.0))[1]
+    k_int, k_int_g = ("k_integrate_pool", "k_integrate_pool_grad") if pooled else ("k_integrate", "k_integrate_grad")
+    n_int = kern.get(k_int, (0, 0))[0]
+    n_int_g = kern.get(k_int_g, (0, 0))[0]
     work = {
         "k_conv": {"bound": "fp64", "flops": conv_flops, "what": f"2*P_s^2 flop per output pixel and plane, {n_dir} direct-convolved sources"},
         "k_fft_rows": {"bound": "hbm", "bytes": float(fft_rows),
@@ -350,9 +353,9 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
                     "what": f"{first_px} first-pass evaluations/launch x {I_V:.0f} nominal FP64 instr (x2 flop)"},
         "k_first_grad": {"bound": "fp64", "flops": 2.0 * I_G * first_px * kern.get("k_first_grad", (0, 0))[0],
                          "what": f"{first_px} first-pass evaluations/launch x {I_G:.0f} nominal FP64 instr (value + derivatives)"},
-        "k_integrate": {"bound": "fp64", "flops": 2.0 * I_V * spe_int * n_int,
+        k_int: {"bound": "fp64", "flops": 2.0 * I_V * spe_int * n_int,
                         "what": f"~{spe_int:.0f} sub-pixel evaluations/launch (last call's queue) x {I_V:.0f} nominal FP64 instr"},
-        "k_integrate_grad": {"bound": "fp64", "flops": 2.0 * I_G * spe_int * n_int_g,
+        k_int_g: {"bound": "fp64", "flops": 2.0 * I_G * spe_int * n_int_g,
                              "what": f"~{spe_int:.0f} sub-pixel evaluations/launch x {I_G:.0f} nominal FP64 instr"},
     }
     return {k: v for k, v in work.items() if v.get("flops", 0) or v.get("bytes", 0)}

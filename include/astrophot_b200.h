@@ -102,7 +102,8 @@ typedef struct {
 typedef struct {
   int64_t queue_capacity; /* entries per refinement level; 0 = automatic (grown by apb_plan_reserve) */
   int32_t flags;          /* bits 0-1: APB_CONV_* override for every source; bit 2: per-depth
-                             refinement launches instead of the fused k_integrate */
+                             refinement launches instead of the fused k_integrate; bit 3: pooled
+                             (throughput) integration kernel whatever the queue length */
   int32_t _pad;
 } apb_opts_t;
 

@@ -127,6 +127,30 @@ def test_fused_integration_equals_per_depth_launches(name):
     assert np.max(np.abs(Ja - Jb) / scale) < 1e-12
 
 
+@pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat", "psf_sersic", "moffat_psf_model", "group",
+                                  "joint", "crowded"])
+def test_pooled_integration_equals_lane_shared(name):
+    """k_integrate_pool (throughput form for long queues: a lane per cell, children of all failing
+    entries pooled over the CTA) against k_integrate: same nodes, same decisions, same counts; sums
+    differ only in the order the children of an entry are added."""
+    from astrophot_b200.cabi import Plan
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name)
+    scene, _ = lower(model)
+    pa, pb = Plan(scene), Plan(scene, pooled_integration=True)
+    a = pa.sample(fix["x_val"])
+    b = pb.sample(fix["x_val"])
+    for u, v in zip(a, b):
+        assert rel_err(u.cpu().numpy(), v.cpu().numpy()) < 1e-13
+    assert pa.stats()["queued"] == pb.stats()["queued"]
+    assert sum(pa.stats()["queued"]) > 0
+    Ja = np.concatenate([j.cpu().numpy().reshape(-1, scene.n_par) for j in pa.jacobian(fix["x_rep"], as_rep=True)])
+    Jb = np.concatenate([j.cpu().numpy().reshape(-1, scene.n_par) for j in pb.jacobian(fix["x_rep"], as_rep=True)])
+    assert pa.stats()["queued"] == pb.stats()["queued"]
+    scale = np.maximum(np.abs(Jb).max(axis=0), 1e-300)
+    assert np.max(np.abs(Ja - Jb) / scale) < 1e-12
+
+
 @pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
 def test_sample_vs_oracle_and_reference(name):
     fix = load_golden(name)
