@@ -42,11 +42,17 @@ class apb_source_t(C.Structure):
                 ("sampling_mode", C.c_int32), ("quad_init", C.c_int32), ("integrate_mode", C.c_int32),
                 ("quad_level", C.c_int32), ("gridding", C.c_int32), ("max_depth", C.c_int32),
                 ("ref_mode", C.c_int32), ("psf", C.c_int32), ("psf_shift", C.c_int32), ("conv_mode", C.c_int32),
+                ("owner", C.c_int32), ("_pad", C.c_int32),
                 ("tolerance", C.c_double), ("softening", C.c_double)]
 
 
+class apb_owner_t(C.Structure):
+    _fields_ = [("image", C.c_int32), ("out", C.c_int32 * 4), ("n_slot", C.c_int32), ("slot", C.c_int32 * MAX_ELEM)]
+
+
 class apb_opts_t(C.Structure):
-    _fields_ = [("queue_capacity", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("queue_capacity", C.c_int64), ("flags", C.c_int32), ("n_owners", C.c_int32),
+                ("owners", C.POINTER(apb_owner_t))]
 
 
 class apb_stats_t(C.Structure):
@@ -58,7 +64,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -91,6 +97,8 @@ def load_library(path=None):
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
     L.apb_lm_solve_sparse.argtypes = [vp, dp, C.c_double, dp, dp, C.c_double, C.c_int, vp]
+    L.apb_plan_block_doubles.argtypes = [vp]
+    L.apb_plan_bind_blocks.argtypes = [vp, dp]
     L.apb_lm_trial.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
     L.apb_lm_trial_begin.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, dp, dp, vp]
     L.apb_lm_trial_end.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp, vp]
@@ -106,6 +114,7 @@ def load_library(path=None):
             getattr(L, name).restype = C.c_int if name != "apb_last_error" else C.c_char_p
     L.apb_last_error.restype = C.c_char_p
     L.apb_launch_count.restype = C.c_longlong
+    L.apb_plan_block_doubles.restype = C.c_longlong
     _lib = L
     return L
 
@@ -203,8 +212,21 @@ class Plan:
             c.quad_level, c.gridding, c.max_depth = s.quad_level, s.gridding, s.max_depth
             c.ref_mode, c.psf, c.psf_shift = s.ref_mode, s.psf, s.psf_shift
             c.conv_mode = int(getattr(s, "conv_mode", 0))
+            c.owner = int(getattr(s, "owner", -1))
             c.tolerance, c.softening = s.tolerance, s.softening
         opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4) | (8 if pooled_integration else 0))
+        owners = getattr(scene, "owners", None)
+        if owners:       # models of the whole fit (the scene holds their pieces: lowering.tile_scene / shard_scene)
+            otab = (apb_owner_t * len(owners))()
+            for k, (img_id, rect, slots) in enumerate(owners):
+                otab[k].image = int(img_id)
+                otab[k].out[:] = [int(v) for v in rect]
+                otab[k].n_slot = len(slots)
+                for e, sl in enumerate(slots):
+                    otab[k].slot[e] = int(sl)
+            opts.n_owners = len(owners)
+            opts.owners = otab
+            self._keep.append(otab)
         handle = C.c_void_p()
         _check(L.apb_plan_create(srcs, n_src, imgs, n_img, psfs, n_psf, pars, self.n_par, C.byref(opts),
                                  C.byref(handle)), "apb_plan_create")
@@ -279,7 +301,8 @@ class Plan:
                    torch.empty(P, dtype=torch.float64, device="cuda"),
                    torch.empty(2, dtype=torch.float64, device="cuda"))
         H, g, c2 = out
-        _check(self._L.apb_normal_eq(self._h, x.data_ptr(), int(as_rep), H.data_ptr(), g.data_ptr(), c2.data_ptr(),
+        _check(self._L.apb_normal_eq(self._h, x.data_ptr(), int(as_rep), H.data_ptr() if H is not None else None,
+                                     g.data_ptr(), c2.data_ptr(),
                                      _stream()), "apb_normal_eq")
         return H, g, c2
 
@@ -325,6 +348,18 @@ class Plan:
             return None
         _check(rc, "apb_lm_solve_sparse")
         return out, info
+
+    def bind_blocks(self):
+        """Torch-owned device array that receives the block-sparse J^T W J of every normal_eq
+        ([64 doubles per owner block | diag H]; same layout on every rank of a tile-sharded fit, so a sum
+        all-reduce of it merges the ranks' normal equations).  None if the plan has no block-sparse form."""
+        n = int(self._L.apb_plan_block_doubles(self._h))
+        if n <= 0:
+            return None
+        buf = torch.zeros(n, dtype=torch.float64, device="cuda")
+        _check(self._L.apb_plan_bind_blocks(self._h, buf.data_ptr()), "apb_plan_bind_blocks")
+        self._keep.append(buf)
+        return buf
 
     def chi2(self, x, out=None):
         """(sum W (Y - model)^2, finite flag) as a 2-element device tensor."""

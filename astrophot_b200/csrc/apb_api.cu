@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unordered_map>
 
 #include "apb_internal.cuh"
 #include "apb_sample.cuh"
@@ -131,6 +132,9 @@ struct apb_plan {
   PcgEntry* d_pentries = nullptr;
   PcgItem* d_pitems = nullptr; int n_pitems = 0;
   double *d_bvals = nullptr, *d_diagH = nullptr, *d_pfac = nullptr, *d_pvec = nullptr;
+  double* d_bvals_own = nullptr;   // the plan's own [blocks | diag H] array (d_bvals may point at a caller's, apb_plan_bind_blocks)
+  long long n_cblocks = 0;
+  int *d_own_slot = nullptr, *d_own_off = nullptr;   // free-parameter lists of the owners (PCG rows are owner rows)
   int pcg_grid = 0;
   double *d_xtmp = nullptr, *d_xtmp2 = nullptr, *d_rpp = nullptr, *d_atmp = nullptr, *d_atmp2 = nullptr, *d_rec2 = nullptr;
   cudaStream_t trial_stream = nullptr;   // concurrent chi^2 pass of apb_lm_trial (on the second plan)
@@ -166,7 +170,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 extern "C" const char* apb_last_error(void) { return g_err.c_str(); }
 static int fft_len(int n);
 extern "C" int apb_fft_length(int n) { return n > 0 ? fft_len(n) : 0; }
-extern "C" int apb_version(void) { return 100; }
+extern "C" int apb_version(void) { return 101; }
 
 static void gauss_legendre(int n, double* x, double* w) {
   // Newton iteration on P_n (same nodes as scipy.special.roots_legendre to rounding)
@@ -649,7 +653,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     std::vector<BlockDesc> blocks, vblocks;
     auto add_block = [&](int a, int b, int pa0, int na, int pb0, int nb, int diag, int x0, int y0, int w, int h,
                          std::vector<BlockItem>& it, std::vector<BlockDesc>& bl) {
-      BlockDesc bd{a, b, pa0, na, pb0, nb, diag, (int)it.size(), 0};
+      BlockDesc bd{a, b, pa0, na, pb0, nb, diag, (int)it.size(), 0, -1, 0};
       const int rows = std::max(1, 2048 / std::max(w, 1));
       for (int r = 0; r < h; r += rows) {
         BlockItem bi{a, b, pa0, na, pb0, nb, x0, y0 + r, w, std::min(rows, h - r), diag, (int)bl.size()};
@@ -708,6 +712,164 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
                       x0, y0, x1 - x0, y1 - y0, items, blocks);
       }
     }
+    // ---- block-sparse structure of J^T W J for the PCG solver, laid out on the OWNERS (the models of the whole
+    //      fit; without an owner table every source is its own owner): row blocks = (owner, plane chunk), one
+    //      block per (owner pair, chunk pair) that overlaps anywhere -- the same list on every rank of a fit
+    //      sharded by image tile.  Every local block adds into its owner block (BlockDesc.cblock).
+    {
+      const int RPS = APB_MAX_ELEM / NB_MAX + 1;
+      const bool tabled = opts && opts->owners && opts->n_owners > 0;
+      const int n_own = tabled ? opts->n_owners : n_src;
+      std::vector<int> own_off(n_own + 1, 0), own_slot, owner_of(n_src, -1);
+      struct Rect { int image, x0, y0, w, h; };
+      std::vector<Rect> orect(n_own);
+      bool ok = n_par > 0;
+      if (tabled) {
+        for (int o = 0; o < n_own; ++o) {
+          const apb_owner_t& ow = opts->owners[o];
+          if (ow.n_slot < 0 || ow.n_slot > APB_MAX_ELEM) PFAIL("owner table: bad n_slot");
+          for (int k = 0; k < ow.n_slot; ++k) {
+            if (ow.slot[k] < 0 || ow.slot[k] >= n_par) PFAIL("owner table: parameter slot out of range");
+            own_slot.push_back(ow.slot[k]);
+          }
+          own_off[o + 1] = (int)own_slot.size();
+          orect[o] = Rect{ow.image, ow.out[0], ow.out[1], ow.out[2], ow.out[3]};
+        }
+        for (int i = 0; i < n_src; ++i) {
+          const int o = src[i].owner;
+          if (o < 0 || o >= n_own) PFAIL("source owner index out of range");
+          if (own_off[o + 1] - own_off[o] != S[i].n_act) PFAIL("a source and its owner disagree on the free parameters");
+          for (int k = 0; k < S[i].n_act; ++k)
+            if (own_slot[own_off[o] + k] != act_slot[act_off[i] + k]) PFAIL("a source and its owner disagree on the free parameters");
+          owner_of[i] = o;
+        }
+      } else {
+        own_slot = act_slot; own_off = act_off;
+        for (int i = 0; i < n_src; ++i) { owner_of[i] = i; orect[i] = Rect{S[i].image, S[i].ox, S[i].oy, S[i].ow, S[i].oh}; }
+      }
+      {   // the PCG needs every free parameter in exactly one owner
+        std::vector<int> uses(std::max(n_par, 1), 0);
+        for (int sl : own_slot)
+          if (++uses[sl] > 1) ok = false;
+        for (int k = 0; k < n_par; ++k)
+          if (uses[k] == 0) ok = false;   // a free parameter no model depends on: singular block, leave it to the dense path
+      }
+      if (ok) {
+        struct CB { int oa, ob, pa0, na, pb0, nb, diag; };
+        std::vector<CB> cbs;
+        std::unordered_map<unsigned long long, int> cb_of;
+        const unsigned long long KR = (unsigned long long)n_own * RPS;
+        auto key = [&](int oa, int ca, int ob, int cb) { return ((unsigned long long)oa * RPS + ca) * KR + ((unsigned long long)ob * RPS + cb); };
+        auto nact = [&](int o) { return own_off[o + 1] - own_off[o]; };
+        auto add_cb = [&](int oa, int pa0, int ob, int pb0, int diag) {
+          cb_of[key(oa, pa0 / NB_MAX, ob, pb0 / NB_MAX)] = (int)cbs.size();
+          cbs.push_back(CB{oa, ob, pa0, std::min(NB_MAX, nact(oa) - pa0), pb0, std::min(NB_MAX, nact(ob) - pb0), diag});
+        };
+        for (int o = 0; o < n_own; ++o)
+          for (int pa0 = 0; pa0 < nact(o); pa0 += NB_MAX)
+            for (int pb0 = pa0; pb0 < nact(o); pb0 += NB_MAX) add_cb(o, pa0, o, pb0, pa0 == pb0);
+        // overlapping owner pairs per (uncut) image, via a coarse grid
+        std::vector<int> order(n_own);
+        for (int o = 0; o < n_own; ++o) order[o] = o;
+        std::stable_sort(order.begin(), order.end(), [&](int u, int v) { return orect[u].image < orect[v].image; });
+        for (size_t g0 = 0; g0 < order.size();) {
+          size_t g1 = g0;
+          while (g1 < order.size() && orect[order[g1]].image == orect[order[g0]].image) ++g1;
+          std::vector<int> ids;
+          int maxx = 1, maxy = 1;
+          for (size_t k = g0; k < g1; ++k) {
+            const int o = order[k];
+            if (nact(o) == 0 || orect[o].w <= 0 || orect[o].h <= 0) continue;
+            ids.push_back(o);
+            maxx = std::max(maxx, orect[o].x0 + orect[o].w); maxy = std::max(maxy, orect[o].y0 + orect[o].h);
+          }
+          g0 = g1;
+          const int CELL = 64;
+          const int ncx = ceil_div(maxx, CELL), ncy = ceil_div(maxy, CELL);
+          std::vector<std::vector<int>> cells((size_t)ncx * ncy);
+          std::vector<int> big;   // owners covering many cells (sky): pair with everything directly
+          for (int a : ids) {
+            const Rect& A = orect[a];
+            const int c0x = std::max(A.x0, 0) / CELL, c1x = (A.x0 + A.w - 1) / CELL, c0y = std::max(A.y0, 0) / CELL, c1y = (A.y0 + A.h - 1) / CELL;
+            if ((long long)(c1x - c0x + 1) * (c1y - c0y + 1) > 64) { big.push_back(a); continue; }
+            for (int cy = c0y; cy <= c1y; ++cy)
+              for (int cx = c0x; cx <= c1x; ++cx) cells[(size_t)cy * ncx + cx].push_back(a);
+          }
+          std::vector<std::pair<int, int>> pairs;
+          for (auto& c : cells)
+            for (size_t u = 0; u < c.size(); ++u)
+              for (size_t v = u + 1; v < c.size(); ++v) pairs.emplace_back(std::min(c[u], c[v]), std::max(c[u], c[v]));
+          for (int a : big)
+            for (int b : ids)
+              if (b != a) pairs.emplace_back(std::min(a, b), std::max(a, b));
+          std::sort(pairs.begin(), pairs.end());
+          pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+          for (auto& pr : pairs) {
+            const Rect& A = orect[pr.first];
+            const Rect& B = orect[pr.second];
+            if (std::min(A.x0 + A.w, B.x0 + B.w) <= std::max(A.x0, B.x0) || std::min(A.y0 + A.h, B.y0 + B.h) <= std::max(A.y0, B.y0)) continue;
+            for (int pa0 = 0; pa0 < nact(pr.first); pa0 += NB_MAX)
+              for (int pb0 = 0; pb0 < nact(pr.second); pb0 += NB_MAX) add_cb(pr.first, pa0, pr.second, pb0, 0);
+          }
+        }
+        // local blocks -> owner blocks
+        for (auto& bd : blocks) {
+          int oa = owner_of[bd.a], ob = owner_of[bd.b], pa0 = bd.pa0, pb0 = bd.pb0, tr = 0;
+          if (oa == ob && bd.a != bd.b) PFAIL("two pieces of one model overlap on one image");
+          if (oa > ob) { std::swap(oa, ob); std::swap(pa0, pb0); tr = 1; }
+          auto itb = cb_of.find(key(oa, pa0 / NB_MAX, ob, pb0 / NB_MAX));
+          if (itb == cb_of.end()) PFAIL("owner table: two sources overlap but their owners' windows do not");
+          bd.cblock = itb->second; bd.ctrans = tr;
+        }
+        std::vector<PcgRow> prows;
+        std::vector<std::vector<PcgEntry>> ents;
+        std::vector<int> row_of((size_t)n_own * RPS, -1);
+        for (size_t k = 0; k < cbs.size(); ++k) {
+          const CB& cb = cbs[k];
+          if (!cb.diag) continue;
+          row_of[(size_t)cb.oa * RPS + cb.pa0 / NB_MAX] = (int)prows.size();
+          prows.push_back(PcgRow{cb.oa, cb.pa0, cb.na, (int)k});
+          ents.emplace_back();
+        }
+        for (size_t k = 0; k < cbs.size(); ++k) {
+          const CB& cb = cbs[k];
+          const int ra = row_of[(size_t)cb.oa * RPS + cb.pa0 / NB_MAX], rb = row_of[(size_t)cb.ob * RPS + cb.pb0 / NB_MAX];
+          ents[ra].push_back(PcgEntry{(int)k, 0, own_off[cb.ob] + cb.pb0, cb.nb});
+          if (!cb.diag) ents[rb].push_back(PcgEntry{(int)k, 1, own_off[cb.oa] + cb.pa0, cb.na});
+        }
+        std::vector<PcgEntry> flat;
+        std::vector<PcgItem> pitems;
+        const int CH = 32;
+        for (size_t r = 0; r < prows.size(); ++r) {
+          const int e0 = (int)flat.size();
+          flat.insert(flat.end(), ents[r].begin(), ents[r].end());
+          const int e1 = (int)flat.size();
+          const bool multi = e1 - e0 > CH;
+          for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), multi ? (e == e0 ? 1 : 2) : 0});
+        }
+        p->n_prows = (int)prows.size(); p->n_pitems = (int)pitems.size();
+        p->n_cblocks = (long long)cbs.size();
+        PRC(own_upload(p, prows, &p->d_prows));
+        PRC(own_upload(p, flat, &p->d_pentries));
+        PRC(own_upload(p, pitems, &p->d_pitems));
+        PRC(own_upload(p, own_slot, &p->d_own_slot));
+        PRC(own_upload(p, own_off, &p->d_own_off));
+        PRC(own_alloc(p, (void**)&p->d_bvals_own, sizeof(double) * (64 * (size_t)p->n_cblocks + (size_t)n_par)));
+        p->d_bvals = p->d_bvals_own; p->d_diagH = p->d_bvals + 64 * p->n_cblocks;
+        PRC(own_alloc(p, (void**)&p->d_pfac, sizeof(double) * 64 * std::max<size_t>(prows.size(), 1)));
+        PRC(own_alloc(p, (void**)&p->d_pvec, sizeof(double) * 5 * (size_t)n_par));
+        int dev = 0, sms = 148, per_sm = 1;
+        PCU(cudaGetDevice(&dev));
+        PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
+        // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
+        const int want = std::max(1, std::min(sms * std::min(per_sm, 2), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
+        p->pcg_grid = want;
+        p->sparse_ok = true;
+      } else if (tabled) {
+        PFAIL("owner table: a free parameter belongs to no owner or to several");
+      }
+    }
     p->n_items = (int)items.size(); p->n_blocks = (int)blocks.size();
     p->n_vitems = (int)vitems.size(); p->n_vblocks = (int)vblocks.size();
     PRC(own_upload(p, items, &p->d_items));
@@ -717,66 +879,6 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PRC(own_upload(p, act_slot, &p->d_act_slot));
     PRC(own_upload(p, act_off, &p->d_act_off));
     PRC(own_alloc(p, (void**)&p->d_part, sizeof(double) * BLK_VALS * (size_t)std::max(items.size(), vitems.size())));
-
-    // ---- block-sparse structure of J^T W J for the PCG solver: row blocks = (source, plane chunk),
-    //      every block feeds the row block of its a side and (off-diagonal blocks) of its b side
-    {
-      std::vector<int> uses(std::max(n_par, 1), 0);
-      bool unique = n_par > 0;
-      for (int sl : act_slot)
-        if (++uses[sl] > 1) unique = false;
-      for (int k = 0; k < n_par; ++k)
-        if (uses[k] == 0) unique = false;   // a free parameter no source depends on: singular block, leave it to the dense path
-      if (unique) {
-        std::vector<PcgRow> prows;
-        std::vector<std::vector<PcgEntry>> ents;
-        std::vector<int> row_of((size_t)n_src * (APB_MAX_ELEM / NB_MAX + 1), -1);
-        const int RPS = APB_MAX_ELEM / NB_MAX + 1;
-        for (size_t k = 0; k < blocks.size(); ++k) {
-          const BlockDesc& bd = blocks[k];
-          if (!bd.diag) continue;
-          row_of[(size_t)bd.a * RPS + bd.pa0 / NB_MAX] = (int)prows.size();
-          prows.push_back(PcgRow{bd.a, bd.pa0, bd.na, (int)k});
-          ents.emplace_back();
-        }
-        for (size_t k = 0; k < blocks.size(); ++k) {
-          const BlockDesc& bd = blocks[k];
-          const int ra = row_of[(size_t)bd.a * RPS + bd.pa0 / NB_MAX], rb = row_of[(size_t)bd.b * RPS + bd.pb0 / NB_MAX];
-          if (ra < 0 || rb < 0) { unique = false; break; }
-          ents[ra].push_back(PcgEntry{(int)k, 0, act_off[bd.b] + bd.pb0, bd.nb});
-          if (!bd.diag) ents[rb].push_back(PcgEntry{(int)k, 1, act_off[bd.a] + bd.pa0, bd.na});
-        }
-        if (unique) {
-          std::vector<PcgEntry> flat;
-          std::vector<PcgItem> pitems;
-          const int CH = 32;
-          for (size_t r = 0; r < prows.size(); ++r) {
-            const int e0 = (int)flat.size();
-            flat.insert(flat.end(), ents[r].begin(), ents[r].end());
-            const int e1 = (int)flat.size();
-            const bool multi = e1 - e0 > CH;
-            for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), multi ? (e == e0 ? 1 : 2) : 0});
-          }
-          p->n_prows = (int)prows.size(); p->n_pitems = (int)pitems.size();
-          PRC(own_upload(p, prows, &p->d_prows));
-          PRC(own_upload(p, flat, &p->d_pentries));
-          PRC(own_upload(p, pitems, &p->d_pitems));
-          PRC(own_alloc(p, (void**)&p->d_bvals, sizeof(double) * 64 * std::max<size_t>(blocks.size(), 1)));
-          PRC(own_alloc(p, (void**)&p->d_diagH, sizeof(double) * (size_t)n_par));
-          PRC(own_alloc(p, (void**)&p->d_pfac, sizeof(double) * 64 * std::max<size_t>(prows.size(), 1)));
-          PRC(own_alloc(p, (void**)&p->d_pvec, sizeof(double) * 5 * (size_t)n_par));
-          PCU(cudaMemset(p->d_bvals, 0, sizeof(double) * 64 * std::max<size_t>(blocks.size(), 1)));
-          int dev = 0, sms = 148, per_sm = 1;
-          PCU(cudaGetDevice(&dev));
-          PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-          PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
-          // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
-          const int want = std::max(1, std::min(sms * std::min(per_sm, 2), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
-          p->pcg_grid = want;
-          p->sparse_ok = true;
-        }
-      }
-    }
   }
 
   // ---- tables and arenas
@@ -1093,8 +1195,10 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
     if ((rc = sample_pass(p, x, as_rep, 1, 1, st))) return rc;
     if ((rc = assemble(p, 1, nullptr, p->d_resid, chi2, 1, st))) return rc;
   }
-  CU(cudaMemsetAsync(JtWJ, 0, sizeof(double) * (size_t)P * P, st));
+  if (!JtWJ && !p->sparse_ok) APB_FAIL("apb_normal_eq: JtWJ may only be NULL when the plan has a block-sparse form");
+  if (JtWJ) CU(cudaMemsetAsync(JtWJ, 0, sizeof(double) * (size_t)P * P, st));
   CU(cudaMemsetAsync(JtWr, 0, sizeof(double) * (size_t)P, st));
+  if (p->sparse_ok) CU(cudaMemsetAsync(p->d_bvals, 0, sizeof(double) * (64 * (size_t)p->n_cblocks + (size_t)P), st));
   if (p->n_items) {
     PB(K_BLOCKS);
     k_blocks<<<p->n_items, 256, 0, st>>>(p->d_src, p->d_img, p->d_items, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid,
@@ -1261,12 +1365,25 @@ extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, dou
   if (!p->sparse_ok) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = (size_t)p->n_par;
-  PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_act_slot, p->d_act_off,
+  PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_own_slot, p->d_own_off,
             p->d_bvals, p->d_diagH, p->d_pfac, g, h, p->d_pvec, p->d_pvec + P, p->d_pvec + 2 * P, p->d_pvec + 3 * P,
             info, p->n_par, max_iter > 0 ? max_iter : 2000, L, tol > 0.0 ? tol : 1e-14};
   void* args[] = {&A};
   CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(256), args, 0, st));
   g_launches++;
+  return 0;
+}
+
+extern "C" long long apb_plan_block_doubles(apb_plan_t* p) {
+  if (!p || !p->sparse_ok) return 0;
+  return 64 * p->n_cblocks + (long long)p->n_par;
+}
+
+extern "C" int apb_plan_bind_blocks(apb_plan_t* p, double* buf) {
+  if (!p) APB_FAIL("plan is NULL");
+  if (!p->sparse_ok) APB_FAIL("apb_plan_bind_blocks: the plan has no block-sparse form");
+  p->d_bvals = buf ? buf : p->d_bvals_own;
+  p->d_diagH = p->d_bvals + 64 * p->n_cblocks;
   return 0;
 }
 

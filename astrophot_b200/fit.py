@@ -26,7 +26,7 @@ import torch
 
 from . import AP_config
 from .errors import OptimizeStop
-from .lowering import lower, shard_scene
+from .lowering import lower, shard_scene, tile_scene
 
 __all__ = ["BaseOptimizer", "LM"]
 
@@ -105,6 +105,10 @@ class LM(BaseOptimizer):
             for im in scene.images:
                 im.weight = W[at : at + im.H * im.W].reshape(im.H, im.W)
                 at += im.H * im.W
+        # tiles=(ny, nx): cut every image into tiles (one big image sharded over the ranks);
+        # the tiles are then dealt to the ranks like the bands of a joint fit
+        if kwargs.get("tiles", None) is not None:
+            scene = tile_scene(scene, int(kwargs["tiles"][0]), int(kwargs["tiles"][1]))
         if self.distributed and kwargs.get("shard_images", True):
             scene = shard_scene(scene, torch.distributed.get_rank(self.group), torch.distributed.get_world_size(self.group))
         self.scene, self.info = scene, info
@@ -146,6 +150,14 @@ class LM(BaseOptimizer):
         self._hess_version, self._factor_key, self._factor = 0, None, None
         self._sparse_solver = bool(kwargs.get("sparse_solver", True))
         self._blocks_version = -1       # _hess_version whose blocks the plan holds (set by _step, not by natural-units builds)
+        # sharded fit of a large system: the ranks merge their normal equations as the block-sparse J^T W J
+        # (a few MB, same owner layout on every rank) instead of the dense P x P matrix
+        self._blk = None
+        self._hess_reduced = True
+        if self.distributed and self._sparse_solver and P > self._small_solver_max:
+            self._blk = self.plan.bind_blocks()
+            if self._blk is not None:
+                self._hs = torch.empty(P + 2, dtype=torch.float64, device=dev)
         self.pcg_iterations = []
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
@@ -192,8 +204,17 @@ class LM(BaseOptimizer):
             return lm_solve(self.hess, rhs, L)
         # large systems, no parameter shared between sources: block-sparse PCG on the <= 8x8 source-pair blocks the
         # normal-equation kernels produced (one cooperative launch); checked by its final relative residual
-        if self._sparse_solver and not self.distributed and self._blocks_version == self._hess_version:
-            res = self.plan.solve_sparse(rhs.contiguous(), L)
+        if self._sparse_solver and (not self.distributed or self._blk is not None) \
+                and self._blocks_version == self._hess_version:
+            if self.distributed:
+                # every rank solves the same merged system; rank 0's answer is the one all use (the split sky row of
+                # the PCG is summed with atomics, so the ranks' solutions may differ in the last bit)
+                res = self.plan.solve_sparse(rhs.contiguous(), L, out=self._hs[:P], info=self._hs[P:])
+                torch.distributed.broadcast(self._hs, src=torch.distributed.get_global_rank(self.group, 0)
+                                            if self.group is not None else 0, group=self.group)
+                res = (self._hs[:P].clone(), self._hs[P:])
+            else:
+                res = self.plan.solve_sparse(rhs.contiguous(), L)
             if res is None:
                 self._sparse_solver = False
             else:
@@ -202,6 +223,9 @@ class LM(BaseOptimizer):
                 self.pcg_iterations.append(int(its))
                 if rel <= 1e-10:
                     return h
+        if self.distributed and not self._hess_reduced:
+            self._allreduce(self._H)
+            self._hess_reduced = True
         # otherwise: same damped matrix (lm.py:359-371), library dense solver on the device.  The matrix is
         # symmetric positive definite for L > 0, so it is Cholesky-factored once per (H, L) and the factor serves
         # both solves of a lambda-trial (h and the geodesic correction); LU is the fallback.
@@ -244,7 +268,11 @@ class LM(BaseOptimizer):
         self.n_forward += 1
         self.n_jacobian += 1
         if self.distributed:
-            self._allreduce(self._H)
+            if self._blk is not None:
+                self._allreduce(self._blk)     # the dense copy stays local until a dense fallback asks for it
+                self._hess_reduced = False
+            else:
+                self._allreduce(self._H)
             self._allreduce(self._g)
         self.hess, self.grad = self._H, self._g
         self._hess_version += 1

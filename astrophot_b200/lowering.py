@@ -21,7 +21,7 @@ from .image import (Image_List, Jacobian_Image, Jacobian_Image_List, Model_Image
                     PSF_Image, Window, Window_List)
 from .param import Parameter_Node
 
-__all__ = ["lower", "shard_scene", "wrap_model_images", "wrap_jacobian_images", "LoweringInfo"]
+__all__ = ["lower", "shard_scene", "tile_scene", "wrap_model_images", "wrap_jacobian_images", "LoweringInfo"]
 
 
 class LoweringInfo:
@@ -312,4 +312,56 @@ def shard_scene(scene, rank, world):
             s2.image = remap[s.image]
             srcs.append(s2)
     return sc.Scene(images=[scene.images[i] for i in keep], sources=srcs, psfs=scene.psfs,
-                    transform=scene.transform, lo=scene.lo, hi=scene.hi, identities=scene.identities)
+                    transform=scene.transform, lo=scene.lo, hi=scene.hi, identities=scene.identities,
+                    owners=scene.owners)
+
+
+def tile_scene(scene, ny, nx):
+    """Cut every image of the scene into ``ny`` x ``nx`` tiles (one big image, as in a
+    crowded field or a mosaic, partitioned by image tile).  Every tile becomes an image of its own (a
+    view of data / weight / mask with the pixel origin moved), and a source is handed to every tile its
+    output window intersects with that window clipped to the tile; its working windows (``fwd``, ``jac``:
+    integration threshold, mean reference, curvature edge) are only translated, so the clipped source
+    computes the same pixel values as the whole one.  Each pixel is owned by exactly one tile:
+    chi^2, J^T W r and J^T W J of the tiles add up to those of the whole image, and ``shard_scene`` deals the
+    tiles to the ranks.  A source near a tile border is evaluated (PSF border included) by each tile it
+    touches -- redundant work instead of a halo exchange.  ``Scene.owners`` records the uncut models (the
+    block-sparse J^T W J is laid out on them, identically on every rank)."""
+    if ny * nx <= 1:
+        return scene
+    owners = [(s.image, tuple(s.out), [sl for sl in s.slot if sl >= 0]) for s in scene.sources]
+    images, sources, origin = [], [], []
+    first_tile = []
+    for im in scene.images:
+        first_tile.append(len(images))
+        ys = [round(k * im.H / ny) for k in range(ny + 1)]
+        xs = [round(k * im.W / nx) for k in range(nx + 1)]
+        for a in range(ny):
+            for b in range(nx):
+                y0, y1, x0, x1 = ys[a], ys[a + 1], xs[b], xs[b + 1]
+                if y1 <= y0 or x1 <= x0:
+                    continue
+                cut = lambda t: None if t is None else t[y0:y1, x0:x1].contiguous()
+                images.append(sc.SceneImage(H=y1 - y0, W=x1 - x0, S=np.array(im.S, dtype=np.float64).copy(),
+                                            rij=np.asarray(im.rij, dtype=np.float64) - np.array([x0, y0], dtype=np.float64),
+                                            rxy=np.array(im.rxy, dtype=np.float64).copy(),
+                                            data=cut(im.data), weight=cut(im.weight), mask=cut(im.mask)))
+                origin.append((x0, y0, x1 - x0, y1 - y0))
+    n_tiles_of = first_tile[1:] + [len(images)]
+    for k, s in enumerate(scene.sources):
+        for t in range(first_tile[s.image], n_tiles_of[s.image]):
+            tx, ty, tw, th = origin[t]
+            ox, oy, ow, oh = s.out
+            ix0, iy0 = max(ox, tx), max(oy, ty)
+            ix1, iy1 = min(ox + ow, tx + tw), min(oy + oh, ty + th)
+            if ix1 <= ix0 or iy1 <= iy0:
+                continue
+            s2 = sc.SceneSource(**{**s.__dict__})
+            s2.image = t
+            s2.owner = k
+            s2.out = (ix0 - tx, iy0 - ty, ix1 - ix0, iy1 - iy0)
+            s2.fwd = (s.fwd[0] - tx, s.fwd[1] - ty, s.fwd[2], s.fwd[3])
+            s2.jac = (s.jac[0] - tx, s.jac[1] - ty, s.jac[2], s.jac[3])
+            sources.append(s2)
+    return sc.Scene(images=images, sources=sources, psfs=scene.psfs, transform=scene.transform, lo=scene.lo,
+                    hi=scene.hi, identities=scene.identities, owners=owners)

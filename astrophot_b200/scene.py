@@ -85,6 +85,7 @@ class SceneSource:
     psf_shift: int = SHIFT_BILINEAR
     conv_mode: int = CONV_AUTO
     name: str = ""
+    owner: int = -1          # index into Scene.owners (the model this source is a tile-clipped piece of)
 
     @property
     def n_elem(self):
@@ -100,6 +101,9 @@ class Scene:
     lo: np.ndarray           # (P,) float64 (nan when absent)
     hi: np.ndarray           # (P,)
     identities: Optional[list] = None   # (P,) parameter identity strings (host only)
+    # models of the whole fit when the scene holds tile-clipped pieces (lowering.tile_scene):
+    # (uncut image index, (x0, y0, w, h) on it, [free parameter slots]) -- identical on every rank
+    owners: Optional[list] = None
 
     @property
     def n_par(self):

@@ -17,6 +17,11 @@ sub-pixel integration.  At N=1 that is exactly config[1].  `value` counts
 band-iterations per second (= LM iterations/s at N=1), weak scaling; the only
 collective is the all-reduce of J^T W J / J^T W r / chi^2 (P^2+P+2 doubles).
 
+Other workloads (`--workload`): `c3` = BASELINE config[2], the 4096^2 crowded field (at N GPUs the image is
+cut into N tiles, one per GPU: strong scaling, `value` = LM iterations/s of the one fit), `c3s` its 1024^2
+scale model, `c4` = config[3], the 8-band joint fit on 2048^2 per band (8 bands whatever N: strong scaling,
+8/N bands per GPU, `value` = LM iterations/s of the joint fit).
+
 `--impl reference` times the CPU oracle port of the reference algorithm
 (oracle/astrophot_oracle.py, numpy + scipy FFT convolution like the reference's
 default psf_convolve_mode) on the host cores, same config, one LM iteration
@@ -75,7 +80,34 @@ def build_joint(ap, n_bands, datas, size=SIZE):
                                      target=ap.image.Target_Image_List(tars), psf_mode="full")
 
 
-C3 = {"c3": (4096, 1000, 5000), "c3s": (1024, 62, 312)}     # size, Sersic sources, point sources
+C4_BANDS, C4_SIZE, C4_PSF = 8, 2048, 25
+
+
+def build_c4(ap, datas, size=C4_SIZE):
+    """BASELINE config[3]: 8 bands, shared centre / q / PA / n / Re, per-band Ie = 0.3 + 0.1 b,
+    per-band Gaussian PSF 25x25 with sigma = 1.2 + 0.1 b px, psf_mode full, Target_Image_List."""
+    tars, models = [], []
+    for b in range(C4_BANDS):
+        d = datas[b] if datas is not None else None
+        kw = {} if d is None else {"variance": d["variance"]}
+        psf_np = ap.utils.gaussian_psf(1.2 + 0.1 * b, C4_PSF, 1.0)
+        tars.append(ap.image.Target_Image(data=np.zeros((size, size)) if d is None else d["data"], pixelscale=1.0,
+                                          zeropoint=22.5, psf=ap.image.PSF_Image(data=psf_np, pixelscale=1.0), **kw))
+    for b in range(C4_BANDS):
+        pars = {"center": [size / 2 + 0.3, size / 2 - 0.4], "q": 0.6, "PA": 1.0, "n": 2.5, "Re": 60.0 * size / 1024,
+                "Ie": 0.3 + 0.1 * b}
+        m = ap.models.AstroPhot_Model(name=f"band{b}", model_type="sersic galaxy model", target=tars[b],
+                                      psf_mode="full", parameters=pars)
+        if b > 0:
+            for p in ("center", "q", "PA", "n", "Re"):
+                m[p].value = models[0][p]
+        models.append(m)
+    return ap.models.AstroPhot_Model(name="joint8", model_type="group model", models=models,
+                                     target=ap.image.Target_Image_List(tars), psf_mode="full")
+
+
+TILES = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}         # image tiles of the crowded field at N GPUs
+C3 = {"c3": (4096, 1000, 5000), "c3s": (1024, 62, 312), "c3t": (512, 15, 78)}     # size, Sersic sources, point sources (SURVEY.md §8d)
 
 
 def build_crowded(ap, workload, data=None):
@@ -113,16 +145,36 @@ def build_crowded(ap, workload, data=None):
 def build_workload(ap, workload, n_bands, datas):
     if workload == "c2":
         return build_joint(ap, n_bands, datas)
+    if workload == "c4":
+        return build_c4(ap, datas) if n_bands > 1 else build_c4_band(ap, datas)
     return build_crowded(ap, workload, None if datas is None else datas[0])
 
 
-def workload_text(workload, n_bands):
+def build_c4_band(ap, datas, b=0):
+    """One band of c4 on its own (truth images are sampled band by band)."""
+    d = datas[0] if datas is not None else None
+    kw = {} if d is None else {"variance": d["variance"]}
+    psf_np = ap.utils.gaussian_psf(1.2 + 0.1 * b, C4_PSF, 1.0)
+    tar = ap.image.Target_Image(data=np.zeros((C4_SIZE, C4_SIZE)) if d is None else d["data"], pixelscale=1.0,
+                                zeropoint=22.5, psf=ap.image.PSF_Image(data=psf_np, pixelscale=1.0), **kw)
+    pars = {"center": [C4_SIZE / 2 + 0.3, C4_SIZE / 2 - 0.4], "q": 0.6, "PA": 1.0, "n": 2.5, "Re": 60.0 * C4_SIZE / 1024,
+            "Ie": 0.3 + 0.1 * b}
+    return ap.models.AstroPhot_Model(name=f"band{b}", model_type="sersic galaxy model", target=tar, psf_mode="full",
+                                     parameters=pars)
+
+
+def workload_text(workload, n_bands, world=1):
+    if workload == "c4":
+        return (f"c4: {C4_BANDS}-band joint fit (shared centre/q/PA/n/Re, per-band Ie), PSF-convolved Sersic on "
+                f"{C4_SIZE}x{C4_SIZE} per band, {C4_PSF}x{C4_PSF} Gaussian PSF per band, threshold sub-pixel integration, "
+                f"LM fp64, {C4_BANDS // world} band(s) per GPU")
     if workload == "c2":
         return (f"c2 x {n_bands} band(s): PSF-convolved Sersic, {SIZE}x{SIZE} per band, {PSF_W}x{PSF_W} Moffat PSF, "
                 "threshold sub-pixel integration, LM fp64, joint fit sharded 1 band/GPU")
     size, n_gal, n_pt = C3[workload]
     return (f"{workload}: crowded field, {n_gal} PSF-convolved Sersic (128^2 windows) + {n_pt} point sources (53^2 windows) "
-            f"+ flat sky on {size}x{size}, {PSF_W}x{PSF_W} Moffat PSF, threshold sub-pixel integration, LM fp64")
+            f"+ flat sky on {size}x{size}, {PSF_W}x{PSF_W} Moffat PSF, threshold sub-pixel integration, LM fp64"
+            + (f", image cut into {TILES[world][0]}x{TILES[world][1]} tiles, one per GPU" if world > 1 else ""))
 
 
 def make_data(truth, seed):
@@ -137,7 +189,7 @@ def start_state(x_rep, seed=2, scale=0.05):
 
 
 def start_scale(workload):
-    return 0.05 if workload == "c2" else 0.02
+    return 0.05 if workload in ("c2", "c4") else 0.02
 
 
 # ---------------------------------------------------------------------------
@@ -220,8 +272,8 @@ def cpu_scene(workload="c2"):
     import astrophot_oracle as orc
     from astrophot_b200.lowering import lower
 
-    if workload == "c3":
-        workload = "c3s"
+    if workload in ("c3", "c3s"):
+        workload = "c3t"
     dev = ap.AP_config.ap_device
     ap.AP_config.ap_device = "cpu"
     try:
@@ -239,10 +291,15 @@ def cpu_scene(workload="c2"):
 
 
 def cpu_scale(workload):
-    """(factor, note): c3 is 16 x c3s in sources and pixels; the CPU cost per LM iteration is taken as
-    linear in that (it is super-linear for the dense J^T W J, so this flatters the CPU)."""
-    if workload == "c3":
-        return 1.0 / 16.0, " on the scale model c3s (1024^2, 62 Sersic + 312 points + sky, P = 1371), divided by 16 (linear extrapolation to c3: EXTRAPOLATED)"
+    """(factor, note): the crowded field is timed on its 512^2 scale model c3t (same source densities; c3 is
+    64 x, c3s 4 x c3t in sources and pixels) and the CPU cost per LM iteration is taken as linear in that (it
+    is super-linear for the dense J^T W J, so this flatters the CPU); c4 is timed on one of its 8 bands."""
+    if workload in ("c3", "c3s"):
+        k = 64 if workload == "c3" else 4
+        return 1.0 / k, (f" on the scale model c3t (512^2, 15 Sersic + 78 points + sky, P = 340), divided by {k} "
+                         f"(linear extrapolation to {workload}: EXTRAPOLATED)")
+    if workload == "c4":
+        return 1.0 / C4_BANDS, f" on ONE band of the {C4_BANDS}-band joint fit (2048^2, P = 7), divided by {C4_BANDS} (EXTRAPOLATED)"
     return 1.0, ""
 
 
@@ -256,18 +313,24 @@ def run_reference(args):
     torch.set_num_threads(cores)
     scene, x0 = cpu_scene(args.workload)
     fac, note = cpu_scale(args.workload)
-    times = []
-    for k in range(args.warmup + args.steps):
+    # every step is one full LM iteration of the port from the perturbed start (seconds each): the run is bounded
+    # by a time budget, so fewer than K steps may be timed (steps_timed says how many)
+    times, budget, t_start = [], float(os.environ.get("APB_REF_BUDGET_S", "150")), time.perf_counter()
+    n_warm = min(args.warmup, 1)
+    for k in range(n_warm + args.steps):
         dt, res = cpu_lm_iteration_seconds(scene, x0, 1)
-        if k >= args.warmup:
+        if k >= n_warm:
             times.append(dt)
+        if times and time.perf_counter() - t_start > budget:
+            break
     ms = 1e3 * float(np.mean(times)) / fac
     val = 1e3 / ms
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "steps_timed": len(times), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload, 1),
+        "config": {"workload": workload_text(args.workload, 1, 1),
                    "note": "CPU oracle port of the reference algorithm (numpy + scipy FFT conv); one LM iteration from the perturbed start per step" + note},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "1 full-size LM iteration (1 normal-equation build + lambda trials) per step" + note},
@@ -379,29 +442,43 @@ def run_ours(args):
     from astrophot_b200 import cabi
 
     ap.AP_config.ap_device = f"cuda:{local}"
-    n_bands = world
     dev = torch.device("cuda", local)
     wl = args.workload
-    if wl != "c2" and world > 1:
-        raise SystemExit("the crowded-field workloads run on one GPU (tile sharding of one image is not built yet)")
+    crowded = wl in C3
+    if crowded and world not in TILES:
+        raise SystemExit("the crowded field is cut into 1, 2, 4 or 8 tiles")
+    if wl == "c4" and C4_BANDS % world:
+        raise SystemExit("c4 has 8 bands: --gpus must divide 8")
+    # c2: one band per GPU (weak scaling); c4: 8 bands dealt to the GPUs; c3: one image cut into `world` tiles (strong)
+    n_bands = world if wl == "c2" else (C4_BANDS if wl == "c4" else 1)
+    scaling = "weak" if wl == "c2" else "strong"
+    units_per_step = n_bands if wl == "c2" else 1
 
-    # truth + noisy data for the band(s); every rank builds all bands' descriptions, data only for its own
-    truth_model = build_workload(ap, wl, 1, None)
+    # truth + noisy data; every rank builds all descriptions, data only for the bands it owns (the crowded field's
+    # one image is built whole on every rank and cut by LM(tiles=...))
     datas = []
-    for b in range(n_bands):
-        if b % world == rank:
-            if wl == "c2":
-                truth_model["Ie"].value = band_truth(b)["Ie"]
-            t = truth_model().data.cpu().numpy()
-            datas.append(make_data(t, 10 + b))
-        else:
-            datas.append(None)
-    del truth_model
+    if crowded:
+        t = build_workload(ap, wl, 1, None)().data.cpu().numpy()
+        datas.append(make_data(t, 10))
+    else:
+        truth_model = build_workload(ap, wl, 1, None) if wl == "c2" else None
+        for b in range(n_bands):
+            if b % world == rank:
+                if wl == "c2":
+                    truth_model["Ie"].value = band_truth(b)["Ie"]
+                    t = truth_model().data.cpu().numpy()
+                else:
+                    t = build_c4_band(ap, None, b)().data.cpu().numpy()
+                datas.append(make_data(t, 10 + b))
+            else:
+                datas.append(None)
+        del truth_model
+    torch.cuda.empty_cache()
     model = build_workload(ap, wl, n_bands, datas)
     x_true = model.parameters.vector_representation().numpy()
     x0 = start_state(x_true, scale=start_scale(wl))
     lm = ap.fit.LM(model, initial_state=x0, max_iter=10**6, relative_tolerance=0.0, distributed=(world > 1),
-                   conv=args.conv)
+                   conv=args.conv, tiles=(TILES[world] if crowded and world > 1 else None))
     plan = lm.plan
     n_pix_local = sum(h * w for h, w in plan.shapes)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
@@ -468,7 +545,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = n_bands * args.steps / (total_ms * 1e-3)
+    value = units_per_step * args.steps / (total_ms * 1e-3)
 
     # ---- the same K iterations again with every kernel launch bracketed by CUDA events on its stream
     #      (per-kernel durations for the roofline; kept out of `value` because the event records cost time)
@@ -491,8 +568,8 @@ def run_ours(args):
     st = plan.stats()
 
     # ---- e2e: every step streams the band's data + weight from pinned host memory and reads the result back
-    pin = {k: v.cpu().pin_memory() for k, v in plan.image_buffers[0].items()}
-    h2d = sum(v.numel() * 8 for v in pin.values())
+    pin = [{k: v.cpu().pin_memory() for k, v in bufs.items()} for bufs in plan.image_buffers]   # every local band / tile
+    h2d = sum(v.numel() * 8 for pb in pin for v in pb.values())
     out_pin = torch.empty(len(x0) + 1, dtype=torch.float64).pin_memory()
     reset()
     barrier()
@@ -502,8 +579,9 @@ def run_ours(args):
         flush.zero_()
         barrier()
         e0.record()
-        for name, buf in plan.image_buffers[0].items():
-            buf.copy_(pin[name], non_blocking=True)
+        for bufs, pb in zip(plan.image_buffers, pin):
+            for name, buf in bufs.items():
+                buf.copy_(pb[name], non_blocking=True)
         one_iteration()
         out_pin[:-1].copy_(lm.current_state, non_blocking=True)
         out_pin[-1] = lm.loss_history[-1]
@@ -516,7 +594,7 @@ def run_ours(args):
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_bands * args.steps / (float(t.item()) * 1e-3)
+    e2e_value = units_per_step * args.steps / (float(t.item()) * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -582,9 +660,9 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_text(wl, n_bands),
+        "config": {"workload": workload_text(wl, n_bands, world),
                    "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
                    "kernel_timing": "second pass of the same K iterations with CUDA events around every launch "
                                     f"({profiled_ms / args.steps:.3f} ms/step with the event records)",
@@ -596,7 +674,7 @@ def run_ours(args):
         "roofline": roof,
         "roofline_all": {k: {"bound": v["bound"], "frac": round(v["frac"], 4)} for k, v in roof_all.items()},
         "cpu_baseline": cpu,
-        "mpix_per_s_sampled": n_bands * forwards * (n_pix_local / 1e6) / (profiled_ms * 1e-3),
+        "mpix_per_s_sampled": world * forwards * (n_pix_local / 1e6) / (profiled_ms * 1e-3),
         "kernel_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])},
         "refine_queue_last": st["queued"], "peaks_now": {"dfma_tflops": dfma_tflops, "copy_gbs": copy_gbs},
     }
@@ -612,9 +690,9 @@ def main():
     ap_.add_argument("--steps", type=int, default=100)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap_.add_argument("--workload", default="c2", choices=["c2", "c3s", "c3"],
+    ap_.add_argument("--workload", default="c2", choices=["c2", "c3t", "c3s", "c3", "c4"],
                      help="c2 = BASELINE config[1] (default, the metric's configuration); c3 = config[2] crowded field, "
-                          "c3s = its 1024^2 scale model")
+                          "c3s / c3t = its 1024^2 / 512^2 scale models; c4 = config[3], 8-band joint fit on 2048^2")
     ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap_.add_argument("--conv", default=None, choices=["direct", "fft"],
                      help="force one PSF-convolution kernel family (default: automatic, FFT for the 51x51 PSF)")

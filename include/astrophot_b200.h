@@ -96,15 +96,32 @@ typedef struct {
   int32_t sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth;
   int32_t ref_mode, psf, psf_shift;
   int32_t conv_mode; /* APB_CONV_*: psf_convolve_mode (_model_methods.py:245-255) */
+  int32_t owner;     /* index into apb_opts_t.owners of the model this source is a piece of (an image
+                        cut into tiles hands every tile its clipped copy of the model); ignored when no
+                        owner table is given */
+  int32_t _pad;
   double tolerance, softening;
 } apb_source_t;
+
+/* One component model of the WHOLE fit, for fits whose pixels are split into tiles and / or over
+ * ranks: the pieces of a model (apb_source_t.owner) share its parameter slots, and
+ * the block-sparse form of J^T W J (apb_lm_solve_sparse) is laid out on the owners -- the same
+ * layout on every rank, so that the ranks' blocks add up with one sum all-reduce.  `image` and
+ * `out` are in the coordinates of the uncut images and only serve to find which owners overlap. */
+typedef struct {
+  int32_t image;
+  int32_t out[4];             /* x0 y0 w h of the model's window on the uncut image       */
+  int32_t n_slot;
+  int32_t slot[APB_MAX_ELEM]; /* its free parameters (indices into x), in element order   */
+} apb_owner_t;
 
 typedef struct {
   int64_t queue_capacity; /* entries per refinement level; 0 = automatic (grown by apb_plan_reserve) */
   int32_t flags;          /* bits 0-1: APB_CONV_* override for every source; bit 2: per-depth
                              refinement launches instead of the fused k_integrate; bit 3: pooled
                              (throughput) integration kernel whatever the queue length */
-  int32_t _pad;
+  int32_t n_owners;       /* 0: every source is its own owner */
+  const apb_owner_t *owners;
 } apb_opts_t;
 
 /* counters of the last call, for benchmarks (SURVEY.md §8d "SPE") */
@@ -170,6 +187,16 @@ int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, i
  * use apb_lm_solve or a dense library solver on the JtWJ of apb_normal_eq instead. */
 int apb_lm_solve_sparse(apb_plan_t *plan, const double *g, double L, double *h, double *info, double tol,
                         int max_iter, void *stream);
+
+/* The block-sparse J^T W J of the plan as one flat array: 64 doubles per block (row-major 8x8) followed
+ * by diag(J^T W J) (n_par doubles).  apb_plan_block_doubles returns its length (0: the plan has no
+ * block-sparse form, see apb_lm_solve_sparse).  apb_plan_bind_blocks makes apb_normal_eq write it into a
+ * caller-owned device buffer of that length instead of the plan's own, which is how a fit sharded by
+ * image tile merges the ranks' normal equations: sum all-reduce of that buffer and of JtWr, then every
+ * rank solves the same system (fit/lm.py:256-260 on the pixels of all ranks).  With blocks bound,
+ * apb_normal_eq accepts JtWJ == NULL (no dense copy). */
+long long apb_plan_block_doubles(apb_plan_t *plan);
+int apb_plan_bind_blocks(apb_plan_t *plan, double *buf);
 
 /* fit/lm.py:268-293, one pass of the lambda search with every tensor operation on the device:
  *   h = solve(L, g);  rpp = geodesic(x + d h, h, d);  a = -solve(L, rpp)/2 (zeros when L <= 1e-4);

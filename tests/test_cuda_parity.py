@@ -344,3 +344,120 @@ def test_unknown_modes_raise():
                                   parameters={"center": [8, 8], "q": 0.5, "PA": 0.1, "n": 1, "Re": 2, "Ie": 0})
     with pytest.raises(ap.errors.SpecificationConflict):
         m()
+
+
+# ---------------------------------------------------------------------------
+# one image cut into tiles: lowering.tile_scene, owner-level block-sparse J^T W J
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,tiles", [("crowded", (2, 2)), ("crowded", (3, 2)), ("group", (1, 2)), ("group_nosky", (2, 1))])
+def test_tiled_plan_equals_whole_image(name, tiles):
+    from astrophot_b200.lowering import tile_scene
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    tiled = tile_scene(scene, *tiles)
+    whole, cut = _plan(scene), _plan(tiled)
+    x0 = fix["x0"]
+    H0, g0, c0 = [t.cpu().numpy() for t in whole.normal_eq(x0, check=True)]
+    H1, g1, c1 = [t.cpu().numpy() for t in cut.normal_eq(x0, check=True)]
+    d = np.sqrt(np.diag(fix["hess0"]))
+    assert np.max(np.abs(H1 - fix["hess0"]) / np.outer(d, d)) < 1e-9
+    assert np.max(np.abs(H1 - H0) / np.outer(d, d)) < 1e-12
+    assert np.max(np.abs(g1 - g0)) / np.abs(g0).max() < 1e-11
+    assert abs(c1[0] - c0[0]) / c0[0] < 1e-12
+    # model image: the tiles stitched together
+    img0 = whole.sample(x0, as_rep=True)[0].cpu().numpy()
+    parts = [t.cpu().numpy() for t in cut.sample(x0, as_rep=True)]
+    ny, nx = tiles
+    ys = [round(k * img0.shape[0] / ny) for k in range(ny + 1)]
+    xs = [round(k * img0.shape[1] / nx) for k in range(nx + 1)]
+    for a in range(ny):
+        for b in range(nx):
+            assert rel_err(parts[a * nx + b], img0[ys[a]:ys[a + 1], xs[b]:xs[b + 1]]) < 1e-12
+    # the pieces of a model share its parameters; the sparse matrix is laid out on the owners and still solves
+    rng = np.random.default_rng(11)
+    for L in (1e-3, 1.0):
+        for rhs in (g1, rng.normal(size=len(g1))):
+            res = cut.solve_sparse(torch.as_tensor(rhs, device="cuda"), L)
+            assert res is not None
+            h, info = res
+            its, rel = info.tolist()
+            want = orc.lm_solve(H1, rhs, L)
+            assert rel <= 1e-12 and its < 1000
+            np.testing.assert_allclose(h.cpu().numpy(), want, rtol=1e-8, atol=1e-11 * np.abs(want).max())
+    # caller-owned block array (what a tile-sharded fit all-reduces), no dense copy
+    blk = cut.bind_blocks()
+    assert blk is not None and blk.numel() > len(g1)
+    _, g2, _ = cut.normal_eq(x0, out=(None, torch.empty_like(torch.as_tensor(g1, device="cuda")), torch.empty(2, dtype=torch.float64, device="cuda")))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(blk[-len(g1):].cpu().numpy(), np.diag(H1), rtol=1e-12)
+    h, info = cut.solve_sparse(g2, 1.0)
+    np.testing.assert_allclose(h.cpu().numpy(), orc.lm_solve(H1, g1, 1.0), rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("small", [159, 0])
+def test_lm_tiled_fit_matches_reference(small):
+    """LM(tiles=(2, 2)) on one GPU: same LM history as the reference's fit of the whole image, through the fused
+    trial (P = 99) and through the owner-level block-sparse PCG (small_solver_max=0)."""
+    fix = load_golden("crowded")
+    m, _ = scenes.build(ap, "crowded", data=golden_data(fix))
+    r = ap.fit.LM(m, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, tiles=(2, 2),
+                  small_solver_max=small).fit()
+    assert len(r.plan.shapes) == 4
+    if small == 0:
+        assert r._factor is None and len(r.pcg_iterations) > 0
+    ref_loss = fix["loss_history"]
+    n = min(len(ref_loss), len(r.loss_history))
+    moving = 1
+    while moving < n and abs(ref_loss[moving] - ref_loss[moving - 1]) / ref_loss[moving] > 1e-12:
+        moving += 1
+    assert moving >= 3
+    np.testing.assert_allclose(r.loss_history[:moving], ref_loss[:moving], rtol=1e-8)
+    np.testing.assert_allclose(r.L_history[:moving], fix["L_history"][:moving], rtol=1e-12)
+    for k in range(moving):
+        np.testing.assert_allclose(r.lambda_history[k], fix["lambda_history"][k], rtol=1e-8, atol=1e-8)
+
+
+def _nccl_tile_worker(rank, world, port, out_dir, small):
+    import os, sys
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ap.AP_config.ap_device = f"cuda:{rank}"
+    fix = load_golden("crowded")
+    m, _ = scenes.build(ap, "crowded", data=golden_data(fix))
+    r = ap.fit.LM(m, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, tiles=(2, 2), distributed=True,
+                  small_solver_max=small).fit()
+    assert len(r.plan.shapes) == 4 // world
+    if small == 0:
+        assert r._blk is not None and len(r.pcg_iterations) > 0 and r._factor is None
+    if rank == 0:
+        np.savez(os.path.join(out_dir, f"lm_{small}.npz"), loss=np.array(r.loss_history), L=np.array(r.L_history),
+                 lam=np.array(r.lambda_history))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("small", [159, 0])
+def test_lm_tile_sharded_over_two_gpus(tmp_path, small):
+    """Tiles dealt to 2 ranks over NCCL: dense all-reduce of J^T W J (fused two-halves trial) and the block-array
+    all-reduce + replicated PCG; both against the reference's LM history."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000) + (1 if small else 0)
+    mp.spawn(_nccl_tile_worker, args=(2, port, str(tmp_path), small), nprocs=2, join=True)
+    got = np.load(tmp_path / f"lm_{small}.npz")
+    fix = load_golden("crowded")
+    ref_loss = fix["loss_history"]
+    n = min(len(ref_loss), len(got["loss"]))
+    moving = 1
+    while moving < n and abs(ref_loss[moving] - ref_loss[moving - 1]) / ref_loss[moving] > 1e-12:
+        moving += 1
+    assert moving >= 3
+    np.testing.assert_allclose(got["loss"][:moving], ref_loss[:moving], rtol=1e-8)
+    np.testing.assert_allclose(got["L"][:moving], fix["L_history"][:moving], rtol=1e-12)
+    np.testing.assert_allclose(got["lam"][:moving], fix["lambda_history"][:moving], rtol=1e-8, atol=1e-8)

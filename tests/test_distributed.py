@@ -62,3 +62,82 @@ def test_band_sharded_normal_equations_allreduce(tmp_path):
     assert np.max(np.abs(g - fix["grad0"])) / np.abs(fix["grad0"]).max() < 1e-9
     assert npix == 3 * 48 * 48
     assert abs(chi2 / (npix - P) - fix["loss_history"][0]) / fix["loss_history"][0] < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# tile sharding of ONE image: lowering.tile_scene
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,tiles", [("crowded", (2, 2)), ("crowded", (2, 3)), ("group", (1, 2)), ("group_nosky", (2, 1))])
+def test_tiles_reproduce_the_whole_image(name, tiles):
+    """Pixels owned once, sources handed to every tile they touch: model image, J^T W J, J^T W r and
+    chi^2 of the tiles stitch / add up to those of the whole image and to the reference's golden."""
+    import astrophot_b200 as ap
+    import astrophot_oracle as orc
+    import scenes
+    from astrophot_b200.lowering import lower, tile_scene
+
+    ap.AP_config.ap_device = "cpu"
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    tiled = tile_scene(scene, *tiles)
+    assert len(tiled.images) == tiles[0] * tiles[1] * len(scene.images)
+    assert sum(im.H * im.W for im in tiled.images) == sum(im.H * im.W for im in scene.images)
+    x0 = fix["x0"]
+    whole = orc.sample(scene, x0)[0]
+    parts = orc.sample(tiled, x0)
+    ny, nx = tiles
+    H0, W0 = scene.images[0].H, scene.images[0].W
+    ys = [round(k * H0 / ny) for k in range(ny + 1)]
+    xs = [round(k * W0 / nx) for k in range(nx + 1)]
+    stitched = np.zeros_like(whole)
+    for a in range(ny):
+        for b in range(nx):
+            stitched[ys[a]:ys[a + 1], xs[b]:xs[b + 1]] = parts[a * nx + b]
+    assert np.max(np.abs(stitched - whole)) <= 1e-13 * np.max(np.abs(whole))
+    H, g, chi2, _ = orc.normal_eq(tiled, x0)
+    d = np.sqrt(np.diag(fix["hess0"]))
+    assert np.max(np.abs(H - fix["hess0"]) / np.outer(d, d)) < 1e-9
+    assert np.max(np.abs(g - fix["grad0"])) / np.abs(fix["grad0"]).max() < 1e-9
+
+
+def _tile_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import astrophot_b200 as ap
+    import astrophot_oracle as orc
+    import scenes
+    from astrophot_b200.lowering import lower, shard_scene, tile_scene
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ap.AP_config.ap_device = "cpu"
+    fix = load_golden("crowded")
+    model, _ = scenes.build(ap, "crowded", data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    local = shard_scene(tile_scene(scene, 2, 2), rank, world)
+    assert len(local.images) == 2 and local.n_par == scene.n_par
+    H, g, chi2, _ = orc.normal_eq(local, fix["x0"])
+    buf = torch.cat([torch.as_tensor(H).reshape(-1), torch.as_tensor(g), torch.tensor([chi2])])
+    dist.all_reduce(buf)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "reduced_tiles.npy"), buf.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tile_sharded_normal_equations_allreduce(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_tile_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    red = np.load(tmp_path / "reduced_tiles.npy")
+    fix = load_golden("crowded")
+    P = len(fix["x0"])
+    H, g, chi2 = red[: P * P].reshape(P, P), red[P * P : P * P + P], red[P * P + P]
+    d = np.sqrt(np.diag(fix["hess0"]))
+    assert np.max(np.abs(H - fix["hess0"]) / np.outer(d, d)) < 1e-9
+    assert np.max(np.abs(g - fix["grad0"])) / np.abs(fix["grad0"]).max() < 1e-9
+    npix = 192 * 192
+    assert abs(chi2 / (npix - P) - fix["loss_history"][0]) / fix["loss_history"][0] < 1e-10
