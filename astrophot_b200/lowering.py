@@ -159,26 +159,11 @@ def lower(model, window=None, for_fit=False):
             n += 1
     info.identities = list(model.parameters.vector_identities())
 
-    # ---- sources
     psfs, psf_index = [], {}
-    sources = []
-    for comp in _components(model):
-        if not isinstance(comp, Component_Model) or comp._kind is None:
-            raise SpecificationConflict(
-                f"model type '{comp.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §2)")
+
+    def build_source(comp, ii, region, out, fwd, jac):
         if comp.mask is not None:
             raise SpecificationConflict("per-model masks are not supported by astrophot_b200 yet")
-        ii = ident_to_img.get(comp.target.identity)
-        if ii is None:
-            raise SpecificationConflict(f"{comp.name}: target not part of the evaluated model's target")
-        region = info.windows[ii]
-        cwin = comp.window
-        out = _rect(region, cwin)
-        if out[2] <= 0 or out[3] <= 0:
-            continue
-        jac = out
-        fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
-
         # elements
         names = list(sc.ELEMS[comp._kind])
         nodes = []
@@ -254,29 +239,75 @@ def lower(model, window=None, for_fit=False):
             psf = comp.psf
             if psf is None:
                 raise SpecificationConflict(f"{comp.name}: psf_mode='full' but no PSF on model or target")
-            if not isinstance(psf, PSF_Image):
-                raise SpecificationConflict(
-                    "PSF *models* as auxiliary PSFs are not lowered yet; sample the PSF model once and pass the PSF_Image")
-            up = int(np.round(float(region.pixel_length) / float(psf.window.pixel_length)))
+            pwin = psf.window if isinstance(psf, PSF_Image) else psf.target.window
+            up = int(np.round(float(region.pixel_length) / float(pwin.pixel_length)))
             if up != 1:
                 raise SpecificationConflict("super-sampled PSFs (psf_upscale > 1) are not implemented yet (SURVEY.md §8f)")
             if id(psf) not in psf_index:
-                psf_index[id(psf)] = len(psfs)
-                psfs.append(sc.ScenePSF(data=psf.data.contiguous()))
+                if isinstance(psf, PSF_Image):
+                    psfs.append(sc.ScenePSF(data=psf.data.contiguous()))
+                else:
+                    if comp._kind == sc.KIND_POINT:
+                        raise SpecificationConflict(
+                            "point sources with a PSF *model* (point_source.py:122-140) are not lowered yet; "
+                            "sample the PSF model once and pass the PSF_Image")
+                    psrc, shape = aux_psf_source(psf)
+                    psfs.append(sc.ScenePSF(data=None, source=psrc, shape=shape))
+                psf_index[id(psf)] = len(psfs) - 1
             pidx = psf_index[id(psf)]
         flags = comp._flags
         if isinstance(comp, PSF_Model) and comp.normalize_psf:
             flags |= sc.FLAG_NORMALIZE
-        sources.append(sc.SceneSource(
+        return sc.SceneSource(
             kind=comp._kind, image=ii, out=out, fwd=fwd, jac=jac, slot=slot, cval=cval, flags=flags, prof=prof,
             sampling_mode=smode, quad_init=quad_init, integrate_mode=imode,
             quad_level=int(comp.integrate_quad_level), gridding=int(comp.integrate_gridding),
             max_depth=int(comp.integrate_max_depth), tolerance=float(comp.sampling_tolerance),
             softening=float(comp.softening), ref_mode=comp._ref_mode, psf=pidx,
             psf_shift=_shift_code(comp.psf_subpixel_shift),
-            conv_mode=sc.CONV_DIRECT if comp.psf_convolve_mode == "direct" else sc.CONV_AUTO, name=comp.name))
+            conv_mode=sc.CONV_DIRECT if comp.psf_convolve_mode == "direct" else sc.CONV_AUTO, name=comp.name)
+
+    # ---- sources
+    sources = []
+    aux_images = []          # grids of auxiliary PSF models (PSF_Image targets), appended after the target images
+    n_real = len(images)
+
+    def aux_psf_source(pm):
+        """PSF *model* used as the PSF of a host model (model_object.py:133-147): it is sampled on its own
+        PSF_Image grid on every pass (model_object.py:307-310), like a stand-alone PSF model, and its free
+        parameters are parameters of the host."""
+        if not isinstance(pm, PSF_Model) or getattr(pm, "_kind", None) is None:
+            raise SpecificationConflict(
+                f"auxiliary PSF model type '{pm.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §8f)")
+        w = pm.window
+        ii = n_real + len(aux_images)
+        aux_images.append(sc.SceneImage(H=int(w._shape[1]), W=int(w._shape[0]), S=w._S.copy(), rij=w._rij.copy(),
+                                        rxy=w._rxy.copy(), aux=True))
+        rect = (0, 0, int(w._shape[0]), int(w._shape[1]))
+        src = build_source(pm, ii, w, rect, rect, rect)
+        sources.append(src)
+        info.components.append(pm)
+        return len(sources) - 1, (int(w._shape[1]), int(w._shape[0]))
+
+    for comp in _components(model):
+        if not isinstance(comp, Component_Model) or comp._kind is None:
+            raise SpecificationConflict(
+                f"model type '{comp.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §2)")
+        ii = ident_to_img.get(comp.target.identity)
+        if ii is None:
+            raise SpecificationConflict(f"{comp.name}: target not part of the evaluated model's target")
+        region = info.windows[ii]
+        cwin = comp.window
+        out = _rect(region, cwin)
+        if out[2] <= 0 or out[3] <= 0:
+            continue
+        jac = out
+        fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
+        src = build_source(comp, ii, region, out, fwd, jac)
+        sources.append(src)
         info.components.append(comp)
 
+    images = images + aux_images
     scene = sc.Scene(images=images, sources=sources, psfs=psfs,
                      transform=np.array(transform, dtype=np.int32),
                      lo=np.array(lo, dtype=np.float64), hi=np.array(hi, dtype=np.float64),

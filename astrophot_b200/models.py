@@ -316,12 +316,14 @@ class Component_Model(AstroPhot_Model):
     def __init__(self, *, name=None, **kwargs):
         self._psf = None
         super().__init__(name=name, **kwargs)
+        # as in the reference (core_model.py:128-134 sets user attributes before the model's own parameters exist):
+        # the parameters of an auxiliary PSF model come first in the parameter vector
+        if "psf" in kwargs:
+            self.psf = kwargs["psf"]
         self.parameter_specs = self.build_parameter_specs(kwargs.get("parameters", None))
         self.build_parameters()
         if isinstance(kwargs.get("parameters", None), torch.Tensor):
             self.parameters.value = kwargs["parameters"]
-        if "psf" in kwargs:
-            self.psf = kwargs["psf"]
 
     @property
     def psf(self):

@@ -54,11 +54,16 @@ class SceneImage:
     data: object = None      # (H,W) tensor/array or None
     weight: object = None    # (H,W) or None (= ones)
     mask: object = None      # (H,W) bool/uint8, True = ignore; or None
+    aux: bool = False        # grid of an auxiliary PSF model (a PSF_Image): sampled, never an output or a chi^2 term;
+                             # aux images come after the target images
 
 
 @dataclass
 class ScenePSF:
-    data: object             # (h,w) odd-shaped stamp, un-normalised
+    data: object             # (h,w) odd-shaped stamp, un-normalised; None when produced by a source
+    source: int = -1         # index of the PSF-model source (on an aux image) that produces the stamp on every
+                             # sampling pass (model_object.py:133-147,307-310), or -1
+    shape: tuple = None      # (h, w) when data is None
 
 
 @dataclass

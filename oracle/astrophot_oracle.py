@@ -358,6 +358,27 @@ def normalized_shifted_psf(psf, shift, method, keep_pad, want_grad):
     return out, dout
 
 
+def shifted_psf_param_derivative(psf, dpsf, shift, method, keep_pad):
+    """d/d theta of the shifted, normalised stamp when the PSF itself depends on theta (auxiliary PSF
+    model): the shift is linear in the PSF, so  d P = S(dpsf)/T - S(psf) sum(S(dpsf))/T^2,  T = sum S(psf)."""
+    if method == sc.SHIFT_NONE or shift is None:
+        st, dst = np.asarray(psf, dtype=np.float64), np.asarray(dpsf, dtype=np.float64)
+    else:
+        st, _ = shift_psf_bilinear(psf, shift, keep_pad, False)
+        dst, _ = shift_psf_bilinear(dpsf, shift, keep_pad, False)
+    tot = st.sum()
+    return dst / tot - st * (dst.sum() / tot**2)
+
+
+def aux_psf(scene, ps, vals, mode, want_grad):
+    """Stamp of an auxiliary PSF model (model_object.py:307-310: ``psf = self.psf(parameters=...)``), sampled
+    on its own grid like any PSF model (psf_model_object.py:180-264), with its derivatives (natural units)."""
+    psrc = scene.sources[ps.source]
+    el = source_elements(psrc, vals)
+    r = sample_source(scene, ps.source, el, mode, want_grad)
+    return psrc, r
+
+
 def conv_same(img, ker):
     """Linear 'same' convolution, direct sum (what the reference's FFT /
     conv2d paths compute up to rounding, _model_methods.py:245-255)."""
@@ -402,12 +423,13 @@ class SourceResult:
     """Output-window stamps of one source: value (oh, ow) and derivatives
     (n_elem, oh, ow) in natural units (None when not requested)."""
 
-    def __init__(self, value, grad):
+    def __init__(self, value, grad, extra=None):
         self.value = value
         self.grad = grad
+        self.extra = extra or []   # [(slot, plane)]: derivatives wrt parameters of an auxiliary PSF model (natural units)
 
 
-def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None):
+def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, vals=None):
     """One component model on its output window.
 
     mode: "fwd" (working window = group window; group_model_object.py:211-227
@@ -433,8 +455,14 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None):
 
     has_psf = src.psf >= 0
     bx = by = 0
+    psf_src = psf_res = None
     if has_psf:
-        psf = _host(scene.psfs[src.psf].data)
+        ps = scene.psfs[src.psf]
+        if getattr(ps, "source", -1) >= 0:
+            psf_src, psf_res = aux_psf(scene, ps, vals, mode, want_grad)
+            psf = psf_res.value
+        else:
+            psf = _host(ps.data)
         bx, by = _psf_border(psf)
     # evaluation region: output window + psf border; working region likewise
     ex0, ey0, ew, eh = ox - bx, oy - by, ow + 2 * bx, oh + 2 * by
@@ -565,7 +593,13 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None):
             gsy = cfn(deep_e, dP[1])[crop]
             grad[0] = Sinv[0, 0] * gsx + Sinv[1, 0] * gsy
             grad[1] = Sinv[0, 1] * gsx + Sinv[1, 1] * gsy
-    return SourceResult(val, grad)
+    extra = []
+    if want_grad and psf_src is not None:
+        for e, sl in enumerate(psf_src.slot):
+            if sl >= 0:
+                dPe = shifted_psf_param_derivative(psf, psf_res.grad[e], shift, src.psf_shift, True)
+                extra.append((sl, cfn(deep_e, dPe)[crop]))
+    return SourceResult(val, grad, extra)
 
 
 def _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh):
@@ -634,10 +668,12 @@ def _values(scene, x, as_rep):
 def sample(scene, x, as_rep=True, mode="fwd", conv="direct", stats=None):
     """Model image per scene image: sum of all sources (group_model_object.py:183-231)."""
     vals, _ = _values(scene, x, as_rep)
-    out = [np.zeros((im.H, im.W)) for im in scene.images]
+    out = [np.zeros((im.H, im.W)) for im in scene.images if not getattr(im, "aux", False)]
     for si, src in enumerate(scene.sources):
+        if getattr(scene.images[src.image], "aux", False):
+            continue        # auxiliary PSF model: sampled by the sources that use it
         el = source_elements(src, vals)
-        r = sample_source(scene, si, el, mode, False, conv, stats)
+        r = sample_source(scene, si, el, mode, False, conv, stats, vals=vals)
         ox, oy, ow, oh = src.out
         out[src.image][oy : oy + oh, ox : ox + ow] += r.value
     return out
@@ -648,26 +684,32 @@ def jacobian(scene, x, as_rep=True, conv="direct", stats=None):
     Only for small scenes."""
     vals, dv = _values(scene, x, as_rep)
     P = scene.n_par
-    out = [np.zeros((im.H, im.W, P)) for im in scene.images]
+    out = [np.zeros((im.H, im.W, P)) for im in scene.images if not getattr(im, "aux", False)]
     for si, src in enumerate(scene.sources):
-        if all(s < 0 for s in src.slot):
+        if getattr(scene.images[src.image], "aux", False):
+            continue
+        aux = src.psf >= 0 and getattr(scene.psfs[src.psf], "source", -1) >= 0
+        if all(s < 0 for s in src.slot) and not aux:
             continue
         el = source_elements(src, vals)
-        r = sample_source(scene, si, el, "jac", True, conv, stats)
+        r = sample_source(scene, si, el, "jac", True, conv, stats, vals=vals)
         ox, oy, ow, oh = src.out
         for e, s in enumerate(src.slot):
             if s >= 0:
                 out[src.image][oy : oy + oh, ox : ox + ow, s] += r.grad[e] * dv[s]
+        for s, plane in r.extra:
+            out[src.image][oy : oy + oh, ox : ox + ow, s] += plane * dv[s]
     return out
 
 
 def flat_targets(scene):
     """Y, W, keep-mask as flat vectors over all images (lm.py:191-222)."""
-    Y = np.concatenate([_host(im.data).reshape(-1) for im in scene.images])
+    ims = [im for im in scene.images if not getattr(im, "aux", False)]
+    Y = np.concatenate([_host(im.data).reshape(-1) for im in ims])
     W = np.concatenate([(np.ones(im.H * im.W) if im.weight is None else _host(im.weight).reshape(-1))
-                        for im in scene.images])
+                        for im in ims])
     keep = np.concatenate([(np.ones(im.H * im.W, dtype=bool) if im.mask is None else ~_host(im.mask, bool).reshape(-1))
-                           for im in scene.images])
+                           for im in ims])
     return Y, W, keep
 
 

@@ -92,6 +92,20 @@ def build(ap, name, data=None):
               psf_subpixel_shift="bilinear" if name == "psf_sersic" else "none",
               parameters={"center": [30.8, 33.3], "q": 0.55, "PA": 2.4, "n": 2.5, "Re": 6.0, "Ie": 1.0})
         return m, {}
+    if name in ("aux_psf_moffat", "aux_psf_gauss_noshift"):
+        # PSF *model* as the auxiliary PSF of a galaxy model: its parameters are fitted with the galaxy's
+        # (model_object.py:133-147,307-310; BASELINE config[1] variant B)
+        if name == "aux_psf_moffat":
+            ptar = ap.image.PSF_Image(data=np.zeros((13, 13)), pixelscale=1.0)
+            pm = M(name="auxm", model_type="moffat psf model", target=ptar, parameters={"n": 2.5, "Rd": 2.2})
+        else:
+            ptar = ap.image.PSF_Image(data=np.zeros((11, 11)), pixelscale=1.0)
+            pm = M(name="auxg", model_type="gaussian psf model", target=ptar, parameters={"sigma": 1.4})
+        tar = _target(ap, (60, 64), data)
+        m = M(name=name, model_type="sersic galaxy model", target=tar, psf_mode="full", psf=pm,
+              psf_subpixel_shift="bilinear" if name == "aux_psf_moffat" else "none",
+              parameters={"center": [31.7, 28.4], "q": 0.6, "PA": 0.8, "n": 2.2, "Re": 6.5, "Ie": 0.9})
+        return m, {}
     if name == "point":
         psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 15), pixelscale=1.0)
         tar = _target(ap, (40, 44), data, psf=psf)
@@ -188,9 +202,10 @@ def build(ap, name, data=None):
 
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
-                 "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded"]
+                 "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
+                 "aux_psf_gauss_noshift"]
 # scenes with an LM golden (noise seed, start perturbation)
-LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9}
+LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12}
 
 
 def make_data(truth_images, seed):
