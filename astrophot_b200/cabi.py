@@ -27,11 +27,12 @@ class apb_param_t(C.Structure):
 
 class apb_image_t(C.Structure):
     _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("S", C.c_double * 4), ("rij", C.c_double * 2),
-                ("rxy", C.c_double * 2), ("data", C.c_void_p), ("weight", C.c_void_p), ("mask", C.c_void_p)]
+                ("rxy", C.c_double * 2), ("data", C.c_void_p), ("weight", C.c_void_p), ("mask", C.c_void_p),
+                ("flags", C.c_int32), ("_pad", C.c_int32)]
 
 
 class apb_psf_t(C.Structure):
-    _fields_ = [("h", C.c_int32), ("w", C.c_int32), ("data", C.c_void_p)]
+    _fields_ = [("h", C.c_int32), ("w", C.c_int32), ("data", C.c_void_p), ("source", C.c_int32), ("_pad", C.c_int32)]
 
 
 class apb_source_t(C.Structure):
@@ -161,13 +162,17 @@ class Plan:
         self._masks = {}
         n_img, n_src, n_psf = len(scene.images), len(scene.sources), len(scene.psfs)
         imgs = (apb_image_t * max(n_img, 1))()
-        self.shapes = []
+        self.shapes = []          # target images only (grids of auxiliary PSF models are no outputs)
+        self._aux = []
         self.image_buffers = []   # per image: device tensors the plan reads (refill in place to stream new data)
         for i, im in enumerate(scene.images):
             imgs[i].H, imgs[i].W = im.H, im.W
             imgs[i].S[:] = [float(v) for v in np.asarray(im.S).reshape(4)]
             imgs[i].rij[:] = [float(v) for v in im.rij]
             imgs[i].rxy[:] = [float(v) for v in im.rxy]
+            aux = bool(getattr(im, "aux", False))
+            imgs[i].flags = 1 if aux else 0
+            self._aux.append(aux)
             bufs = {}
             for name in ("data", "weight"):
                 arr = getattr(im, name)
@@ -183,14 +188,19 @@ class Plan:
                 self._keep.append(m)
                 imgs[i].mask = m.data_ptr()
                 self._masks[i] = m
-            self.shapes.append((im.H, im.W))
+            if not aux:
+                self.shapes.append((im.H, im.W))
         psfs = (apb_psf_t * max(n_psf, 1))()
         self._psfs = []
         for i, ps in enumerate(scene.psfs):
+            if getattr(ps, "source", -1) >= 0:      # stamp produced by a PSF-model source on every pass
+                self._psfs.append(None)
+                psfs[i].h, psfs[i].w, psfs[i].data, psfs[i].source = int(ps.shape[0]), int(ps.shape[1]), None, int(ps.source)
+                continue
             t = share._psfs[i] if share is not None else _dev_f64(ps.data)
             self._keep.append(t)
             self._psfs.append(t)
-            psfs[i].h, psfs[i].w, psfs[i].data = t.shape[0], t.shape[1], t.data_ptr()
+            psfs[i].h, psfs[i].w, psfs[i].data, psfs[i].source = t.shape[0], t.shape[1], t.data_ptr(), -1
         pars = (apb_param_t * max(self.n_par, 1))()
         for k in range(self.n_par):
             pars[k].transform = int(scene.transform[k])
@@ -250,9 +260,11 @@ class Plan:
         return t
 
     def _ptrs(self, tensors):
-        arr = (C.c_void_p * len(tensors))()
-        for i, t in enumerate(tensors):
-            arr[i] = t.data_ptr()
+        """Pointer per plan image: the target images' output tensors in order, NULL for aux images."""
+        arr = (C.c_void_p * max(len(self._aux), 1))()
+        it = iter(tensors)
+        for i, aux in enumerate(self._aux):
+            arr[i] = None if aux else next(it).data_ptr()
         return arr
 
     # -- refinement-queue capacity ------------------------------------------------

@@ -128,6 +128,7 @@ struct apb_plan {
   double* d_part = nullptr;
   // block-sparse PCG solver (apb_solve.cuh): usable when no parameter is shared between sources
   bool sparse_ok = false;
+  bool any_aux_psf = false;   // PSF stamps depend on a PSF-model source sampled in the same pass
   PcgRow* d_prows = nullptr; int n_prows = 0;
   PcgEntry* d_pentries = nullptr;
   PcgItem* d_pitems = nullptr; int n_pitems = 0;
@@ -170,7 +171,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 extern "C" const char* apb_last_error(void) { return g_err.c_str(); }
 static int fft_len(int n);
 extern "C" int apb_fft_length(int n) { return n > 0 ? fft_len(n) : 0; }
-extern "C" int apb_version(void) { return 101; }
+extern "C" int apb_version(void) { return 102; }
 
 static void gauss_legendre(int n, double* x, double* w) {
   // Newton iteration on P_n (same nodes as scipy.special.roots_legendre to rounding)
@@ -371,6 +372,18 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     opts = &opts_env;
   }
   const int conv_force = opts ? (opts->flags & 3) : 0;   // 1: direct everywhere, 2: FFT everywhere
+  auto is_aux_img = [&](int ii) { return (img[ii].flags & APB_IMG_AUX) != 0; };
+  for (int k = 0; k < n_psf; ++k)
+    if (psf[k].source >= 0) {
+      if (psf[k].source >= n_src) PFAIL("psf source index out of range");
+      const apb_source_t& ps = src[psf[k].source];
+      if (ps.image < 0 || ps.image >= n_img || !is_aux_img(ps.image)) PFAIL("a PSF-model source must sit on an APB_IMG_AUX image");
+      if (ps.psf >= 0) PFAIL("a PSF-model source cannot itself be PSF-convolved");
+      if (img[ps.image].W != psf[k].w || img[ps.image].H != psf[k].h || ps.out[0] != 0 || ps.out[1] != 0 ||
+          ps.out[2] != psf[k].w || ps.out[3] != psf[k].h)
+        PFAIL("a PSF-model source must cover its aux image, which must have the PSF's shape");
+      p->any_aux_psf = true;
+    }
   for (int i = 0; i < n_src; ++i) {
     const apb_source_t& a = src[i];
     DevSrc& s = S[i];
@@ -378,7 +391,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     if (a.kind < 0 || a.kind > APB_FLAT_SKY) PFAIL("unknown source kind");
     if (a.image < 0 || a.image >= n_img) PFAIL("source image index out of range");
     if (a.n_elem < 3 || a.n_elem > APB_MAX_ELEM) PFAIL("bad n_elem");
-    if (a.sampling_mode == APB_SAMPLE_TRAPEZOID) PFAIL("sampling_mode trapezoid is not implemented");
+    if (a.sampling_mode < APB_SAMPLE_MIDPOINT || a.sampling_mode > APB_SAMPLE_TRAPEZOID) PFAIL("unknown sampling_mode");
     if (a.max_depth < 1 || a.max_depth > APB_MAX_DEPTH) PFAIL("integrate_max_depth out of range (1..4)");
     if (a.quad_level < 1 || a.quad_level > APB_MAX_QUAD || a.quad_init < 1 || a.quad_init > APB_MAX_QUAD)
       PFAIL("quadrature level out of range (1..9)");
@@ -393,6 +406,21 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       s.slot[e] = a.slot[e]; s.cval[e] = a.cval[e];
       if (a.slot[e] >= n_par) PFAIL("parameter slot out of range");
       if (a.slot[e] >= 0) { s.plane[e] = ++s.n_act; act_slot.push_back(a.slot[e]); } else s.plane[e] = 0;
+    }
+    s.n_elem_all = s.n_elem; s.psf_src = -1; s.n_pp = 0;
+    if (a.psf >= 0 && a.psf < n_psf && psf[a.psf].source >= 0 && a.kind != APB_FLAT_SKY) {
+      // auxiliary PSF model: its free parameters become pseudo-elements (and derivative planes) of this source
+      if (a.kind == APB_POINT) PFAIL("point sources with a PSF model are not supported");
+      s.psf_src = psf[a.psf].source;
+      const apb_source_t& ps = src[s.psf_src];
+      for (int e = 0; e < ps.n_elem; ++e)
+        if (ps.slot[e] >= 0) {
+          if (s.n_elem_all >= APB_MAX_ELEM) PFAIL("too many parameters for one source (own + auxiliary PSF model)");
+          s.slot[s.n_elem_all] = ps.slot[e];
+          s.plane[s.n_elem_all] = ++s.n_act;
+          act_slot.push_back(ps.slot[e]);
+          ++s.n_elem_all; ++s.n_pp;
+        }
     }
     act_off[i + 1] = (int)act_slot.size();
     max_nact = std::max(max_nact, s.n_act);
@@ -422,12 +450,13 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       const bool pad = (a.psf_shift != APB_SHIFT_NONE) && a.kind != APB_POINT;
       s.spw = s.pw + (pad ? 2 : 0); s.sph = s.ph + (pad ? 2 : 0);
       if (a.kind != APB_POINT) { s.bx = (s.pw + 2) / 2; s.by = (s.ph + 2) / 2; }  // ceil((1+P)/2), psf_image.py:71-93
-      s.psf_off = psfst_total; psfst_total += 3LL * s.spw * s.sph;
+      s.psf_off = psfst_total; psfst_total += (3LL + s.n_pp) * s.spw * s.sph;
       s.out_off = out_total; out_total += (long long)(1 + s.n_act) * s.ow * s.oh;
       psf_list.push_back(i);
       if (a.kind == APB_POINT) point_list.push_back(i);
     }
-    const bool ring = (a.kind != APB_FLAT_SKY && a.kind != APB_POINT && s.sampling_mode == APB_SAMPLE_MIDPOINT &&
+    const bool ring = (a.kind != APB_FLAT_SKY && a.kind != APB_POINT &&
+                       (s.sampling_mode == APB_SAMPLE_MIDPOINT || s.sampling_mode == APB_SAMPLE_TRAPEZOID) &&
                        s.integrate_mode == APB_INTEGRATE_THRESHOLD);
     set_geo(s.geo[0], a.out, a.fwd, s.bx, s.by, ring);
     set_geo(s.geo[1], a.out, a.jac, s.bx, s.by, ring);
@@ -471,8 +500,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           s.fft_nf = nf; s.fft_nc = nc; s.fft_ld = ldy0 + pad;
           s.specA_off = spec_total; spec_total += (long long)(1 + s.n_act) * g.eh * s.nxp;
           s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.oh * s.nxp;
-          s.specK_off = spec_total; spec_total += 3LL * s.sph * s.nxp;
-          s.specKT_off = spec_total; spec_total += 3LL * s.nxh * Ny;
+          s.specK_off = spec_total; spec_total += (3LL + s.n_pp) * s.sph * s.nxp;
+          s.specKT_off = spec_total; spec_total += (3LL + s.n_pp) * s.nxh * Ny;
           p->fft_smem_rows = std::max(p->fft_smem_rows, row_bytes);
           p->fft_smem_cols = std::max(p->fft_smem_cols, col_bytes);
           p->n_fft_src++;
@@ -543,6 +572,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
             if (e < 2 && shifted) add_job(0, 1 + e, s.plane[e]);   // centre: through the PSF shift
             else add_job(s.plane[e], 0, s.plane[e]);
           }
+          for (int k = 0; k < s.n_pp; ++k) add_job(0, 3 + k, s.plane[s.n_elem + k]);   // auxiliary PSF parameters
         }
         const size_t need = ((size_t)s.spw * s.sph + (size_t)(CONV_TH + s.sph - 1) * ((CONV_TW + s.spw - 1) | 1)) * sizeof(double);
         smem = std::max(smem, need);
@@ -573,7 +603,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       auto add_cols = [&](std::vector<int4>& v, int job) {
         for (int k = 0; k < s.nxh; k += s.fft_nc) v.push_back(make_int4(job, k, std::min(s.fft_nc, s.nxh - k), 0));
       };
-      bool need_k[3] = {true, false, false};
+      bool need_k[3 + APB_MAX_ELEM] = {true};
       std::vector<int> in_planes(1, 0);
       std::vector<int4> conv;   // {in_plane, kernel, out_plane}
       conv.push_back(make_int4(0, 0, 0, 0));
@@ -583,7 +613,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           if (e < 2 && shifted) { need_k[1 + e] = true; conv.push_back(make_int4(0, 1 + e, s.plane[e], 0)); }
           else { in_planes.push_back(s.plane[e]); conv.push_back(make_int4(s.plane[e], 0, s.plane[e], 0)); }
         }
-      for (int k = 0; k < 3; ++k)
+      if (gr)
+        for (int k = 0; k < s.n_pp; ++k) { need_k[3 + k] = true; conv.push_back(make_int4(0, 3 + k, s.plane[s.n_elem + k], 0)); }
+      for (int k = 0; k < 3 + s.n_pp; ++k)
         if (need_k[k]) {
           add_rows(rpsf, -1 - k, s.sph);
           jobs.push_back(make_int4(i, -1 - k, 0, 0));
@@ -621,6 +653,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     std::vector<int4> itiles;
     std::vector<int> bptr(1, 0), bsrc;
     for (int ii = 0; ii < n_img; ++ii) {
+      if (is_aux_img(ii)) continue;   // PSF-model grids are no output and no chi^2 term
       const int ntx = ceil_div(img[ii].W, 32), nty = ceil_div(img[ii].H, 32);
       std::vector<std::vector<int>> bins((size_t)ntx * nty);
       for (int i = 0; i < n_src; ++i) {
@@ -664,6 +697,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     };
     // spatial hash of sources per image to find overlapping pairs
     for (int ii = 0; ii < n_img; ++ii) {
+      if (is_aux_img(ii)) continue;
       std::vector<int> ids;
       for (int i = 0; i < n_src; ++i)
         if (S[i].image == ii && S[i].n_act > 0) ids.push_back(i);
@@ -996,8 +1030,10 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   const FftTables& F = p->ft[grad];
   // (while per-kernel timing is on, everything stays on one stream: an event pair around a side-stream
   //  kernel would also measure its wait for SMs held by the main stream's kernels)
-  const bool fork = p->n_psf_list && !p->profiling;
-  if (p->n_psf_list) {
+  // With an auxiliary PSF model the stamps depend on a source sampled in this very pass: the PSF branch then runs
+  // on the main stream after the sampling kernels.
+  const bool fork = p->n_psf_list && !p->profiling && !p->any_aux_psf;
+  auto psf_branch = [&]() -> int {
     cudaStream_t main_st = st;
     if (fork) {
       if (cudaEventRecord(p->ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev_fork, 0) != cudaSuccess)
@@ -1005,7 +1041,8 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
       st = p->side;
     }
     PB(K_PSF);
-    k_psf_stamp<<<p->n_psf_list, 256, 0, st>>>(p->d_src, p->d_dyn, p->psf_list, p->d_psf, p->d_psfst, grad);
+    k_psf_stamp<<<p->n_psf_list, 256, 0, st>>>(p->d_src, p->d_dyn, p->psf_list, p->d_psf, p->d_psfst, grad, mode, p->d_stamp,
+                                               p->d_out);
     LAUNCH_CHECK();
     if (p->n_fft_src) {
       PB(K_FFTROWS);
@@ -1019,6 +1056,11 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
     }
     if (fork && cudaEventRecord(p->ev_join, st) != cudaSuccess) APB_FAIL("PSF stream event failed");
     st = main_st;
+    return 0;
+  };
+  if (p->n_psf_list && !p->any_aux_psf) {
+    const int rc = psf_branch();
+    if (rc) return rc;
   }
   if (T.n_tiles) {
     PB(grad ? K_FIRST_G : K_FIRST);
@@ -1083,6 +1125,10 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
       k_normalize<<<p->n_norm, 256, 0, st>>>(p->d_src, p->norm_list, mode, p->d_stamp, grad);
       LAUNCH_CHECK();
     }
+  }
+  if (p->n_psf_list && p->any_aux_psf) {
+    const int rc = psf_branch();
+    if (rc) return rc;
   }
   if (fork && cudaStreamWaitEvent(st, p->ev_join, 0) != cudaSuccess) APB_FAIL("join of the PSF stream failed");
   if (p->n_point) {
@@ -1149,7 +1195,8 @@ extern "C" int apb_jacobian(apb_plan_t* p, const double* x, int as_rep, double* 
   if (begin_call(p, st)) return -1;
   if (!jac_out) APB_FAIL("apb_jacobian: jac_out is NULL");
   for (int ii = 0; ii < p->n_img; ++ii)
-    CU(cudaMemsetAsync(jac_out[ii], 0, sizeof(double) * (size_t)p->h_img[ii].H * p->h_img[ii].W * p->n_par, st));
+    if (!(p->h_img[ii].flags & APB_IMG_AUX))
+      CU(cudaMemsetAsync(jac_out[ii], 0, sizeof(double) * (size_t)p->h_img[ii].H * p->h_img[ii].W * p->n_par, st));
   if (p->n_par == 0) return 0;
   CU(cudaMemcpyAsync(p->d_userptr, jac_out, sizeof(double*) * p->n_img, cudaMemcpyHostToDevice, st));
   int rc = sample_pass(p, x, as_rep, 1, 1, st);
@@ -1164,7 +1211,7 @@ extern "C" int apb_jacobian(apb_plan_t* p, const double* x, int as_rep, double* 
 
 static int chi2_core(apb_plan* p, const double* x_rep, double* out2, cudaStream_t st) {
   for (int ii = 0; ii < p->n_img; ++ii)
-    if (!p->h_img[ii].data) APB_FAIL("apb_chi2: image without data");
+    if (!p->h_img[ii].data && !(p->h_img[ii].flags & APB_IMG_AUX)) APB_FAIL("apb_chi2: image without data");
   int rc = sample_pass(p, x_rep, 1, 0, 0, st);
   if (rc) return rc;
   return assemble(p, 0, nullptr, nullptr, out2, 1, st);
@@ -1183,7 +1230,7 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
   cudaStream_t st = (cudaStream_t)stream;
   if (begin_call(p, st)) return -1;
   for (int ii = 0; ii < p->n_img; ++ii)
-    if (!p->h_img[ii].data) APB_FAIL("apb_normal_eq: image without data");
+    if (!p->h_img[ii].data && !(p->h_img[ii].flags & APB_IMG_AUX)) APB_FAIL("apb_normal_eq: image without data");
   const int P = p->n_par;
   int rc;
   if (!p->all_same_geo) {

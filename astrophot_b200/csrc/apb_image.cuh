@@ -11,7 +11,8 @@
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                    const int* __restrict__ list, const apb_psf_t* __restrict__ psfs,
-                                                   double* __restrict__ psfst, int grad) {
+                                                   double* __restrict__ psfst, int grad, int mode,
+                                                   const double* __restrict__ stamp, const double* __restrict__ outar) {
   __shared__ double sh[8];
   __shared__ double tot_s[3];
   const int si = list[blockIdx.x];
@@ -24,6 +25,14 @@ __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ sr
   double* K1 = K0 + n;
   double* K2 = K1 + n;
   const bool shifted = s.psf_shift != APB_SHIFT_NONE;
+  // the raw stamp: a static PSF image, or plane 0 of the auxiliary PSF model sampled earlier in this pass
+  const double* pdat = P.data;
+  int pstride = pw;
+  if (s.psf_src >= 0) {
+    const PlaneView pv = out_plane(src[s.psf_src], mode, 0, stamp, outar);
+    pdat = pv.p;
+    pstride = pv.stride;
+  }
   // padded image is (ph+2) x (pw+2); stamps either keep the pad (galaxies) or crop it (points)
   const int crop = (s.kind == APB_POINT && shifted) ? 1 : 0;
   const int W2 = pw + 2, H2 = ph + 2;
@@ -32,7 +41,7 @@ __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ sr
     const int a = q / spw, b = q % spw;
     double val, gx = 0, gy = 0;
     if (!shifted) {
-      val = P.data[a * pw + b];
+      val = pdat[a * pstride + b];
     } else {
       const int i = b + crop, j = a + crop;  // index in the padded image
       const double x = (double)i - d.sx, y = (double)j - d.sy;
@@ -41,7 +50,7 @@ __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ sr
       x0 = min(max(x0, 0), W2 - 2);
       y0 = min(max(y0, 0), H2 - 2);
       auto pad = [&](int yy, int xx) -> double {
-        return (yy >= 1 && yy <= ph && xx >= 1 && xx <= pw) ? P.data[(yy - 1) * pw + (xx - 1)] : 0.0;
+        return (yy >= 1 && yy <= ph && xx >= 1 && xx <= pw) ? pdat[(yy - 1) * pstride + (xx - 1)] : 0.0;
       };
       const double fa = pad(y0, x0), fb = pad(y1, x0), fc = pad(y0, x1), fd = pad(y1, x1);
       const double wx0 = (double)x1 - x, wx1 = x - (double)x0, wy0 = (double)y1 - y, wy1 = y - (double)y0;
@@ -66,6 +75,45 @@ __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ sr
   if (threadIdx.x == 0) tot_s[2] = t;
   __syncthreads();
   const double tot = tot_s[0], tx = tot_s[1], ty = tot_s[2];
+  // auxiliary PSF model: d/d theta of the shifted, normalised stamp.  The shift is linear in the PSF, so with
+  // D = shift(d psf / d theta):  dK = D / T - shift(psf) sum(D) / T^2  (planes 3.. of this source's stamps; the PSF
+  // source's planes already carry d value / d representation)
+  if (grad && s.psf_src >= 0) {
+    const DevSrc& psrc = src[s.psf_src];
+    for (int k = 0; k < s.n_pp; ++k) {
+      const PlaneView dv = out_plane(psrc, mode, 1 + k, stamp, outar);
+      double* Kk = K0 + (long long)(3 + k) * n;
+      double vk = 0.0;
+      for (int q = threadIdx.x; q < n; q += 256) {
+        const int a = q / spw, b = q % spw;
+        double val;
+        if (!shifted) {
+          val = dv.p[a * dv.stride + b];
+        } else {
+          const int i = b + crop, j = a + crop;
+          const double x = (double)i - d.sx, y = (double)j - d.sy;
+          int x0 = (int)floor(x), y0 = (int)floor(y);
+          int x1 = min(max(x0 + 1, 1), W2 - 1), y1 = min(max(y0 + 1, 1), H2 - 1);
+          x0 = min(max(x0, 0), W2 - 2);
+          y0 = min(max(y0, 0), H2 - 2);
+          auto pad = [&](int yy, int xx) -> double {
+            return (yy >= 1 && yy <= ph && xx >= 1 && xx <= pw) ? dv.p[(yy - 1) * dv.stride + (xx - 1)] : 0.0;
+          };
+          const double wx0 = (double)x1 - x, wx1 = x - (double)x0, wy0 = (double)y1 - y, wy1 = y - (double)y0;
+          val = pad(y0, x0) * (wx0 * wy0) + pad(y1, x0) * (wx0 * wy1) + pad(y0, x1) * (wx1 * wy0) + pad(y1, x1) * (wx1 * wy1);
+        }
+        Kk[q] = val;
+        vk += val;
+      }
+      const double tk = block_sum<256>(vk, sh);
+      __shared__ double tk_s;
+      if (threadIdx.x == 0) tk_s = tk;
+      __syncthreads();
+      const double tks = tk_s;
+      for (int q = threadIdx.x; q < n; q += 256) Kk[q] = Kk[q] / tot - K0[q] * (tks / (tot * tot));
+      __syncthreads();
+    }
+  }
   for (int q = threadIdx.x; q < n; q += 256) {
     const double st = K0[q];
     if (grad && shifted) {
@@ -290,7 +338,7 @@ __global__ void __launch_bounds__(256) k_jac_dense(const DevSrc* __restrict__ sr
       const int si = bin_src[b];
       const DevSrc& s = src[si];
       if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
-      for (int e = 0; e < s.n_elem; ++e) {
+      for (int e = 0; e < s.n_elem_all; ++e) {
         const int p = s.plane[e];
         if (p <= 0) continue;
         double v;
@@ -479,7 +527,7 @@ __global__ void __launch_bounds__(256) k_geo_v(const DevSrc* __restrict__ src, c
       const int si = bin_src[b];
       const DevSrc& s = src[si];
       if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
-      for (int e = 0; e < s.n_elem; ++e) {
+      for (int e = 0; e < s.n_elem_all; ++e) {
         const int pl = s.plane[e];
         if (pl <= 0) continue;
         jh += plane_at(s, pl, x, y, stamp, outar, skyJ, si) * h[s.slot[e]];

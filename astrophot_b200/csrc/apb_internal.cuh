@@ -28,6 +28,9 @@ struct DevSrc {
   double cval[APB_MAX_ELEM];
   int plane[APB_MAX_ELEM];  // derivative plane (1..n_act) of each element, 0 = none
   int n_act;
+  // auxiliary PSF model: its n_pp free parameters are pseudo-elements n_elem .. n_elem_all-1 of this source
+  // (slot / plane filled, never seen by the profile evaluation); psf_src = the source that samples the PSF
+  int n_elem_all, psf_src, n_pp;
   int n_prof;
   double prof[APB_MAX_PROF];
   int sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth, ref_mode;

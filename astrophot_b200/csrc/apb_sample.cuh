@@ -211,6 +211,21 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
   double acc[(GRAD ? NE : 0) + 1];
   if (s.sampling_mode == APB_SAMPLE_MIDPOINT) {
     acc[0] = eval_point<KIND, GRAD>(s, d, X, Y, 1.0, acc + 1);
+  } else if (s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
+    // mean of the four pixel-corner values (_model_methods.py:124-143); error proxy = curvature, as for midpoint
+    double dI[GRAD ? NE : 1];
+    acc[0] = 0.0;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc[1 + e] = 0.0;
+    for (int a = -1; a <= 1; a += 2)
+      for (int b = -1; b <= 1; b += 2) {
+        const double ox = 0.5 * b, oy = 0.5 * a;
+        const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy),
+                                                1.0, dI);
+        acc[0] += 0.25 * I;
+        if (GRAD)
+          for (int e = 0; e < ne; ++e) acc[1 + e] += 0.25 * dI[e];
+      }
   } else if (s.sampling_mode == APB_SAMPLE_QUAD) {
     const double centre = gl_integrate<KIND, GRAD>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
     base[(long long)err_plane * s.plane_stride] = fabs(acc[0] - centre);
@@ -272,6 +287,15 @@ template <int KIND>
 __device__ __forceinline__ double first_value(const DevSrc& s, const DevDyn& d, double X, double Y) {
   double acc[1];
   if (s.sampling_mode == APB_SAMPLE_MIDPOINT) return eval_point<KIND, false>(s, d, X, Y, 1.0, acc);
+  if (s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
+    double tot = 0.0;
+    for (int a = -1; a <= 1; a += 2)
+      for (int b = -1; b <= 1; b += 2) {
+        const double ox = 0.5 * b, oy = 0.5 * a;
+        tot += 0.25 * eval_point<KIND, false>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy), 1.0, acc);
+      }
+    return tot;
+  }
   if (s.sampling_mode == APB_SAMPLE_QUAD) {
     gl_integrate<KIND, false>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
     return acc[0];
@@ -347,7 +371,7 @@ __device__ __forceinline__ void select_tile(const DevSrc* __restrict__ src, cons
     if (pi >= g.ex0 && pi < g.ex0 + g.ew && pj >= g.ey0 && pj < g.ey0 + g.eh) {
       const double* m = stamp + s.stamp_off;
       double err;
-      if (s.sampling_mode == APB_SAMPLE_MIDPOINT) {
+      if (s.sampling_mode == APB_SAMPLE_MIDPOINT || s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
         if (g.rw >= 3 && g.rh >= 3) {
           // 3x3 Laplacian, replicate-padded over the working region (_model_methods.py:87-98)
           int ic = min(max(pi, g.rx0 + 1), g.rx0 + g.rw - 2) - g.mx0;

@@ -103,6 +103,8 @@ class LM(BaseOptimizer):
             W = torch.as_tensor(kwargs["W"], dtype=torch.float64).flatten()
             at = 0
             for im in scene.images:
+                if im.aux:
+                    continue
                 im.weight = W[at : at + im.H * im.W].reshape(im.H, im.W)
                 at += im.H * im.W
         # tiles=(ny, nx): cut every image into tiles (one big image sharded over the ranks);
@@ -114,6 +116,8 @@ class LM(BaseOptimizer):
         self.scene, self.info = scene, info
         n_keep = 0
         for im in scene.images:
+            if im.aux:
+                continue
             n_keep += im.H * im.W if im.mask is None else int((~torch.as_tensor(im.mask).bool()).sum())
         if n_keep == 0:
             raise OptimizeStop("No data to fit. All pixels are masked")

@@ -215,8 +215,6 @@ def lower(model, window=None, for_fit=False):
         else:
             raise SpecificationConflict(
                 f"{comp.name} has unknown sampling mode: {sm}. Should be one of: midpoint, simpsons, quad:level, trapezoid")
-        if smode == sc.SAMPLE_TRAPEZOID:
-            raise SpecificationConflict("sampling_mode='trapezoid' is not implemented in astrophot_b200 yet")
         im = comp.integrate_mode
         if im == "none":
             imode = sc.INTEGRATE_NONE
@@ -333,18 +331,29 @@ def shard_scene(scene, rank, world):
     sources on them; the parameter table stays global so that every rank's
     J^T W J lands in the same (P, P) layout and a plain sum all-reduce merges
     them."""
-    keep = [i for i in range(len(scene.images)) if i % world == rank]
+    real = [i for i, im in enumerate(scene.images) if not im.aux]
+    keep = [i for k, i in enumerate(real) if k % world == rank] + [i for i, im in enumerate(scene.images) if im.aux]
     remap = {old: new for new, old in enumerate(keep)}
-    srcs = []
-    psf_used = {}
-    for s in scene.sources:
+    srcs, new_index = [], {}
+    for k, s in enumerate(scene.sources):
         if s.image in remap:
             s2 = sc.SceneSource(**{**s.__dict__})
             s2.image = remap[s.image]
+            new_index[k] = len(srcs)
             srcs.append(s2)
-    return sc.Scene(images=[scene.images[i] for i in keep], sources=srcs, psfs=scene.psfs,
+    return sc.Scene(images=[scene.images[i] for i in keep], sources=srcs, psfs=_remap_psfs(scene.psfs, new_index),
                     transform=scene.transform, lo=scene.lo, hi=scene.hi, identities=scene.identities,
                     owners=scene.owners)
+
+
+def _remap_psfs(psfs, new_index):
+    """PSFs produced by an auxiliary PSF-model source point at it by index into the source list."""
+    out = []
+    for ps in psfs:
+        if ps.source >= 0:
+            ps = sc.ScenePSF(data=None, source=new_index[ps.source], shape=ps.shape)
+        out.append(ps)
+    return out
 
 
 def tile_scene(scene, ny, nx):
@@ -360,11 +369,17 @@ def tile_scene(scene, ny, nx):
     block-sparse J^T W J is laid out on them, identically on every rank)."""
     if ny * nx <= 1:
         return scene
-    owners = [(s.image, tuple(s.out), [sl for sl in s.slot if sl >= 0]) for s in scene.sources]
+    has_aux = any(im.aux for im in scene.images)
+    # (with an auxiliary PSF model its parameters are shared by every source using it: no owner layout, dense solve)
+    owners = None if has_aux else [(s.image, tuple(s.out), [sl for sl in s.slot if sl >= 0]) for s in scene.sources]
     images, sources, origin = [], [], []
     first_tile = []
     for im in scene.images:
         first_tile.append(len(images))
+        if im.aux:                      # grid of an auxiliary PSF model: never cut
+            images.append(im)
+            origin.append((0, 0, im.W, im.H))
+            continue
         ys = [round(k * im.H / ny) for k in range(ny + 1)]
         xs = [round(k * im.W / nx) for k in range(nx + 1)]
         for a in range(ny):
@@ -379,6 +394,7 @@ def tile_scene(scene, ny, nx):
                                             data=cut(im.data), weight=cut(im.weight), mask=cut(im.mask)))
                 origin.append((x0, y0, x1 - x0, y1 - y0))
     n_tiles_of = first_tile[1:] + [len(images)]
+    new_index = {}
     for k, s in enumerate(scene.sources):
         for t in range(first_tile[s.image], n_tiles_of[s.image]):
             tx, ty, tw, th = origin[t]
@@ -393,6 +409,13 @@ def tile_scene(scene, ny, nx):
             s2.out = (ix0 - tx, iy0 - ty, ix1 - ix0, iy1 - iy0)
             s2.fwd = (s.fwd[0] - tx, s.fwd[1] - ty, s.fwd[2], s.fwd[3])
             s2.jac = (s.jac[0] - tx, s.jac[1] - ty, s.jac[2], s.jac[3])
+            new_index[k] = len(sources)
             sources.append(s2)
-    return sc.Scene(images=images, sources=sources, psfs=scene.psfs, transform=scene.transform, lo=scene.lo,
+    # the tiles come first, aux images last (as lower() lays them out)
+    order = [i for i, im in enumerate(images) if not im.aux] + [i for i, im in enumerate(images) if im.aux]
+    pos = {old: new for new, old in enumerate(order)}
+    images = [images[i] for i in order]
+    for s2 in sources:
+        s2.image = pos[s2.image]
+    return sc.Scene(images=images, sources=sources, psfs=_remap_psfs(scene.psfs, new_index), transform=scene.transform, lo=scene.lo,
                     hi=scene.hi, identities=scene.identities, owners=owners)

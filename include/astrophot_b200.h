@@ -73,12 +73,23 @@ typedef struct {
   const double *data;    /* device, H*W; may be NULL when only sampling     */
   const double *weight;  /* device, H*W; NULL = ones (target_image.py:182)  */
   const uint8_t *mask;   /* device, H*W; 1 = ignore pixel; NULL = none      */
+  int32_t flags;         /* APB_IMG_AUX: grid of an auxiliary PSF model     */
+  int32_t _pad;
 } apb_image_t;
+/* APB_IMG_AUX: the image is the PSF_Image grid an auxiliary PSF model is sampled on
+ * (model_object.py:133-147,307-310): its sources are evaluated on every pass, but it is no output of
+ * apb_sample / apb_jacobian (its model_out / jac_out entry is ignored) and no term of chi^2. */
+enum { APB_IMG_AUX = 1 };
 
 /* a PSF stamp (image/psf_image.py:17-93): odd h, w; un-normalised is fine */
 typedef struct {
   int32_t h, w;
-  const double *data; /* device, h*w */
+  const double *data; /* device, h*w; NULL when the stamp comes from `source`                       */
+  int32_t source;     /* >= 0: index of the PSF-model source (APB_F_NORMALIZE, alone on an
+                         APB_IMG_AUX image of h x w pixels) that produces the stamp on every pass; its
+                         free parameters become columns of the Jacobian of every source using this
+                         PSF (model_object.py:133-147: set_aux_psf links the parameters).  -1: data */
+  int32_t _pad;
 } apb_psf_t;
 
 /* one component model, lowered (models/model_object.py:64-95 for the knobs) */

@@ -490,9 +490,15 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, val
     jj, ii = np.meshgrid(np.arange(my0, my1, dtype=np.float64), np.arange(mx0, mx1, dtype=np.float64), indexing="ij")
     X, Y = coords(ii, jj)
     nspe = 0
-    if src.sampling_mode == sc.SAMPLE_MIDPOINT:
-        deep, ddeep = eval_profile(src, el, X, Y, area, want_grad)
-        nspe += X.size
+    if src.sampling_mode in (sc.SAMPLE_MIDPOINT, sc.SAMPLE_TRAPEZOID):
+        if src.sampling_mode == sc.SAMPLE_MIDPOINT:
+            deep, ddeep = eval_profile(src, el, X, Y, area, want_grad)
+            nspe += X.size
+        else:
+            # trapezoid (_model_methods.py:124-143): mean of the four pixel-corner values, then the same
+            # curvature proxy as midpoint on that image
+            deep, ddeep = _trapezoid(src, el, X, Y, S, area, want_grad)
+            nspe += 4 * X.size
         # curvature: valid 3x3 Laplacian, replicate-padded *over the working region*
         # (_model_methods.py:87-98): evaluate the stencil at the index clamped to the interior
         def lap_at(i, j):   # absolute pixel indices (arrays)
@@ -545,7 +551,8 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, val
         if src.ref_mode == sc.REF_SERSIC_FLUX:
             ref = sersic_total_flux(10.0 ** el[6], el[4], el[5], el[2]) / (rw * rh)
         else:
-            if (mx0, my0, mx1, my1) == (rx0, ry0, rx0 + rw, ry0 + rh) or src.sampling_mode != sc.SAMPLE_MIDPOINT and (ex0, ey0, ew, eh) == (rx0, ry0, rw, rh):
+            ringed = src.sampling_mode in (sc.SAMPLE_MIDPOINT, sc.SAMPLE_TRAPEZOID)
+            if (mx0, my0, mx1, my1) == (rx0, ry0, rx0 + rw, ry0 + rh) or not ringed and (ex0, ey0, ew, eh) == (rx0, ry0, rw, rh):
                 ref = mean_src.sum() / (rw * rh)
             else:
                 ref = _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh)
@@ -602,6 +609,18 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, val
     return SourceResult(val, grad, extra)
 
 
+def _trapezoid(src, el, X, Y, S, area, want_grad):
+    """Mean of the profile at the four corners of every pixel (2x2 box filter on the corner lattice)."""
+    tot, dtot = 0.0, 0.0
+    for a in (-0.5, 0.5):
+        for b in (-0.5, 0.5):
+            I, dI = eval_profile(src, el, X + (S[0, 0] * b + S[0, 1] * a), Y + (S[1, 0] * b + S[1, 1] * a), area, want_grad)
+            tot = tot + 0.25 * I
+            if want_grad:
+                dtot = dtot + 0.25 * dI
+    return tot, (dtot if want_grad else None)
+
+
 def _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh):
     """Mean of the first-pass image over the whole working region (the default
     ``_integrate_reference``, _model_methods.py:151-152), in row blocks."""
@@ -612,6 +631,8 @@ def _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh):
         X, Y = coords(ii, jj)
         if src.sampling_mode == sc.SAMPLE_MIDPOINT:
             I, _ = eval_profile(src, el, X, Y, area, False)
+        elif src.sampling_mode == sc.SAMPLE_TRAPEZOID:
+            I, _ = _trapezoid(src, el, X, Y, S, area, False)
         elif src.sampling_mode == sc.SAMPLE_QUAD:
             I, _, _ = _gl(src, el, X, Y, S, area, src.quad_init, False)
         else:

@@ -64,6 +64,11 @@ def build(ap, name, data=None):
         m = M(name="noint", model_type="sersic galaxy model", target=tar, integrate_mode="none",
               parameters={"center": [31.2, 33.9], "q": 0.7, "PA": 0.4, "n": 1.5, "Re": 8.0, "Ie": 0.5})
         return m, {}
+    if name == "sersic_trapezoid":
+        tar = _target(ap, (56, 52), data, pixelscale=0.9)
+        m = M(name="trz", model_type="sersic galaxy model", target=tar, sampling_mode="trapezoid",
+              parameters={"center": [22.4, 26.1], "q": 0.55, "PA": 1.3, "n": 1.8, "Re": 7.0, "Ie": 0.8})
+        return m, {}
     if name == "sersic_quad5":
         tar = _target(ap, (50, 50), data, pixelscale=0.8)
         m = M(name="q5", model_type="sersic galaxy model", target=tar, sampling_mode="quad:5",
@@ -203,7 +208,7 @@ def build(ap, name, data=None):
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
-                 "aux_psf_gauss_noshift"]
+                 "aux_psf_gauss_noshift", "sersic_trapezoid"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12}
 

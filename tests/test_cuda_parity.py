@@ -19,7 +19,8 @@ def _plan(scene, conv=None):
     return Plan(scene, conv=conv)
 
 
-PSF_SCENES = ["psf_sersic", "psf_sersic_noshift", "group", "group_nosky", "joint", "crowded"]
+PSF_SCENES = ["psf_sersic", "psf_sersic_noshift", "group", "group_nosky", "joint", "crowded", "aux_psf_moffat",
+              "aux_psf_gauss_noshift"]
 
 
 @pytest.mark.parametrize("name", PSF_SCENES)
@@ -128,7 +129,7 @@ def test_fused_integration_equals_per_depth_launches(name):
 
 
 @pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat", "psf_sersic", "moffat_psf_model", "group",
-                                  "joint", "crowded"])
+                                  "joint", "crowded", "aux_psf_moffat"])
 def test_pooled_integration_equals_lane_shared(name):
     """k_integrate_pool (throughput form for long queues: a lane per cell, children of all failing
     entries pooled over the CTA) against k_integrate: same nodes, same decisions, same counts; sums
@@ -349,6 +350,20 @@ def test_unknown_modes_raise():
 # ---------------------------------------------------------------------------
 # one image cut into tiles: lowering.tile_scene, owner-level block-sparse J^T W J
 # ---------------------------------------------------------------------------
+def test_tiled_plan_with_auxiliary_psf_model():
+    """Tiles + an auxiliary PSF model: the PSF grid is never cut, every tile's piece of the host uses it."""
+    from astrophot_b200.lowering import tile_scene
+    fix = load_golden("aux_psf_moffat")
+    model, _ = scenes.build(ap, "aux_psf_moffat", data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    cut = _plan(tile_scene(scene, 2, 2))
+    H1, g1, c1 = [t.cpu().numpy() for t in cut.normal_eq(fix["x0"], check=True)]
+    d = np.sqrt(np.diag(fix["hess0"]))
+    assert np.max(np.abs(H1 - fix["hess0"]) / np.outer(d, d)) < 1e-9
+    assert np.max(np.abs(g1 - fix["grad0"])) / np.abs(fix["grad0"]).max() < 1e-9
+    assert cut.bind_blocks() is None      # PSF parameters are shared by all pieces: dense solve only
+
+
 @pytest.mark.parametrize("name,tiles", [("crowded", (2, 2)), ("crowded", (3, 2)), ("group", (1, 2)), ("group_nosky", (2, 1))])
 def test_tiled_plan_equals_whole_image(name, tiles):
     from astrophot_b200.lowering import tile_scene
