@@ -361,6 +361,10 @@ class Plan:
         _check(rc, "apb_lm_solve_sparse")
         return out, info
 
+    def block_doubles(self):
+        """Length of the block-sparse J^T W J array (0: the plan has no block-sparse form)."""
+        return int(self._L.apb_plan_block_doubles(self._h))
+
     def bind_blocks(self):
         """Torch-owned device array that receives the block-sparse J^T W J of every normal_eq
         ([64 doubles per owner block | diag H]; same layout on every rank of a tile-sharded fit, so a sum

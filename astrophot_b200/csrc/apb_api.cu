@@ -44,11 +44,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_PCG, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad", "k_pcg"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -106,6 +106,7 @@ struct apb_plan {
   int pool_min = 150000;                        // depth-1 queue length from which the pooled kernel takes over
   int pool_g2 = 25, pool_nv = 8;                // largest gridding^2 / values per child of the plan
   bool pool_ok = false;
+  int* h_qlast = nullptr;   // pinned: depth-1 queue length of the last pass per mode (-1: unknown), read back asynchronously
   // arenas
   double *d_stamp = nullptr, *d_out = nullptr, *d_psfst = nullptr, *d_meanpart = nullptr, *d_skyJ = nullptr;
   // queues
@@ -241,6 +242,7 @@ static int fft_len(int n) {
 extern "C" int apb_plan_destroy(apb_plan_t* p) {
   if (!p) return 0;
   for (void* q : p->owned) cudaFree(q);
+  if (p->h_qlast) cudaFreeHost(p->h_qlast);
   if (p->side) cudaStreamDestroy(p->side);
   if (p->trial_stream) cudaStreamDestroy(p->trial_stream);
   if (p->ev_trial_fork) cudaEventDestroy(p->ev_trial_fork);
@@ -539,10 +541,10 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       if (s.integrate_mode == APB_INTEGRATE_THRESHOLD && s.ref_mode == APB_REF_MEAN) {
         mean_list.push_back(i);
         g.chunk0 = (int)chunks.size();
-        const long long npx = (long long)g.rw * g.rh;
-        const int CH = 8192;
-        for (long long f = 0; f < npx; f += CH)
-          chunks.push_back(make_int4(i, (int)f, (int)std::min<long long>(CH, npx - f), (int)chunks.size()));
+        // row bands of the working region: >= 8192 pixels each, at most 128 per source ({src, row0, nrows, slot})
+        const int rows = std::max(ceil_div(g.rh, 128), ceil_div(8192, std::max(g.rw, 1)));
+        for (int r0 = 0; r0 < g.rh; r0 += rows)
+          chunks.push_back(make_int4(i, r0, std::min(rows, g.rh - r0), (int)chunks.size()));
         g.nchunk = (int)chunks.size() - g.chunk0;
       }
     }
@@ -988,6 +990,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     p->pool_grid[1] = sms * std::max(1, b1);
   }
 
+  PCU(cudaMallocHost((void**)&p->h_qlast, 2 * sizeof(int)));
+  p->h_qlast[0] = p->h_qlast[1] = -1;
   PCU(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
   PCU(cudaStreamCreateWithFlags(&p->trial_stream, cudaStreamNonBlocking));
   PCU(cudaEventCreateWithFlags(&p->ev_trial_fork, cudaEventDisableTiming));
@@ -1085,18 +1089,26 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
         // the queue length is known only on the device: short queues are integrated by k_integrate (lanes share an
         // entry: lowest latency), long ones by k_integrate_pool (a lane per cell: full lanes); each kernel returns at
         // once when the queue is not its kind.  A queue cannot be longer than the first pass has pixels.
+        // Which kernel the queue belongs to is a guess from the length the previous pass of this mode reported
+        // (copied back asynchronously, never waited for); only while that is unknown are both launched.  Either
+        // kernel integrates any queue correctly, so a stale guess costs time, not parity.
         const bool may_pool = p->pool_ok && p->first_evals[mode] >= p->pool_min;
-        const int n_max = may_pool ? p->pool_min : INT_MAX;
-        if (n_max > 0) {
+        const int last = may_pool ? *(volatile int*)&p->h_qlast[mode] : -1;
+        const bool run_lane = !may_pool || last < p->pool_min;     // unknown (-1) counts as short
+        const bool run_pool = may_pool && (last < 0 || last >= p->pool_min);
+        const int n_max = run_pool ? p->pool_min : INT_MAX;        // alone, k_integrate takes any length
+        const int n_min = run_lane ? p->pool_min : 0;              // alone, k_integrate_pool takes any length
+        if (may_pool) CU(cudaMemcpyAsync(&p->h_qlast[mode], p->q.count + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (run_lane && n_max > 0) {
           PB(grad ? K_INTEGRATE_G : K_INTEGRATE);
           if (grad) k_integrate<true><<<p->integrate_grid[1], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
           else k_integrate<false><<<p->integrate_grid[0], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
           LAUNCH_CHECK();
         }
-        if (may_pool) {
+        if (run_pool) {
           PB(grad ? K_POOL_G : K_POOL);
-          if (grad) k_integrate_pool<true><<<p->pool_grid[1], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->pool_min, p->pool_g2, p->pool_nv);
-          else k_integrate_pool<false><<<p->pool_grid[0], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->pool_min, p->pool_g2, 1);
+          if (grad) k_integrate_pool<true><<<p->pool_grid[1], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, p->pool_nv);
+          else k_integrate_pool<false><<<p->pool_grid[0], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, 1);
           LAUNCH_CHECK();
         }
       } else {
@@ -1416,7 +1428,9 @@ extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, dou
             p->d_bvals, p->d_diagH, p->d_pfac, g, h, p->d_pvec, p->d_pvec + P, p->d_pvec + 2 * P, p->d_pvec + 3 * P,
             info, p->n_par, max_iter > 0 ? max_iter : 2000, L, tol > 0.0 ? tol : 1e-14};
   void* args[] = {&A};
+  p->pbegin(K_PCG, st);
   CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(256), args, 0, st));
+  p->pend(st);
   g_launches++;
   return 0;
 }

@@ -62,6 +62,7 @@ struct DevDyn {
   int rx, ry;                  // rounded centre pixel
   double thr[2];               // tolerance * reference per mode
   double spl_m[APB_MAX_PROF];  // spline slopes
+  double rcut;                 // plane-unit radius beyond which the profile cannot change the mean reference (inf: none)
 };
 
 // view of one output plane of a source, in the output window

@@ -150,6 +150,26 @@ __global__ void __launch_bounds__(128) k_prep(const DevSrc* __restrict__ src, De
         d.spl_m[k] = m;
       }
     }
+  } else if (lane == 5) {
+    // Mean reference over a working region much larger than the source (a model inside a big group window,
+    // _model_methods.py:151-152 with group_model_object.py:211-227): beyond rcut every pixel is below 1e-22 / N_pix of
+    // the central value, i.e. far below the rounding of the sum, and is skipped by k_mean_partial.  Elliptical radius
+    // >= Euclidean distance (q <= 1), so a Euclidean cut is conservative.  Power-law profiles get no cut.
+    double rc = INFINITY;
+    if (profile && s.integrate_mode == APB_INTEGRATE_THRESHOLD && s.ref_mode == APB_REF_MEAN &&
+        (s.flags & APB_F_RADIAL ? true : d.el[2] <= 1.0)) {
+      const double npx = fmax((double)s.geo[0].rw * s.geo[0].rh, (double)s.geo[1].rw * s.geo[1].rh);
+      const double lg = log(npx * 1e22);
+      if (kind == APB_EXPONENTIAL) rc = d.el[4] * lg / sersic_b(1.0);
+      else if (kind == APB_GAUSSIAN) rc = d.el[4] * sqrt(2.0 * lg);
+      else if (kind == APB_SPLINE) {
+        const int K = s.n_prof;
+        const double* v = d.el + 4;
+        const double m = (v[K - 1] - v[K - 2]) / (s.prof[K - 1] - s.prof[K - 2]);   // log10 per unit radius beyond the last node
+        if (m < 0.0) rc = s.prof[K - 1] + fmax(0.0, (-lg / APB_LN10 + fmin(v[0], v[1]) - v[K - 1]) / m);
+      }
+    }
+    d.rcut = rc;
   }
 }
 
@@ -319,13 +339,30 @@ __global__ void __launch_bounds__(256) k_mean_partial(const DevSrc* __restrict__
   const DevDyn& d = dyn[c.x];
   const Geo& g = s.geo[mode];
   const bool from_stamp = (g.mx0 == g.rx0 && g.my0 == g.ry0 && g.mw == g.rw && g.mh == g.rh);
+  // this chunk's rows, clipped to the box outside which the profile is negligible (k_prep: rcut) when the centre
+  // lies inside the working region
+  int i0 = 0, i1 = g.rw, j0 = c.y, j1 = c.y + c.z;
+  if (!from_stamp && isfinite(d.rcut)) {
+    const double cx = d.el[0], cy = d.el[1];
+    const double pcx = s.Sinv[0] * (cx - s.rxy[0]) + s.Sinv[1] * (cy - s.rxy[1]) + s.rij[0];
+    const double pcy = s.Sinv[2] * (cx - s.rxy[0]) + s.Sinv[3] * (cy - s.rxy[1]) + s.rij[1];
+    if (pcx >= g.rx0 && pcx < g.rx0 + g.rw && pcy >= g.ry0 && pcy < g.ry0 + g.rh) {
+      const double hx = d.rcut * sqrt(s.Sinv[0] * s.Sinv[0] + s.Sinv[1] * s.Sinv[1]) + 3.0;
+      const double hy = d.rcut * sqrt(s.Sinv[2] * s.Sinv[2] + s.Sinv[3] * s.Sinv[3]) + 3.0;
+      i0 = max(i0, (int)fmax(floor(pcx - hx) - g.rx0, -1.0e9));
+      i1 = min(i1, (int)fmin(ceil(pcx + hx) - g.rx0 + 1.0, 1.0e9));
+      j0 = max(j0, (int)fmax(floor(pcy - hy) - g.ry0, -1.0e9));
+      j1 = min(j1, (int)fmin(ceil(pcy + hy) - g.ry0 + 1.0, 1.0e9));
+    }
+  }
+  const int nc = max(i1 - i0, 0), nr = max(j1 - j0, 0);
+  const long long npx = (long long)nc * nr;
   double v = 0.0;
-  for (int q = threadIdx.x; q < c.z; q += 256) {
-    const int p = c.y + q;
+  for (long long q = threadIdx.x; q < npx; q += 256) {
+    const int i = i0 + (int)(q % nc), j = j0 + (int)(q / nc);
     if (from_stamp) {
-      v += stamp[s.stamp_off + p];
+      v += stamp[s.stamp_off + (long long)j * g.rw + i];
     } else {
-      const int i = p % g.rw, j = p / g.rw;
       double X, Y;
       pix_coords(s, d, (double)(g.rx0 + i), (double)(g.ry0 + j), X, Y);
       switch (s.kind) {

@@ -2,17 +2,24 @@
 // conjugate gradients, one persistent cooperative kernel per solve.
 //
 // The reference forms the dense P x P matrix  A = H o (I + (1-I)/(1+L)) + L I (1 + diag H)  and calls
-// torch.linalg.solve (fit/lm.py:359-371).  For a crowded field H = J^T W J is block-sparse: a source
-// only couples to the sources its window overlaps (and to the sky), so the matrix is kept as the
-// list of <=8x8 blocks k_blocks already produces, and A p is a block-sparse product (a few MB
-// instead of P^2 doubles per product).  A is symmetric positive definite for L > 0, the
-// preconditioner is block-Jacobi (Cholesky of the damped diagonal block of every source), which
-// removes the ill-conditioning inside a source (Sersic n / Re / Ie); what is left -- overlaps and the
-// sky row -- converges in a few dozen iterations.
+// torch.linalg.solve (fit/lm.py:359-371).  For a crowded field H = J^T W J is block-sparse: a model
+// only couples to the models its window overlaps (and to the sky), so the matrix is kept as the
+// list of <= 8x8 blocks the normal-equation kernels produce -- stored tightly (n_a x n_b doubles per
+// block: a galaxy-star block is 7x3, not 8x8) -- and A p is a block-sparse product.  A is symmetric
+// positive definite for L > 0, the preconditioner is block-Jacobi (Cholesky of the damped diagonal
+// block of every model), which removes the ill-conditioning inside a model (Sersic n / Re / Ie);
+// what is left -- overlaps and the sky row -- converges in a few dozen to a few hundred iterations.
 //
-// One launch runs the whole iteration: grid = resident CTAs, three grid barriers per iteration,
-// every CTA evaluates the (small) dot products redundantly in a fixed order, so alpha / beta and the
-// stopping decision are bit-identical in all CTAs without a broadcast.
+// One launch runs the whole iteration with TWO grid barriers per iteration:
+//   phase 1  q = A p  with  p = z + beta p_old  formed on the fly (the warp that owns a row also stores
+//            p), and the CTA's share of p.q;
+//   phase 2  alpha from the summed shares;  x += alpha p,  r -= alpha q,  z = M^-1 r  per row block, and
+//            the CTA's shares of r.z and r.r.
+// Dot products are never a pass over the vectors: every CTA writes its share, and after the barrier
+// every CTA adds the shares in the same order, so alpha, beta and the stopping decision are
+// bit-identical in all CTAs without a broadcast.  Rows whose product is split over several warps
+// (the sky row couples to every model) write per-warp partial rows that their owner adds in order:
+// no atomics, run-to-run deterministic.
 #pragma once
 #include <cooperative_groups.h>
 #include "apb_internal.cuh"
@@ -20,46 +27,47 @@
 
 namespace cg = cooperative_groups;
 
-struct PcgRow {      // row block: planes [p0, p0+n) of source `src`
-  int src, p0, n, diag_block;   // diag_block: id of its diagonal block
+struct PcgRow {      // row block: free parameters [p0, p0+n) of owner `src`
+  int src, p0, n;
+  int item0, nitem;  // its work items (nitem > 1: product split over several warps)
+  long long doff;    // offset of its diagonal block (n x n, row-major) in bvals
 };
 struct PcgEntry {    // one block contributing to a row block
-  int block;         // block id (values at bvals + 64*block, row-major [i of a][j of b])
+  long long off;     // offset of the block in bvals (row-major [i of a][j of b], leading dimension ld)
+  int ld;
   int transposed;    // 1: the row block is the block's b side
-  int slot0;         // index into act_slot of the other side's first plane
-  int n;             // planes of the other side
+  int slot0;         // index into act_slot of the other side's first parameter
+  int n;             // parameters of the other side
 };
-struct PcgItem {     // work item: entries [e0, e1) of row block rb
+struct PcgItem {     // work item (one warp): entries [e0, e1) of row block rb
   int rb, e0, e1;
-  int multi;         // 0: the only item of its row; 1: first, 2: further item of a row split over several
+  int multi;         // 0: the only item of its row; 1: first, 2: further item of a split row
 };
 
 struct PcgArgs {
   const PcgRow* rows; int n_rows;
   const PcgEntry* entries;
   const PcgItem* items; int n_items;
+  const int* multi_rows; int n_multi;   // rows split over several items
   const int* act_slot; const int* act_off;
-  const double* bvals;     // n_blocks x 64
+  const double* bvals;     // tightly packed blocks
   const double* diagH;     // P: diagonal of H
   double* fac;             // n_rows x 64: Cholesky factors of the damped diagonal blocks
   const double* b;         // right-hand side (P)
   double* x;               // solution (P)
-  double *r, *z, *p, *q;   // work vectors (P)
-  double* info;            // {iterations, final |r|/|b|, 0, 0}
+  double *r, *z, *pa, *pb, *q;   // work vectors (P)
+  double* qpart;           // n_items x 8: partial rows of split rows
+  double* part;            // gridDim x 4: per-CTA shares of the dot products
+  double* info;            // {iterations, final |r|/|b|}
   int P, max_iter;
   double L, tol;
 };
 
-// full dot product by one CTA, fixed order (identical in every CTA)
-__device__ __forceinline__ double pcg_dot(const double* __restrict__ a, const double* __restrict__ b, int n, double* sh) {
-  double v0 = 0.0, v1 = 0.0;
-  int i = threadIdx.x;
-  for (; i + 256 < n; i += 512) {
-    v0 = fma(__ldcg(a + i), __ldcg(b + i), v0);
-    v1 = fma(__ldcg(a + i + 256), __ldcg(b + i + 256), v1);
-  }
-  for (; i < n; i += 256) v0 = fma(__ldcg(a + i), __ldcg(b + i), v0);
-  double r = block_sum<256>(v0 + v1, sh);
+// sum of one column of the per-CTA shares, same order in every CTA
+__device__ __forceinline__ double pcg_total(const double* part, int col, int ncta, double* sh) {
+  double v = 0.0;
+  for (int k = threadIdx.x; k < ncta; k += 256) v += __ldcg(part + 4 * k + col);
+  double r = block_sum<256>(v, sh);
   __shared__ double bc;
   if (threadIdx.x == 0) bc = r;
   __syncthreads();
@@ -68,35 +76,25 @@ __device__ __forceinline__ double pcg_dot(const double* __restrict__ a, const do
   return r;
 }
 
-// z = M^-1 r for the diagonal block of one row block (one thread): L L^T z = r
-__device__ __forceinline__ void pcg_precond(const PcgArgs& A, int rb, const double* __restrict__ r, double* __restrict__ z) {
-  const PcgRow row = A.rows[rb];
+// z = M^-1 r for the diagonal block of one row block (one thread): L L^T z = r.  Returns r.z of the block.
+__device__ __forceinline__ double pcg_precond(const PcgArgs& A, int rb, const PcgRow& row, const double* rv, double* __restrict__ z) {
   const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
   const double* F = A.fac + (long long)rb * 64;
   double y[NB_MAX];
   for (int i = 0; i < row.n; ++i) {
-    double v = __ldcg(r + sl[i]);
+    double v = rv[i];
     for (int k = 0; k < i; ++k) v -= F[i * 8 + k] * y[k];
     y[i] = v / F[i * 8 + i];
   }
+  double dot = 0.0;
   for (int i = row.n - 1; i >= 0; --i) {
     double v = y[i];
     for (int k = i + 1; k < row.n; ++k) v -= F[k * 8 + i] * y[k];
     y[i] = v / F[i * 8 + i];
     z[sl[i]] = y[i];
+    dot = fma(rv[i], y[i], dot);
   }
-}
-
-// rows whose product is accumulated by several work items (the sky row) are zeroed one phase ahead
-__device__ __forceinline__ void pcg_zero_multi(const PcgArgs& A, int gtid, int gsz) {
-  for (int k = gtid; k < A.n_items; k += gsz) {
-    const PcgItem w = A.items[k];
-    if (w.multi == 1) {   // first item of a split row
-      const PcgRow row = A.rows[w.rb];
-      const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
-      for (int i = 0; i < row.n; ++i) A.q[sl[i]] = 0.0;
-    }
-  }
+  return dot;
 }
 
 __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
@@ -105,17 +103,19 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = gtid >> 5, nwarp = gsz >> 5;
+  const int ncta = gridDim.x;
   const double inv1L = 1.0 / (1.0 + A.L);
 
-  // ---- setup: Cholesky of every damped diagonal block; x = 0, r = b, z = M^-1 r, p = z
+  // ---- setup: Cholesky of every damped diagonal block; x = 0, r = b, z = M^-1 r, p_old = 0
+  double s_rz = 0.0, s_bb = 0.0;
   for (int rb = gtid; rb < A.n_rows; rb += gsz) {
     const PcgRow row = A.rows[rb];
-    const double* V = A.bvals + (long long)row.diag_block * 64;
+    const double* V = A.bvals + row.doff;
     double* F = A.fac + (long long)rb * 64;
     double M[NB_MAX][NB_MAX];
     for (int i = 0; i < row.n; ++i)
       for (int j = 0; j <= i; ++j) {
-        const double h = V[i * 8 + j];
+        const double h = V[i * row.n + j];
         M[i][j] = (i == j) ? h + A.L * (1.0 + h) : h * inv1L;
       }
     for (int j = 0; j < row.n; ++j) {
@@ -132,22 +132,32 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
     for (int i = 0; i < row.n; ++i)
       for (int j = 0; j <= i; ++j) F[i * 8 + j] = M[i][j];
     const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+    double rv[NB_MAX];
     for (int i = 0; i < row.n; ++i) {
+      const double bi = A.b[sl[i]];
+      rv[i] = bi;
       A.x[sl[i]] = 0.0;
-      A.r[sl[i]] = A.b[sl[i]];
+      A.r[sl[i]] = bi;
+      A.pa[sl[i]] = 0.0;
+      s_bb = fma(bi, bi, s_bb);
     }
-    pcg_precond(A, rb, A.b, A.z);
-    for (int i = 0; i < row.n; ++i) A.p[sl[i]] = A.z[sl[i]];
+    s_rz += pcg_precond(A, rb, row, rv, A.z);
   }
-  pcg_zero_multi(A, gtid, gsz);
+  {
+    const double t0 = block_sum<256>(s_rz, sh), t1 = block_sum<256>(s_bb, sh);
+    if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
+  }
   grid.sync();
-  double rz = pcg_dot(A.r, A.z, A.P, sh);
-  const double bb = pcg_dot(A.b, A.b, A.P, sh);
-  double rr = bb;
+  double rz = pcg_total(A.part, 1, ncta, sh);
+  const double bb = pcg_total(A.part, 2, ncta, sh);
+  double rr = bb, beta = 0.0;
+  double* pold = A.pa;
+  double* pnew = A.pb;
   int it = 0;
   if (bb > 0.0) {
-    for (; it < A.max_iter; ++it) {
-      // ---- q = A p: one warp per work item
+    for (; it < A.max_iter;) {
+      // ---- phase 1: p = z + beta p_old (on the fly), q = A p, share of p.q.  One warp per work item.
+      double s_pq = 0.0;
       for (int k = gwarp; k < A.n_items; k += nwarp) {
         const PcgItem w = A.items[k];
         const PcgRow row = A.rows[w.rb];
@@ -155,12 +165,16 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         double acc = 0.0;
         for (int e = w.e0; e < w.e1; ++e) {
           const PcgEntry en = A.entries[e];
-          const double* V = A.bvals + (long long)en.block * 64;
+          const double* V = A.bvals + en.off;
           const int* so = A.act_slot + en.slot0;
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
             const int j = 2 * jg + jj;
-            if (j < en.n && i < row.n) acc = fma(en.transposed ? V[j * 8 + i] : V[i * 8 + j], __ldcg(A.p + so[j]), acc);
+            if (j < en.n && i < row.n) {
+              const int sj = so[j];
+              const double pj = fma(beta, __ldcg(pold + sj), __ldcg(A.z + sj));
+              acc = fma(en.transposed ? V[j * en.ld + i] : V[i * en.ld + j], pj, acc);
+            }
           }
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 8);
@@ -168,42 +182,81 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         if (lane < row.n) {
           const int sl = A.act_slot[A.act_off[row.src] + row.p0 + lane];
           double v = acc * inv1L;
-          if (w.multi < 2) {   // the damped diagonal, once per row
+          if (w.multi < 2) {   // the row's first (or only) item: the damped diagonal, and it stores p
+            const double pi = fma(beta, __ldcg(pold + sl), __ldcg(A.z + sl));
             const double d = A.diagH[sl];
-            v += (d + A.L * (1.0 + d) - d * inv1L) * __ldcg(A.p + sl);
+            v += (d + A.L * (1.0 + d) - d * inv1L) * pi;
+            pnew[sl] = pi;
+            if (!w.multi) {
+              A.q[sl] = v;
+              s_pq = fma(pi, v, s_pq);
+            }
           }
-          if (w.multi) atomicAdd(A.q + sl, v);
-          else A.q[sl] = v;
+          if (w.multi) A.qpart[(long long)k * 8 + lane] = v;
         }
       }
+      {
+        const double t0 = block_sum<256>(s_pq, sh);
+        if (threadIdx.x == 0) A.part[4 * blockIdx.x + 0] = t0;
+      }
       grid.sync();
-      // ---- alpha; x += alpha p; r -= alpha q; z = M^-1 r
-      const double pq = pcg_dot(A.p, A.q, A.P, sh);
+      // ---- alpha (split rows: their partial rows are added in item order by every CTA alike)
+      double pq = pcg_total(A.part, 0, ncta, sh);
+      {
+        double extra = 0.0;
+        if (threadIdx.x == 0)
+          for (int m = 0; m < A.n_multi; ++m) {
+            const PcgRow row = A.rows[A.multi_rows[m]];
+            const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+            for (int i = 0; i < row.n; ++i) {
+              double qi = 0.0;
+              for (int t = 0; t < row.nitem; ++t) qi += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
+              extra = fma(__ldcg(pnew + sl[i]), qi, extra);
+            }
+          }
+        __shared__ double bc2;
+        if (threadIdx.x == 0) bc2 = extra;
+        __syncthreads();
+        pq += bc2;
+        __syncthreads();
+      }
+      if (!(pq > 0.0)) break;
       const double alpha = rz / pq;
+      // ---- phase 2: x += alpha p; r -= alpha q; z = M^-1 r; shares of r.z and r.r
+      double s_rz2 = 0.0, s_rr = 0.0;
       for (int rb = gtid; rb < A.n_rows; rb += gsz) {
         const PcgRow row = A.rows[rb];
         const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+        double rv[NB_MAX];
         for (int i = 0; i < row.n; ++i) {
           const int s = sl[i];
-          A.x[s] = fma(alpha, A.p[s], A.x[s]);
-          A.r[s] = fma(-alpha, __ldcg(A.q + s), A.r[s]);
+          double qi;
+          if (row.nitem > 1) {
+            qi = 0.0;
+            for (int t = 0; t < row.nitem; ++t) qi += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
+          } else {
+            qi = __ldcg(A.q + s);
+          }
+          A.x[s] = fma(alpha, __ldcg(pnew + s), A.x[s]);
+          const double ri = fma(-alpha, qi, A.r[s]);
+          A.r[s] = ri;
+          rv[i] = ri;
+          s_rr = fma(ri, ri, s_rr);
         }
-        pcg_precond(A, rb, A.r, A.z);
+        s_rz2 += pcg_precond(A, rb, row, rv, A.z);
+      }
+      {
+        const double t0 = block_sum<256>(s_rz2, sh), t1 = block_sum<256>(s_rr, sh);
+        if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
       }
       grid.sync();
-      // ---- beta; p = z + beta p
-      const double rz_new = pcg_dot(A.r, A.z, A.P, sh);
-      rr = pcg_dot(A.r, A.r, A.P, sh);
-      if (!(rr > A.tol * A.tol * bb) || !(pq > 0.0)) { ++it; break; }
-      const double beta = rz_new / rz;
+      const double rz_new = pcg_total(A.part, 1, ncta, sh);
+      rr = pcg_total(A.part, 2, ncta, sh);
+      ++it;
+      if (!(rr > A.tol * A.tol * bb)) break;
+      beta = rz_new / rz;
       rz = rz_new;
-      for (int rb = gtid; rb < A.n_rows; rb += gsz) {
-        const PcgRow row = A.rows[rb];
-        const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
-        for (int i = 0; i < row.n; ++i) A.p[sl[i]] = fma(beta, A.p[sl[i]], A.z[sl[i]]);
-      }
-      pcg_zero_multi(A, gtid, gsz);
-      grid.sync();
+      double* t = pold; pold = pnew; pnew = t;
     }
   }
   if (gtid == 0) {

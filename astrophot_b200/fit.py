@@ -130,7 +130,14 @@ class LM(BaseOptimizer):
         P = len(self.current_state)
         self.ndf = max(1.0, n_keep - P) if ndf is None else ndf
         dev = self.current_state.device
-        self._H = torch.empty(P, P, dtype=torch.float64, device=dev)
+        self._small_solver_max = kwargs.get("small_solver_max", 159)   # single-CTA device solver up to this P
+        self._sparse_solver = bool(kwargs.get("sparse_solver", True))
+        # Large systems with a block-sparse form (crowded fields) never build the dense P x P matrix: the PCG works on
+        # the <= 8x8 blocks inside the plan.  It is allocated (and that iteration's normal equations redone) only if
+        # a dense fallback solve is ever needed.
+        self._dense = not (self._sparse_solver and P > self._small_solver_max and self.plan.block_doubles() > 0
+                           and P > kwargs.get("dense_hess_max", 4096))
+        self._H = torch.empty(P, P, dtype=torch.float64, device=dev) if self._dense else None
         self._g = torch.empty(P, dtype=torch.float64, device=dev)
         self._c2 = torch.empty(2, dtype=torch.float64, device=dev)
         self._rpp = torch.empty(P, dtype=torch.float64, device=dev)
@@ -150,9 +157,7 @@ class LM(BaseOptimizer):
             self.plan2 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
                               share=self.plan)
         self.hess = self.grad = None
-        self._small_solver_max = kwargs.get("small_solver_max", 159)   # single-CTA device solver up to this P
         self._hess_version, self._factor_key, self._factor = 0, None, None
-        self._sparse_solver = bool(kwargs.get("sparse_solver", True))
         self._blocks_version = -1       # _hess_version whose blocks the plan holds (set by _step, not by natural-units builds)
         # sharded fit of a large system: the ranks merge their normal equations as the block-sparse J^T W J
         # (a few MB, same owner layout on every rank) instead of the dense P x P matrix
@@ -227,6 +232,15 @@ class LM(BaseOptimizer):
                 self.pcg_iterations.append(int(its))
                 if rel <= 1e-10:
                     return h
+        if self._H is None:
+            # first dense fallback of a fit that ran on the blocks alone: build the dense matrix of this iteration
+            self._H = torch.empty(P, P, dtype=torch.float64, device=rhs.device)
+            g = torch.empty_like(self._g)
+            self.plan.normal_eq(self._x_hess, as_rep=True, out=(self._H, g, torch.empty_like(self._c2)))
+            if self._blk is not None:
+                self._allreduce(self._blk)     # the rebuild overwrote the merged blocks with this rank's
+            self.hess = self._H
+            self._hess_reduced = not self.distributed
         if self.distributed and not self._hess_reduced:
             self._allreduce(self._H)
             self._hess_reduced = True
@@ -268,6 +282,7 @@ class LM(BaseOptimizer):
     def _step(self, chi2):
         """Normal equations once, then search over the damping parameter."""
         x = self.current_state
+        self._x_hess = x
         self.plan.normal_eq(x, as_rep=True, out=(self._H, self._g, self._c2))
         self.n_forward += 1
         self.n_jacobian += 1
@@ -275,7 +290,7 @@ class LM(BaseOptimizer):
             if self._blk is not None:
                 self._allreduce(self._blk)     # the dense copy stays local until a dense fallback asks for it
                 self._hess_reduced = False
-            else:
+            elif self._H is not None:
                 self._allreduce(self._H)
             self._allreduce(self._g)
         self.hess, self.grad = self._H, self._g

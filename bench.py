@@ -142,7 +142,43 @@ def build_crowded(ap, workload, data=None):
     return M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
 
 
+C5 = {"c5": (16384, 10000), "c5s": (2048, 156), "c5t": (512, 10)}     # size, galaxies
+C5_PROF = [0.0, 1.0, 2.0, 3.0, 4.5, 6.5, 9.0, 12.0, 16.0, 22.0, 30.0, 42.0]
+
+
+def build_mosaic(ap, workload, data=None):
+    """BASELINE config[4]: low-surface-brightness mosaic, galaxies in 96^2 windows (70 % Sersic, 30 % spline
+    galaxy models with 12 radii) plus a flat sky, no PSF.  `c5s` / `c5t` are scale models with the same density."""
+    size, n_gal = C5[workload]
+    rng = np.random.default_rng(5)
+    kw = {} if data is None else {"variance": data["variance"]}
+    tar = ap.image.Target_Image(data=np.zeros((size, size)) if data is None else data["data"], pixelscale=1.0,
+                                zeropoint=22.5, **kw)
+    M = ap.models.AstroPhot_Model
+    models = []
+    prof = np.array(C5_PROF)
+    for k in range(n_gal):
+        cx, cy = rng.uniform(50, size - 50, size=2)
+        win = [[int(cx) - 48, int(cx) + 48], [int(cy) - 48, int(cy) + 48]]
+        q, pa, n, re, ie = rng.uniform(0.4, 0.9), rng.uniform(0, np.pi), rng.uniform(1, 4), rng.uniform(3, 12), rng.uniform(0, 1)
+        if rng.uniform() < 0.7:
+            models.append(M(name=f"g{k}", model_type="sersic galaxy model", target=tar, window=win,
+                            parameters={"center": [cx, cy], "q": q, "PA": pa, "n": n, "Re": re, "Ie": ie}))
+        else:
+            bn = 2 * n - 1 / 3
+            val = ie - bn * ((np.maximum(prof, 0.05) / re) ** (1 / n) - 1) / np.log(10)
+            models.append(M(name=f"s{k}", model_type="spline galaxy model", target=tar, window=win,
+                            parameters={"center": [cx, cy], "q": q, "PA": pa,
+                                        "I(R)": {"value": [float(v) for v in val], "prof": [float(r) for r in prof]}}))
+    sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": -2.0})
+    sky.initialize()
+    models.append(sky)
+    return M(name="mosaic", model_type="group model", models=models, target=tar)
+
+
 def build_workload(ap, workload, n_bands, datas):
+    if workload in C5:
+        return build_mosaic(ap, workload, None if datas is None else datas[0])
     if workload == "c2":
         return build_joint(ap, n_bands, datas)
     if workload == "c4":
@@ -168,6 +204,11 @@ def workload_text(workload, n_bands, world=1):
         return (f"c4: {C4_BANDS}-band joint fit (shared centre/q/PA/n/Re, per-band Ie), PSF-convolved Sersic on "
                 f"{C4_SIZE}x{C4_SIZE} per band, {C4_PSF}x{C4_PSF} Gaussian PSF per band, threshold sub-pixel integration, "
                 f"LM fp64, {C4_BANDS // world} band(s) per GPU")
+    if workload in C5:
+        size, n_gal = C5[workload]
+        return (f"{workload}: LSB mosaic, {n_gal} galaxies in 96^2 windows (70 % Sersic, 30 % spline with 12 radii) + flat sky "
+                f"on {size}x{size}, no PSF, threshold sub-pixel integration, LM fp64"
+                + (f", image cut into {TILES[world][0]}x{TILES[world][1]} tiles, one per GPU" if world > 1 else ""))
     if workload == "c2":
         return (f"c2 x {n_bands} band(s): PSF-convolved Sersic, {SIZE}x{SIZE} per band, {PSF_W}x{PSF_W} Moffat PSF, "
                 "threshold sub-pixel integration, LM fp64, joint fit sharded 1 band/GPU")
@@ -274,6 +315,8 @@ def cpu_scene(workload="c2"):
 
     if workload in ("c3", "c3s"):
         workload = "c3t"
+    if workload in ("c5", "c5s"):
+        workload = "c5t"
     dev = ap.AP_config.ap_device
     ap.AP_config.ap_device = "cpu"
     try:
@@ -297,6 +340,10 @@ def cpu_scale(workload):
     if workload in ("c3", "c3s"):
         k = 64 if workload == "c3" else 4
         return 1.0 / k, (f" on the scale model c3t (512^2, 15 Sersic + 78 points + sky, P = 340), divided by {k} "
+                         f"(linear extrapolation to {workload}: EXTRAPOLATED)")
+    if workload in ("c5", "c5s"):
+        k = 1024 if workload == "c5" else 16
+        return 1.0 / k, (f" on the scale model c5t (512^2, 10 galaxies + sky), divided by {k} "
                          f"(linear extrapolation to {workload}: EXTRAPOLATED)")
     if workload == "c4":
         return 1.0 / C4_BANDS, f" on ONE band of the {C4_BANDS}-band joint fit (2048^2, P = 7), divided by {C4_BANDS} (EXTRAPOLATED)"
@@ -444,7 +491,7 @@ def run_ours(args):
     ap.AP_config.ap_device = f"cuda:{local}"
     dev = torch.device("cuda", local)
     wl = args.workload
-    crowded = wl in C3
+    crowded = wl in C3 or wl in C5        # one big image: cut into tiles at N > 1
     if crowded and world not in TILES:
         raise SystemExit("the crowded field is cut into 1, 2, 4 or 8 tiles")
     if wl == "c4" and C4_BANDS % world:
@@ -667,7 +714,9 @@ def run_ours(args):
                    "kernel_timing": "second pass of the same K iterations with CUDA events around every launch "
                                     f"({profiled_ms / args.steps:.3f} ms/step with the event records)",
                    "params": len(x0), "lambda_trials_per_iter": trials / args.steps, "forwards_per_iter": forwards / args.steps,
-                   "fit_restarts": state["restarts"]},
+                   "fit_restarts": state["restarts"],
+                   "pcg_iterations_mean": (float(np.mean(lm.pcg_iterations)) if lm.pcg_iterations else None),
+                   "pcg_solves": len(lm.pcg_iterations), "block_array_doubles": plan.block_doubles()},
         "clocks": clock_summary,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_pin.numel() * 8},
         "gpu_launches": launches,
@@ -690,9 +739,10 @@ def main():
     ap_.add_argument("--steps", type=int, default=100)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap_.add_argument("--workload", default="c2", choices=["c2", "c3t", "c3s", "c3", "c4"],
+    ap_.add_argument("--workload", default="c2", choices=["c2", "c3t", "c3s", "c3", "c4", "c5t", "c5s", "c5"],
                      help="c2 = BASELINE config[1] (default, the metric's configuration); c3 = config[2] crowded field, "
-                          "c3s / c3t = its 1024^2 / 512^2 scale models; c4 = config[3], 8-band joint fit on 2048^2")
+                          "c3s / c3t = its 1024^2 / 512^2 scale models; c4 = config[3], 8-band joint fit on 2048^2; c5 = config[4], 16384^2 mosaic with 10000 galaxies, c5s / c5t its "
+                          "2048^2 / 512^2 scale models")
     ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap_.add_argument("--conv", default=None, choices=["direct", "fft"],
                      help="force one PSF-convolution kernel family (default: automatic, FFT for the 51x51 PSF)")

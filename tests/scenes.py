@@ -156,6 +156,20 @@ def build(ap, name, data=None):
                parameters={"center": [55.2, 47.9], "q": 0.8, "PA": 2.5, "Re": 6.0, "Ie": 0.5})
         g = M(name="grp2", model_type="group model", models=[m1, m2], target=tar, psf_mode="full")
         return g, {}
+    if name == "group_meanref":
+        # compact sources with the mean-of-window integration reference inside a much larger group window: the far
+        # field of each profile is below the rounding of that mean (the device skips it, the reference sums it)
+        tar = _target(ap, (120, 128), data)
+        m1 = M(name="mg", model_type="gaussian galaxy model", target=tar, window=[[20, 52], [30, 62]],
+               parameters={"center": [36.3, 45.8], "q": 0.8, "PA": 0.6, "sigma": 1.6, "flux": 2.0})
+        m2 = M(name="me", model_type="exponential galaxy model", target=tar, window=[[70, 110], [60, 100]],
+               parameters={"center": [90.4, 80.1], "q": 0.7, "PA": 2.0, "Re": 1.2, "Ie": 1.5})
+        prof = [0.0, 0.8, 1.6, 2.5, 3.5, 5.0]
+        val = [2.0, 1.7, 1.1, 0.2, -1.0, -3.0]
+        m3 = M(name="ms", model_type="spline galaxy model", target=tar, window=[[40, 80], [8, 48]],
+               parameters={"center": [60.2, 27.7], "q": 0.9, "PA": 1.1, "I(R)": {"value": val, "prof": prof}})
+        g = M(name="grp3", model_type="group model", models=[m1, m2, m3], target=tar)
+        return g, {}
     if name == "joint":
         tars, models = [], []
         for b in range(3):
@@ -208,7 +222,7 @@ def build(ap, name, data=None):
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
-                 "aux_psf_gauss_noshift", "sersic_trapezoid"]
+                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12}
 
