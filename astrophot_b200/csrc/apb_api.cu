@@ -135,7 +135,10 @@ struct apb_plan {
   PcgItem* d_pitems = nullptr; int n_pitems = 0;
   double *d_bvals = nullptr, *d_diagH = nullptr, *d_pfac = nullptr, *d_pvec = nullptr;
   double* d_bvals_own = nullptr;   // the plan's own [blocks | diag H] array (d_bvals may point at a caller's, apb_plan_bind_blocks)
-  long long n_cblocks = 0;
+  long long n_cblocks = 0, n_bvals = 0;   // owner blocks; doubles they occupy (packed n_a x n_b each)
+  int* d_multi_rows = nullptr; int n_multi = 0;
+  double *d_qpart = nullptr, *d_pcg_part = nullptr;
+  unsigned int* d_pcg_bar = nullptr;
   int *d_own_slot = nullptr, *d_own_off = nullptr;   // free-parameter lists of the owners (PCG rows are owner rows)
   int pcg_grid = 0;
   double *d_xtmp = nullptr, *d_xtmp2 = nullptr, *d_rpp = nullptr, *d_atmp = nullptr, *d_atmp2 = nullptr, *d_rec2 = nullptr;
@@ -688,7 +691,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     std::vector<BlockDesc> blocks, vblocks;
     auto add_block = [&](int a, int b, int pa0, int na, int pb0, int nb, int diag, int x0, int y0, int w, int h,
                          std::vector<BlockItem>& it, std::vector<BlockDesc>& bl) {
-      BlockDesc bd{a, b, pa0, na, pb0, nb, diag, (int)it.size(), 0, -1, 0};
+      BlockDesc bd{a, b, pa0, na, pb0, nb, diag, (int)it.size(), 0, -1, 0, 0};
       const int rows = std::max(1, 2048 / std::max(w, 1));
       for (int r = 0; r < h; r += rows) {
         BlockItem bi{a, b, pa0, na, pb0, nb, x0, y0 + r, w, std::min(rows, h - r), diag, (int)bl.size()};
@@ -791,7 +794,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           if (uses[k] == 0) ok = false;   // a free parameter no model depends on: singular block, leave it to the dense path
       }
       if (ok) {
-        struct CB { int oa, ob, pa0, na, pb0, nb, diag; };
+        struct CB { int oa, ob, pa0, na, pb0, nb, diag; long long off; };
         std::vector<CB> cbs;
         std::unordered_map<unsigned long long, int> cb_of;
         const unsigned long long KR = (unsigned long long)n_own * RPS;
@@ -799,7 +802,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         auto nact = [&](int o) { return own_off[o + 1] - own_off[o]; };
         auto add_cb = [&](int oa, int pa0, int ob, int pb0, int diag) {
           cb_of[key(oa, pa0 / NB_MAX, ob, pb0 / NB_MAX)] = (int)cbs.size();
-          cbs.push_back(CB{oa, ob, pa0, std::min(NB_MAX, nact(oa) - pa0), pb0, std::min(NB_MAX, nact(ob) - pb0), diag});
+          CB c{oa, ob, pa0, std::min(NB_MAX, nact(oa) - pa0), pb0, std::min(NB_MAX, nact(ob) - pb0), diag, p->n_bvals};
+          p->n_bvals += (long long)c.na * c.nb;
+          cbs.push_back(c);
         };
         for (int o = 0; o < n_own; ++o)
           for (int pa0 = 0; pa0 < nact(o); pa0 += NB_MAX)
@@ -855,7 +860,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           if (oa > ob) { std::swap(oa, ob); std::swap(pa0, pb0); tr = 1; }
           auto itb = cb_of.find(key(oa, pa0 / NB_MAX, ob, pb0 / NB_MAX));
           if (itb == cb_of.end()) PFAIL("owner table: two sources overlap but their owners' windows do not");
-          bd.cblock = itb->second; bd.ctrans = tr;
+          bd.coff = cbs[itb->second].off; bd.cld = cbs[itb->second].nb; bd.ctrans = tr;
         }
         std::vector<PcgRow> prows;
         std::vector<std::vector<PcgEntry>> ents;
@@ -864,24 +869,34 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           const CB& cb = cbs[k];
           if (!cb.diag) continue;
           row_of[(size_t)cb.oa * RPS + cb.pa0 / NB_MAX] = (int)prows.size();
-          prows.push_back(PcgRow{cb.oa, cb.pa0, cb.na, (int)k});
+          prows.push_back(PcgRow{cb.oa, cb.pa0, cb.na, 0, 0, cb.off});
           ents.emplace_back();
         }
         for (size_t k = 0; k < cbs.size(); ++k) {
           const CB& cb = cbs[k];
           const int ra = row_of[(size_t)cb.oa * RPS + cb.pa0 / NB_MAX], rb = row_of[(size_t)cb.ob * RPS + cb.pb0 / NB_MAX];
-          ents[ra].push_back(PcgEntry{(int)k, 0, own_off[cb.ob] + cb.pb0, cb.nb});
-          if (!cb.diag) ents[rb].push_back(PcgEntry{(int)k, 1, own_off[cb.oa] + cb.pa0, cb.na});
+          PcgEntry ea{cb.off, cb.nb, 0, cb.nb, {0}}, eb{cb.off, cb.nb, 1, cb.na, {0}};
+          for (int j = 0; j < cb.nb; ++j) ea.sl[j] = own_slot[own_off[cb.ob] + cb.pb0 + j];
+          for (int j = 0; j < cb.na; ++j) eb.sl[j] = own_slot[own_off[cb.oa] + cb.pa0 + j];
+          ents[ra].push_back(ea);
+          if (!cb.diag) ents[rb].push_back(eb);
         }
         std::vector<PcgEntry> flat;
         std::vector<PcgItem> pitems;
-        const int CH = 32;
+        std::vector<int> multi_rows;
+        // a row is one warp's work unless it has very many blocks (the sky row couples to every model): then it is
+        // split into chunks whose partial rows the solver adds in order
+        const int CH = 128, SPLIT = 512;
         for (size_t r = 0; r < prows.size(); ++r) {
           const int e0 = (int)flat.size();
           flat.insert(flat.end(), ents[r].begin(), ents[r].end());
           const int e1 = (int)flat.size();
-          const bool multi = e1 - e0 > CH;
-          for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), multi ? (e == e0 ? 1 : 2) : 0});
+          const bool multi = e1 - e0 > SPLIT;
+          prows[r].item0 = (int)pitems.size();
+          if (!multi) pitems.push_back(PcgItem{(int)r, e0, e1, 0});
+          else for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), e == e0 ? 1 : 2});
+          prows[r].nitem = (int)pitems.size() - prows[r].item0;
+          if (multi) multi_rows.push_back((int)r);
         }
         p->n_prows = (int)prows.size(); p->n_pitems = (int)pitems.size();
         p->n_cblocks = (long long)cbs.size();
@@ -890,8 +905,10 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         PRC(own_upload(p, pitems, &p->d_pitems));
         PRC(own_upload(p, own_slot, &p->d_own_slot));
         PRC(own_upload(p, own_off, &p->d_own_off));
-        PRC(own_alloc(p, (void**)&p->d_bvals_own, sizeof(double) * (64 * (size_t)p->n_cblocks + (size_t)n_par)));
-        p->d_bvals = p->d_bvals_own; p->d_diagH = p->d_bvals + 64 * p->n_cblocks;
+        PRC(own_upload(p, multi_rows, &p->d_multi_rows)); p->n_multi = (int)multi_rows.size();
+        PRC(own_alloc(p, (void**)&p->d_qpart, sizeof(double) * 8 * std::max<size_t>(pitems.size(), 1)));
+        PRC(own_alloc(p, (void**)&p->d_bvals_own, sizeof(double) * ((size_t)p->n_bvals + (size_t)n_par)));
+        p->d_bvals = p->d_bvals_own; p->d_diagH = p->d_bvals + p->n_bvals;
         PRC(own_alloc(p, (void**)&p->d_pfac, sizeof(double) * 64 * std::max<size_t>(prows.size(), 1)));
         PRC(own_alloc(p, (void**)&p->d_pvec, sizeof(double) * 5 * (size_t)n_par));
         int dev = 0, sms = 148, per_sm = 1;
@@ -901,6 +918,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
         const int want = std::max(1, std::min(sms * std::min(per_sm, 2), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
         p->pcg_grid = want;
+        PRC(own_alloc(p, (void**)&p->d_pcg_part, sizeof(double) * 4 * (size_t)want));
+        PRC(own_alloc(p, (void**)&p->d_pcg_bar, sizeof(unsigned int)));
         p->sparse_ok = true;
       } else if (tabled) {
         PFAIL("owner table: a free parameter belongs to no owner or to several");
@@ -1257,7 +1276,7 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
   if (!JtWJ && !p->sparse_ok) APB_FAIL("apb_normal_eq: JtWJ may only be NULL when the plan has a block-sparse form");
   if (JtWJ) CU(cudaMemsetAsync(JtWJ, 0, sizeof(double) * (size_t)P * P, st));
   CU(cudaMemsetAsync(JtWr, 0, sizeof(double) * (size_t)P, st));
-  if (p->sparse_ok) CU(cudaMemsetAsync(p->d_bvals, 0, sizeof(double) * (64 * (size_t)p->n_cblocks + (size_t)P), st));
+  if (p->sparse_ok) CU(cudaMemsetAsync(p->d_bvals, 0, sizeof(double) * ((size_t)p->n_bvals + (size_t)P), st));
   if (p->n_items) {
     PB(K_BLOCKS);
     k_blocks<<<p->n_items, 256, 0, st>>>(p->d_src, p->d_img, p->d_items, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid,
@@ -1424,10 +1443,12 @@ extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, dou
   if (!p->sparse_ok) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = (size_t)p->n_par;
-  PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_own_slot, p->d_own_off,
-            p->d_bvals, p->d_diagH, p->d_pfac, g, h, p->d_pvec, p->d_pvec + P, p->d_pvec + 2 * P, p->d_pvec + 3 * P,
+  PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_multi_rows, p->n_multi,
+            p->d_own_slot, p->d_own_off, p->d_bvals, p->d_diagH, p->d_pfac, g, h, p->d_pvec, p->d_pvec + P,
+            p->d_pvec + 2 * P, p->d_pvec + 3 * P, p->d_pvec + 4 * P, p->d_qpart, p->d_pcg_part, p->d_pcg_bar,
             info, p->n_par, max_iter > 0 ? max_iter : 2000, L, tol > 0.0 ? tol : 1e-14};
   void* args[] = {&A};
+  CU(cudaMemsetAsync(p->d_pcg_bar, 0, sizeof(unsigned int), st));
   p->pbegin(K_PCG, st);
   CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(256), args, 0, st));
   p->pend(st);
@@ -1437,14 +1458,14 @@ extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, dou
 
 extern "C" long long apb_plan_block_doubles(apb_plan_t* p) {
   if (!p || !p->sparse_ok) return 0;
-  return 64 * p->n_cblocks + (long long)p->n_par;
+  return p->n_bvals + (long long)p->n_par;
 }
 
 extern "C" int apb_plan_bind_blocks(apb_plan_t* p, double* buf) {
   if (!p) APB_FAIL("plan is NULL");
   if (!p->sparse_ok) APB_FAIL("apb_plan_bind_blocks: the plan has no block-sparse form");
   p->d_bvals = buf ? buf : p->d_bvals_own;
-  p->d_diagH = p->d_bvals + 64 * p->n_cblocks;
+  p->d_diagH = p->d_bvals + p->n_bvals;
   return 0;
 }
 

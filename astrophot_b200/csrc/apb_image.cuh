@@ -454,7 +454,10 @@ __global__ void __launch_bounds__(256) k_blocks(const DevSrc* __restrict__ src, 
 // block descriptor: its items are contiguous [item0, item0+nitem)
 struct BlockDesc {
   int a, b, pa0, na, pb0, nb, diag, item0, nitem;
-  int cblock, ctrans;   // block of the owner-level sparse matrix this one adds into (-1: none); 1: transposed
+  // block of the owner-level sparse matrix this one adds into: offset in the packed block array (-1: none), its leading
+  // dimension (parameters of its b side), 1: transposed
+  long long coff;
+  int cld, ctrans;
 };
 
 // grid (blocks, BLK_VALS/8): one warp per value of a block; its lanes stride over the block's partials
@@ -498,10 +501,10 @@ __global__ void __launch_bounds__(256) k_block_final(const DevSrc* __restrict__ 
       atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
       if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
     }
-    if (bvals && bd.cblock >= 0) {
+    if (bvals && bd.coff >= 0) {
       // block-sparse copy for the PCG solver (apb_solve.cuh), zeroed before this launch.  One writer per value
       // (exact) unless a model is cut into tiles: its pieces add into the same owner block.
-      atomicAdd(&bvals[(long long)bd.cblock * (NB_MAX * NB_MAX) + (bd.ctrans ? j * NB_MAX + i : i * NB_MAX + j)], tot);
+      atomicAdd(&bvals[bd.coff + (bd.ctrans ? j * bd.cld + i : i * bd.cld + j)], tot);
       if (bd.diag && i == j) atomicAdd(&diagH[sa[i]], tot);
     }
   }

@@ -36,8 +36,8 @@ struct PcgEntry {    // one block contributing to a row block
   long long off;     // offset of the block in bvals (row-major [i of a][j of b], leading dimension ld)
   int ld;
   int transposed;    // 1: the row block is the block's b side
-  int slot0;         // index into act_slot of the other side's first parameter
   int n;             // parameters of the other side
+  int sl[NB_MAX];    // their indices in x (held here: one dependent load less per product)
 };
 struct PcgItem {     // work item (one warp): entries [e0, e1) of row block rb
   int rb, e0, e1;
@@ -58,10 +58,29 @@ struct PcgArgs {
   double *r, *z, *pa, *pb, *q;   // work vectors (P)
   double* qpart;           // n_items x 8: partial rows of split rows
   double* part;            // gridDim x 4: per-CTA shares of the dot products
+  unsigned int* barrier;   // arrival counter of pcg_barrier, zero at launch
   double* info;            // {iterations, final |r|/|b|}
   int P, max_iter;
   double L, tol;
 };
+
+// Grid barrier for the (cooperatively launched, hence co-resident) CTAs of k_pcg.  cooperative_groups' grid.sync()
+// invalidates the whole L1 at every barrier, which sends every load of the solver's read-only tables (work items, row
+// blocks, block values: the same ones every iteration) back to L2 -- measured: the phases were chains of ~7 dependent
+// L2 round trips.  Here the vectors that change hands between CTAs are read with ld.cg (L2) and written through, the
+// barrier is a monotonic arrival counter (zeroed before the launch), and the tables stay in L1.
+__device__ __forceinline__ void pcg_barrier(unsigned int* counter, unsigned int& goal) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    goal += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*(volatile unsigned int*)counter < goal) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
 
 // sum of one column of the per-CTA shares, same order in every CTA
 __device__ __forceinline__ double pcg_total(const double* part, int col, int ncta, double* sh) {
@@ -98,8 +117,9 @@ __device__ __forceinline__ double pcg_precond(const PcgArgs& A, int rb, const Pc
 }
 
 __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
-  cg::grid_group grid = cg::this_grid();
+  unsigned int goal = 0;
   __shared__ double sh[8];
+  __shared__ double bc2;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int gwarp = gtid >> 5, nwarp = gsz >> 5;
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
     const double t0 = block_sum<256>(s_rz, sh), t1 = block_sum<256>(s_bb, sh);
     if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
   }
-  grid.sync();
+  pcg_barrier(A.barrier, goal);
   double rz = pcg_total(A.part, 1, ncta, sh);
   const double bb = pcg_total(A.part, 2, ncta, sh);
   double rr = bb, beta = 0.0;
@@ -161,24 +181,42 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
       for (int k = gwarp; k < A.n_items; k += nwarp) {
         const PcgItem w = A.items[k];
         const PcgRow row = A.rows[w.rb];
-        const int i = lane & 7, jg = lane >> 3;
-        double acc = 0.0;
-        for (int e = w.e0; e < w.e1; ++e) {
+        // A lane per block: all blocks of a row (up to 32 per sweep) are fetched at once -- the products are tiny, what
+        // the phase costs is its chain of dependent L2 loads (item -> row -> entry -> values), so that chain is walked
+        // once per sweep, not once per block.  Lane l accumulates its blocks' contribution to all row elements; a
+        // shuffle tree adds the lanes (fixed order).
+        double racc[NB_MAX];
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) racc[i] = 0.0;
+        for (int e = w.e0 + lane; e < w.e1; e += 32) {
           const PcgEntry en = A.entries[e];
           const double* V = A.bvals + en.off;
-          const int* so = A.act_slot + en.slot0;
+          double pj[NB_MAX];
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int j = 2 * jg + jj;
-            if (j < en.n && i < row.n) {
-              const int sj = so[j];
-              const double pj = fma(beta, __ldcg(pold + sj), __ldcg(A.z + sj));
-              acc = fma(en.transposed ? V[j * en.ld + i] : V[i * en.ld + j], pj, acc);
+          for (int j = 0; j < NB_MAX; ++j) {
+            const bool on = j < en.n;
+            const int sj = en.sl[on ? j : 0];
+            pj[j] = on ? fma(beta, __ldcg(pold + sj), __ldcg(A.z + sj)) : 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < NB_MAX; ++i) {
+            if (i < row.n) {
+              double a = 0.0;
+#pragma unroll
+              for (int j = 0; j < NB_MAX; ++j)
+                if (j < en.n) a = fma(en.transposed ? V[j * en.ld + i] : V[i * en.ld + j], pj[j], a);
+              racc[i] += a;
             }
           }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) {
+          double v = racc[i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == i) acc = v;
+        }
         if (lane < row.n) {
           const int sl = A.act_slot[A.act_off[row.src] + row.p0 + lane];
           double v = acc * inv1L;
@@ -199,22 +237,24 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         const double t0 = block_sum<256>(s_pq, sh);
         if (threadIdx.x == 0) A.part[4 * blockIdx.x + 0] = t0;
       }
-      grid.sync();
-      // ---- alpha (split rows: their partial rows are added in item order by every CTA alike)
+      pcg_barrier(A.barrier, goal);
+      // ---- alpha.  Split rows: every CTA adds their partial rows (same order everywhere), stores q and adds p.q
       double pq = pcg_total(A.part, 0, ncta, sh);
       {
         double extra = 0.0;
-        if (threadIdx.x == 0)
-          for (int m = 0; m < A.n_multi; ++m) {
-            const PcgRow row = A.rows[A.multi_rows[m]];
-            const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
-            for (int i = 0; i < row.n; ++i) {
-              double qi = 0.0;
-              for (int t = 0; t < row.nitem; ++t) qi += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
+        for (int m = 0; m < A.n_multi; ++m) {
+          const PcgRow row = A.rows[A.multi_rows[m]];
+          const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+          for (int i = 0; i < row.n; ++i) {
+            double v = 0.0;
+            for (int t = threadIdx.x; t < row.nitem; t += 256) v += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
+            const double qi = block_sum<256>(v, sh);
+            if (threadIdx.x == 0) {
+              A.q[sl[i]] = qi;   // every CTA stores the same value; the row's owner reads the copy its own CTA wrote
               extra = fma(__ldcg(pnew + sl[i]), qi, extra);
             }
           }
-        __shared__ double bc2;
+        }
         if (threadIdx.x == 0) bc2 = extra;
         __syncthreads();
         pq += bc2;
@@ -230,13 +270,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         double rv[NB_MAX];
         for (int i = 0; i < row.n; ++i) {
           const int s = sl[i];
-          double qi;
-          if (row.nitem > 1) {
-            qi = 0.0;
-            for (int t = 0; t < row.nitem; ++t) qi += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
-          } else {
-            qi = __ldcg(A.q + s);
-          }
+          const double qi = __ldcg(A.q + s);
           A.x[s] = fma(alpha, __ldcg(pnew + s), A.x[s]);
           const double ri = fma(-alpha, qi, A.r[s]);
           A.r[s] = ri;
@@ -249,7 +283,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         const double t0 = block_sum<256>(s_rz2, sh), t1 = block_sum<256>(s_rr, sh);
         if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
       }
-      grid.sync();
+      pcg_barrier(A.barrier, goal);
       const double rz_new = pcg_total(A.part, 1, ncta, sh);
       rr = pcg_total(A.part, 2, ncta, sh);
       ++it;

@@ -55,21 +55,30 @@ def band_truth(b):
     return {"center": [SIZE / 2 + 0.3, SIZE / 2 - 0.4], "q": 0.6, "PA": 1.0, "n": 2.5, "Re": 60.0, "Ie": 1.0 + 0.1 * b}
 
 
-def build_joint(ap, n_bands, datas, size=SIZE):
+def build_joint(ap, n_bands, datas, size=SIZE, aux_psf=False):
     """n_bands PSF-convolved Sersic models sharing shape parameters
-    (docs/source/tutorials/JointModels.ipynb recipe).  datas[b] = dict(data, variance) or None."""
+    (docs/source/tutorials/JointModels.ipynb recipe).  datas[b] = dict(data, variance) or None.
+    aux_psf: the PSF is a `moffat psf model` (n = 2.5, Rd = 3.0 on a 51x51 PSF_Image grid) fitted together with
+    the galaxy (SURVEY.md §8d C2 variant B, P = 9) instead of a fixed PSF_Image."""
     psf_np = ap.utils.moffat_psf(2.5, 3.0, PSF_W, 1.0)
     tars, models = [], []
     for b in range(n_bands):
         d = datas[b] if datas is not None else None
         kw = {} if d is None else {"variance": d["variance"]}
+        if not aux_psf:
+            kw["psf"] = ap.image.PSF_Image(data=psf_np, pixelscale=1.0)
         tars.append(ap.image.Target_Image(data=np.zeros((size, size)) if d is None else d["data"], pixelscale=1.0,
-                                          zeropoint=22.5, psf=ap.image.PSF_Image(data=psf_np, pixelscale=1.0), **kw))
+                                          zeropoint=22.5, **kw))
     for b in range(n_bands):
         pars = band_truth(b)
         pars["center"] = [size / 2 + 0.3, size / 2 - 0.4]
+        kw = {}
+        if aux_psf:
+            ptar = ap.image.PSF_Image(data=np.zeros((PSF_W, PSF_W)), pixelscale=1.0)
+            kw["psf"] = ap.models.AstroPhot_Model(name=f"psf{b}", model_type="moffat psf model", target=ptar,
+                                                  parameters={"n": 2.5, "Rd": 3.0})
         m = ap.models.AstroPhot_Model(name=f"band{b}", model_type="sersic galaxy model", target=tars[b],
-                                      psf_mode="full", parameters=pars)
+                                      psf_mode="full", parameters=pars, **kw)
         if b > 0:
             for p in ("center", "q", "PA", "n", "Re"):
                 m[p].value = models[0][p]
@@ -181,6 +190,8 @@ def build_workload(ap, workload, n_bands, datas):
         return build_mosaic(ap, workload, None if datas is None else datas[0])
     if workload == "c2":
         return build_joint(ap, n_bands, datas)
+    if workload == "c2b":
+        return build_joint(ap, 1, datas, aux_psf=True)
     if workload == "c4":
         return build_c4(ap, datas) if n_bands > 1 else build_c4_band(ap, datas)
     return build_crowded(ap, workload, None if datas is None else datas[0])
@@ -209,6 +220,9 @@ def workload_text(workload, n_bands, world=1):
         return (f"{workload}: LSB mosaic, {n_gal} galaxies in 96^2 windows (70 % Sersic, 30 % spline with 12 radii) + flat sky "
                 f"on {size}x{size}, no PSF, threshold sub-pixel integration, LM fp64"
                 + (f", image cut into {TILES[world][0]}x{TILES[world][1]} tiles, one per GPU" if world > 1 else ""))
+    if workload == "c2b":
+        return (f"c2b: PSF-convolved Sersic on {SIZE}x{SIZE}, PSF = moffat psf model on a {PSF_W}x{PSF_W} grid fitted as "
+                "auxiliary parameters (P = 9), threshold sub-pixel integration, LM fp64")
     if workload == "c2":
         return (f"c2 x {n_bands} band(s): PSF-convolved Sersic, {SIZE}x{SIZE} per band, {PSF_W}x{PSF_W} Moffat PSF, "
                 "threshold sub-pixel integration, LM fp64, joint fit sharded 1 band/GPU")
@@ -230,7 +244,7 @@ def start_state(x_rep, seed=2, scale=0.05):
 
 
 def start_scale(workload):
-    return 0.05 if workload in ("c2", "c4") else 0.02
+    return 0.05 if workload in ("c2", "c2b", "c4") else 0.02
 
 
 # ---------------------------------------------------------------------------
@@ -418,7 +432,7 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
                 first_px += (ow + 2) * (oh + 2)
             continue
         ps = scene.psfs[src.psf]
-        pw = int(ps.data.shape[1])
+        pw = int(ps.data.shape[1]) if ps.data is not None else int(ps.shape[1])
         shifted = src.psf_shift != 0
         spw = pw + (2 if shifted else 0)      # bilinear-shifted stamp keeps its 1-px pad
         b = (pw + 2) // 2                     # psf_border_int = ceil((P+1)/2)
@@ -492,12 +506,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     wl = args.workload
     crowded = wl in C3 or wl in C5        # one big image: cut into tiles at N > 1
+    if wl == "c2b" and world > 1:
+        raise SystemExit("c2b is a single-band fit (replicas only)")
     if crowded and world not in TILES:
         raise SystemExit("the crowded field is cut into 1, 2, 4 or 8 tiles")
     if wl == "c4" and C4_BANDS % world:
         raise SystemExit("c4 has 8 bands: --gpus must divide 8")
     # c2: one band per GPU (weak scaling); c4: 8 bands dealt to the GPUs; c3: one image cut into `world` tiles (strong)
-    n_bands = world if wl == "c2" else (C4_BANDS if wl == "c4" else 1)
+    n_bands = world if wl == "c2" else (C4_BANDS if wl == "c4" else 1)   # c2b, c3*, c5*: one image
     scaling = "weak" if wl == "c2" else "strong"
     units_per_step = n_bands if wl == "c2" else 1
 
@@ -508,10 +524,10 @@ def run_ours(args):
         t = build_workload(ap, wl, 1, None)().data.cpu().numpy()
         datas.append(make_data(t, 10))
     else:
-        truth_model = build_workload(ap, wl, 1, None) if wl == "c2" else None
+        truth_model = build_workload(ap, wl, 1, None) if wl in ("c2", "c2b") else None
         for b in range(n_bands):
             if b % world == rank:
-                if wl == "c2":
+                if wl in ("c2", "c2b"):
                     truth_model["Ie"].value = band_truth(b)["Ie"]
                     t = truth_model().data.cpu().numpy()
                 else:
@@ -739,7 +755,7 @@ def main():
     ap_.add_argument("--steps", type=int, default=100)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap_.add_argument("--workload", default="c2", choices=["c2", "c3t", "c3s", "c3", "c4", "c5t", "c5s", "c5"],
+    ap_.add_argument("--workload", default="c2", choices=["c2", "c2b", "c3t", "c3s", "c3", "c4", "c5t", "c5s", "c5"],
                      help="c2 = BASELINE config[1] (default, the metric's configuration); c3 = config[2] crowded field, "
                           "c3s / c3t = its 1024^2 / 512^2 scale models; c4 = config[3], 8-band joint fit on 2048^2; c5 = config[4], 16384^2 mosaic with 10000 galaxies, c5s / c5t its "
                           "2048^2 / 512^2 scale models")

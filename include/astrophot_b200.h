@@ -199,13 +199,13 @@ int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, i
 int apb_lm_solve_sparse(apb_plan_t *plan, const double *g, double L, double *h, double *info, double tol,
                         int max_iter, void *stream);
 
-/* The block-sparse J^T W J of the plan as one flat array: 64 doubles per block (row-major 8x8) followed
- * by diag(J^T W J) (n_par doubles).  apb_plan_block_doubles returns its length (0: the plan has no
+/* The block-sparse J^T W J of the plan as one flat array: the blocks, tightly packed (n_a x n_b doubles each,
+ * row-major), followed by diag(J^T W J) (n_par doubles).  apb_plan_block_doubles returns its length (0: the plan has no
  * block-sparse form, see apb_lm_solve_sparse).  apb_plan_bind_blocks makes apb_normal_eq write it into a
  * caller-owned device buffer of that length instead of the plan's own, which is how a fit sharded by
  * image tile merges the ranks' normal equations: sum all-reduce of that buffer and of JtWr, then every
- * rank solves the same system (fit/lm.py:256-260 on the pixels of all ranks).  With blocks bound,
- * apb_normal_eq accepts JtWJ == NULL (no dense copy). */
+ * rank solves the same system (fit/lm.py:256-260 on the pixels of all ranks).  A plan with a block-sparse
+ * form accepts JtWJ == NULL in apb_normal_eq (no dense copy). */
 long long apb_plan_block_doubles(apb_plan_t *plan);
 int apb_plan_bind_blocks(apb_plan_t *plan, double *buf);
 

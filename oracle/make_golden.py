@@ -111,6 +111,14 @@ def main(names):
             fix["lambda_history"] = np.array(res.lambda_history)
             fix["message"] = np.array(res.message)
             print(name, "LM:", res.message, res.loss_history)
+            if name in getattr(scenes, "ITER_SCENES", ()):
+                # fit/iterative.py Iter: 3 sweeps, every sub-fit 4 LM iterations (fixed counts on both sides)
+                m3, _ = scenes.build(ap, name, data=data)
+                it = ap.fit.Iter(m3, initial_state=x0, max_iter=3,
+                                 method_kwargs={"max_iter": 4, "relative_tolerance": 0.0}).fit()
+                fix["iter_loss_history"] = np.array(it.loss_history)
+                fix["iter_lambda_history"] = np.array(it.lambda_history)
+                print(name, "Iter:", it.message, it.loss_history)
         path = os.path.join(out_dir, f"{name}.npz")
         np.savez_compressed(path, **fix)
         print(f"wrote {path}: P={len(x_val)} sum={[float(d.sum()) for d in imgs]} "

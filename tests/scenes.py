@@ -227,6 +227,9 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12}
 
 
+ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens
+
+
 def make_data(truth_images, seed):
     """Noisy data + variance from noiseless truth (tests/utils.py:73 recipe)."""
     rng = np.random.default_rng(seed)
