@@ -28,7 +28,7 @@ from . import AP_config
 from .errors import OptimizeStop
 from .lowering import lower, shard_scene, tile_scene
 
-__all__ = ["BaseOptimizer", "LM", "Iter"]
+__all__ = ["BaseOptimizer", "LM", "Iter", "Iter_LM"]
 
 
 class BaseOptimizer:
@@ -547,6 +547,95 @@ class Iter(BaseOptimizer):
     def fit(self):
         self.iteration = 0
         self.Y = self.model(parameters=self.current_state.cpu(), as_representation=True)
+        try:
+            while True:
+                self.step()
+                if self.iteration > 2 and self._count_finish >= 2:
+                    self.message = self.message + "success"
+                    break
+                elif self.iteration >= self.max_iter:
+                    self.message = self.message + f"fail max iterations reached: {self.iteration}"
+                    break
+        except KeyboardInterrupt:
+            self.message = self.message + "fail interrupted"
+        self.model.parameters.vector_set_representation(self.res())
+        return self
+
+
+class Iter_LM(BaseOptimizer):
+    """Levenberg-Marquardt on one chunk of the parameters at a time (drop-in for ``ap.fit.Iter_LM``, reference
+    `fit/iterative.py:183-338`): the parameter vector is cut into chunks (``chunks``: a size, or explicit tuples of
+    parameter identities), every chunk is fitted with the device LM while the others are held fixed
+    (``Param_Mask``), and the sweep over all chunks repeats until chi^2 stops moving.  A chunk fit is one plan
+    whose free parameters are the chunk: the fused normal equations only carry those columns."""
+
+    def __init__(self, model, initial_state=None, chunks=50, max_iter=100, method="random", LM_kwargs=None, **kwargs):
+        super().__init__(model, initial_state, max_iter=max_iter, **kwargs)
+        self.max_iter = max_iter
+        self.chunks = chunks
+        self.method = method
+        self.LM_kwargs = dict(LM_kwargs or {})
+        sub = self.model.target[self.model.window]
+        self.ndf = sub.flatten("data").numel() - len(self.current_state)
+        if self.model.target.has_mask:
+            self.ndf -= int(torch.sum(sub.flatten("mask")).item())
+        self._count_finish = 0
+
+    def step(self):
+        import random
+        from .param import Param_Mask
+
+        param_ids = list(self.model.parameters.vector_identities())
+        init_param_ids = list(param_ids)
+        chunk_index, chunk_choices, res = 0, None, None
+        if self.verbose > 0:
+            AP_config.ap_logger.info("--------iter-------")
+        while True:
+            chunk = torch.zeros(len(init_param_ids), dtype=torch.bool)
+            if isinstance(self.chunks, int):
+                if len(param_ids) == 0:
+                    break
+                picked = random.sample(param_ids, min(len(param_ids), self.chunks)) if self.method == "random" \
+                    else param_ids[: self.chunks]
+                for pid in picked:
+                    chunk[init_param_ids.index(pid)] = True
+                for pid in np.array(init_param_ids)[chunk.numpy()]:
+                    param_ids.pop(param_ids.index(pid))
+            elif isinstance(self.chunks, (tuple, list)):
+                if chunk_choices is None:
+                    chunk_choices = list(range(len(self.chunks)))
+                if self.method == "random":
+                    if len(chunk_choices) == 0:
+                        break
+                    sub_index = random.choice(chunk_choices)
+                    chunk_choices.pop(chunk_choices.index(sub_index))
+                    for pid in self.chunks[sub_index]:
+                        chunk[param_ids.index(pid)] = True
+                else:
+                    if chunk_index >= len(self.chunks):
+                        break
+                    for pid in self.chunks[chunk_index]:
+                        chunk[param_ids.index(pid)] = True
+                    chunk_index += 1
+            else:
+                raise ValueError(f"Unrecognized chunks value, should be one of int, tuple. not: {type(self.chunks)}")
+            if self.verbose > 1:
+                AP_config.ap_logger.info(str(chunk))
+            with Param_Mask(self.model.parameters, chunk):
+                res = LM(self.model, ndf=self.ndf, **self.LM_kwargs).fit()
+            if self.verbose > 0:
+                AP_config.ap_logger.info(f"chunk loss: {res.res_loss()}")
+        self.loss_history.append(res.res_loss())
+        self.lambda_history.append(self.model.parameters.vector_representation().detach().cpu().numpy())
+        if self.iteration >= 2 and (-self.relative_tolerance * 1e-3) < (
+                (self.loss_history[-2] - self.loss_history[-1]) / self.loss_history[-1]) < (self.relative_tolerance / 10):
+            self._count_finish += 1
+        else:
+            self._count_finish = 0
+        self.iteration += 1
+
+    def fit(self):
+        self.iteration = 0
         try:
             while True:
                 self.step()

@@ -119,6 +119,15 @@ def main(names):
                 fix["iter_loss_history"] = np.array(it.loss_history)
                 fix["iter_lambda_history"] = np.array(it.lambda_history)
                 print(name, "Iter:", it.message, it.loss_history)
+                # fit/iterative.py Iter_LM: sequential chunks of 8 parameters, 2 sweeps, 3 LM iterations per chunk;
+                # the chunk fits start from the model's parameters
+                m4, _ = scenes.build(ap, name, data=data)
+                m4.parameters.vector_set_representation(torch.as_tensor(x0, dtype=ap.AP_config.ap_dtype))
+                il = ap.fit.Iter_LM(m4, initial_state=x0, chunks=8, method="sequential", max_iter=2,
+                                    LM_kwargs={"max_iter": 3, "relative_tolerance": 0.0}).fit()
+                fix["iterlm_loss_history"] = np.array(il.loss_history)
+                fix["iterlm_lambda_history"] = np.array(il.lambda_history)
+                print(name, "Iter_LM:", il.message, il.loss_history)
         path = os.path.join(out_dir, f"{name}.npz")
         np.savez_compressed(path, **fix)
         print(f"wrote {path}: P={len(x_val)} sum={[float(d.sum()) for d in imgs]} "

@@ -476,3 +476,31 @@ def test_lm_tile_sharded_over_two_gpus(tmp_path, small):
     np.testing.assert_allclose(got["loss"][:moving], ref_loss[:moving], rtol=1e-8)
     np.testing.assert_allclose(got["L"][:moving], fix["L_history"][:moving], rtol=1e-12)
     np.testing.assert_allclose(got["lam"][:moving], fix["lambda_history"][:moving], rtol=1e-8, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", list(scenes.ITER_SCENES))
+def test_iter_fit_matches_reference(name):
+    """fit.Iter (fit/iterative.py:19-180): sub-models fitted one at a time on the residual image, 3 sweeps with 4 LM
+    iterations per sub-fit on both sides; chi^2 and state per sweep against the reference's."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    res = ap.fit.Iter(model, initial_state=fix["x0"], max_iter=3,
+                      method_kwargs={"max_iter": 4, "relative_tolerance": 0.0}).fit()
+    assert len(res.loss_history) == len(fix["iter_loss_history"]) == 3
+    np.testing.assert_allclose(res.loss_history, fix["iter_loss_history"], rtol=1e-8)
+    np.testing.assert_allclose(np.array(res.lambda_history), fix["iter_lambda_history"], rtol=1e-7, atol=1e-7)
+    assert res.message.startswith("fail max iterations")
+
+
+@pytest.mark.parametrize("name", list(scenes.ITER_SCENES))
+def test_iter_lm_fit_matches_reference(name):
+    """fit.Iter_LM (fit/iterative.py:183-338): LM on sequential chunks of 8 parameters under Param_Mask, 2 sweeps,
+    3 LM iterations per chunk on both sides."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    model.parameters.vector_set_representation(torch.as_tensor(fix["x0"]))
+    res = ap.fit.Iter_LM(model, initial_state=fix["x0"], chunks=8, method="sequential", max_iter=2,
+                         LM_kwargs={"max_iter": 3, "relative_tolerance": 0.0}).fit()
+    assert len(res.loss_history) == 2
+    np.testing.assert_allclose(res.loss_history, fix["iterlm_loss_history"], rtol=1e-8)
+    np.testing.assert_allclose(np.array(res.lambda_history), fix["iterlm_lambda_history"], rtol=1e-7, atol=1e-7)
