@@ -110,6 +110,10 @@ def main(names):
             fix["L_history"] = np.array(res.L_history)
             fix["lambda_history"] = np.array(res.lambda_history)
             fix["message"] = np.array(res.message)
+            # uncertainties in natural units at the fitted state (lm.py:408-425,495-539)
+            fix["cov"] = res.covariance_matrix.detach().cpu().numpy()
+            res.update_uncertainty()
+            fix["uncertainty"] = m2.parameters.vector_uncertainty().detach().cpu().numpy()
             print(name, "LM:", res.message, res.loss_history)
             if name in getattr(scenes, "ITER_SCENES", ()):
                 # fit/iterative.py Iter: 3 sweeps, every sub-fit 4 LM iterations (fixed counts on both sides)

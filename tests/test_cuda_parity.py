@@ -504,3 +504,20 @@ def test_iter_lm_fit_matches_reference(name):
     assert len(res.loss_history) == 2
     np.testing.assert_allclose(res.loss_history, fix["iterlm_loss_history"], rtol=1e-8)
     np.testing.assert_allclose(np.array(res.lambda_history), fix["iterlm_lambda_history"], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(scenes.LM_SCENES))
+def test_covariance_and_uncertainty_match_reference(name):
+    """LM.covariance_matrix / update_uncertainty (lm.py:408-425,495-539): inverse of J^T W J in NATURAL parameter
+    units at the fitted state, one more normal-equation build with as_representation=False."""
+    fix = load_golden(name)
+    if "cov" not in fix:
+        pytest.skip("golden without covariance")
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=8, relative_tolerance=0.0).fit()
+    cov = res.covariance_matrix.cpu().numpy()
+    ref = fix["cov"]
+    d = np.sqrt(np.abs(np.diag(ref)))
+    assert np.max(np.abs(cov - ref) / np.outer(d, d)) < 1e-6
+    res.update_uncertainty()
+    np.testing.assert_allclose(model.parameters.vector_uncertainty().numpy(), fix["uncertainty"], rtol=1e-6)
