@@ -393,7 +393,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     const apb_source_t& a = src[i];
     DevSrc& s = S[i];
     memset(&s, 0, sizeof(s));
-    if (a.kind < 0 || a.kind > APB_FLAT_SKY) PFAIL("unknown source kind");
+    if (a.kind < 0 || a.kind > APB_PLANE_SKY) PFAIL("unknown source kind");
+    if (a.kind == APB_PLANE_SKY && (a.n_elem != 5 || a.psf >= 0 || a.integrate_mode != APB_INTEGRATE_NONE))
+      PFAIL("plane sky: 5 elements, no PSF, no sub-pixel integration");
     if (a.image < 0 || a.image >= n_img) PFAIL("source image index out of range");
     if (a.n_elem < 3 || a.n_elem > APB_MAX_ELEM) PFAIL("bad n_elem");
     if (a.sampling_mode < APB_SAMPLE_MIDPOINT || a.sampling_mode > APB_SAMPLE_TRAPEZOID) PFAIL("unknown sampling_mode");

@@ -113,6 +113,17 @@ __device__ __forceinline__ double sersic_db(double n) {
 template <int KIND, bool GRAD>
 __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, double X, double Y, double ascale,
                                              double* __restrict__ dI) {
+  if (KIND == APB_PLANE_SKY) {
+    // planesky_model.py:65-74:  pixel_area F + X dx + Y dy  (natural flux units; only ever sampled at pixel centres)
+    if (GRAD) {
+      dI[0] = -d.el[3] * ascale;
+      dI[1] = -d.el[4] * ascale;
+      dI[2] = s.area * ascale;
+      dI[3] = X * ascale;
+      dI[4] = Y * ascale;
+    }
+    return ascale * (s.area * d.el[2] + X * d.el[3] + Y * d.el[4]);
+  }
   double xp, yp;
   const bool radial = (s.flags & APB_F_RADIAL) != 0;
   if (radial) {
@@ -246,6 +257,7 @@ __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, d
 template <int KIND>
 struct KindInfo {};
 template <> struct KindInfo<APB_SERSIC> { static constexpr int NE = 7; };
+template <> struct KindInfo<APB_PLANE_SKY> { static constexpr int NE = 5; };
 template <> struct KindInfo<APB_EXPONENTIAL> { static constexpr int NE = 6; };
 template <> struct KindInfo<APB_GAUSSIAN> { static constexpr int NE = 6; };
 template <> struct KindInfo<APB_MOFFAT> { static constexpr int NE = 7; };

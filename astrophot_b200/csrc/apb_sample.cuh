@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(256) k_first(const DevSrc* __restrict__ src, c
     case APB_GAUSSIAN: first_pass_pixel<APB_GAUSSIAN, GRAD>(s, d, g, i, j, stamp, errp); break;
     case APB_MOFFAT: first_pass_pixel<APB_MOFFAT, GRAD>(s, d, g, i, j, stamp, errp); break;
     case APB_SPLINE: first_pass_pixel<APB_SPLINE, GRAD>(s, d, g, i, j, stamp, errp); break;
+    case APB_PLANE_SKY: first_pass_pixel<APB_PLANE_SKY, GRAD>(s, d, g, i, j, stamp, errp); break;
     default: break;
   }
 }

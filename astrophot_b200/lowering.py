@@ -172,6 +172,8 @@ def lower(model, window=None, for_fit=False):
         for nm in names:
             if nm in ("cx", "cy"):
                 nodes.append((comp.parameters["center"], 0 if nm == "cx" else 1))
+            elif nm in ("dx", "dy"):          # plane sky slopes: the two elements of `delta`
+                nodes.append((comp.parameters["delta"], 0 if nm == "dx" else 1))
             elif isinstance(comp, PSF_Model) and nm in ("q", "PA") and nm not in have:
                 nodes.append((None, 1.0 if nm == "q" else 0.0))
             else:
@@ -196,7 +198,7 @@ def lower(model, window=None, for_fit=False):
                 continue
             leaf = _resolve_leaf(node)
             if leaf.value is None:
-                if leaf.name == "center":   # sky models: centre is irrelevant
+                if leaf.name == "center" and comp._kind == sc.KIND_FLAT_SKY:   # flat sky: centre is irrelevant
                     slot.append(-1)
                     cval.append(0.0)
                     continue
@@ -223,7 +225,7 @@ def lower(model, window=None, for_fit=False):
         else:
             raise SpecificationConflict(
                 f"{comp.name} has unknown integration mode: {im}. Should be one of: none, threshold")
-        if comp._kind in (sc.KIND_FLAT_SKY, sc.KIND_POINT):
+        if comp._kind in (sc.KIND_FLAT_SKY, sc.KIND_POINT, sc.KIND_PLANE_SKY):
             imode = sc.INTEGRATE_NONE
 
         # psf

@@ -510,6 +510,18 @@ class Flat_Sky(Sky_Model):
     _kind = sc.KIND_FLAT_SKY
 
 
+class Plane_Sky(Sky_Model):
+    """Sky brightness plane  I = pixel_area F + X dx + Y dy  about the (locked) centre, natural flux units
+    (reference: `planesky_model.py:13-74`)."""
+
+    model_type = f"plane {Sky_Model.model_type}"
+    parameter_specs = {"F": {"units": "flux/arcsec^2"}, "delta": {"units": "flux/arcsec"}}
+    _parameter_order = Sky_Model._parameter_order + ("F", "delta")
+    usable = True
+    _kind = sc.KIND_PLANE_SKY
+    _flags = sc.FLAG_RADIAL        # no rotation / axis ratio elements
+
+
 # ---------------------------------------------------------------------------
 # PSF models: target is a PSF_Image, centre locked at (0, 0), normalised
 # ---------------------------------------------------------------------------

@@ -13,8 +13,8 @@ from typing import List, Optional
 import numpy as np
 
 # -- enumerations (values are part of the C ABI) -------------------------------
-KIND_SERSIC, KIND_EXPONENTIAL, KIND_GAUSSIAN, KIND_MOFFAT, KIND_SPLINE, KIND_POINT, KIND_FLAT_SKY = range(7)
-KIND_NAMES = ["sersic", "exponential", "gaussian", "moffat", "spline", "point", "flat_sky"]
+KIND_SERSIC, KIND_EXPONENTIAL, KIND_GAUSSIAN, KIND_MOFFAT, KIND_SPLINE, KIND_POINT, KIND_FLAT_SKY, KIND_PLANE_SKY = range(8)
+KIND_NAMES = ["sersic", "exponential", "gaussian", "moffat", "spline", "point", "flat_sky", "plane_sky"]
 
 FLAG_RADIAL = 1        # no rotation / axis ratio (PSF-model kinds): elements skip q, PA
 FLAG_NORMALIZE = 2     # divide the sampled stamp by its sum (PSF models)
@@ -40,6 +40,7 @@ ELEMS = {
     KIND_SPLINE: ("cx", "cy", "q", "PA"),
     KIND_POINT: ("cx", "cy", "flux"),
     KIND_FLAT_SKY: ("cx", "cy", "F"),
+    KIND_PLANE_SKY: ("cx", "cy", "F", "dx", "dy"),
 }
 
 

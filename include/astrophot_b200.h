@@ -44,7 +44,8 @@ enum {
   APB_MOFFAT = 3,      /* cx cy q PA n Rd I0      models/moffat_model.py:23       */
   APB_SPLINE = 4,      /* cx cy q PA v[0..K-1]    models/spline_model.py:27       */
   APB_POINT = 5,       /* cx cy flux              models/point_source.py:17       */
-  APB_FLAT_SKY = 6     /* cx cy F                 models/flatsky_model.py:13      */
+  APB_FLAT_SKY = 6,    /* cx cy F                 models/flatsky_model.py:13      */
+  APB_PLANE_SKY = 7    /* cx cy F dx dy           models/planesky_model.py:13 (set APB_F_RADIAL) */
 };
 enum { APB_F_RADIAL = 1, APB_F_NORMALIZE = 2 }; /* psf_model_object.py:36-57,255 */
 enum { APB_TR_NONE = 0, APB_TR_LOWER, APB_TR_UPPER, APB_TR_BOTH, APB_TR_CYCLIC }; /* utils/conversions/optimization.py:6-54 */

@@ -168,6 +168,15 @@ def eval_profile(src, el, X, Y, area, want_grad):
         dI = np.zeros((ne,) + X.shape)
         dI[2] = LN10 * I
         return I, dI
+    if kind == sc.KIND_PLANE_SKY:
+        # planesky_model.py:65-74:  pixel_area F + X dx + Y dy  (X, Y relative to the centre)
+        I = area * el[2] + X * el[3] + Y * el[4]
+        if not want_grad:
+            return I, None
+        dI = np.zeros((ne,) + X.shape)
+        dI[0], dI[1] = -el[3], -el[4]
+        dI[2], dI[3], dI[4] = area, X, Y
+        return I, dI
     if kind == sc.KIND_POINT:
         raise ValueError("point sources are not profile-evaluated")
     q, PA = el[2], el[3]

@@ -170,6 +170,16 @@ def build(ap, name, data=None):
                parameters={"center": [60.2, 27.7], "q": 0.9, "PA": 1.1, "I(R)": {"value": val, "prof": prof}})
         g = M(name="grp3", model_type="group model", models=[m1, m2, m3], target=tar)
         return g, {}
+    if name == "plane_sky_group":
+        # galaxy on a tilted background: `plane sky model` (planesky_model.py), natural flux units, slopes fitted
+        psf = ap.image.PSF_Image(data=_psf_gauss(1.2, 7), pixelscale=0.8)
+        tar = _target(ap, (72, 64), data, pixelscale=0.8, psf=psf)
+        m1 = M(name="pg", model_type="sersic galaxy model", target=tar, psf_mode="full", window=[[12, 52], [16, 60]],
+               parameters={"center": [25.3, 30.6], "q": 0.7, "PA": 0.5, "n": 1.7, "Re": 5.0, "Ie": 0.9})
+        sky = M(name="psky", model_type="plane sky model", target=tar,
+                parameters={"center": [25.6, 28.8], "F": 0.35, "delta": [0.004, -0.0025]})
+        g = M(name="grp_plane", model_type="group model", models=[m1, sky], target=tar, psf_mode="full")
+        return g, {}
     if name == "joint":
         tars, models = [], []
         for b in range(3):
@@ -222,9 +232,10 @@ def build(ap, name, data=None):
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
-                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref"]
+                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group"]
 # scenes with an LM golden (noise seed, start perturbation)
-LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12}
+LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
+             "plane_sky_group": 13}
 
 
 ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens

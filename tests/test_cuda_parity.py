@@ -521,3 +521,21 @@ def test_covariance_and_uncertainty_match_reference(name):
     assert np.max(np.abs(cov - ref) / np.outer(d, d)) < 1e-6
     res.update_uncertainty()
     np.testing.assert_allclose(model.parameters.vector_uncertainty().numpy(), fix["uncertainty"], rtol=1e-6)
+
+
+def test_float32_images_are_accepted_and_returned():
+    """AP_config.ap_dtype = float32 (AP_config.py:7): images come in and go out as fp32; the kernels compute in
+    fp64 whatever the image dtype, so the fp32 bar of the north star (1e-5 of the image scale) is met with margin."""
+    fix = load_golden("psf_sersic")
+    old = ap.AP_config.ap_dtype
+    ap.AP_config.ap_dtype = torch.float32
+    try:
+        model, _ = scenes.build(ap, "psf_sersic", data=golden_data(fix))
+        assert model.target.data.dtype == torch.float32
+        img = model()
+        assert img.data.dtype == torch.float32
+        assert rel_err(img.data.double().cpu().numpy(), fix["img0"]) < 1e-6
+        res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0).fit()
+        np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-5)
+    finally:
+        ap.AP_config.ap_dtype = old
