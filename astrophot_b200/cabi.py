@@ -65,7 +65,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_plan_set_image_data", "apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -98,6 +98,7 @@ def load_library(path=None):
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
     L.apb_lm_solve_sparse.argtypes = [vp, dp, C.c_double, dp, dp, C.c_double, C.c_int, vp]
+    L.apb_plan_set_image_data.argtypes = [vp, C.c_int, dp, dp, dp, vp]
     L.apb_plan_block_doubles.argtypes = [vp]
     L.apb_plan_bind_blocks.argtypes = [vp, dp]
     L.apb_lm_trial.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
@@ -360,6 +361,22 @@ class Plan:
             return None
         _check(rc, "apb_lm_solve_sparse")
         return out, info
+
+    def set_image_data(self, i, data, weight=None, mask=None):
+        """Rebind image ``i`` to other device tensors of the same shape (fp64 data / weight, uint8 mask); work enqueued on
+        the current stream afterwards reads them.  ``image_buffers[i]`` follows."""
+        for t in (data, weight):
+            if t is not None and (t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or
+                                  tuple(t.shape) != (self.scene.images[i].H, self.scene.images[i].W)):
+                raise NativeLibraryError("set_image_data: contiguous fp64 CUDA tensors of the image's shape are required")
+        if mask is not None:
+            mask = mask.to(dtype=torch.uint8).contiguous()
+        _check(self._L.apb_plan_set_image_data(self._h, int(i), data.data_ptr(), weight.data_ptr() if weight is not None else None,
+                                               mask.data_ptr() if mask is not None else None, _stream()),
+               "apb_plan_set_image_data")
+        self._bound = getattr(self, "_bound", {})
+        self._bound[i] = (data, weight, mask)          # keep the storage alive while the plan points at it
+        self.image_buffers[i] = {k: v for k, v in (("data", data), ("weight", weight)) if v is not None}
 
     def block_doubles(self):
         """Length of the block-sparse J^T W J array (0: the plan has no block-sparse form)."""

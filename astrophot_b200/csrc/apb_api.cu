@@ -262,6 +262,17 @@ extern "C" int apb_plan_destroy(apb_plan_t* p) {
   return 0;
 }
 
+extern "C" int apb_plan_set_image_data(apb_plan_t* p, int image, const double* data, const double* weight,
+                                       const uint8_t* mask, void* stream) {
+  if (!p) APB_FAIL("plan is NULL");
+  if (image < 0 || image >= p->n_img) APB_FAIL("apb_plan_set_image_data: image index out of range");
+  apb_image_t& im = p->h_img[image];
+  im.data = data; im.weight = weight; im.mask = mask;
+  // pageable source: the copy is staged before the call returns, and ordered on `stream` like a kernel
+  CU(cudaMemcpyAsync(p->d_img + image, &im, sizeof(apb_image_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 template <typename T>
 static int own_upload(apb_plan* p, const std::vector<T>& v, T** out) {
   int rc = upload(v, out);

@@ -152,6 +152,14 @@ int apb_plan_create(const apb_source_t *src, int n_src, const apb_image_t *img, 
                     const apb_opts_t *opts, apb_plan_t **out);
 int apb_plan_destroy(apb_plan_t *plan);
 
+/* Point image `image` of the plan at other data / weight / mask buffers of the same shape (device pointers, same
+ * meaning as in apb_image_t; weight / mask may be NULL).  Takes effect for work enqueued on `stream` after this call:
+ * a fit loop can upload the next exposure into a second set of buffers while the current one is being fitted, and
+ * one plan serves every image that shares the model geometry (the reference rebuilds Y, W, mask per LM object,
+ * fit/lm.py:191-222). */
+int apb_plan_set_image_data(apb_plan_t *plan, int image, const double *data, const double *weight,
+                            const uint8_t *mask, void *stream);
+
 /* seam 1 — model(parameters=x, as_representation=as_rep) -> model image(s)
  * (core_model.py:484-502, model_object.py:258-375, group_model_object.py:183-231).
  * x: device, n_par doubles.  model_out[i]: device, H_i*W_i doubles, OVERWRITTEN. */
