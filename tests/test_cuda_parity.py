@@ -539,3 +539,29 @@ def test_float32_images_are_accepted_and_returned():
         np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-5)
     finally:
         ap.AP_config.ap_dtype = old
+
+
+def test_plan_rebinds_image_data():
+    """apb_plan_set_image_data: the same plan, pointed at other data / weight buffers, gives the normal equations of
+    a plan built on those buffers (streaming many exposures through one plan)."""
+    fix = load_golden("group")
+    model, _ = scenes.build(ap, "group", data=golden_data(fix))
+    scene, _ = lower(model, for_fit=True)
+    plan = _plan(scene)
+    H0, g0, c0 = [t.clone() for t in plan.normal_eq(fix["x0"], check=True)]
+    d2 = plan.image_buffers[0]["data"] * 1.01 + 0.003
+    w2 = plan.image_buffers[0]["weight"] * 0.9
+    old = dict(plan.image_buffers[0])
+    plan.set_image_data(0, d2, w2, plan._masks.get(0))
+    H1, g1, c1 = [t.clone() for t in plan.normal_eq(fix["x0"], check=True)]
+    import copy
+    sc2 = copy.copy(scene)
+    sc2.images = [copy.copy(scene.images[0])]
+    sc2.images[0].data, sc2.images[0].weight = d2.cpu(), w2.cpu()
+    H2, g2, c2 = _plan(sc2).normal_eq(fix["x0"], check=True)
+    assert torch.allclose(H1, H2, rtol=1e-13, atol=0) and torch.allclose(g1, g2, rtol=1e-12, atol=1e-12 * float(g2.abs().max()))
+    assert abs(c1[0].item() - c2[0].item()) <= 1e-13 * abs(c2[0].item())
+    assert abs(c1[0].item() - c0[0].item()) > 1e-3 * abs(c0[0].item())
+    plan.set_image_data(0, old["data"], old["weight"], plan._masks.get(0))
+    H3, g3, c3 = plan.normal_eq(fix["x0"], check=True)
+    assert torch.equal(H3, H0) and torch.equal(g3, g0)
