@@ -66,6 +66,16 @@ def _rect(region: Window, win: Window):
     return (cols.start, rows.start, max(cols.stop - cols.start, 0), max(rows.stop - rows.start, 0))
 
 
+def _rect_unclipped(region: Window, win: Window):
+    """Pixel rectangle of ``win`` in ``region``'s pixel grid WITHOUT clipping to it (may start below 0 / reach past
+    the region).  The reference hands an explicitly requested window to the sampling code as it is
+    (`model_object.py:296-299`: ``working_window = window.copy()``) while the output image is the target cut to it:
+    a model window that sticks out of the target is sampled on all of it."""
+    lo = np.round(region._plane2pix(win._origin)[:, 0] + 0.5).astype(np.int64)
+    hi = np.round(region._plane2pix(win._origin + win._end)[:, 0] + 0.5).astype(np.int64)
+    return (int(lo[0]), int(lo[1]), int(max(hi[0] - lo[0], 0)), int(max(hi[1] - lo[1], 0)))
+
+
 _SAMPLING = {"midpoint": sc.SAMPLE_MIDPOINT, "simpsons": sc.SAMPLE_SIMPSONS, "trapezoid": sc.SAMPLE_TRAPEZOID}
 
 
@@ -101,6 +111,8 @@ def lower(model, window=None, for_fit=False):
     else:
         targets = [target]
         regions = [mwin]
+    asked = [r.copy() for r in regions]     # the requested windows as they are (may stick out of their targets)
+    explicit = window is not None
     images = []
     fmask = None
     if for_fit:
@@ -301,8 +313,16 @@ def lower(model, window=None, for_fit=False):
         out = _rect(region, cwin)
         if out[2] <= 0 or out[3] <= 0:
             continue
-        jac = out
-        fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
+        # Working windows.  The Jacobian is always taken on (own window & requested window) as it is
+        # (_model_methods.py:294-299); the forward model on the window it is asked for as it is when one is passed
+        # explicitly (LM: fit/lm.py:199 hands fit_window to every forward), else on the target cut to the model's
+        # window (model_object.py:291-296).  Inside a group both sub-model passes get the group's window
+        # (group_model_object.py:211-227) / its overlap with the sub-model's own (group_model_object.py:258-266).
+        jac = _rect_unclipped(region, cwin & asked[ii])
+        if explicit:
+            fwd = _rect_unclipped(region, asked[ii]) if is_group else jac
+        else:
+            fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
         src = build_source(comp, ii, region, out, fwd, jac)
         sources.append(src)
         info.components.append(comp)

@@ -180,6 +180,19 @@ def build(ap, name, data=None):
                 parameters={"center": [25.6, 28.8], "F": 0.35, "delta": [0.004, -0.0025]})
         g = M(name="grp_plane", model_type="group model", models=[m1, sky], target=tar, psf_mode="full")
         return g, {}
+    if name == "masked_locked_edge":
+        # target mask (a block + scattered pixels), locked parameters, model window cut by the image edge so that the
+        # PSF border reaches outside the image
+        rng = np.random.default_rng(21)
+        mask = np.zeros((56, 60), dtype=bool)
+        mask[20:26, 30:41] = True
+        mask[rng.integers(0, 56, 40), rng.integers(0, 60, 40)] = True
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 1.6, 9), pixelscale=1.0)
+        tar = _target(ap, (56, 60), data, psf=psf, mask=mask)
+        m = M(name="mle", model_type="sersic galaxy model", target=tar, psf_mode="full", window=[[-6, 34], [18, 62]],
+              parameters={"center": [9.4, 39.2], "q": 0.65, "PA": 1.2, "n": {"value": 2.0, "locked": True},
+                          "Re": 6.0, "Ie": 0.8})
+        return m, {}
     if name == "joint":
         tars, models = [], []
         for b in range(3):
@@ -232,10 +245,10 @@ def build(ap, name, data=None):
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
-                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group"]
+                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
-             "plane_sky_group": 13}
+             "plane_sky_group": 13, "masked_locked_edge": 14}
 
 
 ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens
