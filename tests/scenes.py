@@ -193,6 +193,23 @@ def build(ap, name, data=None):
               parameters={"center": [9.4, 39.2], "q": 0.65, "PA": 1.2, "n": {"value": 2.0, "locked": True},
                           "Re": 6.0, "Ie": 0.8})
         return m, {}
+    if name == "psf_sheared_novar":
+        # general 2x2 pixelscale with a PSF (sub-pixel shift through S^-1), target without variance (weights = 1)
+        S = np.array([[0.7, 0.08], [-0.05, 0.75]])
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 1.7, 9), pixelscale=S)
+        if data is not None:
+            data = {k: {"data": v["data"]} for k, v in data.items()}
+        tar = _target(ap, (60, 66), data, pixelscale=S, origin=[1.0, -3.0], psf=psf)
+        m = M(name="psn", model_type="sersic galaxy model", target=tar, psf_mode="full",
+              parameters={"center": [24.3, 17.9], "q": 0.6, "PA": 0.3, "n": 1.4, "Re": 5.5, "Ie": 1.1})
+        return m, {}
+    if name == "sersic_knobs":
+        # non-default integration knobs: 3x3 re-gridding, two levels, 2-point Gauss-Legendre, tighter tolerance
+        tar = _target(ap, (64, 64), data)
+        m = M(name="knb", model_type="sersic galaxy model", target=tar, integrate_gridding=3, integrate_max_depth=2,
+              integrate_quad_level=2, sampling_tolerance=3e-3,
+              parameters={"center": [30.6, 33.2], "q": 0.5, "PA": 2.0, "n": 3.5, "Re": 6.0, "Ie": 0.7})
+        return m, {}
     if name == "joint":
         tars, models = [], []
         for b in range(3):
@@ -245,10 +262,10 @@ def build(ap, name, data=None):
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
-                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge"]
+                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
-             "plane_sky_group": 13, "masked_locked_edge": 14}
+             "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15}
 
 
 ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens
