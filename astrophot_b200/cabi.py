@@ -97,7 +97,7 @@ def load_library(path=None):
     L.apb_geodesic.argtypes = [vp, dp, dp, C.c_double, dp, vp]
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
-    L.apb_lm_solve_sparse.argtypes = [vp, dp, C.c_double, dp, dp, C.c_double, C.c_int, vp]
+    L.apb_lm_solve_sparse.argtypes = [vp, dp, C.c_double, dp, dp, dp, C.c_double, C.c_int, vp]
     L.apb_plan_set_image_data.argtypes = [vp, C.c_int, dp, dp, dp, vp]
     L.apb_plan_block_doubles.argtypes = [vp]
     L.apb_plan_bind_blocks.argtypes = [vp, dp]
@@ -348,15 +348,17 @@ class Plan:
                                         ha_out.data_ptr(), rec.data_ptr(), _stream()), "apb_lm_trial_end")
         return rec
 
-    def solve_sparse(self, g, L, out=None, info=None, tol=0.0, max_iter=0):
+    def solve_sparse(self, g, L, out=None, info=None, tol=0.0, max_iter=0, x0=None):
         """Damped LM solve by block-sparse PCG on the blocks of the last normal_eq (apb_lm_solve_sparse).
         Returns (h, info) device tensors, info = [iterations, |r|/|b|]; None if the plan cannot use it."""
         if out is None:
             out = torch.empty(self.n_par, dtype=torch.float64, device="cuda")
         if info is None:
             info = torch.zeros(2, dtype=torch.float64, device="cuda")
-        rc = self._L.apb_lm_solve_sparse(self._h, g.data_ptr(), float(L), out.data_ptr(), info.data_ptr(), float(tol),
-                                         int(max_iter), _stream())
+        if x0 is not None and x0.data_ptr() == out.data_ptr():
+            x0 = x0.clone()
+        rc = self._L.apb_lm_solve_sparse(self._h, g.data_ptr(), float(L), x0.data_ptr() if x0 is not None else None,
+                                         out.data_ptr(), info.data_ptr(), float(tol), int(max_iter), _stream())
         if rc == 1:
             return None
         _check(rc, "apb_lm_solve_sparse")

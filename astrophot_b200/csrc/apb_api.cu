@@ -1450,14 +1450,14 @@ extern "C" int apb_lm_solve(const double* H, const double* g, double L, int P, d
 // Damped solve of the system of the last apb_normal_eq by block-sparse PCG (apb_solve.cuh).
 //   g: device, n_par;  h: device, n_par (out);  info: device, 2 doubles {iterations, |r|/|b|}.
 // Returns 1 (not an error) when the plan cannot use it (parameters shared between sources).
-extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, double* h, double* info, double tol,
-                                   int max_iter, void* stream) {
+extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, const double* x0, double* h, double* info,
+                                   double tol, int max_iter, void* stream) {
   if (!p) APB_FAIL("plan is NULL");
   if (!p->sparse_ok) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = (size_t)p->n_par;
   PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_multi_rows, p->n_multi,
-            p->d_own_slot, p->d_own_off, p->d_bvals, p->d_diagH, p->d_pfac, g, h, p->d_pvec, p->d_pvec + P,
+            p->d_own_slot, p->d_own_off, p->d_bvals, p->d_diagH, p->d_pfac, g, x0, h, p->d_pvec, p->d_pvec + P,
             p->d_pvec + 2 * P, p->d_pvec + 3 * P, p->d_pvec + 4 * P, p->d_qpart, p->d_pcg_part, p->d_pcg_bar,
             info, p->n_par, max_iter > 0 ? max_iter : 2000, L, tol > 0.0 ? tol : 1e-14};
   void* args[] = {&A};

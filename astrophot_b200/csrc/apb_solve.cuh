@@ -54,6 +54,7 @@ struct PcgArgs {
   const double* diagH;     // P: diagonal of H
   double* fac;             // n_rows x 64: Cholesky factors of the damped diagonal blocks
   const double* b;         // right-hand side (P)
+  const double* x0;        // starting point (P) or NULL = 0 (the previous lambda-trial's solution is a good one)
   double* x;               // solution (P)
   double *r, *z, *pa, *pb, *q;   // work vectors (P)
   double* qpart;           // n_items x 8: partial rows of split rows
@@ -126,7 +127,10 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
   const int ncta = gridDim.x;
   const double inv1L = 1.0 / (1.0 + A.L);
 
-  // ---- setup: Cholesky of every damped diagonal block; x = 0, r = b, z = M^-1 r, p_old = 0
+  // ---- setup: Cholesky of every damped diagonal block; x = 0, r = b, z = M^-1 r, p_old = 0.
+  //      With a starting point the first pass of the loop below is a PRE-pass: z holds x0, so that phase 1 forms
+  //      q = A x0, and phase 2 turns it into r = b - q, z = M^-1 r; the iteration proper starts from there.
+  bool pre = A.x0 != nullptr;
   double s_rz = 0.0, s_bb = 0.0;
   for (int rb = gtid; rb < A.n_rows; rb += gsz) {
     const PcgRow row = A.rows[rb];
@@ -156,12 +160,16 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
     for (int i = 0; i < row.n; ++i) {
       const double bi = A.b[sl[i]];
       rv[i] = bi;
-      A.x[sl[i]] = 0.0;
+      A.x[sl[i]] = pre ? A.x0[sl[i]] : 0.0;
       A.r[sl[i]] = bi;
       A.pa[sl[i]] = 0.0;
       s_bb = fma(bi, bi, s_bb);
     }
-    s_rz += pcg_precond(A, rb, row, rv, A.z);
+    if (pre) {
+      for (int i = 0; i < row.n; ++i) A.z[sl[i]] = A.x0[sl[i]];
+    } else {
+      s_rz += pcg_precond(A, rb, row, rv, A.z);
+    }
   }
   {
     const double t0 = block_sum<256>(s_rz, sh), t1 = block_sum<256>(s_bb, sh);
@@ -260,8 +268,8 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         pq += bc2;
         __syncthreads();
       }
-      if (!(pq > 0.0)) break;
-      const double alpha = rz / pq;
+      if (!pre && !(pq > 0.0)) break;
+      const double alpha = pre ? 0.0 : rz / pq;
       // ---- phase 2: x += alpha p; r -= alpha q; z = M^-1 r; shares of r.z and r.r
       double s_rz2 = 0.0, s_rr = 0.0;
       for (int rb = gtid; rb < A.n_rows; rb += gsz) {
@@ -271,8 +279,13 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         for (int i = 0; i < row.n; ++i) {
           const int s = sl[i];
           const double qi = __ldcg(A.q + s);
-          A.x[s] = fma(alpha, __ldcg(pnew + s), A.x[s]);
-          const double ri = fma(-alpha, qi, A.r[s]);
+          double ri;
+          if (pre) {
+            ri = A.r[s] - qi;                        // r = b - A x0
+          } else {
+            A.x[s] = fma(alpha, __ldcg(pnew + s), A.x[s]);
+            ri = fma(-alpha, qi, A.r[s]);
+          }
           A.r[s] = ri;
           rv[i] = ri;
           s_rr = fma(ri, ri, s_rr);
@@ -286,6 +299,14 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
       pcg_barrier(A.barrier, goal);
       const double rz_new = pcg_total(A.part, 1, ncta, sh);
       rr = pcg_total(A.part, 2, ncta, sh);
+      if (pre) {            // the iteration proper starts here: p = z
+        pre = false;
+        rz = rz_new;
+        beta = 0.0;
+        if (!(rr > A.tol * A.tol * bb)) break;
+        double* t = pold; pold = pnew; pnew = t;
+        continue;
+      }
       ++it;
       if (!(rr > A.tol * A.tol * bb)) break;
       beta = rz_new / rz;

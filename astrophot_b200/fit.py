@@ -168,6 +168,7 @@ class LM(BaseOptimizer):
             if self._blk is not None:
                 self._hs = torch.empty(P + 2, dtype=torch.float64, device=dev)
         self.pcg_iterations = []
+        self._warm = None               # (hess version, h, solve(rpp)) of the previous lambda-trial
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
     # -- damping -------------------------------------------------------------
@@ -205,7 +206,7 @@ class LM(BaseOptimizer):
             c2[1] = torch.where(rec[2] > 0, -1.0, (rec[1] == 0).to(c2.dtype))
         return c2
 
-    def _solve(self, L, rhs, loose=False):
+    def _solve(self, L, rhs, loose=False, x0=None):
         from .cabi import lm_solve
 
         P = rhs.numel()
@@ -221,12 +222,12 @@ class LM(BaseOptimizer):
             if self.distributed:
                 # every rank solves the same merged system; rank 0's answer is the one all use (the split sky row of
                 # the PCG is summed with atomics, so the ranks' solutions may differ in the last bit)
-                res = self.plan.solve_sparse(rhs.contiguous(), L, out=self._hs[:P], info=self._hs[P:], tol=tol)
+                res = self.plan.solve_sparse(rhs.contiguous(), L, out=self._hs[:P], info=self._hs[P:], tol=tol, x0=x0)
                 torch.distributed.broadcast(self._hs, src=torch.distributed.get_global_rank(self.group, 0)
                                             if self.group is not None else 0, group=self.group)
                 res = (self._hs[:P].clone(), self._hs[P:])
             else:
-                res = self.plan.solve_sparse(rhs.contiguous(), L, tol=tol)
+                res = self.plan.solve_sparse(rhs.contiguous(), L, tol=tol, x0=x0)
             if res is None:
                 self._sparse_solver = False
             else:
@@ -380,11 +381,19 @@ class LM(BaseOptimizer):
     def _trial_pieces(self, x, d):
         """One lambda-trial from separate calls (distributed fits need an all-reduce between the
         pieces; large systems use the library solver).  Returns (ha, chi2/ndf, |a|, |h|)."""
-        h = self._solve(self.L, self.grad)
+        # the previous trial of this LM iteration solved the same matrix with another damping: its solutions are the
+        # starting points of this trial's two PCG solves
+        warm = self._warm if self._warm is not None and self._warm[0] == self._hess_version else (None, None, None)
+        h = self._solve(self.L, self.grad, x0=warm[1])
         # geodesic acceleration (second directional derivative along h)
         self.n_forward += 1
         rpp = self._allreduce(self.plan.geodesic(x + d * h, h, d, out=self._rpp))
-        a = -self._solve(self.L, rpp, loose=(self.acceleration == 0)) / 2 if self.L > 1e-4 else torch.zeros_like(h)
+        if self.L > 1e-4:
+            s2 = self._solve(self.L, rpp, loose=(self.acceleration == 0), x0=warm[2])
+            a = -s2 / 2
+        else:
+            s2, a = None, torch.zeros_like(h)
+        self._warm = (self._hess_version, h.clone(), None if s2 is None else s2.clone())
         ha = h + a * self.acceleration
         self.n_forward += 1
         c2 = self._allreduce_chi(self.plan.chi2(x + ha, out=self._c2))

@@ -202,11 +202,13 @@ int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, i
 /* The same damped system for large parameter counts (crowded fields, fit/lm.py:359-371 with P ~ 1e4):
  * J^T W J of the last apb_normal_eq is kept inside the plan as its list of <= 8x8 source-pair blocks, and the
  * system is solved by block-Jacobi preconditioned conjugate gradients in one persistent cooperative kernel.
- * g, h: device, n_par.  info: device, 2 doubles {iterations, final |r|/|b|}.  tol <= 0: 1e-14; max_iter <= 0: 2000.
+ * g, h: device, n_par.  x0: device, n_par, starting point of the iteration, or NULL for zero (the solution of the previous
+ * lambda-trial of the same LM iteration saves iterations; x0 must not alias h).  info: device, 2 doubles
+ * {iterations, final |r|/|b|}.  tol <= 0: 1e-14; max_iter <= 0: 2000.
  * Returns 1 (no error set) if the plan cannot use it (a parameter shared between sources, as in joint fits):
  * use apb_lm_solve or a dense library solver on the JtWJ of apb_normal_eq instead. */
-int apb_lm_solve_sparse(apb_plan_t *plan, const double *g, double L, double *h, double *info, double tol,
-                        int max_iter, void *stream);
+int apb_lm_solve_sparse(apb_plan_t *plan, const double *g, double L, const double *x0, double *h, double *info,
+                        double tol, int max_iter, void *stream);
 
 /* The block-sparse J^T W J of the plan as one flat array: the blocks, tightly packed (n_a x n_b doubles each,
  * row-major), followed by diag(J^T W J) (n_par doubles).  apb_plan_block_doubles returns its length (0: the plan has no

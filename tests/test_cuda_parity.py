@@ -319,6 +319,15 @@ def test_sparse_pcg_solve_vs_dense(name):
             want = orc.lm_solve(Hn, rhs, L)
             assert rel <= 1e-12 and its < 1000, (L, its, rel)
             np.testing.assert_allclose(h.cpu().numpy(), want, rtol=1e-8, atol=1e-11 * np.abs(want).max())
+            # warm start from the solution at another damping (what consecutive lambda-trials do): same answer
+            h2, info2 = plan.solve_sparse(torch.as_tensor(rhs, device="cuda"), L / 9.0, x0=h)
+            its2, rel2 = info2.tolist()
+            want2 = orc.lm_solve(Hn, rhs, L / 9.0)
+            assert rel2 <= 1e-12 and its2 < 1000
+            np.testing.assert_allclose(h2.cpu().numpy(), want2, rtol=1e-8, atol=1e-11 * np.abs(want2).max())
+            # and from the exact solution: nothing left to do
+            h3, info3 = plan.solve_sparse(torch.as_tensor(rhs, device="cuda"), L / 9.0, x0=h2)
+            assert info3.tolist()[0] <= 2
 
 
 def test_sparse_pcg_refuses_shared_parameters():
