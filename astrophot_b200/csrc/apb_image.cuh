@@ -521,25 +521,57 @@ __global__ void __launch_bounds__(256) k_geo_v(const DevSrc* __restrict__ src, c
   const apb_image_t im = imgs[t.x];
   const int b0 = bin_ptr[t.w], b1 = bin_ptr[t.w + 1];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  for (int r = 0; r < 4; ++r) {
-    const int x = t.y + lx, y = t.z + ly + 8 * r;
-    if (x >= im.W || y >= im.H) continue;
-    const long long p = (long long)y * im.W + x;
-    double jh = 0.0;
+  // a thread owns four pixels of one column (rows ly, ly+8, ly+16, ly+24 of the tile): per derivative plane their four
+  // loads are independent and in flight together -- the kernel is a stream over the planes, bound by loads in flight
+  const int x = t.y + lx;
+  double jh[4] = {0.0, 0.0, 0.0, 0.0};
+  if (x < im.W) {
     for (int b = b0; b < b1; ++b) {
       const int si = bin_src[b];
       const DevSrc& s = src[si];
-      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
+      if (x < s.ox || x >= s.ox + s.ow) continue;
+      bool in[4];
+      long long off[4];
+      bool any = false;
+      const bool sky = s.kind == APB_FLAT_SKY;
+      const PlaneView pv = sky ? PlaneView{nullptr, 0} : out_plane(s, 1, 0, stamp, outar);
+      const long long pstride = s.out_off >= 0 ? (long long)s.ow * s.oh : s.plane_stride;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int y = t.z + ly + 8 * r;
+        in[r] = y < im.H && y >= s.oy && y < s.oy + s.oh;
+        off[r] = in[r] ? (long long)(y - s.oy) * pv.stride + (x - s.ox) : 0;
+        any |= in[r];
+      }
+      if (!any) continue;
       for (int e = 0; e < s.n_elem_all; ++e) {
         const int pl = s.plane[e];
         if (pl <= 0) continue;
-        jh += plane_at(s, pl, x, y, stamp, outar, skyJ, si) * h[s.slot[e]];
+        const double hv = h[s.slot[e]];
+        if (sky) {
+          const double c = skyJ[si] * hv;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) jh[r] += in[r] ? c : 0.0;
+        } else {
+          const double* base = pv.p + (long long)pl * pstride;
+          double v[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) v[r] = in[r] ? base[off[r]] : 0.0;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) jh[r] = fma(v[r], hv, jh[r]);
+        }
       }
     }
-    const bool keep = !(im.mask && im.mask[p]);
-    const double w = im.weight ? im.weight[p] : 1.0;
-    const double v = keep ? (2.0 / dstep) * ((rh_inout[t.x][p] - r0[t.x][p]) / dstep - w * jh) : 0.0;
-    rh_inout[t.x][p] = v;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int y = t.z + ly + 8 * r;
+      if (y >= im.H) continue;
+      const long long p = (long long)y * im.W + x;
+      const bool keep = !(im.mask && im.mask[p]);
+      const double w = im.weight ? im.weight[p] : 1.0;
+      const double v = keep ? (2.0 / dstep) * ((rh_inout[t.x][p] - r0[t.x][p]) / dstep - w * jh[r]) : 0.0;
+      rh_inout[t.x][p] = v;
+    }
   }
 }
 
