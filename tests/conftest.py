@@ -14,6 +14,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # a fresh checkout has no built library (it is git-ignored): build it once, like the driver's build() step
+    try:
+        import __graft_entry__ as entry
+        if not os.path.exists(entry.LIB) and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            entry.build()
+    except Exception as e:      # the tests that need the library will say so
+        print(f"conftest: could not build the native library: {e}")
 
 
 def load_golden(name):
