@@ -169,6 +169,7 @@ class LM(BaseOptimizer):
                 self._hs = torch.empty(P + 2, dtype=torch.float64, device=dev)
         self.pcg_iterations = []
         self._warm = None               # (hess version, h, solve(rpp)) of the previous lambda-trial
+        self._pcg_tol = float(kwargs.get("pcg_tol", 1e-12))   # relative residual of the damped solve (accepted up to 1e-10)
         self.n_forward = self.n_jacobian = self.n_trials = 0
 
     # -- damping -------------------------------------------------------------
@@ -218,7 +219,7 @@ class LM(BaseOptimizer):
                 and self._blocks_version == self._hess_version:
             # `loose`: the geodesic correction a = -solve(rpp)/2 when acceleration == 0 only enters the trial through
             # the curvature ratio |a| / |h| compared with curvature_limit (lm.py:282-306): 1e-8 is plenty
-            tol = 1e-8 if loose else 0.0
+            tol = 1e-8 if loose else self._pcg_tol
             if self.distributed:
                 # every rank solves the same merged system; rank 0's answer is the one all use (the split sky row of
                 # the PCG is summed with atomics, so the ranks' solutions may differ in the last bit)
