@@ -65,7 +65,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_plan_set_image_data", "apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_lm_trial_spec", "apb_plan_set_image_data", "apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -102,6 +102,7 @@ def load_library(path=None):
     L.apb_plan_block_doubles.argtypes = [vp]
     L.apb_plan_bind_blocks.argtypes = [vp, dp]
     L.apb_lm_trial.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
+    L.apb_lm_trial_spec.argtypes = [vp, vp, vp, dp, dp, C.c_double, dp, C.c_double, C.c_double, dp, dp, dp, vp]
     L.apb_lm_trial_begin.argtypes = [vp, vp, dp, dp, C.c_double, dp, C.c_double, dp, dp, vp]
     L.apb_lm_trial_end.argtypes = [vp, dp, C.c_double, dp, dp, dp, dp, dp, vp]
     L.apb_plan_stats.argtypes = [vp, C.POINTER(apb_stats_t)]
@@ -327,13 +328,16 @@ class Plan:
                "apb_geodesic")
         return out
 
-    def lm_trial(self, H, g, L, x, d, acceleration, h_out, ha_out, rec, twin=None):
+    def lm_trial(self, H, g, L, x, d, acceleration, h_out, ha_out, rec, twin=None, donor=None):
         """One lambda-trial on the device (fit/lm.py:274-293); rec <- [chi2, flag, |a|, |h|].
-        ``twin``: second Plan of the same scene for the concurrent chi^2 pass (acceleration == 0)."""
-        _check(self._L.apb_lm_trial(self._h, twin._h if twin is not None else None, H.data_ptr(), g.data_ptr(),
-                                    float(L), x.data_ptr(), float(d),
-                                    float(acceleration), h_out.data_ptr(), ha_out.data_ptr(), rec.data_ptr(), _stream()),
-               "apb_lm_trial")
+        ``twin``: second Plan of the same scene for the concurrent chi^2 pass (acceleration == 0).
+        ``donor``: the Plan holding the stamp Jacobian of the last normal_eq when this plan is a forward-only
+        copy running a speculative trial (apb_lm_trial_spec)."""
+        _check(self._L.apb_lm_trial_spec(self._h, twin._h if twin is not None else None,
+                                         donor._h if donor is not None else None, H.data_ptr(), g.data_ptr(),
+                                         float(L), x.data_ptr(), float(d),
+                                         float(acceleration), h_out.data_ptr(), ha_out.data_ptr(), rec.data_ptr(), _stream()),
+               "apb_lm_trial_spec")
         return rec
 
     def lm_trial_begin(self, H, g, L, x, d, h_out, buf, twin=None):

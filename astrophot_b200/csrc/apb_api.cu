@@ -1305,29 +1305,32 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
   return 0;
 }
 
-static int geodesic_core(apb_plan* p, const double* xdh, const double* h, double d, double* rpp, cudaStream_t st);
+static int geodesic_core(apb_plan* p, apb_plan* pj, const double* xdh, const double* h, double d, double* rpp, cudaStream_t st);
 extern "C" int apb_geodesic(apb_plan_t* p, const double* xdh, const double* h, double d, double* rpp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (begin_call(p, st)) return -1;
-  int rc = geodesic_core(p, xdh, h, d, rpp, st);
+  int rc = geodesic_core(p, p, xdh, h, d, rpp, st);
   p->stats.launches = p->launches;
   return rc;
 }
 
-static int geodesic_core(apb_plan* p, const double* xdh, const double* h, double d, double* rpp, cudaStream_t st) {
+// pj: the plan whose last apb_normal_eq left the stamp Jacobian (derivative planes) and the residual r at x; p itself,
+// or -- for a speculative lambda-trial running beside the main one -- another plan of the same scene (only read here:
+// a forward pass never writes derivative planes).
+static int geodesic_core(apb_plan* p, apb_plan* pj, const double* xdh, const double* h, double d, double* rpp, cudaStream_t st) {
   const int P = p->n_par;
   int rc;
   // rh = W (Y(x + d h) - Y): forward pass only touches plane 0, the cached derivative planes stay valid
   if ((rc = sample_pass(p, xdh, 1, 0, 0, st))) return rc;
   if ((rc = assemble(p, 0, nullptr, p->d_resid2, nullptr, 0, st))) return rc;
   PB(K_GEOV);
-  k_geo_v<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, p->d_stamp, p->d_out,
-                                          p->d_skyJ, h, d, p->d_resid, p->d_resid2);
+  k_geo_v<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, pj->d_stamp, pj->d_out,
+                                          pj->d_skyJ, h, d, pj->d_resid, p->d_resid2);
   LAUNCH_CHECK();
   CU(cudaMemsetAsync(rpp, 0, sizeof(double) * (size_t)P, st));
   if (p->n_vitems) {
     PB(K_BLOCKS);
-    k_blocks<<<p->n_vitems, 256, 0, st>>>(p->d_src, p->d_img, p->d_vitems, p->d_stamp, p->d_out, p->d_skyJ, p->d_resid2,
+    k_blocks<<<p->n_vitems, 256, 0, st>>>(p->d_src, p->d_img, p->d_vitems, pj->d_stamp, pj->d_out, pj->d_skyJ, p->d_resid2,
                                           1.0, 1, p->d_part);
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
@@ -1359,11 +1362,23 @@ static int lm_solve_launch(const double* H, const double* g, double L, int P, do
 // term, so when a second, forward-only plan of the same scene is supplied the chi^2 pass runs on
 // it concurrently (own stream, own workspace) with the geodesic pass: both are chains of small
 // latency-bound launches, and side by side they take about the time of one.
+extern "C" int apb_lm_trial_spec(apb_plan_t* p, apb_plan_t* p2, apb_plan_t* donor, const double* H, const double* g,
+                                 double L, const double* x_rep, double d, double acceleration, double* h_out,
+                                 double* ha_out, double* rec, void* stream);
 extern "C" int apb_lm_trial(apb_plan_t* p, apb_plan_t* p2, const double* H, const double* g, double L,
                             const double* x_rep, double d, double acceleration, double* h_out, double* ha_out,
                             double* rec, void* stream) {
+  return apb_lm_trial_spec(p, p2, p, H, g, L, x_rep, d, acceleration, h_out, ha_out, rec, stream);
+}
+
+extern "C" int apb_lm_trial_spec(apb_plan_t* p, apb_plan_t* p2, apb_plan_t* donor, const double* H, const double* g,
+                                 double L, const double* x_rep, double d, double acceleration, double* h_out,
+                                 double* ha_out, double* rec, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (begin_call(p, st)) return -1;
+  if (!donor) donor = p;
+  if (donor->n_par != p->n_par || donor->n_img != p->n_img || donor->n_src != p->n_src)
+    APB_FAIL("apb_lm_trial_spec: the donor plan does not describe the same scene");
   const int P = p->n_par;
   if (P <= 0) APB_FAIL("apb_lm_trial: no parameters");
   const bool overlap = p2 != nullptr && acceleration == 0.0;
@@ -1380,7 +1395,7 @@ extern "C" int apb_lm_trial(apb_plan_t* p, apb_plan_t* p2, const double* H, cons
     if ((rc = chi2_core(p2, p->d_xtmp2, p->d_rec2, p->trial_stream))) return rc;
     CU(cudaEventRecord(p->ev_trial_join, p->trial_stream));
   }
-  if ((rc = geodesic_core(p, p->d_xtmp, h_out, d, p->d_rpp, st))) return rc;
+  if ((rc = geodesic_core(p, donor, p->d_xtmp, h_out, d, p->d_rpp, st))) return rc;
   LmEpi e2{2, x_rep, h_out, d, acceleration, overlap ? p->d_atmp : p->d_xtmp2, ha_out, rec, nullptr};
   if ((rc = lm_solve_launch(H, p->d_rpp, L, P, p->d_atmp2, nullptr, e2, st))) return rc;
   if (overlap) {
@@ -1419,7 +1434,7 @@ extern "C" int apb_lm_trial_begin(apb_plan_t* p, apb_plan_t* p2, const double* H
     if ((rc = chi2_core(p2, p->d_xtmp2, p->d_rec2, p->trial_stream))) return rc;
     CU(cudaEventRecord(p->ev_trial_join, p->trial_stream));
   }
-  if ((rc = geodesic_core(p, p->d_xtmp, h_out, d, buf, st))) return rc;
+  if ((rc = geodesic_core(p, p, p->d_xtmp, h_out, d, buf, st))) return rc;
   if (p2) {
     CU(cudaStreamWaitEvent(st, p->ev_trial_join, 0));
     p->launches += p2->launches;

@@ -156,6 +156,28 @@ class LM(BaseOptimizer):
         if self._fused_trial and self.acceleration == 0 and kwargs.get("overlap_trial", True):
             self.plan2 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
                               share=self.plan)
+        # Speculative lambda search (single GPU, fused trial; OFF by default): the damping of the next trial is
+        # L / Ldn after an improvement, so that trial can be evaluated on a second pair of forward-only plans and a
+        # second stream while the current one runs (apb_lm_trial_spec reads the stamp Jacobian of the main plan).
+        # Same trials, same decisions, same results.  Measured on B200 (config[1]): half of the consumed trials are
+        # correct guesses, but two trials side by side slow each other by almost 2x (the persistent integration
+        # kernel and the FFT passes already occupy every SM), and every wrong guess is wasted work: 654 -> 564 LM
+        # iterations/s.  Kept as an option for problems small enough to leave SMs idle.
+        self._lanes = None
+        self._pending = {}
+        self.n_spec_hits = self.n_spec_launched = 0
+        if self.plan2 is not None and not self.distributed and not self._split_trial and kwargs.get("speculate", False):
+            mk = lambda: torch.empty(P, dtype=torch.float64, device=dev)
+            plan3 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0), share=self.plan)
+            plan4 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0), share=self.plan)
+            self._spec_stream = torch.cuda.Stream(device=dev)
+            self._lanes = [
+                {"plan": self.plan, "twin": self.plan2, "donor": None, "h": self._h, "ha": self._ha, "rec": self._rec,
+                 "event": torch.cuda.Event(), "busy": False},
+                {"plan": plan3, "twin": plan4, "donor": self.plan, "h": mk(), "ha": mk(),
+                 "rec": torch.empty(4, dtype=torch.float64, device=dev), "event": torch.cuda.Event(), "busy": False}]
+            self._ev_ready = torch.cuda.Event()
+        self.speculate = self._lanes is not None      # may be switched off between steps (per-kernel timing)
         self.hess = self.grad = None
         self._hess_version, self._factor_key, self._factor = 0, None, None
         self._blocks_version = -1       # _hess_version whose blocks the plan holds (set by _step, not by natural-units builds)
@@ -193,9 +215,8 @@ class LM(BaseOptimizer):
             c, ok = out.tolist()
             if ok >= 0.0:
                 return c / self.ndf if ok >= 1.0 else float("nan")
-            self.plan.reserve()
-            if self.plan2 is not None:
-                self.plan2.reserve()
+            for pl in self.all_plans:
+                pl.reserve()
         raise OptimizeStop("sub-pixel refinement queues keep overflowing")
 
     def _allreduce_chi(self, c2):
@@ -206,6 +227,54 @@ class LM(BaseOptimizer):
             c2[0] = rec[0]
             c2[1] = torch.where(rec[2] > 0, -1.0, (rec[1] == 0).to(c2.dtype))
         return c2
+
+    @property
+    def all_plans(self):
+        """Every plan this optimiser launches work on (main, chi^2 twin, speculative pair)."""
+        out = [self.plan] + ([self.plan2] if self.plan2 is not None else [])
+        if self._lanes is not None:
+            out += [self._lanes[1]["plan"], self._lanes[1]["twin"]]
+        return out
+
+    def _launch_trial(self, k, L, x, d):
+        """Enqueue the trial at damping L on lane k (0: main stream and plans, 1: speculative stream and plans)."""
+        ln = self._lanes[k]
+        main = torch.cuda.current_stream()
+        stream = main if k == 0 else self._spec_stream
+        if k == 1:
+            stream.wait_event(self._ev_ready)       # the normal equations of this iteration (main stream)
+            x.record_stream(stream)
+        with torch.cuda.stream(stream):
+            ln["plan"].lm_trial(self.hess, self.grad, L, x, d, self.acceleration, ln["h"], ln["ha"], ln["rec"],
+                                twin=ln["twin"], donor=ln["donor"])
+            ln["event"].record(stream)
+        ln["busy"] = True
+        self.n_forward += 2
+        self.n_spec_launched += 1
+
+    def _trial_result(self, x, d):
+        """(chi2 sum, flag, |a|, |h|, ha) of the trial at the current damping: taken from the lane that already runs
+        it, else launched now; the likely next trial (L / Ldn) is started on the other lane before waiting."""
+        k = self._pending.pop(self.L, None)
+        if k is None:
+            k = 0 if not any(v == 0 for v in self._pending.values()) else 1
+            for Lp in [Lp for Lp, v in self._pending.items() if v == k]:
+                del self._pending[Lp]              # a stale guess on that lane: it simply runs out
+            self._launch_trial(k, self.L, x, d)
+        else:
+            self.n_spec_hits += 1
+        nxt = max(1e-9, self.L / self._Ldn)
+        other = 1 - k
+        if nxt != self.L and nxt not in self._pending:
+            for Lp in [Lp for Lp, v in self._pending.items() if v == other]:
+                del self._pending[Lp]
+            self._launch_trial(other, nxt, x, d)
+            self._pending[nxt] = other
+        ln = self._lanes[k]
+        ln["event"].synchronize()
+        ln["busy"] = False
+        csum, ok, na, nh = ln["rec"].tolist()
+        return csum, ok, na, nh, ln["ha"].clone()
 
     def _solve(self, L, rhs, loose=False, x0=None):
         from .cabi import lm_solve
@@ -278,9 +347,9 @@ class LM(BaseOptimizer):
             try:
                 return self._step(chi2)
             except _QueueOverflow:
-                self.plan.reserve()
-                if self.plan2 is not None:
-                    self.plan2.reserve()
+                for pl in self.all_plans:
+                    pl.reserve()
+                self._pending.clear()
                 self.L = L0
         raise OptimizeStop("sub-pixel refinement queues keep overflowing")
 
@@ -288,7 +357,13 @@ class LM(BaseOptimizer):
         """Normal equations once, then search over the damping parameter."""
         x = self.current_state
         self._x_hess = x
+        if self._lanes is not None:
+            # a guess of the previous iteration may still be running: it reads H, g and the stamp Jacobian
+            self._pending.clear()
+            torch.cuda.current_stream().wait_event(self._lanes[1]["event"])
         self.plan.normal_eq(x, as_rep=True, out=(self._H, self._g, self._c2))
+        if self._lanes is not None:
+            self._ev_ready.record()
         self.n_forward += 1
         self.n_jacobian += 1
         if self.distributed:
@@ -318,13 +393,20 @@ class LM(BaseOptimizer):
                     self.plan.lm_trial_begin(self.hess, self.grad, self.L, x, d, self._h, self._tbuf, twin=self.plan2)
                     self._allreduce(self._tbuf)
                     self.plan.lm_trial_end(self.hess, self.L, x, self._h, self._tbuf, self._ha, self._rec)
+                elif self._lanes is not None and self.speculate:
+                    self.n_forward -= 2                        # counted per launch (guesses included)
+                    csum, ok, na, nh, ha = self._trial_result(x, d)
+                    if ok < 0.0:
+                        raise _QueueOverflow()
+                    chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
                 else:
                     self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha,
                                        self._rec, twin=self.plan2)
-                csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
-                if ok < 0.0:
-                    raise _QueueOverflow()
-                ha = self._ha.clone()
+                if not (self._lanes is not None and self.speculate):
+                    csum, ok, na, nh = self._rec.tolist()          # the one host sync of this trial
+                    if ok < 0.0:
+                        raise _QueueOverflow()
+                    ha = self._ha.clone()
                 chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
             else:
                 ha, chi2, na, nh = self._trial_pieces(x, d)

@@ -613,7 +613,9 @@ def run_ours(args):
     # ---- the same K iterations again with every kernel launch bracketed by CUDA events on its stream
     #      (per-kernel durations for the roofline; kept out of `value` because the event records cost time)
     reset()
-    plans = [plan] + ([lm.plan2] if lm.plan2 is not None else [])   # the twin plan runs the concurrent chi^2 passes
+    plans = lm.all_plans     # main plan, chi^2 twin, speculative pair
+    spec = lm.speculate
+    lm.speculate = False     # per-kernel durations are taken without the concurrent guess trials
     for pl in plans:
         pl.profile(True)
         pl.profile_read(reset=True)
@@ -625,6 +627,7 @@ def run_ours(args):
             a = kern.get(kname, (0, 0.0))
             kern[kname] = (a[0] + nl, a[1] + ms)
         pl.profile(False)
+    lm.speculate = spec
     trials = lm.n_trials - trials0
     forwards = lm.n_forward - fwd0
     jacobians = lm.n_jacobian - jac0
@@ -773,7 +776,8 @@ def run_ours(args):
                    "params": len(x0), "lambda_trials_per_iter": trials / args.steps, "forwards_per_iter": forwards / args.steps,
                    "fit_restarts": state["restarts"],
                    "pcg_iterations_mean": (float(np.mean(lm.pcg_iterations)) if lm.pcg_iterations else None),
-                   "pcg_solves": len(lm.pcg_iterations), "block_array_doubles": plan.block_doubles()},
+                   "pcg_solves": len(lm.pcg_iterations), "block_array_doubles": plan.block_doubles(),
+                   "speculative_trials": {"launched": lm.n_spec_launched, "used_guesses": lm.n_spec_hits} if spec else None},
         "clocks": clock_summary,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_pin.numel() * 8,
                 "pipeline": "double-buffered: step k+1's data + weight upload from pinned memory on a copy stream while step k "

@@ -232,6 +232,15 @@ int apb_lm_trial(apb_plan_t *plan, apb_plan_t *plan2, const double *H, const dou
                  const double *x_rep, double d, double acceleration, double *h_out, double *ha_out, double *rec,
                  void *stream);
 
+/* The same trial, run SPECULATIVELY beside another one: `donor` is the plan whose last apb_normal_eq left the stamp
+ * Jacobian and the residual at x (read only), `plan` / `plan2` are forward-only plans of the same scene with their own
+ * workspace.  The lambda search of fit/lm.py:268-357 is sequential, but its next damping is one of two values
+ * (L / Ldn after an improvement, L * Lup after a failure): evaluating the likely one on a second stream while the
+ * current trial runs halves the latency of the search without changing any result. */
+int apb_lm_trial_spec(apb_plan_t *plan, apb_plan_t *plan2, apb_plan_t *donor, const double *H, const double *g, double L,
+                      const double *x_rep, double d, double acceleration, double *h_out, double *ha_out, double *rec,
+                      void *stream);
+
 /* The same trial in two halves for fits sharded over several GPUs (acceleration == 0 only):
  *   begin: h = solve(L, g); buf = { local rpp[n_par], local chi2(x + h), #non-finite, #overflow }
  *   -- the caller sums buf over the ranks (n_par + 3 doubles, one all-reduce per trial) --

@@ -580,3 +580,16 @@ def test_plan_rebinds_image_data():
     plan.set_image_data(0, old["data"], old["weight"], plan._masks.get(0))
     H3, g3, c3 = plan.normal_eq(fix["x0"], check=True)
     assert torch.equal(H3, H0) and torch.equal(g3, g0)
+
+
+def test_speculative_lambda_search_gives_the_same_fit():
+    """LM(speculate=True): the likely next lambda-trial runs on a second stream and a forward-only plan pair
+    (apb_lm_trial_spec with the main plan as Jacobian donor); histories must be identical to the sequential search."""
+    fix = load_golden("psf_sersic")
+    m1, _ = scenes.build(ap, "psf_sersic", data=golden_data(fix))
+    m2, _ = scenes.build(ap, "psf_sersic", data=golden_data(fix))
+    r1 = ap.fit.LM(m1, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0).fit()
+    r2 = ap.fit.LM(m2, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, speculate=True).fit()
+    assert r2._lanes is not None and r2.n_spec_hits > 0 and r1._lanes is None
+    assert r1.loss_history == r2.loss_history and r1.L_history == r2.L_history
+    np.testing.assert_array_equal(np.array(r1.lambda_history), np.array(r2.lambda_history))
