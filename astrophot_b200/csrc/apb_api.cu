@@ -1505,7 +1505,9 @@ extern "C" int apb_plan_stats(apb_plan_t* p, apb_stats_t* out) {
   CU(cudaMemcpy(&ovf, p->q.overflow, sizeof(int), cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
   out->first_pass_evals = p->first_evals[0];
-  for (int d = 1; d <= APB_MAX_DEPTH; ++d) out->queued[d] = cnt[d];
+  // the fused integration kernels only COUNT the entries of depth >= 2 (32-bit atomics): read them as unsigned, a
+  // 16k x 16k mosaic passes 2^31
+  for (int d = 1; d <= APB_MAX_DEPTH; ++d) out->queued[d] = (d >= 2 && p->use_coop) ? (long long)(unsigned int)cnt[d] : cnt[d];
   out->launches = p->stats.launches;
   out->overflow = ovf;
   return 0;
