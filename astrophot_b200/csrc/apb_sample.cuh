@@ -789,16 +789,10 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
   const unsigned gmask = L == 32 ? 0xffffffffu : (((1u << L) - 1u) << (g * L));
   // persistent warps draw tasks (32/L queue entries) from a global counter: a warp that lands on
   // entries needing subdivision simply draws fewer tasks (q.count[0] is zeroed by k_prep)
-  // (the first task of every warp is its own index: no burst of same-address atomics when the grid starts)
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  bool first = true;
   for (;;) {
-    int task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (!first) {
-      if (lane == 0) task = nwarps + atomicAdd(&q.count[0], 1);
-      task = __shfl_sync(0xffffffffu, task, 0);
-    }
-    first = false;
+    int task = 0;
+    if (lane == 0) task = atomicAdd(&q.count[0], 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
     const int base = task * epw;
     if (base >= n) break;
     const int t = base + g;
