@@ -92,7 +92,7 @@ def main(names):
                 f = np.zeros(tuple(t.data.shape))
                 f[t.window.get_self_indices(w)] = d
                 full.append(f)
-            data = scenes.make_data(full, seed)
+            data = scenes.make_data(full, seed, scale=getattr(scenes, "NOISE_SCALE", {}).get(name, 1.0))
             for i, d in data.items():
                 fix[f"data{i}"], fix[f"var{i}"] = d["data"], d["variance"]
             m2, _ = scenes.build(ap, name, data=data)

@@ -249,7 +249,8 @@ def build(ap, name, data=None):
         g = M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
         return g, {}
     if name == "moffat_psf_model":
-        ptar = ap.image.PSF_Image(data=np.zeros((25, 25)), pixelscale=1.0)
+        # a PSF model fitted to a star cut-out held as a PSF_Image (no variance: unit weights)
+        ptar = ap.image.PSF_Image(data=np.zeros((25, 25)) if data is None else data[0]["data"], pixelscale=1.0)
         m = M(name="mpsf", model_type="moffat psf model", target=ptar, parameters={"n": 2.5, "Rd": 3.0})
         return m, {}
     if name == "gaussian_psf_model":
@@ -265,18 +266,20 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
-             "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15}
+             "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
+             "moffat_psf_model": 16}
+NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
 
 
 ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens
 
 
-def make_data(truth_images, seed):
+def make_data(truth_images, seed, scale=1.0):
     """Noisy data + variance from noiseless truth (tests/utils.py:73 recipe)."""
     rng = np.random.default_rng(seed)
     out = {}
     for i, t in enumerate(truth_images):
-        var = 0.1**2 + t / 100.0
+        var = (0.1 * scale) ** 2 + scale * t / 100.0
         out[i] = {"data": t + rng.normal(size=t.shape) * np.sqrt(var), "variance": var}
     return out
 
