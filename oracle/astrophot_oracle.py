@@ -27,6 +27,24 @@ from astrophot_b200 import scene as sc
 
 LN10 = math.log(10.0)
 
+# Host threads for the timed CPU legs of bench.py (numpy releases the GIL inside its array loops): sources of a
+# scene and the planes of a PSF convolution are independent.  1 (the default, used by the tests) = plain loops.
+N_THREADS = 1
+
+
+def set_threads(n):
+    global N_THREADS
+    N_THREADS = max(1, int(n))
+
+
+def _pmap(fn, items):
+    items = list(items)
+    if N_THREADS <= 1 or len(items) <= 1:
+        return [fn(it) for it in items]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(N_THREADS, len(items))) as ex:
+        return list(ex.map(fn, items))
+
 
 def _host(a, dtype=np.float64):
     """numpy view of an array or (possibly CUDA) torch tensor."""
@@ -600,9 +618,9 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, val
     if want_grad:
         grad = np.zeros((ne, oh, ow))
         first = 0 if center_in_grid else 2
-        for e in range(first, ne):
-            if src.slot[e] >= 0:
-                grad[e] = cfn(ddeep_e[e], P)[crop]
+        todo = [e for e in range(first, ne) if src.slot[e] >= 0]
+        for e, plane in zip(todo, _pmap(lambda e: cfn(ddeep_e[e], P)[crop], todo)):
+            grad[e] = plane
         if not center_in_grid:
             # centre enters only through the PSF shift: d shift / d centre = S^-1
             gsx = cfn(deep_e, dP[0])[crop]
@@ -699,13 +717,14 @@ def sample(scene, x, as_rep=True, mode="fwd", conv="direct", stats=None):
     """Model image per scene image: sum of all sources (group_model_object.py:183-231)."""
     vals, _ = _values(scene, x, as_rep)
     out = [np.zeros((im.H, im.W)) for im in scene.images if not getattr(im, "aux", False)]
-    for si, src in enumerate(scene.sources):
-        if getattr(scene.images[src.image], "aux", False):
-            continue        # auxiliary PSF model: sampled by the sources that use it
-        el = source_elements(src, vals)
-        r = sample_source(scene, si, el, mode, False, conv, stats, vals=vals)
-        ox, oy, ow, oh = src.out
-        out[src.image][oy : oy + oh, ox : ox + ow] += r.value
+    todo = [si for si, src in enumerate(scene.sources) if not getattr(scene.images[src.image], "aux", False)]
+    # (auxiliary PSF models are sampled by the sources that use them)
+    st = stats if N_THREADS <= 1 else None        # the counters are not thread-safe
+    res = _pmap(lambda si: sample_source(scene, si, source_elements(scene.sources[si], vals), mode, False, conv, st,
+                                         vals=vals), todo)
+    for si, r in zip(todo, res):
+        ox, oy, ow, oh = scene.sources[si].out
+        out[scene.sources[si].image][oy : oy + oh, ox : ox + ow] += r.value
     return out
 
 
@@ -715,14 +734,19 @@ def jacobian(scene, x, as_rep=True, conv="direct", stats=None):
     vals, dv = _values(scene, x, as_rep)
     P = scene.n_par
     out = [np.zeros((im.H, im.W, P)) for im in scene.images if not getattr(im, "aux", False)]
+    todo = []
     for si, src in enumerate(scene.sources):
         if getattr(scene.images[src.image], "aux", False):
             continue
         aux = src.psf >= 0 and getattr(scene.psfs[src.psf], "source", -1) >= 0
         if all(s < 0 for s in src.slot) and not aux:
             continue
-        el = source_elements(src, vals)
-        r = sample_source(scene, si, el, "jac", True, conv, stats, vals=vals)
+        todo.append(si)
+    st = stats if N_THREADS <= 1 else None
+    res = _pmap(lambda si: sample_source(scene, si, source_elements(scene.sources[si], vals), "jac", True, conv, st,
+                                         vals=vals), todo)
+    for si, r in zip(todo, res):
+        src = scene.sources[si]
         ox, oy, ow, oh = src.out
         for e, s in enumerate(src.slot):
             if s >= 0:
