@@ -495,11 +495,17 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         // shared-memory sequences are skewed (FPAD): i -> i + i/16
         const int ldx = Nx + Nx / 16 + 1, ldy0 = Ny + Ny / 16 + 1;
         // columns per CTA: as many as keep two CTAs per SM resident (<= 110 KB), at least one
+        // (APB_FFT_COL_KB / APB_FFT_NF_MAX / APB_FFT_NT_COLS / APB_FFT_NT_ROWS: tuning knobs for experiments)
+        const char* ekb = getenv("APB_FFT_COL_KB");
+        const size_t col_kb = ekb ? (size_t)atoi(ekb) : 110;
         int nc = 8;
-        while (nc > 1 && (size_t)(2 * nc * (ldy0 + 8)) * sizeof(cpx) > 110 * 1024) nc /= 2;
+        while (nc > 1 && (size_t)(2 * nc * (ldy0 + 8)) * sizeof(cpx) > col_kb * 1024) nc /= 2;
         // row transforms per CTA (each carries two real rows)
-        int nf = std::max(1, std::min(16, 4096 / Nx));
+        const char* enf = getenv("APB_FFT_NF_MAX");
+        int nf = std::max(1, std::min(enf ? atoi(enf) : 16, 4096 / Nx));
         while (nf > 1 && (size_t)(2 * nf * ldx) * sizeof(cpx) > 110 * 1024) --nf;
+        if (const char* e = getenv("APB_FFT_NT_COLS")) p->fft_nt_cols = atoi(e);
+        if (const char* e = getenv("APB_FFT_NT_ROWS")) p->fft_nt_rows = atoi(e);
         // pad the column tile so that a quarter-warp of the transposing load hits 8 distinct 16-byte banks
         int pad = 0, best_conf = 1 << 30;
         for (int pd = 0; pd < 8; ++pd) {
