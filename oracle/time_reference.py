@@ -18,6 +18,8 @@ sys.argv = ["bench.py"]
 import bench  # noqa: E402
 
 ap = import_reference()
+import astrophot_b200.utils as _u  # noqa: E402  (synthetic-PSF helpers: the reference keeps its own under utils.initialize)
+ap.utils.moffat_psf, ap.utils.gaussian_psf = _u.moffat_psf, _u.gaussian_psf
 torch.set_num_threads(os.cpu_count())
 n_iter = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
 truth_model = bench.build_joint(ap, 1, None)
