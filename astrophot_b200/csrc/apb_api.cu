@@ -127,6 +127,7 @@ struct apb_plan {
   BlockDesc* d_vblocks = nullptr; int n_vblocks = 0;
   int *d_act_slot = nullptr, *d_act_off = nullptr;
   double* d_part = nullptr;
+  size_t part_cap = 0;     // work items d_part has room for
   // block-sparse PCG solver (apb_solve.cuh): usable when no parameter is shared between sources
   bool sparse_ok = false;
   bool any_aux_psf = false;   // PSF stamps depend on a PSF-model source sampled in the same pass
@@ -608,9 +609,24 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       PRC(own_upload(p, ctiles, &T.conv_tiles[gr]));
     }
   }
-  if (p->mt[0].conv_smem > 48 * 1024 || p->mt[1].conv_smem > 48 * 1024)
-    PCU(cudaFuncSetAttribute(k_conv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)std::max(p->mt[0].conv_smem, p->mt[1].conv_smem)));
+  // The dynamic shared-memory ceiling is an attribute of the KERNEL, not of a launch: several plans with different
+  // tile sizes live in one process, so every kernel is simply opted in to the device maximum (227 KB on sm_100).
+  {
+    int dev = 0, optin = 227 * 1024;
+    PCU(cudaGetDevice(&dev));
+    PCU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    auto opt_in = [&](const void* fn) -> cudaError_t {
+      cudaFuncAttributes fa;
+      cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    };
+    PCU(opt_in((const void*)k_conv));
+    PCU(opt_in((const void*)k_fft_rows));
+    PCU(opt_in((const void*)k_fft_rows_inv));
+    PCU(opt_in((const void*)k_fft_cols));
+    PCU(opt_in((const void*)k_lm_solve_small));
+  }
 
   // ---- FFT convolution work lists
   for (int gr = 0; gr < 2 && p->n_fft_src; ++gr) {
@@ -664,12 +680,6 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PRC(own_upload(p, fdescs, &p->d_fftdesc));
     PRC(own_upload(p, twid, &p->d_twid));
     PRC(own_alloc(p, (void**)&p->d_spec, sizeof(cpx) * (size_t)spec_total));
-    if (p->fft_smem_rows > 48 * 1024) {
-      PCU(cudaFuncSetAttribute(k_fft_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fft_smem_rows));
-      PCU(cudaFuncSetAttribute(k_fft_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fft_smem_rows));
-    }
-    if (p->fft_smem_cols > 48 * 1024)
-      PCU(cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->fft_smem_cols));
   }
 
   // ---- image tiles and source bins (32x32 pixels)
@@ -952,7 +962,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PRC(own_upload(p, vblocks, &p->d_vblocks));
     PRC(own_upload(p, act_slot, &p->d_act_slot));
     PRC(own_upload(p, act_off, &p->d_act_off));
-    PRC(own_alloc(p, (void**)&p->d_part, sizeof(double) * BLK_VALS * (size_t)std::max(items.size(), vitems.size())));
+    p->part_cap = std::max(items.size(), vitems.size());
+    PRC(own_alloc(p, (void**)&p->d_part, sizeof(double) * BLK_VALS * p->part_cap));
   }
 
   // ---- tables and arenas
@@ -1329,19 +1340,23 @@ static int geodesic_core(apb_plan* p, apb_plan* pj, const double* xdh, const dou
   // rh = W (Y(x + d h) - Y): forward pass only touches plane 0, the cached derivative planes stay valid
   if ((rc = sample_pass(p, xdh, 1, 0, 0, st))) return rc;
   if ((rc = assemble(p, 0, nullptr, p->d_resid2, nullptr, 0, st))) return rc;
+  // everything that reads the stamp Jacobian runs on the DONOR's tables (its sources may be cut differently from
+  // this plan's: a model whose window exceeds image_chunksize is one piece here and one piece per chunk there)
   PB(K_GEOV);
-  k_geo_v<<<p->n_img_tiles, 256, 0, st>>>(p->d_src, p->d_img, p->img_tiles, p->bin_ptr, p->bin_src, pj->d_stamp, pj->d_out,
-                                          pj->d_skyJ, h, d, pj->d_resid, p->d_resid2);
+  k_geo_v<<<pj->n_img_tiles, 256, 0, st>>>(pj->d_src, pj->d_img, pj->img_tiles, pj->bin_ptr, pj->bin_src, pj->d_stamp, pj->d_out,
+                                           pj->d_skyJ, h, d, pj->d_resid, p->d_resid2);
   LAUNCH_CHECK();
   CU(cudaMemsetAsync(rpp, 0, sizeof(double) * (size_t)P, st));
-  if (p->n_vitems) {
+  if (pj->n_vitems) {
+    // partial sums go to this plan's scratch when it is large enough (two trials may share one donor)
+    double* part = p->part_cap >= (size_t)pj->n_vitems ? p->d_part : pj->d_part;
     PB(K_BLOCKS);
-    k_blocks<<<p->n_vitems, 256, 0, st>>>(p->d_src, p->d_img, p->d_vitems, pj->d_stamp, pj->d_out, pj->d_skyJ, p->d_resid2,
-                                          1.0, 1, p->d_part);
+    k_blocks<<<pj->n_vitems, 256, 0, st>>>(pj->d_src, pj->d_img, pj->d_vitems, pj->d_stamp, pj->d_out, pj->d_skyJ, p->d_resid2,
+                                           1.0, 1, part);
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
-    k_block_final<<<dim3(p->n_vblocks, BLK_VALS / 8), 256, 0, st>>>(p->d_src, p->d_vblocks, p->n_vblocks, p->d_act_slot,
-                                                             p->d_act_off, p->d_part, nullptr, rpp, P, 1.0, 1, nullptr, nullptr);
+    k_block_final<<<dim3(pj->n_vblocks, BLK_VALS / 8), 256, 0, st>>>(pj->d_src, pj->d_vblocks, pj->n_vblocks, pj->d_act_slot,
+                                                              pj->d_act_off, part, nullptr, rpp, P, 1.0, 1, nullptr, nullptr);
     LAUNCH_CHECK();
   }
   return 0;
@@ -1351,7 +1366,11 @@ static int lm_solve_launch(const double* H, const double* g, double L, int P, do
                            cudaStream_t st) {
   const size_t smem = sizeof(double) * (size_t)P * (P + 1);
   if (smem > 200 * 1024) APB_FAIL("apb_lm_solve: P too large for the single-CTA solver (max 159); use a library solver");
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_lm_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) {   // (plans opt the kernel in at creation; a bare apb_lm_solve call may come first)
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, (const void*)k_lm_solve_small));
+    CU(cudaFuncSetAttribute(k_lm_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - (int)fa.sharedSizeBytes));
+  }
   k_lm_solve_small<<<1, 256, smem, st>>>(H, g, L, P, h, info, epi);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) APB_FAIL(std::string("apb_lm_solve launch: ") + cudaGetErrorString(e));
@@ -1383,8 +1402,8 @@ extern "C" int apb_lm_trial_spec(apb_plan_t* p, apb_plan_t* p2, apb_plan_t* dono
   cudaStream_t st = (cudaStream_t)stream;
   if (begin_call(p, st)) return -1;
   if (!donor) donor = p;
-  if (donor->n_par != p->n_par || donor->n_img != p->n_img || donor->n_src != p->n_src)
-    APB_FAIL("apb_lm_trial_spec: the donor plan does not describe the same scene");
+  if (donor->n_par != p->n_par || donor->n_img != p->n_img)
+    APB_FAIL("apb_lm_trial_spec: the donor plan does not describe the same fit (parameters, images)");
   const int P = p->n_par;
   if (P <= 0) APB_FAIL("apb_lm_trial: no parameters");
   const bool overlap = p2 != nullptr && acceleration == 0.0;

@@ -153,8 +153,19 @@ class LM(BaseOptimizer):
         # acceleration == 0 (default): chi2(x + h) is independent of the geodesic term; a forward-only twin
         # plan lets apb_lm_trial evaluate it concurrently with the geodesic pass
         self.plan2 = None
+        # A model whose window exceeds image_chunksize is cut into one piece per Jacobian chunk in the main plan (the
+        # reference's chunked Jacobian, lowering.lower).  Forward passes do not need the cut -- and pay for it, every
+        # piece re-evaluates its PSF border: the lambda-trials then run on forward-only plans of the UNCUT scene and
+        # read the stamp Jacobian of the main plan (apb_lm_trial_spec, donor).
+        self.planF = None
+        scene_f = scene
+        if info.chunked and self._fused_trial and not self.distributed and not self._split_trial \
+                and kwargs.get("tiles", None) is None and kwargs.get("W", None) is None:
+            scene_f, _ = lower(model, window=kwargs.get("fit_window", None), for_fit=True, chunk_jacobian=False)
+            self.planF = Plan(scene_f, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
+                              share=self.plan)
         if self._fused_trial and self.acceleration == 0 and kwargs.get("overlap_trial", True):
-            self.plan2 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
+            self.plan2 = Plan(scene_f, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0),
                               share=self.plan)
         # Speculative lambda search (single GPU, fused trial; OFF by default): the damping of the next trial is
         # L / Ldn after an improvement, so that trial can be evaluated on a second pair of forward-only plans and a
@@ -166,7 +177,8 @@ class LM(BaseOptimizer):
         self._lanes = None
         self._pending = {}
         self.n_spec_hits = self.n_spec_launched = 0
-        if self.plan2 is not None and not self.distributed and not self._split_trial and kwargs.get("speculate", False):
+        if self.plan2 is not None and self.planF is None and not self.distributed and not self._split_trial \
+                and kwargs.get("speculate", False):
             mk = lambda: torch.empty(P, dtype=torch.float64, device=dev)
             plan3 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0), share=self.plan)
             plan4 = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0), share=self.plan)
@@ -211,7 +223,7 @@ class LM(BaseOptimizer):
         """chi^2/ndf (host float) of the model at x."""
         self.n_forward += 1
         for _ in range(12):
-            out = self._allreduce_chi(self.plan.chi2(x, out=self._c2))
+            out = self._allreduce_chi((self.planF or self.plan).chi2(x, out=self._c2))
             c, ok = out.tolist()
             if ok >= 0.0:
                 return c / self.ndf if ok >= 1.0 else float("nan")
@@ -231,7 +243,8 @@ class LM(BaseOptimizer):
     @property
     def all_plans(self):
         """Every plan this optimiser launches work on (main, chi^2 twin, speculative pair)."""
-        out = [self.plan] + ([self.plan2] if self.plan2 is not None else [])
+        out = [self.plan] + ([self.plan2] if self.plan2 is not None else []) + \
+            ([self.planF] if self.planF is not None else [])
         if self._lanes is not None:
             out += [self._lanes[1]["plan"], self._lanes[1]["twin"]]
         return out
@@ -399,6 +412,9 @@ class LM(BaseOptimizer):
                     if ok < 0.0:
                         raise _QueueOverflow()
                     chi2 = csum / self.ndf if ok >= 1.0 else float("nan")
+                elif self.planF is not None:
+                    self.planF.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha,
+                                        self._rec, twin=self.plan2, donor=self.plan)
                 else:
                     self.plan.lm_trial(self.hess, self.grad, self.L, x, d, self.acceleration, self._h, self._ha,
                                        self._rec, twin=self.plan2)

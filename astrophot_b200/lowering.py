@@ -33,6 +33,7 @@ class LoweringInfo:
         self.is_list = False
         self.identities = None
         self.components = []    # component model per source
+        self.chunked = False    # some model was cut into Jacobian chunks (window > image_chunksize)
 
 
 def _resolve_leaf(node):
@@ -89,11 +90,12 @@ def _shift_code(name):
     raise SpecificationConflict(f"unrecognized subpixel shift method: {name}")
 
 
-def lower(model, window=None, for_fit=False):
+def lower(model, window=None, for_fit=False, chunk_jacobian=True):
     """Build (Scene, LoweringInfo) for ``model`` evaluated on ``window``
     (default: the model's own window).  ``for_fit`` ORs the model's
     ``fit_mask()`` into each image mask the way ``LM.__init__`` does
-    (`fit/lm.py:204-222`)."""
+    (`fit/lm.py:204-222`).  ``chunk_jacobian=False`` leaves models whose window exceeds ``image_chunksize`` in one
+    piece: right for forward-only plans (the reference never chunks the forward model), see below."""
     from .models import Group_Model, PSF_Model, Point_Source, Component_Model
 
     info = LoweringInfo()
@@ -324,6 +326,38 @@ def lower(model, window=None, for_fit=False):
         else:
             fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
         src = build_source(comp, ii, region, out, fwd, jac)
+        # Windows larger than image_chunksize pixels: the reference evaluates the Jacobian chunk by chunk
+        # (_model_methods.py:349-395), each chunk sampled on its OWN sub-window -- so the integration threshold
+        # (total_flux / numel, mean reference) of the derivative pass is the chunk's, not the window's.  Reproduced by
+        # cutting the source into one piece per chunk: output window = the chunk, Jacobian working window = the chunk,
+        # forward working window unchanged (the forward model is never chunked).  The chunk grid is the reference's,
+        # including its rounding (a remainder smaller than half a chunk is left uncovered by its Jacobian).
+        csize = int(getattr(comp, "image_chunksize", 1000))
+        threshold_kind = comp._kind not in (sc.KIND_FLAT_SKY, sc.KIND_PLANE_SKY, sc.KIND_POINT)
+        if chunk_jacobian and threshold_kind and src.integrate_mode == sc.INTEGRATE_THRESHOLD and max(jac[2], jac[3]) > csize:
+            info.chunked = True
+            ncx, ncy = int(np.ceil(jac[2] / csize)), int(np.ceil(jac[3] / csize))
+            cw, ch = int(np.round(jac[2] / ncx)), int(np.round(jac[3] / ncy))
+            covered = np.zeros((out[3], out[2]), dtype=bool)
+            for nx_ in range(ncx):
+                for ny_ in range(ncy):
+                    x0c, x1c = jac[0] + cw * nx_, jac[0] + min(jac[2], cw * (nx_ + 1))
+                    y0c, y1c = jac[1] + ch * ny_, jac[1] + min(jac[3], ch * (ny_ + 1))
+                    ox0, oy0 = max(out[0], x0c), max(out[1], y0c)
+                    ox1, oy1 = min(out[0] + out[2], x1c), min(out[1] + out[3], y1c)
+                    if ox1 <= ox0 or oy1 <= oy0:
+                        continue
+                    piece = sc.SceneSource(**{**src.__dict__})
+                    piece.out = (ox0, oy0, ox1 - ox0, oy1 - oy0)
+                    piece.jac = (x0c, y0c, x1c - x0c, y1c - y0c)
+                    sources.append(piece)
+                    info.components.append(comp)
+                    covered[oy0 - out[1]:oy1 - out[1], ox0 - out[0]:ox1 - out[0]] = True
+            if not covered.all():
+                raise SpecificationConflict(
+                    f"{comp.name}: window {jac[2]}x{jac[3]} does not divide into image_chunksize={csize} chunks the way the "
+                    "reference rounds them (its Jacobian would skip the last pixels); choose another image_chunksize")
+            continue
         sources.append(src)
         info.components.append(comp)
 

@@ -35,3 +35,9 @@ dt = time.perf_counter() - t0
 its = max(1, len(res.loss_history) - 1)
 print(json.dumps({"workload": "c2 (1024^2 Sersic, 51x51 Moffat PSF)", "cores": os.cpu_count(), "sample_s": t_sample,
                   "lm_iterations": its, "s_per_lm_iteration": dt / its, "loss_history": res.loss_history}))
+# the reference's LM history at FULL size: fixture for tests/test_cuda_fullsize.py (data are regenerated there from the
+# same seeds; the truth images of the two packages agree to 1e-15)
+np.savez_compressed(os.path.join(os.path.dirname(HERE), "tests", "golden", "c2_fullsize_lm.npz"), x0=x0,
+                    loss_history=np.array(res.loss_history), L_history=np.array(res.L_history),
+                    lambda_history=np.array(res.lambda_history), truth_sum=np.array(truth.sum()),
+                    truth_probe=truth[::97, ::89].copy())

@@ -90,3 +90,21 @@ def test_crowded_field_tiles_add_up_and_sparse_solve_matches_dense():
             its, rel = info.tolist()
             assert rel <= 1e-12 and its < 2000
             assert float((h - want).abs().max()) <= 1e-8 * float(want.abs().max())
+
+
+def test_config1_lm_history_matches_the_reference_itself():
+    """BASELINE config[1] at full size against the REFERENCE's own fit (oracle/time_reference.py ran
+    astrophot.fit.LM on the same seeded inputs in the build container): truth image, chi^2 and state per iteration."""
+    fix_path = os.path.join(ROOT, "tests", "golden", "c2_fullsize_lm.npz")
+    if not os.path.exists(fix_path):
+        pytest.skip("full-size reference fixture not generated")
+    fix = dict(np.load(fix_path))
+    ap, model, scene, x0, truth = _workload("c2")
+    np.testing.assert_allclose(x0, fix["x0"], rtol=0, atol=0)
+    assert abs(truth.sum() - float(fix["truth_sum"])) <= 1e-11 * float(fix["truth_sum"])
+    np.testing.assert_allclose(truth[::97, ::89], fix["truth_probe"], rtol=0, atol=1e-10 * float(truth.max()))
+    n = len(fix["loss_history"]) - 1
+    res = ap.fit.LM(model, initial_state=x0, max_iter=n, relative_tolerance=0.0).fit()
+    np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss_history"], rtol=1e-8)
+    np.testing.assert_allclose(res.L_history[: n + 1], fix["L_history"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lambda_history"], rtol=1e-8, atol=1e-8)
