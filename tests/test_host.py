@@ -115,3 +115,42 @@ def test_fit_mask_of_group():
     model, _ = scenes.build(ap, "group_nosky")
     fm = model.fit_mask()
     assert fm.shape == (58, 70) and 0 < int(fm.sum()) < fm.numel()
+
+
+def test_jacobian_chunks_of_large_windows():
+    """A window larger than image_chunksize is cut into the reference's Jacobian chunks (_model_methods.py:349-395):
+    one piece per chunk with the chunk as output and Jacobian working window, the forward working window untouched."""
+    from astrophot_b200.lowering import lower
+    ap.AP_config.ap_device = "cpu"
+    tar = ap.image.Target_Image(data=np.zeros((1300, 2100)), pixelscale=1.0)
+    m = ap.models.AstroPhot_Model(name="big", model_type="sersic galaxy model", target=tar,
+                                  parameters={"center": [1000.0, 600.0], "q": 0.6, "PA": 1.0, "n": 2.0, "Re": 50.0, "Ie": 1.0})
+    scene, info = lower(m)
+    assert info.chunked and len(scene.sources) == 3 * 2           # ceil(2100/1000) x ceil(1300/1000) chunks of 700 x 650
+    assert sorted(s.out for s in scene.sources) == sorted((700 * a, 650 * b, 700, 650) for a in range(3) for b in range(2))
+    assert all(s.jac == s.out and s.fwd == (0, 0, 2100, 1300) for s in scene.sources)
+    assert len({tuple(s.slot) for s in scene.sources}) == 1       # the pieces share the model's parameters
+    whole, info2 = lower(m, chunk_jacobian=False)
+    assert not info2.chunked and len(whole.sources) == 1 and whole.sources[0].out == (0, 0, 2100, 1300)
+    m.image_chunksize = 4000                                      # a user knob of the reference (model_object.py:109)
+    assert len(lower(m)[0].sources) == 1
+    # sky and point models have no integration threshold: never cut
+    sky = ap.models.AstroPhot_Model(name="sk", model_type="flat sky model", target=tar, parameters={"F": -1.0})
+    sky.initialize()
+    assert len(lower(sky)[0].sources) == 1
+
+
+def test_auxiliary_psf_model_survives_tiling_and_sharding():
+    from astrophot_b200.lowering import lower, shard_scene, tile_scene
+    import scenes
+    ap.AP_config.ap_device = "cpu"
+    model, _ = scenes.build(ap, "aux_psf_moffat")
+    scene, _ = lower(model)
+    assert [im.aux for im in scene.images] == [False, True] and scene.psfs[0].source == 0
+    cut = tile_scene(scene, 2, 2)
+    assert [im.aux for im in cut.images] == [False] * 4 + [True] and cut.owners is None
+    for rank in range(2):
+        part = shard_scene(cut, rank, 2)
+        assert [im.aux for im in part.images] == [False, False, True]
+        ps = part.psfs[0]
+        assert part.sources[ps.source].image == 2 and all(s.psf == 0 for s in part.sources if s.image < 2)
