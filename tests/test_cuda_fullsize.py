@@ -108,3 +108,26 @@ def test_config1_lm_history_matches_the_reference_itself():
     np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss_history"], rtol=1e-8)
     np.testing.assert_allclose(res.L_history[: n + 1], fix["L_history"], rtol=1e-12)
     np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lambda_history"], rtol=1e-8, atol=1e-8)
+
+
+def test_config3_band_lm_history_matches_the_reference_itself():
+    """One 2048^2 band of BASELINE config[3] (25x25 Gaussian PSF; its Jacobian is taken in 3 x 3 chunks of 683 / 682
+    pixels) against astrophot.fit.LM run on the same seeded inputs in the build container."""
+    import bench
+    import astrophot_b200 as ap
+    fix_path = os.path.join(ROOT, "tests", "golden", "c4band_fullsize_lm.npz")
+    if not os.path.exists(fix_path):
+        pytest.skip("full-size reference fixture not generated")
+    fix = dict(np.load(fix_path))
+    ap.AP_config.ap_device = "cuda:0"
+    truth = bench.build_c4_band(ap, None, 0)().data.cpu().numpy()
+    assert abs(truth.sum() - float(fix["truth_sum"])) <= 1e-11 * float(fix["truth_sum"])
+    model = bench.build_c4_band(ap, [bench.make_data(truth, 10)], 0)
+    x0 = bench.start_state(model.parameters.vector_representation().numpy(), scale=bench.start_scale("c4"))
+    np.testing.assert_allclose(x0, fix["x0"], rtol=0, atol=0)
+    n = len(fix["loss"]) - 1
+    res = ap.fit.LM(model, initial_state=x0, max_iter=n, relative_tolerance=0.0).fit()
+    assert res.info.chunked and res.planF is not None and len(res.plan.scene.sources) == 9
+    np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)
+    np.testing.assert_allclose(res.L_history[: n + 1], fix["L"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lam"], rtol=1e-8, atol=1e-8)
