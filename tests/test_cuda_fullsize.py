@@ -131,3 +131,23 @@ def test_config3_band_lm_history_matches_the_reference_itself():
     np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)
     np.testing.assert_allclose(res.L_history[: n + 1], fix["L"], rtol=1e-12)
     np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lam"], rtol=1e-8, atol=1e-8)
+
+
+def test_crowded_scale_model_lm_history_matches_the_reference_itself():
+    """The 512^2 scale model of BASELINE config[2] (15 PSF-convolved Sersic + 78 point sources + sky, P = 340: the
+    block-sparse PCG path) against astrophot.fit.LM run on the same seeded inputs in the build container."""
+    import bench
+    import astrophot_b200 as ap
+    fix = dict(np.load(os.path.join(ROOT, "tests", "golden", "c3t_lm.npz")))
+    ap.AP_config.ap_device = "cuda:0"
+    truth = bench.build_crowded(ap, "c3t", None)().data.cpu().numpy()
+    assert abs(truth.sum() - float(fix["truth_sum"])) <= 1e-11 * float(fix["truth_sum"])
+    model = bench.build_crowded(ap, "c3t", bench.make_data(truth, 10))
+    x0 = bench.start_state(model.parameters.vector_representation().numpy(), scale=bench.start_scale("c3t"))
+    np.testing.assert_allclose(x0, fix["x0"], rtol=0, atol=0)
+    n = len(fix["loss"]) - 1
+    res = ap.fit.LM(model, initial_state=x0, max_iter=n, relative_tolerance=0.0).fit()
+    assert len(res.pcg_iterations) > 0 and res._factor is None        # solved on the source-pair blocks
+    np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)
+    np.testing.assert_allclose(res.L_history[: n + 1], fix["L"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lam"], rtol=1e-8, atol=1e-8)
