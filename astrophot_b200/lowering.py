@@ -317,9 +317,11 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             continue
         # Working windows.  The Jacobian is always taken on (own window & requested window) as it is
         # (_model_methods.py:294-299); the forward model on the window it is asked for as it is when one is passed
-        # explicitly (LM: fit/lm.py:199 hands fit_window to every forward), else on the target cut to the model's
-        # window (model_object.py:291-296).  Inside a group both sub-model passes get the group's window
-        # (group_model_object.py:211-227) / its overlap with the sub-model's own (group_model_object.py:258-266).
+        # explicitly (``model(window=...)``), else on the target cut to the model's window (model_object.py:291-296)
+        # -- which is what the reference's LM does: its forward is ``partial(model, as_representation=True)``
+        # without a window (fit/lm.py:173), only its Jacobian sees the uncut window.  Inside a group both sub-model
+        # passes get the group's window (group_model_object.py:211-227) / its overlap with the sub-model's own
+        # (group_model_object.py:258-266).
         jac = _rect_unclipped(region, cwin & asked[ii])
         if explicit:
             fwd = _rect_unclipped(region, asked[ii]) if is_group else jac
