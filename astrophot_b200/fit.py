@@ -689,44 +689,44 @@ class Iter_LM(BaseOptimizer):
             self.ndf -= int(torch.sum(sub.flatten("mask")).item())
         self._count_finish = 0
 
-    def step(self):
+    def _sweep(self, identities):
+        """Boolean masks over ``identities``, one per chunk of this sweep, in the order the reference visits them
+        (`fit/iterative.py:225-275`): an integer ``chunks`` deals the identities out ``chunks`` at a time (front of the
+        remaining list, or ``random.sample`` of it), explicit chunks are taken in order or drawn without replacement."""
         import random
+
+        n = len(identities)
+        where = {pid: k for k, pid in enumerate(identities)}
+
+        def mask_of(pids):
+            m = torch.zeros(n, dtype=torch.bool)
+            m[[where[p] for p in pids]] = True
+            return m
+
+        if isinstance(self.chunks, int):
+            left = list(identities)
+            while left:
+                take = random.sample(left, min(len(left), self.chunks)) if self.method == "random" else left[: self.chunks]
+                m = mask_of(take)
+                left = [pid for pid in left if not m[where[pid]]]
+                yield m
+        elif isinstance(self.chunks, (tuple, list)):
+            left = list(range(len(self.chunks)))
+            while left:
+                k = random.choice(left) if self.method == "random" else left[0]
+                left.remove(k)
+                yield mask_of(self.chunks[k])
+        else:
+            raise ValueError(f"Unrecognized chunks value, should be one of int, tuple. not: {type(self.chunks)}")
+
+    def step(self):
+        """One sweep: every chunk fitted once with the others held fixed, then the bookkeeping of the sweep."""
         from .param import Param_Mask
 
-        param_ids = list(self.model.parameters.vector_identities())
-        init_param_ids = list(param_ids)
-        chunk_index, chunk_choices, res = 0, None, None
+        res = None
         if self.verbose > 0:
             AP_config.ap_logger.info("--------iter-------")
-        while True:
-            chunk = torch.zeros(len(init_param_ids), dtype=torch.bool)
-            if isinstance(self.chunks, int):
-                if len(param_ids) == 0:
-                    break
-                picked = random.sample(param_ids, min(len(param_ids), self.chunks)) if self.method == "random" \
-                    else param_ids[: self.chunks]
-                for pid in picked:
-                    chunk[init_param_ids.index(pid)] = True
-                for pid in np.array(init_param_ids)[chunk.numpy()]:
-                    param_ids.pop(param_ids.index(pid))
-            elif isinstance(self.chunks, (tuple, list)):
-                if chunk_choices is None:
-                    chunk_choices = list(range(len(self.chunks)))
-                if self.method == "random":
-                    if len(chunk_choices) == 0:
-                        break
-                    sub_index = random.choice(chunk_choices)
-                    chunk_choices.pop(chunk_choices.index(sub_index))
-                    for pid in self.chunks[sub_index]:
-                        chunk[param_ids.index(pid)] = True
-                else:
-                    if chunk_index >= len(self.chunks):
-                        break
-                    for pid in self.chunks[chunk_index]:
-                        chunk[param_ids.index(pid)] = True
-                    chunk_index += 1
-            else:
-                raise ValueError(f"Unrecognized chunks value, should be one of int, tuple. not: {type(self.chunks)}")
+        for chunk in self._sweep(list(self.model.parameters.vector_identities())):
             if self.verbose > 1:
                 AP_config.ap_logger.info(str(chunk))
             with Param_Mask(self.model.parameters, chunk):
@@ -735,11 +735,9 @@ class Iter_LM(BaseOptimizer):
                 AP_config.ap_logger.info(f"chunk loss: {res.res_loss()}")
         self.loss_history.append(res.res_loss())
         self.lambda_history.append(self.model.parameters.vector_representation().detach().cpu().numpy())
-        if self.iteration >= 2 and (-self.relative_tolerance * 1e-3) < (
-                (self.loss_history[-2] - self.loss_history[-1]) / self.loss_history[-1]) < (self.relative_tolerance / 10):
-            self._count_finish += 1
-        else:
-            self._count_finish = 0
+        gain = (self.loss_history[-2] - self.loss_history[-1]) / self.loss_history[-1] if self.iteration >= 2 else None
+        flat = gain is not None and -self.relative_tolerance * 1e-3 < gain < self.relative_tolerance / 10
+        self._count_finish = self._count_finish + 1 if flat else 0
         self.iteration += 1
 
     def fit(self):

@@ -154,3 +154,42 @@ def test_auxiliary_psf_model_survives_tiling_and_sharding():
         assert [im.aux for im in part.images] == [False, False, True]
         ps = part.psfs[0]
         assert part.sources[ps.source].image == 2 and all(s.psf == 0 for s in part.sources if s.image < 2)
+
+
+def test_iter_lm_visits_the_chunks_like_the_reference():
+    """Iter_LM._sweep against the reference's selection rules (fit/iterative.py:225-275), restated here: integer
+    chunks deal the identities out from the front / by random.sample of the remaining ones, explicit chunks go in
+    order / by random.choice without replacement -- same RNG calls, so the same sweep under the same seed."""
+    import random
+    import scenes
+    from astrophot_b200.fit import Iter_LM
+    ap.AP_config.ap_device = "cpu"
+    model, _ = scenes.build(ap, "group_nosky")
+    ids = list(model.parameters.vector_identities())
+    assert len(ids) == 13
+
+    def expected(chunks, method, seed):
+        random.seed(seed)
+        out, left = [], list(ids)
+        if isinstance(chunks, int):
+            while left:
+                take = random.sample(left, min(len(left), chunks)) if method == "random" else left[:chunks]
+                out.append(sorted(ids.index(p) for p in take))
+                left = [p for p in left if p not in take]
+        else:
+            choices = list(range(len(chunks)))
+            while choices:
+                k = random.choice(choices) if method == "random" else choices[0]
+                choices.remove(k)
+                out.append(sorted(ids.index(p) for p in chunks[k]))
+        return out
+
+    explicit = (tuple(ids[0:5]), tuple(ids[5:6]), tuple(ids[6:13]))
+    for chunks in (5, 13, 50, explicit):
+        for method in ("sequential", "random"):
+            opt = Iter_LM(model, initial_state=np.zeros(13), chunks=chunks, method=method)
+            for seed in (0, 7):
+                random.seed(seed)
+                got = [sorted(np.flatnonzero(m.numpy()).tolist()) for m in opt._sweep(ids)]
+                assert got == expected(chunks, method, seed), (chunks, method, seed)
+                assert sorted(sum(got, [])) == list(range(13))      # every parameter exactly once per sweep
