@@ -193,3 +193,42 @@ def test_iter_lm_visits_the_chunks_like_the_reference():
                 got = [sorted(np.flatnonzero(m.numpy()).tolist()) for m in opt._sweep(ids)]
                 assert got == expected(chunks, method, seed), (chunks, method, seed)
                 assert sorted(sum(got, [])) == list(range(13))      # every parameter exactly once per sweep
+
+
+def test_iter_lm_control_flow_on_the_oracle(monkeypatch):
+    """Iter_LM end to end without a GPU: the per-chunk LM is replaced by the CPU oracle's LM on the scene lowered
+    under the chunk's Param_Mask; the sweep history must reproduce the reference's (golden `iterlm_*`)."""
+    import astrophot_oracle as orc
+    import scenes
+    from astrophot_b200 import fit as fitmod
+    from astrophot_b200.lowering import lower
+    from conftest import load_golden, golden_data
+
+    class OracleLM:
+        def __init__(self, model, ndf=None, max_iter=100, relative_tolerance=1e-5, **kw):
+            self.model, self.ndf, self.max_iter, self.rtol = model, ndf, max_iter, relative_tolerance
+
+        def fit(self):
+            scene, _ = lower(self.model, for_fit=True)
+            x0 = self.model.parameters.vector_representation().numpy()
+            self.r = orc.lm_fit(scene, x0, max_iter=self.max_iter, relative_tolerance=self.rtol, ndf=self.ndf)
+            loss = np.array(self.r["loss_history"])
+            ok = np.isfinite(loss)
+            best = np.array(self.r["lambda_history"])[ok][np.argmin(loss[ok])]
+            self.model.parameters.vector_set_representation(torch.as_tensor(best))
+            return self
+
+        def res_loss(self):
+            loss = np.array(self.r["loss_history"])
+            return float(np.min(loss[np.isfinite(loss)]))
+
+    ap.AP_config.ap_device = "cpu"
+    monkeypatch.setattr(fitmod, "LM", OracleLM)
+    for name in scenes.ITER_SCENES:
+        fix = load_golden(name)
+        model, _ = scenes.build(ap, name, data=golden_data(fix))
+        model.parameters.vector_set_representation(torch.as_tensor(fix["x0"]))
+        res = fitmod.Iter_LM(model, initial_state=fix["x0"], chunks=8, method="sequential", max_iter=2,
+                             LM_kwargs={"max_iter": 3, "relative_tolerance": 0.0}).fit()
+        np.testing.assert_allclose(res.loss_history, fix["iterlm_loss_history"], rtol=1e-8)
+        np.testing.assert_allclose(np.array(res.lambda_history), fix["iterlm_lambda_history"], rtol=1e-7, atol=1e-7)
