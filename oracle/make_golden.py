@@ -82,8 +82,8 @@ def main(names):
                 idx = np.sort(rng.choice(Jflat.shape[0], size=min(3000, Jflat.shape[0]), replace=False))
                 fix["jac_idx"] = idx
             fix[f"jac_{tag}"] = Jflat[fix["jac_idx"]]
-        if name in scenes.LM_SCENES:
-            seed = scenes.LM_SCENES[name]
+        if name in scenes.ALL_LM_SCENES:
+            seed = scenes.ALL_LM_SCENES[name]
             # embed the truth in full-size target frames (group windows may be smaller)
             tars = model.target.image_list if hasattr(model.target, "image_list") else [model.target]
             wins = model.window.window_list if hasattr(model.window, "window_list") else [model.window]

@@ -210,6 +210,16 @@ def build(ap, name, data=None):
               integrate_quad_level=2, sampling_tolerance=3e-3,
               parameters={"center": [30.6, 33.2], "q": 0.5, "PA": 2.0, "n": 3.5, "Re": 6.0, "Ie": 0.7})
         return m, {}
+    if name == "group_edge":
+        # a group whose sub-model windows stick out of the image on two sides (group window = their union)
+        psf = ap.image.PSF_Image(data=_psf_gauss(1.1, 7), pixelscale=1.0)
+        tar = _target(ap, (64, 72), data, psf=psf)
+        m1 = M(name="ge1", model_type="sersic galaxy model", target=tar, psf_mode="full", window=[[-10, 30], [20, 70]],
+               parameters={"center": [8.3, 50.6], "q": 0.7, "PA": 0.4, "n": 2.2, "Re": 5.0, "Ie": 0.9})
+        m2 = M(name="ge2", model_type="exponential galaxy model", target=tar, window=[[40, 80], [-6, 30]],
+               parameters={"center": [60.4, 10.7], "q": 0.6, "PA": 2.2, "Re": 4.0, "Ie": 0.7})
+        g = M(name="grp_edge", model_type="group model", models=[m1, m2], target=tar, psf_mode="full")
+        return g, {}
     if name == "joint":
         tars, models = [], []
         for b in range(3):
@@ -264,10 +274,14 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs"]
+# scenes checked on the CPU only (oracle vs reference): added after the round's GPU budget was spent
+CPU_ONLY_SCENES = ["group_edge"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
              "moffat_psf_model": 16}
+CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
+ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
 
 

@@ -11,7 +11,7 @@ from astrophot_b200.lowering import lower
 from conftest import load_golden, golden_data, rel_err
 
 
-@pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
+@pytest.mark.parametrize("name", scenes.SAMPLE_SCENES + scenes.CPU_ONLY_SCENES)
 def test_sample_matches_reference(name):
     fix = load_golden(name)
     model, _ = scenes.build(ap, name)
@@ -29,7 +29,7 @@ def test_sample_matches_reference(name):
             np.testing.assert_allclose(im, ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max() * 1e-6)
 
 
-@pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
+@pytest.mark.parametrize("name", scenes.SAMPLE_SCENES + scenes.CPU_ONLY_SCENES)
 @pytest.mark.parametrize("tag", ["rep", "nat"])
 def test_jacobian_matches_reference(name, tag):
     fix = load_golden(name)
@@ -47,7 +47,7 @@ def test_jacobian_matches_reference(name, tag):
     assert np.max(np.abs(jtj - fix[f"jtj_{tag}"]) / np.outer(d, d)) < 1e-9, name
 
 
-@pytest.mark.parametrize("name", list(scenes.LM_SCENES))
+@pytest.mark.parametrize("name", list(scenes.ALL_LM_SCENES))
 def test_lm_matches_reference(name):
     fix = load_golden(name)
     model, _ = scenes.build(ap, name, data=golden_data(fix))
