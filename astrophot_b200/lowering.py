@@ -269,6 +269,10 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
                     psfs.append(sc.ScenePSF(data=None, source=psrc, shape=shape))
                 psf_index[id(psf)] = len(psfs) - 1
             pidx = psf_index[id(psf)]
+        if comp._kind == sc.KIND_POINT and comp.psf_subpixel_shift == "none":
+            # the reference shifts a point source's PSF unconditionally (point_source.py:157-162 -> _shift_psf), which
+            # has no "none" method: same error here
+            raise SpecificationConflict("unrecognized subpixel shift method: none")
         flags = comp._flags
         if isinstance(comp, PSF_Model) and comp.normalize_psf:
             flags |= sc.FLAG_NORMALIZE
