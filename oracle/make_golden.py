@@ -115,6 +115,15 @@ def main(names):
             res.update_uncertainty()
             fix["uncertainty"] = m2.parameters.vector_uncertainty().detach().cpu().numpy()
             print(name, "LM:", res.message, res.loss_history)
+            if name in getattr(scenes, "LM_KWARGS_SCENES", ()):
+                # the same fit with non-default LM knobs (geodesic acceleration on, other damping schedule)
+                m5, _ = scenes.build(ap, name, data=data)
+                r5 = ap.fit.LM(m5, initial_state=x0, max_iter=6, relative_tolerance=0.0, verbose=0,
+                               **scenes.LM_KWARGS).fit()
+                fix["kw_loss_history"] = np.array(r5.loss_history)
+                fix["kw_L_history"] = np.array(r5.L_history)
+                fix["kw_lambda_history"] = np.array(r5.lambda_history)
+                print(name, "LM kwargs:", r5.message, r5.loss_history)
             if name in getattr(scenes, "ITER_SCENES", ()):
                 # fit/iterative.py Iter: 3 sweeps, every sub-fit 4 LM iterations (fixed counts on both sides)
                 m3, _ = scenes.build(ap, name, data=data)

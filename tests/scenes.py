@@ -286,6 +286,8 @@ NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to t
 
 
 ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens
+LM_KWARGS_SCENES = ("psf_sersic",)         # also fitted with non-default LM knobs
+LM_KWARGS = dict(acceleration=0.7, curvature_limit=0.6, Lup=7.0, Ldn=5.0, L0=3.0, max_step_iter=8)
 
 
 def make_data(truth_images, seed, scale=1.0):
