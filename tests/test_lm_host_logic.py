@@ -22,6 +22,10 @@ class OraclePlan:
     def block_doubles(self):
         return 0
 
+    def sample(self, x, as_rep=False):
+        x = np.asarray(torch.as_tensor(x).cpu().numpy(), dtype=np.float64)
+        return [torch.as_tensor(m) for m in orc.sample(self.scene, x, as_rep)]
+
     def reserve(self, caps=None):
         pass
 
@@ -124,3 +128,14 @@ def test_lm_non_default_knobs(host_only, name):
     np.testing.assert_allclose(res.L_history[:moving - 1], fix["kw_L_history"][:moving - 1], rtol=1e-12)
     for k in range(moving):
         np.testing.assert_allclose(res.lambda_history[k], fix["kw_lambda_history"][k], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", list(scenes.ITER_SCENES))
+def test_iter_control_flow_reproduces_the_reference(host_only, name):
+    """fit.Iter (sub-models one at a time on the residual image) end to end on the stand-in plan."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    res = ap.fit.Iter(model, initial_state=fix["x0"], max_iter=3,
+                      method_kwargs={"max_iter": 4, "relative_tolerance": 0.0, "fused_trial": False}).fit()
+    np.testing.assert_allclose(res.loss_history, fix["iter_loss_history"], rtol=1e-8)
+    np.testing.assert_allclose(np.array(res.lambda_history), fix["iter_lambda_history"], rtol=1e-7, atol=1e-7)
