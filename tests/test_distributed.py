@@ -141,3 +141,46 @@ def test_tile_sharded_normal_equations_allreduce(tmp_path):
     assert np.max(np.abs(g - fix["grad0"])) / np.abs(fix["grad0"]).max() < 1e-9
     npix = 192 * 192
     assert abs(chi2 / (npix - P) - fix["loss_history"][0]) / fix["loss_history"][0] < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# the whole distributed LM (fit.LM(distributed=True, tiles=...)) on CPU: gloo ranks, oracle-backed stand-in plans
+# ---------------------------------------------------------------------------
+def _lm_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import astrophot_b200 as ap
+    import scenes
+    from astrophot_b200 import cabi
+    from test_lm_host_logic import OraclePlan, _solve
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ap.AP_config.ap_device = "cpu"
+    cabi.Plan, cabi.lm_solve = OraclePlan, _solve
+    fix = load_golden("group")
+    model, _ = scenes.build(ap, "group", data=golden_data(fix))
+    res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=4, relative_tolerance=0.0, distributed=True, tiles=(2, 1),
+                    fused_trial=False).fit()
+    assert len(res.plan.shapes) == 1              # one of the two tiles
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "lm_tiles.npz"), loss=np.array(res.loss_history), L=np.array(res.L_history),
+                 lam=np.array(res.lambda_history))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_tiled_lm_control_flow(tmp_path):
+    """Two gloo ranks, one image tile each: the ranks' normal equations, geodesic right-hand sides and chi^2 records
+    are all-reduced where fit.LM says, every rank takes the same decisions, and the history is the reference's."""
+    world = 2
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_lm_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "lm_tiles.npz")
+    fix = load_golden("group")
+    n = len(got["loss"])
+    np.testing.assert_allclose(got["loss"], fix["loss_history"][:n], rtol=1e-8)
+    np.testing.assert_allclose(got["L"][:4], fix["L_history"][:4], rtol=1e-12)
+    np.testing.assert_allclose(got["lam"], fix["lambda_history"][:n], rtol=1e-8, atol=1e-8)
