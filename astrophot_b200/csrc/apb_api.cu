@@ -44,11 +44,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_PCG, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_PCG, K_AMP, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad", "k_pcg"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad", "k_pcg", "k_amp"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -96,6 +96,7 @@ struct apb_plan {
   int* psf_list = nullptr; int n_psf_list = 0;      // sources needing a shifted PSF stamp
   int* point_list = nullptr; int n_point = 0;
   int* norm_list = nullptr; int n_norm = 0;
+  int* amp_list = nullptr; int n_amp = 0;     // APB_F_AMP sources
   bool any_threshold = false, all_same_geo = true;
   int max_depth = 1;
   int NVp_grad = 1;
@@ -176,7 +177,7 @@ static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 extern "C" const char* apb_last_error(void) { return g_err.c_str(); }
 static int fft_len(int n);
 extern "C" int apb_fft_length(int n) { return n > 0 ? fft_len(n) : 0; }
-extern "C" int apb_version(void) { return 102; }
+extern "C" int apb_version(void) { return 103; }
 
 static void gauss_legendre(int n, double* x, double* w) {
   // Newton iteration on P_n (same nodes as scipy.special.roots_legendre to rounding)
@@ -366,7 +367,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   std::vector<DevSrc>& S = p->h_src;
   S.resize(n_src);
   long long stamp_total = 0, out_total = 0, psfst_total = 0, spec_total = 0;
-  std::vector<int> psf_list, point_list, norm_list, act_slot, act_off(n_src + 1, 0);
+  std::vector<int> psf_list, point_list, norm_list, amp_list, act_slot, act_off(n_src + 1, 0);
   int max_nact = 0;
   std::vector<FftDesc> fdescs;
   std::vector<cpx> twid;
@@ -410,13 +411,18 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       PFAIL("plane sky: 5 elements, no PSF, no sub-pixel integration");
     if (a.image < 0 || a.image >= n_img) PFAIL("source image index out of range");
     if (a.n_elem < 3 || a.n_elem > APB_MAX_ELEM) PFAIL("bad n_elem");
+    // APB_F_AMP: the last element is the amplitude; the profile sees the elements before it
+    const bool has_amp = (a.flags & APB_F_AMP) != 0;
+    const int n_el = a.n_elem - (has_amp ? 1 : 0);
+    if (has_amp && (a.kind == APB_POINT || a.kind == APB_FLAT_SKY || a.kind == APB_PLANE_SKY || a.psf >= 0 || n_el < 4))
+      PFAIL("APB_F_AMP: a profile source without PSF whose last element is the amplitude");
     if (a.sampling_mode < APB_SAMPLE_MIDPOINT || a.sampling_mode > APB_SAMPLE_TRAPEZOID) PFAIL("unknown sampling_mode");
     if (a.max_depth < 1 || a.max_depth > APB_MAX_DEPTH) PFAIL("integrate_max_depth out of range (1..4)");
     if (a.quad_level < 1 || a.quad_level > APB_MAX_QUAD || a.quad_init < 1 || a.quad_init > APB_MAX_QUAD)
       PFAIL("quadrature level out of range (1..9)");
     if (a.gridding < 1 || a.gridding > 16) PFAIL("integrate_gridding out of range (1..16)");
     const apb_image_t& im = img[a.image];
-    s.kind = a.kind; s.flags = a.flags; s.image = a.image; s.n_elem = a.n_elem;
+    s.kind = a.kind; s.flags = a.flags; s.image = a.image; s.n_elem = n_el;
     s.ox = a.out[0]; s.oy = a.out[1]; s.ow = a.out[2]; s.oh = a.out[3];
     if (s.ow <= 0 || s.oh <= 0 || s.ox < 0 || s.oy < 0 || s.ox + s.ow > im.W || s.oy + s.oh > im.H)
       PFAIL("source output window outside its image");
@@ -426,7 +432,10 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       if (a.slot[e] >= n_par) PFAIL("parameter slot out of range");
       if (a.slot[e] >= 0) { s.plane[e] = ++s.n_act; act_slot.push_back(a.slot[e]); } else s.plane[e] = 0;
     }
-    s.n_elem_all = s.n_elem; s.psf_src = -1; s.n_pp = 0;
+    // (with APB_F_AMP the loop above has already filed the amplitude as pseudo-element n_elem: its plane is the last)
+    s.n_elem_all = a.n_elem; s.psf_src = -1; s.n_pp = 0;
+    s.amp_elem = has_amp ? n_el : -1;
+    if (has_amp) amp_list.push_back(i);
     if (a.psf >= 0 && a.psf < n_psf && psf[a.psf].source >= 0 && a.kind != APB_FLAT_SKY) {
       // auxiliary PSF model: its free parameters become pseudo-elements (and derivative planes) of this source
       if (a.kind == APB_POINT) PFAIL("point sources with a PSF model are not supported");
@@ -444,7 +453,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     act_off[i + 1] = (int)act_slot.size();
     max_nact = std::max(max_nact, s.n_act);
     s.n_prof = a.n_prof;
-    if (a.kind == APB_SPLINE && (a.n_prof < 2 || a.n_prof > APB_MAX_PROF || a.n_elem != 4 + a.n_prof))
+    if (a.kind == APB_SPLINE && (a.n_prof < 2 || a.n_prof > APB_MAX_PROF || n_el != 4 + a.n_prof))
       PFAIL("spline source needs 2..20 nodes and n_elem = 4 + n_prof");
     for (int k = 0; k < a.n_prof && k < APB_MAX_PROF; ++k) s.prof[k] = a.prof[k];
     s.sampling_mode = a.sampling_mode; s.quad_init = a.quad_init; s.integrate_mode = a.integrate_mode;
@@ -975,6 +984,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   PRC(own_upload(p, psf_list, &p->psf_list)); p->n_psf_list = (int)psf_list.size();
   PRC(own_upload(p, point_list, &p->point_list)); p->n_point = (int)point_list.size();
   PRC(own_upload(p, norm_list, &p->norm_list)); p->n_norm = (int)norm_list.size();
+  PRC(own_upload(p, amp_list, &p->amp_list)); p->n_amp = (int)amp_list.size();
   PRC(own_alloc(p, (void**)&p->d_stamp, sizeof(double) * (size_t)stamp_total));
   PRC(own_alloc(p, (void**)&p->d_out, sizeof(double) * (size_t)out_total));
   PRC(own_alloc(p, (void**)&p->d_psfst, sizeof(double) * (size_t)psfst_total));
@@ -1184,6 +1194,11 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
     if (p->n_norm) {
       PB(K_NORM);
       k_normalize<<<p->n_norm, 256, 0, st>>>(p->d_src, p->norm_list, mode, p->d_stamp, grad);
+      LAUNCH_CHECK();
+    }
+    if (p->n_amp) {
+      PB(K_AMP);
+      k_amp<<<p->n_amp, 256, 0, st>>>(p->d_src, p->d_dyn, p->amp_list, mode, p->d_stamp, grad);
       LAUNCH_CHECK();
     }
   }

@@ -31,6 +31,9 @@ struct DevSrc {
   // auxiliary PSF model: its n_pp free parameters are pseudo-elements n_elem .. n_elem_all-1 of this source
   // (slot / plane filled, never seen by the profile evaluation); psf_src = the source that samples the PSF
   int n_elem_all, psf_src, n_pp;
+  // APB_F_AMP: pseudo-element (slot / cval / plane filled, value and chain factor in DevDyn::el / chain) holding the
+  // log10 amplitude applied by k_amp after sampling and normalisation; -1 = none
+  int amp_elem;
   int n_prof;
   double prof[APB_MAX_PROF];
   int sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth, ref_mode;

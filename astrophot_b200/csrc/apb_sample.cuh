@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(128) k_prep(const DevSrc* __restrict__ src, De
   if (si >= n_src) return;
   const DevSrc& s = src[si];
   DevDyn& d = dyn[si];
-  for (int e = lane; e < s.n_elem; e += 32) {
+  // (the amplitude pseudo-element of an APB_F_AMP source sits right after the profile's elements)
+  for (int e = lane; e < s.n_elem + (s.amp_elem >= 0 ? 1 : 0); e += 32) {
     const int sl = s.slot[e];
     double v = s.cval[e], ch = 0.0;
     if (sl >= 0) {
@@ -1055,7 +1056,9 @@ __global__ void __launch_bounds__(256) k_normalize(const DevSrc* __restrict__ sr
   __syncthreads();
   const double tot = tot_s;
   const int np = grad ? s.n_act : 0;
+  const int pamp = s.amp_elem >= 0 ? s.plane[s.amp_elem] : 0;   // written by k_amp afterwards
   for (int p = 1; p <= np; ++p) {
+    if (p == pamp) continue;
     double* pp = p0 + (long long)p * s.plane_stride;
     v = 0.0;
     for (int q = threadIdx.x; q < n; q += 256) v += pp[(long long)(q / g.ew) * g.mw + (q % g.ew)];
@@ -1072,5 +1075,35 @@ __global__ void __launch_bounds__(256) k_normalize(const DevSrc* __restrict__ sr
   for (int q = threadIdx.x; q < n; q += 256) {
     const long long o = (long long)(q / g.ew) * g.mw + (q % g.ew);
     p0[o] = p0[o] / tot;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// APB_F_AMP: point source drawn from a PSF *model* (point_source.py:122-140).  The sampled (and normalised) PSF-model
+// stamp and its derivative planes are scaled by A = 10^flux; the flux plane is ln10 A value (times the chain factor
+// of the flux parameter).  One CTA per source, over the evaluation region (= the output window: no PSF border).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_amp(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+                                             const int* __restrict__ list, int mode, double* __restrict__ stamp,
+                                             int grad) {
+  const int si = list[blockIdx.x];
+  const DevSrc& s = src[si];
+  const DevDyn& d = dyn[si];
+  const Geo& g = s.geo[mode];
+  const int n = g.ew * g.eh;
+  const long long off0 = (long long)(g.ey0 - g.my0) * g.mw + (g.ex0 - g.mx0);
+  double* p0 = stamp + s.stamp_off + off0;
+  const double A = exp10(d.el[s.amp_elem]);
+  const int pamp = s.plane[s.amp_elem];
+  const double ca = APB_LN10 * d.chain[s.amp_elem];
+  const int np = grad ? s.n_act : 0;
+  for (int q = threadIdx.x; q < n; q += 256) {
+    const long long o = (long long)(q / g.ew) * g.mw + (q % g.ew);
+    const double v = A * p0[o];
+    p0[o] = v;
+    for (int p = 1; p <= np; ++p) {
+      double* pp = p0 + (long long)p * s.plane_stride;
+      pp[o] = (p == pamp) ? ca * v : A * pp[o];
+    }
   }
 }

@@ -96,7 +96,7 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
     ``fit_mask()`` into each image mask the way ``LM.__init__`` does
     (`fit/lm.py:204-222`).  ``chunk_jacobian=False`` leaves models whose window exceeds ``image_chunksize`` in one
     piece: right for forward-only plans (the reference never chunks the forward model), see below."""
-    from .models import Group_Model, PSF_Model, Point_Source, Component_Model
+    from .models import AstroPhot_Model, Group_Model, PSF_Model, Point_Source, Component_Model
 
     info = LoweringInfo()
     target = model.target
@@ -175,8 +175,10 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
 
     psfs, psf_index = [], {}
 
-    def build_source(comp, ii, region, out, fwd, jac):
-        if comp.mask is not None:
+    def build_source(comp, ii, region, out, fwd, jac, host=None):
+        """``host``: the point source that draws ``comp`` (a PSF model) at its own centre, times 10^flux
+        (point_source.py:122-140)."""
+        if comp.mask is not None or (host is not None and host.mask is not None):
             raise SpecificationConflict("per-model masks are not supported by astrophot_b200 yet")
         # elements
         names = list(sc.ELEMS[comp._kind])
@@ -185,7 +187,7 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             have = set(comp._parameter_order)
         for nm in names:
             if nm in ("cx", "cy"):
-                nodes.append((comp.parameters["center"], 0 if nm == "cx" else 1))
+                nodes.append(((comp if host is None else host).parameters["center"], 0 if nm == "cx" else 1))
             elif nm in ("dx", "dy"):          # plane sky slopes: the two elements of `delta`
                 nodes.append((comp.parameters["delta"], 0 if nm == "dx" else 1))
             elif isinstance(comp, PSF_Model) and nm in ("q", "PA") and nm not in have:
@@ -204,6 +206,10 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
                 raise SpecificationConflict("extend_profile=False is not supported by astrophot_b200")
             for k in range(len(prof)):
                 nodes.append((comp.parameters["I(R)"], k))
+        if host is not None:
+            nodes.append((host.parameters["flux"], 0))      # FLAG_AMP: the last element
+            if len(nodes) > sc.MAX_ELEM:
+                raise SpecificationConflict(f"{host.name}: too many elements for one source")
         slot, cval = [], []
         for node, e in nodes:
             if node is None:
@@ -261,21 +267,26 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
                 if isinstance(psf, PSF_Image):
                     psfs.append(sc.ScenePSF(data=psf.data.contiguous()))
                 else:
-                    if comp._kind == sc.KIND_POINT:
-                        raise SpecificationConflict(
-                            "point sources with a PSF *model* (point_source.py:122-140) are not lowered yet; "
-                            "sample the PSF model once and pass the PSF_Image")
                     psrc, shape = aux_psf_source(psf)
                     psfs.append(sc.ScenePSF(data=None, source=psrc, shape=shape))
                 psf_index[id(psf)] = len(psfs) - 1
             pidx = psf_index[id(psf)]
         if comp._kind == sc.KIND_POINT and comp.psf_subpixel_shift == "none":
-            # the reference shifts a point source's PSF unconditionally (point_source.py:157-162 -> _shift_psf), which
-            # has no "none" method: same error here
+            # the reference shifts a point source's PSF image unconditionally (point_source.py:157-162 -> _shift_psf),
+            # which has no "none" method: same error here
             raise SpecificationConflict("unrecognized subpixel shift method: none")
         flags = comp._flags
         if isinstance(comp, PSF_Model) and comp.normalize_psf:
             flags |= sc.FLAG_NORMALIZE
+        if host is not None:
+            flags |= sc.FLAG_AMP
+            if (flags & sc.FLAG_NORMALIZE) and not (tuple(out) == tuple(fwd) == tuple(jac)):
+                # the reference normalises the PSF model over the whole working window (inside a group: the GROUP
+                # window in the forward pass, the point source's own window in the Jacobian, psf_model_object.py:255)
+                raise SpecificationConflict(
+                    f"{host.name}: a point source with a normalised PSF model must have the window it is sampled on "
+                    "(inside a group: the group's) as its own window; set normalize_psf=False on the PSF model or "
+                    "give the point source the group's window")
         return sc.SceneSource(
             kind=comp._kind, image=ii, out=out, fwd=fwd, jac=jac, slot=slot, cval=cval, flags=flags, prof=prof,
             sampling_mode=smode, quad_init=quad_init, integrate_mode=imode,
@@ -307,6 +318,28 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
         info.components.append(pm)
         return len(sources) - 1, (int(w._shape[1]), int(w._shape[0]))
 
+    def point_from_psf_model(comp, ii, region, out, fwd, jac):
+        """Point source whose PSF is a PSF *model* (point_source.py:122-140): the reference samples the PSF model on
+        the working window shifted by -centre -- the model's own sampling mode and integration knobs, normalised over
+        that window when ``normalize_psf`` -- and multiplies by 10^flux.  No PSF stamp, no shift, no convolution: it is
+        lowered as a source of the PSF model's kind on the target's grid whose centre elements are the point source's
+        and whose last element is the flux (FLAG_AMP)."""
+        pm = comp.psf
+        if not AP_config.allow_unverified:
+            raise SpecificationConflict(
+                "point sources with a PSF *model* (point_source.py:122-140): the device path for them has not run on "
+                "hardware yet; set astrophot_b200.AP_config.allow_unverified = True to use it, or sample the PSF model "
+                "once and pass the PSF_Image")
+        if not isinstance(pm, PSF_Model) or getattr(pm, "_kind", None) is None:
+            raise SpecificationConflict(
+                f"PSF model type '{pm.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §8f)")
+        up = int(np.round(float(region.pixel_length) / float(pm.target.window.pixel_length)))
+        if up != 1:
+            raise SpecificationConflict("super-sampled PSFs (psf_upscale > 1) are not implemented yet (SURVEY.md §8f)")
+        if getattr(pm, "model_integrated", False) is not False:
+            raise SpecificationConflict("model_integrated PSF models are not supported by astrophot_b200")
+        return build_source(pm, ii, region, out, fwd, jac, host=comp)
+
     for comp in _components(model):
         if not isinstance(comp, Component_Model) or comp._kind is None:
             raise SpecificationConflict(
@@ -331,7 +364,10 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             fwd = _rect_unclipped(region, asked[ii]) if is_group else jac
         else:
             fwd = (0, 0, images[ii].W, images[ii].H) if is_group else out
-        src = build_source(comp, ii, region, out, fwd, jac)
+        if comp._kind == sc.KIND_POINT and isinstance(comp.psf, AstroPhot_Model):
+            src = point_from_psf_model(comp, ii, region, out, fwd, jac)
+        else:
+            src = build_source(comp, ii, region, out, fwd, jac)
         # Windows larger than image_chunksize pixels: the reference evaluates the Jacobian chunk by chunk
         # (_model_methods.py:349-395), each chunk sampled on its OWN sub-window -- so the integration threshold
         # (total_flux / numel, mean reference) of the derivative pass is the chunk's, not the window's.  Reproduced by
@@ -431,8 +467,9 @@ def tile_scene(scene, ny, nx):
     block-sparse J^T W J is laid out on them, identically on every rank)."""
     if ny * nx <= 1:
         return scene
-    has_aux = any(im.aux for im in scene.images)
-    # (with an auxiliary PSF model its parameters are shared by every source using it: no owner layout, dense solve)
+    has_aux = any(im.aux for im in scene.images) or any(s.flags & sc.FLAG_AMP for s in scene.sources)
+    # (the parameters of an auxiliary PSF model, or of the PSF model point sources are drawn from, are shared by every
+    # source using it: no owner layout, dense solve)
     owners = None if has_aux else [(s.image, tuple(s.out), [sl for sl in s.slot if sl >= 0]) for s in scene.sources]
     images, sources, origin = [], [], []
     first_tile = []
@@ -465,6 +502,10 @@ def tile_scene(scene, ny, nx):
             ix1, iy1 = min(ox + ow, tx + tw), min(oy + oh, ty + th)
             if ix1 <= ix0 or iy1 <= iy0:
                 continue
+            if (s.flags & sc.FLAG_NORMALIZE) and (ix0, iy0, ix1, iy1) != (ox, oy, ox + ow, oy + oh):
+                # the stamp of a normalised source must cover the window it is normalised over
+                raise SpecificationConflict(
+                    f"{s.name}: a point source drawn from a normalised PSF model cannot be cut by a tile border")
             s2 = sc.SceneSource(**{**s.__dict__})
             s2.image = t
             s2.owner = k

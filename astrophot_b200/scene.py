@@ -18,6 +18,9 @@ KIND_NAMES = ["sersic", "exponential", "gaussian", "moffat", "spline", "point", 
 
 FLAG_RADIAL = 1        # no rotation / axis ratio (PSF-model kinds): elements skip q, PA
 FLAG_NORMALIZE = 2     # divide the sampled stamp by its sum (PSF models)
+FLAG_AMP = 4           # the LAST element is a log10 amplitude applied after sampling / normalisation, never seen by the
+                       # profile: a point source drawn from a PSF *model* (point_source.py:122-140) is that model's
+                       # profile centred on the point source, times 10^flux
 
 TR_NONE, TR_LOWER, TR_UPPER, TR_BOTH, TR_CYCLIC = range(5)
 

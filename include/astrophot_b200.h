@@ -47,7 +47,10 @@ enum {
   APB_FLAT_SKY = 6,    /* cx cy F                 models/flatsky_model.py:13      */
   APB_PLANE_SKY = 7    /* cx cy F dx dy           models/planesky_model.py:13 (set APB_F_RADIAL) */
 };
-enum { APB_F_RADIAL = 1, APB_F_NORMALIZE = 2 }; /* psf_model_object.py:36-57,255 */
+enum { APB_F_RADIAL = 1, APB_F_NORMALIZE = 2, /* psf_model_object.py:36-57,255 */
+       APB_F_AMP = 4 };  /* the LAST element is a log10 amplitude applied after sampling / normalisation and never seen
+                            by the profile: a point source drawn from a PSF *model* (point_source.py:122-140) is that
+                            model's profile centred on the point source, times 10^flux.  No PSF on such a source. */
 enum { APB_TR_NONE = 0, APB_TR_LOWER, APB_TR_UPPER, APB_TR_BOTH, APB_TR_CYCLIC }; /* utils/conversions/optimization.py:6-54 */
 enum { APB_SAMPLE_MIDPOINT = 0, APB_SAMPLE_SIMPSONS, APB_SAMPLE_QUAD, APB_SAMPLE_TRAPEZOID }; /* _model_methods.py:82-148 */
 enum { APB_INTEGRATE_NONE = 0, APB_INTEGRATE_THRESHOLD };                                  /* _model_methods.py:155-184 */

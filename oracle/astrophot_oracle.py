@@ -480,6 +480,22 @@ def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, val
     if src.kind == sc.KIND_POINT:
         return _sample_point(scene, src, img, el, want_grad)
 
+    if src.flags & sc.FLAG_AMP:
+        # Point source drawn from a PSF *model* (point_source.py:122-140): the PSF model sampled on the working window
+        # shifted by -centre (its own sampling / integration knobs, normalised over that window when normalize_psf),
+        # then scaled by 10^flux.  The amplitude is the last element; the profile never sees it.
+        import dataclasses
+        base = dataclasses.replace(src, slot=list(src.slot[:-1]), cval=list(src.cval[:-1]),
+                                   flags=src.flags & ~sc.FLAG_AMP)
+        scene1 = dataclasses.replace(scene, sources=[base])
+        r = sample_source(scene1, 0, el[:-1], mode, want_grad, conv, stats, vals)
+        A = 10.0 ** el[-1]
+        val = A * r.value
+        grad = None
+        if want_grad:
+            grad = np.concatenate([A * r.grad, (LN10 * val)[None]], axis=0)
+        return SourceResult(val, grad)
+
     has_psf = src.psf >= 0
     bx = by = 0
     psf_src = psf_res = None
@@ -662,6 +678,15 @@ def _mean_over_region(src, el, coords, S, area, rx0, ry0, rw, rh):
             I, _ = _trapezoid(src, el, X, Y, S, area, False)
         elif src.sampling_mode == sc.SAMPLE_QUAD:
             I, _, _ = _gl(src, el, X, Y, S, area, src.quad_init, False)
+        elif src.sampling_mode == sc.SAMPLE_SIMPSONS:
+            # 3x3 Simpson weights on the half-pixel lattice (_model_methods.py:99-109)
+            I = np.zeros(X.shape)
+            for a in (-1, 0, 1):
+                for b in (-1, 0, 1):
+                    wt = (4.0 if a == 0 else 1.0) * (4.0 if b == 0 else 1.0) / 36.0
+                    dxp = S[0, 0] * (0.5 * b) + S[0, 1] * (0.5 * a)
+                    dyp = S[1, 0] * (0.5 * b) + S[1, 1] * (0.5 * a)
+                    I += wt * eval_profile(src, el, X + dxp, Y + dyp, area, False)[0]
         else:
             raise NotImplementedError
         tot += I.sum()

@@ -267,6 +267,38 @@ def build(ap, name, data=None):
         ptar = ap.image.PSF_Image(data=np.zeros((21, 21)), pixelscale=1.0)
         m = M(name="gpsf", model_type="gaussian psf model", target=ptar, parameters={"sigma": 1.5})
         return m, {}
+    if name == "point_psf_model":
+        # point source drawn from a PSF *model* (point_source.py:122-140): PSF parameters fitted with centre and flux
+        ptar = ap.image.PSF_Image(data=np.zeros((15, 15)), pixelscale=0.8)
+        pm = M(name="ppm_psf", model_type="moffat psf model", target=ptar, parameters={"n": 2.2, "Rd": 2.4})
+        tar = _target(ap, (40, 44), data, pixelscale=0.8)
+        m = M(name="ppm", model_type="point model", target=tar, psf=pm,
+              parameters={"center": [17.3, 14.9], "flux": 1.2})
+        return m, {}
+    if name == "point_psf_model_group":
+        # two stars sharing one (normalised) Moffat PSF model, a third with an un-normalised Gaussian PSF model on its
+        # own small window, a galaxy and the sky; the shared PSF parameters are fitted with everything else
+        ptar = ap.image.PSF_Image(data=np.zeros((17, 17)), pixelscale=1.0)
+        pm = M(name="shared_psf", model_type="moffat psf model", target=ptar, parameters={"n": 2.6, "Rd": 2.1})
+        ptar2 = ap.image.PSF_Image(data=np.zeros((13, 13)), pixelscale=1.0)
+        pg = M(name="gauss_psf", model_type="gaussian psf model", target=ptar2, normalize_psf=False,
+               parameters={"sigma": 1.6, "flux": 0.0})
+        tar = _target(ap, (56, 60), data)
+        models = [
+            M(name="starA", model_type="point model", target=tar, psf=pm,
+              parameters={"center": [18.4, 20.7], "flux": 2.0}),
+            M(name="starB", model_type="point model", target=tar, psf=pm,
+              parameters={"center": [41.6, 33.2], "flux": 1.6}),
+            M(name="starC", model_type="point model", target=tar, psf=pg, window=[[22, 41], [38, 55]],
+              parameters={"center": [31.3, 46.8], "flux": 1.4}),
+            M(name="ppg_gal", model_type="sersic galaxy model", target=tar,
+              parameters={"center": [30.2, 14.6], "q": 0.6, "PA": 1.1, "n": 1.7, "Re": 5.0, "Ie": 0.2}),
+        ]
+        sky = M(name="ppg_sky", model_type="flat sky model", target=tar, parameters={"F": -1.5})
+        sky.initialize()
+        models.append(sky)
+        g = M(name="ppg", model_type="group model", models=models, target=tar)
+        return g, {}
     raise KeyError(name)
 
 
@@ -275,12 +307,15 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs"]
 # scenes checked on the CPU only (oracle vs reference): added after the round's GPU budget was spent
-CPU_ONLY_SCENES = ["group_edge"]
+CPU_ONLY_SCENES = ["group_edge", "point_psf_model", "point_psf_model_group"]
+# scenes whose device path is refused unless AP_config.allow_unverified (written after the GPU budget was spent; the
+# tests switch it on, and the GPU tests of these scenes only run with APB_ALLOW_UNVERIFIED=1)
+UNVERIFIED_SCENES = ["point_psf_model", "point_psf_model_group"]
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
              "moffat_psf_model": 16}
-CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
+CPU_LM_SCENES = {"point_psf_model": 17, "point_psf_model_group": 18}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
 

@@ -156,6 +156,46 @@ def test_auxiliary_psf_model_survives_tiling_and_sharding():
         assert part.sources[ps.source].image == 2 and all(s.psf == 0 for s in part.sources if s.image < 2)
 
 
+def test_point_source_from_a_psf_model_lowers_to_an_amplitude_source(monkeypatch):
+    """point_source.py:122-140: the PSF model's profile at the point source's centre times 10^flux (FLAG_AMP)."""
+    from astrophot_b200 import scene as sc
+    from astrophot_b200.lowering import lower, tile_scene
+    import scenes
+    ap.AP_config.ap_device = "cpu"
+    model, _ = scenes.build(ap, "point_psf_model_group")
+    # refused by default: the device path has not run on hardware yet
+    monkeypatch.setattr(ap.AP_config, "allow_unverified", False)
+    with pytest.raises(ap.errors.SpecificationConflict, match="allow_unverified"):
+        lower(model)
+    monkeypatch.setattr(ap.AP_config, "allow_unverified", True)
+    scene, _ = lower(model)
+    assert not scene.psfs and all(s.psf < 0 for s in scene.sources)         # no stamp, no shift, no convolution
+    a, b, c = scene.sources[:3]
+    for s in (a, b):
+        assert s.kind == sc.KIND_MOFFAT and s.flags == sc.FLAG_RADIAL | sc.FLAG_NORMALIZE | sc.FLAG_AMP
+        assert s.n_elem == len(sc.ELEMS[sc.KIND_MOFFAT]) + 1 and s.slot[-1] >= 0          # flux: the last element
+        assert s.sampling_mode == sc.SAMPLE_SIMPSONS and s.tolerance == 1e-3                # the PSF model's knobs
+        assert s.out == s.fwd == s.jac
+    assert a.slot[4:6] == b.slot[4:6] and min(a.slot[4:6]) >= 0                          # one shared PSF model
+    assert a.slot[:2] != b.slot[:2] and a.slot[-1] != b.slot[-1]                         # own centre and flux
+    assert a.slot[2] == a.slot[3] == -1 and (a.cval[2], a.cval[3]) == (1.0, 0.0)         # radial: q = 1, PA = 0
+    assert c.kind == sc.KIND_GAUSSIAN and c.flags == sc.FLAG_RADIAL | sc.FLAG_AMP and c.fwd != c.out
+    # shared PSF parameters: dense solve, no owner layout; a normalised piece may not be cut
+    with pytest.raises(ap.errors.SpecificationConflict, match="tile"):
+        tile_scene(scene, 2, 2)
+    # a normalised PSF model is normalised over the window it is sampled on: inside a group that is the group's
+    tar = model.target
+    pm = model.models["starA"].psf
+    small = ap.models.AstroPhot_Model(name="starS", model_type="point model", target=tar, psf=pm,
+                                      window=[[10, 30], [12, 32]], parameters={"center": [18.4, 20.7], "flux": 2.0})
+    sky = ap.models.AstroPhot_Model(name="skyS", model_type="flat sky model", target=tar, parameters={"F": -1.0})
+    sky.initialize()
+    g = ap.models.AstroPhot_Model(name="gS", model_type="group model", models=[small, sky], target=tar)
+    with pytest.raises(ap.errors.SpecificationConflict, match="normalised PSF model"):
+        lower(g)
+    assert lower(small)[0].sources[0].out == (0, 0, 20, 20)          # on its own (scene image = its window) it is fine
+
+
 def test_iter_lm_visits_the_chunks_like_the_reference():
     """Iter_LM._sweep against the reference's selection rules (fit/iterative.py:225-275), restated here: integer
     chunks deal the identities out from the front / by random.sample of the remaining ones, explicit chunks go in

@@ -86,7 +86,7 @@ def host_only(monkeypatch):
 
 
 @pytest.mark.parametrize("name", ["c1_sersic", "psf_sersic", "group", "joint", "group_nosky", "masked_locked_edge",
-                                  "aux_psf_moffat", "plane_sky_group"])
+                                  "aux_psf_moffat", "plane_sky_group", "point_psf_model", "point_psf_model_group"])
 def test_lm_control_flow_reproduces_the_reference(host_only, name):
     fix = load_golden(name)
     model, _ = scenes.build(ap, name, data=golden_data(fix))
