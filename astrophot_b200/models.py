@@ -260,7 +260,33 @@ class AstroPhot_Model:
         return result
 
     def total_flux(self, parameters=None, window=None):
-        return torch.sum(self.sample(window=window).data)
+        """Sum of the model image (reference: `core_model.py:265-268`)."""
+        img = self(parameters=parameters, window=window)
+        datas = [i.data for i in img.image_list] if isinstance(img, Image_List) else [img.data]
+        return sum(torch.sum(d.to(torch.float64)) for d in datas).cpu()
+
+    def total_flux_uncertainty(self, parameters=None, window=None):
+        """Linear propagation of the parameter uncertainties (natural units) through the total flux: the column sums
+        of the Jacobian are d(total flux)/d(parameter) (reference: `core_model.py:270-276`, which builds the dense
+        Jacobian as well)."""
+        if parameters is not None:
+            self.parameters.vector_set_values(parameters)
+        jac = self.jacobian(window=window)
+        datas = [j.data for j in jac.image_list] if isinstance(jac, Image_List) else [jac.data]
+        dF = sum(torch.sum(d.to(torch.float64).reshape(-1, d.shape[-1]), dim=0) for d in datas).cpu()
+        unc = self.parameters.vector_uncertainty().to(torch.float64)
+        return torch.sqrt(torch.sum((dF * unc) ** 2))
+
+    def total_magnitude(self, parameters=None, window=None):
+        """-2.5 log10(total flux) + zeropoint (reference: `core_model.py:278-282`)."""
+        F = self.total_flux(parameters=parameters, window=window)
+        return -2.5 * torch.log10(F) + self.target.zeropoint
+
+    def total_magnitude_uncertainty(self, parameters=None, window=None):
+        """|2.5 dF / (F ln 10)| (reference: `core_model.py:284-290`)."""
+        F = self.total_flux(parameters=parameters, window=window)
+        dF = self.total_flux_uncertainty(parameters=parameters, window=window)
+        return torch.abs(2.5 * dF / (F * np.log(10)))
 
     def get_state(self, *args, **kwargs):
         return {"name": self.name, "model_type": self.model_type}
@@ -283,6 +309,21 @@ class AstroPhot_Model:
 
     def __str__(self):
         return str(self.parameters)
+
+
+def _sersic_b(n):
+    """b(n) of the Sérsic profile (reference: `utils/conversions/functions.py:7-22`)."""
+    return (2 * n - 1 / 3 + 4 / (405 * n) + 46 / (25515 * n**2) + 131 / (1148175 * n**3)
+            - 2194697 / (30690717750 * n**4))
+
+
+def _pval(model, name):
+    return model.parameters[name].value.to(torch.float64).reshape(-1)[0]
+
+
+def _moffat_total_flux(I0, n, Rd, q):
+    """Reference: `utils/conversions/functions.py:227-237`."""
+    return I0 * np.pi * Rd**2 * q / (n - 1)
 
 
 class Component_Model(AstroPhot_Model):
@@ -408,6 +449,15 @@ class Sersic_Galaxy(Galaxy_Model):
     _kind = sc.KIND_SERSIC
     _ref_mode = sc.REF_SERSIC_FLUX    # total_flux / numel, sersic_model.py:87-89
 
+    def total_flux(self, parameters=None, window=None):
+        """Analytic flux to infinity, not the image sum (reference: `sersic_model.py:79-85`,
+        `utils/conversions/functions.py:168-190`)."""
+        if isinstance(parameters, (torch.Tensor, np.ndarray, list, tuple)):
+            self.parameters.vector_set_values(parameters)
+        n, Re, q, Ie = (_pval(self, k) for k in ("n", "Re", "q", "Ie"))
+        bn = _sersic_b(n)
+        return 2 * np.pi * 10**Ie * Re**2 * q * n * (torch.exp(bn) * bn ** (-2 * n)) * torch.exp(torch.lgamma(2 * n))
+
 
 class Exponential_Galaxy(Galaxy_Model):
     model_type = f"exponential {Galaxy_Model.model_type}"
@@ -441,6 +491,12 @@ class Moffat_Galaxy(Galaxy_Model):
     _parameter_order = Galaxy_Model._parameter_order + ("n", "Rd", "I0")
     usable = True
     _kind = sc.KIND_MOFFAT
+
+    def total_flux(self, parameters=None, window=None):
+        """Analytic flux to infinity (reference: `moffat_model.py:60-66`)."""
+        if isinstance(parameters, (torch.Tensor, np.ndarray, list, tuple)):
+            self.parameters.vector_set_values(parameters)
+        return _moffat_total_flux(10 ** _pval(self, "I0"), _pval(self, "n"), _pval(self, "Rd"), _pval(self, "q"))
 
 
 class Spline_Galaxy(Galaxy_Model):
@@ -607,8 +663,15 @@ class Moffat_PSF(PSF_Model):
     usable = True
     _kind = sc.KIND_MOFFAT
 
+    def total_flux(self, parameters=None, window=None):
+        """Analytic flux to infinity with q = 1 (reference: `moffat_model.py:111-117`)."""
+        if isinstance(parameters, (torch.Tensor, np.ndarray, list, tuple)):
+            self.parameters.vector_set_values(parameters)
+        return _moffat_total_flux(10 ** _pval(self, "I0"), _pval(self, "n"), _pval(self, "Rd"), 1.0)
+
 
 class Moffat2D_PSF(PSF_Model):
+    total_flux = Moffat_PSF.total_flux       # the reference's Moffat2D_PSF inherits it (q = 1 there too)
     model_type = f"moffat2d {PSF_Model.model_type}"
     parameter_specs = {
         "q": {"units": "b/a", "limits": (0, 1), "uncertainty": 0.03},

@@ -320,6 +320,8 @@ ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
 
 
+# total_flux / total_flux_uncertainty / total_magnitude(_uncertainty) fixture (oracle/make_flux_golden.py)
+FLUX_SCENES = ["c1_sersic", "psf_sersic", "point", "group", "plane_sky_group", "moffat", "spline"]   # (the reference cannot do image lists)
 ITER_SCENES = ("group", "group_nosky")     # also fitted with fit.Iter in the goldens
 LM_KWARGS_SCENES = ("psf_sersic",)         # also fitted with non-default LM knobs
 LM_KWARGS = dict(acceleration=0.7, curvature_limit=0.6, Lup=7.0, Ldn=5.0, L0=3.0, max_step_iter=8)

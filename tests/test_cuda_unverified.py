@@ -7,7 +7,8 @@ and these tests only run with that variable -- the first GPU visit of the next r
 
 and, once green, the scenes move to scenes.SAMPLE_SCENES / LM_SCENES and the gate goes away.
 
-Covered: point sources drawn from a PSF *model* (point_source.py:122-140; APB_F_AMP, k_amp)."""
+Covered: point sources drawn from a PSF *model* (point_source.py:122-140; APB_F_AMP, k_amp); the total-flux uncertainty
+methods of the model (host arithmetic on model() and model.jacobian(), CPU-tested on the stand-in plan)."""
 import os
 
 import pytest
@@ -42,3 +43,9 @@ def test_normal_equations_lm_and_covariance(name):
 def test_integration_variants_agree(name):
     tp.test_fused_integration_equals_per_depth_launches(name)
     tp.test_pooled_integration_equals_lane_shared(name)
+
+
+@pytest.mark.parametrize("scene_name", scenes.FLUX_SCENES)
+def test_total_flux_and_its_uncertainty(scene_name):
+    from test_lm_host_logic import check_flux_uncertainties
+    check_flux_uncertainties(scene_name)

@@ -26,6 +26,10 @@ class OraclePlan:
         x = np.asarray(torch.as_tensor(x).cpu().numpy(), dtype=np.float64)
         return [torch.as_tensor(m) for m in orc.sample(self.scene, x, as_rep)]
 
+    def jacobian(self, x, as_rep=False):
+        x = np.asarray(torch.as_tensor(x).cpu().numpy(), dtype=np.float64)
+        return [torch.as_tensor(j) for j in orc.jacobian(self.scene, x, as_rep)]
+
     def reserve(self, caps=None):
         pass
 
@@ -139,3 +143,19 @@ def test_iter_control_flow_reproduces_the_reference(host_only, name):
                       method_kwargs={"max_iter": 4, "relative_tolerance": 0.0, "fused_trial": False}).fit()
     np.testing.assert_allclose(res.loss_history, fix["iter_loss_history"], rtol=1e-8)
     np.testing.assert_allclose(np.array(res.lambda_history), fix["iter_lambda_history"], rtol=1e-7, atol=1e-7)
+
+
+def check_flux_uncertainties(name):
+    """total_flux / total_flux_uncertainty / total_magnitude / total_magnitude_uncertainty (core_model.py:265-290) against
+    the reference's own numbers (oracle/make_flux_golden.py), with the same seeded parameter uncertainties."""
+    ref = load_golden("flux_uncertainty")[name]
+    model, _ = scenes.build(ap, name)
+    unc = np.random.default_rng(500 + scenes.FLUX_SCENES.index(name)).uniform(0.01, 0.1, size=len(model.parameters.vector_values()))
+    model.parameters.vector_set_uncertainty(torch.as_tensor(unc))
+    got = [model.total_flux(), model.total_flux_uncertainty(), model.total_magnitude(), model.total_magnitude_uncertainty()]
+    np.testing.assert_allclose([float(g) for g in got], ref, rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", scenes.FLUX_SCENES)
+def test_total_flux_and_its_uncertainty(host_only, name):
+    check_flux_uncertainties(name)
