@@ -13,8 +13,8 @@ torch/CPU evaluation path in this package.
 
 In scope: sersic / exponential / gaussian / moffat / spline
 galaxy, point, flat sky, group; sersic / exponential / gaussian / moffat /
-moffat2d / spline psf models.  Parameter initialisation heuristics are out of
-scope: give parameter values explicitly.
+moffat2d / spline psf models.  ``initialize()`` fills the parameters the user left
+open from the data with the reference's recipes (``init_heuristics.py``, host numpy).
 """
 from collections import OrderedDict
 from copy import deepcopy
@@ -189,14 +189,22 @@ class AstroPhot_Model:
     def is_initialized(self):
         return all((not P.leaf) or (P.value is not None) for P in self.parameters)
 
+    default_uncertainty = 1e-2   # relative start uncertainty when none is given (reference: `core_model.py:93`)
+
     def initialize(self, target=None, parameters=None, **kwargs):
-        """Guessing start values from the data is input prep (out of scope);
-        this only checks that values exist."""
-        for P in self.parameters.flat(include_locked=True).values():
-            if P.value is None:
-                raise InvalidParameter(
-                    f"{self.name}: parameter '{P.name}' has no value. astrophot_b200 does not implement the "
-                    "reference's initialisation heuristics; pass explicit parameter values.")
+        """When this returns every parameter should have a value (reference: `core_model.py:180-186`).  The
+        subclasses fill in what the user left open from the data (``init_heuristics.py``); nothing here."""
+
+    def _init_target(self, target):
+        """The image to take start values from (reference: ``select_target``, `_shared_methods.py:33-49`)."""
+        if target is None:
+            return self.target
+        if isinstance(target, Target_Image_List) and not isinstance(self.target, Image_List):
+            for sub in target:
+                if sub.identity == self.target.identity:
+                    return sub
+            raise RuntimeError(f"{self.name} could not find matching target to initialize with")
+        return target
 
     def make_model_image(self, window=None):
         window = self.window if window is None else self.window & window
@@ -394,12 +402,80 @@ class Component_Model(AstroPhot_Model):
         if add_parameters:
             self.parameters.link(aux_psf.parameters)
 
+    _init_family = None      # key of init_heuristics.PROFILE_FITS for the parametric profile families
+
+    @torch.no_grad()
     def initialize(self, target=None, parameters=None, **kwargs):
+        """Fill in the parameters the user left open from the data, in the reference's order: centre
+        (`model_object.py:176-233`), shape (`galaxy_model_object.py:56-113`), then the family's own parameters."""
+        target = self._init_target(target)
+        self._init_center(target)
+        self._init_shape(target)
+        self._init_own(target)
+
+    def _init_shape(self, target):
+        pass
+
+    def _init_own(self, target):
+        if self._init_family is not None:
+            self._init_profile(target, self._init_family)
+
+    def _init_center(self, target):
+        """The window's centre refined by an iterated centre-of-light search, when no centre was given."""
+        from . import init_heuristics as ih
+
         c = self.parameters["center"]
-        if c.value is None:
-            with Param_Unlock(c), Param_SoftLimits(c):
-                c.value = self.window.center
-        super().initialize(target=target, parameters=parameters)
+        if c.value is not None:
+            return
+        with Param_Unlock(c), Param_SoftLimits(c):
+            c.value = self.window.center
+        if c.locked or target is None:
+            return
+        area = target[self.window]
+        pc = area.plane_to_pixel(c.value)
+        dat = area.data.detach().cpu().numpy()
+        com = ih.light_centroid((float(pc[1]), float(pc[0])), dat)
+        if np.any(np.array(com) < 0) or np.any(np.array(com) >= np.array(dat.shape)):
+            AP_config.ap_logger.warning("center of mass failed, using center of window")
+            return
+        c.value = area.pixel_to_plane(torch.tensor([com[1], com[0]], dtype=torch.float64))
+
+    # -- pieces shared by the initialize() methods of the profile families ------------------------
+    def _init_radii(self, area):
+        """Radius of every pixel of ``area`` in the model's own metric (rotation, axis ratio, softening)."""
+        coords = area.get_coordinate_meshgrid()
+        cen = self.parameters["center"].value.to(torch.float64)
+        X, Y = coords[0] - cen[0], coords[1] - cen[1]
+        X, Y = self._init_transform(X, Y, area)
+        return torch.sqrt(X**2 + Y**2 + self.softening**2).detach().cpu().numpy()
+
+    def _init_transform(self, X, Y, area):
+        return X, Y
+
+    def _init_profile(self, target, family):
+        """Start values of a parametric profile: Nelder-Mead fit to the binned radial profile
+        (reference: `_shared_methods.py:125-164`)."""
+        from . import init_heuristics as ih
+
+        names, prof, x0_of = ih.PROFILE_FITS[family]
+        pars = [self.parameters[k] for k in names]
+        if all(P.value is not None for P in pars):
+            return
+        area = target[self.window]
+        mask = area.mask.detach().cpu().numpy().astype(bool) if area.has_mask else None
+        R, I, _ = ih.radial_profile(area.data.detach().cpu().numpy().astype(np.float64), mask, self._init_radii(area),
+                                    float(area.pixel_area))
+        x0 = list(x0_of(R, I))
+        for k, P in enumerate(pars):
+            if P.value is not None:
+                x0[k] = float(P.value)
+        x, ok, spread = ih.fit_profile(R, I, prof, x0)
+        for k, P in enumerate(pars):
+            with Param_Unlock(P), Param_SoftLimits(P):
+                if P.value is None:
+                    P.value = x[k] if ok else x0[k]
+                if P.uncertainty is None:
+                    P.uncertainty = spread[k]
 
     @property
     def target(self):
@@ -434,6 +510,49 @@ class Galaxy_Model(Component_Model):
     }
     _parameter_order = Component_Model._parameter_order + ("q", "PA")
 
+    def _init_transform(self, X, Y, area):
+        th = -(self.parameters["PA"].value.to(torch.float64) - area.north)
+        s, c = torch.sin(th), torch.cos(th)
+        return c * X - s * Y, (s * X + c * Y) / self.parameters["q"].value.to(torch.float64)
+
+    def _init_shape(self, target):
+        """PA from the second angular moment of the light, q from the m=2 Fourier amplitude of trial isophotes
+        (reference: `galaxy_model_object.py:56-113`)."""
+        from . import init_heuristics as ih
+
+        PA, q = self.parameters["PA"], self.parameters["q"]
+        if PA.value is not None and q.value is not None:
+            return
+        area = target[self.window]
+        dat = area.data.detach().cpu().numpy().astype(np.float64).copy()
+        mask = area.mask.detach().cpu().numpy().astype(bool) if area.has_mask else None
+        if mask is not None:
+            dat[mask] = np.median(dat[~mask])
+        edge = ih.edge_pixels(dat)
+        edge_average = np.nanmedian(edge)
+        edge_scatter = ih.half_spread(edge[np.isfinite(edge)])
+        cen = self.parameters["center"].value.to(torch.float64)
+        pc = area.plane_to_pixel(cen)
+        if PA.value is None:
+            coords = area.get_coordinate_meshgrid()
+            X, Y = (coords[0] - cen[0]).cpu().numpy(), (coords[1] - cen[1]).cpu().numpy()
+            w = dat - edge_average
+            ang = ih.moment_position_angle(w, X, Y) if mask is None else ih.moment_position_angle(w[~mask], X[~mask], Y[~mask])
+            with Param_Unlock(PA), Param_SoftLimits(PA):
+                PA.value = (ang + area.north) % np.pi
+                if PA.uncertainty is None:
+                    PA.uncertainty = (5 * np.pi / 180) * torch.ones_like(PA.value)
+        if q.value is None:
+            q_samples = np.linspace(0.2, 0.9, 15)
+            # (quirk 1 of init_heuristics: the centre goes in as (pixel-y, pixel-x) and is used as (x, y))
+            best = ih.axis_ratio_scan(area.data.detach().cpu().numpy().astype(np.float64) - edge_average,
+                                      float(pc[1]), float(pc[0]), 3 * edge_scatter,
+                                      float(PA.value) - target.north, q_samples)
+            with Param_Unlock(q), Param_SoftLimits(q):
+                q.value = best
+                if q.uncertainty is None:
+                    q.uncertainty = q.value * self.default_uncertainty
+
 
 class Sersic_Galaxy(Galaxy_Model):
     """I(R) = Ie exp(-b_n ((R/Re)^(1/n) - 1)) (reference: `sersic_model.py:41-91`)."""
@@ -446,6 +565,7 @@ class Sersic_Galaxy(Galaxy_Model):
     }
     _parameter_order = Galaxy_Model._parameter_order + ("n", "Re", "Ie")
     usable = True
+    _init_family = "sersic"
     _kind = sc.KIND_SERSIC
     _ref_mode = sc.REF_SERSIC_FLUX    # total_flux / numel, sersic_model.py:87-89
 
@@ -467,6 +587,7 @@ class Exponential_Galaxy(Galaxy_Model):
     }
     _parameter_order = Galaxy_Model._parameter_order + ("Re", "Ie")
     usable = True
+    _init_family = "exponential"
     _kind = sc.KIND_EXPONENTIAL
 
 
@@ -478,6 +599,7 @@ class Gaussian_Galaxy(Galaxy_Model):
     }
     _parameter_order = Galaxy_Model._parameter_order + ("sigma", "flux")
     usable = True
+    _init_family = "gaussian"
     _kind = sc.KIND_GAUSSIAN
 
 
@@ -490,6 +612,7 @@ class Moffat_Galaxy(Galaxy_Model):
     }
     _parameter_order = Galaxy_Model._parameter_order + ("n", "Rd", "I0")
     usable = True
+    _init_family = "moffat"
     _kind = sc.KIND_MOFFAT
 
     def total_flux(self, parameters=None, window=None):
@@ -510,6 +633,32 @@ class Spline_Galaxy(Galaxy_Model):
     extend_profile = True
     _kind = sc.KIND_SPLINE
 
+    def _init_own(self, target):
+        """Node radii growing by 20 % per node out to the window's half-diagonal, node values from the binned radial
+        profile (reference: `_shared_methods.py:426-453`)."""
+        from . import init_heuristics as ih
+
+        P = self.parameters["I(R)"]
+        if P.value is not None and P.prof is not None:
+            return
+        if P.prof is None:
+            half = self.window.shape.to(torch.float64) / 2
+            step = 2 * float(target.pixel_length)
+            prof = [0.0, step]
+            while prof[-1] < float(torch.max(half)):
+                prof.append(prof[-1] + max(step, prof[-1] * 0.2))
+            prof = prof[:-2] + [float(torch.sqrt(torch.sum(half**2)))]
+            P.prof = prof
+        pr = P.prof.detach().cpu().numpy().astype(np.float64)
+        area = target[self.window]
+        mask = area.mask.detach().cpu().numpy().astype(bool) if area.has_mask else None
+        bins = [pr[0]] + list((pr[:-1] + pr[1:]) / 2) + [pr[-1] * 100]
+        _, I, S = ih.radial_profile(area.data.detach().cpu().numpy().astype(np.float64), mask, self._init_radii(area),
+                                    float(area.pixel_area), rad_bins=bins)
+        with Param_Unlock(P), Param_SoftLimits(P):
+            P.value = I
+            P.uncertainty = S
+
 
 class Point_Source(Component_Model):
     """Delta function times the PSF (reference: `point_source.py:17-189`)."""
@@ -524,6 +673,19 @@ class Point_Source(Component_Model):
         super().__init__(*args, **kwargs)
         if self.psf is None:
             raise ValueError("Point_Source needs psf information")
+
+    def _init_own(self, target):
+        """Flux: the light in the window above the median of its edge pixels (reference: `point_source.py:40-65`)."""
+        from . import init_heuristics as ih
+
+        F = self.parameters["flux"]
+        if F.value is not None:
+            return
+        area = target[self.window]
+        dat = area.data.detach().cpu().numpy().astype(np.float64)
+        with Param_Unlock(F), Param_SoftLimits(F):
+            F.value = np.log10(np.abs(np.sum(dat - np.median(ih.edge_pixels(dat)))))
+            F.uncertainty = torch.std(area.data.to(torch.float64).cpu()) / (np.log(10) * 10 ** F.value)
 
     @property
     def psf_mode(self):
@@ -565,6 +727,23 @@ class Flat_Sky(Sky_Model):
     usable = True
     _kind = sc.KIND_FLAT_SKY
 
+    def _init_own(self, target):
+        """F: median of the window per unit area; uncertainty: the 1-sigma range of the pixels over sqrt(window size)
+        (reference: `flatsky_model.py:29-52`)."""
+        from . import init_heuristics as ih
+
+        F = self.parameters["F"]
+        dat = target[self.window].data.detach().cpu().numpy().astype(np.float64)
+        area = float(target.pixel_area)
+        with Param_Unlock(F), Param_SoftLimits(F):
+            if F.value is None:
+                # (torch.median: the LOWER of the two middle values of an even count, as in the reference)
+                F.value = np.log10(np.abs(float(torch.median(torch.as_tensor(dat)))) / area)
+            if F.uncertainty is None:
+                spread = ih.half_spread(dat, 31.731 / 2, 100 - 31.731 / 2) / area
+                F.uncertainty = (spread / np.sqrt(np.prod(self.window.shape.detach().cpu().numpy()))) / (
+                    10 ** float(F.value) * np.log(10))
+
 
 class Plane_Sky(Sky_Model):
     """Sky brightness plane  I = pixel_area F + X dx + Y dy  about the (locked) centre, natural flux units
@@ -576,6 +755,23 @@ class Plane_Sky(Sky_Model):
     usable = True
     _kind = sc.KIND_PLANE_SKY
     _flags = sc.FLAG_RADIAL        # no rotation / axis ratio elements
+
+    def _init_own(self, target):
+        """F: median of the window per unit area; no slope (reference: `planesky_model.py:37-63`)."""
+        from . import init_heuristics as ih
+
+        F, delta = self.parameters["F"], self.parameters["delta"]
+        dat = target[self.window].data.detach().cpu().numpy().astype(np.float64)
+        with Param_Unlock(F), Param_SoftLimits(F):
+            if F.value is None:
+                F.value = np.median(dat) / float(target.pixel_area)
+            if F.uncertainty is None:
+                F.uncertainty = ih.half_spread(dat, 31.731 / 2, 100 - 31.731 / 2) / np.sqrt(
+                    np.prod(self.window.shape.detach().cpu().numpy()))
+        with Param_Unlock(delta), Param_SoftLimits(delta):
+            if delta.value is None:
+                delta.value = [0.0, 0.0]
+                delta.uncertainty = [self.default_uncertainty, self.default_uncertainty]
 
 
 # ---------------------------------------------------------------------------
@@ -627,6 +823,7 @@ class Sersic_PSF(PSF_Model):
     }
     _parameter_order = PSF_Model._parameter_order + ("n", "Re", "Ie")
     usable = True
+    _init_family = "sersic"
     _kind = sc.KIND_SERSIC
 
 
@@ -638,6 +835,7 @@ class Exponential_PSF(PSF_Model):
     }
     _parameter_order = PSF_Model._parameter_order + ("Re", "Ie")
     usable = True
+    _init_family = "exponential"
     _kind = sc.KIND_EXPONENTIAL
 
 
@@ -649,6 +847,7 @@ class Gaussian_PSF(PSF_Model):
     }
     _parameter_order = PSF_Model._parameter_order + ("sigma", "flux")
     usable = True
+    _init_family = "gaussian"
     _kind = sc.KIND_GAUSSIAN
 
 
@@ -661,6 +860,7 @@ class Moffat_PSF(PSF_Model):
     }
     _parameter_order = PSF_Model._parameter_order + ("n", "Rd", "I0")
     usable = True
+    _init_family = "moffat"
     _kind = sc.KIND_MOFFAT
 
     def total_flux(self, parameters=None, window=None):
@@ -682,6 +882,7 @@ class Moffat2D_PSF(PSF_Model):
     }
     _parameter_order = PSF_Model._parameter_order + ("q", "PA", "n", "Rd", "I0")
     usable = True
+    _init_family = "moffat"
     _kind = sc.KIND_MOFFAT
     _flags = 0
 
@@ -693,6 +894,32 @@ class Spline_PSF(PSF_Model):
     usable = True
     extend_profile = True
     _kind = sc.KIND_SPLINE
+
+    def _init_own(self, target):
+        """Node radii growing by 20 % per node out to the window's half-diagonal, node values from the binned radial
+        profile (reference: `_shared_methods.py:426-453`)."""
+        from . import init_heuristics as ih
+
+        P = self.parameters["I(R)"]
+        if P.value is not None and P.prof is not None:
+            return
+        if P.prof is None:
+            half = self.window.shape.to(torch.float64) / 2
+            step = 2 * float(target.pixel_length)
+            prof = [0.0, step]
+            while prof[-1] < float(torch.max(half)):
+                prof.append(prof[-1] + max(step, prof[-1] * 0.2))
+            prof = prof[:-2] + [float(torch.sqrt(torch.sum(half**2)))]
+            P.prof = prof
+        pr = P.prof.detach().cpu().numpy().astype(np.float64)
+        area = target[self.window]
+        mask = area.mask.detach().cpu().numpy().astype(bool) if area.has_mask else None
+        bins = [pr[0]] + list((pr[:-1] + pr[1:]) / 2) + [pr[-1] * 100]
+        _, I, S = ih.radial_profile(area.data.detach().cpu().numpy().astype(np.float64), mask, self._init_radii(area),
+                                    float(area.pixel_area), rad_bins=bins)
+        with Param_Unlock(P), Param_SoftLimits(P):
+            P.value = I
+            P.uncertainty = S
 
 
 # ---------------------------------------------------------------------------
@@ -787,9 +1014,15 @@ class Group_Model(AstroPhot_Model):
         for model in getattr(self, "models", {}).values():
             model.psf_mode = value
 
+    @torch.no_grad()
     def initialize(self, target=None, parameters=None, **kwargs):
+        """Initialise the sub-models in order, each on what the earlier ones leave of the target
+        (reference: `group_model_object.py:130-150`)."""
+        target = self._init_target(target)
+        left = target.copy()
         for model in self.models.values():
-            model.initialize(target=target)
+            model.initialize(target=left)
+            left -= model()
 
     def fit_mask(self):
         """True where no sub-model has anything to say (reference:

@@ -340,3 +340,60 @@ def make_data(truth_images, seed, scale=1.0):
 def perturb(x_rep, seed, scale=0.05):
     rng = np.random.default_rng(1000 + seed)
     return np.asarray(x_rep, dtype=np.float64) + scale * rng.normal(size=len(x_rep))
+
+
+# ---------------------------------------------------------------------------
+# model.initialize(): models built WITHOUT parameter values on noisy data (oracle/make_init_golden.py)
+# ---------------------------------------------------------------------------
+INIT_SCENES = ["init_sersic", "init_sersic_fixed_shape", "init_exponential", "init_gaussian", "init_moffat", "init_spline",
+               "init_point", "init_flat_sky", "init_plane_sky", "init_moffat_psf", "init_gaussian_psf", "init_masked_sheared",
+               "init_group"]
+
+
+def init_data(name, load_golden):
+    """Noisy image for an initialisation scene: the reference's own model image of a golden scene + seeded noise."""
+    src = {"init_sersic": "c1_sersic", "init_sersic_fixed_shape": "c1_sersic", "init_exponential": "exponential",
+           "init_gaussian": "gaussian", "init_moffat": "moffat", "init_spline": "spline", "init_point": "point",
+           "init_flat_sky": "group", "init_plane_sky": "plane_sky_group", "init_moffat_psf": "moffat_psf_model",
+           "init_gaussian_psf": "gaussian_psf_model", "init_masked_sheared": "sersic_sheared", "init_group": "group_nosky"}[name]
+    truth = load_golden(src)["img0"]
+    scale = 0.02 if "psf" in name else 1.0
+    if name in ("init_flat_sky", "init_group"):
+        truth = truth + 0.3          # a sky level to find
+    return make_data([truth], 700 + INIT_SCENES.index(name), scale=scale)[0]["data"]
+
+
+def build_init(ap, name, dat):
+    """Model of an initialisation scene with its parameters left open."""
+    M = ap.models.AstroPhot_Model
+    if name in ("init_sersic", "init_sersic_fixed_shape"):
+        tar = ap.image.Target_Image(data=dat, pixelscale=1.0, zeropoint=22.5)
+        pars = {} if name == "init_sersic" else {"center": [50.3, 49.6], "q": 0.6, "PA": 1.0}
+        return M(name=name, model_type="sersic galaxy model", target=tar, parameters=pars)
+    if name in ("init_exponential", "init_gaussian", "init_moffat", "init_spline"):
+        tar = ap.image.Target_Image(data=dat, pixelscale=0.9, zeropoint=22.5)
+        return M(name=name, model_type=f"{name[5:]} galaxy model", target=tar)
+    if name == "init_point":
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 15), pixelscale=1.0)
+        tar = ap.image.Target_Image(data=dat, pixelscale=1.0, zeropoint=22.5, psf=psf)
+        return M(name=name, model_type="point model", target=tar)
+    if name in ("init_flat_sky", "init_plane_sky"):
+        tar = ap.image.Target_Image(data=dat, pixelscale=1.0, zeropoint=22.5)
+        return M(name=name, model_type=f"{name[5:-4]} sky model", target=tar, window=[[5, 80], [10, 90]])
+    if name in ("init_moffat_psf", "init_gaussian_psf"):
+        ptar = ap.image.PSF_Image(data=dat, pixelscale=1.0)
+        return M(name=name, model_type=f"{name[5:-4]} psf model", target=ptar)
+    if name == "init_masked_sheared":
+        S = np.array([[0.8, 0.1], [-0.05, 0.9]])
+        mask = np.zeros(dat.shape, dtype=bool)
+        mask[10:18, 50:60] = True
+        tar = ap.image.Target_Image(data=dat, pixelscale=S, origin=[3.0, -2.0], zeropoint=22.5, mask=mask)
+        return M(name=name, model_type="sersic galaxy model", target=tar, window=[[8, 72], [4, 68]])
+    if name == "init_group":
+        tar = ap.image.Target_Image(data=dat, pixelscale=1.0, zeropoint=22.5)
+        sky = M(name="ig_sky", model_type="flat sky model", target=tar)
+        gals = [M(name=f"ig_gal{k}", model_type="sersic galaxy model", target=tar,
+                  window=[[int(cx) - 16, int(cx) + 16], [int(cy) - 16, int(cy) + 16]])
+                for k, (cx, cy) in enumerate([(28.3, 30.6), (60.2, 40.1), (45.7, 70.4)])]
+        return M(name=name, model_type="group model", models=[sky] + gals, target=tar)
+    raise KeyError(name)
