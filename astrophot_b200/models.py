@@ -733,6 +733,8 @@ class Flat_Sky(Sky_Model):
         from . import init_heuristics as ih
 
         F = self.parameters["F"]
+        if F.value is not None and F.uncertainty is not None:
+            return
         dat = target[self.window].data.detach().cpu().numpy().astype(np.float64)
         area = float(target.pixel_area)
         with Param_Unlock(F), Param_SoftLimits(F):
@@ -761,7 +763,9 @@ class Plane_Sky(Sky_Model):
         from . import init_heuristics as ih
 
         F, delta = self.parameters["F"], self.parameters["delta"]
-        dat = target[self.window].data.detach().cpu().numpy().astype(np.float64)
+        dat = None
+        if F.value is None or F.uncertainty is None:
+            dat = target[self.window].data.detach().cpu().numpy().astype(np.float64)
         with Param_Unlock(F), Param_SoftLimits(F):
             if F.value is None:
                 F.value = np.median(dat) / float(target.pixel_area)

@@ -145,7 +145,7 @@ def build_crowded(ap, workload, data=None):
         cx, cy = rng.uniform(40, size - 40, size=2)
         models.append(M(name=f"p{k}", model_type="point model", target=tar, window=[box(cx, 26, 27), box(cy, 26, 27)],
                         parameters={"center": [cx, cy], "flux": rng.uniform(1, 2)}))
-    sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": -2.0})
+    sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": {"value": -2.0, "uncertainty": 0.01}})
     sky.initialize()
     models.append(sky)
     return M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
@@ -179,7 +179,7 @@ def build_mosaic(ap, workload, data=None):
             models.append(M(name=f"s{k}", model_type="spline galaxy model", target=tar, window=win,
                             parameters={"center": [cx, cy], "q": q, "PA": pa,
                                         "I(R)": {"value": [float(v) for v in val], "prof": [float(r) for r in prof]}}))
-    sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": -2.0})
+    sky = M(name="sky", model_type="flat sky model", target=tar, parameters={"F": {"value": -2.0, "uncertainty": 0.01}})
     sky.initialize()
     models.append(sky)
     return M(name="mosaic", model_type="group model", models=models, target=tar)
