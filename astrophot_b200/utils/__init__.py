@@ -2,7 +2,7 @@
 equivalents under `utils/initialize/construct_psf.py:8-65`)."""
 import numpy as np
 
-__all__ = ["gaussian_psf", "moffat_psf"]
+__all__ = ["gaussian_psf", "moffat_psf", "initialize"]
 
 
 def _grid(img_width, pixelscale, upsample):
@@ -30,3 +30,6 @@ def moffat_psf(n, Rd, img_width, pixelscale, upsample=4):
     X, Y = _grid(img_width, pixelscale, upsample)
     z = _bin(1.0 / (1.0 + (X**2 + Y**2) / Rd**2) ** n, img_width, upsample)
     return z / z.sum()
+
+
+from . import initialize  # noqa: E402  (ap.utils.initialize.*, as in the reference)

@@ -30,6 +30,30 @@ def main():
         if "spline" in name:
             fix[f"{name}:prof"] = model["I(R)"].prof.detach().cpu().numpy()
         print(name, fix[f"{name}:value"], fix[f"{name}:uncertainty"])
+    # windows / start values from a segmentation map (utils/initialize/segmentation_map.py)
+    import torch
+    seg, img = scenes.segmentation_inputs(load_golden)
+    I = ap.utils.initialize
+    cen = I.centroids_from_segmentation_map(seg, img)
+    pas = I.PA_from_segmentation_map(seg, img, cen)
+    qs = I.q_from_segmentation_map(seg, img, cen, pas)
+    win = I.windows_from_segmentation_map(seg)
+    scaled = I.scale_windows(win, image_shape=img.shape, expand_scale=1.5, expand_border=3)
+    kept = I.filter_windows(scaled, min_size=12, max_size=120, min_area=200, max_area=9000, min_flux=40.0, image=img)
+    base = ap.image.Target_Image(data=img, pixelscale=1.0, zeropoint=22.5)
+    other = ap.image.Target_Image(data=np.zeros((300, 280)), pixelscale=torch.tensor([[0.6, 0.1], [-0.1, 0.6]]),
+                                  origin=[-5.0, 3.0], zeropoint=22.5)
+    moved = I.transfer_windows(kept, base, other)
+    ids = sorted(cen)
+    fix["seg:ids"] = np.array(ids)
+    fix["seg:centroids"] = np.array([cen[i] for i in ids], dtype=np.float64)
+    fix["seg:PA"] = np.array([pas[i] for i in ids], dtype=np.float64)
+    fix["seg:q"] = np.array([qs[i] for i in ids], dtype=np.float64)
+    fix["seg:windows"] = np.array([win[i] for i in ids], dtype=np.float64)
+    fix["seg:scaled"] = np.array([scaled[i] for i in ids], dtype=np.float64)
+    fix["seg:kept_ids"] = np.array(sorted(kept))
+    fix["seg:moved"] = np.array([moved[i] for i in sorted(kept)], dtype=np.float64)
+    print("segments", len(ids), "kept", len(kept))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "initialize.npz"), **fix)
 
 

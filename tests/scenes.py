@@ -397,3 +397,14 @@ def build_init(ap, name, dat):
                 for k, (cx, cy) in enumerate([(28.3, 30.6), (60.2, 40.1), (45.7, 70.4)])]
         return M(name=name, model_type="group model", models=[sky] + gals, target=tar)
     raise KeyError(name)
+
+
+def segmentation_inputs(load_golden):
+    """(segmentation map, image) for the ap.utils.initialize tests: the crowded golden scene + seeded noise, segments =
+    connected regions above a threshold (scipy.ndimage.label), ids shuffled so that they are not 1..K in scan order."""
+    from scipy import ndimage
+    img = make_data([load_golden("crowded")["img0"]], 321)[0]["data"]
+    lab, n = ndimage.label(ndimage.gaussian_filter(img, 1.5) > 0.25)
+    perm = np.random.default_rng(5).permutation(n) + 3
+    seg = np.where(lab > 0, perm[np.maximum(lab, 1) - 1], 0)
+    return seg, img

@@ -26,3 +26,37 @@ def test_initialize_matches_reference(host_only, name):  # noqa: F811
                                atol=1e-9)
     if "spline" in name:
         np.testing.assert_allclose(model["I(R)"].prof.numpy(), fix[f"{name}:prof"], rtol=1e-12)
+
+
+def test_segmentation_map_utilities_match_reference():
+    """ap.utils.initialize (windows, centroids, PA, q from a segmentation map; scaling, filtering and transfer of windows)
+    against the reference's own output on the same map (`utils/initialize/segmentation_map.py`)."""
+    import torch
+    fix = load_golden("initialize")
+    seg, img = scenes.segmentation_inputs(load_golden)
+    I = ap.utils.initialize
+    cen = I.centroids_from_segmentation_map(seg, img)
+    pas = I.PA_from_segmentation_map(seg, img, cen)
+    qs = I.q_from_segmentation_map(seg, img, cen, pas)
+    win = I.windows_from_segmentation_map(seg)
+    ids = sorted(cen)
+    assert ids == list(fix["seg:ids"]) and sorted(win) == ids and len(ids) > 10
+    np.testing.assert_allclose([cen[i] for i in ids], fix["seg:centroids"], rtol=1e-12)
+    np.testing.assert_allclose([pas[i] for i in ids], fix["seg:PA"], rtol=1e-10)
+    np.testing.assert_allclose([qs[i] for i in ids], fix["seg:q"], rtol=1e-10)
+    np.testing.assert_array_equal(np.array([win[i] for i in ids]), fix["seg:windows"])
+    # defaults recompute what is not passed
+    np.testing.assert_allclose([I.q_from_segmentation_map(seg, img)[i] for i in ids], fix["seg:q"], rtol=1e-10)
+    scaled = I.scale_windows(win, image_shape=img.shape, expand_scale=1.5, expand_border=3)
+    np.testing.assert_array_equal(np.array([scaled[i] for i in ids]), fix["seg:scaled"])
+    kept = I.filter_windows(scaled, min_size=12, max_size=120, min_area=200, max_area=9000, min_flux=40.0, image=img)
+    assert sorted(kept) == list(fix["seg:kept_ids"]) and 0 < len(kept) < len(ids)
+    base = ap.image.Target_Image(data=img, pixelscale=1.0, zeropoint=22.5)
+    other = ap.image.Target_Image(data=np.zeros((300, 280)), pixelscale=torch.tensor([[0.6, 0.1], [-0.1, 0.6]]),
+                                  origin=[-5.0, 3.0], zeropoint=22.5)
+    moved = I.transfer_windows(kept, base, other)
+    np.testing.assert_array_equal(np.array([moved[i] for i in sorted(kept)]), fix["seg:moved"])
+    # the windows feed straight into models
+    k = sorted(kept)[0]
+    m = ap.models.AstroPhot_Model(name="w", model_type="sersic galaxy model", target=base, window=kept[k])
+    assert tuple(int(v) for v in m.window.pixel_shape) == (kept[k][0][1] - kept[k][0][0], kept[k][1][1] - kept[k][1][0])
