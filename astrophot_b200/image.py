@@ -639,12 +639,19 @@ class Model_Image(Image):
         return super().reduce(scale, target_identity=self.target_identity, **kwargs)
 
     def replace(self, other, data=None):
+        """Overwrite the overlap with another image, a window's worth of ``data``, or everything (reference:
+        `model_image.py:51-63`)."""
         if isinstance(other, Image):
             mine = self.window.get_self_indices(other)
             theirs = other.window.get_self_indices(self)
+            if self._data[mine].numel() == 0 or other._data[theirs].numel() == 0:
+                return
             self._data[mine] = other._data[theirs]
+        elif isinstance(other, Window):
+            self._data[self.window.get_self_indices(other)] = torch.as_tensor(data, dtype=self._data.dtype,
+                                                                              device=self._data.device)
         else:
-            raise TypeError("Model_Image can only replace with Image objects")
+            self.data = other
 
 
 class Jacobian_Image(Image):
@@ -944,8 +951,13 @@ class Image_List(Image):
 
     def _each(self, other, op):
         if isinstance(other, Image_List):
-            for o in other.image_list:
-                op(self.image_list[self.index(o)], o)
+            try:
+                pairs = [(self.image_list[self.index(o)], o) for o in other.image_list]
+            except ValueError:
+                # unrelated images: element by element, like the reference's base list (image_object.py:619-638)
+                pairs = list(zip(self.image_list, other.image_list))
+            for a, b in pairs:
+                op(a, b)
         elif isinstance(other, Image):
             op(self.image_list[self.index(other)], other)
         else:
@@ -996,9 +1008,15 @@ class Model_Image_List(Image_List, Model_Image):
         for im in self.image_list:
             im.clear_image()
 
+    def replace(self, other, data=None):
+        """Element by element (reference: `model_image.py:110-116`)."""
+        for k, (im, oth) in enumerate(zip(self.image_list, other)):
+            im.replace(oth, None if data is None else data[k])
+
     @property
     def target_identity(self):
-        return tuple(im.target_identity for im in self.image_list)
+        ids = tuple(im.target_identity for im in self.image_list)
+        return None if any(i is None for i in ids) else ids
 
     def index(self, other):
         key = getattr(other, "target_identity", None) or other.identity

@@ -2,7 +2,7 @@
 equivalents under `utils/initialize/construct_psf.py:8-65`)."""
 import numpy as np
 
-__all__ = ["gaussian_psf", "moffat_psf", "initialize"]
+__all__ = ["gaussian_psf", "moffat_psf", "initialize", "conversions", "parametric_profiles", "angle_operations"]
 
 
 def _grid(img_width, pixelscale, upsample):
@@ -18,18 +18,20 @@ def _bin(z, img_width, upsample):
     return z.reshape(img_width, upsample, img_width, upsample).sum(axis=(1, 3))
 
 
-def gaussian_psf(sigma, img_width, pixelscale, upsample=4):
-    """Normalised, pixel-integrated (by ``upsample``^2 sub-sampling) circular Gaussian."""
+def gaussian_psf(sigma, img_width, pixelscale, upsample=4, normalize=True):
+    """Pixel-integrated (mean of ``upsample``^2 sub-samples) circular Gaussian, normalised to unit sum by default."""
     X, Y = _grid(img_width, pixelscale, upsample)
-    z = _bin(np.exp(-0.5 * (X**2 + Y**2) / sigma**2), img_width, upsample)
-    return z / z.sum()
+    z = _bin(np.exp(-0.5 * (X**2 + Y**2) / sigma**2), img_width, upsample) / upsample**2
+    return z / z.sum() if normalize else z
 
 
-def moffat_psf(n, Rd, img_width, pixelscale, upsample=4):
-    """Normalised, pixel-integrated circular Moffat."""
+def moffat_psf(n, Rd, img_width, pixelscale, upsample=4, normalize=True):
+    """Pixel-integrated circular Moffat, normalised to unit sum by default."""
     X, Y = _grid(img_width, pixelscale, upsample)
-    z = _bin(1.0 / (1.0 + (X**2 + Y**2) / Rd**2) ** n, img_width, upsample)
-    return z / z.sum()
+    z = _bin(1.0 / (1.0 + (X**2 + Y**2) / Rd**2) ** n, img_width, upsample) / upsample**2
+    return z / z.sum() if normalize else z
 
 
-from . import initialize  # noqa: E402  (ap.utils.initialize.*, as in the reference)
+from . import angle_operations, conversions, initialize, parametric_profiles  # noqa: E402  (ap.utils.<module>.*, as in the reference)
+
+initialize.gaussian_psf, initialize.moffat_psf = gaussian_psf, moffat_psf      # where the reference keeps them
