@@ -941,8 +941,11 @@ class Image_List(Image):
         return self.__class__([im.get_window(w) for im, w in zip(self.image_list, window)])
 
     def index(self, other):
+        """Position of ``other`` (or, for a model / Jacobian image, of the target it was made for; reference:
+        `target_image.py:602-630`)."""
+        keys = {other.identity, getattr(other, "target_identity", None)} - {None}
         for i, im in enumerate(self.image_list):
-            if other.identity == im.identity:
+            if im.identity in keys:
                 return i
         raise ValueError("Could not find identity match between image list and input image")
 

@@ -341,7 +341,9 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
         return build_source(pm, ii, region, out, fwd, jac, host=comp)
 
     for comp in _components(model):
-        if not isinstance(comp, Component_Model) or comp._kind is None:
+        if isinstance(comp, Component_Model) and comp._kind is None:
+            continue     # the abstract bases ("model", "galaxy model", ...) evaluate to zero (model_object.py:235-256)
+        if not isinstance(comp, Component_Model):
             raise SpecificationConflict(
                 f"model type '{comp.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §2)")
         ii = ident_to_img.get(comp.target.identity)

@@ -219,7 +219,7 @@ class AstroPhot_Model:
         from .cabi import Plan
 
         scene, info = lower(self, window=window)
-        return Plan(scene), scene, info
+        return (Plan(scene) if scene.sources else None), scene, info
 
     def __call__(self, image=None, parameters=None, window=None, as_representation=False, **kwargs):
         if isinstance(parameters, (torch.Tensor, np.ndarray, list, tuple)):
@@ -238,7 +238,10 @@ class AstroPhot_Model:
         plan, scene, info = self._plan(window)
         x = torch.as_tensor(self.parameters.vector_values().numpy(), dtype=torch.float64,
                             device=AP_config.ap_device)
-        outs = plan.sample(x, as_rep=False)
+        if scene.sources:
+            outs = plan.sample(x, as_rep=False)
+        else:       # nothing but abstract base models: zero flux, nothing to launch
+            outs = [torch.zeros((im.H, im.W), dtype=torch.float64, device=AP_config.ap_device) for im in scene.images]
         result = wrap_model_images(self, info, outs)
         if image is None:
             return result
@@ -260,7 +263,11 @@ class AstroPhot_Model:
         plan, scene, info = self._plan(window)
         vec = self.parameters.vector_representation() if as_representation else self.parameters.vector_values()
         x = torch.as_tensor(vec.numpy(), dtype=torch.float64, device=AP_config.ap_device)
-        outs = plan.jacobian(x, as_rep=as_representation)
+        if scene.sources:
+            outs = plan.jacobian(x, as_rep=as_representation)
+        else:
+            outs = [torch.zeros((im.H, im.W, scene.n_par), dtype=torch.float64, device=AP_config.ap_device)
+                    for im in scene.images]
         result = wrap_jacobian_images(self, info, outs)
         if pass_jacobian is not None:
             pass_jacobian += result
@@ -876,6 +883,17 @@ class Moffat_PSF(PSF_Model):
 
 class Moffat2D_PSF(PSF_Model):
     total_flux = Moffat_PSF.total_flux       # the reference's Moffat2D_PSF inherits it (q = 1 there too)
+
+    def _init_shape(self, target):
+        """Fixed start shape (reference: `moffat_model.py:139-148`)."""
+        for name, start in (("q", 0.9), ("PA", 0.1)):
+            P = self.parameters[name]
+            with Param_Unlock(P), Param_SoftLimits(P):
+                if P.value is None:
+                    P.value = start
+
+    def _init_transform(self, X, Y, area):
+        return Galaxy_Model._init_transform(self, X, Y, area)
     model_type = f"moffat2d {PSF_Model.model_type}"
     parameter_specs = {
         "q": {"units": "b/a", "limits": (0, 1), "uncertainty": 0.03},
@@ -938,6 +956,8 @@ class Group_Model(AstroPhot_Model):
     usable = True
 
     def __init__(self, *, name=None, models=None, **kwargs):
+        if "model" in kwargs:
+            AP_config.ap_logger.warning("kwarg `model` is not used in Group_Model, did you mean `models` instead?")
         self.models = OrderedDict()
         self._psf_mode = "none"
         super().__init__(name=name, models=models, **kwargs)

@@ -2,7 +2,7 @@
 equivalents under `utils/initialize/construct_psf.py:8-65`)."""
 import numpy as np
 
-__all__ = ["gaussian_psf", "moffat_psf", "initialize", "conversions", "parametric_profiles", "angle_operations"]
+__all__ = ["gaussian_psf", "moffat_psf", "initialize", "conversions", "parametric_profiles", "angle_operations", "optimization"]
 
 
 def _grid(img_width, pixelscale, upsample):
@@ -32,6 +32,6 @@ def moffat_psf(n, Rd, img_width, pixelscale, upsample=4, normalize=True):
     return z / z.sum() if normalize else z
 
 
-from . import angle_operations, conversions, initialize, parametric_profiles  # noqa: E402  (ap.utils.<module>.*, as in the reference)
+from . import angle_operations, conversions, initialize, optimization, parametric_profiles  # noqa: E402  (ap.utils.<module>.*, as in the reference)
 
 initialize.gaussian_psf, initialize.moffat_psf = gaussian_psf, moffat_psf      # where the reference keeps them
