@@ -122,11 +122,16 @@ class Window:
 
     @property
     def pixel_area(self):
-        return _ht(abs(np.linalg.det(self._S)))
+        return _ht(abs(self._det()))
 
     @property
     def pixel_length(self):
-        return _ht(np.sqrt(abs(np.linalg.det(self._S))))
+        return _ht(np.sqrt(abs(self._det())))
+
+    def _det(self):
+        # (written out: LAPACK's LU gives 15.999999999999998 for diag(4, 4))
+        S = self._S
+        return S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]
 
     # -- coordinate maps (numpy core, tensor wrappers) ----------------------
     def _pix2plane(self, p):
@@ -572,6 +577,10 @@ class Image:
 
     def reduce(self, scale, **kwargs):
         """Sum ``scale`` x ``scale`` pixel blocks (reference: `image_object.py:348-376`)."""
+        if isinstance(scale, torch.Tensor) and scale.dtype in (torch.int32, torch.int64):
+            scale = int(scale)
+        if not isinstance(scale, (int, np.integer)) or isinstance(scale, bool):
+            raise SpecificationConflict(f"Reduce scale must be an integer! not {type(scale)}")
         scale = int(scale)
         if scale == 1:
             return self
@@ -829,16 +838,19 @@ class Target_Image(Image):
         if variance is None:
             self._weight = None
             return
-        if isinstance(variance, str):
-            raise SpecificationConflict("variance='auto' is an input-prep heuristic outside the scope of astrophot_b200")
+        if isinstance(variance, str) and variance == "auto":
+            self.set_weight("auto")
+            return
         self.set_weight(1.0 / _dev(variance))
 
     def set_weight(self, weight):
         if weight is None:
             self._weight = None
             return
-        if isinstance(weight, str):
-            raise SpecificationConflict("weight='auto' is an input-prep heuristic outside the scope of astrophot_b200")
+        if isinstance(weight, str) and weight == "auto":
+            # estimated from the image itself (reference: `target_image.py:291-292`, `utils/initialize/variance.py`)
+            from .utils.initialize import auto_variance
+            weight = torch.as_tensor(1 / auto_variance(self._data, self._mask))
         if tuple(weight.shape) != tuple(self._data.shape):
             raise SpecificationConflict(
                 f"weight/variance must have same shape as data ({tuple(weight.shape)} vs {tuple(self._data.shape)})")
@@ -899,7 +911,21 @@ class Target_Image(Image):
                               window=self.window, zeropoint=self.zeropoint, **kwargs)
 
     def reduce(self, scale, **kwargs):
-        raise NotImplementedError("Target_Image.reduce is input prep, outside the scope of astrophot_b200")
+        """Lower resolution copy: data and variance summed over ``scale`` x ``scale`` blocks, a block masked when any
+        of its pixels is, the PSF reduced alike (reference: `target_image.py:443-478`)."""
+        if scale == 1:
+            return self
+        MS, NS = self._data.shape[0] // scale, self._data.shape[1] // scale
+
+        def blocks(t):
+            return t[: MS * scale, : NS * scale].reshape(MS, scale, NS, scale)
+
+        return super().reduce(
+            scale,
+            variance=blocks(self.variance).sum(dim=(1, 3)) if self.has_variance else None,
+            mask=blocks(self.mask).amax(dim=(1, 3)) if self.has_mask else None,
+            psf=self.psf.reduce(scale) if self.has_psf else None,
+            **kwargs)
 
 
 class Image_List(Image):

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 from scipy import ndimage
 
-__all__ = ("centroids_from_segmentation_map", "PA_from_segmentation_map", "q_from_segmentation_map",
+__all__ = ("auto_variance", "centroids_from_segmentation_map", "PA_from_segmentation_map", "q_from_segmentation_map",
            "windows_from_segmentation_map", "scale_windows", "filter_windows", "transfer_windows")
 
 
@@ -138,3 +138,43 @@ def transfer_windows(windows, base_image, new_image):
         hi = np.clip(np.ceil(to_new(x1, y1)), a_min=0, a_max=top)
         out[key] = [[lo[0], hi[0]], [lo[1], hi[1]]]
     return out
+
+
+def auto_variance(data, mask=None):
+    """Variance map estimated from the image itself (reference: `utils/initialize/variance.py:12-55`): the scatter of
+    the pixels about a lightly smoothed copy of the image, binned by flux, is fitted with a straight line in flux
+    (read noise + Poisson term) and evaluated at every pixel; masked pixels get infinite variance.  Images too small
+    or too flat for that get a constant."""
+    from scipy.ndimage import gaussian_filter
+    from scipy.stats import binned_statistic
+
+    from ..errors import InvalidData
+
+    if isinstance(data, torch.Tensor):
+        data = data.detach().cpu().numpy()
+    if isinstance(mask, torch.Tensor):
+        mask = mask.detach().cpu().numpy()
+    if mask is None:
+        mask = np.zeros(data.shape, dtype=int)
+    good = np.logical_not(mask)
+    flat = np.var(data[good])
+    if not np.isfinite(flat) or flat == 0:
+        return np.ones_like(data)
+    if min(data.shape) < 20:
+        return np.ones_like(data) * flat
+    inner = (slice(4, -4), slice(4, -4))                       # away from the filter's edge effects
+    clean = gaussian_filter(mask, 1.1)[inner] == 0             # pixels whose smoothing kernel saw no masked pixel
+    flux = data[inner][clean]
+    resid = (data[inner] - gaussian_filter(data, 1.1)[inner])[clean]
+    lo, hi = np.quantile(data[good], 0.01), np.quantile(data[good], 0.99)
+    std, edges, _ = binned_statistic(flux.flatten(), resid.flatten(), statistic="std", bins=np.linspace(lo, hi, 11))
+    left = edges[:-1]
+    empty = ~np.isfinite(std)
+    if np.any(empty):
+        std[empty] = np.sqrt(np.interp(left[empty], left[~empty], std[~empty] ** 2))
+    slope, offset = np.polyfit(left[:-2], std[:-2] ** 2, 1)   # the two brightest bins are left out
+    if slope < 0:
+        raise InvalidData("Variance appears to be decreasing with flux! Cannot accurately estimate variance.")
+    variance = np.clip(slope * data + offset, np.min(std) ** 2, None)
+    variance[~good] = np.inf
+    return variance

@@ -54,6 +54,14 @@ def main():
     fix["seg:kept_ids"] = np.array(sorted(kept))
     fix["seg:moved"] = np.array([moved[i] for i in sorted(kept)], dtype=np.float64)
     print("segments", len(ids), "kept", len(kept))
+    # variance map estimated from the image (utils/initialize/variance.py), with and without a mask
+    amask = np.zeros(img.shape, dtype=bool)
+    amask[30:50, 100:130] = True
+    fix["autovar:plain"] = I.auto_variance(img)
+    fix["autovar:masked"] = I.auto_variance(img, amask)
+    fix["autovar:small"] = I.auto_variance(img[:15, :40])
+    t = ap.image.Target_Image(data=img, pixelscale=1.0, zeropoint=22.5, variance="auto", mask=amask)
+    fix["autovar:weight"] = t.weight.detach().cpu().numpy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "initialize.npz"), **fix)
 
 

@@ -60,3 +60,25 @@ def test_segmentation_map_utilities_match_reference():
     k = sorted(kept)[0]
     m = ap.models.AstroPhot_Model(name="w", model_type="sersic galaxy model", target=base, window=kept[k])
     assert tuple(int(v) for v in m.window.pixel_shape) == (kept[k][0][1] - kept[k][0][0], kept[k][1][1] - kept[k][1][0])
+
+
+def test_auto_variance_matches_reference():
+    """variance="auto": the variance map estimated from the image itself (`utils/initialize/variance.py:12-55`,
+    `target_image.py:278-292`) -- the W of the fit when the user has no variance map."""
+    fix = load_golden("initialize")
+    _, img = scenes.segmentation_inputs(load_golden)
+    amask = np.zeros(img.shape, dtype=bool)
+    amask[30:50, 100:130] = True
+    I = ap.utils.initialize
+    np.testing.assert_allclose(I.auto_variance(img), fix["autovar:plain"], rtol=1e-10)
+    got = I.auto_variance(img, amask)
+    assert np.all(np.isinf(got[amask])) and np.all(np.isfinite(got[~amask])) and got[~amask].min() > 0
+    np.testing.assert_allclose(got, fix["autovar:masked"], rtol=1e-10)
+    np.testing.assert_allclose(I.auto_variance(img[:15, :40]), fix["autovar:small"], rtol=1e-12)      # too small: constant
+    assert np.all(I.auto_variance(np.zeros((30, 30))) == 1.0)                                         # flat: ones
+    ap.AP_config.ap_device = "cpu"
+    t = ap.image.Target_Image(data=img, pixelscale=1.0, zeropoint=22.5, variance="auto", mask=amask)
+    np.testing.assert_allclose(t.weight.numpy(), fix["autovar:weight"], rtol=1e-10)
+    assert np.all(t.weight.numpy()[amask] == 0)
+    t2 = ap.image.Target_Image(data=img, pixelscale=1.0, zeropoint=22.5, weight="auto")
+    np.testing.assert_allclose(t2.variance.numpy(), fix["autovar:plain"], rtol=1e-10)
