@@ -68,6 +68,9 @@ class Node:
             raise ValueError(f"Node names must not have ':' character. Cannot use name: {name}")
         self.name = name
         self.nodes = OrderedDict()
+        if "state" in kwargs:
+            self.set_state(kwargs["state"])
+            return
         if "link" in kwargs:
             self.link(*kwargs["link"])
         self.locked = kwargs.get("locked", False)
@@ -88,6 +91,22 @@ class Node:
 
     def dump(self):
         self.unlink(*list(self.nodes.values()))
+
+    # -- state (plain dict; reference: `param/base.py:134-161`) ------------------------------------------------------
+    def get_state(self):
+        state = {"name": self.name, "identity": self.identity}
+        if self.locked:
+            state["locked"] = True
+        if len(self.nodes) > 0:
+            state["nodes"] = [n.get_state() for n in self.nodes.values()]
+        return state
+
+    def set_state(self, state):
+        self.name = state["name"]
+        self._identity = state["identity"]
+        for sub in state.get("nodes", ()):
+            self.link(self.__class__(name=sub["name"], state=sub))
+        self.locked = state.get("locked", False)
 
     @property
     def leaf(self):
@@ -165,6 +184,8 @@ class Parameter_Node(Node):
 
     def __init__(self, name, **kwargs):
         super().__init__(name, **kwargs)
+        if "state" in kwargs:          # rebuilt by set_state (called from Node.__init__)
+            return
         hold = self.locked
         self.locked = False
         self._value = None
@@ -439,12 +460,33 @@ class Parameter_Node(Node):
         return self
 
     # -- persistence / display ----------------------------------------
+    def set_state(self, state):
+        """Rebuild this node from ``get_state()`` of another (reference: `parameter.py:632-647`)."""
+        for attr, default in (("_value", None), ("_shape", None), ("_uncertainty", None), ("_prof", None),
+                              ("_limits", (None, None)), ("cyclic", False), ("units", "none")):
+            if not hasattr(self, attr):
+                object.__setattr__(self, attr, default)
+        self.locked = False
+        Node.set_state(self, state)
+        hold = self.locked
+        self.locked = False
+        self.units = state.get("units", None)
+        self.limits = state.get("limits", (None, None))
+        self.cyclic = state.get("cyclic", False)
+        if "shape" in state and "value" in state and not isinstance(state["value"], str):
+            self.shape = state["shape"]
+        if not isinstance(state.get("value"), str):        # (pointer / function nodes are re-linked by their owner)
+            self.value = state.get("value", None)
+        self.uncertainty = state.get("uncertainty", None)
+        self.prof = state.get("prof", None)
+        self.locked = hold
+
     def get_state(self):
-        state = {"name": self.name, "identity": self.identity}
-        if self.locked:
-            state["locked"] = True
-        if len(self.nodes) > 0:
-            state["nodes"] = [n.get_state() for n in self.nodes.values()]
+        state = Node.get_state(self)
+        if isinstance(self._value, Parameter_Node):
+            state["value"] = "NODE:" + str(self._value.identity)
+        elif isinstance(self._value, FunctionType):
+            state["value"] = "FUNCTION:" + self._value.__name__
         if self.leaf and self.value is not None:
             state["value"] = self.value.tolist()
             state["shape"] = list(self.shape)
@@ -460,13 +502,49 @@ class Parameter_Node(Node):
                 state["prof"] = self.prof.tolist()
         return state
 
-    def __str__(self):
-        v = self.value
-        if self.leaf and v is not None:
-            return f"{self.name}: {v.tolist()}"
-        return f"{self.name}: [" + ", ".join(str(n) for n in self.nodes.values()) + "]"
+    # -- report (the text users read after a fit; same layout as the reference, `parameter.py:677-742`) ------------
+    def print_params(self, include_locked=True, include_prof=True, include_id=True):
+        """One line for this node: ``name: value +- uncertainty [units], limits: (lo, hi), cyclic, locked, prof: ...``
+        for a leaf; ``name points to: <line of the target>`` for a pointer; ``name:`` for a branch or function node."""
+        tag = f" (id-{self.identity})" if include_id else ""
+        if isinstance(self._value, Parameter_Node):
+            return f"{self.name}{tag} points to: " + self._value.print_params(include_locked, include_prof, include_id)
+        if not self.leaf:
+            if include_id:
+                kind = f"function node, {self._value.__name__}" if isinstance(self._value, FunctionType) else "branch node"
+                tag = f" (id-{self.identity}, {kind})"
+            return f"{self.name}{tag}:\n"
 
-    __repr__ = __str__
+        def listed(t):
+            return None if t is None else t.detach().cpu().tolist()
+
+        lo, hi = self.limits
+        parts = [f"{self.name}{tag}: {listed(self.value)}"]
+        if self.uncertainty is not None:
+            parts.append(f" +- {listed(self.uncertainty)}")
+        parts.append(f" [{self.units}]")
+        if lo is not None or hi is not None:
+            parts.append(f", limits: ({listed(lo)}, {listed(hi)})")
+        if self.cyclic:
+            parts.append(", cyclic")
+        if self.locked:
+            parts.append(", locked")
+        if include_prof and self.prof is not None:
+            parts.append(f", prof: {listed(self.prof)}")
+        return "".join(parts)
+
+    def __str__(self):
+        head = self.print_params(include_locked=True, include_prof=False, include_id=False)
+        if self.leaf or isinstance(self._value, Parameter_Node):
+            return head
+        return head + "\n".join(n.print_params(include_locked=True, include_prof=False, include_id=False)
+                                for n in self.flat(include_locked=True, include_links=False).values())
+
+    def __repr__(self, level=0, indent="  "):
+        head = indent * level + self.print_params(include_locked=True, include_prof=False, include_id=True)
+        if self.leaf or isinstance(self._value, Parameter_Node):
+            return head
+        return head + "\n".join(n.__repr__(level=level + 1, indent=indent) for n in self.nodes.values())
 
 
 class Param_Unlock:

@@ -272,3 +272,25 @@ def test_iter_lm_control_flow_on_the_oracle(monkeypatch):
                              LM_kwargs={"max_iter": 3, "relative_tolerance": 0.0}).fit()
         np.testing.assert_allclose(res.loss_history, fix["iterlm_loss_history"], rtol=1e-8)
         np.testing.assert_allclose(np.array(res.lambda_history), fix["iterlm_lambda_history"], rtol=1e-7, atol=1e-7)
+
+
+def test_parameter_report_and_state_round_trip():
+    """The text a user reads after a fit (``print(model.parameters)``) and the plain-dict state of the parameter graph
+    (reference: `parameter.py:598-647,677-742`, `param/base.py:134-161`)."""
+    from astrophot_b200.param import Parameter_Node
+    a = Parameter_Node("a", value=[1.0, 2.0], uncertainty=[0.1, 0.2], limits=(0, None), units="arcsec")
+    b = Parameter_Node("b", value=3.0, locked=True, prof=[0.0, 1.0], cyclic=True, limits=(0, 3.5))
+    ptr = Parameter_Node("ptr", value=a)
+    g = Parameter_Node("g", link=(a, b, ptr))
+    assert str(a) == "a: [1.0, 2.0] +- [0.1, 0.2] [arcsec], limits: (0.0, None)"
+    assert str(b) == "b: 3.0 [none], limits: (0.0, 3.5), cyclic, locked"
+    assert str(g) == "g:\n" + str(a) + "\n" + str(b)            # every leaf once, pointers are not repeated
+    lines = repr(g).split("\n")
+    assert lines[0].startswith("g (id-") and lines[0].endswith(", branch node):")
+    assert lines[1].startswith("  a (id-") and " points to: a (id-" in lines[3]
+    assert b.print_params(include_id=False).endswith("prof: [0.0, 1.0]")
+    g2 = Parameter_Node("other", state=Parameter_Node("g", link=(a, b)).get_state())
+    assert g2.name == "g" and list(g2.nodes) == ["a", "b"]
+    assert str(g2["a"]) == str(a) and str(g2["b"]) == str(b) and g2["b"].locked and g2["a"].identity == a.identity
+    np.testing.assert_array_equal(g2["b"].prof.numpy(), [0.0, 1.0])
+    assert g.get_state()["nodes"][2]["value"] == f"NODE:{a.identity}"
