@@ -309,6 +309,10 @@ class AstroPhot_Model:
     @classmethod
     def List_Models(cls, usable=None):
         models = _all_subclasses(cls)
+        if cls is not AstroPhot_Model and not issubclass(cls, PSF_Model):
+            # PSF models share the component machinery here but are a separate family in the reference
+            # (psf_model_object.py: PSF_Model(AstroPhot_Model)): Component_Model.List_Models() does not list them
+            models = [m for m in models if not issubclass(m, PSF_Model)]
         if usable is not None:
             models = [m for m in models if m.usable is usable]
         return models
