@@ -60,7 +60,8 @@ class AstroPhot_Model:
 
     def __new__(cls, *, filename=None, model_type=None, **kwargs):
         if filename is not None:
-            raise NotImplementedError("loading models from file is outside the hot-path scope of astrophot_b200")
+            # a saved model names its own type (reference: `core_model.py:99-106`)
+            model_type = AstroPhot_Model.load(filename)["model_type"]
         if model_type is not None:
             for M in _all_subclasses(AstroPhot_Model):
                 if M.model_type == model_type:
@@ -303,8 +304,43 @@ class AstroPhot_Model:
         dF = self.total_flux_uncertainty(parameters=parameters, window=window)
         return torch.abs(2.5 * dF / (F * np.log(10)))
 
+    # -- saved state (reference: `core_model.py:374-451`); the target image is never part of it ------------------
     def get_state(self, *args, **kwargs):
         return {"name": self.name, "model_type": self.model_type}
+
+    def save(self, filename="AstroPhot.yaml"):
+        """Write ``get_state()`` as YAML or JSON."""
+        state = self.get_state()
+        if isinstance(filename, str) and filename.endswith(".yaml"):
+            import yaml
+            with open(filename, "w") as f:
+                yaml.dump(state, f, indent=2, sort_keys=False)      # (the order of a group's models is part of the state)
+        elif isinstance(filename, str) and filename.endswith(".json"):
+            import json
+            with open(filename, "w") as f:
+                json.dump(state, f, indent=2)
+        else:
+            raise ValueError(f"Unrecognized filename format: {filename}, must be one of: .json, .yaml "
+                             "(hdf5 needs h5py, which astrophot_b200 does not depend on)")
+
+    @classmethod
+    def load(cls, filename="AstroPhot.yaml"):
+        """The state dictionary of a saved model: a dict (returned as it is), an open text stream, a .yaml or .json file."""
+        import io
+        if isinstance(filename, dict):
+            return filename
+        if isinstance(filename, io.TextIOBase):
+            import yaml
+            return yaml.load(filename, Loader=yaml.FullLoader)
+        if isinstance(filename, str) and filename.endswith(".yaml"):
+            import yaml
+            with open(filename, "r") as f:
+                return yaml.load(f, Loader=yaml.FullLoader)
+        if isinstance(filename, str) and filename.endswith(".json"):
+            import json
+            with open(filename, "r") as f:
+                return json.load(f)
+        raise ValueError(f"Unrecognized filename format: {filename}, must be one of: .json, .yaml or python dictionary.")
 
     @classmethod
     def List_Models(cls, usable=None):
@@ -378,12 +414,63 @@ class Component_Model(AstroPhot_Model):
         super().__init__(name=name, **kwargs)
         # as in the reference (core_model.py:128-134 sets user attributes before the model's own parameters exist):
         # the parameters of an auxiliary PSF model come first in the parameter vector
+        if "filename" in kwargs:
+            self.load(kwargs["filename"], new_name=name)
+            return
         if "psf" in kwargs:
             self.psf = kwargs["psf"]
         self.parameter_specs = self.build_parameter_specs(kwargs.get("parameters", None))
         self.build_parameters()
         if isinstance(kwargs.get("parameters", None), torch.Tensor):
             self.parameters.value = kwargs["parameters"]
+
+    def get_state(self, save_params=True):
+        """Name, type, window, parameters, the knobs that differ from the class defaults and the model's own PSF
+        (reference: `model_object.py:408-428`)."""
+        state = super().get_state()
+        state["window"] = self.window.get_state()
+        if save_params:
+            state["parameters"] = self.parameters.get_state()
+        state["target_identity"] = getattr(self, "_target_identity", None)
+        if isinstance(self._psf, PSF_Image):
+            state["psf"] = {"type": "PSF_Image", "data": self._psf.data.detach().cpu().tolist(),
+                            "window": self._psf.window.get_state()}
+        elif isinstance(self._psf, AstroPhot_Model):
+            state["psf"] = self._psf.get_state()
+            # (the grid a PSF model is sampled on is its target's; zeros stand in for the pixel data)
+            state["psf"]["target_window"] = self._psf.target.window.get_state()
+        for key in self.track_attrs:
+            if getattr(self, key) != getattr(self.__class__, key):
+                state[key] = getattr(self, key)
+        return state
+
+    def load(self, filename="AstroPhot.yaml", new_name=None):
+        """Take window, knobs, parameters and PSF from a saved state; the target stays the one this model was given
+        (reference: `_model_methods.py:437-482`)."""
+        from .image import Window
+
+        state = AstroPhot_Model.load(filename)
+        self.name = state["name"] if new_name is None else new_name
+        self.window = Window(state=state["window"])
+        self._target_identity = state.get("target_identity", None)
+        self.target = self.target
+        for key in self.track_attrs:
+            if key in state:
+                setattr(self, key, state[key])
+        if isinstance(state["parameters"], Parameter_Node):
+            self.parameters = state["parameters"]
+        else:
+            self.parameters = Parameter_Node(self.name, state=state["parameters"]).relink()
+        if "psf" in state:
+            if state["psf"].get("type", "AstroPhot_Model") == "PSF_Image":
+                self._psf = PSF_Image(data=np.array(state["psf"]["data"]), window=Window(state=state["psf"]["window"]))
+            else:
+                sub = dict(state["psf"])
+                sub["parameters"] = self.parameters[sub["name"]]
+                grid = Window(state=sub["target_window"])
+                ptar = PSF_Image(data=np.zeros((int(grid.pixel_shape[1]), int(grid.pixel_shape[0]))), window=grid)
+                self.set_aux_psf(AstroPhot_Model(name=sub["name"], filename=sub, target=ptar), add_parameters=False)
+        return state
 
     @property
     def psf(self):
@@ -798,6 +885,7 @@ class PSF_Model(Component_Model):
     _parameter_order = ("center",)
     model_integrated = False
     normalize_psf = True
+    track_attrs = Component_Model.track_attrs + ["normalize_psf", "model_integrated"]      # saved with the model
     sampling_mode = "simpsons"
     sampling_tolerance = 1e-3
     integrate_mode = "threshold"
@@ -967,6 +1055,8 @@ class Group_Model(AstroPhot_Model):
         super().__init__(name=name, models=models, **kwargs)
         if models is not None:
             self.add_model(models)
+        if "filename" in kwargs:
+            self.load(kwargs["filename"], new_name=name)
         self.update_window()
         if "psf_mode" in kwargs:
             self.psf_mode = kwargs["psf_mode"]
@@ -1042,6 +1132,38 @@ class Group_Model(AstroPhot_Model):
         for model in getattr(self, "models", {}).values():
             model.psf_mode = value
 
+    def get_state(self, save_params=True):
+        """The group's parameter graph once, and every sub-model's state without its parameters (reference:
+        `group_model_object.py:325-337`)."""
+        state = AstroPhot_Model.get_state(self)
+        if save_params:
+            state["parameters"] = self.parameters.get_state()
+        state["models"] = {m.name: m.get_state(save_params=False) for m in self.models.values()}
+        if self.psf_mode != "none":
+            state["psf_mode"] = self.psf_mode
+        return state
+
+    def load(self, filename="AstroPhot.yaml", new_name=None):
+        """Rebuild the parameter graph and hand every sub-model its branch of it; sub-models the group does not hold
+        yet are created on the group's target (reference: `group_model_object.py:339-365`)."""
+        state = AstroPhot_Model.load(filename)
+        self.name = state["name"] if new_name is None else new_name
+        if isinstance(state["parameters"], Parameter_Node):
+            self.parameters = state["parameters"]
+        else:
+            self.parameters = Parameter_Node(self.name, state=state["parameters"]).relink()
+        for name, sub in state["models"].items():
+            sub = dict(sub)
+            sub["parameters"] = self.parameters[name]
+            if name in self.models:
+                self.models[name].load(sub)
+            else:
+                self.add_model(AstroPhot_Model(name=name, filename=sub, target=self.target))
+        self.update_window()
+        if "psf_mode" in state:
+            self.psf_mode = state["psf_mode"]
+        return state
+
     @torch.no_grad()
     def initialize(self, target=None, parameters=None, **kwargs):
         """Initialise the sub-models in order, each on what the earlier ones leave of the target
@@ -1079,8 +1201,3 @@ class Group_Model(AstroPhot_Model):
 
     def __iter__(self):
         return iter(self.models.values())
-
-    def get_state(self, *args, **kwargs):
-        state = super().get_state()
-        state["models"] = {m.name: m.get_state() for m in self.models.values()}
-        return state

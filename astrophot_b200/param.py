@@ -101,12 +101,25 @@ class Node:
             state["nodes"] = [n.get_state() for n in self.nodes.values()]
         return state
 
+    _loading = None      # identity -> node built so far by the set_state call in progress
+
     def set_state(self, state):
-        self.name = state["name"]
-        self._identity = state["identity"]
-        for sub in state.get("nodes", ()):
-            self.link(self.__class__(name=sub["name"], state=sub))
-        self.locked = state.get("locked", False)
+        """(A node that hangs under several parents appears once per parent in the state, with one identity: it is
+        rebuilt once and linked to all of them, so shared parameters stay shared.)"""
+        root = Node._loading is None
+        if root:
+            Node._loading = {}
+        try:
+            self.name = state["name"]
+            self._identity = state["identity"]
+            Node._loading[state["identity"]] = self
+            for sub in state.get("nodes", ()):
+                known = Node._loading.get(sub["identity"])
+                self.link(known if known is not None else self.__class__(name=sub["name"], state=sub))
+            self.locked = state.get("locked", False)
+        finally:
+            if root:
+                Node._loading = None
 
     @property
     def leaf(self):
@@ -475,11 +488,37 @@ class Parameter_Node(Node):
         self.cyclic = state.get("cyclic", False)
         if "shape" in state and "value" in state and not isinstance(state["value"], str):
             self.shape = state["shape"]
-        if not isinstance(state.get("value"), str):        # (pointer / function nodes are re-linked by their owner)
+        if isinstance(state.get("value"), str):            # pointer / function place-holder: see relink()
+            self._value = state["value"]
+        else:
             self.value = state.get("value", None)
         self.uncertainty = state.get("uncertainty", None)
         self.prof = state.get("prof", None)
         self.locked = hold
+
+    def relink(self):
+        """After ``set_state`` on the root of a graph: turn the ``NODE:<identity>`` place-holders of pointer nodes back
+        into pointers (identities travel with the state).  The reference saves these place-holders but never resolves
+        them; here a saved joint fit keeps its shared parameters."""
+        seen = {}
+
+        def walk(n):
+            if n.identity in seen:
+                return
+            seen[n.identity] = n
+            for c in n.nodes.values():
+                walk(c)
+
+        walk(self)
+        by_id = {str(k): v for k, v in seen.items()}
+        for n in seen.values():
+            v = getattr(n, "_value", None)
+            if isinstance(v, str) and v.startswith("NODE:") and v[5:] in by_id:
+                hold, n.locked = n.locked, False
+                n._value = None
+                n.value = by_id[v[5:]]
+                n.locked = hold
+        return self
 
     def get_state(self):
         state = Node.get_state(self)

@@ -294,3 +294,35 @@ def test_parameter_report_and_state_round_trip():
     assert str(g2["a"]) == str(a) and str(g2["b"]) == str(b) and g2["b"].locked and g2["a"].identity == a.identity
     np.testing.assert_array_equal(g2["b"].prof.numpy(), [0.0, 1.0])
     assert g.get_state()["nodes"][2]["value"] == f"NODE:{a.identity}"
+
+
+@pytest.mark.parametrize("name,ext", [("psf_sersic", ".yaml"), ("group", ".yaml"), ("aux_psf_moffat", ".json"), ("joint", ".yaml"),
+                                      ("crowded", ".json"), ("spline", ".yaml"), ("masked_locked_edge", ".yaml"),
+                                      ("point_psf_model_group", ".yaml"), ("moffat_psf_model", ".yaml")])
+def test_model_save_load_round_trip(tmp_path, name, ext):
+    """model.save() / AstroPhot_Model(filename=...) (reference: `core_model.py:374-451`, `_model_methods.py:437-482`,
+    `group_model_object.py:325-365`): the reloaded model lowers to the very same scene tables -- windows, knobs, PSFs,
+    parameter order, limits, locks -- and parameters shared between sub-models (joint fits, one PSF model for several
+    stars) are still shared afterwards."""
+    import scenes
+    from astrophot_b200.lowering import lower
+    ap.AP_config.ap_device = "cpu"
+    model, _ = scenes.build(ap, name)
+    path = str(tmp_path / f"saved{ext}")
+    model.save(path)
+    again = ap.models.AstroPhot_Model(name=f"again {name}", filename=path, target=model.target)
+    assert type(again) is type(model) and again.name == f"again {name}"
+    a, b = lower(model)[0], lower(again)[0]
+    assert len(a.sources) == len(b.sources) and len(a.psfs) == len(b.psfs)
+    for x, y in zip(a.sources, b.sources):
+        assert {k: v for k, v in x.__dict__.items() if k != "name"} == {k: v for k, v in y.__dict__.items() if k != "name"}
+    np.testing.assert_array_equal(a.transform, b.transform)
+    np.testing.assert_array_equal(a.lo, b.lo)
+    np.testing.assert_array_equal(a.hi, b.hi)
+    moved = model.parameters.vector_values() * 1.01
+    model.parameters.vector_set_values(moved)
+    again.parameters.vector_set_values(moved)
+    for x, y in zip(lower(model)[0].sources, lower(again)[0].sources):
+        assert x.cval == y.cval
+    with pytest.raises(ValueError):
+        model.save(str(tmp_path / "saved.hdf5"))

@@ -30,9 +30,6 @@ EXPECTED_FAILURES = {
     "test_image.py::TestImage::test_image_errors": "Image.expand",
     "test_image.py::TestModelImage::test_shift": "Model_Image.shift_origin",
     "test_image.py::TestImage::test_image_manipulation": "4-element crop convention",
-    # model save / load: out of scope
-    "test_model.py::TestSersic::test_sersic_save_load": "save / load",
-    "test_group_models.py::TestGroup::test_groupmodel_saveload": "save / load",
     "test_group_models.py::TestPSFGroup::test_psfgroupmodel_saveload": "psf group model",
     # CPU torch convolution / interpolation helpers: deliberately absent (convolution lives on the device only),
     # star-stacking PSF construction, hdf5
@@ -64,7 +61,7 @@ EXPECTED_FAILURES = {
 def test_reference_test_files_against_this_package():
     out = subprocess.run(["bash", os.path.join(ROOT, "oracle", "run_reference_tests.sh")], capture_output=True, text=True,
                          timeout=900).stdout
-    passed = set(re.findall(r"^PASSED (\S+)", out, flags=re.M))
-    failed = set(re.findall(r"^(?:FAILED|ERROR) (\S+)", out, flags=re.M))
+    passed = {t.rsplit("/", 1)[-1] for t in re.findall(r"^PASSED (\S+)", out, flags=re.M)}
+    failed = {t.rsplit("/", 1)[-1] for t in re.findall(r"^(?:FAILED|ERROR) (\S+)", out, flags=re.M)}
     assert failed == set(EXPECTED_FAILURES), (sorted(failed - set(EXPECTED_FAILURES)), sorted(set(EXPECTED_FAILURES) - failed))
-    assert len(passed) >= 75, out[-2000:]
+    assert len(passed) >= 77, out[-2000:]
