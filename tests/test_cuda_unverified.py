@@ -49,3 +49,9 @@ def test_integration_variants_agree(name):
 def test_total_flux_and_its_uncertainty(scene_name):
     from test_lm_host_logic import check_flux_uncertainties
     check_flux_uncertainties(scene_name)
+
+
+def test_getting_started_flow_on_the_device(tmp_path):
+    """The tutorial flow end to end on the GPU: host start values (initialize, variance="auto") into the device LM."""
+    from test_tutorial_flow import getting_started_flow
+    getting_started_flow(tmp_path)
