@@ -994,7 +994,7 @@ class Moffat2D_PSF(PSF_Model):
         "Rd": {"units": "arcsec", "limits": (0, None)},
         "I0": {"units": "log10(flux/arcsec^2)", "value": 0.0, "locked": True},
     }
-    _parameter_order = PSF_Model._parameter_order + ("q", "PA", "n", "Rd", "I0")
+    _parameter_order = PSF_Model._parameter_order + ("n", "Rd", "I0", "q", "PA")   # (moffat_model.py:134: q, PA come last)
     usable = True
     _init_family = "moffat"
     _kind = sc.KIND_MOFFAT

@@ -326,3 +326,27 @@ def test_model_save_load_round_trip(tmp_path, name, ext):
         assert x.cval == y.cval
     with pytest.raises(ValueError):
         model.save(str(tmp_path / "saved.hdf5"))
+
+
+def test_parameter_order_of_every_model_family():
+    """The column order of the Jacobian is the models' ``parameter_order`` (reference: each model's ``_parameter_order``;
+    the moffat2d psf model appends q, PA after the Moffat parameters, `moffat_model.py:134`)."""
+    want = {
+        "sersic galaxy model": ("center", "q", "PA", "n", "Re", "Ie"),
+        "exponential galaxy model": ("center", "q", "PA", "Re", "Ie"),
+        "gaussian galaxy model": ("center", "q", "PA", "sigma", "flux"),
+        "moffat galaxy model": ("center", "q", "PA", "n", "Rd", "I0"),
+        "spline galaxy model": ("center", "q", "PA", "I(R)"),
+        "point model": ("center", "flux"),
+        "flat sky model": ("center", "F"),
+        "plane sky model": ("center", "F", "delta"),
+        "sersic psf model": ("center", "n", "Re", "Ie"),
+        "exponential psf model": ("center", "Re", "Ie"),
+        "gaussian psf model": ("center", "sigma", "flux"),
+        "moffat psf model": ("center", "n", "Rd", "I0"),
+        "moffat2d psf model": ("center", "n", "Rd", "I0", "q", "PA"),
+        "spline psf model": ("center", "I(R)"),
+    }
+    have = {m.model_type: tuple(m._parameter_order) for m in ap.models.AstroPhot_Model.List_Models(usable=True)
+            if m.model_type != "group model"}
+    assert have == want
