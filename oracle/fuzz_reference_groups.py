@@ -1,7 +1,9 @@
 """Random GROUP scenes -- 2-4 galaxies of mixed families on their own windows (some sticking out of the image), point
 sources, a flat or plane sky, a PSF image, random sampling / integration knobs per model -- sampled and differentiated
-by the REFERENCE and by the oracle (through astrophot_b200.lowering).  Build container only.
-python oracle/fuzz_reference_groups.py         Recorded: 16 scenes, worst relative difference 2.5e-14 (images and Jacobians)."""
+by the REFERENCE and by the oracle (through astrophot_b200.lowering); the first 8 are also fitted for three LM iterations on
+noisy data with a masked block.  Build container only.
+python oracle/fuzz_reference_groups.py         Recorded: 16 scenes, worst relative difference 2.5e-14 (images and Jacobians); LM on 8 of them: chi^2 per iteration
+<= 1.7e-14, state <= 6e-12, damping history identical."""
 import os, sys
 HERE = os.path.dirname(os.path.abspath(__file__)); sys.path[:0] = [HERE, os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "tests")]
 from make_golden import import_reference, _datas
@@ -40,10 +42,14 @@ for k in range(16):
                       {"center": [float(cx * ps), float(cy * ps)], "flux": float(rng.uniform(0.5, 2))}, {}))
     sky_plane = bool(rng.integers(0, 2))
 
-    def build(ap):
+    def build(ap, dat=None, var=None, mask=None):
         psf = ap.image.PSF_Image(data=scenes._psf_moffat(2.5, 1.2 + 0.1 * pw, pw), pixelscale=ps)
-        tar = ap.image.Target_Image(data=np.zeros((H, W)), pixelscale=ps, zeropoint=22.5, psf=psf)
-        models = [ap.models.AstroPhot_Model(name=f"g{k}m{i}", model_type=mt, target=tar, window=win, parameters=dict(pars), **kw)
+        extra = {} if dat is None else {"variance": var, "mask": mask}
+        tar = ap.image.Target_Image(data=np.zeros((H, W)) if dat is None else dat, pixelscale=ps, zeropoint=22.5, psf=psf, **extra)
+        def inside(win):     # (for the LM phase: the reference's fit_mask cannot handle windows that stick out)
+            return [[max(0, win[0][0]), min(W, win[0][1])], [max(0, win[1][0]), min(H, win[1][1])]]
+        models = [ap.models.AstroPhot_Model(name=f"g{k}m{i}", model_type=mt, target=tar, window=win if dat is None else inside(win),
+                                            parameters=dict(pars), **kw)
                   for i, (mt, win, pars, kw) in enumerate(specs)]
         if sky_plane:
             sky = ap.models.AstroPhot_Model(name=f"g{k}sky", model_type="plane sky model", target=tar,
@@ -71,4 +77,26 @@ for k in range(16):
     print(f"{k:2d} {W}x{H} ps={ps} psf={pw} group_psf={int(group_psf)} models={len(specs)} plane={int(sky_plane)} P={len(xo)} img {e:.1e} jac {ej:.1e}{flag}", flush=True)
     if flag:
         for mt, win, pars, kw in specs: print("     ", mt, win, kw)
+    if k < 8:
+        # three LM iterations on noisy data with a masked block: chi^2 / lambda histories (fit/lm.py:248-357)
+        noisy = scenes.make_data([a], 4000 + k)[0]
+        mask = np.zeros(a.shape, dtype=bool)
+        mask[10:18, 20:33] = True
+        mr2, mo2 = build(ref, noisy["data"], noisy["variance"], mask), build(ours, noisy["data"], noisy["variance"], mask)
+        x0 = scenes.perturb(mr2.parameters.vector_representation().detach().cpu().numpy(), k, scale=0.02)
+        try:
+            res = ref.fit.LM(mr2, initial_state=x0, max_iter=3, relative_tolerance=0.0, verbose=0).fit()
+        except RuntimeError:
+            # the reference's Group_Model.fit_mask mis-sizes model windows that stick out of the image
+            print("      LM: the reference cannot fit this scene (a window sticks out of the image)", flush=True)
+            continue
+        scene2, _ = lower(mo2, for_fit=True)
+        mine = orc.lm_fit(scene2, x0, max_iter=3, relative_tolerance=0.0)
+        n = min(len(res.loss_history), len(mine["loss_history"]))
+        el = np.max(np.abs(np.array(res.loss_history[:n]) - np.array(mine["loss_history"][:n])) / np.array(res.loss_history[:n]))
+        same_L = list(np.array(res.L_history[:n])) == list(np.array(mine["L_history"][:n]))
+        ex = np.max(np.abs(np.array(res.lambda_history[n - 1]) - np.array(mine["lambda_history"][n - 1])))
+        worst = max(worst, el)
+        print(f"      LM {n} iterations: chi2 {el:.1e}  state {ex:.1e}  L equal {same_L}  {np.array(res.loss_history[:n]).round(4)}"
+              + ("" if el < 1e-8 and same_L else "   <-- CHECK"), flush=True)
 print("worst", worst)
