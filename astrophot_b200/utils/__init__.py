@@ -21,15 +21,15 @@ def _bin(z, img_width, upsample):
 def gaussian_psf(sigma, img_width, pixelscale, upsample=4, normalize=True):
     """Pixel-integrated (mean of ``upsample``^2 sub-samples) circular Gaussian, normalised to unit sum by default."""
     X, Y = _grid(img_width, pixelscale, upsample)
-    z = _bin(np.exp(-0.5 * (X**2 + Y**2) / sigma**2), img_width, upsample) / upsample**2
-    return z / z.sum() if normalize else z
+    z = _bin(np.exp(-0.5 * (X**2 + Y**2) / sigma**2), img_width, upsample)
+    return z / z.sum() if normalize else z / upsample**2
 
 
 def moffat_psf(n, Rd, img_width, pixelscale, upsample=4, normalize=True):
     """Pixel-integrated circular Moffat, normalised to unit sum by default."""
     X, Y = _grid(img_width, pixelscale, upsample)
-    z = _bin(1.0 / (1.0 + (X**2 + Y**2) / Rd**2) ** n, img_width, upsample) / upsample**2
-    return z / z.sum() if normalize else z
+    z = _bin(1.0 / (1.0 + (X**2 + Y**2) / Rd**2) ** n, img_width, upsample)
+    return z / z.sum() if normalize else z / upsample**2
 
 
 from . import angle_operations, conversions, initialize, optimization, parametric_profiles  # noqa: E402  (ap.utils.<module>.*, as in the reference)
