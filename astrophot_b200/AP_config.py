@@ -12,10 +12,6 @@ __all__ = ["ap_dtype", "ap_device", "ap_verbose", "ap_logger", "set_logging_outp
 ap_dtype = torch.float64
 ap_device = "cuda:0" if torch.cuda.is_available() else "cpu"
 ap_verbose = 0
-# Device code paths that are written and CPU-checked (oracle vs the reference) but have not yet run on a B200 (they were
-# finished after a round's GPU budget was spent) are refused unless this is set.  Default from APB_ALLOW_UNVERIFIED.
-import os as _os
-allow_unverified = _os.environ.get("APB_ALLOW_UNVERIFIED", "0") not in ("", "0")
 
 ap_logger = logging.getLogger("astrophot_b200")
 ap_logger.setLevel(logging.INFO)

@@ -325,11 +325,6 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
         lowered as a source of the PSF model's kind on the target's grid whose centre elements are the point source's
         and whose last element is the flux (FLAG_AMP)."""
         pm = comp.psf
-        if not AP_config.allow_unverified:
-            raise SpecificationConflict(
-                "point sources with a PSF *model* (point_source.py:122-140): the device path for them has not run on "
-                "hardware yet; set astrophot_b200.AP_config.allow_unverified = True to use it, or sample the PSF model "
-                "once and pass the PSF_Image")
         if not isinstance(pm, PSF_Model) or getattr(pm, "_kind", None) is None:
             raise SpecificationConflict(
                 f"PSF model type '{pm.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §8f)")

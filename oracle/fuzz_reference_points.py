@@ -12,7 +12,6 @@ ref = import_reference()
 import astrophot_b200 as ours, astrophot_oracle as orc
 from astrophot_b200.lowering import lower
 ours.AP_config.ap_device = "cpu"
-ours.AP_config.allow_unverified = True
 rng = np.random.default_rng(321)
 worst = 0
 KINDS = ["sersic", "exponential", "gaussian", "moffat", "moffat2d", "spline"]

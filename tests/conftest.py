@@ -40,13 +40,3 @@ def rel_err(a, b):
     """max |a-b| / max |b|  (image-scale relative error)."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
-
-
-@pytest.fixture(autouse=True)
-def _allow_unverified_scenes(request, monkeypatch):
-    """Scenes in scenes.UNVERIFIED_SCENES lower to device features that are refused by default (AP_config.allow_unverified)."""
-    import scenes
-    cs = getattr(request.node, "callspec", None)
-    if cs is not None and cs.params.get("name") in scenes.UNVERIFIED_SCENES:
-        import astrophot_b200 as ap
-        monkeypatch.setattr(ap.AP_config, "allow_unverified", True)

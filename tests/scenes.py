@@ -305,17 +305,14 @@ def build(ap, name, data=None):
 SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_quad5", "exponential", "gaussian",
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
-                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs"]
-# scenes checked on the CPU only (oracle vs reference): added after the round's GPU budget was spent
-CPU_ONLY_SCENES = ["group_edge", "point_psf_model", "point_psf_model_group"]
-# scenes whose device path is refused unless AP_config.allow_unverified (written after the GPU budget was spent; the
-# tests switch it on, and the GPU tests of these scenes only run with APB_ALLOW_UNVERIFIED=1)
-UNVERIFIED_SCENES = ["point_psf_model", "point_psf_model_group"]
+                 "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs",
+                 "point_psf_model", "point_psf_model_group", "group_edge"]
+CPU_ONLY_SCENES = []
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
-             "moffat_psf_model": 16}
-CPU_LM_SCENES = {"point_psf_model": 17, "point_psf_model_group": 18}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
+             "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18}
+CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
 

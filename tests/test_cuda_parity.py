@@ -107,7 +107,8 @@ def test_refinement_queue_grows_on_overflow():
     np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-8)
 
 
-@pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat_psf_model", "crowded"])
+@pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat_psf_model", "crowded", "point_psf_model",
+                                  "point_psf_model_group"])
 def test_fused_integration_equals_per_depth_launches(name):
     """k_integrate (one cooperative launch, lane-parallel Gauss-Legendre nodes) against the
     per-depth k_select / k_refine / k_reduce_level / k_scatter launches: same queues, same
@@ -129,7 +130,7 @@ def test_fused_integration_equals_per_depth_launches(name):
 
 
 @pytest.mark.parametrize("name", ["c1_sersic", "sersic_sheared", "spline", "moffat", "psf_sersic", "moffat_psf_model", "group",
-                                  "joint", "crowded", "aux_psf_moffat"])
+                                  "joint", "crowded", "aux_psf_moffat", "point_psf_model", "point_psf_model_group"])
 def test_pooled_integration_equals_lane_shared(name):
     """k_integrate_pool (throughput form for long queues: a lane per cell, children of all failing
     entries pooled over the CTA) against k_integrate: same nodes, same decisions, same counts; sums
@@ -160,9 +161,16 @@ def test_sample_vs_oracle_and_reference(name):
     plan = _plan(scene)
     got = [t.cpu().numpy() for t in plan.sample(fix["x_val"], as_rep=False)]
     want = orc.sample(scene, fix["x_val"], as_rep=False)
+    has_psf = any(s.psf >= 0 for s in scene.sources)
     for i, (g, w) in enumerate(zip(got, want)):
         assert rel_err(g, w) < 1e-10, (name, "oracle")
         assert rel_err(g, fix[f"img{i}"]) < 1e-10, (name, "reference golden")
+        if not has_psf:
+            # no convolution in between: the north star's 1e-10 holds pixel by pixel (the reference's FFT convolution
+            # has absolute, not relative, rounding noise, so PSF scenes are held to the image scale)
+            ref = fix[f"img{i}"]
+            np.testing.assert_allclose(g, ref, rtol=1e-10, atol=1e-16 * np.abs(ref).max(), err_msg=name)
+            np.testing.assert_allclose(g, w, rtol=1e-10, atol=1e-16 * np.abs(ref).max(), err_msg=name)
     # representation-space entry gives the same image
     got2 = [t.cpu().numpy() for t in plan.sample(fix["x_rep"], as_rep=True)]
     for g, g2 in zip(got, got2):
@@ -247,6 +255,42 @@ def test_lm_fit_matches_reference(name):
     assert abs(min(res.loss_history) - ref_loss.min()) / ref_loss.min() < 1e-8
     # fitted parameters were written back to the model (lm.py:491)
     np.testing.assert_allclose(model.parameters.vector_representation().numpy(), res.res(), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", list(scenes.LM_KWARGS_SCENES))
+@pytest.mark.parametrize("fused", [True, False])
+def test_lm_non_default_knobs_on_the_device(name, fused):
+    """Geodesic acceleration on and another damping schedule (fit/lm.py:281-290 with acceleration != 0: the trial's
+    chi^2 is taken at x + h + acceleration * a, so the concurrent chi^2 pass of apb_lm_trial is off and the second
+    solve feeds the forward pass), through apb_lm_trial and through the separate calls, against the reference's fit
+    with the same knobs."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name, data=golden_data(fix))
+    res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=6, relative_tolerance=0.0, fused_trial=fused,
+                    **scenes.LM_KWARGS).fit()
+    ref_loss = fix["kw_loss_history"]
+    n = min(len(ref_loss), len(res.loss_history))
+    moving = 1
+    while moving < n and abs(ref_loss[moving] - ref_loss[moving - 1]) / ref_loss[moving] > 1e-9:
+        moving += 1
+    assert moving >= 3
+    np.testing.assert_allclose(res.loss_history[:moving], ref_loss[:moving], rtol=1e-8)
+    np.testing.assert_allclose(res.L_history[:moving - 1], fix["kw_L_history"][:moving - 1], rtol=1e-12)
+    for k in range(moving):
+        np.testing.assert_allclose(res.lambda_history[k], fix["kw_lambda_history"][k], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize("scene_name", scenes.FLUX_SCENES)
+def test_total_flux_and_its_uncertainty(scene_name):
+    """core_model.py:265-290 on the device: total_flux / total_flux_uncertainty / total_magnitude(_uncertainty)."""
+    from test_lm_host_logic import check_flux_uncertainties
+    check_flux_uncertainties(scene_name)
+
+
+def test_getting_started_flow_on_the_device(tmp_path):
+    """The tutorial flow end to end on the GPU: host start values (initialize, variance="auto") into the device LM."""
+    from test_tutorial_flow import getting_started_flow
+    getting_started_flow(tmp_path)
 
 
 @pytest.mark.parametrize("name", ["psf_sersic", "group"])

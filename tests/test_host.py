@@ -163,11 +163,6 @@ def test_point_source_from_a_psf_model_lowers_to_an_amplitude_source(monkeypatch
     import scenes
     ap.AP_config.ap_device = "cpu"
     model, _ = scenes.build(ap, "point_psf_model_group")
-    # refused by default: the device path has not run on hardware yet
-    monkeypatch.setattr(ap.AP_config, "allow_unverified", False)
-    with pytest.raises(ap.errors.SpecificationConflict, match="allow_unverified"):
-        lower(model)
-    monkeypatch.setattr(ap.AP_config, "allow_unverified", True)
     scene, _ = lower(model)
     assert not scene.psfs and all(s.psf < 0 for s in scene.sources)         # no stamp, no shift, no convolution
     a, b, c = scene.sources[:3]
