@@ -58,7 +58,9 @@ class apb_opts_t(C.Structure):
 
 class apb_stats_t(C.Structure):
     _fields_ = [("first_pass_evals", C.c_int64), ("queued", C.c_int64 * (MAX_DEPTH + 1)),
-                ("launches", C.c_int64), ("overflow", C.c_int64)]
+                ("launches", C.c_int64), ("overflow", C.c_int64),
+                ("cum_passes", C.c_int64 * 2), ("cum_first_pass_evals", C.c_int64 * 2),
+                ("cum_queued", (C.c_int64 * (MAX_DEPTH + 1)) * 2)]
 
 
 class apb_kernel_time_t(C.Structure):
@@ -422,7 +424,9 @@ class Plan:
         st = apb_stats_t()
         _check(self._L.apb_plan_stats(self._h, C.byref(st)), "apb_plan_stats")
         return {"first_pass_evals": st.first_pass_evals, "queued": list(st.queued)[1:], "launches": st.launches,
-                "overflow": st.overflow}
+                "overflow": st.overflow, "cum_passes": list(st.cum_passes),
+                "cum_first_pass_evals": list(st.cum_first_pass_evals),
+                "cum_queued": [list(st.cum_queued[k])[1:] for k in range(2)]}
 
 
 def lm_solve(H, g, L, out=None, info=None):

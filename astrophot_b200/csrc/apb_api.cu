@@ -169,6 +169,7 @@ struct apb_plan {
     cudaEventRecord(prof.back().b, st);
   }
   int first_evals[2] = {0, 0};
+  long long cum_passes[2] = {0, 0}, cum_first[2] = {0, 0};
 };
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -361,6 +362,9 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       for (int i = 0; i < n; ++i) { qt.a[n][i] = x[i] / 2.0; qt.w[n][i] = w[i] / 2.0; }
     }
     PCU(cudaMemcpyToSymbol(c_quad, &qt, sizeof(qt)));
+    static ApbMathTab mt;     // exp / log tables of the profile kernels (apb_math.cuh)
+    apb_math_fill(&mt);
+    PCU(cudaMemcpyToSymbol(g_mathtab, &mt, sizeof(mt)));
   }
 
   // ---- sources
@@ -1007,6 +1011,10 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     PRC(own_alloc(p, (void**)&p->q.overflow, sizeof(int)));
     PCU(cudaMemset(p->q.overflow, 0, sizeof(int)));
     PCU(cudaMemset(p->q.count, 0, sizeof(int) * (APB_MAX_DEPTH + 2)));
+    PRC(own_alloc(p, (void**)&p->q.cum, sizeof(unsigned long long) * 2 * (APB_MAX_DEPTH + 2)));
+    PRC(own_alloc(p, (void**)&p->q.last_kind, sizeof(int)));
+    PCU(cudaMemset(p->q.cum, 0, sizeof(unsigned long long) * 2 * (APB_MAX_DEPTH + 2)));
+    PCU(cudaMemset(p->q.last_kind, 0, sizeof(int)));
     p->q.NVp = 1;
     if (p->any_threshold) {
       long long caps[APB_MAX_DEPTH + 1] = {0};
@@ -1086,8 +1094,11 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   if (n_src == 0) return 0;
   ModeTables& T = p->mt[mode];
   PB(K_PREP);
-  k_prep<<<ceil_div(n_src, 4), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad);
+  k_prep<<<ceil_div(n_src, 4), 128, 0, st>>>(p->d_src, p->d_dyn, n_src, p->d_par, x, as_rep, p->q.count, p->d_skyJ, grad,
+                                             p->q.cum, p->q.last_kind);
   LAUNCH_CHECK();
+  p->cum_passes[grad ? 1 : 0]++;
+  p->cum_first[grad ? 1 : 0] += p->first_evals[mode];
   // PSF branch on the side stream: shifted stamps and (FFT sources) their spectra depend only on
   // k_prep, so they overlap the first pass and the adaptive integration of the profiles
   const FftTables& F = p->ft[grad];
@@ -1550,6 +1561,16 @@ extern "C" int apb_plan_stats(apb_plan_t* p, apb_stats_t* out) {
   for (int d = 1; d <= APB_MAX_DEPTH; ++d) out->queued[d] = (d >= 2 && p->use_coop) ? (long long)(unsigned int)cnt[d] : cnt[d];
   out->launches = p->stats.launches;
   out->overflow = ovf;
+  unsigned long long cum[2][APB_MAX_DEPTH + 2];
+  int last = 0;
+  CU(cudaMemcpy(cum, p->q.cum, sizeof(cum), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&last, p->q.last_kind, sizeof(int), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 2; ++k) {
+    out->cum_passes[k] = p->cum_passes[k];
+    out->cum_first_pass_evals[k] = p->cum_first[k];
+    for (int d = 1; d <= APB_MAX_DEPTH; ++d)
+      out->cum_queued[k][d] = (long long)cum[k][d] + (last == k ? (long long)(unsigned int)cnt[d] : 0);
+  }
   return 0;
 }
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "../../include/astrophot_b200.h"
+#include "apb_math.cuh"
 
 #define APB_LN10 2.302585092994045684
 #define APB_PI 3.141592653589793238
@@ -110,72 +111,109 @@ __device__ __forceinline__ double sersic_db(double n) {
   return 2 - i2 * (4.0 / 405 + i * (92.0 / 25515 + i * (393.0 / 1148175 - i * (4 * 2194697.0 / 30690717750.0))));
 }
 
-// Evaluate brightness I at plane offset (X, Y) from the centre, scaled by `ascale`
-// (sub-pixel area factor), and optionally dI/d(element) for every element.
-// NE = compile-time element bound for the kind.  dI must hold n_elem doubles.
+// Per-source values of a profile evaluation, held in registers while a thread works on one source (the kernels used to
+// re-read them from the DevSrc / DevDyn tables at every node: a third of the instructions of an evaluation).
+struct PCtx {
+  double c, s, qinv, soft2;   // rotation by -(PA - pi/2), 1/q, softening^2
+  double k0;                  // amplitude constant times the sub-pixel area factor of the cell being integrated
+  double k1, k2, k3, k4, k5, k6;
+  double q;                   // axis ratio (d/dPA)
+  int radial;
+};
+__device__ __forceinline__ void pctx_load(PCtx& c, const DevSrc& s, const DevDyn& d, double ascale) {
+  c.c = d.c; c.s = d.s; c.qinv = d.qinv; c.soft2 = s.soft2;
+  c.k0 = ascale * d.k[0];
+  c.k1 = d.k[1]; c.k2 = d.k[2]; c.k3 = d.k[3]; c.k4 = d.k[4]; c.k5 = d.k[5]; c.k6 = d.k[6];
+  c.q = d.el[2];
+  c.radial = s.flags & APB_F_RADIAL;
+}
+
+// softened squared radius: ONE expression for every kernel, so that all of them see the same bits
+__device__ __forceinline__ double r2_of(double xp, double yp, double soft2) { return fma(xp, xp, fma(yp, yp, soft2)); }
+
+// rotated, axis-ratio-scaled offsets (_shared_methods.py:274-307, coordinates.py:5-13).  PSF models are circular: k_prep
+// gives them c = 1, s = 0, 1/q = 1, for which these products are exact.
+__device__ __forceinline__ void rot_coords(const PCtx& c, double X, double Y, double& xp, double& yp) {
+  xp = c.c * X - c.s * Y;
+  yp = (c.s * X + c.c * Y) * c.qinv;
+}
+
+// Value of an analytic profile at squared radius R2 WITHOUT range checks in exp / log: `bad` is raised instead when an
+// argument leaves their fast range (then the value is garbage and the caller redoes it with eval_rot).  Three of these
+// run side by side per thread in the integration kernels; one predicate and one branch serve all of them.
+template <int KIND>
+__device__ __forceinline__ double prof_fast(const PCtx& c, double R2, bool& bad) {
+  if (KIND == APB_SERSIC) {
+    const double z = R2 * c.k1;
+    const double L2 = apb_log_nc(z, s_mathtab);
+    const double t = L2 * c.k2;
+    const double u = apb_exp_nc(t, s_mathtab);
+    const double v = fma(-c.k3, u, c.k3);
+    bad = bad || apb_log_bad(z) || apb_exp_bad(t) || apb_exp_bad(v);
+    return c.k0 * apb_exp_nc(v, s_mathtab);
+  } else if (KIND == APB_EXPONENTIAL) {
+    const double R = sqrt(R2);
+    const double v = -c.k2 * (R * c.k1 - 1.0);
+    bad = bad || apb_exp_bad(v);
+    return c.k0 * apb_exp_nc(v, s_mathtab);
+  } else if (KIND == APB_GAUSSIAN) {
+    const double v = -0.5 * R2 * c.k1;
+    bad = bad || apb_exp_bad(v);
+    return c.k0 * apb_exp_nc(v, s_mathtab);
+  } else {   // APB_MOFFAT
+    const double t = 1.0 + R2 * c.k1;
+    const double lt = apb_log_nc(t, s_mathtab);
+    const double v = -c.k2 * lt;
+    bad = bad || apb_log_bad(t) || apb_exp_bad(v);
+    return c.k0 * apb_exp_nc(v, s_mathtab);
+  }
+}
+
+// Brightness at rotated offsets (xp, yp) -- c.k0 carries the sub-pixel area factor -- and optionally dI/d(element) for
+// every element (natural units).  dI must hold the kind's element count.
 template <int KIND, bool GRAD>
-__device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, double X, double Y, double ascale,
-                                             double* __restrict__ dI) {
-  if (KIND == APB_PLANE_SKY) {
-    // planesky_model.py:65-74:  pixel_area F + X dx + Y dy  (natural flux units; only ever sampled at pixel centres)
-    if (GRAD) {
-      dI[0] = -d.el[3] * ascale;
-      dI[1] = -d.el[4] * ascale;
-      dI[2] = s.area * ascale;
-      dI[3] = X * ascale;
-      dI[4] = Y * ascale;
-    }
-    return ascale * (s.area * d.el[2] + X * d.el[3] + Y * d.el[4]);
-  }
-  double xp, yp;
-  const bool radial = (s.flags & APB_F_RADIAL) != 0;
-  if (radial) {
-    xp = X;
-    yp = Y;
-  } else {
-    xp = d.c * X - d.s * Y;
-    yp = (d.s * X + d.c * Y) * d.qinv;
-  }
-  const double R2 = xp * xp + yp * yp + s.soft2;
+__device__ __forceinline__ double eval_rot(const PCtx& c, const DevSrc& s, const DevDyn& d, double xp, double yp,
+                                           double* __restrict__ dI) {
+  const double R2 = r2_of(xp, yp, c.soft2);
   double I, dIdR_over_R;  // (dI/dR)/R : multiply by xp, yp pieces to get dI/dX
   if (KIND == APB_SERSIC) {
     // k0 = area*10^Ie, k1 = 1/Re^2, k2 = 1/(2n), k3 = b_n, k4 = b'_n, k5 = 1/n, k6 = 1/Re
-    const double L2 = log(R2 * d.k[1]);  // 2 ln(R/Re)
-    const double u = exp(L2 * d.k[2]);
-    I = ascale * d.k[0] * exp(-d.k[3] * (u - 1.0));
+    const double L2 = apb_log(R2 * c.k1, s_mathtab);  // 2 ln(R/Re)
+    const double u = apb_exp(L2 * c.k2, s_mathtab);
+    I = c.k0 * apb_exp(fma(-c.k3, u, c.k3), s_mathtab);
     if (GRAD) {
-      const double bu = d.k[3] * u;
-      dIdR_over_R = -I * bu * d.k[5] / R2;
-      dI[4] = I * (-d.k[4] * (u - 1.0) + bu * (0.5 * L2) * d.k[5] * d.k[5]);
-      dI[5] = I * bu * d.k[5] * d.k[6];
+      const double bu = c.k3 * u;
+      dIdR_over_R = -I * bu * c.k5 * apb_rcp(R2);
+      dI[4] = I * (-c.k4 * (u - 1.0) + bu * (0.5 * L2) * c.k5 * c.k5);
+      dI[5] = I * bu * c.k5 * c.k6;
       dI[6] = APB_LN10 * I;
     }
   } else if (KIND == APB_EXPONENTIAL) {
     // k0 = area*10^Ie, k1 = 1/Re, k2 = b_1
     const double R = sqrt(R2);
-    I = ascale * d.k[0] * exp(-d.k[2] * (R * d.k[1] - 1.0));
+    I = c.k0 * apb_exp(-c.k2 * (R * c.k1 - 1.0), s_mathtab);
     if (GRAD) {
-      dIdR_over_R = -I * d.k[2] * d.k[1] / R;
-      dI[4] = I * d.k[2] * R * d.k[1] * d.k[1];
+      dIdR_over_R = -I * c.k2 * c.k1 / R;
+      dI[4] = I * c.k2 * R * c.k1 * c.k1;
       dI[5] = APB_LN10 * I;
     }
   } else if (KIND == APB_GAUSSIAN) {
     // k0 = area*10^flux/sqrt(2 pi sigma^2), k1 = 1/sigma^2, k2 = 1/sigma
-    I = ascale * d.k[0] * exp(-0.5 * R2 * d.k[1]);
+    I = c.k0 * apb_exp(-0.5 * R2 * c.k1, s_mathtab);
     if (GRAD) {
-      dIdR_over_R = -I * d.k[1];
-      dI[4] = I * (-d.k[2] + R2 * d.k[1] * d.k[2]);
+      dIdR_over_R = -I * c.k1;
+      dI[4] = I * (-c.k2 + R2 * c.k1 * c.k2);
       dI[5] = APB_LN10 * I;
     }
   } else if (KIND == APB_MOFFAT) {
     // k0 = area*10^I0, k1 = 1/Rd^2, k2 = n, k3 = 1/Rd
-    const double t = 1.0 + R2 * d.k[1];
-    const double lt = log(t);
-    I = ascale * d.k[0] * exp(-d.k[2] * lt);
+    const double t = 1.0 + R2 * c.k1;
+    const double lt = apb_log(t, s_mathtab);
+    I = c.k0 * apb_exp(-c.k2 * lt, s_mathtab);
     if (GRAD) {
-      dIdR_over_R = -I * d.k[2] * 2.0 * d.k[1] / t;
+      dIdR_over_R = -I * c.k2 * 2.0 * c.k1 / t;
       dI[4] = -I * lt;
-      dI[5] = I * d.k[2] * 2.0 * R2 * d.k[1] * d.k[3] / t;
+      dI[5] = I * c.k2 * 2.0 * R2 * c.k1 * c.k3 / t;
       dI[6] = APB_LN10 * I;
     }
   } else {  // APB_SPLINE: k0 = area
@@ -194,7 +232,7 @@ __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, d
       const double f = (R - s.prof[K - 2]) / h;
       sv = v[K - 2] + (R - s.prof[K - 2]) * ((v[K - 1] - v[K - 2]) / h);
       dsdR = (v[K - 1] - v[K - 2]) / h;
-      I = ascale * d.k[0] * exp(APB_LN10 * sv);
+      I = c.k0 * apb_exp(APB_LN10 * sv, s_mathtab);
       if (GRAD) {
         dI[4 + K - 2] = APB_LN10 * I * (1.0 - f);
         dI[4 + K - 1] = APB_LN10 * I * f;
@@ -207,7 +245,7 @@ __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, d
       const double t2 = t * t, t3 = t2 * t;
       const double h00 = 1 - 3 * t2 + 2 * t3, h10 = t - 2 * t2 + t3, h01 = 3 * t2 - 2 * t3, h11 = t3 - t2;
       sv = h00 * v[i0] + h10 * d.spl_m[i0] * dx + h01 * v[i1] + h11 * d.spl_m[i1] * dx;
-      I = ascale * d.k[0] * exp(APB_LN10 * sv);
+      I = c.k0 * apb_exp(APB_LN10 * sv, s_mathtab);
       if (GRAD) {
         dsdR = ((-6 * t + 6 * t2) * v[i0] + (1 - 4 * t + 3 * t2) * d.spl_m[i0] * dx + (6 * t - 6 * t2) * v[i1] +
                 (-2 * t + 3 * t2) * d.spl_m[i1] * dx) / dx;
@@ -242,19 +280,44 @@ __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, d
   }
   if (GRAD) {
     // dR/dX * R = xp*c + yp*s/q ; dR/dY * R = -xp*s + yp*c/q
-    if (radial) {
+    if (c.radial) {
       dI[0] = -dIdR_over_R * xp;
       dI[1] = -dIdR_over_R * yp;
       dI[2] = 0.0;
       dI[3] = 0.0;
     } else {
-      dI[0] = -dIdR_over_R * (xp * d.c + yp * d.s * d.qinv);
-      dI[1] = -dIdR_over_R * (-xp * d.s + yp * d.c * d.qinv);
-      dI[2] = dIdR_over_R * (-(yp * yp) * d.qinv);
-      dI[3] = dIdR_over_R * (xp * yp * (d.el[2] - d.qinv));
+      dI[0] = -dIdR_over_R * (xp * c.c + yp * c.s * c.qinv);
+      dI[1] = -dIdR_over_R * (-xp * c.s + yp * c.c * c.qinv);
+      dI[2] = dIdR_over_R * (-(yp * yp) * c.qinv);
+      dI[3] = dIdR_over_R * (xp * yp * (c.q - c.qinv));
     }
   }
   return I;
+}
+
+// Evaluate brightness I at plane offset (X, Y) from the centre, scaled by `ascale`
+// (sub-pixel area factor), and optionally dI/d(element) for every element.
+// NE = compile-time element bound for the kind.  dI must hold n_elem doubles.
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, double X, double Y, double ascale,
+                                             double* __restrict__ dI) {
+  if constexpr (KIND == APB_PLANE_SKY) {
+    // planesky_model.py:65-74:  pixel_area F + X dx + Y dy  (natural flux units; only ever sampled at pixel centres)
+    if (GRAD) {
+      dI[0] = -d.el[3] * ascale;
+      dI[1] = -d.el[4] * ascale;
+      dI[2] = s.area * ascale;
+      dI[3] = X * ascale;
+      dI[4] = Y * ascale;
+    }
+    return ascale * (s.area * d.el[2] + X * d.el[3] + Y * d.el[4]);
+  } else {
+    PCtx c;
+    pctx_load(c, s, d, ascale);
+    double xp, yp;
+    rot_coords(c, X, Y, xp, yp);
+    return eval_rot<KIND, GRAD>(c, s, d, xp, yp, dI);
+  }
 }
 
 template <int KIND>

@@ -18,6 +18,8 @@ struct Queues {
   Level lv[APB_MAX_DEPTH + 1];  // index by depth (1-based)
   int* count;                   // [APB_MAX_DEPTH + 2] entries per depth, device
   int* overflow;                // device flag
+  unsigned long long* cum;      // [2][APB_MAX_DEPTH + 2] entries per depth summed over all earlier passes (value-only / derivative)
+  int* last_kind;               // 0 / 1: kind of the pass whose counts `count` holds
   int cap[APB_MAX_DEPTH + 2];   // entries allocated per depth
   int NVp;                      // planes carried per entry in this pass
 };
@@ -30,10 +32,20 @@ struct Queues {
 // Every sampling pass waits on this kernel, so its latency, not its throughput, is what counts.
 __global__ void __launch_bounds__(128) k_prep(const DevSrc* __restrict__ src, DevDyn* __restrict__ dyn, int n_src,
                                               const apb_param_t* __restrict__ par, const double* __restrict__ x, int as_rep,
-                                              int* qcount, double* skyJ, int write_skyJ) {
+                                              int* qcount, double* skyJ, int write_skyJ,
+                                              unsigned long long* qcum, int* qlast) {
   const int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (si == 0 && lane < APB_MAX_DEPTH + 2 && qcount) qcount[lane] = 0;
+  if (si == 0 && qcount) {
+    // the counts of the previous pass move into the running totals (apb_plan_stats), then the queues are empty again
+    const int prev = *qlast;
+    __syncwarp();
+    if (lane < APB_MAX_DEPTH + 2) {
+      qcum[prev * (APB_MAX_DEPTH + 2) + lane] += (unsigned int)qcount[lane];
+      qcount[lane] = 0;
+    }
+    if (lane == 0) *qlast = write_skyJ ? 1 : 0;
+  }
   if (si >= n_src) return;
   const DevSrc& s = src[si];
   DevDyn& d = dyn[si];
@@ -189,30 +201,98 @@ __device__ __forceinline__ void pix_coords(const DevSrc& s, const DevDyn& d, dou
   }
 }
 
-// Gauss-Legendre n x n over one (sub)pixel whose edge vectors are S*scale.
+template <bool GRAD, int NE>
+struct Acc {
+  double v[(GRAD ? NE : 0) + 1];
+};
+
+// Gauss-Legendre nodes k0, k0 + kstep, ... of the n x n rule (n = s.quad_level unless given) over the cell centred
+// (X, Y) whose edges are the pixel's times `scale`; acc.v[0] = weighted sum, acc.v[1+e] = derivative wrt element e
+// (natural units); returns the value at the centre node (0 for lanes that do not own it).
+// The rotation (_shared_methods.py:274-307) is linear, so it is applied once to the cell centre and once to the two
+// pixel edges; node (ax, ay) (pixel units) then sits at
+//     xp = fma(ax, uxi, fma(ay, uxj, xp0)),   yp = fma(ax, vyi, fma(ay, vyj, yp0))
+// -- the SAME expressions in every kernel and for every split of the nodes over lanes, so that all integration kernels
+// see bit-identical node values (their refinement decisions must agree).
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double gl_nodes_n(const DevSrc& s, const DevDyn& d, double X, double Y, int n, double scale,
+                                             double ascale, int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
+  constexpr int NE = KindInfo<KIND>::NE;
+  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
+  PCtx c;
+  pctx_load(c, s, d, ascale);
+  double xp0, yp0, uxi, vyi, uxj, vyj;
+  rot_coords(c, X, Y, xp0, yp0);
+  rot_coords(c, s.S[0] * scale, s.S[2] * scale, uxi, vyi);
+  rot_coords(c, s.S[1] * scale, s.S[3] * scale, uxj, vyj);
+  acc.v[0] = 0.0;
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) acc.v[1 + e] = 0.0;
+  double centre = 0.0;
+  const int nn = n * n, mid = nn / 2;
+  if constexpr (!GRAD && KIND != APB_SPLINE) {
+    if (n == 3 && kstep == 1) {
+      // the default 3x3 rule, all nodes on one lane: a row of three at a time with unchecked exp / log, so that three
+      // independent chains are in flight and one range test serves the row (kept rolled: three inlined evaluations
+      // are ~250 instructions; nine would crowd the other phases of the integration kernels out of the instruction cache)
+      const double a0 = c_quad.a[3][0], a2 = c_quad.a[3][2];          // a[3][1] == 0
+      const double w0 = c_quad.w[3][0], w1 = c_quad.w[3][1], w2 = c_quad.w[3][2];
+      double tot = 0.0;
+#pragma unroll 1
+      for (int ky = 0; ky < 3; ++ky) {
+        const double ay = c_quad.a[3][ky];
+        const double tx = fma(ay, uxj, xp0), ty = fma(ay, vyj, yp0);
+        const double xa = fma(a0, uxi, tx), ya = fma(a0, vyi, ty);
+        const double xb = fma(a2, uxi, tx), yb = fma(a2, vyi, ty);
+        bool bad = false;
+        double Ia = prof_fast<KIND>(c, r2_of(xa, ya, c.soft2), bad);
+        double Im = prof_fast<KIND>(c, r2_of(tx, ty, c.soft2), bad);
+        double Ib = prof_fast<KIND>(c, r2_of(xb, yb, c.soft2), bad);
+        if (bad) {   // an argument outside the fast range of exp / log (extreme or non-finite parameters)
+          Ia = eval_rot<KIND, false>(c, s, d, xa, ya, nullptr);
+          Im = eval_rot<KIND, false>(c, s, d, tx, ty, nullptr);
+          Ib = eval_rot<KIND, false>(c, s, d, xb, yb, nullptr);
+        }
+        if (ky == 1) centre = Im;
+        tot = fma(c_quad.w[3][ky], fma(w2, Ib, fma(w1, Im, w0 * Ia)), tot);
+      }
+      acc.v[0] = tot;
+      return centre;
+    }
+  }
+  double dI[GRAD ? NE : 1];
+  for (int k = k0; k < nn; k += kstep) {
+    const int kx = k % n, ky = k / n;
+    const double ax = c_quad.a[n][kx], ay = c_quad.a[n][ky];
+    const double w = c_quad.w[n][kx] * c_quad.w[n][ky];
+    const double xp = fma(ax, uxi, fma(ay, uxj, xp0)), yp = fma(ax, vyi, fma(ay, vyj, yp0));
+    const double I = eval_rot<KIND, GRAD>(c, s, d, xp, yp, dI);
+    if (k == mid) centre = I;
+    acc.v[0] += I * w;
+    if (GRAD)
+      for (int e = 0; e < ne; ++e) acc.v[1 + e] += dI[e] * w;
+  }
+  return centre;
+}
+
+template <int KIND, bool GRAD>
+__device__ __forceinline__ double gl_nodes(const DevSrc& s, const DevDyn& d, double X, double Y, double scale, double ascale,
+                                           int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
+  return gl_nodes_n<KIND, GRAD>(s, d, X, Y, s.quad_level, scale, ascale, k0, kstep, acc);
+}
+
+// Gauss-Legendre n x n over one (sub)pixel, all nodes on the calling thread.
 // acc[0] = integral, acc[1+e] = derivative wrt element e (natural units); returns the centre node.
 template <int KIND, bool GRAD>
 __device__ __forceinline__ double gl_integrate(const DevSrc& s, const DevDyn& d, double X, double Y, int n,
                                                double scale, double ascale, double* __restrict__ acc) {
   constexpr int NE = KindInfo<KIND>::NE;
-  double dI[GRAD ? NE : 1];
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
-  acc[0] = 0.0;
+  Acc<GRAD, NE> a;
+  const double centre = gl_nodes_n<KIND, GRAD>(s, d, X, Y, n, scale, ascale, 0, 1, a);
+  acc[0] = a.v[0];
   if (GRAD)
-    for (int e = 0; e < ne; ++e) acc[1 + e] = 0.0;
-  double centre = 0.0;
-  const int mid = (n * n) / 2;
-  for (int k = 0; k < n * n; ++k) {
-    const int kx = k % n, ky = k / n;
-    const double ax = c_quad.a[n][kx] * scale, ay = c_quad.a[n][ky] * scale;
-    const double w = c_quad.w[n][kx] * c_quad.w[n][ky];
-    const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ax + s.S[1] * ay), Y + (s.S[2] * ax + s.S[3] * ay),
-                                            ascale, dI);
-    if (k == mid) centre = I;
-    acc[0] += I * w;
-    if (GRAD)
-      for (int e = 0; e < ne; ++e) acc[1 + e] += dI[e] * w;
-  }
+    for (int e = 0; e < ne; ++e) acc[1 + e] = a.v[1 + e];
   return centre;
 }
 
@@ -282,6 +362,7 @@ template <bool GRAD>
 __global__ void __launch_bounds__(256) k_first(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                const int4* __restrict__ tiles, int mode, double* __restrict__ stamp,
                                                int err_plane_unused) {
+  apb_math_load();
   const int4 t = tiles[blockIdx.x];
   const DevSrc& s = src[t.x];
   const DevDyn& d = dyn[t.x];
@@ -336,6 +417,7 @@ __global__ void __launch_bounds__(256) k_mean_partial(const DevSrc* __restrict__
                                                       const int4* __restrict__ chunks, int mode,
                                                       const double* __restrict__ stamp, double* __restrict__ part) {
   __shared__ double sh[8];
+  apb_math_load();
   const int4 c = chunks[blockIdx.x];
   const DevSrc& s = src[c.x];
   const DevDyn& d = dyn[c.x];
@@ -487,6 +569,7 @@ __device__ __forceinline__ bool refine_entry(const DevSrc& s, const DevDyn& d, i
 template <bool GRAD>
 __global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                 int mode, int depth, Queues q) {
+  apb_math_load();
   const int n = min(q.count[depth], q.cap[depth]);
   const Level& L = q.lv[depth];
   const int lane = threadIdx.x & 31;
@@ -597,57 +680,6 @@ __global__ void k_scatter(const DevSrc* __restrict__ src, Queues q, double* __re
 // Queue entries are dealt round-robin to the warps of the grid so that the expensive entries, which
 // cluster at the source centre, spread over all SMs.
 // ----------------------------------------------------------------------------
-template <bool GRAD, int NE>
-struct Acc {
-  double v[(GRAD ? NE : 0) + 1];
-};
-
-template <int KIND, bool GRAD>
-__device__ __forceinline__ double gl_nodes(const DevSrc& s, const DevDyn& d, double X, double Y, double scale, double ascale,
-                                           int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
-  constexpr int NE = KindInfo<KIND>::NE;
-  const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
-  acc.v[0] = 0.0;
-  if (GRAD)
-    for (int e = 0; e < ne; ++e) acc.v[1 + e] = 0.0;
-  double centre = 0.0;
-  const int n = s.quad_level, nn = n * n, mid = nn / 2;
-  if (!GRAD && n == 3 && kstep == 1 && KIND != APB_SPLINE) {
-    // the default 3x3 rule, all nodes on one lane: a row of three nodes at a time, so that three
-    // independent log/exp chains are in flight (these launches are latency-bound, not pipe-bound)
-    for (int ky = 0; ky < 3; ++ky) {
-      double I3[3], dI3[3][GRAD ? NE : 1];
-      const double ay = c_quad.a[3][ky] * scale;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const double ax = c_quad.a[3][kx] * scale;
-        I3[kx] = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ax + s.S[1] * ay), Y + (s.S[2] * ax + s.S[3] * ay), ascale, dI3[kx]);
-      }
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const double w = c_quad.w[3][kx] * c_quad.w[3][ky];
-        if (ky == 1 && kx == 1) centre = I3[kx];
-        acc.v[0] += I3[kx] * w;
-        if (GRAD)
-          for (int e = 0; e < NE; ++e) acc.v[1 + e] += dI3[kx][e] * w;
-      }
-    }
-    return centre;
-  }
-  double dI[GRAD ? NE : 1];
-  for (int k = k0; k < nn; k += kstep) {
-    const int kx = k % n, ky = k / n;
-    const double ax = c_quad.a[n][kx] * scale, ay = c_quad.a[n][ky] * scale;
-    const double w = c_quad.w[n][kx] * c_quad.w[n][ky];
-    const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ax + s.S[1] * ay), Y + (s.S[2] * ax + s.S[3] * ay), ascale, dI);
-    if (k == mid) centre = I;
-    acc.v[0] += I * w;
-    if (GRAD)
-      for (int e = 0; e < ne; ++e) acc.v[1 + e] += dI[e] * w;
-  }
-  return centre;
-}
-
 template <int KIND, bool GRAD>
 __device__ __forceinline__ void acc_shuffle_sum(const DevSrc& s, Acc<GRAD, KindInfo<KIND>::NE>& acc, unsigned mask, int width) {
   constexpr int NE = KindInfo<KIND>::NE;
@@ -784,6 +816,7 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
                                                       double* __restrict__ stamp, Queues q, int L, int n_max) {
   const int n = min(q.count[1], q.cap[1]);
   if (n >= n_max) return;   // long queues belong to k_integrate_pool
+  apb_math_load();
   const Level& Lv = q.lv[1];
   const int lane = threadIdx.x & 31;
   const int epw = 32 / L, g = lane / L, gl = lane - g * L;
@@ -926,6 +959,7 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
   __shared__ int s_base, s_nf1, s_nf2;
   const int n = min(q.count[1], q.cap[1]);
   if (n < n_min) return;
+  apb_math_load();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int per_chunk = max(1, POOL_CSUM / (g2 * nv));   // listed entries whose children fit in csum
   for (;;) {

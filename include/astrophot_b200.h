@@ -145,6 +145,11 @@ typedef struct {
   int64_t queued[APB_MAX_DEPTH + 1];  /* entries processed per refinement depth 1..  */
   int64_t launches;                   /* kernels launched by the last call           */
   int64_t overflow;                   /* !=0: a queue overflowed, results invalid    */
+  /* totals since the plan was created; [0]: value-only sampling passes, [1]: value + derivative passes.
+     profile evaluations of a pass = first-pass evaluations + quad_level^2 x the entries of every depth */
+  int64_t cum_passes[2];
+  int64_t cum_first_pass_evals[2];
+  int64_t cum_queued[2][APB_MAX_DEPTH + 1];
 } apb_stats_t;
 
 /* Build the device tables and workspace for a lowered model tree.
