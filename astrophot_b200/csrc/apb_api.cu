@@ -463,6 +463,17 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     s.sampling_mode = a.sampling_mode; s.quad_init = a.quad_init; s.integrate_mode = a.integrate_mode;
     s.quad_level = a.quad_level; s.gridding = a.gridding; s.max_depth = a.max_depth; s.ref_mode = a.ref_mode;
     s.tol = a.tolerance; s.soft2 = a.softening * a.softening;
+    {
+      const int G = a.gridding;
+      s.gsc[0] = s.gasc[0] = s.gsc[1] = s.gasc[1] = 1.0;
+      for (int dd = 2; dd <= APB_MAX_DEPTH + 1; ++dd) {
+        s.gsc[dd] = s.gsc[dd - 1] / (double)G;
+        s.gasc[dd] = s.gasc[dd - 1] / (double)(G * G);
+      }
+      for (int k = 0; k < 16; ++k) s.goff[k] = -(G - 1) / (2.0 * G) + (double)k / G;
+      s.g2d = (double)(G * G);
+      s.gmagic = (65536 + G - 1) / G;
+    }
     s.psf = a.psf; s.psf_shift = a.psf_shift;
     for (int k = 0; k < 4; ++k) s.S[k] = im.S[k];
     const double det = im.S[0] * im.S[3] - im.S[1] * im.S[2];

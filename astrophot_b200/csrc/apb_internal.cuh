@@ -39,6 +39,13 @@ struct DevSrc {
   double prof[APB_MAX_PROF];
   int sampling_mode, quad_init, integrate_mode, quad_level, gridding, max_depth, ref_mode;
   double tol, soft2;
+  // sub-pixel re-gridding (utils/operations.py:94-102,150-247), precomputed by the host with the arithmetic the kernels
+  // used to repeat per cell (divisions: ~60 instructions each on the device):
+  //   gsc[d], gasc[d]: edge / area of a depth-d cell in pixel units (gsc[1] = 1, gsc[d+1] = gsc[d] / G, gasc[d+1] = gasc[d] / G^2)
+  //   goff[i]: offset of child column / row i of a cell, in units of the cell's edge: -(G-1)/(2G) + i/G
+  //   g2d = G^2 (the error threshold grows by it per level);  gmagic: (ch * gmagic) >> 16 == ch / G for ch < G^2
+  double gsc[APB_MAX_DEPTH + 2], gasc[APB_MAX_DEPTH + 2], goff[16], g2d;
+  int gmagic;
   int psf, psf_shift, bx, by, pw, ph;  // pw, ph: raw PSF size
   long long stamp_off;     // doubles, into the stamp arena; plane p at stamp_off + p*plane_stride
   long long plane_stride;  // >= mw*mh of both modes

@@ -359,7 +359,7 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(256) k_first(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
+__global__ void __launch_bounds__(256, GRAD ? 2 : 4) k_first(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                const int4* __restrict__ tiles, int mode, double* __restrict__ stamp,
                                                int err_plane_unused) {
   apb_math_load();
@@ -548,13 +548,9 @@ __device__ __forceinline__ bool refine_entry(const DevSrc& s, const DevDyn& d, i
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
   double acc[(GRAD ? NE : 0) + 1];
-  double scale = 1.0, ascale = 1.0, thr = d.thr[mode];
-  const double G = (double)s.gridding;
-  for (int k = 1; k < depth; ++k) {
-    scale /= G;
-    ascale /= G * G;
-    thr *= G * G;
-  }
+  const double scale = s.gsc[depth], ascale = s.gasc[depth];
+  double thr = d.thr[mode];
+  for (int k = 1; k < depth; ++k) thr *= s.g2d;
   const double centre = gl_integrate<KIND, GRAD>(s, d, X, Y, s.quad_level, scale, ascale, acc);
   if (depth < s.max_depth && fabs(acc[0] - centre) > thr) return true;
   res[0] = acc[0];
@@ -615,12 +611,11 @@ __global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, 
         L.child[t] = first;
         const Level& C = q.lv[depth + 1];
         const int G = s.gridding;
-        double scale = 1.0;
-        for (int k = 1; k < depth; ++k) scale /= (double)G;
+        const double scale = s.gsc[depth];
         for (int k = 0; k < nchild; ++k) {
           // displacement_grid: linspace(-(G-1)/(2G), (G-1)/(2G), G)  (utils/operations.py:94-102)
-          const double dx = (-(G - 1) / (2.0 * G) + (double)(k % G) / G) * scale;
-          const double dy = (-(G - 1) / (2.0 * G) + (double)(k / G) / G) * scale;
+          const double dx = s.goff[k % G] * scale;
+          const double dy = s.goff[k / G] * scale;
           const int c = first + k;
           C.src[c] = si;
           C.x[c] = X + (s.S[0] * dx + s.S[1] * dy);
@@ -700,13 +695,9 @@ __device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
   const int lane = threadIdx.x & 31;
   const int G = s.gridding, nchild = G * G, cd = depth + 1;
-  double scale = 1.0, ascale = 1.0, thr = d.thr[mode], pscale = 1.0;
-  for (int k = 1; k < cd; ++k) {
-    pscale = scale;
-    scale /= (double)G;
-    ascale /= (double)(G * G);
-    thr *= (double)(G * G);
-  }
+  const double scale = s.gsc[cd], ascale = s.gasc[cd], pscale = s.gsc[depth];
+  double thr = d.thr[mode];
+  for (int k = 1; k < cd; ++k) thr *= s.g2d;
   if (lane == 0) atomicAdd(&qcount[cd], nchild);
   out.v[0] = 0.0;
   if (GRAD)
@@ -722,8 +713,9 @@ __device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int
     bool again = false;
     if (have) {
       // displacement_grid: linspace(-(G-1)/(2G), (G-1)/(2G), G) of the parent cell (utils/operations.py:94-102)
-      const double dx = (-(G - 1) / (2.0 * G) + (double)(c % G) / G) * pscale;
-      const double dy = (-(G - 1) / (2.0 * G) + (double)(c / G) / G) * pscale;
+      const int cyi = (c * s.gmagic) >> 16, cxi = c - cyi * G;
+      const double dx = s.goff[cxi] * pscale;
+      const double dy = s.goff[cyi] * pscale;
       cx = X + (s.S[0] * dx + s.S[1] * dy);
       cy = Y + (s.S[2] * dx + s.S[3] * dy);
       const double centre = gl_nodes<KIND, GRAD>(s, d, cx, cy, scale, ascale, 0, 1, ca);
@@ -902,12 +894,9 @@ __device__ __forceinline__ bool pool_child(const DevSrc& s, const DevDyn& d, int
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
   const int G = s.gridding;
-  double scale = 1.0, ascale = 1.0, thr = d.thr[mode];
-  scale /= (double)G;
-  ascale /= (double)(G * G);
-  thr *= (double)(G * G);
-  const double dx = (-(G - 1) / (2.0 * G) + (double)(ch % G) / G);
-  const double dy = (-(G - 1) / (2.0 * G) + (double)(ch / G) / G);
+  const double scale = s.gsc[2], ascale = s.gasc[2], thr = d.thr[mode] * s.g2d;
+  const int cyi = (ch * s.gmagic) >> 16, cxi = ch - cyi * G;
+  const double dx = s.goff[cxi], dy = s.goff[cyi];
   const double cx = X + (s.S[0] * dx + s.S[1] * dy);
   const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
   Acc<GRAD, NE> ca;
@@ -924,8 +913,8 @@ __device__ __forceinline__ void pool_split_child(const DevSrc& s, const DevDyn& 
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
   const int G = s.gridding;
-  const double dx = (-(G - 1) / (2.0 * G) + (double)(ch % G) / G);
-  const double dy = (-(G - 1) / (2.0 * G) + (double)(ch / G) / G);
+  const int cyi = (ch * s.gmagic) >> 16, cxi = ch - cyi * G;
+  const double dx = s.goff[cxi], dy = s.goff[cyi];
   const double cx = X + (s.S[0] * dx + s.S[1] * dy);
   const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
   Acc<GRAD, NE> sub;
@@ -962,6 +951,7 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
   apb_math_load();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int per_chunk = max(1, POOL_CSUM / (g2 * nv));   // listed entries whose children fit in csum
+  const int step_pi = POOL_B / g2, step_ch = POOL_B - step_pi * g2;
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -1007,8 +997,9 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
       __syncthreads();
       // ---- phase 2
       int nchild_sum = 0;
-      for (int c = tid; c < nb * g2; c += POOL_B) {
-        const int pi = c / g2, ch = c - pi * g2;
+      int pi = tid / g2, ch = tid - pi * g2;          // (entry, child) of c = tid, advanced by POOL_B per trip
+      for (int c = tid; c < nb * g2; c += POOL_B, pi += step_pi, ch += step_ch) {
+        if (ch >= g2) { ch -= g2; ++pi; }
         const int e = list1[c0 + pi];
         const DevSrc& s = src[eS[e]];
         if (ch >= s.gridding * s.gridding) continue;

@@ -1,31 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the AstroPhot forward-model-and-fit hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
 
-Metric (BASELINE.json): LM iterations/s (model + PSF + J^T J), fp64.  A *step*
-is one Levenberg-Marquardt iteration (fit/lm.py:450-467): one fused
-sample+Jacobian+normal-equation build and k lambda-trials, each with a damped
-solve, a geodesic pass and a chi^2 pass.  The fit restarts from the perturbed
-start whenever it converges, so K steps are K real iterations drawn from the
-fit trajectory.
+Metric (BASELINE.json): LM iterations/s (model + PSF + J^T J), fp64.  A *step* is one Levenberg-Marquardt iteration
+(fit/lm.py:450-467): one fused sample+Jacobian+normal-equation build and k lambda-trials, each with a damped solve, a
+geodesic pass and a chi^2 pass.  Steps follow the fit trajectory from a perturbed start; the fit restarts whenever it
+has converged, so K steps are K real iterations.  The K-step block is repeated until 2 s have been timed and the median
+block is reported.
 
-Workload at N GPUs: an N-band joint fit (Target_Image_List; shared centre / q /
-PA / n / Re, per-band Ie), one band per GPU, every band being BASELINE config[1]
-— a PSF-convolved Sersic on 1024x1024 with a 51x51 Moffat PSF and threshold
-sub-pixel integration.  At N=1 that is exactly config[1].  `value` counts
-band-iterations per second (= LM iterations/s at N=1), weak scaling; the only
-collective is the all-reduce of J^T W J / J^T W r / chi^2 (P^2+P+2 doubles).
+Headline workload (default, every N): `c3` = BASELINE config[2], the crowded field the north star's 1-GPU target is
+quoted on -- 1000 PSF-convolved Sersic + 5000 point sources + sky on 4096x4096, P = 22001.  At N > 1 the image is cut
+into N tiles, one per GPU (strong scaling; `value` = LM iterations/s of the one fit); the ranks exchange the block-sparse
+J^T W J, J^T W r and chi^2 (NCCL all-reduce).  The other configurations are measured in the same run with shorter timed
+regions and attached to the line as `other_workloads`: `c4` = config[3], the 8-band joint fit on 2048^2 per band
+(8/N bands per GPU, strong scaling), `c2` = config[1] (one 1024^2 band per GPU, weak scaling) and, at N = 1, `c5s`, the
+2048^2 scale model of config[4].  `--workload X` measures X alone.
 
-Other workloads (`--workload`): `c3` = BASELINE config[2], the 4096^2 crowded field (at N GPUs the image is
-cut into N tiles, one per GPU: strong scaling, `value` = LM iterations/s of the one fit), `c3s` its 1024^2
-scale model, `c4` = config[3], the 8-band joint fit on 2048^2 per band (8 bands whatever N: strong scaling,
-8/N bands per GPU, `value` = LM iterations/s of the joint fit).
-
-`--impl reference` times the CPU oracle port of the reference algorithm
-(oracle/astrophot_oracle.py, numpy + scipy FFT convolution like the reference's
-default psf_convolve_mode) on the host cores, same config, one LM iteration
-per step.  /root/reference is not needed at run time.
+`--impl reference` times the CPU oracle port of the reference algorithm (oracle/astrophot_oracle.py, numpy + scipy FFT
+convolution like the reference's default psf_convolve_mode) on the host cores with the same iteration mix; the crowded
+field on its 512^2 scale model c3t (the dense Jacobian of c3 itself would need 2.9 TB), extrapolated linearly in the
+source count (factor 64, stated in `config`).  /root/reference is not needed at run time.
 """
 import argparse
 import json
@@ -310,21 +305,37 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # reference arm: CPU oracle port
 # ---------------------------------------------------------------------------
-def cpu_lm_iteration_seconds(scene, x0, n_iter=1):
+RESTART_TOL = 1e-9     # both arms: a fit whose chi^2 moved by less than this over two iterations is restarted
+
+
+def converged(loss):
+    return len(loss) >= 3 and abs(loss[-3] - loss[-1]) / loss[-1] < RESTART_TOL
+
+
+def cpu_lm_iterations(scene, x0, n_skip, n_timed, budget_s=None):
+    """Seconds of each of `n_timed` consecutive LM iterations of the oracle port, taken after `n_skip` untimed ones, along
+    the SAME trajectory the GPU arm walks: the fit starts from the perturbed state x0, continues iteration after
+    iteration, and starts over from x0 whenever it converges (`converged`) or cannot improve chi^2 any more."""
     import astrophot_oracle as orc
 
     orc.set_threads(os.cpu_count())      # sources / convolution planes on all host cores; BLAS threads for J^T W J
-
-    t0 = time.perf_counter()
-    res = orc.lm_fit(scene, x0, max_iter=n_iter, relative_tolerance=0.0, conv="fft")
-    dt = time.perf_counter() - t0
-    its = max(1, len(res["loss_history"]) - 1)
-    return dt / its, res
+    times, t_start, restarts = [], time.perf_counter(), 0
+    while len(times) < n_skip + n_timed:
+        res = orc.lm_fit(scene, x0, max_iter=n_skip + n_timed - len(times), relative_tolerance=0.0, conv="fft",
+                         stop=converged)
+        times += list(res["iter_seconds"])
+        if len(times) < n_skip + n_timed:
+            restarts += 1
+        if not res["iter_seconds"]:
+            break
+        if budget_s is not None and len(times) > n_skip and time.perf_counter() - t_start > budget_s:
+            break
+    return times[n_skip:n_skip + n_timed], restarts
 
 
 def cpu_scene(workload="c2"):
     """Scene tables for the CPU arm (host numpy only, no GPU needed).  The crowded field is timed on its
-    scale model c3s: the reference's (and the port's) dense Jacobian of c3 itself would need 2.9 TB."""
+    scale model c3t: the reference's (and the port's) dense Jacobian of c3 itself would need 2.9 TB."""
     import astrophot_b200 as ap
     import astrophot_oracle as orc
     from astrophot_b200.lowering import lower
@@ -350,20 +361,27 @@ def cpu_scene(workload="c2"):
 
 
 def cpu_scale(workload):
-    """(factor, note): the crowded field is timed on its 512^2 scale model c3t (same source densities; c3 is
-    64 x, c3s 4 x c3t in sources and pixels) and the CPU cost per LM iteration is taken as linear in that (it
-    is super-linear for the dense J^T W J, so this flatters the CPU); c4 is timed on one of its 8 bands."""
+    """(factor, note, scale-model description): the crowded field is timed on its 512^2 scale model c3t (same source
+    densities; c3 is 64 x, c3s 4 x c3t in sources and pixels) and the CPU cost per LM iteration is taken as linear in that
+    (it is super-linear for the dense J^T W J, so this flatters the CPU); c4 is timed on one of its 8 bands."""
     if workload in ("c3", "c3s"):
         k = 64 if workload == "c3" else 4
         return 1.0 / k, (f" on the scale model c3t (512^2, 15 Sersic + 78 points + sky, P = 340), divided by {k} "
-                         f"(linear extrapolation to {workload}: EXTRAPOLATED)")
+                         f"(linear extrapolation to {workload}: EXTRAPOLATED)"), {"scale_model": "c3t", "extrapolation_factor": k}
     if workload in ("c5", "c5s"):
         k = 1024 if workload == "c5" else 16
         return 1.0 / k, (f" on the scale model c5t (512^2, 10 galaxies + sky), divided by {k} "
-                         f"(linear extrapolation to {workload}: EXTRAPOLATED)")
+                         f"(linear extrapolation to {workload}: EXTRAPOLATED)"), {"scale_model": "c5t", "extrapolation_factor": k}
     if workload == "c4":
-        return 1.0 / C4_BANDS, f" on ONE band of the {C4_BANDS}-band joint fit (2048^2, P = 7), divided by {C4_BANDS} (EXTRAPOLATED)"
-    return 1.0, ""
+        return 1.0 / C4_BANDS, (f" on ONE band of the {C4_BANDS}-band joint fit (2048^2, P = 7), divided by {C4_BANDS} "
+                                "(EXTRAPOLATED)"), {"scale_model": "one band of c4", "extrapolation_factor": C4_BANDS}
+    return 1.0, "", {"scale_model": None, "extrapolation_factor": 1}
+
+
+def default_workload(world):
+    """The headline workload: BASELINE config[2], the 4096^2 crowded field -- the configuration the north star's 1-GPU
+    target is quoted on -- at every N (N > 1: the image cut into N tiles, strong scaling)."""
+    return "c3"
 
 
 def run_reference(args):
@@ -374,31 +392,31 @@ def run_reference(args):
 
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    scene, x0 = cpu_scene(args.workload)
-    fac, note = cpu_scale(args.workload)
-    # every step is one full LM iteration of the port from the perturbed start (seconds each): the run is bounded
-    # by a time budget, so fewer than K steps may be timed (steps_timed says how many)
-    times, budget, t_start = [], float(os.environ.get("APB_REF_BUDGET_S", "150")), time.perf_counter()
-    n_warm = min(args.warmup, 1)
-    for k in range(n_warm + args.steps):
-        dt, res = cpu_lm_iteration_seconds(scene, x0, 1)
-        if k >= n_warm:
-            times.append(dt)
-        if times and time.perf_counter() - t_start > budget:
-            break
+    wl = args.workload or default_workload(args.gpus)
+    scene, x0 = cpu_scene(wl)
+    fac, note, scale_info = cpu_scale(wl)
+    # the same iteration mix as the GPU arm: W untimed iterations from the perturbed start, then K timed ones along the
+    # same trajectory, restarting whenever the fit has converged.  The run is bounded by a time budget, so fewer than K
+    # iterations may be timed (steps_timed says how many).
+    budget = float(os.environ.get("APB_REF_BUDGET_S", "170"))
+    times, restarts = cpu_lm_iterations(scene, x0, args.warmup, args.steps, budget_s=budget)
     ms = 1e3 * float(np.mean(times)) / fac
     val = 1e3 / ms
+    crowded = wl in C3 or wl in C5
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "steps_timed": len(times), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak" if args.workload == "c2" else "strong", "vs_baseline": None,
+        "scaling": "weak" if wl == "c2" else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_text(args.workload, 1, 1),
-                   "note": "CPU oracle port of the reference algorithm (numpy + scipy FFT conv); one LM iteration from the perturbed start per step" + note},
+        "config": dict({"workload": workload_text(wl, args.gpus if wl == "c2" else 1, args.gpus if crowded or wl == "c4" else 1),
+                        "fit_restarts": restarts,
+                        "note": "CPU oracle port of the reference algorithm (numpy + scipy FFT conv); LM iterations along the fit "
+                                "trajectory from the perturbed start, restarted on convergence: the GPU arm's iteration mix" + note},
+                       **scale_info),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "1 full-size LM iteration (1 normal-equation build + lambda trials) per step; sources and "
-                                   "convolution planes on a thread pool of all cores, BLAS threads for J^T W J (the numpy port "
-                                   "is mostly serial: ~1.2x over one thread)" + note},
+                         "sample": f"{len(times)} consecutive LM iterations (1 normal-equation build + lambda trials each) after "
+                                   f"{args.warmup} untimed ones; sources and convolution planes on a thread pool of all cores, BLAS "
+                                   "threads for J^T W J (the numpy port is mostly serial: ~1.2x over one thread)" + note},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -406,23 +424,32 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------
-# algorithmic work of the kernels on config[1] (one PSF-convolved Sersic), summed over the timed
-# region: n_fwd value-only sampling passes and n_jac value+derivative passes
+# algorithmic work of the kernels, summed over the profiled region
 # ---------------------------------------------------------------------------
 def _fft_len(n):
     from astrophot_b200 import cabi
     return cabi.fft_length(n)
 
 
-def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
-    """Algorithmic bytes / FP64 work of each kernel over the profiled region,
-    summed over the sources of the scene.  n_fwd value-only sampling passes, n_jac value+derivative
-    passes, n_geo geodesic J^T v passes."""
+# FP64-pipe instructions per profile evaluation (SPE), Sersic:
+#   NOMINAL: SURVEY.md §8d, reference-faithful pow form -- 138 value-only, 230 value + 7 derivatives;
+#   EXECUTED: what this implementation issues per SPE (table-driven exp / log, rotation once per cell), counted from the
+#   ncu source page of the integration kernels (profiles/r02_summary.md): 40 value-only, 95 with derivatives.
+# `frac` of an FP64-bound kernel uses the EXECUTED count (it then reads as FP64-pipe utilisation and can be checked
+# against ncu's sm__pipe_fp64_cycles_active); `frac_nominal` uses the SURVEY figure and may exceed 1.
+SPE_NOMINAL = {"v": 138.0, "g": 230.0}
+SPE_EXECUTED = {"v": 40.0, "g": 95.0}
+
+
+def algorithmic_work(scene, spe, kern, n_fwd, n_jac, n_geo=0):
+    """Algorithmic bytes / FP64 instructions of each kernel over the profiled region, summed over the sources of the
+    scene.  n_fwd value-only sampling passes, n_jac value+derivative passes, n_geo geodesic J^T v passes;
+    spe = {"first": [value-only, derivative], "queue": [value-only, derivative]} profile evaluations the first pass and
+    the refinement queues really did in that region (apb_plan_stats totals)."""
     from astrophot_b200 import scene as sc
 
     tot = lambda f, j: n_fwd * f + n_jac * j
     fft_rows = fft_cols = fft_inv = conv_flops = blocks = 0.0
-    first_px = 0
     n_fft = n_dir = 0
     for src in scene.sources:
         n_act = sum(1 for sl in src.slot if sl >= 0)
@@ -432,8 +459,6 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
             # (n_act derivative planes + weight + residual) x 8 B + mask per pixel per build; J^T v: planes + v + mask
             blocks += n_jac * px * ((n_act + 2) * 8 + 1) + n_geo * px * ((n_act + 1) * 8 + 1)
         if src.psf < 0 or src.kind in (sc.KIND_POINT, sc.KIND_FLAT_SKY):
-            if src.kind not in (sc.KIND_POINT, sc.KIND_FLAT_SKY):
-                first_px += (ow + 2) * (oh + 2)
             continue
         ps = scene.psfs[src.psf]
         pw = int(ps.data.shape[1]) if ps.data is not None else int(ps.shape[1])
@@ -441,7 +466,6 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
         spw = pw + (2 if shifted else 0)      # bilinear-shifted stamp keeps its 1-px pad
         b = (pw + 2) // 2                     # psf_border_int = ceil((P+1)/2)
         ew, eh = ow + 2 * b, oh + 2 * b
-        first_px += (ew + 2) * (eh + 2)
         # planes per pass: value-only: 1 image plane, 1 PSF plane, 1 product; derivative pass: value + (n_act-2)
         # non-centre planes in, 3 PSF planes (K, dK/dcx, dK/dcy), 1 + n_act products out
         in_j, k_j, j_j = 1 + max(n_act - 2, 0), 3, 1 + n_act
@@ -458,17 +482,18 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
         else:
             n_dir += 1
             conv_flops += 2.0 * spw * spw * px * tot(1, j_j)
-    # profile evaluations: nominal FP64-pipe instructions per Sersic evaluation: 138 value-only,
-    # 230 value + 7 derivatives (reference-faithful pow form; the kernels use a cheaper log/exp form)
-    I_V, I_G = 138.0, 230.0
-    spe_int = 9.0 * sum(st["queued"])      # Gauss-Legendre 3x3 nodes per queue entry of the last call (approximate for the sum)
     # k_integrate and k_integrate_pool are launched back to back; the one whose kind of queue it is not returns at once
     pooled = kern.get("k_integrate_pool", (0, 0.0))[1] > kern.get("k_integrate", (0, 0.0))[1]
     k_int, k_int_g = ("k_integrate_pool", "k_integrate_pool_grad") if pooled else ("k_integrate", "k_integrate_grad")
-    n_int = kern.get(k_int, (0, 0))[0]
-    n_int_g = kern.get(k_int_g, (0, 0))[0]
+
+    def fp64(n_spe, kind, what):
+        return {"bound": "fp64", "flops": 2.0 * SPE_EXECUTED[kind] * n_spe, "flops_nominal": 2.0 * SPE_NOMINAL[kind] * n_spe,
+                "spe": n_spe, "what": f"{n_spe:.0f} profile evaluations x {SPE_EXECUTED[kind]:.0f} FP64 instr executed "
+                                      f"(x2 flop; nominal {SPE_NOMINAL[kind]:.0f}): {what}"}
+
     work = {
-        "k_conv": {"bound": "fp64", "flops": conv_flops, "what": f"2*P_s^2 flop per output pixel and plane, {n_dir} direct-convolved sources"},
+        "k_conv": {"bound": "fp64", "flops": conv_flops, "flops_nominal": conv_flops,
+                   "what": f"2*P_s^2 flop per output pixel and plane, {n_dir} direct-convolved sources"},
         "k_fft_rows": {"bound": "hbm", "bytes": float(fft_rows),
                        "what": f"real rows in (8 B/px) + half spectra out (16 B x nxh/row), {n_fft} FFT-convolved sources"},
         "k_fft_cols": {"bound": "hbm", "bytes": float(fft_cols),
@@ -477,14 +502,10 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
         "k_blocks": {"bound": "hbm", "bytes": float(blocks),
                      "what": "J^T W J build: n_act derivative planes + weight + residual (8 B) + mask per pixel of every source window; "
                              "geodesic J^T v: n_act planes + v + mask per pixel (pair blocks not counted)"},
-        "k_first": {"bound": "fp64", "flops": 2.0 * I_V * first_px * kern.get("k_first", (0, 0))[0],
-                    "what": f"{first_px} first-pass evaluations/launch x {I_V:.0f} nominal FP64 instr (x2 flop)"},
-        "k_first_grad": {"bound": "fp64", "flops": 2.0 * I_G * first_px * kern.get("k_first_grad", (0, 0))[0],
-                         "what": f"{first_px} first-pass evaluations/launch x {I_G:.0f} nominal FP64 instr (value + derivatives)"},
-        k_int: {"bound": "fp64", "flops": 2.0 * I_V * spe_int * n_int,
-                        "what": f"~{spe_int:.0f} sub-pixel evaluations/launch (last call's queue) x {I_V:.0f} nominal FP64 instr"},
-        k_int_g: {"bound": "fp64", "flops": 2.0 * I_G * spe_int * n_int_g,
-                             "what": f"~{spe_int:.0f} sub-pixel evaluations/launch x {I_G:.0f} nominal FP64 instr"},
+        "k_first": fp64(spe["first"][0], "v", "first-pass evaluations of the value-only passes"),
+        "k_first_grad": fp64(spe["first"][1], "g", "first-pass evaluations of the derivative passes"),
+        k_int: fp64(spe["queue"][0], "v", "Gauss-Legendre nodes of every refinement-queue entry, all depths, value-only passes"),
+        k_int_g: fp64(spe["queue"][1], "g", "Gauss-Legendre nodes of every refinement-queue entry, derivative passes"),
     }
     return {k: v for k, v in work.items() if v.get("flops", 0) or v.get("bytes", 0)}
 
@@ -492,23 +513,16 @@ def algorithmic_work(scene, st, kern, dfma_tflops, n_fwd, n_jac, n_geo=0):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
-def run_ours(args):
+def measure(wl, args, ctx, main=True):
+    """Every number of one workload at the current world size: device-resident value, per-kernel times + roofline,
+    end-to-end value; the dict is (for the main workload) the bench line."""
     import torch
     import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import astrophot_b200 as ap
     from astrophot_b200 import cabi
+    from astrophot_b200.errors import OptimizeStop
 
-    ap.AP_config.ap_device = f"cuda:{local}"
-    dev = torch.device("cuda", local)
-    wl = args.workload
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
     crowded = wl in C3 or wl in C5        # one big image: cut into tiles at N > 1
     if wl == "c2b" and world > 1:
         raise SystemExit("c2b is a single-band fit (replicas only)")
@@ -520,6 +534,8 @@ def run_ours(args):
     n_bands = world if wl == "c2" else (C4_BANDS if wl == "c4" else 1)   # c2b, c3*, c5*: one image
     scaling = "weak" if wl == "c2" else "strong"
     units_per_step = n_bands if wl == "c2" else 1
+    steps, warmup = args.steps, args.warmup
+    min_timed_s = 2.0 if main else 0.5
 
     # truth + noisy data; every rank builds all descriptions, data only for the bands it owns (the crowded field's
     # one image is built whole on every rank and cut by LM(tiles=...))
@@ -548,9 +564,9 @@ def run_ours(args):
                    conv=args.conv, tiles=(TILES[world] if crowded and world > 1 else None))
     plan = lm.plan
     n_pix_local = sum(h * w for h, w in plan.shapes)
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
+    flush = ctx["flush"]
 
-    state = {"fresh": True, "iters_in_fit": 0, "restarts": 0}
+    state = {"iters_in_fit": 0, "restarts": 0}
 
     def reset():
         lm.current_state = torch.as_tensor(x0, dtype=torch.float64, device=dev)
@@ -560,8 +576,7 @@ def run_ours(args):
         state["iters_in_fit"] = 0
 
     def one_iteration():
-        """One pass of the `for iteration in range(max_iter)` loop of LM.fit."""
-        from astrophot_b200.errors import OptimizeStop
+        """One pass of the `for iteration in range(max_iter)` loop of LM.fit (fit/lm.py:450-467)."""
         try:
             res = lm.step(chi2=lm.loss_history[-1])
         except OptimizeStop:
@@ -574,7 +589,7 @@ def run_ours(args):
         lm.loss_history.append(res[1])
         lm.Ldn()
         state["iters_in_fit"] += 1
-        if len(lm.loss_history) >= 3 and abs(lm.loss_history[-3] - lm.loss_history[-1]) / lm.loss_history[-1] < 1e-9:
+        if converged(lm.loss_history):
             state["restarts"] += 1
             reset()     # converged: start the next fit (outside the next step's timing)
 
@@ -583,40 +598,47 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local)
-    clocks.__enter__()          # sampling spans warm-up, the timed region and the e2e region (all under load)
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ctx["clocks"]
     reset()
     m0 = clocks.mark()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_iteration()
     barrier()
 
-    # ---- timed region (device-resident inputs): K iterations, L2 flushed between them
-    def timed_steps():
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # ---- timed region (device-resident inputs): blocks of K iterations, L2 flushed between iterations; the block is
+    #      repeated until min_timed_s have been timed and the MEDIAN block is reported (every rank runs the same count)
+    def timed_block():
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
-        for k in range(args.steps):
+        for k in range(steps):
             flush.zero_()
             barrier()
             ev[k][0].record()
             one_iteration()
             ev[k][1].record()
         barrier()
-        return float(sum(a.elapsed_time(b) for a, b in ev))
+        return allmax(float(sum(a.elapsed_time(b) for a, b in ev)))     # max over ranks
 
     launches0 = cabi.launch_count()
-    total_ms = timed_steps()
+    blocks_ms = [timed_block()]
+    while sum(blocks_ms) < 1e3 * min_timed_s and len(blocks_ms) < 400:
+        blocks_ms.append(timed_block())
     launches = cabi.launch_count() - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = units_per_step * args.steps / (total_ms * 1e-3)
+    total_ms = float(np.median(blocks_ms))
+    ms_per_step = total_ms / steps
+    value = units_per_step * steps / (total_ms * 1e-3)
 
     # ---- the same K iterations again with every kernel launch bracketed by CUDA events on its stream
     #      (per-kernel durations for the roofline; kept out of `value` because the event records cost time)
     reset()
+    for _ in range(warmup):
+        one_iteration()
     plans = lm.all_plans     # main plan, chi^2 twin, speculative pair
     spec = lm.speculate
     lm.speculate = False     # per-kernel durations are taken without the concurrent guess trials
@@ -624,18 +646,28 @@ def run_ours(args):
         pl.profile(True)
         pl.profile_read(reset=True)
     trials0, fwd0, jac0 = lm.n_trials, lm.n_forward, lm.n_jacobian
-    profiled_ms = timed_steps()
+    st0 = [pl.stats() for pl in plans]
+    profiled_ms = timed_block()
     kern = {}
     for pl in plans:
         for kname, (nl, ms) in pl.profile_read(reset=True).items():
             a = kern.get(kname, (0, 0.0))
             kern[kname] = (a[0] + nl, a[1] + ms)
         pl.profile(False)
+    st1 = [pl.stats() for pl in plans]
     lm.speculate = spec
     trials = lm.n_trials - trials0
     forwards = lm.n_forward - fwd0
     jacobians = lm.n_jacobian - jac0
     st = plan.stats()
+    # profile evaluations really done in the profiled region: first pass and refinement queues (quad_level^2 nodes per
+    # entry, every depth), value-only and derivative passes apart -- totals of every plan of the fit
+    q2 = max([s.quad_level for s in plan.scene.sources] or [3]) ** 2
+    spe = {"first": [0, 0], "queue": [0, 0]}
+    for a, b in zip(st0, st1):
+        for k in range(2):
+            spe["first"][k] += b["cum_first_pass_evals"][k] - a["cum_first_pass_evals"][k]
+            spe["queue"][k] += q2 * (sum(b["cum_queued"][k]) - sum(a["cum_queued"][k]))
 
     # ---- e2e: every step's data + weight come from pinned host memory and its result goes back to the host.
     #      Double-buffered like a survey pipeline would run it: while step k is fitted from one set of device buffers,
@@ -663,7 +695,7 @@ def run_ours(args):
                 if bufs:
                     pl.set_image_data(i, bufs["data"], bufs.get("weight"), pl._masks.get(i))
 
-    def e2e_pass(n_steps, do_upload=True, do_bind=True, do_readback=True):
+    def e2e_pass(n_steps):
         reset()
         barrier()
         for ev in consumed:
@@ -675,46 +707,128 @@ def run_ours(args):
             barrier()
             e0.record()
             cur = k % 2
-            if do_upload:
-                if k == 0:
-                    upload(cur)                      # nothing to hide the first upload behind
-                torch.cuda.current_stream().wait_event(uploaded[cur])
-            if do_bind:
-                bind(cur)
-            if do_upload and k + 1 < n_steps:
+            if k == 0:
+                upload(cur)                      # nothing to hide the first upload behind
+            torch.cuda.current_stream().wait_event(uploaded[cur])
+            bind(cur)
+            if k + 1 < n_steps:
                 upload(1 - cur)                  # next step's images, concurrent with this step's fit
             one_iteration()
             consumed[cur].record()
-            if do_readback:
-                out_pin[:-1].copy_(lm.current_state, non_blocking=True)
-                out_pin[-1] = lm.loss_history[-1]
+            out_pin[:-1].copy_(lm.current_state, non_blocking=True)
+            out_pin[-1] = lm.loss_history[-1]
             e1.record()
             torch.cuda.synchronize()
             total += e0.elapsed_time(e1)
         bind(0)
         return total
 
-    if os.environ.get("APB_E2E_DEBUG"):
-        for flags in ((False, False, False), (False, False, True), (False, True, True), (True, True, True)):
-            print("e2e debug upload/bind/readback", flags, e2e_pass(args.steps, *flags) / args.steps, "ms/step", file=sys.stderr, flush=True)
-    e2e_pass(max(args.warmup, 3))     # untimed warm-up of the streaming path (copy stream, second buffer set, pinned staging)
-    e2e_ms = e2e_pass(args.steps)
+    e2e_pass(max(min(warmup, 5), 3))     # untimed warm-up of the streaming path (copy stream, second buffer set, pinned staging)
+    e2e_ms = allmax(e2e_pass(steps))
     m1 = clocks.mark()
-    clocks.__exit__()
     clock_summary = clocks.summary(m0, m1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step * args.steps / (float(t.item()) * 1e-3)
+    e2e_value = units_per_step * steps / (e2e_ms * 1e-3)
 
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_text(wl, n_bands, world),
+                   "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
+                   "timing": f"median of {len(blocks_ms)} block(s) of {steps} consecutive LM iterations, "
+                             f"{sum(blocks_ms) * 1e-3:.2f} s timed in all; iterations follow the fit trajectory from the perturbed "
+                             "start and the fit restarts when it has converged (the reference arm does the same)",
+                   "kernel_timing": "one more block of the same K iterations with CUDA events around every launch "
+                                    f"({profiled_ms / steps:.3f} ms/step with the event records)",
+                   "params": len(x0), "lambda_trials_per_iter": trials / steps, "forwards_per_iter": forwards / steps,
+                   "fit_restarts": state["restarts"],
+                   "pcg_iterations_mean": (float(np.mean(lm.pcg_iterations)) if lm.pcg_iterations else None),
+                   "pcg_solves": len(lm.pcg_iterations), "block_array_doubles": plan.block_doubles()},
+        "clocks": clock_summary,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_pin.numel() * 8,
+                "pipeline": "double-buffered: step k+1's data + weight upload from pinned memory on a copy stream while step k "
+                            "is fitted; the plan is rebound with apb_plan_set_image_data; uploads and read-back are inside the timed region"},
+        "gpu_launches": launches,
+        "blocks_ms": [round(b, 3) for b in blocks_ms[:32]],
+    }
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        del lm, plan, plans, sets, pin
+        torch.cuda.empty_cache()
+        return None
 
     # ---- roofline of the dominant kernel (algorithmic work per DESIGN.md §4 / SURVEY.md §8d)
-    dfma_tflops, copy_gbs = cabi.bench_peaks()
+    dfma_tflops, copy_gbs = ctx["peaks"]
+    hbm_peak, hbm_src = ctx["hbm_peak"], ctx["hbm_src"]
+    work = algorithmic_work(plan.scene, spe, kern, n_fwd=forwards - jacobians, n_jac=jacobians, n_geo=trials)
+    traffic_all = {}
+    try:   # dram bytes per launch from the committed ncu --set full capture of this command
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+
+    def roof_of(kname):
+        nl, ms = kern[kname]
+        w = work.get(kname)
+        r = {"kernel": kname, "launches": nl, "avg_ms": ms / max(nl, 1),
+             "share_of_step": ms / max(sum(v[1] for v in kern.values()), 1e-9)}
+        tr = traffic_all.get(f"{wl}:{kname}", traffic_all.get(kname))
+        if w is None:
+            r.update({"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": tr})
+        elif w["bound"] == "fp64":
+            ach = w["flops"] / (ms * 1e-3) / 1e12
+            r.update({"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
+                      "frac_nominal": w["flops_nominal"] / (ms * 1e-3) / 1e12 / dfma_tflops,
+                      "traffic": tr, "peak_source": "apb_bench_peaks DFMA stream measured in this run "
+                      "(MEASURED_PEAKS.json has no fp64 figure; nominal 37.2)", "algorithmic": w["what"]})
+        else:
+            ach = w["bytes"] / (ms * 1e-3) / 1e9
+            r.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                      "traffic": tr, "peak_source": hbm_src, "algorithmic": w["what"],
+                      "algorithmic_bytes_per_launch": w["bytes"] / max(nl, 1)})
+        return r
+
+    top = max(kern.items(), key=lambda kv: kv[1][1])[0] if kern else None
+    roof = roof_of(top) if top else {"kernel": "none"}
+    roof_all = {}
+    for kname in kern:
+        if kname in work and kern[kname][1] > 0:
+            r = roof_of(kname)
+            roof_all[kname] = {"bound": r["bound"], "frac": round(r["frac"], 4)}
+            if "frac_nominal" in r:
+                roof_all[kname]["frac_nominal"] = round(r["frac_nominal"], 4)
+    out.update({
+        "roofline": roof, "roofline_all": roof_all,
+        "mpix_per_s_sampled": world * forwards * (n_pix_local / 1e6) / (profiled_ms * 1e-3),
+        "spe_per_s": (sum(spe["first"]) + sum(spe["queue"])) / (profiled_ms * 1e-3),
+        "kernel_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])},
+        "refine_queue_last": st["queued"], "peaks_now": {"dfma_tflops": dfma_tflops, "copy_gbs": copy_gbs},
+    })
+    del lm, plan, plans, sets, pin
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import astrophot_b200 as ap
+    from astrophot_b200 import cabi
+
+    ap.AP_config.ap_device = f"cuda:{local}"
+    dev = torch.device("cuda", local)
+    main_wl = args.workload or default_workload(world)
+    extras = []
+    if args.workload is None and not args.no_extras:
+        # the other BASELINE configurations at this world size, as extra keys of the line (shorter timed regions)
+        extras = ["c4", "c2"] + (["c5s"] if world == 1 else [])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -725,77 +839,41 @@ def run_ours(args):
         if isinstance(peaks.get(key), (int, float)):
             hbm_peak = float(peaks[key])
             break
-    hbm_src = "MEASURED_PEAKS.json" if hbm_peak else "apb_bench_peaks fp64 copy measured in this run (MEASURED_PEAKS.json absent)"
-    hbm_peak = hbm_peak or copy_gbs
-    top = max(kern.items(), key=lambda kv: kv[1][1]) if kern else ("none", (0, 0.0))
-    name, (n_launch, k_ms) = top
-    work = algorithmic_work(plan.scene, st, kern, dfma_tflops, n_fwd=forwards - jacobians, n_jac=jacobians, n_geo=trials)
-    roof = {"kernel": name, "launches": n_launch, "avg_ms": k_ms / max(n_launch, 1),
-            "share_of_step": k_ms / max(sum(v[1] for v in kern.values()), 1e-9)}
-    w = work.get(name)
-    traffic = None
-    try:   # dram bytes per launch from the committed ncu --set full capture of this command
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
-    except Exception:
-        pass
-    if w is None:
-        roof.update({"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": traffic})
-    elif w["bound"] == "fp64":
-        ach = w["flops"] / (k_ms * 1e-3) / 1e12
-        roof.update({"bound": "fp64", "achieved": ach, "peak": dfma_tflops, "unit": "TFLOP/s", "frac": ach / dfma_tflops,
-                     "traffic": traffic, "peak_source": "apb_bench_peaks DFMA stream measured in this run "
-                     "(MEASURED_PEAKS.json has no fp64 figure; nominal 37.2)", "algorithmic": w["what"]})
-    else:
-        ach = w["bytes"] / (k_ms * 1e-3) / 1e9
-        roof.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                     "traffic": traffic, "peak_source": hbm_src, "algorithmic": w["what"],
-                     "algorithmic_bytes_per_launch": w["bytes"] / max(n_launch, 1)})
-    roof_all = {}
-    for kname, (nl, ms) in kern.items():
-        ww = work.get(kname)
-        if ww is None or ms <= 0:
-            continue
-        if ww["bound"] == "fp64":
-            roof_all[kname] = {"frac": ww["flops"] / (ms * 1e-3) / 1e12 / dfma_tflops, "bound": "fp64"}
-        else:
-            roof_all[kname] = {"frac": ww["bytes"] / (ms * 1e-3) / 1e9 / hbm_peak, "bound": "hbm"}
-
-    # ---- CPU baseline (bounded sample: one full-size LM iteration of the oracle port)
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        scene_c, x0_c = cpu_scene(wl)
-        dt, _ = cpu_lm_iteration_seconds(scene_c, x0_c, 1)
-        fac, note = cpu_scale(wl)
-        cpu = {"value": fac / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": "1 full-size LM iteration of the numpy/scipy oracle port (FFT convolution; thread pool over sources and "
-                         "convolution planes + BLAS threads, ~1.2x over one thread), same workload" + note}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": workload_text(wl, n_bands, world),
-                   "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
-                   "kernel_timing": "second pass of the same K iterations with CUDA events around every launch "
-                                    f"({profiled_ms / args.steps:.3f} ms/step with the event records)",
-                   "params": len(x0), "lambda_trials_per_iter": trials / args.steps, "forwards_per_iter": forwards / args.steps,
-                   "fit_restarts": state["restarts"],
-                   "pcg_iterations_mean": (float(np.mean(lm.pcg_iterations)) if lm.pcg_iterations else None),
-                   "pcg_solves": len(lm.pcg_iterations), "block_array_doubles": plan.block_doubles(),
-                   "speculative_trials": {"launched": lm.n_spec_launched, "used_guesses": lm.n_spec_hits} if spec else None},
-        "clocks": clock_summary,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_pin.numel() * 8,
-                "pipeline": "double-buffered: step k+1's data + weight upload from pinned memory on a copy stream while step k "
-                            "is fitted; the plan is rebound with apb_plan_set_image_data; uploads and read-back are inside the timed region"},
-        "gpu_launches": launches,
-        "roofline": roof,
-        "roofline_all": {k: {"bound": v["bound"], "frac": round(v["frac"], 4)} for k, v in roof_all.items()},
-        "cpu_baseline": cpu,
-        "mpix_per_s_sampled": world * forwards * (n_pix_local / 1e6) / (profiled_ms * 1e-3),
-        "kernel_ms": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1])},
-        "refine_queue_last": st["queued"], "peaks_now": {"dfma_tflops": dfma_tflops, "copy_gbs": copy_gbs},
-    }
-    print(json.dumps(line), flush=True)
+    dfma_tflops, copy_gbs = cabi.bench_peaks()
+    clocks = ClockSampler(local)
+    clocks.__enter__()          # sampling spans warm-up, the timed region and the e2e region (all under load)
+    ctx = {"world": world, "rank": rank, "dev": dev, "clocks": clocks, "peaks": (dfma_tflops, copy_gbs),
+           "hbm_peak": hbm_peak or copy_gbs,
+           "hbm_src": "MEASURED_PEAKS.json" if hbm_peak else "apb_bench_peaks fp64 copy measured in this run (MEASURED_PEAKS.json absent)",
+           "flush": torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)}   # > 126 MB L2
+    line = measure(main_wl, args, ctx, main=True)
+    others = {}
+    for wl in extras:
+        try:
+            r = measure(wl, args, ctx, main=False)
+        except Exception as e:      # an extra workload must never cost the headline its line
+            r = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and r is not None:
+            keep = ("value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "roofline_all",
+                    "kernel_ms", "error")
+            others[wl] = {k: r[k] for k in keep if k in r}
+    clocks.__exit__()
+    if rank == 0:
+        # ---- CPU baseline (bounded sample of the oracle port on the host cores, the GPU arm's iteration mix)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            scene_c, x0_c = cpu_scene(main_wl)
+            n_cpu = 4 if main_wl in ("c3", "c3s", "c3t") else 2
+            times, _ = cpu_lm_iterations(scene_c, x0_c, 1, n_cpu, budget_s=40.0)
+            fac, note, scale_info = cpu_scale(main_wl)
+            cpu = dict({"value": fac / float(np.mean(times)), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{len(times)} consecutive LM iterations of the numpy/scipy oracle port after 1 untimed one (FFT "
+                                  "convolution; thread pool over sources and convolution planes + BLAS threads, ~1.2x over one "
+                                  "thread), same workload" + note}, **scale_info)
+        line["cpu_baseline"] = cpu
+        if others:
+            line["other_workloads"] = others
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -804,14 +882,17 @@ def run_ours(args):
 def main():
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
-    ap_.add_argument("--steps", type=int, default=100)
+    ap_.add_argument("--steps", type=int, default=20)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap_.add_argument("--workload", default="c2", choices=["c2", "c2b", "c3t", "c3s", "c3", "c4", "c5t", "c5s", "c5"],
-                     help="c2 = BASELINE config[1] (default, the metric's configuration); c3 = config[2] crowded field, "
-                          "c3s / c3t = its 1024^2 / 512^2 scale models; c4 = config[3], 8-band joint fit on 2048^2; c5 = config[4], 16384^2 mosaic with 10000 galaxies, c5s / c5t its "
-                          "2048^2 / 512^2 scale models")
+    ap_.add_argument("--workload", default=None, choices=["c2", "c2b", "c3t", "c3s", "c3", "c4", "c5t", "c5s", "c5"],
+                     help="default: c3 = BASELINE config[2], the 4096^2 crowded field (the configuration the 1-GPU target is "
+                          "quoted on; N > 1: cut into N tiles), with c4 / c2 / c5s measured too and attached as "
+                          "`other_workloads`.  c2 = config[1]; c3s / c3t = 1024^2 / 512^2 scale models of c3; c4 = config[3], "
+                          "8-band joint fit on 2048^2 (strong scaling, 8/N bands per GPU); c5 = config[4], 16384^2 mosaic with "
+                          "10000 galaxies, c5s / c5t its 2048^2 / 512^2 scale models")
     ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap_.add_argument("--no-extras", action="store_true", help="only the headline workload")
     ap_.add_argument("--conv", default=None, choices=["direct", "fft"],
                      help="force one PSF-convolution kernel family (default: automatic, FFT for the 51x51 PSF)")
     args = ap_.parse_args()

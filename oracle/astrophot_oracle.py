@@ -824,8 +824,11 @@ class OptimizeStop(Exception):
 
 
 def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_iter=10,
-           curvature_limit=1.0, Lup=11.0, Ldn=9.0, L0=1.0, acceleration=0.0, conv="direct", verbose=0):
-    """Levenberg-Marquardt loop, control flow of fit/lm.py:248-357,428-493."""
+           curvature_limit=1.0, Lup=11.0, Ldn=9.0, L0=1.0, acceleration=0.0, conv="direct", verbose=0, stop=None):
+    """Levenberg-Marquardt loop, control flow of fit/lm.py:248-357,428-493.
+    ``stop``: optional callable(loss_history) -> bool checked after every iteration (bench.py ends a fit with the same
+    rule as its GPU arm); the result carries the wall-clock seconds of every iteration in ``iter_seconds``."""
+    import time as _time
     x = np.asarray(x0, dtype=np.float64).copy()
     Y, W, keep = flat_targets(scene)
     if ndf is None:
@@ -849,7 +852,9 @@ def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_
     x_hist = [x.copy()]
     trials_hist = []
     message = ""
+    iter_seconds = []
     for it in range(max_iter):
+        _t0 = _time.perf_counter()
         # ---- step (lm.py:248-357)
         Y0 = fwd(x)
         J = np.concatenate([j.reshape(-1, scene.n_par) for j in jacobian(scene, x, True, conv)])
@@ -909,6 +914,7 @@ def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_
             if (best[1] - init) / init < -0.1:
                 break
         trials_hist.append(ntr)
+        iter_seconds.append(_time.perf_counter() - _t0)
         if nostep:
             if scary[0] is not None:
                 res = scary
@@ -925,6 +931,9 @@ def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_
         L = dn(L)
         if verbose:
             print(f"Chi^2/DoF: {loss[-1]}, L: {L}")
+        if stop is not None and stop(loss):
+            message += "stopped"
+            break
         if len(loss) >= 3 and (loss[-3] - loss[-1]) / loss[-1] < relative_tolerance and L < 0.1:
             message += "success"
             break
@@ -934,4 +943,4 @@ def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_
     else:
         message += "fail. Maximum iterations"
     return {"x": x, "loss_history": loss, "L_history": L_hist, "lambda_history": x_hist,
-            "message": message, "trials": trials_hist}
+            "message": message, "trials": trials_hist, "iter_seconds": iter_seconds}
