@@ -1462,11 +1462,16 @@ extern "C" int apb_lm_trial_spec(apb_plan_t* p, apb_plan_t* p2, apb_plan_t* dono
   if ((rc = lm_solve_launch(H, p->d_rpp, L, P, p->d_atmp2, nullptr, e2, st))) return rc;
   if (overlap) {
     CU(cudaStreamWaitEvent(st, p->ev_trial_join, 0));
-    k_trial_join<<<1, 1, 0, st>>>(p->d_rec2, p->q.overflow, p2->q.overflow, rec);
+    k_trial_join<<<1, 1, 0, st>>>(p->d_rec2, p->q.overflow, p2->q.overflow, donor != p ? donor->q.overflow : nullptr, rec);
     p->launches += p2->launches + 1;
     g_launches++;
   } else {
     if ((rc = chi2_core(p, p->d_xtmp2, rec, st))) return rc;
+    if (donor != p) {
+      k_trial_join<<<1, 1, 0, st>>>(rec, p->q.overflow, nullptr, donor->q.overflow, rec);
+      p->launches++;
+      g_launches++;
+    }
   }
   p->stats.launches = p->launches + 2;
   return 0;

@@ -595,10 +595,14 @@ struct LmEpi {
 };
 
 // joins the concurrent chi^2 pass of a trial into the record the host reads
-__global__ void k_trial_join(const double* __restrict__ c2, const int* __restrict__ ovf_a, const int* __restrict__ ovf_b,
-                             double* __restrict__ rec) {
-  rec[0] = c2[0];
-  rec[1] = (*ovf_a || *ovf_b) ? -1.0 : c2[1];
+// (ovf_c: the donor plan of a trial that reads another plan's stamp Jacobian -- a queue overflow during THAT plan's
+//  Jacobian pass left J^T W J and J^T W r without some sub-pixel refinements; it must reach the record the host reads,
+//  or the grow-and-retry of LM.step never fires.  c2 may alias rec.)
+__global__ void k_trial_join(const double* c2, const int* __restrict__ ovf_a, const int* __restrict__ ovf_b,
+                             const int* __restrict__ ovf_c, double* rec) {
+  const double chi = c2[0], flag = c2[1];
+  rec[0] = chi;
+  rec[1] = (*ovf_a || (ovf_b && *ovf_b) || (ovf_c && *ovf_c)) ? -1.0 : flag;
 }
 // same, as summable counts for a cross-rank all-reduce: tail = {chi^2, ranks with non-finite pixels,
 // ranks whose refinement queues overflowed}

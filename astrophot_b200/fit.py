@@ -31,6 +31,21 @@ from .lowering import lower, shard_scene, tile_scene
 __all__ = ["BaseOptimizer", "LM", "Iter", "Iter_LM"]
 
 
+def _state_device():
+    """Device of the optimiser's state vectors.  The native library launches on the CURRENT CUDA device and the plans
+    allocate there (cabi), so the state lives there too: a multi-GPU run that calls ``torch.cuda.set_device(rank)`` but
+    leaves ``AP_config.ap_device`` at its default would otherwise hand cuda:0 pointers to kernels on cuda:rank."""
+    if torch.cuda.is_available() and str(AP_config.ap_device).startswith("cuda"):
+        cur = torch.device("cuda", torch.cuda.current_device())
+        want = torch.device(AP_config.ap_device)
+        if want.index is not None and want.index != cur.index:
+            AP_config.ap_logger.warning(
+                f"AP_config.ap_device is {want} but the current CUDA device is {cur}: the fit runs on {cur} "
+                "(set AP_config.ap_device to match, or call torch.cuda.set_device)")
+        return cur
+    return torch.device(AP_config.ap_device)
+
+
 class BaseOptimizer:
     """State shared by optimisers (reference: `fit/base.py:26-129`)."""
 
@@ -44,7 +59,7 @@ class BaseOptimizer:
         if isinstance(initial_state, torch.Tensor):
             initial_state = initial_state.detach().cpu().numpy()
         self.current_state = torch.as_tensor(np.asarray(initial_state, dtype=np.float64), dtype=torch.float64,
-                                             device=AP_config.ap_device)
+                                             device=_state_device())
         if self.verbose > 1:
             AP_config.ap_logger.info(f"initial state: {self.current_state}")
         self.max_iter = kwargs.get("max_iter", 100 * len(initial_state))
@@ -119,12 +134,14 @@ class LM(BaseOptimizer):
             if im.aux:
                 continue
             n_keep += im.H * im.W if im.mask is None else int((~torch.as_tensor(im.mask).bool()).sum())
-        if n_keep == 0:
-            raise OptimizeStop("No data to fit. All pixels are masked")
         if self.distributed:
-            t = torch.tensor([float(n_keep)], dtype=torch.float64, device=AP_config.ap_device)
+            # the count of the WHOLE fit decides (lm.py:206-209): a rank whose tile is fully masked must not stop alone
+            # while the others wait in this all-reduce
+            t = torch.tensor([float(n_keep)], dtype=torch.float64, device=self.current_state.device)
             torch.distributed.all_reduce(t, group=self.group)
             n_keep = int(t.item())
+        if n_keep == 0:
+            raise OptimizeStop("No data to fit. All pixels are masked")
         self.plan = Plan(scene, conv=kwargs.get("conv", None), queue_capacity=kwargs.get("queue_capacity", 0))   # conv: force "direct"/"fft" (tests, benchmarks)
         self._covariance_matrix = None
         P = len(self.current_state)
@@ -239,6 +256,15 @@ class LM(BaseOptimizer):
             c2[0] = rec[0]
             c2[1] = torch.where(rec[2] > 0, -1.0, (rec[1] == 0).to(c2.dtype))
         return c2
+
+    def set_image_data(self, i, data, weight=None, mask=None):
+        """Point image ``i`` of the fit at other device tensors of the same shape (the next exposure of a survey, uploaded
+        while the current one was fitted).  EVERY plan of the optimiser is rebound -- the main plan builds the normal
+        equations, the forward-only twins evaluate the trial chi^2: rebinding only one of them would compare chi^2 of
+        different data and take wrong accept / reject decisions without any error."""
+        for pl in self.all_plans:
+            pl.set_image_data(i, data, weight, mask if mask is not None else pl._masks.get(i))
+        self._covariance_matrix = None
 
     @property
     def all_plans(self):
@@ -632,7 +658,7 @@ class Iter(BaseOptimizer):
                 AP_config.ap_logger.info(model.name)
             self.sub_step(model)
         self.current_state = torch.as_tensor(self.model.parameters.vector_representation().numpy(), dtype=torch.float64,
-                                             device=AP_config.ap_device)
+                                             device=_state_device())
         self.Y = self.model(parameters=self.current_state.cpu(), as_representation=True)
         sub = self.model.target[self.model.window]
         D = sub.flatten("data")

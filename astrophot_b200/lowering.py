@@ -427,6 +427,12 @@ def shard_scene(scene, rank, world):
     J^T W J lands in the same (P, P) layout and a plain sum all-reduce merges
     them."""
     real = [i for i, im in enumerate(scene.images) if not im.aux]
+    if world > len(real):
+        # decided from the whole scene, so every rank raises the same error (a rank without images would otherwise stop
+        # alone and leave the others waiting in their first collective)
+        raise SpecificationConflict(
+            f"a fit over {world} ranks needs at least {world} images (bands or tiles) to deal out, this one has "
+            f"{len(real)}: use fewer ranks, cut the image into more tiles (LM(tiles=...)), or run replicas")
     keep = [i for k, i in enumerate(real) if k % world == rank] + [i for i, im in enumerate(scene.images) if im.aux]
     remap = {old: new for new, old in enumerate(keep)}
     srcs, new_index = [], {}

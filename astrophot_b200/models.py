@@ -1076,9 +1076,10 @@ class Group_Model(AstroPhot_Model):
                 f"{self.name} already has model with name {model.name}, every model must have a unique name.")
         self.models[model.name] = model
         self.parameters.link(model.parameters)
-        # the group's psf_mode and target override the sub-model's (group_model_object.py:85-89)
+        # the group's psf_mode overrides the sub-model's; its target is handed to sub-models that have none
+        # (group_model_object.py:85-89,306-323)
         model.psf_mode = self.psf_mode
-        model.target = self.target
+        self._offer_target(model, self.target)
         if _update:
             self.update_window()
 
@@ -1120,7 +1121,20 @@ class Group_Model(AstroPhot_Model):
             raise InvalidTarget("Group_Model target must be a Target_Image instance.")
         self._target = tar
         for model in getattr(self, "models", {}).values():
+            self._offer_target(model, tar)
+
+    @staticmethod
+    def _offer_target(model, tar):
+        """group_model_object.py:312-323: a sub-model without a target takes the group's; one that has its own keeps it
+        (a mismatch is only reported); with an image list every sub-model keeps the member it was built on."""
+        if tar is None or isinstance(tar, Image_List):
+            return
+        if model.target is None:
             model.target = tar
+        elif isinstance(model.target, Image_List) or model.target.identity != tar.identity:
+            AP_config.ap_logger.warning(
+                f"Group_Model target does not match model {model.name} target. This may cause issues. Use the same "
+                "Target_Image object for all relevant models.")
 
     @property
     def psf_mode(self):

@@ -690,10 +690,9 @@ def measure(wl, args, ctx, main=True):
             uploaded[which].record(copy_stream)
 
     def bind(which):
-        for pl in plans:
-            for i, bufs in enumerate(sets[which]):
-                if bufs:
-                    pl.set_image_data(i, bufs["data"], bufs.get("weight"), pl._masks.get(i))
+        for i, bufs in enumerate(sets[which]):
+            if bufs:
+                lm.set_image_data(i, bufs["data"], bufs.get("weight"))      # every plan of the fit
 
     def e2e_pass(n_steps):
         reset()

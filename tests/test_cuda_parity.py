@@ -626,6 +626,25 @@ def test_plan_rebinds_image_data():
     assert torch.equal(H3, H0) and torch.equal(g3, g0)
 
 
+def test_lm_rebinds_every_plan():
+    """LM.set_image_data rebinds the main plan AND the forward-only twins: a fit of other data through the same LM
+    object equals a fit of an LM built on those data (rebinding the main plan alone would build the normal equations
+    from the new image and judge the trials on the old one)."""
+    fix = load_golden("psf_sersic")
+    data = golden_data(fix)
+    m1, _ = scenes.build(ap, "psf_sersic", data=data)
+    lm = ap.fit.LM(m1, initial_state=fix["x0"], max_iter=4, relative_tolerance=0.0)
+    assert len(lm.all_plans) >= 2
+    d2 = data[0]["data"] * 1.02 + 0.01
+    m2, _ = scenes.build(ap, "psf_sersic", data={0: {"data": d2, "variance": data[0]["variance"]}})
+    want = ap.fit.LM(m2, initial_state=fix["x0"], max_iter=4, relative_tolerance=0.0).fit()
+    new = torch.as_tensor(d2, dtype=torch.float64, device="cuda")
+    lm.set_image_data(0, new, lm.plan.image_buffers[0].get("weight"))
+    got = lm.fit()
+    np.testing.assert_allclose(got.loss_history, want.loss_history, rtol=1e-12)
+    np.testing.assert_allclose(got.res(), want.res(), rtol=1e-12, atol=1e-14)
+
+
 def test_speculative_lambda_search_gives_the_same_fit():
     """LM(speculate=True): the likely next lambda-trial runs on a second stream and a forward-only plan pair
     (apb_lm_trial_spec with the main plan as Jacobian donor); histories must be identical to the sequential search."""

@@ -184,3 +184,18 @@ def test_distributed_tiled_lm_control_flow(tmp_path):
     np.testing.assert_allclose(got["loss"], fix["loss_history"][:n], rtol=1e-8)
     np.testing.assert_allclose(got["L"][:4], fix["L_history"][:4], rtol=1e-12)
     np.testing.assert_allclose(got["lam"], fix["lambda_history"][:n], rtol=1e-8, atol=1e-8)
+
+
+def test_more_ranks_than_images_is_refused_on_every_rank():
+    """shard_scene decides from the whole scene: with more ranks than bands / tiles every rank raises the same error
+    (a rank left without images would otherwise stop alone and the others would hang in their first collective)."""
+    import astrophot_b200 as ap
+    from astrophot_b200.lowering import lower, shard_scene
+    ap.AP_config.ap_device = "cpu"
+    model, _ = scenes.build(ap, "joint")
+    scene, _ = lower(model)
+    n_img = len([im for im in scene.images if not im.aux])
+    for rank in range(n_img + 1):
+        with pytest.raises(ap.errors.SpecificationConflict, match="at least"):
+            shard_scene(scene, rank, n_img + 1)
+    assert len(shard_scene(scene, 0, n_img).images) == 1
