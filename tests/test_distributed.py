@@ -190,6 +190,7 @@ def test_more_ranks_than_images_is_refused_on_every_rank():
     """shard_scene decides from the whole scene: with more ranks than bands / tiles every rank raises the same error
     (a rank left without images would otherwise stop alone and the others would hang in their first collective)."""
     import astrophot_b200 as ap
+    import scenes
     from astrophot_b200.lowering import lower, shard_scene
     ap.AP_config.ap_device = "cpu"
     model, _ = scenes.build(ap, "joint")
