@@ -44,7 +44,8 @@ class apb_source_t(C.Structure):
                 ("quad_level", C.c_int32), ("gridding", C.c_int32), ("max_depth", C.c_int32),
                 ("ref_mode", C.c_int32), ("psf", C.c_int32), ("psf_shift", C.c_int32), ("conv_mode", C.c_int32),
                 ("owner", C.c_int32), ("_pad", C.c_int32),
-                ("tolerance", C.c_double), ("softening", C.c_double)]
+                ("tolerance", C.c_double), ("softening", C.c_double),
+                ("mask", C.c_void_p), ("mask_rect", C.c_int32 * 4)]
 
 
 class apb_owner_t(C.Structure):
@@ -228,6 +229,17 @@ class Plan:
             c.conv_mode = int(getattr(s, "conv_mode", 0))
             c.owner = int(getattr(s, "owner", -1))
             c.tolerance, c.softening = s.tolerance, s.softening
+            mk = getattr(s, "mask", None)
+            if mk is not None:
+                key = id(mk)
+                self._src_masks = getattr(self, "_src_masks", {})
+                if key not in self._src_masks:      # (the pieces of a model cut into chunks or tiles share one mask)
+                    t = torch.as_tensor(np.ascontiguousarray(mk)).to(device="cuda", dtype=torch.uint8).contiguous()
+                    self._src_masks[key] = t
+                    self._keep.append(t)
+                t = self._src_masks[key]
+                c.mask = t.data_ptr()
+                c.mask_rect[:] = [int(s.mask_origin[0]), int(s.mask_origin[1]), int(t.shape[1]), int(t.shape[0])]
         opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4) | (8 if pooled_integration else 0))
         owners = getattr(scene, "owners", None)
         if owners:       # models of the whole fit (the scene holds their pieces: lowering.tile_scene / shard_scene)

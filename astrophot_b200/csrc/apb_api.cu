@@ -475,6 +475,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       s.gmagic = (65536 + G - 1) / G;
     }
     s.psf = a.psf; s.psf_shift = a.psf_shift;
+    s.mask = a.mask; s.mask_x0 = a.mask_rect[0]; s.mask_y0 = a.mask_rect[1]; s.mask_w = a.mask_rect[2]; s.mask_h = a.mask_rect[3];
+    if (a.mask && (a.mask_rect[2] <= 0 || a.mask_rect[3] <= 0)) PFAIL("source mask with an empty shape");
     for (int k = 0; k < 4; ++k) s.S[k] = im.S[k];
     const double det = im.S[0] * im.S[3] - im.S[1] * im.S[2];
     if (det == 0.0) PFAIL("singular pixelscale");

@@ -252,14 +252,14 @@ __global__ void __launch_bounds__(256) k_assemble(const DevSrc* __restrict__ src
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = t.z + ly + 8 * r;
-        if (y >= s.oy && y < s.oy + s.oh) m[r] += v;
+        if (y >= s.oy && y < s.oy + s.oh && !src_masked(s, x, y)) m[r] += v;
       }
     } else {
       const PlaneView v = out_plane(s, mode, 0, stamp, outar);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = t.z + ly + 8 * r;
-        if (y >= s.oy && y < s.oy + s.oh) m[r] += v.p[(long long)(y - s.oy) * v.stride + (x - s.ox)];
+        if (y >= s.oy && y < s.oy + s.oh && !src_masked(s, x, y)) m[r] += v.p[(long long)(y - s.oy) * v.stride + (x - s.ox)];
       }
     }
   }
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) k_jac_dense(const DevSrc* __restrict__ sr
     for (int b = b0; b < b1; ++b) {
       const int si = bin_src[b];
       const DevSrc& s = src[si];
-      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh) continue;
+      if (x < s.ox || x >= s.ox + s.ow || y < s.oy || y >= s.oy + s.oh || src_masked(s, x, y)) continue;
       for (int e = 0; e < s.n_elem_all; ++e) {
         const int p = s.plane[e];
         if (p <= 0) continue;
@@ -428,9 +428,9 @@ __global__ void __launch_bounds__(256) k_blocks(const DevSrc* __restrict__ src, 
       if (!masked) {
         w = im.weight ? im.weight[p] : 1.0;
         if (need_r) r = rimg[p];
-        if (has_a) ja = a_sky ? ca : va.p[(long long)(y - A.oy) * va.stride + (x - A.ox)];
+        if (has_a && !src_masked(A, x, y)) ja = a_sky ? ca : va.p[(long long)(y - A.oy) * va.stride + (x - A.ox)];
         if (it.diag) jb = ja;
-        else if (has_b && !vec_only) jb = b_sky ? cb : vb.p[(long long)(y - B.oy) * vb.stride + (x - B.ox)];
+        else if (has_b && !vec_only && !src_masked(B, x, y)) jb = b_sky ? cb : vb.p[(long long)(y - B.oy) * vb.stride + (x - B.ox)];
       }
     }
     gv = fma(r, ja, gv);
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(256) k_geo_v(const DevSrc* __restrict__ src, c
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int y = t.z + ly + 8 * r;
-        in[r] = y < im.H && y >= s.oy && y < s.oy + s.oh;
+        in[r] = y < im.H && y >= s.oy && y < s.oy + s.oh && !src_masked(s, x, y);
         off[r] = in[r] ? (long long)(y - s.oy) * pv.stride + (x - s.ox) : 0;
         any |= in[r];
       }

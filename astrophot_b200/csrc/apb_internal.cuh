@@ -53,6 +53,8 @@ struct DevSrc {
   long long psf_off;       // offset of this source's shifted PSF stamps (3 x spw*sph) or -1
   int spw, sph;            // shifted stamp size
   double S[4], Sinv[4], rij[2], rxy[2], area;
+  const unsigned char* mask;            // the model's own mask (non-zero: no contribution) or NULL
+  int mask_x0, mask_y0, mask_w, mask_h; // image pixel of its element (0, 0), its shape
   int same_geo;            // forward and jacobian geometry identical
   // FFT convolution (apb_fft.cuh); conv_fft = 0: tiled direct convolution
   int conv_fft;
@@ -94,6 +96,13 @@ __device__ __forceinline__ PlaneView out_plane(const DevSrc& s, int mode, int pl
     v.stride = g.mw;
   }
   return v;
+}
+
+// model_object.py:370-371: working_image.data * logical_not(self.mask), applied where a source's planes are consumed
+__device__ __forceinline__ bool src_masked(const DevSrc& s, int x, int y) {
+  if (!s.mask) return false;
+  const int mx = x - s.mask_x0, my = y - s.mask_y0;
+  return mx >= 0 && mx < s.mask_w && my >= 0 && my < s.mask_h && s.mask[(long long)my * s.mask_w + mx] != 0;
 }
 
 // -----------------------------------------------------------------------------

@@ -178,8 +178,21 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
     def build_source(comp, ii, region, out, fwd, jac, host=None):
         """``host``: the point source that draws ``comp`` (a PSF model) at its own centre, times 10^flux
         (point_source.py:122-140)."""
-        if comp.mask is not None or (host is not None and host.mask is not None):
-            raise SpecificationConflict("per-model masks are not supported by astrophot_b200 yet")
+        # the model's own mask (model_object.py:370-371): zeroes the model (and, through autodiff, its Jacobian) on the
+        # image it was sampled on, so it must have that image's shape -- the model's window, which inside a group must
+        # then equal the window the group samples it on
+        mk, mk_origin = (comp if host is None else host).mask, (0, 0)
+        if host is not None and comp.mask is not None:
+            raise SpecificationConflict(f"{comp.name}: a mask on a PSF model that a point source is drawn from is not supported")
+        if mk is not None:
+            mk = np.ascontiguousarray(torch.as_tensor(mk).detach().cpu().numpy() != 0)
+            for rect in (out, fwd):
+                if mk.shape == (rect[3], rect[2]):
+                    mk_origin = (int(rect[0]), int(rect[1]))
+                    break
+            else:
+                raise SpecificationConflict(
+                    f"{comp.name}: the model mask has shape {mk.shape}, the image the model is sampled on {(out[3], out[2])}")
         # elements
         names = list(sc.ELEMS[comp._kind])
         nodes = []
@@ -294,7 +307,8 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             max_depth=int(comp.integrate_max_depth), tolerance=float(comp.sampling_tolerance),
             softening=float(comp.softening), ref_mode=comp._ref_mode, psf=pidx,
             psf_shift=_shift_code(comp.psf_subpixel_shift),
-            conv_mode=sc.CONV_DIRECT if comp.psf_convolve_mode == "direct" else sc.CONV_AUTO, name=comp.name)
+            conv_mode=sc.CONV_DIRECT if comp.psf_convolve_mode == "direct" else sc.CONV_AUTO, name=comp.name,
+            mask=mk, mask_origin=mk_origin)
 
     # ---- sources
     sources = []
@@ -308,6 +322,8 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
         if not isinstance(pm, PSF_Model) or getattr(pm, "_kind", None) is None:
             raise SpecificationConflict(
                 f"auxiliary PSF model type '{pm.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §8f)")
+        if pm.mask is not None:
+            raise SpecificationConflict(f"{pm.name}: a mask on an auxiliary PSF model is not supported")
         w = pm.window
         ii = n_real + len(aux_images)
         aux_images.append(sc.SceneImage(H=int(w._shape[1]), W=int(w._shape[0]), S=w._S.copy(), rij=w._rij.copy(),
@@ -515,6 +531,7 @@ def tile_scene(scene, ny, nx):
             s2.out = (ix0 - tx, iy0 - ty, ix1 - ix0, iy1 - iy0)
             s2.fwd = (s.fwd[0] - tx, s.fwd[1] - ty, s.fwd[2], s.fwd[3])
             s2.jac = (s.jac[0] - tx, s.jac[1] - ty, s.jac[2], s.jac[3])
+            s2.mask_origin = (s.mask_origin[0] - tx, s.mask_origin[1] - ty)
             new_index[k] = len(sources)
             sources.append(s2)
     # the tiles come first, aux images last (as lower() lays them out)

@@ -95,6 +95,9 @@ class SceneSource:
     conv_mode: int = CONV_AUTO
     name: str = ""
     owner: int = -1          # index into Scene.owners (the model this source is a tile-clipped piece of)
+    mask: object = None      # the model's own mask (model_object.py:370-371): 2-D bool array, True = the model contributes
+                             # nothing there (value and derivatives); element [0, 0] is image pixel `mask_origin`
+    mask_origin: tuple = (0, 0)
 
     @property
     def n_elem(self):

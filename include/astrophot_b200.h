@@ -116,6 +116,11 @@ typedef struct {
                         owner table is given */
   int32_t _pad;
   double tolerance, softening;
+  /* the model's own mask (models/model_object.py:370-371, point_source.py:184-185): device, mask_rect[2] x mask_rect[3]
+   * bytes, row-major, element (0, 0) = image pixel (mask_rect[0], mask_rect[1]); where it is non-zero the source
+   * contributes nothing -- value and derivatives (the reference differentiates through the product).  NULL = none. */
+  const uint8_t *mask;
+  int32_t mask_rect[4];
 } apb_source_t;
 
 /* One component model of the WHOLE fit, for fits whose pixels are split into tiles and / or over

@@ -457,6 +457,25 @@ class SourceResult:
 
 
 def sample_source(scene, si, el, mode, want_grad, conv="direct", stats=None, vals=None):
+    """One component model on its output window, times the model's own mask (model_object.py:370-371,
+    point_source.py:184-185, psf_model_object.py:259-260: ``working_image.data * logical_not(self.mask)`` -- the
+    reference differentiates through that product, so the derivative planes are masked too)."""
+    r = _sample_source_unmasked(scene, si, el, mode, want_grad, conv, stats, vals)
+    src = scene.sources[si]
+    m = getattr(src, "mask", None)
+    if m is None:
+        return r
+    mx0, my0 = src.mask_origin
+    ox, oy, ow, oh = src.out
+    keep = ~np.asarray(m, dtype=bool)[oy - my0 : oy - my0 + oh, ox - mx0 : ox - mx0 + ow]
+    r.value = r.value * keep
+    if r.grad is not None:
+        r.grad = r.grad * keep[None]
+    r.extra = [(sl, pl * keep) for sl, pl in r.extra]
+    return r
+
+
+def _sample_source_unmasked(scene, si, el, mode, want_grad, conv="direct", stats=None, vals=None):
     """One component model on its output window.
 
     mode: "fwd" (working window = group window; group_model_object.py:211-227

@@ -97,6 +97,18 @@ def build(ap, name, data=None):
               psf_subpixel_shift="bilinear" if name == "psf_sersic" else "none",
               parameters={"center": [30.8, 33.3], "q": 0.55, "PA": 2.4, "n": 2.5, "Re": 6.0, "Ie": 1.0})
         return m, {}
+    if name in ("sersic_modelmask", "psf_sersic_modelmask"):
+        # the model's OWN mask (model_object.py:370-371; not the target's): the model contributes nothing there
+        import torch
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 11), pixelscale=1.0)
+        tar = _target(ap, (60, 64), data, psf=psf)
+        mk = np.zeros((60, 64), dtype=bool)
+        mk[20:27, 30:41] = True
+        mk[np.random.default_rng(77).integers(0, 60, 40), np.random.default_rng(78).integers(0, 64, 40)] = True
+        m = M(name=name, model_type="sersic galaxy model", target=tar, mask=torch.as_tensor(mk),
+              psf_mode="full" if name.startswith("psf") else "none",
+              parameters={"center": [30.8, 31.3], "q": 0.55, "PA": 2.4, "n": 2.1, "Re": 6.0, "Ie": 1.0})
+        return m, {}
     if name in ("aux_psf_moffat", "aux_psf_gauss_noshift"):
         # PSF *model* as the auxiliary PSF of a galaxy model: its parameters are fitted with the galaxy's
         # (model_object.py:133-147,307-310; BASELINE config[1] variant B)
@@ -306,12 +318,13 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs",
-                 "point_psf_model", "point_psf_model_group", "group_edge"]
+                 "point_psf_model", "point_psf_model_group", "group_edge", "sersic_modelmask", "psf_sersic_modelmask"]
 CPU_ONLY_SCENES = []
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
-             "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18}
+             "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18,
+             "psf_sersic_modelmask": 19}
 CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe

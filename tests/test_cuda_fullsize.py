@@ -151,3 +151,48 @@ def test_crowded_scale_model_lm_history_matches_the_reference_itself():
     np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)
     np.testing.assert_allclose(res.L_history[: n + 1], fix["L"], rtol=1e-12)
     np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lam"], rtol=1e-8, atol=1e-8)
+
+
+def test_mosaic_scale_model_lm_history_matches_the_reference_itself():
+    """The 512^2 scale model of BASELINE config[4] (Sersic + 12-node spline galaxies + sky, no PSF: the block-sparse
+    solver, the mean integration reference of spline models inside a group) against astrophot.fit.LM run on the same
+    seeded inputs in the build container (oracle/make_workload_golden.py c5t)."""
+    import bench
+    import astrophot_b200 as ap
+    fix = dict(np.load(os.path.join(ROOT, "tests", "golden", "c5t_lm.npz")))
+    ap.AP_config.ap_device = "cuda:0"
+    truth = bench.build_mosaic(ap, "c5t", None)().data.cpu().numpy()
+    assert abs(truth.sum() - float(fix["truth_sum"][0])) <= 1e-11 * float(fix["truth_sum"][0])
+    np.testing.assert_allclose(truth[::37, ::41].reshape(-1), fix["truth_probe"], rtol=1e-10, atol=1e-16 * truth.max())
+    model = bench.build_mosaic(ap, "c5t", bench.make_data(truth, 10))
+    x0 = bench.start_state(model.parameters.vector_representation().numpy(), scale=bench.start_scale("c5t"))
+    np.testing.assert_allclose(x0, fix["x0"], rtol=0, atol=0)
+    n = len(fix["loss"]) - 1
+    res = ap.fit.LM(model, initial_state=x0, max_iter=n, relative_tolerance=0.0).fit()
+    np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)
+    np.testing.assert_allclose(res.L_history[: n + 1], fix["L"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lam"], rtol=1e-8, atol=1e-8)
+
+
+def test_eight_band_joint_fit_lm_history_matches_the_reference_itself():
+    """BASELINE config[3] at 160^2 per band -- 8 bands in a Target_Image_List, centre / q / PA / n / Re shared, per-band Ie
+    and Gaussian PSF, P = 13 -- against astrophot.fit.LM on the same seeded inputs (oracle/make_workload_golden.py joint8)."""
+    import bench
+    import astrophot_b200 as ap
+    fix = dict(np.load(os.path.join(ROOT, "tests", "golden", "joint8_lm.npz")))
+    ap.AP_config.ap_device = "cuda:0"
+    size = 160
+    truth = []
+    for b in range(bench.C4_BANDS):
+        full = bench.build_c4(ap, None, size=size)
+        truth.append(list(full.models.values())[b]().data.cpu().numpy())
+    np.testing.assert_allclose([t.sum() for t in truth], fix["truth_sum"], rtol=1e-11)
+    model = bench.build_c4(ap, [bench.make_data(t, 10 + b) for b, t in enumerate(truth)], size=size)
+    x0 = bench.start_state(model.parameters.vector_representation().numpy(), scale=bench.start_scale("c4"))
+    np.testing.assert_allclose(x0, fix["x0"], rtol=0, atol=0)
+    assert len(x0) == 13
+    n = len(fix["loss"]) - 1
+    res = ap.fit.LM(model, initial_state=x0, max_iter=n, relative_tolerance=0.0).fit()
+    np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)
+    np.testing.assert_allclose(res.L_history[: n + 1], fix["L"], rtol=1e-12)
+    np.testing.assert_allclose(np.array(res.lambda_history)[: n + 1], fix["lam"], rtol=1e-8, atol=1e-8)

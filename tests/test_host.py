@@ -30,7 +30,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(cabi.apb_param_t) == 24
     assert C.sizeof(cabi.apb_image_t) == 8 + 8 * 8 + 3 * 8 + 8
     assert C.sizeof(cabi.apb_psf_t) == 24
-    assert C.sizeof(cabi.apb_source_t) == 4 * 40 + 8 * 24 + 8 + 8 * 20 + 4 * 12 + 16
+    assert C.sizeof(cabi.apb_source_t) == 4 * 40 + 8 * 24 + 8 + 8 * 20 + 4 * 12 + 16 + 8 + 16
     assert C.sizeof(cabi.apb_owner_t) == 4 * (6 + 24)
     assert C.sizeof(cabi.apb_opts_t) == 24
     assert C.sizeof(cabi.apb_stats_t) == 8 * (1 + 5 + 2 + 2 + 2 + 10)
