@@ -154,12 +154,19 @@ def _dev_f64(x):
 class Plan:
     """A lowered model tree resident on the device (``apb_plan_t``)."""
 
-    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True, share=None, pooled_integration=False):
+    def __init__(self, scene, queue_capacity=0, conv=None, fused_integration=True, share=None, pooled_integration=False,
+                 fp32=None):
         """``conv``: None (per-source psf_convolve_mode), "direct" or "fft" to force one
         convolution kernel family for every source (tests, benchmarks).
         ``share``: another Plan of the same scene whose device copies of data / weight / mask / PSFs
-        are reused (the forward-only twin LM uses for the concurrent chi^2 pass)."""
+        are reused (the forward-only twin LM uses for the concurrent chi^2 pass).
+        ``fp32``: profile kernels (first pass, mean reference, sub-pixel integration) in single-precision arithmetic;
+        default: ``AP_config.ap_dtype == torch.float32``, the reference's switch (AP_config.py:7)."""
         _require_cuda()
+        if fp32 is None:
+            from . import AP_config
+            fp32 = AP_config.ap_dtype == torch.float32
+        self.fp32 = bool(fp32) and fused_integration
         L = lib()
         self.scene = scene
         self.n_par = scene.n_par
@@ -240,7 +247,7 @@ class Plan:
                 t = self._src_masks[key]
                 c.mask = t.data_ptr()
                 c.mask_rect[:] = [int(s.mask_origin[0]), int(s.mask_origin[1]), int(t.shape[1]), int(t.shape[0])]
-        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4) | (8 if pooled_integration else 0))
+        opts = apb_opts_t(queue_capacity=int(queue_capacity), flags={None: 0, "auto": 0, "direct": 1, "fft": 2}[conv] | (0 if fused_integration else 4) | (8 if pooled_integration else 0) | (16 if self.fp32 else 0))
         owners = getattr(scene, "owners", None)
         if owners:       # models of the whole fit (the scene holds their pieces: lowering.tile_scene / shard_scene)
             otab = (apb_owner_t * len(owners))()

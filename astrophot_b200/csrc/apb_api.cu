@@ -100,6 +100,7 @@ struct apb_plan {
   bool any_threshold = false, all_same_geo = true;
   int max_depth = 1;
   int NVp_grad = 1;
+  bool fp32 = false;               // profile kernels in single precision (opts.flags bit 4; AP_config.ap_dtype = float32)
   bool use_coop = false;           // fused integration kernel (k_integrate) instead of per-depth launches
   int refine_lanes = 16;           // lanes sharing one queue entry
   int integrate_grid[2] = {148 * 4, 148 * 3};   // [grad] persistent CTAs of k_integrate (one resident wave)
@@ -394,6 +395,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     opts = &opts_env;
   }
   const int conv_force = opts ? (opts->flags & 3) : 0;   // 1: direct everywhere, 2: FFT everywhere
+  p->fp32 = opts && (opts->flags & 16);
+  if (p->fp32 && (opts->flags & 4)) PFAIL("single-precision profile kernels need the fused integration (flags bit 2 unset)");
   auto is_aux_img = [&](int ii) { return (img[ii].flags & APB_IMG_AUX) != 0; };
   for (int k = 0; k < n_psf; ++k)
     if (psf[k].source >= 0) {
@@ -1049,8 +1052,13 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     int dev = 0, sms = 148, b0 = 4, b1 = 4;
     PCU(cudaGetDevice(&dev));
     PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate<false>, 128, 0));
-    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate<true>, 128, 0));
+    if (p->fp32) {
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate<false, float>, 128, 0));
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate<true, float>, 128, 0));
+    } else {
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate<false, double>, 128, 0));
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate<true, double>, 128, 0));
+    }
     p->integrate_grid[0] = sms * std::max(1, b0);
     p->integrate_grid[1] = sms * std::max(1, b1);
     // throughput form (k_integrate_pool) for long queues
@@ -1064,8 +1072,13 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     p->pool_ok = g2 * nv <= POOL_CSUM;
     if (const char* e = getenv("APB_POOL_MIN")) p->pool_min = atoi(e);
     if (opts && (opts->flags & 8)) p->pool_min = 0;
-    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate_pool<false>, POOL_B, 0));
-    PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate_pool<true>, POOL_B, 0));
+    if (p->fp32) {
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate_pool<false, float>, POOL_B, 0));
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate_pool<true, float>, POOL_B, 0));
+    } else {
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_integrate_pool<false, double>, POOL_B, 0));
+      PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_integrate_pool<true, double>, POOL_B, 0));
+    }
     p->pool_grid[0] = sms * std::max(1, b0);
     p->pool_grid[1] = sms * std::max(1, b1);
   }
@@ -1151,13 +1164,19 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   }
   if (T.n_tiles) {
     PB(grad ? K_FIRST_G : K_FIRST);
-    if (grad) k_first<true><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
-    else k_first<false><<<T.n_tiles, 256, 0, st>>>(p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
+    // (PROFILE_LAUNCH: the profile kernels exist in fp64 and in fp32 arithmetic, AP_config.ap_dtype)
+#define PROFILE_LAUNCH(K, GRID, BLOCK, ...)                                                        \
+    do {                                                                                           \
+      if (p->fp32) { if (grad) K<true, float><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__); else K<false, float><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__); } \
+      else { if (grad) K<true, double><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__); else K<false, double><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__); }      \
+    } while (0)
+    PROFILE_LAUNCH(k_first, T.n_tiles, 256, p->d_src, p->d_dyn, T.tiles, mode, p->d_stamp, 0);
     LAUNCH_CHECK();
     if (p->any_threshold) {
       if (T.n_mean) {
         PB(K_MEAN);
-        k_mean_partial<<<T.n_chunks, 256, 0, st>>>(p->d_src, p->d_dyn, T.chunks, mode, p->d_stamp, p->d_meanpart);
+        if (p->fp32) k_mean_partial<float><<<T.n_chunks, 256, 0, st>>>(p->d_src, p->d_dyn, T.chunks, mode, p->d_stamp, p->d_meanpart);
+        else k_mean_partial<double><<<T.n_chunks, 256, 0, st>>>(p->d_src, p->d_dyn, T.chunks, mode, p->d_stamp, p->d_meanpart);
         LAUNCH_CHECK();
         PB(K_MEAN);
         k_mean_final<<<ceil_div(T.n_mean, 128), 128, 0, st>>>(p->d_src, p->d_dyn, T.mean_list, T.n_mean, mode, p->d_meanpart);
@@ -1184,14 +1203,12 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
         if (may_pool) CU(cudaMemcpyAsync(&p->h_qlast[mode], p->q.count + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (run_lane && n_max > 0) {
           PB(grad ? K_INTEGRATE_G : K_INTEGRATE);
-          if (grad) k_integrate<true><<<p->integrate_grid[1], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
-          else k_integrate<false><<<p->integrate_grid[0], 128, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
+          PROFILE_LAUNCH(k_integrate, p->integrate_grid[grad ? 1 : 0], 128, p->d_src, p->d_dyn, mode, p->d_stamp, q, p->refine_lanes, n_max);
           LAUNCH_CHECK();
         }
         if (run_pool) {
           PB(grad ? K_POOL_G : K_POOL);
-          if (grad) k_integrate_pool<true><<<p->pool_grid[1], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, p->pool_nv);
-          else k_integrate_pool<false><<<p->pool_grid[0], POOL_B, 0, st>>>(p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, 1);
+          PROFILE_LAUNCH(k_integrate_pool, p->pool_grid[grad ? 1 : 0], POOL_B, p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, grad ? p->pool_nv : 1);
           LAUNCH_CHECK();
         }
       } else {

@@ -127,29 +127,61 @@ __device__ __forceinline__ double sersic_db(double n) {
   return 2 - i2 * (4.0 / 405 + i * (92.0 / 25515 + i * (393.0 / 1148175 - i * (4 * 2194697.0 / 30690717750.0))));
 }
 
+template <int KIND>
+struct KindInfo {};
+template <> struct KindInfo<APB_SERSIC> { static constexpr int NE = 7; };
+template <> struct KindInfo<APB_PLANE_SKY> { static constexpr int NE = 5; };
+template <> struct KindInfo<APB_EXPONENTIAL> { static constexpr int NE = 6; };
+template <> struct KindInfo<APB_GAUSSIAN> { static constexpr int NE = 6; };
+template <> struct KindInfo<APB_MOFFAT> { static constexpr int NE = 7; };
+template <> struct KindInfo<APB_SPLINE> { static constexpr int NE = APB_MAX_ELEM; };
+
+// Arithmetic of the profile kernels: fp64 (table-driven exp / log, apb_math.cuh) or fp32 (the reference's
+// AP_config.ap_dtype = float32: the CUDA single-precision functions, 1-2 ulp).
+template <typename T> struct MT;
+template <> struct MT<double> {
+  static __device__ __forceinline__ double exp(double x) { return apb_exp(x, s_mathtab); }
+  static __device__ __forceinline__ double log(double x) { return apb_log(x, s_mathtab); }
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double rcp(double x) { return apb_rcp(x); }
+  static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+};
+template <> struct MT<float> {
+  static __device__ __forceinline__ float exp(float x) { return expf(x); }
+  static __device__ __forceinline__ float log(float x) { return logf(x); }
+  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+};
+
 // Per-source values of a profile evaluation, held in registers while a thread works on one source (the kernels used to
 // re-read them from the DevSrc / DevDyn tables at every node: a third of the instructions of an evaluation).
-struct PCtx {
-  double c, s, qinv, soft2;   // rotation by -(PA - pi/2), 1/q, softening^2
-  double k0;                  // amplitude constant times the sub-pixel area factor of the cell being integrated
-  double k1, k2, k3, k4, k5, k6;
-  double q;                   // axis ratio (d/dPA)
+template <typename T>
+struct PCtxT {
+  T c, s, qinv, soft2;   // rotation by -(PA - pi/2), 1/q, softening^2
+  T k0;                  // amplitude constant times the sub-pixel area factor of the cell being integrated
+  T k1, k2, k3, k4, k5, k6;
+  T q;                   // axis ratio (d/dPA)
   int radial;
 };
-__device__ __forceinline__ void pctx_load(PCtx& c, const DevSrc& s, const DevDyn& d, double ascale) {
-  c.c = d.c; c.s = d.s; c.qinv = d.qinv; c.soft2 = s.soft2;
-  c.k0 = ascale * d.k[0];
-  c.k1 = d.k[1]; c.k2 = d.k[2]; c.k3 = d.k[3]; c.k4 = d.k[4]; c.k5 = d.k[5]; c.k6 = d.k[6];
-  c.q = d.el[2];
+typedef PCtxT<double> PCtx;
+template <typename T>
+__device__ __forceinline__ void pctx_load(PCtxT<T>& c, const DevSrc& s, const DevDyn& d, double ascale) {
+  c.c = (T)d.c; c.s = (T)d.s; c.qinv = (T)d.qinv; c.soft2 = (T)s.soft2;
+  c.k0 = (T)(ascale * d.k[0]);
+  c.k1 = (T)d.k[1]; c.k2 = (T)d.k[2]; c.k3 = (T)d.k[3]; c.k4 = (T)d.k[4]; c.k5 = (T)d.k[5]; c.k6 = (T)d.k[6];
+  c.q = (T)d.el[2];
   c.radial = s.flags & APB_F_RADIAL;
 }
 
 // softened squared radius: ONE expression for every kernel, so that all of them see the same bits
-__device__ __forceinline__ double r2_of(double xp, double yp, double soft2) { return fma(xp, xp, fma(yp, yp, soft2)); }
+template <typename T>
+__device__ __forceinline__ T r2_of(T xp, T yp, T soft2) { return MT<T>::fma(xp, xp, MT<T>::fma(yp, yp, soft2)); }
 
 // rotated, axis-ratio-scaled offsets (_shared_methods.py:274-307, coordinates.py:5-13).  PSF models are circular: k_prep
 // gives them c = 1, s = 0, 1/q = 1, for which these products are exact.
-__device__ __forceinline__ void rot_coords(const PCtx& c, double X, double Y, double& xp, double& yp) {
+template <typename T>
+__device__ __forceinline__ void rot_coords(const PCtxT<T>& c, T X, T Y, T& xp, T& yp) {
   xp = c.c * X - c.s * Y;
   yp = (c.s * X + c.c * Y) * c.qinv;
 }
@@ -157,8 +189,9 @@ __device__ __forceinline__ void rot_coords(const PCtx& c, double X, double Y, do
 // Value of an analytic profile at squared radius R2 WITHOUT range checks in exp / log: `bad` is raised instead when an
 // argument leaves their fast range (then the value is garbage and the caller redoes it with eval_rot).  Three of these
 // run side by side per thread in the integration kernels; one predicate and one branch serve all of them.
+// (fp32: the library functions cover every argument, `bad` stays false.)
 template <int KIND>
-__device__ __forceinline__ double prof_fast(const PCtx& c, double R2, bool& bad) {
+__device__ __forceinline__ double prof_fast(const PCtxT<double>& c, double R2, bool& bad) {
   if (KIND == APB_SERSIC) {
     const double z = R2 * c.k1;
     const double L2 = apb_log_nc(z, s_mathtab);
@@ -184,107 +217,123 @@ __device__ __forceinline__ double prof_fast(const PCtx& c, double R2, bool& bad)
     return c.k0 * apb_exp_nc(v, s_mathtab);
   }
 }
+template <int KIND>
+__device__ __forceinline__ float prof_fast(const PCtxT<float>& c, float R2, bool& bad) {
+  if (KIND == APB_SERSIC) {
+    const float u = expf(logf(R2 * c.k1) * c.k2);
+    return c.k0 * expf(fmaf(-c.k3, u, c.k3));
+  } else if (KIND == APB_EXPONENTIAL) {
+    return c.k0 * expf(-c.k2 * (sqrtf(R2) * c.k1 - 1.0f));
+  } else if (KIND == APB_GAUSSIAN) {
+    return c.k0 * expf(-0.5f * R2 * c.k1);
+  } else {   // APB_MOFFAT
+    return c.k0 * expf(-c.k2 * logf(1.0f + R2 * c.k1));
+  }
+}
 
 // Brightness at rotated offsets (xp, yp) -- c.k0 carries the sub-pixel area factor -- and optionally dI/d(element) for
 // every element (natural units).  dI must hold the kind's element count.
-template <int KIND, bool GRAD>
-__device__ __forceinline__ double eval_rot(const PCtx& c, const DevSrc& s, const DevDyn& d, double xp, double yp,
-                                           double* __restrict__ dI) {
-  const double R2 = r2_of(xp, yp, c.soft2);
-  double I, dIdR_over_R;  // (dI/dR)/R : multiply by xp, yp pieces to get dI/dX
+template <int KIND, bool GRAD, typename T>
+__device__ __forceinline__ T eval_rot(const PCtxT<T>& c, const DevSrc& s, const DevDyn& d, T xp, T yp,
+                                      T* __restrict__ dI) {
+  typedef MT<T> M;
+  const T LN10 = (T)APB_LN10;
+  const T R2 = r2_of<T>(xp, yp, c.soft2);
+  T I, dIdR_over_R;  // (dI/dR)/R : multiply by xp, yp pieces to get dI/dX
   if (KIND == APB_SERSIC) {
     // k0 = area*10^Ie, k1 = 1/Re^2, k2 = 1/(2n), k3 = b_n, k4 = b'_n, k5 = 1/n, k6 = 1/Re
-    const double L2 = apb_log(R2 * c.k1, s_mathtab);  // 2 ln(R/Re)
-    const double u = apb_exp(L2 * c.k2, s_mathtab);
-    I = c.k0 * apb_exp(fma(-c.k3, u, c.k3), s_mathtab);
+    const T L2 = M::log(R2 * c.k1);  // 2 ln(R/Re)
+    const T u = M::exp(L2 * c.k2);
+    I = c.k0 * M::exp(M::fma(-c.k3, u, c.k3));
     if (GRAD) {
-      const double bu = c.k3 * u;
-      dIdR_over_R = -I * bu * c.k5 * apb_rcp(R2);
-      dI[4] = I * (-c.k4 * (u - 1.0) + bu * (0.5 * L2) * c.k5 * c.k5);
+      const T bu = c.k3 * u;
+      dIdR_over_R = -I * bu * c.k5 * M::rcp(R2);
+      dI[4] = I * (-c.k4 * (u - T(1.0)) + bu * (T(0.5) * L2) * c.k5 * c.k5);
       dI[5] = I * bu * c.k5 * c.k6;
-      dI[6] = APB_LN10 * I;
+      dI[6] = LN10 * I;
     }
   } else if (KIND == APB_EXPONENTIAL) {
     // k0 = area*10^Ie, k1 = 1/Re, k2 = b_1
-    const double R = sqrt(R2);
-    I = c.k0 * apb_exp(-c.k2 * (R * c.k1 - 1.0), s_mathtab);
+    const T R = M::sqrt(R2);
+    I = c.k0 * M::exp(-c.k2 * (R * c.k1 - T(1.0)));
     if (GRAD) {
       dIdR_over_R = -I * c.k2 * c.k1 / R;
       dI[4] = I * c.k2 * R * c.k1 * c.k1;
-      dI[5] = APB_LN10 * I;
+      dI[5] = LN10 * I;
     }
   } else if (KIND == APB_GAUSSIAN) {
     // k0 = area*10^flux/sqrt(2 pi sigma^2), k1 = 1/sigma^2, k2 = 1/sigma
-    I = c.k0 * apb_exp(-0.5 * R2 * c.k1, s_mathtab);
+    I = c.k0 * M::exp(T(-0.5) * R2 * c.k1);
     if (GRAD) {
       dIdR_over_R = -I * c.k1;
       dI[4] = I * (-c.k2 + R2 * c.k1 * c.k2);
-      dI[5] = APB_LN10 * I;
+      dI[5] = LN10 * I;
     }
   } else if (KIND == APB_MOFFAT) {
     // k0 = area*10^I0, k1 = 1/Rd^2, k2 = n, k3 = 1/Rd
-    const double t = 1.0 + R2 * c.k1;
-    const double lt = apb_log(t, s_mathtab);
-    I = c.k0 * apb_exp(-c.k2 * lt, s_mathtab);
+    const T t = T(1.0) + R2 * c.k1;
+    const T lt = M::log(t);
+    I = c.k0 * M::exp(-c.k2 * lt);
     if (GRAD) {
-      dIdR_over_R = -I * c.k2 * 2.0 * c.k1 / t;
+      dIdR_over_R = -I * c.k2 * T(2.0) * c.k1 / t;
       dI[4] = -I * lt;
-      dI[5] = I * c.k2 * 2.0 * R2 * c.k1 * c.k3 / t;
-      dI[6] = APB_LN10 * I;
+      dI[5] = I * c.k2 * T(2.0) * R2 * c.k1 * c.k3 / t;
+      dI[6] = LN10 * I;
     }
   } else {  // APB_SPLINE: k0 = area
-    const double R = sqrt(R2);
+    const T R = M::sqrt(R2);
     const int K = s.n_prof;
     // idx = searchsorted(prof[:-1], R, left) - 1, wrapping -1 -> K-1 (utils/interpolate.py:53)
     int idx = -1;
     for (int k = 0; k < K - 1; ++k)
-      if (s.prof[k] < R) idx = k;
+      if ((T)s.prof[k] < R) idx = k;
     const double* v = d.el + 4;
-    double sv, dsdR;
+    T sv, dsdR;
     if (GRAD)
-      for (int k = 0; k < K; ++k) dI[4 + k] = 0.0;
-    if (R > s.prof[K - 1]) {
-      const double h = s.prof[K - 1] - s.prof[K - 2];
-      const double f = (R - s.prof[K - 2]) / h;
-      sv = v[K - 2] + (R - s.prof[K - 2]) * ((v[K - 1] - v[K - 2]) / h);
-      dsdR = (v[K - 1] - v[K - 2]) / h;
-      I = c.k0 * apb_exp(APB_LN10 * sv, s_mathtab);
+      for (int k = 0; k < K; ++k) dI[4 + k] = T(0.0);
+    if (R > (T)s.prof[K - 1]) {
+      const T h = (T)(s.prof[K - 1] - s.prof[K - 2]);
+      const T f = (R - (T)s.prof[K - 2]) / h;
+      sv = (T)v[K - 2] + (R - (T)s.prof[K - 2]) * ((T)(v[K - 1] - v[K - 2]) / h);
+      dsdR = (T)(v[K - 1] - v[K - 2]) / h;
+      I = c.k0 * M::exp(LN10 * sv);
       if (GRAD) {
-        dI[4 + K - 2] = APB_LN10 * I * (1.0 - f);
-        dI[4 + K - 1] = APB_LN10 * I * f;
+        dI[4 + K - 2] = LN10 * I * (T(1.0) - f);
+        dI[4 + K - 1] = LN10 * I * f;
       }
     } else {
       const int i0 = idx < 0 ? K - 1 : idx;
       const int i1 = idx + 1;
-      const double dx = s.prof[i1] - s.prof[i0];
-      const double t = (R - s.prof[i0]) / dx;
-      const double t2 = t * t, t3 = t2 * t;
-      const double h00 = 1 - 3 * t2 + 2 * t3, h10 = t - 2 * t2 + t3, h01 = 3 * t2 - 2 * t3, h11 = t3 - t2;
-      sv = h00 * v[i0] + h10 * d.spl_m[i0] * dx + h01 * v[i1] + h11 * d.spl_m[i1] * dx;
-      I = c.k0 * apb_exp(APB_LN10 * sv, s_mathtab);
+      const T dx = (T)(s.prof[i1] - s.prof[i0]);
+      const T t = (R - (T)s.prof[i0]) / dx;
+      const T t2 = t * t, t3 = t2 * t;
+      const T h00 = 1 - 3 * t2 + 2 * t3, h10 = t - 2 * t2 + t3, h01 = 3 * t2 - 2 * t3, h11 = t3 - t2;
+      const T v0 = (T)v[i0], v1 = (T)v[i1], m0 = (T)d.spl_m[i0], m1 = (T)d.spl_m[i1];
+      sv = h00 * v0 + h10 * m0 * dx + h01 * v1 + h11 * m1 * dx;
+      I = c.k0 * M::exp(LN10 * sv);
       if (GRAD) {
-        dsdR = ((-6 * t + 6 * t2) * v[i0] + (1 - 4 * t + 3 * t2) * d.spl_m[i0] * dx + (6 * t - 6 * t2) * v[i1] +
-                (-2 * t + 3 * t2) * d.spl_m[i1] * dx) / dx;
-        const double g = APB_LN10 * I;
+        dsdR = ((-6 * t + 6 * t2) * v0 + (1 - 4 * t + 3 * t2) * m0 * dx + (6 * t - 6 * t2) * v1 +
+                (-2 * t + 3 * t2) * m1 * dx) / dx;
+        const T g = LN10 * I;
         dI[4 + i0] += g * h00;
         dI[4 + i1] += g * h01;
         // slopes: m_0 = D_0, m_k = (D_{k-1}+D_k)/2, m_{K-1} = D_{K-2},  D_k = (v_{k+1}-v_k)/h_k
         const int ms[2] = {i0, i1};
-        const double mw_[2] = {g * h10 * dx, g * h11 * dx};
+        const T mw_[2] = {g * h10 * dx, g * h11 * dx};
         for (int q = 0; q < 2; ++q) {
           const int m = ms[q];
-          const double w = mw_[q];
+          const T w = mw_[q];
           if (m == 0) {
-            const double ih = 1.0 / (s.prof[1] - s.prof[0]);
+            const T ih = (T)(1.0 / (s.prof[1] - s.prof[0]));
             dI[4 + 1] += w * ih;
             dI[4 + 0] -= w * ih;
           } else if (m == K - 1) {
-            const double ih = 1.0 / (s.prof[K - 1] - s.prof[K - 2]);
+            const T ih = (T)(1.0 / (s.prof[K - 1] - s.prof[K - 2]));
             dI[4 + K - 1] += w * ih;
             dI[4 + K - 2] -= w * ih;
           } else {
-            const double ia = 0.5 / (s.prof[m] - s.prof[m - 1]);
-            const double ib = 0.5 / (s.prof[m + 1] - s.prof[m]);
+            const T ia = (T)(0.5 / (s.prof[m] - s.prof[m - 1]));
+            const T ib = (T)(0.5 / (s.prof[m + 1] - s.prof[m]));
             dI[4 + m] += w * (ia - ib);
             dI[4 + m - 1] -= w * ia;
             dI[4 + m + 1] += w * ib;
@@ -292,15 +341,15 @@ __device__ __forceinline__ double eval_rot(const PCtx& c, const DevSrc& s, const
         }
       }
     }
-    if (GRAD) dIdR_over_R = APB_LN10 * I * dsdR / R;
+    if (GRAD) dIdR_over_R = LN10 * I * dsdR / R;
   }
   if (GRAD) {
     // dR/dX * R = xp*c + yp*s/q ; dR/dY * R = -xp*s + yp*c/q
     if (c.radial) {
       dI[0] = -dIdR_over_R * xp;
       dI[1] = -dIdR_over_R * yp;
-      dI[2] = 0.0;
-      dI[3] = 0.0;
+      dI[2] = T(0.0);
+      dI[3] = T(0.0);
     } else {
       dI[0] = -dIdR_over_R * (xp * c.c + yp * c.s * c.qinv);
       dI[1] = -dIdR_over_R * (-xp * c.s + yp * c.c * c.qinv);
@@ -313,8 +362,8 @@ __device__ __forceinline__ double eval_rot(const PCtx& c, const DevSrc& s, const
 
 // Evaluate brightness I at plane offset (X, Y) from the centre, scaled by `ascale`
 // (sub-pixel area factor), and optionally dI/d(element) for every element.
-// NE = compile-time element bound for the kind.  dI must hold n_elem doubles.
-template <int KIND, bool GRAD>
+// NE = compile-time element bound for the kind.  dI must hold n_elem doubles.  T: arithmetic of the evaluation.
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, double X, double Y, double ascale,
                                              double* __restrict__ dI) {
   if constexpr (KIND == APB_PLANE_SKY) {
@@ -328,22 +377,23 @@ __device__ __forceinline__ double eval_point(const DevSrc& s, const DevDyn& d, d
     }
     return ascale * (s.area * d.el[2] + X * d.el[3] + Y * d.el[4]);
   } else {
-    PCtx c;
+    PCtxT<T> c;
     pctx_load(c, s, d, ascale);
-    double xp, yp;
-    rot_coords(c, X, Y, xp, yp);
-    return eval_rot<KIND, GRAD>(c, s, d, xp, yp, dI);
+    T xp, yp;
+    rot_coords<T>(c, (T)X, (T)Y, xp, yp);
+    if constexpr (sizeof(T) == sizeof(double)) {
+      return eval_rot<KIND, GRAD, T>(c, s, d, xp, yp, (T*)dI);
+    } else {
+      T g[GRAD ? KindInfo<KIND>::NE : 1];
+      const T I = eval_rot<KIND, GRAD, T>(c, s, d, xp, yp, g);
+      if (GRAD) {
+        const int ne = (KIND == APB_SPLINE) ? s.n_elem : KindInfo<KIND>::NE;
+        for (int e = 0; e < ne; ++e) dI[e] = (double)g[e];
+      }
+      return (double)I;
+    }
   }
 }
-
-template <int KIND>
-struct KindInfo {};
-template <> struct KindInfo<APB_SERSIC> { static constexpr int NE = 7; };
-template <> struct KindInfo<APB_PLANE_SKY> { static constexpr int NE = 5; };
-template <> struct KindInfo<APB_EXPONENTIAL> { static constexpr int NE = 6; };
-template <> struct KindInfo<APB_GAUSSIAN> { static constexpr int NE = 6; };
-template <> struct KindInfo<APB_MOFFAT> { static constexpr int NE = 7; };
-template <> struct KindInfo<APB_SPLINE> { static constexpr int NE = APB_MAX_ELEM; };
 
 // deterministic block reduction (fixed tree), result valid in thread 0
 template <int NT>

@@ -214,82 +214,86 @@ struct Acc {
 //     xp = fma(ax, uxi, fma(ay, uxj, xp0)),   yp = fma(ax, vyi, fma(ay, vyj, yp0))
 // -- the SAME expressions in every kernel and for every split of the nodes over lanes, so that all integration kernels
 // see bit-identical node values (their refinement decisions must agree).
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ double gl_nodes_n(const DevSrc& s, const DevDyn& d, double X, double Y, int n, double scale,
                                              double ascale, int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
-  PCtx c;
+  PCtxT<T> c;
   pctx_load(c, s, d, ascale);
-  double xp0, yp0, uxi, vyi, uxj, vyj;
-  rot_coords(c, X, Y, xp0, yp0);
-  rot_coords(c, s.S[0] * scale, s.S[2] * scale, uxi, vyi);
-  rot_coords(c, s.S[1] * scale, s.S[3] * scale, uxj, vyj);
-  acc.v[0] = 0.0;
-  if (GRAD)
-    for (int e = 0; e < ne; ++e) acc.v[1 + e] = 0.0;
-  double centre = 0.0;
+  T xp0, yp0, uxi, vyi, uxj, vyj;
+  rot_coords<T>(c, (T)X, (T)Y, xp0, yp0);
+  rot_coords<T>(c, (T)(s.S[0] * scale), (T)(s.S[2] * scale), uxi, vyi);
+  rot_coords<T>(c, (T)(s.S[1] * scale), (T)(s.S[3] * scale), uxj, vyj);
   const int nn = n * n, mid = nn / 2;
   if constexpr (!GRAD && KIND != APB_SPLINE) {
     if (n == 3 && kstep == 1) {
       // the default 3x3 rule, all nodes on one lane: a row of three at a time with unchecked exp / log, so that three
       // independent chains are in flight and one range test serves the row (kept rolled: three inlined evaluations
       // are ~250 instructions; nine would crowd the other phases of the integration kernels out of the instruction cache)
-      const double a0 = c_quad.a[3][0], a2 = c_quad.a[3][2];          // a[3][1] == 0
-      const double w0 = c_quad.w[3][0], w1 = c_quad.w[3][1], w2 = c_quad.w[3][2];
-      double tot = 0.0;
+      const T a0 = (T)c_quad.a[3][0], a2 = (T)c_quad.a[3][2];          // a[3][1] == 0
+      const T w0 = (T)c_quad.w[3][0], w1 = (T)c_quad.w[3][1], w2 = (T)c_quad.w[3][2];
+      T tot = T(0.0), centre = T(0.0);
 #pragma unroll 1
       for (int ky = 0; ky < 3; ++ky) {
-        const double ay = c_quad.a[3][ky];
-        const double tx = fma(ay, uxj, xp0), ty = fma(ay, vyj, yp0);
-        const double xa = fma(a0, uxi, tx), ya = fma(a0, vyi, ty);
-        const double xb = fma(a2, uxi, tx), yb = fma(a2, vyi, ty);
+        const T ay = (T)c_quad.a[3][ky];
+        const T tx = MT<T>::fma(ay, uxj, xp0), ty = MT<T>::fma(ay, vyj, yp0);
+        const T xa = MT<T>::fma(a0, uxi, tx), ya = MT<T>::fma(a0, vyi, ty);
+        const T xb = MT<T>::fma(a2, uxi, tx), yb = MT<T>::fma(a2, vyi, ty);
         bool bad = false;
-        double Ia = prof_fast<KIND>(c, r2_of(xa, ya, c.soft2), bad);
-        double Im = prof_fast<KIND>(c, r2_of(tx, ty, c.soft2), bad);
-        double Ib = prof_fast<KIND>(c, r2_of(xb, yb, c.soft2), bad);
+        T Ia = prof_fast<KIND>(c, r2_of<T>(xa, ya, c.soft2), bad);
+        T Im = prof_fast<KIND>(c, r2_of<T>(tx, ty, c.soft2), bad);
+        T Ib = prof_fast<KIND>(c, r2_of<T>(xb, yb, c.soft2), bad);
         if (bad) {   // an argument outside the fast range of exp / log (extreme or non-finite parameters)
-          Ia = eval_rot<KIND, false>(c, s, d, xa, ya, nullptr);
-          Im = eval_rot<KIND, false>(c, s, d, tx, ty, nullptr);
-          Ib = eval_rot<KIND, false>(c, s, d, xb, yb, nullptr);
+          Ia = eval_rot<KIND, false, T>(c, s, d, xa, ya, nullptr);
+          Im = eval_rot<KIND, false, T>(c, s, d, tx, ty, nullptr);
+          Ib = eval_rot<KIND, false, T>(c, s, d, xb, yb, nullptr);
         }
         if (ky == 1) centre = Im;
-        tot = fma(c_quad.w[3][ky], fma(w2, Ib, fma(w1, Im, w0 * Ia)), tot);
+        tot = MT<T>::fma((T)c_quad.w[3][ky], MT<T>::fma(w2, Ib, MT<T>::fma(w1, Im, w0 * Ia)), tot);
       }
-      acc.v[0] = tot;
-      return centre;
+      acc.v[0] = (double)tot;
+      return (double)centre;
     }
   }
-  double dI[GRAD ? NE : 1];
+  T av[(GRAD ? NE : 0) + 1];
+  av[0] = T(0.0);
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) av[1 + e] = T(0.0);
+  T centre = T(0.0);
+  T dI[GRAD ? NE : 1];
   for (int k = k0; k < nn; k += kstep) {
     const int kx = k % n, ky = k / n;
-    const double ax = c_quad.a[n][kx], ay = c_quad.a[n][ky];
-    const double w = c_quad.w[n][kx] * c_quad.w[n][ky];
-    const double xp = fma(ax, uxi, fma(ay, uxj, xp0)), yp = fma(ax, vyi, fma(ay, vyj, yp0));
-    const double I = eval_rot<KIND, GRAD>(c, s, d, xp, yp, dI);
+    const T ax = (T)c_quad.a[n][kx], ay = (T)c_quad.a[n][ky];
+    const T w = (T)c_quad.w[n][kx] * (T)c_quad.w[n][ky];
+    const T xp = MT<T>::fma(ax, uxi, MT<T>::fma(ay, uxj, xp0)), yp = MT<T>::fma(ax, vyi, MT<T>::fma(ay, vyj, yp0));
+    const T I = eval_rot<KIND, GRAD, T>(c, s, d, xp, yp, dI);
     if (k == mid) centre = I;
-    acc.v[0] += I * w;
+    av[0] += I * w;
     if (GRAD)
-      for (int e = 0; e < ne; ++e) acc.v[1 + e] += dI[e] * w;
+      for (int e = 0; e < ne; ++e) av[1 + e] += dI[e] * w;
   }
-  return centre;
+  acc.v[0] = (double)av[0];
+  if (GRAD)
+    for (int e = 0; e < ne; ++e) acc.v[1 + e] = (double)av[1 + e];
+  return (double)centre;
 }
 
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ double gl_nodes(const DevSrc& s, const DevDyn& d, double X, double Y, double scale, double ascale,
                                            int k0, int kstep, Acc<GRAD, KindInfo<KIND>::NE>& acc) {
-  return gl_nodes_n<KIND, GRAD>(s, d, X, Y, s.quad_level, scale, ascale, k0, kstep, acc);
+  return gl_nodes_n<KIND, GRAD, T>(s, d, X, Y, s.quad_level, scale, ascale, k0, kstep, acc);
 }
 
 // Gauss-Legendre n x n over one (sub)pixel, all nodes on the calling thread.
 // acc[0] = integral, acc[1+e] = derivative wrt element e (natural units); returns the centre node.
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ double gl_integrate(const DevSrc& s, const DevDyn& d, double X, double Y, int n,
                                                double scale, double ascale, double* __restrict__ acc) {
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
   Acc<GRAD, NE> a;
-  const double centre = gl_nodes_n<KIND, GRAD>(s, d, X, Y, n, scale, ascale, 0, 1, a);
+  const double centre = gl_nodes_n<KIND, GRAD, T>(s, d, X, Y, n, scale, ascale, 0, 1, a);
   acc[0] = a.v[0];
   if (GRAD)
     for (int e = 0; e < ne; ++e) acc[1 + e] = a.v[1 + e];
@@ -299,7 +303,7 @@ __device__ __forceinline__ double gl_integrate(const DevSrc& s, const DevDyn& d,
 // ----------------------------------------------------------------------------
 // first pass over the stamp region (one 32x8 tile per CTA)
 // ----------------------------------------------------------------------------
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& d, const Geo& g, int i, int j,
                                                  double* __restrict__ stamp, int err_plane) {
   constexpr int NE = KindInfo<KIND>::NE;
@@ -311,7 +315,7 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
   const bool in_e = pi >= g.ex0 && pi < g.ex0 + g.ew && pj >= g.ey0 && pj < g.ey0 + g.eh;
   double acc[(GRAD ? NE : 0) + 1];
   if (s.sampling_mode == APB_SAMPLE_MIDPOINT) {
-    acc[0] = eval_point<KIND, GRAD>(s, d, X, Y, 1.0, acc + 1);
+    acc[0] = eval_point<KIND, GRAD, T>(s, d, X, Y, 1.0, acc + 1);
   } else if (s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
     // mean of the four pixel-corner values (_model_methods.py:124-143); error proxy = curvature, as for midpoint
     double dI[GRAD ? NE : 1];
@@ -321,14 +325,14 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
     for (int a = -1; a <= 1; a += 2)
       for (int b = -1; b <= 1; b += 2) {
         const double ox = 0.5 * b, oy = 0.5 * a;
-        const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy),
+        const double I = eval_point<KIND, GRAD, T>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy),
                                                 1.0, dI);
         acc[0] += 0.25 * I;
         if (GRAD)
           for (int e = 0; e < ne; ++e) acc[1 + e] += 0.25 * dI[e];
       }
   } else if (s.sampling_mode == APB_SAMPLE_QUAD) {
-    const double centre = gl_integrate<KIND, GRAD>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
+    const double centre = gl_integrate<KIND, GRAD, T>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
     base[(long long)err_plane * s.plane_stride] = fabs(acc[0] - centre);
   } else {  // simpsons: 3x3 half-pixel lattice, weights [1 4 1; 4 16 4; 1 4 1]/36 (_model_methods.py:99-109)
     double dI[GRAD ? NE : 1];
@@ -340,7 +344,7 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
       for (int b = -1; b <= 1; ++b) {
         const double w = ((a == 0 ? 4.0 : 1.0) * (b == 0 ? 4.0 : 1.0)) / 36.0;
         const double ox = 0.5 * b, oy = 0.5 * a;
-        const double I = eval_point<KIND, GRAD>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy),
+        const double I = eval_point<KIND, GRAD, T>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy),
                                                 1.0, dI);
         if (a == 0 && b == 0) midv = I;
         acc[0] += w * I;
@@ -358,7 +362,7 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
   }
 }
 
-template <bool GRAD>
+template <bool GRAD, typename T>
 __global__ void __launch_bounds__(256, GRAD ? 2 : 4) k_first(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                const int4* __restrict__ tiles, int mode, double* __restrict__ stamp,
                                                int err_plane_unused) {
@@ -371,11 +375,11 @@ __global__ void __launch_bounds__(256, GRAD ? 2 : 4) k_first(const DevSrc* __res
   if (i >= g.mw || j >= g.mh) return;
   const int errp = s.n_act + 1;
   switch (s.kind) {
-    case APB_SERSIC: first_pass_pixel<APB_SERSIC, GRAD>(s, d, g, i, j, stamp, errp); break;
-    case APB_EXPONENTIAL: first_pass_pixel<APB_EXPONENTIAL, GRAD>(s, d, g, i, j, stamp, errp); break;
-    case APB_GAUSSIAN: first_pass_pixel<APB_GAUSSIAN, GRAD>(s, d, g, i, j, stamp, errp); break;
-    case APB_MOFFAT: first_pass_pixel<APB_MOFFAT, GRAD>(s, d, g, i, j, stamp, errp); break;
-    case APB_SPLINE: first_pass_pixel<APB_SPLINE, GRAD>(s, d, g, i, j, stamp, errp); break;
+    case APB_SERSIC: first_pass_pixel<APB_SERSIC, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+    case APB_EXPONENTIAL: first_pass_pixel<APB_EXPONENTIAL, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+    case APB_GAUSSIAN: first_pass_pixel<APB_GAUSSIAN, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+    case APB_MOFFAT: first_pass_pixel<APB_MOFFAT, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+    case APB_SPLINE: first_pass_pixel<APB_SPLINE, GRAD, T>(s, d, g, i, j, stamp, errp); break;
     case APB_PLANE_SKY: first_pass_pixel<APB_PLANE_SKY, GRAD>(s, d, g, i, j, stamp, errp); break;
     default: break;
   }
@@ -386,21 +390,21 @@ __global__ void __launch_bounds__(256, GRAD ? 2 : 4) k_first(const DevSrc* __res
 // WORKING region, _model_methods.py:151-152).  Two stages, fixed order => deterministic.
 // chunk list: {src, first pixel, n pixels, slot}
 // ----------------------------------------------------------------------------
-template <int KIND>
+template <int KIND, typename T = double>
 __device__ __forceinline__ double first_value(const DevSrc& s, const DevDyn& d, double X, double Y) {
   double acc[1];
-  if (s.sampling_mode == APB_SAMPLE_MIDPOINT) return eval_point<KIND, false>(s, d, X, Y, 1.0, acc);
+  if (s.sampling_mode == APB_SAMPLE_MIDPOINT) return eval_point<KIND, false, T>(s, d, X, Y, 1.0, acc);
   if (s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
     double tot = 0.0;
     for (int a = -1; a <= 1; a += 2)
       for (int b = -1; b <= 1; b += 2) {
         const double ox = 0.5 * b, oy = 0.5 * a;
-        tot += 0.25 * eval_point<KIND, false>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy), 1.0, acc);
+        tot += 0.25 * eval_point<KIND, false, T>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy), 1.0, acc);
       }
     return tot;
   }
   if (s.sampling_mode == APB_SAMPLE_QUAD) {
-    gl_integrate<KIND, false>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
+    gl_integrate<KIND, false, T>(s, d, X, Y, s.quad_init, 1.0, 1.0, acc);
     return acc[0];
   }
   double tot = 0.0;
@@ -408,11 +412,12 @@ __device__ __forceinline__ double first_value(const DevSrc& s, const DevDyn& d, 
     for (int b = -1; b <= 1; ++b) {
       const double w = ((a == 0 ? 4.0 : 1.0) * (b == 0 ? 4.0 : 1.0)) / 36.0;
       const double ox = 0.5 * b, oy = 0.5 * a;
-      tot += w * eval_point<KIND, false>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy), 1.0, acc);
+      tot += w * eval_point<KIND, false, T>(s, d, X + (s.S[0] * ox + s.S[1] * oy), Y + (s.S[2] * ox + s.S[3] * oy), 1.0, acc);
     }
   return tot;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) k_mean_partial(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                       const int4* __restrict__ chunks, int mode,
                                                       const double* __restrict__ stamp, double* __restrict__ part) {
@@ -450,11 +455,11 @@ __global__ void __launch_bounds__(256) k_mean_partial(const DevSrc* __restrict__
       double X, Y;
       pix_coords(s, d, (double)(g.rx0 + i), (double)(g.ry0 + j), X, Y);
       switch (s.kind) {
-        case APB_SERSIC: v += first_value<APB_SERSIC>(s, d, X, Y); break;
-        case APB_EXPONENTIAL: v += first_value<APB_EXPONENTIAL>(s, d, X, Y); break;
-        case APB_GAUSSIAN: v += first_value<APB_GAUSSIAN>(s, d, X, Y); break;
-        case APB_MOFFAT: v += first_value<APB_MOFFAT>(s, d, X, Y); break;
-        case APB_SPLINE: v += first_value<APB_SPLINE>(s, d, X, Y); break;
+        case APB_SERSIC: v += first_value<APB_SERSIC, T>(s, d, X, Y); break;
+        case APB_EXPONENTIAL: v += first_value<APB_EXPONENTIAL, T>(s, d, X, Y); break;
+        case APB_GAUSSIAN: v += first_value<APB_GAUSSIAN, T>(s, d, X, Y); break;
+        case APB_MOFFAT: v += first_value<APB_MOFFAT, T>(s, d, X, Y); break;
+        case APB_SPLINE: v += first_value<APB_SPLINE, T>(s, d, X, Y); break;
         default: break;
       }
     }
@@ -688,7 +693,7 @@ __device__ __forceinline__ void acc_shuffle_sum(const DevSrc& s, Acc<GRAD, KindI
 
 // Whole warp: integral of the cell centred (X, Y) at `depth` (already known to need subdivision)
 // as the sum of its gridding^2 children at depth+1.  Arguments are warp-uniform.  Result in every lane.
-template <int KIND, bool GRAD, int LEVELS_LEFT>
+template <int KIND, bool GRAD, int LEVELS_LEFT, typename T = double>
 __device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int mode, int depth, double X, double Y,
                                            Acc<GRAD, KindInfo<KIND>::NE>& out, int* __restrict__ qcount) {
   constexpr int NE = KindInfo<KIND>::NE;
@@ -718,7 +723,7 @@ __device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int
       const double dy = s.goff[cyi] * pscale;
       cx = X + (s.S[0] * dx + s.S[1] * dy);
       cy = Y + (s.S[2] * dx + s.S[3] * dy);
-      const double centre = gl_nodes<KIND, GRAD>(s, d, cx, cy, scale, ascale, 0, 1, ca);
+      const double centre = gl_nodes<KIND, GRAD, T>(s, d, cx, cy, scale, ascale, 0, 1, ca);
       again = cd < s.max_depth && fabs(ca.v[0] - centre) > thr;
     }
     if constexpr (LEVELS_LEFT > 0) {
@@ -728,7 +733,7 @@ __device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int
         bal &= bal - 1;
         const double bx = __shfl_sync(0xffffffffu, cx, b), by = __shfl_sync(0xffffffffu, cy, b);
         Acc<GRAD, NE> sub;
-        split_cell<KIND, GRAD, LEVELS_LEFT - 1>(s, d, mode, cd, bx, by, sub, qcount);
+        split_cell<KIND, GRAD, LEVELS_LEFT - 1, T>(s, d, mode, cd, bx, by, sub, qcount);
         if (lane == b) ca = sub;
       }
     }
@@ -741,7 +746,7 @@ __device__ __forceinline__ void split_cell(const DevSrc& s, const DevDyn& d, int
 
 // depth 1 of one queue entry by the L lanes of a group.  Stores the result unless the entry must be
 // subdivided; returns that decision (same in every lane of the group).
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ bool depth1_entry(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
                                              double* __restrict__ stamp, int L, int gl, unsigned gmask, bool valid) {
   constexpr int NE = KindInfo<KIND>::NE;
@@ -749,7 +754,7 @@ __device__ __forceinline__ bool depth1_entry(const DevSrc& s, const DevDyn& d, i
   Acc<GRAD, NE> acc;
   double centre = 0.0;
   if (valid) {
-    centre = gl_nodes<KIND, GRAD>(s, d, X, Y, 1.0, 1.0, gl, L, acc);
+    centre = gl_nodes<KIND, GRAD, T>(s, d, X, Y, 1.0, 1.0, gl, L, acc);
   } else {
     acc.v[0] = 0.0;
     if (GRAD)
@@ -772,13 +777,13 @@ __device__ __forceinline__ bool depth1_entry(const DevSrc& s, const DevDyn& d, i
 }
 
 // whole warp: subdivide one depth-1 entry and store its integral
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ void split_and_store(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
                                                 double* __restrict__ stamp, int* __restrict__ qcount) {
   constexpr int NE = KindInfo<KIND>::NE;
   const int ne = (KIND == APB_SPLINE) ? s.n_elem : NE;
   Acc<GRAD, NE> out;
-  split_cell<KIND, GRAD, APB_MAX_DEPTH - 2>(s, d, mode, 1, X, Y, out, qcount);
+  split_cell<KIND, GRAD, APB_MAX_DEPTH - 2, T>(s, d, mode, 1, X, Y, out, qcount);
   if ((threadIdx.x & 31) == 0) {
     double* base = stamp + s.stamp_off + parent;
     base[0] = out.v[0];
@@ -792,18 +797,18 @@ __device__ __forceinline__ void split_and_store(const DevSrc& s, const DevDyn& d
 
 // spline sources carry up to 24 elements per accumulator: kept out of line so that their local
 // arrays do not inflate the register allocation of the analytic profiles
-template <bool GRAD>
+template <bool GRAD, typename T = double>
 __device__ __noinline__ bool depth1_entry_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
                                                  double* __restrict__ stamp, int L, int gl, unsigned gmask, bool valid) {
-  return depth1_entry<APB_SPLINE, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid);
+  return depth1_entry<APB_SPLINE, GRAD, T>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid);
 }
-template <bool GRAD>
+template <bool GRAD, typename T = double>
 __device__ __noinline__ void split_and_store_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int parent,
                                                     double* __restrict__ stamp, int* __restrict__ qcount) {
-  split_and_store<APB_SPLINE, GRAD>(s, d, mode, X, Y, parent, stamp, qcount);
+  split_and_store<APB_SPLINE, GRAD, T>(s, d, mode, X, Y, parent, stamp, qcount);
 }
 
-template <bool GRAD>
+template <bool GRAD, typename T>
 __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn, int mode,
                                                       double* __restrict__ stamp, Queues q, int L, int n_max) {
   const int n = min(q.count[1], q.cap[1]);
@@ -836,11 +841,11 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
       const DevSrc& s = src[si];
       const DevDyn& d = dyn[si];
       switch (s.kind) {
-        case APB_SERSIC: split = depth1_entry<APB_SERSIC, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
-        case APB_EXPONENTIAL: split = depth1_entry<APB_EXPONENTIAL, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
-        case APB_GAUSSIAN: split = depth1_entry<APB_GAUSSIAN, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
-        case APB_MOFFAT: split = depth1_entry<APB_MOFFAT, GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
-        case APB_SPLINE: split = depth1_entry_spline<GRAD>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_SERSIC: split = depth1_entry<APB_SERSIC, GRAD, T>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_EXPONENTIAL: split = depth1_entry<APB_EXPONENTIAL, GRAD, T>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_GAUSSIAN: split = depth1_entry<APB_GAUSSIAN, GRAD, T>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_MOFFAT: split = depth1_entry<APB_MOFFAT, GRAD, T>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
+        case APB_SPLINE: split = depth1_entry_spline<GRAD, T>(s, d, mode, X, Y, parent, stamp, L, gl, gmask, valid); break;
         default: break;
       }
     }
@@ -855,11 +860,11 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
       const DevSrc& s = src[sb];
       const DevDyn& d = dyn[sb];
       switch (s.kind) {
-        case APB_SERSIC: split_and_store<APB_SERSIC, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
-        case APB_EXPONENTIAL: split_and_store<APB_EXPONENTIAL, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
-        case APB_GAUSSIAN: split_and_store<APB_GAUSSIAN, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
-        case APB_MOFFAT: split_and_store<APB_MOFFAT, GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
-        case APB_SPLINE: split_and_store_spline<GRAD>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_SERSIC: split_and_store<APB_SERSIC, GRAD, T>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_EXPONENTIAL: split_and_store<APB_EXPONENTIAL, GRAD, T>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_GAUSSIAN: split_and_store<APB_GAUSSIAN, GRAD, T>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_MOFFAT: split_and_store<APB_MOFFAT, GRAD, T>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
+        case APB_SPLINE: split_and_store_spline<GRAD, T>(s, d, mode, Xb, Yb, pb, stamp, q.count); break;
         default: break;
       }
     }
@@ -888,7 +893,7 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
 #endif
 #define POOL_CSUM 3200    // child integrals held per CTA (doubles)
 
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ bool pool_child(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
                                            double* __restrict__ out, int nv) {
   constexpr int NE = KindInfo<KIND>::NE;
@@ -900,14 +905,14 @@ __device__ __forceinline__ bool pool_child(const DevSrc& s, const DevDyn& d, int
   const double cx = X + (s.S[0] * dx + s.S[1] * dy);
   const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
   Acc<GRAD, NE> ca;
-  const double centre = gl_nodes<KIND, GRAD>(s, d, cx, cy, scale, ascale, 0, 1, ca);
+  const double centre = gl_nodes<KIND, GRAD, T>(s, d, cx, cy, scale, ascale, 0, 1, ca);
   out[0] = ca.v[0];
   if (GRAD)
     for (int e = 0; e < ne && 1 + e < nv; ++e) out[1 + e] = ca.v[1 + e];
   return 2 < s.max_depth && fabs(ca.v[0] - centre) > thr;
 }
 
-template <int KIND, bool GRAD>
+template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ void pool_split_child(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
                                                  double* __restrict__ out, int nv, int* __restrict__ qcount) {
   constexpr int NE = KindInfo<KIND>::NE;
@@ -918,26 +923,26 @@ __device__ __forceinline__ void pool_split_child(const DevSrc& s, const DevDyn& 
   const double cx = X + (s.S[0] * dx + s.S[1] * dy);
   const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
   Acc<GRAD, NE> sub;
-  split_cell<KIND, GRAD, APB_MAX_DEPTH - 3>(s, d, mode, 2, cx, cy, sub, qcount);
+  split_cell<KIND, GRAD, APB_MAX_DEPTH - 3, T>(s, d, mode, 2, cx, cy, sub, qcount);
   if ((threadIdx.x & 31) == 0) {
     out[0] = sub.v[0];
     if (GRAD)
       for (int e = 0; e < ne && 1 + e < nv; ++e) out[1 + e] = sub.v[1 + e];
   }
 }
-template <bool GRAD>
+template <bool GRAD, typename T = double>
 __device__ __noinline__ bool pool_child_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
                                                double* __restrict__ out, int nv) {
-  return pool_child<APB_SPLINE, GRAD>(s, d, mode, X, Y, ch, out, nv);
+  return pool_child<APB_SPLINE, GRAD, T>(s, d, mode, X, Y, ch, out, nv);
 }
-template <bool GRAD>
+template <bool GRAD, typename T = double>
 __device__ __noinline__ void pool_split_child_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
                                                      double* __restrict__ out, int nv, int* __restrict__ qcount) {
-  pool_split_child<APB_SPLINE, GRAD>(s, d, mode, X, Y, ch, out, nv, qcount);
+  pool_split_child<APB_SPLINE, GRAD, T>(s, d, mode, X, Y, ch, out, nv, qcount);
 }
 
 // g2 = largest gridding^2 of the plan, nv = values per child (1, or 1 + largest element count)
-template <bool GRAD>
+template <bool GRAD, typename T>
 __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                                           int mode, double* __restrict__ stamp, Queues q,
                                                                           int n_min, int g2, int nv) {
@@ -980,11 +985,11 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
       bool split = false;
       const unsigned me = 1u << lane;
       switch (s.kind) {
-        case APB_SERSIC: split = depth1_entry<APB_SERSIC, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
-        case APB_EXPONENTIAL: split = depth1_entry<APB_EXPONENTIAL, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
-        case APB_GAUSSIAN: split = depth1_entry<APB_GAUSSIAN, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
-        case APB_MOFFAT: split = depth1_entry<APB_MOFFAT, GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
-        case APB_SPLINE: split = depth1_entry_spline<GRAD>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_SERSIC: split = depth1_entry<APB_SERSIC, GRAD, T>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_EXPONENTIAL: split = depth1_entry<APB_EXPONENTIAL, GRAD, T>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_GAUSSIAN: split = depth1_entry<APB_GAUSSIAN, GRAD, T>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_MOFFAT: split = depth1_entry<APB_MOFFAT, GRAD, T>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
+        case APB_SPLINE: split = depth1_entry_spline<GRAD, T>(s, d, mode, X, Y, parent, stamp, 1, 0, me, valid); break;
         default: break;
       }
       if (split) list1[atomicAdd(&s_nf1, 1)] = tid;
@@ -1008,11 +1013,11 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
         double* out = csum + (long long)c * nv;
         bool again = false;
         switch (s.kind) {
-          case APB_SERSIC: again = pool_child<APB_SERSIC, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
-          case APB_EXPONENTIAL: again = pool_child<APB_EXPONENTIAL, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
-          case APB_GAUSSIAN: again = pool_child<APB_GAUSSIAN, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
-          case APB_MOFFAT: again = pool_child<APB_MOFFAT, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
-          case APB_SPLINE: again = pool_child_spline<GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_SERSIC: again = pool_child<APB_SERSIC, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_EXPONENTIAL: again = pool_child<APB_EXPONENTIAL, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_GAUSSIAN: again = pool_child<APB_GAUSSIAN, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_MOFFAT: again = pool_child<APB_MOFFAT, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
+          case APB_SPLINE: again = pool_child_spline<GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv); break;
           default: break;
         }
         if (again) list2[atomicAdd(&s_nf2, 1)] = (unsigned short)c;
@@ -1029,11 +1034,11 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
         const DevDyn& d = dyn[eS[e]];
         double* out = csum + (long long)c * nv;
         switch (s.kind) {
-          case APB_SERSIC: pool_split_child<APB_SERSIC, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
-          case APB_EXPONENTIAL: pool_split_child<APB_EXPONENTIAL, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
-          case APB_GAUSSIAN: pool_split_child<APB_GAUSSIAN, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
-          case APB_MOFFAT: pool_split_child<APB_MOFFAT, GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
-          case APB_SPLINE: pool_split_child_spline<GRAD>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_SERSIC: pool_split_child<APB_SERSIC, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_EXPONENTIAL: pool_split_child<APB_EXPONENTIAL, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_GAUSSIAN: pool_split_child<APB_GAUSSIAN, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_MOFFAT: pool_split_child<APB_MOFFAT, GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
+          case APB_SPLINE: pool_split_child_spline<GRAD, T>(s, d, mode, eX[e], eY[e], ch, out, nv, q.count); break;
           default: break;
         }
       }

@@ -730,7 +730,7 @@ def measure(wl, args, ctx, main=True):
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic",
         "config": {"workload": workload_text(wl, n_bands, world),
                    "l2": "256 MB buffer written between timed iterations (outside the event pairs)",
@@ -822,6 +822,10 @@ def run_ours(args):
     from astrophot_b200 import cabi
 
     ap.AP_config.ap_device = f"cuda:{local}"
+    if args.dtype == "f32":
+        # the reference's switch (AP_config.py:7): images in fp32, profile kernels in fp32 arithmetic; the convolution
+        # planes and the normal equations stay fp64
+        ap.AP_config.ap_dtype = torch.float32
     dev = torch.device("cuda", local)
     main_wl = args.workload or default_workload(world)
     extras = []
@@ -890,6 +894,9 @@ def main():
                           "`other_workloads`.  c2 = config[1]; c3s / c3t = 1024^2 / 512^2 scale models of c3; c4 = config[3], "
                           "8-band joint fit on 2048^2 (strong scaling, 8/N bands per GPU); c5 = config[4], 16384^2 mosaic with "
                           "10000 galaxies, c5s / c5t its 2048^2 / 512^2 scale models")
+    ap_.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                     help="f32: AP_config.ap_dtype = float32 -- the profile kernels (first pass, sub-pixel integration) "
+                          "compute in single precision (parity bar 1e-5); default f64, the metric's precision")
     ap_.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap_.add_argument("--no-extras", action="store_true", help="only the headline workload")
     ap_.add_argument("--conv", default=None, choices=["direct", "fft"],

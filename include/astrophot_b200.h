@@ -139,7 +139,10 @@ typedef struct {
   int64_t queue_capacity; /* entries per refinement level; 0 = automatic (grown by apb_plan_reserve) */
   int32_t flags;          /* bits 0-1: APB_CONV_* override for every source; bit 2: per-depth
                              refinement launches instead of the fused k_integrate; bit 3: pooled
-                             (throughput) integration kernel whatever the queue length */
+                             (throughput) integration kernel whatever the queue length; bit 4: the profile
+                             kernels (first pass, mean reference, sub-pixel integration) compute in fp32 --
+                             the reference's AP_config.ap_dtype = torch.float32 (AP_config.py:7); pixel
+                             offsets from the source centre are still formed in fp64, planes stay fp64 */
   int32_t n_owners;       /* 0: every source is its own owner */
   const apb_owner_t *owners;
 } apb_opts_t;

@@ -1,2 +1,2 @@
-# GPU parity tests only (optionally -k expr)
-timeout 1500 python -m pytest tests -x -q -m gpu ${1:+-k "$1"} 2>&1 | tail -${TAILN:-30}
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -30

@@ -176,7 +176,7 @@ def test_mosaic_scale_model_lm_history_matches_the_reference_itself():
 
 def test_eight_band_joint_fit_lm_history_matches_the_reference_itself():
     """BASELINE config[3] at 160^2 per band -- 8 bands in a Target_Image_List, centre / q / PA / n / Re shared, per-band Ie
-    and Gaussian PSF, P = 13 -- against astrophot.fit.LM on the same seeded inputs (oracle/make_workload_golden.py joint8)."""
+    and Gaussian PSF, P = 14 -- against astrophot.fit.LM on the same seeded inputs (oracle/make_workload_golden.py joint8)."""
     import bench
     import astrophot_b200 as ap
     fix = dict(np.load(os.path.join(ROOT, "tests", "golden", "joint8_lm.npz")))
@@ -190,7 +190,7 @@ def test_eight_band_joint_fit_lm_history_matches_the_reference_itself():
     model = bench.build_c4(ap, [bench.make_data(t, 10 + b) for b, t in enumerate(truth)], size=size)
     x0 = bench.start_state(model.parameters.vector_representation().numpy(), scale=bench.start_scale("c4"))
     np.testing.assert_allclose(x0, fix["x0"], rtol=0, atol=0)
-    assert len(x0) == 13
+    assert len(x0) == 14            # centre (2), q, PA, n, Re shared + 8 x Ie
     n = len(fix["loss"]) - 1
     res = ap.fit.LM(model, initial_state=x0, max_iter=n, relative_tolerance=0.0).fit()
     np.testing.assert_allclose(res.loss_history[: n + 1], fix["loss"], rtol=1e-8)

@@ -583,8 +583,8 @@ def test_covariance_and_uncertainty_match_reference(name):
 
 
 def test_float32_images_are_accepted_and_returned():
-    """AP_config.ap_dtype = float32 (AP_config.py:7): images come in and go out as fp32; the kernels compute in
-    fp64 whatever the image dtype, so the fp32 bar of the north star (1e-5 of the image scale) is met with margin."""
+    """AP_config.ap_dtype = float32 (AP_config.py:7): images come in and go out as fp32 and the profile kernels compute
+    in fp32; the fp32 bar of the north star is 1e-5 of the image scale."""
     fix = load_golden("psf_sersic")
     old = ap.AP_config.ap_dtype
     ap.AP_config.ap_dtype = torch.float32
@@ -593,9 +593,59 @@ def test_float32_images_are_accepted_and_returned():
         assert model.target.data.dtype == torch.float32
         img = model()
         assert img.data.dtype == torch.float32
-        assert rel_err(img.data.double().cpu().numpy(), fix["img0"]) < 1e-6
+        assert rel_err(img.data.double().cpu().numpy(), fix["img0"]) < 1e-5
         res = ap.fit.LM(model, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0).fit()
-        np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-5)
+        np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-4)
+    finally:
+        ap.AP_config.ap_dtype = old
+
+
+F32_SCENES = ["c1_sersic", "sersic_sheared", "exponential", "gaussian", "moffat", "spline", "psf_sersic", "group", "crowded",
+              "moffat_psf_model"]
+
+
+@pytest.mark.parametrize("name", F32_SCENES)
+def test_fp32_profile_kernels_match_the_reference_in_fp32(name):
+    """AP_config.ap_dtype = float32 (AP_config.py:7): the profile kernels (first pass, mean reference, sub-pixel
+    integration) compute in single precision.  Held to the REFERENCE run in fp32 (oracle/make_golden_f32.py) and to the
+    fp64 goldens at the north star's fp32 bar, 1e-5 of the image scale; the reference's own fp32 run sits 2e-6 from its
+    fp64 run on these scenes."""
+    from astrophot_b200.cabi import Plan
+    f32, f64 = load_golden(f"f32_{name}"), load_golden(name)
+    model, _ = scenes.build(ap, name)
+    scene, _ = lower(model)
+    p32, p64 = Plan(scene, fp32=True), Plan(scene, fp32=False)
+    assert p32.fp32 and not p64.fp32
+    got = [t.cpu().numpy() for t in p32.sample(f64["x_val"], as_rep=False)]
+    ref64 = [t.cpu().numpy() for t in p64.sample(f64["x_val"], as_rep=False)]
+    differs = False
+    for i, g in enumerate(got):
+        assert rel_err(g, f32[f"img{i}"].astype(np.float64)) < 1e-5, (name, "reference fp32")
+        assert rel_err(g, f64[f"img{i}"]) < 1e-5, (name, "reference fp64")
+        differs |= bool(np.any(g != ref64[i]))
+    assert differs, "the fp32 plan must not run the fp64 kernels"
+    J = np.concatenate([t.cpu().numpy().reshape(-1, scene.n_par) for t in p32.jacobian(f64["x_rep"], as_rep=True)])
+    ref = f64["jac_rep"]
+    rs = np.maximum(np.abs(ref).max(axis=0), 1e-300)
+    assert np.max(np.abs(J[f64["jac_idx"]] - ref) / rs) < 1e-4, (name, "jacobian vs reference fp64")
+    ref32 = f32["jac_rep"].astype(np.float64)
+    assert np.max(np.abs(J[f32["jac_idx"]] - ref32) / rs) < 1e-3, (name, "jacobian vs reference fp32")
+
+
+def test_fp32_config_switch_runs_the_fp32_kernels_end_to_end():
+    """The public switch: with ap_dtype = float32 model() and LM run on fp32 plans and stay within the fp32 bar."""
+    fix = load_golden("psf_sersic")
+    old = ap.AP_config.ap_dtype
+    ap.AP_config.ap_dtype = torch.float32
+    try:
+        model, _ = scenes.build(ap, "psf_sersic", data=golden_data(fix))
+        img = model()
+        assert img.data.dtype == torch.float32
+        assert rel_err(img.data.double().cpu().numpy(), fix["img0"]) < 1e-5
+        lm = ap.fit.LM(model, initial_state=fix["x0"], max_iter=5, relative_tolerance=0.0)
+        assert lm.plan.fp32
+        res = lm.fit()
+        np.testing.assert_allclose(res.loss_history[:4], fix["loss_history"][:4], rtol=1e-4)
     finally:
         ap.AP_config.ap_dtype = old
 
