@@ -524,27 +524,22 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         const int Nx = fft_len(g.ew), Ny = fft_len(g.eh);
         // shared-memory sequences are skewed (FPAD): i -> i + i/16
         const int ldx = Nx + Nx / 16 + 1, ldy0 = Ny + Ny / 16 + 1;
-        // columns per CTA: as many as keep two CTAs per SM resident (<= 110 KB), at least one
+        // columns per CTA: as many as keep two CTAs per SM resident (<= 112 KB each: landing / ping buffer, pong buffer,
+        // PSF-spectrum tile), at least one
         // (APB_FFT_COL_KB / APB_FFT_NF_MAX / APB_FFT_NT_COLS / APB_FFT_NT_ROWS: tuning knobs for experiments)
         const char* ekb = getenv("APB_FFT_COL_KB");
-        const size_t col_kb = ekb ? (size_t)atoi(ekb) : 110;
+        const size_t col_kb = ekb ? (size_t)atoi(ekb) : 112;
+        auto col_need = [&](int n) { return (size_t)(2 * n * ldy0 + n * Ny) * sizeof(cpx); };
         int nc = 8;
-        while (nc > 1 && (size_t)(2 * nc * (ldy0 + 8)) * sizeof(cpx) > col_kb * 1024) nc /= 2;
+        while (nc > 1 && col_need(nc) > col_kb * 1024) nc /= 2;
         // row transforms per CTA (each carries two real rows)
         const char* enf = getenv("APB_FFT_NF_MAX");
         int nf = std::max(1, std::min(enf ? atoi(enf) : 16, 4096 / Nx));
         while (nf > 1 && (size_t)(2 * nf * ldx) * sizeof(cpx) > 110 * 1024) --nf;
         if (const char* e = getenv("APB_FFT_NT_COLS")) p->fft_nt_cols = atoi(e);
         if (const char* e = getenv("APB_FFT_NT_ROWS")) p->fft_nt_rows = atoi(e);
-        // pad the column tile so that a quarter-warp of the transposing load hits 8 distinct 16-byte banks
-        int pad = 0, best_conf = 1 << 30;
-        for (int pd = 0; pd < 8; ++pd) {
-          int cnt[8] = {0}, conf = 0;
-          for (int l = 0; l < 8; ++l) cnt[((l % nc) * (ldy0 + pd) + l / nc) & 7]++;
-          for (int k = 0; k < 8; ++k) conf = std::max(conf, cnt[k]);
-          if (conf < best_conf) { best_conf = conf; pad = pd; }
-        }
-        const size_t col_bytes = (size_t)(2 * nc * (ldy0 + pad)) * sizeof(cpx);
+        const int pad = 0;     // (the tile arrives by bulk copy: no transposing load whose banks would need a pad)
+        const size_t col_bytes = col_need(nc);
         const size_t row_bytes = (size_t)(2 * nf * ldx) * sizeof(cpx);
         const bool fits = col_bytes <= 227 * 1024 && row_bytes <= 227 * 1024;
         if (fits) {
@@ -552,9 +547,10 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           s.fftx = get_desc(Nx); s.ffty = get_desc(Ny);
           s.fft_nx = Nx; s.nxh = Nx / 2 + 1; s.nxp = (s.nxh + 3) & ~3;
           s.fft_nf = nf; s.fft_nc = nc; s.fft_ld = ldy0 + pad;
-          s.specA_off = spec_total; spec_total += (long long)(1 + s.n_act) * g.eh * s.nxp;
-          s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.oh * s.nxp;
-          s.specK_off = spec_total; spec_total += (3LL + s.n_pp) * s.sph * s.nxp;
+          // column-major spectra (apb_fft.cuh): a column is eh / oh / sph / Ny consecutive complex numbers
+          s.specA_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.nxh * g.eh;
+          s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.nxh * s.oh;
+          s.specK_off = spec_total; spec_total += (3LL + s.n_pp) * s.nxh * s.sph;
           s.specKT_off = spec_total; spec_total += (3LL + s.n_pp) * s.nxh * Ny;
           p->fft_smem_rows = std::max(p->fft_smem_rows, row_bytes);
           p->fft_smem_cols = std::max(p->fft_smem_cols, col_bytes);

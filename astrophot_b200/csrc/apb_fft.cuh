@@ -196,7 +196,7 @@ APB_HD void twiddle_powers(cpx w1, cpx* w) {
 // `in`, applies the stage twiddles and the in-register DFT.  Ns = product of the radices of the
 // stages already done, j in [0, N/R).  Returns the index of output 0; output r goes to o + r*Ns
 // (both through FPAD).  tw = exp(-2 pi i k / N) table (global memory, read through L1).
-template <int R, bool INV>
+template <int R, bool INV, bool PLAIN = false>
 APB_HD int fft_bfly(const cpx* __restrict__ in, int N, int Ns, int j, const cpx* __restrict__ tw, cpx* v) {
   const int nb = N / R;
   int k, jq;
@@ -208,7 +208,7 @@ APB_HD int fft_bfly(const cpx* __restrict__ in, int N, int Ns, int j, const cpx*
     k = j - jq;
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) v[r] = in[FPAD(j + r * nb)];
+  for (int r = 0; r < R; ++r) v[r] = in[PLAIN ? (j + r * nb) : FPAD(j + r * nb)];
   if (k) {
     cpx w1 = tw[k * (N / (Ns * R))];
     if (INV) w1.y = -w1.y;
@@ -236,18 +236,45 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- bulk asynchronous copies (TMA, SASS UBLKCP) completing on an mbarrier -------------------------------------
+// One thread arms the barrier with the byte count and issues the copies; every thread of the CTA waits on the barrier
+// before it reads the landing buffer.  Global source, shared destination and size are multiples of 16 bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
 // One stage for nf sequences: in + f*ld -> out + f*ld, one barrier.  A thread keeps one butterfly
 // (R complex values) in registers at a time.  noinline on purpose: inlined into the stage loop the
 // compiler hoists every radix's fp64 constants out of the loop and spills ~1 KB per thread; as
 // separate functions each radix gets its own allocation (<= 112 registers, no spills).
-template <int R, bool INV>
+// PLAIN: the input sequences are stored without the skew (the landing buffer of a bulk copy); the output always has it.
+template <int R, bool INV, bool PLAIN = false>
 __device__ __noinline__ void fft_stage(const cpx* __restrict__ in, cpx* __restrict__ out, int nf, int ld, int N, int Ns,
                                        const cpx* __restrict__ tw) {
   const int nb = N / R, total = nf * nb;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int f = idx / nb, j = idx - f * nb;
     cpx v[R];
-    const int o = fft_bfly<R, INV>(in + f * ld, N, Ns, j, tw, v);
+    const int o = fft_bfly<R, INV, PLAIN>(in + f * ld, N, Ns, j, tw, v);
 #pragma unroll
     for (int r = 0; r < R; ++r) out[f * ld + FPAD(o + r * Ns)] = v[r];
   }
@@ -257,12 +284,29 @@ __device__ __noinline__ void fft_stage(const cpx* __restrict__ in, cpx* __restri
 // nf FFTs of length D.N at a + f*ld (ping-pong partner b), unnormalised.  All threads of the CTA
 // take part; returns the buffer that holds the result.
 template <bool INV>
-__device__ __forceinline__ cpx* fft_run(cpx* a, cpx* b, int nf, int ld, const FftDesc& D, const cpx* __restrict__ tw) {
+__device__ __forceinline__ cpx* fft_run(cpx* a, cpx* b, int nf, int ld, const FftDesc& D, const cpx* __restrict__ tw,
+                                        bool plain_first = false) {
   int Ns = 1;
   const int N = D.N;
 #pragma unroll 1
   for (int st = 0; st < D.nstage; ++st) {
     const int R = D.radix[st];
+    if (st == 0 && plain_first) {
+      switch (R) {
+        case 16: fft_stage<16, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+        case 9: fft_stage<9, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+        case 8: fft_stage<8, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+        case 5: fft_stage<5, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+        case 4: fft_stage<4, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+        case 3: fft_stage<3, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+        default: fft_stage<2, INV, true>(a, b, nf, ld, N, Ns, tw); break;
+      }
+      cpx* t = a;
+      a = b;
+      b = t;
+      Ns *= R;
+      continue;
+    }
     switch (R) {
       case 16: fft_stage<16, INV>(a, b, nf, ld, N, Ns, tw); break;
       case 9: fft_stage<9, INV>(a, b, nf, ld, N, Ns, tw); break;
@@ -284,8 +328,9 @@ __device__ __forceinline__ cpx* fft_run(cpx* a, cpx* b, int nf, int ld, const Ff
 // pass A: real rows -> half spectra.  work: {src, code, row0, nrows};  code >= 0: plane `code` of
 // the source's stamp (evaluation region, zero-padded to N);  code < 0: shifted PSF plane -1-code,
 // rotated so that its centre sits at column 0.
-// spectra layout (cpx): image planes  specA + ((plane*eh + row) * nxp + kx)
-//                       PSF planes    specK + ((k*sph + a) * nxp + kx)
+// spectra layout (cpx), COLUMN-major so that the column pass moves whole columns with bulk copies:
+//                       image planes  specA + ((plane*nxh + kx) * eh + row)
+//                       PSF planes    specK + ((k*nxh + kx) * sph + a)
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
                                                   const cpx* __restrict__ twid, const int4* __restrict__ work, int mode,
@@ -298,7 +343,7 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ 
   const Geo& g = s.geo[mode];
   if (threadIdx.x == 0) D = descs[s.fftx];
   __syncthreads();
-  const int N = D.N, nxh = N / 2 + 1, nxp = s.nxp;
+  const int N = D.N, nxh = N / 2 + 1;
   const int nf = (wk.w + 1) / 2;
   const int ld = FPAD(N) + 1;
   const cpx* tw = twid + D.tw_off;
@@ -306,21 +351,23 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ 
   cpx* b = a + nf * ld;
   const bool is_psf = wk.y < 0;
   const double* base;
-  int rstride, valid_w, xoff;
+  int rstride, valid_w, xoff, col_len;
   cpx* dst;
   if (!is_psf) {
     base = stamp + s.stamp_off + (long long)wk.y * s.plane_stride + (long long)(g.ey0 - g.my0) * g.mw + (g.ex0 - g.mx0);
     rstride = g.mw;
     valid_w = g.ew;
     xoff = 0;
-    dst = spec + s.specA_off + ((long long)wk.y * g.eh) * nxp;
+    col_len = g.eh;
+    dst = spec + s.specA_off + ((long long)wk.y * nxh) * g.eh;
   } else {
     const int kp = -1 - wk.y;
     base = psfst + s.psf_off + (long long)kp * s.spw * s.sph;
     rstride = s.spw;
     valid_w = s.spw;
     xoff = (s.spw - 1) / 2;
-    dst = spec + s.specK_off + ((long long)kp * s.sph) * nxp;
+    col_len = s.sph;
+    dst = spec + s.specK_off + ((long long)kp * nxh) * s.sph;
   }
   for (int idx = threadIdx.x; idx < nf * N; idx += blockDim.x) {
     const int f = idx / N, x = idx - f * N;
@@ -335,13 +382,16 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ 
   cp_async_wait_all();
   __syncthreads();
   const cpx* r = fft_run<false>(a, b, nf, ld, D, tw);
+  // thread (k, f), f fastest: the two rows of transform f are neighbours in column k, so a warp writes runs of
+  // 2 nf x 16 bytes (ld is odd: the strided shared-memory reads hit distinct banks)
   for (int idx = threadIdx.x; idx < nf * nxh; idx += blockDim.x) {
-    const int f = idx / nxh, k = idx - f * nxh;
+    const int k = idx / nf, f = idx - k * nf;
     const int kn = k ? N - k : 0;
     const cpx zk = r[f * ld + FPAD(k)], zn = r[f * ld + FPAD(kn)];
     const int r0 = wk.z + 2 * f;
-    dst[(long long)r0 * nxp + k] = cpx{0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y)};
-    if (2 * f + 1 < wk.w) dst[(long long)(r0 + 1) * nxp + k] = cpx{0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x)};
+    cpx* col = dst + (long long)k * col_len;
+    col[r0] = cpx{0.5 * (zk.x + zn.x), 0.5 * (zk.y - zn.y)};
+    if (2 * f + 1 < wk.w) col[r0 + 1] = cpx{0.5 * (zk.y + zn.y), -0.5 * (zk.x - zn.x)};
   }
 }
 
@@ -349,48 +399,74 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows(const DevSrc* __restrict__ 
 // pass B: columns.  jobs: {src, in_plane | -1-k (PSF plane k), kernel, out_plane};
 // work: {job, kx0, ncols, 0}.  Image job: forward column FFT of `ncols` columns, multiply by the
 // PSF spectrum, inverse column FFT, keep the rows of the output window:
-//     specB + ((out_plane*oh + y) * nxp + kx)
-// PSF job: forward column FFT only, stored column-major:  specKT + ((k*nxh + kx) * Ny + ky)
+//     specB + ((out_plane*nxh + kx) * oh + y)
+// PSF job: forward column FFT only:  specKT + ((k*nxh + kx) * Ny + ky)
+// Every column is contiguous in global memory (pass A writes column-major), so a tile is moved by bulk asynchronous
+// copies (TMA): one thread issues them -- the input columns on one mbarrier, the PSF-spectrum columns on a second --
+// and the PSF spectrum arrives under the forward transform instead of stalling the multiply.
+// shared memory: A = landing buffer (plain layout) and ping buffer, B = pong buffer, KT = PSF-spectrum tile.
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) k_fft_cols(const DevSrc* __restrict__ src, const FftDesc* __restrict__ descs,
                                                   const cpx* __restrict__ twid, const int4* __restrict__ jobs,
                                                   const int4* __restrict__ work, int mode, cpx* __restrict__ spec) {
   extern __shared__ cpx fsm[];
   __shared__ FftDesc D;
+  __shared__ __align__(8) unsigned long long bar_in, bar_kt;
   const int4 wk = work[blockIdx.x];
   const int4 jb = jobs[wk.x];
   const DevSrc& s = src[jb.x];
   const Geo& g = s.geo[mode];
-  if (threadIdx.x == 0) D = descs[s.ffty];
+  if (threadIdx.x == 0) {
+    D = descs[s.ffty];
+    mbar_init(&bar_in, 1);
+    mbar_init(&bar_kt, 1);
+    mbar_init_fence();
+  }
   __syncthreads();
-  const int N = D.N, nxp = s.nxp, nxh = s.nxh;
+  const int N = D.N, nxh = s.nxh;
   const int nc = wk.z, kx0 = wk.y;
-  const int ld = s.fft_ld;  // skewed length + pad: the transposing tile load/store is bank-conflict free
+  const int ld = s.fft_ld;  // skewed length + pad
   const cpx* tw = twid + D.tw_off;
   cpx* a = fsm;
   cpx* b = a + s.fft_nc * ld;
+  cpx* ktile = b + s.fft_nc * ld;     // nc x N, plain
   const bool is_psf = jb.y < 0;
   const cpx* in;
   int rows_valid, yoff;
   if (!is_psf) {
-    in = spec + s.specA_off + ((long long)jb.y * g.eh) * nxp + kx0;
+    in = spec + s.specA_off + ((long long)jb.y * nxh + kx0) * g.eh;
     rows_valid = g.eh;
     yoff = 0;
   } else {
-    in = spec + s.specK_off + ((long long)(-1 - jb.y) * s.sph) * nxp + kx0;
+    in = spec + s.specK_off + ((long long)(-1 - jb.y) * nxh + kx0) * s.sph;
     rows_valid = s.sph;
     yoff = (s.sph - 1) / 2;
   }
-  for (int idx = threadIdx.x; idx < nc * N; idx += blockDim.x) {
-    const int y = idx / nc, c = idx - y * nc;
-    int sy = y + yoff;
-    if (sy >= N) sy -= N;
-    const bool v = sy < rows_valid;
-    cp_async16(&a[c * ld + FPAD(y)], v ? in + (long long)sy * nxp + c : in, v ? 16 : 0);
+  // sequence element y <- column element (y + yoff) mod N: elements [yoff, rows_valid) land at [0, rows_valid - yoff),
+  // elements [0, yoff) at [N - yoff, N); everything between is the zero padding
+  if (threadIdx.x == 0) {
+    const unsigned n_hi = (unsigned)(rows_valid - yoff) * 16u, n_lo = (unsigned)yoff * 16u;
+    mbar_expect_tx(&bar_in, (unsigned)nc * (n_hi + n_lo));
+    for (int c = 0; c < nc; ++c) {
+      tma_load_1d(a + c * ld, in + (long long)c * rows_valid + yoff, n_hi, &bar_in);
+      if (n_lo) tma_load_1d(a + c * ld + (N - yoff), in + (long long)c * rows_valid, n_lo, &bar_in);
+    }
+    if (!is_psf) {
+      const cpx* kt = spec + s.specKT_off + ((long long)jb.z * nxh + kx0) * N;
+      mbar_expect_tx(&bar_kt, (unsigned)nc * (unsigned)N * 16u);
+      for (int c = 0; c < nc; ++c) tma_load_1d(ktile + c * N, kt + (long long)c * N, (unsigned)N * 16u, &bar_kt);
+    }
   }
-  cp_async_wait_all();
-  __syncthreads();
-  cpx* r = fft_run<false>(a, b, nc, ld, D, tw);
+  {
+    const int z0 = rows_valid - yoff, nz = N - rows_valid;
+    for (int idx = threadIdx.x; idx < nc * nz; idx += blockDim.x) {
+      const int c = idx / nz, y = z0 + (idx - c * nz);
+      a[c * ld + y] = cpx{0.0, 0.0};
+    }
+  }
+  __syncthreads();          // the zero padding is in place
+  mbar_wait(&bar_in, 0);    // the columns have landed
+  cpx* r = fft_run<false>(a, b, nc, ld, D, tw, true);
   if (is_psf) {
     cpx* kt = spec + s.specKT_off + ((long long)(-1 - jb.y) * nxh + kx0) * N;
     for (int idx = threadIdx.x; idx < nc * N; idx += blockDim.x) {
@@ -399,20 +475,20 @@ __global__ void __launch_bounds__(256, 2) k_fft_cols(const DevSrc* __restrict__ 
     }
     return;
   }
-  const cpx* kt = spec + s.specKT_off + ((long long)jb.z * nxh + kx0) * N;
+  mbar_wait(&bar_kt, 0);
   const double scale = 1.0 / ((double)N * (double)s.fft_nx);
 #pragma unroll 4
   for (int idx = threadIdx.x; idx < nc * N; idx += blockDim.x) {
     const int c = idx / N, y = idx - c * N;
-    const cpx v = c_mul(r[c * ld + FPAD(y)], kt[(long long)c * N + y]);
+    const cpx v = c_mul(r[c * ld + FPAD(y)], ktile[c * N + y]);
     r[c * ld + FPAD(y)] = cpx{v.x * scale, v.y * scale};
   }
   __syncthreads();
   const cpx* z = fft_run<true>(r, r == a ? b : a, nc, ld, D, tw);
-  cpx* out = spec + s.specB_off + ((long long)jb.w * s.oh) * nxp + kx0;
+  cpx* out = spec + s.specB_off + ((long long)jb.w * nxh + kx0) * s.oh;
   for (int idx = threadIdx.x; idx < nc * s.oh; idx += blockDim.x) {
-    const int y = idx / nc, c = idx - y * nc;
-    out[(long long)y * nxp + c] = z[c * ld + FPAD(y + s.by)];
+    const int c = idx / s.oh, y = idx - c * s.oh;
+    out[(long long)c * s.oh + y] = z[c * ld + FPAD(y + s.by)];
   }
 }
 
@@ -428,22 +504,24 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows_inv(const DevSrc* __restric
   const DevSrc& s = src[wk.x];
   if (threadIdx.x == 0) D = descs[s.fftx];
   __syncthreads();
-  const int N = D.N, nxp = s.nxp;
+  const int N = D.N, nxh = s.nxh;
   const int nf = (wk.w + 1) / 2;
   const int ld = FPAD(N) + 1;
   const cpx* tw = twid + D.tw_off;
   cpx* a = fsm;
   cpx* b = a + nf * ld;
-  const cpx* in = spec + s.specB_off + ((long long)wk.y * s.oh) * nxp;
+  const cpx* in = spec + s.specB_off + ((long long)wk.y * nxh) * s.oh;
+  // thread (k, f), f fastest: a warp reads runs of 2 nf x 16 bytes of column kk (column-major spectra)
 #pragma unroll 4
   for (int idx = threadIdx.x; idx < nf * N; idx += blockDim.x) {
-    const int f = idx / N, k = idx - f * N;
+    const int k = idx / nf, f = idx - k * nf;
     const int r0 = wk.z + 2 * f;
     const bool second = 2 * f + 1 < wk.w;
     const bool lo = 2 * k <= N;
     const int kk = lo ? k : N - k;
-    const cpx x1 = in[(long long)r0 * nxp + kk];
-    const cpx x2 = second ? in[(long long)(r0 + 1) * nxp + kk] : cpx{0.0, 0.0};
+    const cpx* col = in + (long long)kk * s.oh;
+    const cpx x1 = col[r0];
+    const cpx x2 = second ? col[r0 + 1] : cpx{0.0, 0.0};
     a[f * ld + FPAD(k)] = lo ? cpx{x1.x - x2.y, x1.y + x2.x} : cpx{x1.x + x2.y, -x1.y + x2.x};
   }
   __syncthreads();
