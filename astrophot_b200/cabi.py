@@ -68,7 +68,7 @@ class apb_kernel_time_t(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
-EXPORTS = ["apb_lm_trial_spec", "apb_plan_set_image_data", "apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
+EXPORTS = ["apb_comm_alloc", "apb_comm_create", "apb_allreduce", "apb_comm_destroy", "apb_lm_trial_spec", "apb_plan_set_image_data", "apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
            "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
 
 _lib = None
@@ -113,6 +113,10 @@ def load_library(path=None):
     L.apb_profile.argtypes = [vp, C.c_int]
     L.apb_profile_read.argtypes = [vp, C.POINTER(apb_kernel_time_t), C.c_int, C.POINTER(C.c_int), C.c_int]
     L.apb_bench_peaks.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.apb_comm_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    L.apb_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    L.apb_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.apb_comm_destroy.argtypes = [C.c_void_p]
     L.apb_last_error.restype = C.c_char_p
     L.apb_version.restype = C.c_int
     for name in EXPORTS:
@@ -409,14 +413,15 @@ class Plan:
         """Length of the block-sparse J^T W J array (0: the plan has no block-sparse form)."""
         return int(self._L.apb_plan_block_doubles(self._h))
 
-    def bind_blocks(self):
+    def bind_blocks(self, extra=0):
         """Torch-owned device array that receives the block-sparse J^T W J of every normal_eq
         ([64 doubles per owner block | diag H]; same layout on every rank of a tile-sharded fit, so a sum
-        all-reduce of it merges the ranks' normal equations).  None if the plan has no block-sparse form."""
+        all-reduce of it merges the ranks' normal equations).  None if the plan has no block-sparse form.
+        ``extra``: doubles appended for the caller (J^T W r rides in the same exchange)."""
         n = int(self._L.apb_plan_block_doubles(self._h))
         if n <= 0:
             return None
-        buf = torch.zeros(n, dtype=torch.float64, device="cuda")
+        buf = torch.zeros(n + int(extra), dtype=torch.float64, device="cuda")
         _check(self._L.apb_plan_bind_blocks(self._h, buf.data_ptr()), "apb_plan_bind_blocks")
         self._keep.append(buf)
         return buf
@@ -446,6 +451,55 @@ class Plan:
                 "overflow": st.overflow, "cum_passes": list(st.cum_passes),
                 "cum_first_pass_evals": list(st.cum_first_pass_evals),
                 "cum_queued": [list(st.cum_queued[k])[1:] for k in range(2)]}
+
+
+class PeerComm:
+    """Sum all-reduce over NVLink peer memory for the ranks of ONE node (``apb_allreduce``): one kernel on the current
+    stream, deterministic rank-order sum.  ``group``: the torch.distributed group whose ranks take part (used once, to
+    gather the cudaIpc handles).  Raises NativeLibraryError if the peers' memory cannot be mapped (ranks on different
+    nodes, no P2P): callers fall back to the NCCL all-reduce."""
+
+    def __init__(self, max_doubles, group=None):
+        import torch.distributed as dist
+        _require_cuda()
+        L = lib()
+        self._L, self._h = L, None
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.max_doubles = int(max_doubles)
+        local = C.c_void_p()
+        handle = (C.c_char * 64)()
+        _check(L.apb_comm_alloc(self.max_doubles, C.byref(local), handle), "apb_comm_alloc")
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
+        h = C.c_void_p()
+        rc = L.apb_comm_create(self.rank, self.world, local, blob, self.max_doubles, C.byref(h))
+        # every rank must agree on whether the communicator exists
+        ok = torch.tensor([1.0 if rc == 0 else 0.0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if rc != 0 or ok.item() == 0.0:
+            msg = L.apb_last_error()
+            if rc == 0:
+                L.apb_comm_destroy(h)
+            raise NativeLibraryError(f"peer-memory communicator unavailable: {msg.decode() if msg else '?'}")
+        self._h = h
+
+    def allreduce(self, t):
+        """In-place sum of the contiguous fp64 CUDA tensor ``t`` over the ranks, on the current stream."""
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous() or t.numel() > self.max_doubles:
+            raise NativeLibraryError("PeerComm.allreduce: contiguous fp64 CUDA tensor of at most max_doubles elements required")
+        _check(self._L.apb_allreduce(self._h, t.data_ptr(), t.numel(), _stream()), "apb_allreduce")
+        return t
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._L.apb_comm_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
 
 def lm_solve(H, g, L, out=None, info=None):

@@ -15,6 +15,7 @@
 #include "apb_image.cuh"
 #include "apb_fft.cuh"
 #include "apb_solve.cuh"
+#include "apb_comm.cuh"
 
 
 static thread_local std::string g_err;
@@ -1689,5 +1690,81 @@ extern "C" int apb_bench_peaks(double* dfma_tflops, double* copy_gbs) {
   CU(cudaFree(b));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  return 0;
+}
+
+// ---- one-node all-reduce over NVLink peer memory (apb_comm.cuh) ------------------------------------------------
+static size_t comm_bytes(size_t slot_doubles) { return 2 * slot_doubles * sizeof(double) + APB_COMM_MAX_RANKS * sizeof(unsigned long long); }
+
+extern "C" int apb_comm_alloc(size_t max_doubles, void** local_out, void* handle_out) {
+  if (!local_out || !handle_out || max_doubles == 0) APB_FAIL("apb_comm_alloc: bad arguments");
+  void* buf = nullptr;
+  CU(cudaMalloc(&buf, comm_bytes(max_doubles)));
+  CU(cudaMemset(buf, 0, comm_bytes(max_doubles)));
+  CU(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, buf));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  *local_out = buf;
+  return 0;
+}
+
+extern "C" int apb_comm_create(int rank, int world, void* local, const void* handles, size_t max_doubles, apb_comm_t** out) {
+  if (!out || !local || !handles) APB_FAIL("apb_comm_create: NULL argument");
+  if (world < 1 || world > APB_COMM_MAX_RANKS || rank < 0 || rank >= world) APB_FAIL("apb_comm_create: bad rank / world");
+  apb_comm* c = new apb_comm();
+  c->rank = rank; c->world = world; c->slot_doubles = max_doubles; c->local = local;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { c->peer[r] = local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)r, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&c->peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      g_err = std::string("apb_comm_create: cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e);
+      for (int q = 0; q < r; ++q) if (q != rank && c->peer[q]) cudaIpcCloseMemHandle(c->peer[q]);
+      delete c;
+      return -2;
+    }
+  }
+  CU(cudaMalloc((void**)&c->done, sizeof(unsigned int)));
+  CU(cudaMemset(c->done, 0, sizeof(unsigned int)));
+  int dev = 0, sms = 148;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  c->grid_max = sms;       // one CTA per SM: always co-resident
+  *out = c;
+  return 0;
+}
+
+extern "C" int apb_allreduce(apb_comm_t* c, double* buf, size_t n, void* stream) {
+  if (!c || !buf) APB_FAIL("apb_allreduce: NULL argument");
+  if (n == 0 || c->world == 1) return 0;
+  if (n > c->slot_doubles) APB_FAIL("apb_allreduce: buffer longer than the exchange slots of this communicator");
+  CommArgs A;
+  memset(&A, 0, sizeof(A));
+  c->seq++;
+  const size_t slot_off = (c->seq & 1) ? c->slot_doubles : 0;
+  for (int r = 0; r < c->world; ++r) {
+    A.slot[r] = (double*)c->peer[r] + slot_off;
+    A.flags[r] = (unsigned long long*)((double*)c->peer[r] + 2 * c->slot_doubles);
+  }
+  A.rank = c->rank; A.world = c->world; A.seq = c->seq; A.done = c->done;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_max, (n + 2047) / 2048));
+  k_allreduce_peer<<<grid, 256, 0, (cudaStream_t)stream>>>(A, buf, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) APB_FAIL(std::string("apb_allreduce launch: ") + cudaGetErrorString(e));
+  g_launches++;
+  return 0;
+}
+
+extern "C" int apb_comm_destroy(apb_comm_t* c) {
+  if (!c) return 0;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->local) cudaFree(c->local);
+  if (c->done) cudaFree(c->done);
+  delete c;
   return 0;
 }

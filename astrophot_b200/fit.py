@@ -154,8 +154,10 @@ class LM(BaseOptimizer):
         # a dense fallback solve is ever needed.
         self._dense = not (self._sparse_solver and P > self._small_solver_max and self.plan.block_doubles() > 0
                            and P > kwargs.get("dense_hess_max", 4096))
-        self._H = torch.empty(P, P, dtype=torch.float64, device=dev) if self._dense else None
-        self._g = torch.empty(P, dtype=torch.float64, device=dev)
+        # J^T W J and J^T W r live in ONE buffer: a sharded fit sums them over the ranks with a single exchange
+        self._Hg = torch.empty(P * P + P if self._dense else P, dtype=torch.float64, device=dev)
+        self._H = self._Hg[: P * P].view(P, P) if self._dense else None
+        self._g = self._Hg[-P:] if P > 0 else self._Hg
         self._c2 = torch.empty(2, dtype=torch.float64, device=dev)
         self._rpp = torch.empty(P, dtype=torch.float64, device=dev)
         self._rec = torch.empty(4, dtype=torch.float64, device=dev)
@@ -215,9 +217,25 @@ class LM(BaseOptimizer):
         self._blk = None
         self._hess_reduced = True
         if self.distributed and self._sparse_solver and P > self._small_solver_max:
-            self._blk = self.plan.bind_blocks()
-            if self._blk is not None:
+            # [blocks | diag H | J^T W r] in one array: one exchange per normal-equation build
+            self._blkg = self.plan.bind_blocks(extra=P)
+            if self._blkg is not None:
+                self._blk = self._blkg[:-P]
+                self._g = self._blkg[-P:]
                 self._hs = torch.empty(P + 2, dtype=torch.float64, device=dev)
+        # the exchange itself: one kernel over NVLink peer memory (apb_allreduce) when every rank of the group can map
+        # the others' memory (one node), NCCL otherwise
+        self._peer = None
+        if self.distributed and kwargs.get("peer_allreduce", True) and torch.cuda.is_available():
+            import os
+            need = max(self._Hg.numel(), (self._blkg.numel() if self._blk is not None else 0), P + 3, 8)
+            if os.environ.get("APB_NO_PEER", "0") in ("", "0") and need * 8 <= (256 << 20):
+                try:
+                    from .cabi import PeerComm
+                    self._peer = PeerComm(need, group=self.group)
+                except Exception as e:      # ranks on several nodes, no P2P: NCCL does it
+                    if self.verbose > 0:
+                        AP_config.ap_logger.info(f"peer-memory all-reduce unavailable ({e}); using NCCL")
         self.pcg_iterations = []
         self._warm = None               # (hess version, h, solve(rpp)) of the previous lambda-trial
         self._pcg_tol = float(kwargs.get("pcg_tol", 1e-12))   # relative residual of the damped solve (accepted up to 1e-10)
@@ -233,7 +251,10 @@ class LM(BaseOptimizer):
     # -- device pieces ----------------------------------------------------------
     def _allreduce(self, t):
         if self.distributed:
-            torch.distributed.all_reduce(t, group=self.group)
+            if self._peer is not None and t.is_contiguous() and t.numel() <= self._peer.max_doubles:
+                self._peer.allreduce(t)
+            else:
+                torch.distributed.all_reduce(t, group=self.group)
         return t
 
     def _chi2_record(self, x):
@@ -252,7 +273,7 @@ class LM(BaseOptimizer):
         if self.distributed:
             # per-rank flag: 1 ok, 0 non-finite, -1 queue overflow -> summed as (bad, overflow) counts
             rec = torch.stack([c2[0], (c2[1] == 0).to(c2.dtype), (c2[1] < 0).to(c2.dtype)])
-            torch.distributed.all_reduce(rec, group=self.group)
+            self._allreduce(rec)
             c2[0] = rec[0]
             c2[1] = torch.where(rec[2] > 0, -1.0, (rec[1] == 0).to(c2.dtype))
         return c2
@@ -332,8 +353,13 @@ class LM(BaseOptimizer):
                 # every rank solves the same merged system; rank 0's answer is the one all use (the split sky row of
                 # the PCG is summed with atomics, so the ranks' solutions may differ in the last bit)
                 res = self.plan.solve_sparse(rhs.contiguous(), L, out=self._hs[:P], info=self._hs[P:], tol=tol, x0=x0)
-                torch.distributed.broadcast(self._hs, src=torch.distributed.get_global_rank(self.group, 0)
-                                            if self.group is not None else 0, group=self.group)
+                if self._peer is not None:
+                    if torch.distributed.get_rank(self.group) != 0:
+                        self._hs.zero_()
+                    self._peer.allreduce(self._hs)          # = broadcast of rank 0's answer
+                else:
+                    torch.distributed.broadcast(self._hs, src=torch.distributed.get_global_rank(self.group, 0)
+                                                if self.group is not None else 0, group=self.group)
                 res = (self._hs[:P].clone(), self._hs[P:])
             else:
                 res = self.plan.solve_sparse(rhs.contiguous(), L, tol=tol, x0=x0)
@@ -407,11 +433,10 @@ class LM(BaseOptimizer):
         self.n_jacobian += 1
         if self.distributed:
             if self._blk is not None:
-                self._allreduce(self._blk)     # the dense copy stays local until a dense fallback asks for it
+                self._allreduce(self._blkg)    # [blocks | diag H | g]; the dense copy stays local until a dense fallback asks for it
                 self._hess_reduced = False
-            elif self._H is not None:
-                self._allreduce(self._H)
-            self._allreduce(self._g)
+            else:
+                self._allreduce(self._Hg)      # [H | g] (g alone when the dense matrix is not kept)
         self.hess, self.grad = self._H, self._g
         self._hess_version += 1
         self._blocks_version = self._hess_version

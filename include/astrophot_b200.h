@@ -268,6 +268,23 @@ int apb_lm_trial_end(apb_plan_t *plan, const double *H, double L, const double *
 
 int apb_plan_stats(apb_plan_t *plan, apb_stats_t *out); /* synchronises the plan's last stream */
 
+/* ---- multi-GPU exchange (SURVEY.md 8b `apb_allreduce`, 8e) ------------------------------------------------------
+ * A fit whose pixels are sharded over the GPUs of one node sums J^T W J | J^T W r | chi^2 (fit/lm.py:256-260) and the
+ * per-trial record over the ranks.  These buffers are small (<= a few MB), so the exchange is ONE kernel over NVLink
+ * peer memory, ordered on the caller's stream behind the kernel that produced the buffer -- no host round trip, no NCCL
+ * launch: every rank publishes its buffer in a slot of cudaIpc-shared device memory, flags every peer, and adds all
+ * slots in rank order (deterministic, bit-identical on all ranks).
+ *   apb_comm_alloc   allocates this rank's exchange buffer (slots of max_doubles) and returns its 64-byte IPC handle;
+ *   (the caller gathers the handles of all ranks, e.g. with torch.distributed.all_gather)
+ *   apb_comm_create  maps the peers' buffers; `handles`: world x 64 bytes in rank order; takes ownership of `local`;
+ *   apb_allreduce    buf (device, n <= max_doubles doubles) <- sum over ranks, in place, asynchronous on `stream`.
+ *                    Every rank must make the same sequence of calls. */
+typedef struct apb_comm apb_comm_t;
+int apb_comm_alloc(size_t max_doubles, void **local_out, void *handle_out);
+int apb_comm_create(int rank, int world, void *local, const void *handles, size_t max_doubles, apb_comm_t **out);
+int apb_allreduce(apb_comm_t *comm, double *buf, size_t n, void *stream);
+int apb_comm_destroy(apb_comm_t *comm);
+
 /* ---- measurement (bench.py; no reference counterpart) ---------------------------------- */
 typedef struct {
   char name[32];

@@ -507,11 +507,58 @@ def _nccl_tile_worker(rank, world, port, out_dir, small):
     assert len(r.plan.shapes) == 4 // world
     if small == 0:
         assert r._blk is not None and len(r.pcg_iterations) > 0 and r._factor is None
+    assert r._peer is not None          # one node: the exchange is the peer-memory kernel, not NCCL
     if rank == 0:
         np.savez(os.path.join(out_dir, f"lm_{small}.npz"), loss=np.array(r.loss_history), L=np.array(r.L_history),
                  lam=np.array(r.lambda_history))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _peer_allreduce_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from astrophot_b200.cabi import PeerComm
+    comm = PeerComm(1 << 20)
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    worst = 0.0
+    # many back-to-back calls of changing size: the double-buffered slots and the sequence flags must never let a
+    # fast rank overwrite or read a slot too early; no host synchronisation between the calls
+    sizes = [7, 212, 1 << 20, 3, 4099, 513711, 1, 65536] * 25
+    outs, refs = [], []
+    for k, n in enumerate(sizes):
+        t = torch.randn(n, dtype=torch.float64, device="cuda", generator=g) * (1.0 + k)
+        ref = t.clone()
+        comm.allreduce(t)
+        dist.all_reduce(ref)
+        worst = max(worst, float((t - ref).abs().max() / ref.abs().max()))
+    assert worst <= 1e-15, worst       # two ranks: the sum has one order, the results are identical
+    # every rank holds the same bits
+    t = torch.randn(1000, dtype=torch.float64, device="cuda", generator=g)
+    comm.allreduce(t)
+    both = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(both, t)
+    assert all(torch.equal(both[0], b) for b in both)
+    if rank == 0:
+        open(os.path.join(out_dir, "ok"), "w").write(str(worst))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_allreduce_over_two_gpus(tmp_path):
+    """apb_allreduce (one kernel over NVLink peer memory, rank-order sum) against the NCCL all-reduce: 200 back-to-back
+    calls of sizes 1 .. 2^20 doubles without host synchronisation in between."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import torch.multiprocessing as mp
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_peer_allreduce_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
 
 
 @pytest.mark.parametrize("small", [159, 0])
