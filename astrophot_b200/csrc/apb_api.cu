@@ -493,11 +493,17 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     if (a.kind == APB_FLAT_SKY) s.psf = -1;
     if (s.psf >= 0) {
       if (s.psf >= n_psf) PFAIL("psf index out of range");
-      if (a.psf_shift != APB_SHIFT_NONE && a.psf_shift != APB_SHIFT_BILINEAR) PFAIL("unsupported psf_subpixel_shift");
+      const int lanczos = a.psf_shift >= APB_SHIFT_LANCZOS ? a.psf_shift - APB_SHIFT_LANCZOS : 0;
+      if (a.psf_shift != APB_SHIFT_NONE && a.psf_shift != APB_SHIFT_BILINEAR && (lanczos < 1 || lanczos > 8))
+        PFAIL("unsupported psf_subpixel_shift");
       s.pw = psf[s.psf].w; s.ph = psf[s.psf].h;
       if (s.pw % 2 != 1 || s.ph % 2 != 1) PFAIL("psf must have odd shape");
-      const bool pad = (a.psf_shift != APB_SHIFT_NONE) && a.kind != APB_POINT;
-      s.spw = s.pw + (pad ? 2 : 0); s.sph = s.ph + (pad ? 2 : 0);
+      // the shifted stamp keeps the pad of the shift kernel (1 pixel bilinear, k pixels lanczos:k) except for point sources
+      const int pad = (a.psf_shift == APB_SHIFT_NONE || a.kind == APB_POINT) ? 0 : (lanczos ? lanczos : 1);
+      s.spw = s.pw + 2 * pad; s.sph = s.ph + 2 * pad;
+      if (lanczos > 1 && a.kind != APB_POINT && (memcmp(a.out, a.fwd, sizeof(a.out)) || memcmp(a.out, a.jac, sizeof(a.out))))
+        PFAIL("lanczos:k shifts of a PSF-convolved model need the model's window to be the window it is sampled on "
+              "(the wider stamp wraps around the padded working image in the reference)");
       if (a.kind != APB_POINT) { s.bx = (s.pw + 2) / 2; s.by = (s.ph + 2) / 2; }  // ceil((1+P)/2), psf_image.py:71-93
       s.psf_off = psfst_total; psfst_total += (3LL + s.n_pp) * s.spw * s.sph;
       s.out_off = out_total; out_total += (long long)(1 + s.n_act) * s.ow * s.oh;
@@ -520,6 +526,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     if (s.psf >= 0 && a.kind != APB_POINT) {
       int want = conv_force ? conv_force : a.conv_mode;
       if (want == 0) want = (s.spw * s.sph > 17 * 17) ? 2 : 1;
+      if (s.psf_shift >= APB_SHIFT_LANCZOS) want = 1;   // circular over the padded image: the direct tile kernel wraps its loads
       if (want == 2) {
         const Geo& g = s.geo[0];
         const int Nx = fft_len(g.ew), Ny = fft_len(g.eh);
@@ -583,7 +590,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       if (s.kind == APB_FLAT_SKY || s.kind == APB_POINT) continue;
       Geo& g = s.geo[m];
       g.tile0 = (int)tiles.size();
-      for (int ty = 0; ty < g.mh; ty += 8)
+      for (int ty = 0; ty < g.mh; ty += 32)     // 32 x 32 pixels: a thread of k_first / k_select owns four rows
         for (int tx = 0; tx < g.mw; tx += 32) tiles.push_back(make_int4(i, tx, ty, 0));
       g.ntile = (int)tiles.size() - g.tile0;
       p->first_evals[m] += g.mw * g.mh;
@@ -608,7 +615,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         const DevSrc& s = S[i];
         if (s.psf < 0 || s.kind == APB_POINT || s.conv_fft) continue;
         const int cw = (s.spw - 1) / 2, chh = (s.sph - 1) / 2;
-        if (cw > s.bx || chh > s.by) PFAIL("internal: psf stamp wider than the border");
+        if ((cw > s.bx || chh > s.by) && s.psf_shift < APB_SHIFT_LANCZOS) PFAIL("internal: psf stamp wider than the border");
         auto add_job = [&](int in_plane, int kern, int out_plane) {
           const int j = (int)jobs.size();
           jobs.push_back(make_int4(i, in_plane, kern, out_plane));

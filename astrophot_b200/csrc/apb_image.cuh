@@ -9,6 +9,33 @@
 // Output planes at psfst + s.psf_off: K0, Kcx, Kcy, each sph x spw; Kcx/Kcy already contain
 // d shift / d centre = S^-1 and the chain factor, so conv(value, Kcx) is the J column.
 // ----------------------------------------------------------------------------
+// Lanczos taps (utils/interpolate.py:145-163): f(t) = sinc(t) sinc(t / k), sinc(u) = sin(pi u) / (pi u)
+__device__ __forceinline__ double apb_sinc(double u) { return u == 0.0 ? 1.0 : sinpi(u) / (APB_PI * u); }
+__device__ __forceinline__ double apb_dsinc(double u) {
+  if (fabs(u) < 1e-2) {   // (cos(pi u) - sinc(u)) / u cancels catastrophically near 0: series
+    const double p2 = APB_PI * APB_PI, u2 = u * u;
+    return u * (-p2 / 3.0 + u2 * (p2 * p2 / 30.0 - u2 * (p2 * p2 * p2 / 840.0)));
+  }
+  return (cospi(u) - apb_sinc(u)) / u;
+}
+// value of the zero-padded raw stamp (or of a derivative plane of an auxiliary PSF model) cross-correlated with the
+// separable Lanczos kernel at padded-frame position (yp, xp) (_model_methods.py:209-227: conv2d, padding "same")
+__device__ __forceinline__ double lanczos_corr(const double* __restrict__ p, int stride, int ph, int pw, int lz, int yp, int xp,
+                                               const double* __restrict__ ky, const double* __restrict__ kx) {
+  double acc = 0.0;
+  for (int j = -lz; j <= lz; ++j) {
+    const int y = yp + j - lz;
+    if (y < 0 || y >= ph) continue;
+    double row = 0.0;
+    for (int i = -lz; i <= lz; ++i) {
+      const int x = xp + i - lz;
+      if (x >= 0 && x < pw) row = fma(kx[i + lz], p[y * stride + x], row);
+    }
+    acc = fma(ky[j + lz], row, acc);
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                    const int* __restrict__ list, const apb_psf_t* __restrict__ psfs,
                                                    double* __restrict__ psfst, int grad, int mode,
@@ -33,15 +60,44 @@ __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ sr
     pdat = pv.p;
     pstride = pv.stride;
   }
-  // padded image is (ph+2) x (pw+2); stamps either keep the pad (galaxies) or crop it (points)
-  const int crop = (s.kind == APB_POINT && shifted) ? 1 : 0;
+  // padded image is (ph+2) x (pw+2) [lanczos:k: (ph+2k) x (pw+2k)]; stamps either keep the pad (galaxies) or crop it (points)
+  const int lz = s.psf_shift >= 10 ? s.psf_shift - 10 : 0;      // Lanczos order, 0: bilinear / none
+  const int crop = (s.kind == APB_POINT && shifted) ? (lz ? lz : 1) : 0;
   const int W2 = pw + 2, H2 = ph + 2;
+  __shared__ double lzk[4][17];     // Lx, Ly (normalised), dLx/dsx, dLy/dsy (quotient rule applied)
+  if (lz) {
+    const int nt = 2 * lz + 1;
+    if (threadIdx.x < 2 * nt) {
+      const int axis = threadIdx.x / nt, i = threadIdx.x - axis * nt;
+      const double t = (double)(i - lz) + (axis ? d.sy : d.sx);
+      lzk[axis][i] = apb_sinc(t) * apb_sinc(t / lz);
+      lzk[2 + axis][i] = apb_dsinc(t) * apb_sinc(t / lz) + apb_sinc(t) * apb_dsinc(t / lz) / lz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int axis = threadIdx.x;
+      double S = 0.0, dS = 0.0;
+      for (int i = 0; i < nt; ++i) { S += lzk[axis][i]; dS += lzk[2 + axis][i]; }
+      for (int i = 0; i < nt; ++i) {
+        const double L = lzk[axis][i];
+        lzk[2 + axis][i] = lzk[2 + axis][i] / S - L * (dS / (S * S));
+        lzk[axis][i] = L / S;
+      }
+    }
+    __syncthreads();
+  }
   double v0 = 0, v1 = 0, v2 = 0;
   for (int q = threadIdx.x; q < n; q += 256) {
     const int a = q / spw, b = q % spw;
     double val, gx = 0, gy = 0;
     if (!shifted) {
       val = pdat[a * pstride + b];
+    } else if (lz) {
+      val = lanczos_corr(pdat, pstride, ph, pw, lz, a + crop, b + crop, lzk[1], lzk[0]);
+      if (grad) {
+        gx = lanczos_corr(pdat, pstride, ph, pw, lz, a + crop, b + crop, lzk[1], lzk[2]);
+        gy = lanczos_corr(pdat, pstride, ph, pw, lz, a + crop, b + crop, lzk[3], lzk[0]);
+      }
     } else {
       const int i = b + crop, j = a + crop;  // index in the padded image
       const double x = (double)i - d.sx, y = (double)j - d.sy;
@@ -89,6 +145,8 @@ __global__ void __launch_bounds__(256) k_psf_stamp(const DevSrc* __restrict__ sr
         double val;
         if (!shifted) {
           val = dv.p[a * dv.stride + b];
+        } else if (lz) {
+          val = lanczos_corr(dv.p, dv.stride, ph, pw, lz, a + crop, b + crop, lzk[1], lzk[0]);
         } else {
           const int i = b + crop, j = a + crop;
           const double x = (double)i - d.sx, y = (double)j - d.sy;
@@ -184,9 +242,16 @@ __global__ void __launch_bounds__(256) k_conv(const DevSrc* __restrict__ src, co
   const int ex = tl.y + s.bx - cw, ey = tl.z + s.by - chh;
   const double* in = stamp + s.stamp_off + (long long)jb.y * s.plane_stride +
                      (long long)(g.ey0 - g.my0) * g.mw + (g.ex0 - g.mx0);
+  // lanczos:k stamps are 2 (k - 1) pixels wider than the PSF border: the reference convolves circularly over the padded
+  // image (utils/operations.py:9-36, img_prepadded), so their outer taps wrap around it
+  const bool wrap = s.psf_shift >= 10;
   for (int q = threadIdx.x; q < iw * ih; q += 256) {
     const int r = q / iw, c = q % iw;
-    const int yy = ey + r, xx = ex + c;
+    int yy = ey + r, xx = ex + c;
+    if (wrap) {
+      yy = ((yy % g.eh) + g.eh) % g.eh;
+      xx = ((xx % g.ew) + g.ew) % g.ew;
+    }
     sI[r * istr + c] = (yy >= 0 && yy < g.eh && xx >= 0 && xx < g.ew) ? in[(long long)yy * g.mw + xx] : 0.0;
   }
   __syncthreads();

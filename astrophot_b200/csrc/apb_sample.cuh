@@ -301,7 +301,7 @@ __device__ __forceinline__ double gl_integrate(const DevSrc& s, const DevDyn& d,
 }
 
 // ----------------------------------------------------------------------------
-// first pass over the stamp region (one 32x8 tile per CTA)
+// first pass over the stamp region (one 32x32 tile per CTA, four rows per thread)
 // ----------------------------------------------------------------------------
 template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& d, const Geo& g, int i, int j,
@@ -362,6 +362,36 @@ __device__ __forceinline__ void first_pass_pixel(const DevSrc& s, const DevDyn& 
   }
 }
 
+// Four midpoint evaluations of one thread (rows ly, ly+8, ly+16, ly+24 of a 32x32 tile) side by side: one register
+// context, four independent exp / log chains, one range test.  Same arithmetic as eval_point (bit-identical values:
+// the mean reference may re-evaluate pixels through that path).
+#define FIRST_ROWS 4
+template <int KIND, typename T>
+__device__ __forceinline__ void first_pass_fast(const DevSrc& s, const DevDyn& d, const Geo& g, int i, int j0,
+                                                double* __restrict__ stamp) {
+  PCtxT<T> c;
+  pctx_load(c, s, d, 1.0);
+  T xp[FIRST_ROWS], yp[FIRST_ROWS], I[FIRST_ROWS];
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < FIRST_ROWS; ++r) {
+    double X, Y;
+    pix_coords(s, d, (double)(g.mx0 + i), (double)(g.my0 + j0 + 8 * r), X, Y);
+    rot_coords<T>(c, (T)X, (T)Y, xp[r], yp[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < FIRST_ROWS; ++r) I[r] = prof_fast<KIND>(c, r2_of<T>(xp[r], yp[r], c.soft2), bad);
+  if (bad) {
+#pragma unroll
+    for (int r = 0; r < FIRST_ROWS; ++r) I[r] = eval_rot<KIND, false, T>(c, s, d, xp[r], yp[r], nullptr);
+  }
+  double* base = stamp + s.stamp_off + (long long)j0 * g.mw + i;
+#pragma unroll
+  for (int r = 0; r < FIRST_ROWS; ++r)
+    if (j0 + 8 * r < g.mh) base[(long long)(8 * r) * g.mw] = (double)I[r];
+}
+
+// tiles are 32 x 32 pixels of the stamp region; a thread owns four rows of one column
 template <bool GRAD, typename T>
 __global__ void __launch_bounds__(256, GRAD ? 2 : 4) k_first(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                const int4* __restrict__ tiles, int mode, double* __restrict__ stamp,
@@ -371,17 +401,30 @@ __global__ void __launch_bounds__(256, GRAD ? 2 : 4) k_first(const DevSrc* __res
   const DevSrc& s = src[t.x];
   const DevDyn& d = dyn[t.x];
   const Geo& g = s.geo[mode];
-  const int i = t.y + (threadIdx.x & 31), j = t.z + (threadIdx.x >> 5);
-  if (i >= g.mw || j >= g.mh) return;
+  const int i = t.y + (threadIdx.x & 31), j0 = t.z + (threadIdx.x >> 5);
+  if (i >= g.mw || j0 >= g.mh) return;
+  if constexpr (!GRAD) {
+    if (s.sampling_mode == APB_SAMPLE_MIDPOINT) {
+      switch (s.kind) {
+        case APB_SERSIC: first_pass_fast<APB_SERSIC, T>(s, d, g, i, j0, stamp); return;
+        case APB_EXPONENTIAL: first_pass_fast<APB_EXPONENTIAL, T>(s, d, g, i, j0, stamp); return;
+        case APB_GAUSSIAN: first_pass_fast<APB_GAUSSIAN, T>(s, d, g, i, j0, stamp); return;
+        case APB_MOFFAT: first_pass_fast<APB_MOFFAT, T>(s, d, g, i, j0, stamp); return;
+        default: break;
+      }
+    }
+  }
   const int errp = s.n_act + 1;
-  switch (s.kind) {
-    case APB_SERSIC: first_pass_pixel<APB_SERSIC, GRAD, T>(s, d, g, i, j, stamp, errp); break;
-    case APB_EXPONENTIAL: first_pass_pixel<APB_EXPONENTIAL, GRAD, T>(s, d, g, i, j, stamp, errp); break;
-    case APB_GAUSSIAN: first_pass_pixel<APB_GAUSSIAN, GRAD, T>(s, d, g, i, j, stamp, errp); break;
-    case APB_MOFFAT: first_pass_pixel<APB_MOFFAT, GRAD, T>(s, d, g, i, j, stamp, errp); break;
-    case APB_SPLINE: first_pass_pixel<APB_SPLINE, GRAD, T>(s, d, g, i, j, stamp, errp); break;
-    case APB_PLANE_SKY: first_pass_pixel<APB_PLANE_SKY, GRAD>(s, d, g, i, j, stamp, errp); break;
-    default: break;
+  for (int j = j0; j < g.mh && j < j0 + 8 * FIRST_ROWS; j += 8) {
+    switch (s.kind) {
+      case APB_SERSIC: first_pass_pixel<APB_SERSIC, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+      case APB_EXPONENTIAL: first_pass_pixel<APB_EXPONENTIAL, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+      case APB_GAUSSIAN: first_pass_pixel<APB_GAUSSIAN, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+      case APB_MOFFAT: first_pass_pixel<APB_MOFFAT, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+      case APB_SPLINE: first_pass_pixel<APB_SPLINE, GRAD, T>(s, d, g, i, j, stamp, errp); break;
+      case APB_PLANE_SKY: first_pass_pixel<APB_PLANE_SKY, GRAD>(s, d, g, i, j, stamp, errp); break;
+      default: break;
+    }
   }
 }
 
@@ -489,50 +532,55 @@ __device__ __forceinline__ void select_tile(const DevSrc* __restrict__ src, cons
   if (s.integrate_mode != APB_INTEGRATE_THRESHOLD) return;
   const DevDyn& d = dyn[t.x];
   const Geo& g = s.geo[mode];
-  const int i = t.y + (threadIdx.x & 31), j = t.z + (threadIdx.x >> 5);
-  bool sel = false;
-  double X = 0, Y = 0;
-  if (i < g.mw && j < g.mh) {
-    const int pi = g.mx0 + i, pj = g.my0 + j;
-    if (pi >= g.ex0 && pi < g.ex0 + g.ew && pj >= g.ey0 && pj < g.ey0 + g.eh) {
-      const double* m = stamp + s.stamp_off;
-      double err;
-      if (s.sampling_mode == APB_SAMPLE_MIDPOINT || s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
-        if (g.rw >= 3 && g.rh >= 3) {
-          // 3x3 Laplacian, replicate-padded over the working region (_model_methods.py:87-98)
-          int ic = min(max(pi, g.rx0 + 1), g.rx0 + g.rw - 2) - g.mx0;
-          int jc = min(max(pj, g.ry0 + 1), g.ry0 + g.rh - 2) - g.my0;
-          ic = min(max(ic, 1), g.mw - 2);
-          jc = min(max(jc, 1), g.mh - 2);
-          const double* c = m + (long long)jc * g.mw + ic;
-          err = fabs(c[-g.mw] + c[-1] + c[1] + c[g.mw] - 4.0 * c[0]);
-        } else {
-          err = 0.0;
-        }
-      } else {
-        err = m[(long long)(s.n_act + 1) * s.plane_stride + (long long)j * g.mw + i];
-      }
-      sel = err > d.thr[mode];
-      if (sel) pix_coords(s, d, (double)pi, (double)pj, X, Y);
-    }
-  }
-  const unsigned bal = __ballot_sync(0xffffffffu, sel);
-  if (bal == 0) return;
+  const int i = t.y + (threadIdx.x & 31);
   const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(&q.count[1], __popc(bal));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (sel) {
-    const int e = base + __popc(bal & ((1u << lane) - 1));
-    if (e < q.cap[1]) {
-      const Level& L = q.lv[1];
-      L.src[e] = t.x;
-      L.x[e] = X;
-      L.y[e] = Y;
-      L.parent[e] = j * g.mw + i;
-      L.child[e] = -1;
-    } else {
-      *q.overflow = 1;
+  // tiles are 32 x 32: a warp walks rows ly, ly+8, ly+16, ly+24 (warp-uniform trip count: the ballots stay well defined)
+#pragma unroll 1
+  for (int r = 0; r < FIRST_ROWS; ++r) {
+    const int j = t.z + (threadIdx.x >> 5) + 8 * r;
+    bool sel = false;
+    double X = 0, Y = 0;
+    if (i < g.mw && j < g.mh) {
+      const int pi = g.mx0 + i, pj = g.my0 + j;
+      if (pi >= g.ex0 && pi < g.ex0 + g.ew && pj >= g.ey0 && pj < g.ey0 + g.eh) {
+        const double* m = stamp + s.stamp_off;
+        double err;
+        if (s.sampling_mode == APB_SAMPLE_MIDPOINT || s.sampling_mode == APB_SAMPLE_TRAPEZOID) {
+          if (g.rw >= 3 && g.rh >= 3) {
+            // 3x3 Laplacian, replicate-padded over the working region (_model_methods.py:87-98)
+            int ic = min(max(pi, g.rx0 + 1), g.rx0 + g.rw - 2) - g.mx0;
+            int jc = min(max(pj, g.ry0 + 1), g.ry0 + g.rh - 2) - g.my0;
+            ic = min(max(ic, 1), g.mw - 2);
+            jc = min(max(jc, 1), g.mh - 2);
+            const double* c = m + (long long)jc * g.mw + ic;
+            err = fabs(c[-g.mw] + c[-1] + c[1] + c[g.mw] - 4.0 * c[0]);
+          } else {
+            err = 0.0;
+          }
+        } else {
+          err = m[(long long)(s.n_act + 1) * s.plane_stride + (long long)j * g.mw + i];
+        }
+        sel = err > d.thr[mode];
+        if (sel) pix_coords(s, d, (double)pi, (double)pj, X, Y);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    if (bal == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&q.count[1], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (sel) {
+      const int e = base + __popc(bal & ((1u << lane) - 1));
+      if (e < q.cap[1]) {
+        const Level& L = q.lv[1];
+        L.src[e] = t.x;
+        L.x[e] = X;
+        L.y[e] = Y;
+        L.parent[e] = j * g.mw + i;
+        L.child[e] = -1;
+      } else {
+        *q.overflow = 1;
+      }
     }
   }
 }
@@ -633,6 +681,18 @@ __global__ void __launch_bounds__(128) k_refine(const DevSrc* __restrict__ src, 
         L.child[t] = -1;
         double* res = L.res + (long long)t * q.NVp;
         for (int p = 0; p < q.NVp; ++p) res[p] = 0.0;
+        // The slots this entry reserved below the capacity are inside the range the next depth processes
+        // (min(count, cap)): fill them with inert copies of the parent -- left as they are they hold whatever the
+        // allocation contained, and a garbage source index is an illegal access one launch later.  (Their results
+        // are never read: the parent has no child list, and the host repeats the pass with larger queues anyway.)
+        const Level& C = q.lv[depth + 1];
+        for (int c = first; c < q.cap[depth + 1] && c < first + nchild; ++c) {
+          C.src[c] = si;
+          C.x[c] = X;
+          C.y[c] = Y;
+          C.parent[c] = t;
+          C.child[c] = -1;
+        }
       }
     }
   }

@@ -86,7 +86,14 @@ def _shift_code(name):
     if name == "bilinear":
         return sc.SHIFT_BILINEAR
     if isinstance(name, str) and name.startswith("lanczos"):
-        raise SpecificationConflict("lanczos sub-pixel shifts are not implemented in astrophot_b200 yet (SURVEY.md §8f)")
+        # "lanczos:k" (_model_methods.py:209-227): code 10 + k
+        try:
+            order = int(name[name.find(":") + 1:])
+        except ValueError:
+            raise SpecificationConflict(f"unrecognized subpixel shift method: {name}")
+        if not 1 <= order <= 8:
+            raise SpecificationConflict(f"lanczos order out of range (1..8): {name}")
+        return sc.SHIFT_LANCZOS + order
     raise SpecificationConflict(f"unrecognized subpixel shift method: {name}")
 
 
@@ -284,6 +291,14 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
                     psfs.append(sc.ScenePSF(data=None, source=psrc, shape=shape))
                 psf_index[id(psf)] = len(psfs) - 1
             pidx = psf_index[id(psf)]
+        if pidx >= 0 and comp._kind != sc.KIND_POINT and _shift_code(comp.psf_subpixel_shift) > sc.SHIFT_LANCZOS + 1 \
+                and not (tuple(out) == tuple(fwd) == tuple(jac)):
+            # the lanczos:k stamp is 2 (k - 1) pixels wider than the PSF border: in the reference's circular FFT
+            # convolution its outer taps wrap around the padded WORKING image -- the group's window in a forward pass,
+            # the model's own in the Jacobian.  Reproduced when the two coincide.
+            raise SpecificationConflict(
+                f"{comp.name}: psf_subpixel_shift='{comp.psf_subpixel_shift}' on a PSF-convolved model needs the model's "
+                "window to be the window it is sampled on (stand-alone, or the group's window)")
         if comp._kind == sc.KIND_POINT and comp.psf_subpixel_shift == "none":
             # the reference shifts a point source's PSF image unconditionally (point_source.py:157-162 -> _shift_psf),
             # which has no "none" method: same error here

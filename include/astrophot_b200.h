@@ -55,7 +55,7 @@ enum { APB_TR_NONE = 0, APB_TR_LOWER, APB_TR_UPPER, APB_TR_BOTH, APB_TR_CYCLIC }
 enum { APB_SAMPLE_MIDPOINT = 0, APB_SAMPLE_SIMPSONS, APB_SAMPLE_QUAD, APB_SAMPLE_TRAPEZOID }; /* _model_methods.py:82-148 */
 enum { APB_INTEGRATE_NONE = 0, APB_INTEGRATE_THRESHOLD };                                  /* _model_methods.py:155-184 */
 enum { APB_REF_MEAN = 0, APB_REF_SERSIC_FLUX }; /* _model_methods.py:151-152, sersic_model.py:87-89 */
-enum { APB_SHIFT_NONE = 0, APB_SHIFT_BILINEAR = 1 }; /* _model_methods.py:187-230 */
+enum { APB_SHIFT_NONE = 0, APB_SHIFT_BILINEAR = 1, APB_SHIFT_LANCZOS = 10 }; /* _model_methods.py:187-230; "lanczos:k" = 10 + k, k = 1..8 */
 /* "fft" in the reference = APB_CONV_AUTO here (tiled direct convolution for small stamps, FFT for
  * large ones: same valid region, utils/operations.py:9-36); "direct" = APB_CONV_DIRECT */
 enum { APB_CONV_AUTO = 0, APB_CONV_DIRECT = 1, APB_CONV_FFT = 2 };

@@ -368,15 +368,73 @@ def shift_psf_bilinear(psf, shift, keep_pad=True, want_grad=False):
     return out, grads
 
 
+def _lanczos_taps(d, k, want_grad):
+    """Lx[i] = sinc(t) sinc(t / k), t = i + d, i = -k..k, divided by its sum (utils/interpolate.py:145-163 called with
+    -shift: sinc is even, so the sign flips there cancel), and its derivative wrt d."""
+    t = np.arange(-k, k + 1, dtype=np.float64) + d
+    L = np.sinc(t) * np.sinc(t / k)
+    S = L.sum()
+    if not want_grad:
+        return L / S, None
+
+    def dsinc(u):
+        small = np.abs(u) < 1e-2
+        us = np.where(small, 1.0, u)
+        big = (np.cos(np.pi * us) - np.sinc(us)) / us
+        ser = -(np.pi**2 / 3) * u + (np.pi**4 / 30) * u**3 - (np.pi**6 / 840) * u**5
+        return np.where(small, ser, big)
+
+    dL = dsinc(t) * np.sinc(t / k) + np.sinc(t) * dsinc(t / k) / k
+    return L / S, dL / S - L * (dL.sum() / S**2)
+
+
+def shift_psf_lanczos(psf, shift, k, keep_pad=True, want_grad=False):
+    """_model_methods.py:209-227: the PSF zero-padded by k, cross-correlated ('same') with the normalised separable
+    Lanczos-k kernel of the shift.  Returns stamp (and d/dsx, d/dsy)."""
+    im = np.pad(np.asarray(psf, dtype=np.float64), k)
+    Lx, dLx = _lanczos_taps(shift[0], k, want_grad)
+    Ly, dLy = _lanczos_taps(shift[1], k, want_grad)
+
+    def corr(kx, ky):
+        wide = np.pad(im, k)
+        tmp = sum(kx[i] * wide[:, i : i + im.shape[1]] for i in range(2 * k + 1))
+        return sum(ky[j] * tmp[j : j + im.shape[0], :] for j in range(2 * k + 1))
+
+    out = corr(Lx, Ly)
+    grads = (corr(dLx, Ly), corr(Lx, dLy)) if want_grad else None
+    if not keep_pad:
+        out = out[k:-k, k:-k]
+        if want_grad:
+            grads = (grads[0][k:-k, k:-k], grads[1][k:-k, k:-k])
+    return out, grads
+
+
+def _shift_psf(psf, shift, method, keep_pad, want_grad):
+    if method == sc.SHIFT_BILINEAR:
+        return shift_psf_bilinear(psf, shift, keep_pad, want_grad)
+    if method > sc.SHIFT_LANCZOS:
+        return shift_psf_lanczos(psf, shift, method - sc.SHIFT_LANCZOS, keep_pad, want_grad)
+    raise NotImplementedError(f"sub-pixel shift method {method}")
+
+
+def conv_same_circular(img, ker):
+    """The reference's FFT convolution on the pre-padded image (utils/operations.py:9-36 with img_prepadded=True): a
+    CIRCULAR convolution of the image's own size.  For the bilinear shift the kernel reaches exactly to the PSF border,
+    nothing wraps and this equals the linear convolution; the Lanczos-k stamp is 2 (k - 1) pixels wider, and its outer
+    taps bring pixels of the opposite edge into the k - 1 outermost rows / columns of the cropped result."""
+    H, W = img.shape
+    kh, kw = ker.shape
+    f = np.fft.irfft2(np.fft.rfft2(img) * np.fft.rfft2(ker, s=(H, W)), s=(H, W))
+    return np.roll(f, (-((kh - 1) // 2), -((kw - 1) // 2)), axis=(0, 1))
+
+
 def normalized_shifted_psf(psf, shift, method, keep_pad, want_grad):
     """Shifted PSF divided by its sum (_model_methods.py:239-243), with the
     quotient-rule derivative wrt the shift."""
     if method == sc.SHIFT_NONE or shift is None:
         p = np.asarray(psf, dtype=np.float64)
         return p / p.sum(), None
-    if method != sc.SHIFT_BILINEAR:
-        raise NotImplementedError("only bilinear / none sub-pixel shifts are in the oracle")
-    st, g = shift_psf_bilinear(psf, shift, keep_pad, want_grad)
+    st, g = _shift_psf(psf, shift, method, keep_pad, want_grad)
     tot = st.sum()
     out = st / tot
     if not want_grad:
@@ -391,8 +449,8 @@ def shifted_psf_param_derivative(psf, dpsf, shift, method, keep_pad):
     if method == sc.SHIFT_NONE or shift is None:
         st, dst = np.asarray(psf, dtype=np.float64), np.asarray(dpsf, dtype=np.float64)
     else:
-        st, _ = shift_psf_bilinear(psf, shift, keep_pad, False)
-        dst, _ = shift_psf_bilinear(dpsf, shift, keep_pad, False)
+        st, _ = _shift_psf(psf, shift, method, keep_pad, False)
+        dst, _ = _shift_psf(dpsf, shift, method, keep_pad, False)
     tot = st.sum()
     return dst / tot - st * (dst.sum() / tot**2)
 
@@ -646,6 +704,8 @@ def _sample_source_unmasked(scene, si, el, mode, want_grad, conv="direct", stats
 
     # ---- PSF convolution on the padded region, then crop the border (model_object.py:342-349)
     cfn = conv_same if conv == "direct" else conv_same_fft
+    if src.psf_shift > sc.SHIFT_LANCZOS:
+        cfn = conv_same_circular     # the wider Lanczos stamp wraps around the padded image in the reference
     P, dP = normalized_shifted_psf(psf, shift, src.psf_shift, True, want_grad and shift is not None)
     crop = (slice(by, by + oh), slice(bx, bx + ow))
     val = cfn(deep_e, P)[crop]

@@ -90,11 +90,12 @@ def build(ap, name, data=None):
             pars["I(R)"] = {"value": val, "prof": prof}
         m = M(name=f"k_{name}", model_type=f"{name} galaxy model", target=tar, parameters=pars)
         return m, {}
-    if name in ("psf_sersic", "psf_sersic_noshift"):
+    if name in ("psf_sersic", "psf_sersic_noshift", "psf_sersic_lanczos3"):
         psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 11), pixelscale=1.0)
         tar = _target(ap, (64, 64), data, psf=psf)
         m = M(name=name, model_type="sersic galaxy model", target=tar, psf_mode="full",
-              psf_subpixel_shift="bilinear" if name == "psf_sersic" else "none",
+              psf_subpixel_shift={"psf_sersic": "bilinear", "psf_sersic_noshift": "none",
+                                  "psf_sersic_lanczos3": "lanczos:3"}[name],
               parameters={"center": [30.8, 33.3], "q": 0.55, "PA": 2.4, "n": 2.5, "Re": 6.0, "Ie": 1.0})
         return m, {}
     if name in ("sersic_modelmask", "psf_sersic_modelmask"):
@@ -129,6 +130,21 @@ def build(ap, name, data=None):
         m = M(name="pt", model_type="point model", target=tar,
               parameters={"center": [20.7, 18.4], "flux": 1.0})
         return m, {}
+    if name == "lanczos_group":
+        # lanczos:2 / lanczos:3 sub-pixel shifts (_model_methods.py:209-227): a PSF-convolved galaxy (the wider shifted
+        # stamp wraps around the padded image in the reference's FFT convolution) and two point sources, one at an edge
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 1.8, 9), pixelscale=1.0)
+        tar = _target(ap, (48, 52), data, psf=psf)
+        models = [
+            M(name="lz_gal", model_type="sersic galaxy model", target=tar, psf_mode="full", psf_subpixel_shift="lanczos:2",
+              parameters={"center": [25.7, 22.2], "q": 0.6, "PA": 0.7, "n": 1.8, "Re": 5.0, "Ie": 0.8}),
+            M(name="lz_pt", model_type="point model", target=tar, psf_subpixel_shift="lanczos:3",
+              parameters={"center": [12.3, 30.8], "flux": 1.2}),
+            M(name="lz_pte", model_type="point model", target=tar, psf_subpixel_shift="lanczos:3", window=[[38, 52], [0, 14]],
+              parameters={"center": [49.6, 3.4], "flux": 1.5}),
+        ]
+        g = M(name="lzg", model_type="group model", models=models, target=tar, psf_mode="full")
+        return g, {}
     if name == "point_edge":
         psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 2.0, 15), pixelscale=1.0)
         tar = _target(ap, (40, 44), data, psf=psf)
@@ -318,13 +334,14 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "moffat", "spline", "psf_sersic", "psf_sersic_noshift", "point", "point_edge", "group",
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs",
-                 "point_psf_model", "point_psf_model_group", "group_edge", "sersic_modelmask", "psf_sersic_modelmask"]
+                 "point_psf_model", "point_psf_model_group", "group_edge", "sersic_modelmask", "psf_sersic_modelmask",
+                 "psf_sersic_lanczos3", "lanczos_group"]
 CPU_ONLY_SCENES = []
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
              "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18,
-             "psf_sersic_modelmask": 19}
+             "psf_sersic_modelmask": 19, "psf_sersic_lanczos3": 20, "lanczos_group": 21}
 CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
