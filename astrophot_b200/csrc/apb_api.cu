@@ -1212,7 +1212,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
         }
         if (run_pool) {
           PB(grad ? K_POOL_G : K_POOL);
-          PROFILE_LAUNCH(k_integrate_pool, p->pool_grid[grad ? 1 : 0], POOL_B, p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, grad ? p->pool_nv : 1);
+          PROFILE_LAUNCH(k_integrate_pool, p->pool_grid[grad ? 1 : 0], POOL_B, p->d_src, p->d_dyn, mode, p->d_stamp, q, n_min, p->pool_g2, grad ? p->pool_nv : 1, p->max_depth);
           LAUNCH_CHECK();
         }
       } else {
@@ -1757,7 +1757,8 @@ extern "C" int apb_allreduce(apb_comm_t* c, double* buf, size_t n, void* stream)
     A.flags[r] = (unsigned long long*)((double*)c->peer[r] + 2 * c->slot_doubles);
   }
   A.rank = c->rank; A.world = c->world; A.seq = c->seq; A.done = c->done;
-  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_max, (n + 2047) / 2048));
+  // two elements per thread: the sum is bound by the latency of the peer loads, so spread them wide
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->grid_max, (n + 511) / 512));
   k_allreduce_peer<<<grid, 256, 0, (cudaStream_t)stream>>>(A, buf, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) APB_FAIL(std::string("apb_allreduce launch: ") + cudaGetErrorString(e));

@@ -36,17 +36,19 @@ struct CommArgs {
   unsigned int* done;
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// peer data: volatile (never from a stale L1 line), no memory clobber -- the loads of one element from all ranks are
+// independent and must be in flight together (a clobber would serialise them: world x one NVLink round trip)
 __device__ __forceinline__ double ld_peer(const double* p) {
   double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
 
@@ -57,26 +59,36 @@ __global__ void __launch_bounds__(256) k_allreduce_peer(CommArgs A, double* __re
   // ---- phase 1: publish
   double* mine = A.slot[A.rank];
   for (size_t i = tid; i < n; i += nth) mine[i] = buf[i];
-  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) last_s = atomicAdd(A.done, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence();          // this CTA's copy is visible device-wide before it counts as arrived
+    last_s = atomicAdd(A.done, 1u) == gridDim.x - 1;
+    __threadfence();          // ... and the last CTA sees every other CTA's copy before it raises the flags
+  }
   __syncthreads();
   if (last_s) {
-    // every CTA's copy is visible system-wide (each fenced before its arrival): tell every rank, this one included
-    __threadfence_system();
+    // every CTA has arrived: one system-scope release per peer publishes the whole slot (cumulativity through the
+    // device-scope fences and the arrival counter), then the flag -- this rank's included
     if (threadIdx.x < A.world) st_release_sys(A.flags[threadIdx.x] + A.rank, A.seq);
     if (threadIdx.x == 0) *A.done = 0u;
   }
-  // ---- phase 2: wait for all ranks, then sum in rank order
+  // ---- phase 2: wait for all ranks (relaxed polling of LOCAL memory, one acquire fence at the end), then sum in rank order
   if (threadIdx.x < A.world) {
     const unsigned long long* f = A.flags[A.rank] + threadIdx.x;
-    while (ld_acquire_sys(f) < A.seq) {
+    while (ld_volatile_u64(f) < A.seq) {
     }
+    __threadfence_system();
   }
   __syncthreads();
   for (size_t i = tid; i < n; i += nth) {
-    double v = 0.0;
-    for (int r = 0; r < A.world; ++r) v += ld_peer(A.slot[r] + i);
-    buf[i] = v;
+    double v[APB_COMM_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < APB_COMM_MAX_RANKS; ++r)
+      if (r < A.world) v[r] = ld_peer(A.slot[r] + i);
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < APB_COMM_MAX_RANKS; ++r)
+      if (r < A.world) t += v[r];
+    buf[i] = t;
   }
 }

@@ -952,6 +952,7 @@ __global__ void __launch_bounds__(128, GRAD ? 3 : 4) k_integrate(const DevSrc* _
 #define POOL_MINB 5       // resident CTAs per SM the value-only kernel is compiled for (register budget)
 #endif
 #define POOL_CSUM 3200    // child integrals held per CTA (doubles)
+#define POOL_C2 800       // grandchild integrals held per CTA (value-only kernel, depth-3 phase)
 
 template <int KIND, bool GRAD, typename T = double>
 __device__ __forceinline__ bool pool_child(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
@@ -990,6 +991,28 @@ __device__ __forceinline__ void pool_split_child(const DevSrc& s, const DevDyn& 
       for (int e = 0; e < ne && 1 + e < nv; ++e) out[1 + e] = sub.v[1 + e];
   }
 }
+// Integral of grandchild `gc` of child `ch` of the depth-1 entry at (X, Y): a depth-3 cell, final when max_depth == 3
+// (no further test, utils/operations.py:196-199).  Same centre arithmetic as pool_split_child -> split_cell.
+template <int KIND, typename T = double>
+__device__ __forceinline__ double pool_grandchild(const DevSrc& s, const DevDyn& d, double X, double Y, int ch, int gc) {
+  const int G = s.gridding;
+  const int cyi = (ch * s.gmagic) >> 16, cxi = ch - cyi * G;
+  const double dx = s.goff[cxi], dy = s.goff[cyi];
+  const double cx = X + (s.S[0] * dx + s.S[1] * dy);
+  const double cy = Y + (s.S[2] * dx + s.S[3] * dy);
+  const int gyi = (gc * s.gmagic) >> 16, gxi = gc - gyi * G;
+  const double ex = s.goff[gxi] * s.gsc[2], ey = s.goff[gyi] * s.gsc[2];
+  const double gx = cx + (s.S[0] * ex + s.S[1] * ey);
+  const double gy = cy + (s.S[2] * ex + s.S[3] * ey);
+  Acc<false, KindInfo<KIND>::NE> ca;
+  gl_nodes<KIND, false, T>(s, d, gx, gy, s.gsc[3], s.gasc[3], 0, 1, ca);
+  return ca.v[0];
+}
+template <typename T = double>
+__device__ __noinline__ double pool_grandchild_spline(const DevSrc& s, const DevDyn& d, double X, double Y, int ch, int gc) {
+  return pool_grandchild<APB_SPLINE, T>(s, d, X, Y, ch, gc);
+}
+
 template <bool GRAD, typename T = double>
 __device__ __noinline__ bool pool_child_spline(const DevSrc& s, const DevDyn& d, int mode, double X, double Y, int ch,
                                                double* __restrict__ out, int nv) {
@@ -1005,8 +1028,9 @@ __device__ __noinline__ void pool_split_child_spline(const DevSrc& s, const DevD
 template <bool GRAD, typename T>
 __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool(const DevSrc* __restrict__ src, const DevDyn* __restrict__ dyn,
                                                                           int mode, double* __restrict__ stamp, Queues q,
-                                                                          int n_min, int g2, int nv) {
+                                                                          int n_min, int g2, int nv, int pmax) {
   __shared__ double csum[POOL_CSUM];
+  __shared__ double csum2[POOL_C2];             // grandchild integrals of the pooled depth-3 phase (value-only kernel)
   __shared__ double eX[POOL_B], eY[POOL_B];
   __shared__ int eS[POOL_B], eP[POOL_B], list1[POOL_B];
   __shared__ unsigned short list2[POOL_CSUM];   // child index < POOL_CSUM
@@ -1086,7 +1110,52 @@ __global__ void __launch_bounds__(POOL_B, GRAD ? 3 : POOL_MINB) k_integrate_pool
       __syncthreads();
       // ---- phase 3
       const int nf2 = s_nf2;
-      for (int k = wid; k < nf2; k += POOL_B / 32) {
+      bool pooled3 = false;
+      if constexpr (!GRAD) {
+        // Value-only passes with max_depth <= 3 (the default): a listed child's grandchildren are final, so they are
+        // pooled like the children were -- thread c takes grandchild c % G^2 of listed child c / G^2, every lane on its
+        // own cell (the warp-per-child form below keeps 25 of 32 lanes busy and one cell per lane in flight).
+        pooled3 = pmax <= 3 && g2 <= POOL_C2;
+        if (pooled3) {
+          const int per3 = POOL_C2 / g2;             // listed children whose grandchildren fit in csum2
+          const int st_k = POOL_B / g2, st_g = POOL_B - st_k * g2;
+          for (int k0 = 0; k0 < nf2; k0 += per3) {
+            const int nk = min(per3, nf2 - k0);
+            int ngc = 0;
+            int kk = tid / g2, gc = tid - kk * g2;
+            for (int c = tid; c < nk * g2; c += POOL_B, kk += st_k, gc += st_g) {
+              if (gc >= g2) { gc -= g2; ++kk; }
+              const int cidx = list2[k0 + kk];
+              const int pi = cidx / g2, ch = cidx - pi * g2;
+              const int e = list1[c0 + pi];
+              const DevSrc& s = src[eS[e]];
+              double v = 0.0;
+              if (gc < s.gridding * s.gridding) {
+                const DevDyn& d = dyn[eS[e]];
+                ++ngc;
+                switch (s.kind) {
+                  case APB_SERSIC: v = pool_grandchild<APB_SERSIC, T>(s, d, eX[e], eY[e], ch, gc); break;
+                  case APB_EXPONENTIAL: v = pool_grandchild<APB_EXPONENTIAL, T>(s, d, eX[e], eY[e], ch, gc); break;
+                  case APB_GAUSSIAN: v = pool_grandchild<APB_GAUSSIAN, T>(s, d, eX[e], eY[e], ch, gc); break;
+                  case APB_MOFFAT: v = pool_grandchild<APB_MOFFAT, T>(s, d, eX[e], eY[e], ch, gc); break;
+                  case APB_SPLINE: v = pool_grandchild_spline<T>(s, d, eX[e], eY[e], ch, gc); break;
+                  default: break;
+                }
+              }
+              csum2[c] = v;
+            }
+            if (ngc) atomicAdd(&q.count[3], ngc);
+            __syncthreads();
+            for (int k = tid; k < nk; k += POOL_B) {      // grandchildren added in order: deterministic
+              double tot = 0.0;
+              for (int g = 0; g < g2; ++g) tot += csum2[k * g2 + g];
+              csum[(long long)list2[k0 + k] * nv] = tot;
+            }
+            __syncthreads();
+          }
+        }
+      }
+      for (int k = wid; k < nf2 && !pooled3; k += POOL_B / 32) {
         const int c = list2[k];
         const int pi = c / g2, ch = c - pi * g2;
         const int e = list1[c0 + pi];

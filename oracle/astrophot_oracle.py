@@ -905,7 +905,7 @@ class OptimizeStop(Exception):
 def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_iter=10,
            curvature_limit=1.0, Lup=11.0, Ldn=9.0, L0=1.0, acceleration=0.0, conv="direct", verbose=0, stop=None):
     """Levenberg-Marquardt loop, control flow of fit/lm.py:248-357,428-493.
-    ``stop``: optional callable(loss_history) -> bool checked after every iteration (bench.py ends a fit with the same
+    ``stop``: optional callable(loss_history, L) -> bool checked after every iteration (bench.py ends a fit with the same
     rule as its GPU arm); the result carries the wall-clock seconds of every iteration in ``iter_seconds``."""
     import time as _time
     x = np.asarray(x0, dtype=np.float64).copy()
@@ -1010,7 +1010,7 @@ def lm_fit(scene, x0, max_iter=100, relative_tolerance=1e-5, ndf=None, max_step_
         L = dn(L)
         if verbose:
             print(f"Chi^2/DoF: {loss[-1]}, L: {L}")
-        if stop is not None and stop(loss):
+        if stop is not None and stop(loss, L):
             message += "stopped"
             break
         if len(loss) >= 3 and (loss[-3] - loss[-1]) / loss[-1] < relative_tolerance and L < 0.1:
