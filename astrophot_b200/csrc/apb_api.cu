@@ -931,7 +931,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           const CB& cb = cbs[k];
           if (!cb.diag) continue;
           row_of[(size_t)cb.oa * RPS + cb.pa0 / NB_MAX] = (int)prows.size();
-          prows.push_back(PcgRow{cb.oa, cb.pa0, cb.na, 0, 0, cb.off});
+          prows.push_back(PcgRow{cb.oa, cb.pa0, cb.na, 0, 0, cb.off, own_off[cb.oa] + cb.pa0, 0});
           ents.emplace_back();
         }
         for (size_t k = 0; k < cbs.size(); ++k) {
@@ -948,15 +948,15 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         std::vector<int> multi_rows;
         // a row is one warp's work unless it has very many blocks (the sky row couples to every model): then it is
         // split into chunks whose partial rows the solver adds in order
-        const int CH = 128, SPLIT = 512;
+        const int CH = 32, SPLIT = 64;   // one 32-lane sweep per item: the split rows are on the critical path of every iteration
         for (size_t r = 0; r < prows.size(); ++r) {
           const int e0 = (int)flat.size();
           flat.insert(flat.end(), ents[r].begin(), ents[r].end());
           const int e1 = (int)flat.size();
           const bool multi = e1 - e0 > SPLIT;
           prows[r].item0 = (int)pitems.size();
-          if (!multi) pitems.push_back(PcgItem{(int)r, e0, e1, 0});
-          else for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), e == e0 ? 1 : 2});
+          if (!multi) pitems.push_back(PcgItem{(int)r, e0, e1, 0, prows[r].n, prows[r].slot0});
+          else for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), e == e0 ? 1 : 2, prows[r].n, prows[r].slot0});
           prows[r].nitem = (int)pitems.size() - prows[r].item0;
           if (multi) multi_rows.push_back((int)r);
         }
@@ -978,7 +978,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
         // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
-        const int want = std::max(1, std::min(sms * std::min(per_sm, 2), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
+        const int cap_sm = getenv("APB_PCG_PER_SM") ? atoi(getenv("APB_PCG_PER_SM")) : 2;   // (experiments)
+        const int want = std::max(1, std::min(sms * std::min(per_sm, cap_sm), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
         p->pcg_grid = want;
         PRC(own_alloc(p, (void**)&p->d_pcg_part, sizeof(double) * 4 * (size_t)want));
         PRC(own_alloc(p, (void**)&p->d_pcg_bar, sizeof(unsigned int)));

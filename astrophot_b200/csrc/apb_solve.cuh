@@ -26,11 +26,15 @@
 #include "apb_image.cuh"
 
 namespace cg = cooperative_groups;
+#ifndef PCG_SPIN_NS
+#define PCG_SPIN_NS 200
+#endif
 
 struct PcgRow {      // row block: free parameters [p0, p0+n) of owner `src`
   int src, p0, n;
   int item0, nitem;  // its work items (nitem > 1: product split over several warps)
   long long doff;    // offset of its diagonal block (n x n, row-major) in bvals
+  int slot0, _pad;   // act_off[src] + p0: where its parameter indices start in act_slot (one dependent load less)
 };
 struct PcgEntry {    // one block contributing to a row block
   long long off;     // offset of the block in bvals (row-major [i of a][j of b], leading dimension ld)
@@ -42,6 +46,7 @@ struct PcgEntry {    // one block contributing to a row block
 struct PcgItem {     // work item (one warp): entries [e0, e1) of row block rb
   int rb, e0, e1;
   int multi;         // 0: the only item of its row; 1: first, 2: further item of a split row
+  int n, slot0;      // copies of the row's size and slot start: the product does not wait for the row record
 };
 
 struct PcgArgs {
@@ -76,8 +81,8 @@ __device__ __forceinline__ void pcg_barrier(unsigned int* counter, unsigned int&
     goal += gridDim.x;
     __threadfence();
     atomicAdd(counter, 1u);
-    while (*(volatile unsigned int*)counter < goal) {
-    }
+    // (back off between polls: a few hundred CTAs spinning on one L2 line delay the arrivals they are waiting for)
+    while (*(volatile unsigned int*)counter < goal) __nanosleep(PCG_SPIN_NS);
     __threadfence();
   }
   __syncthreads();
@@ -96,28 +101,67 @@ __device__ __forceinline__ double pcg_total(const double* part, int col, int nct
   return r;
 }
 
+// two columns of the per-CTA shares in one pass (r.z and r.r are always wanted together)
+__device__ __forceinline__ void pcg_total2(const double* part, int col_a, int col_b, int ncta, double* sh, double& ta, double& tb) {
+  double va = 0.0, vb = 0.0;
+  for (int k = threadIdx.x; k < ncta; k += 256) {
+    va += __ldcg(part + 4 * k + col_a);
+    vb += __ldcg(part + 4 * k + col_b);
+  }
+  __shared__ double bc[2];
+  const double ra = block_sum<256>(va, sh);
+  if (threadIdx.x == 0) bc[0] = ra;
+  const double rb = block_sum<256>(vb, sh);
+  if (threadIdx.x == 0) bc[1] = rb;
+  __syncthreads();
+  ta = bc[0];
+  tb = bc[1];
+  __syncthreads();
+}
+
 // z = M^-1 r for the diagonal block of one row block (one thread): L L^T z = r.  Returns r.z of the block.
+// The factor (<= 36 numbers) is fetched with independent loads BEFORE the substitutions: read element by element inside
+// them it was a chain of ~70 dependent L2 round trips, the critical path of every iteration (ncu: half of all warp
+// samples waited at the barrier behind it).  Rows beyond the block's size are identity rows.
 __device__ __forceinline__ double pcg_precond(const PcgArgs& A, int rb, const PcgRow& row, const double* rv, double* __restrict__ z) {
-  const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+  const int* sl = A.act_slot + row.slot0;
   const double* F = A.fac + (long long)rb * 64;
+  const int n = row.n;
+  double Fr[NB_MAX * (NB_MAX + 1) / 2];
+  int slr[NB_MAX];
+#pragma unroll
+  for (int i = 0; i < NB_MAX; ++i) {
+    slr[i] = i < n ? sl[i] : 0;
+#pragma unroll
+    for (int k = 0; k <= i; ++k) Fr[i * (i + 1) / 2 + k] = i < n ? F[i * 8 + k] : (i == k ? 1.0 : 0.0);
+  }
   double y[NB_MAX];
-  for (int i = 0; i < row.n; ++i) {
-    double v = rv[i];
-    for (int k = 0; k < i; ++k) v -= F[i * 8 + k] * y[k];
-    y[i] = v / F[i * 8 + i];
+#pragma unroll
+  for (int i = 0; i < NB_MAX; ++i) {
+    double v = i < n ? rv[i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= Fr[i * (i + 1) / 2 + k] * y[k];
+    y[i] = v / Fr[i * (i + 1) / 2 + i];
   }
   double dot = 0.0;
-  for (int i = row.n - 1; i >= 0; --i) {
+#pragma unroll
+  for (int i = NB_MAX - 1; i >= 0; --i) {
     double v = y[i];
-    for (int k = i + 1; k < row.n; ++k) v -= F[k * 8 + i] * y[k];
-    y[i] = v / F[i * 8 + i];
-    z[sl[i]] = y[i];
-    dot = fma(rv[i], y[i], dot);
+#pragma unroll
+    for (int k = i + 1; k < NB_MAX; ++k) v -= Fr[k * (k + 1) / 2 + i] * y[k];
+    y[i] = v / Fr[i * (i + 1) / 2 + i];
+    if (i < n) {
+      z[slr[i]] = y[i];
+      dot = fma(rv[i], y[i], dot);
+    }
   }
   return dot;
 }
 
-__global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
+#ifndef PCG_MINB
+#define PCG_MINB 2
+#endif
+__global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
   unsigned int goal = 0;
   __shared__ double sh[8];
   __shared__ double bc2;
@@ -132,7 +176,10 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
   //      q = A x0, and phase 2 turns it into r = b - q, z = M^-1 r; the iteration proper starts from there.
   bool pre = A.x0 != nullptr;
   double s_rz = 0.0, s_bb = 0.0;
-  for (int rb = gtid; rb < A.n_rows; rb += gsz) {
+  // (row blocks are dealt CTA-first -- row rb to thread rb / #CTAs of CTA rb % #CTAs -- so that every SM works on them
+  //  and each keeps its own few factors in L1; the same mapping in setup and in phase 2)
+  const int rb0 = blockIdx.x + gridDim.x * threadIdx.x;
+  for (int rb = rb0; rb < A.n_rows; rb += gsz) {
     const PcgRow row = A.rows[rb];
     const double* V = A.bvals + row.doff;
     double* F = A.fac + (long long)rb * 64;
@@ -155,7 +202,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
     }
     for (int i = 0; i < row.n; ++i)
       for (int j = 0; j <= i; ++j) F[i * 8 + j] = M[i][j];
-    const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+    const int* sl = A.act_slot + row.slot0;
     double rv[NB_MAX];
     for (int i = 0; i < row.n; ++i) {
       const double bi = A.b[sl[i]];
@@ -176,8 +223,9 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
     if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
   }
   pcg_barrier(A.barrier, goal);
-  double rz = pcg_total(A.part, 1, ncta, sh);
-  const double bb = pcg_total(A.part, 2, ncta, sh);
+  double rz, bb_;
+  pcg_total2(A.part, 1, 2, ncta, sh, rz, bb_);
+  const double bb = bb_;
   double rr = bb, beta = 0.0;
   double* pold = A.pa;
   double* pnew = A.pb;
@@ -188,7 +236,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
       double s_pq = 0.0;
       for (int k = gwarp; k < A.n_items; k += nwarp) {
         const PcgItem w = A.items[k];
-        const PcgRow row = A.rows[w.rb];
+        struct { int n; } row = {w.n};
         // A lane per block: all blocks of a row (up to 32 per sweep) are fetched at once -- the products are tiny, what
         // the phase costs is its chain of dependent L2 loads (item -> row -> entry -> values), so that chain is walked
         // once per sweep, not once per block.  Lane l accumulates its blocks' contribution to all row elements; a
@@ -226,7 +274,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
           if (lane == i) acc = v;
         }
         if (lane < row.n) {
-          const int sl = A.act_slot[A.act_off[row.src] + row.p0 + lane];
+          const int sl = A.act_slot[w.slot0 + lane];
           double v = acc * inv1L;
           if (w.multi < 2) {   // the row's first (or only) item: the damped diagonal, and it stores p
             const double pi = fma(beta, __ldcg(pold + sl), __ldcg(A.z + sl));
@@ -252,7 +300,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         double extra = 0.0;
         for (int m = 0; m < A.n_multi; ++m) {
           const PcgRow row = A.rows[A.multi_rows[m]];
-          const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+          const int* sl = A.act_slot + row.slot0;
           for (int i = 0; i < row.n; ++i) {
             double v = 0.0;
             for (int t = threadIdx.x; t < row.nitem; t += 256) v += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
@@ -272,21 +320,35 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
       const double alpha = pre ? 0.0 : rz / pq;
       // ---- phase 2: x += alpha p; r -= alpha q; z = M^-1 r; shares of r.z and r.r
       double s_rz2 = 0.0, s_rr = 0.0;
-      for (int rb = gtid; rb < A.n_rows; rb += gsz) {
+      for (int rb = rb0; rb < A.n_rows; rb += gsz) {
         const PcgRow row = A.rows[rb];
-        const int* sl = A.act_slot + A.act_off[row.src] + row.p0;
+        const int* sl = A.act_slot + row.slot0;
         double rv[NB_MAX];
-        for (int i = 0; i < row.n; ++i) {
-          const int s = sl[i];
-          const double qi = __ldcg(A.q + s);
+        // (all loads of the row issued before the first use)
+        int ss[NB_MAX];
+        double qv[NB_MAX], pv[NB_MAX], xv[NB_MAX], rr0[NB_MAX];
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) ss[i] = i < row.n ? sl[i] : -1;
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) {
+          const bool on = ss[i] >= 0;
+          qv[i] = on ? __ldcg(A.q + ss[i]) : 0.0;
+          pv[i] = (on && !pre) ? __ldcg(pnew + ss[i]) : 0.0;
+          xv[i] = (on && !pre) ? A.x[ss[i]] : 0.0;
+          rr0[i] = on ? A.r[ss[i]] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NB_MAX; ++i) {
+          rv[i] = 0.0;
+          if (ss[i] < 0) continue;
           double ri;
           if (pre) {
-            ri = A.r[s] - qi;                        // r = b - A x0
+            ri = rr0[i] - qv[i];                        // r = b - A x0
           } else {
-            A.x[s] = fma(alpha, __ldcg(pnew + s), A.x[s]);
-            ri = fma(-alpha, qi, A.r[s]);
+            A.x[ss[i]] = fma(alpha, pv[i], xv[i]);
+            ri = fma(-alpha, qv[i], rr0[i]);
           }
-          A.r[s] = ri;
+          A.r[ss[i]] = ri;
           rv[i] = ri;
           s_rr = fma(ri, ri, s_rr);
         }
@@ -297,8 +359,8 @@ __global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
         if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
       }
       pcg_barrier(A.barrier, goal);
-      const double rz_new = pcg_total(A.part, 1, ncta, sh);
-      rr = pcg_total(A.part, 2, ncta, sh);
+      double rz_new;
+      pcg_total2(A.part, 1, 2, ncta, sh, rz_new, rr);
       if (pre) {            // the iteration proper starts here: p = z
         pre = false;
         rz = rz_new;
