@@ -135,7 +135,9 @@ struct apb_plan {
   bool sparse_ok = false;
   bool any_aux_psf = false;   // PSF stamps depend on a PSF-model source sampled in the same pass
   PcgRow* d_prows = nullptr; int n_prows = 0;
-  PcgEntry* d_pentries = nullptr;
+  PcgPass* d_ppasses = nullptr; int n_ppass = 0;
+  int *d_pack_src = nullptr, *d_pslots = nullptr;
+  double* d_packed = nullptr; long long n_ppacked = 0;
   PcgItem* d_pitems = nullptr; int n_pitems = 0;
   double *d_bvals = nullptr, *d_diagH = nullptr, *d_pfac = nullptr, *d_pvec = nullptr;
   double* d_bvals_own = nullptr;   // the plan's own [blocks | diag H] array (d_bvals may point at a caller's, apb_plan_bind_blocks)
@@ -946,24 +948,94 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         std::vector<PcgEntry> flat;
         std::vector<PcgItem> pitems;
         std::vector<int> multi_rows;
-        // a row is one warp's work unless it has very many blocks (the sky row couples to every model): then it is
-        // split into chunks whose partial rows the solver adds in order
-        const int CH = 32, SPLIT = 64;   // one 32-lane sweep per item: the split rows are on the critical path of every iteration
+        // a row is one work item unless it has very many blocks (the sky row couples to every model): then it is
+        // split into chunks whose partial rows the solver adds in order.  A row's widest blocks go first (the lanes of
+        // one sweep then hold blocks of similar width: less padding in the packed copy).
+        const int SPLIT = 64, CH = 8;
         for (size_t r = 0; r < prows.size(); ++r) {
+          std::stable_sort(ents[r].begin(), ents[r].end(), [](const PcgEntry& x, const PcgEntry& y) { return x.n > y.n; });
           const int e0 = (int)flat.size();
           flat.insert(flat.end(), ents[r].begin(), ents[r].end());
           const int e1 = (int)flat.size();
           const bool multi = e1 - e0 > SPLIT;
-          prows[r].item0 = (int)pitems.size();
           if (!multi) pitems.push_back(PcgItem{(int)r, e0, e1, 0, prows[r].n, prows[r].slot0});
           else for (int e = e0; e < e1; e += CH) pitems.push_back(PcgItem{(int)r, e, std::min(e + CH, e1), e == e0 ? 1 : 2, prows[r].n, prows[r].slot0});
-          prows[r].nitem = (int)pitems.size() - prows[r].item0;
           if (multi) multi_rows.push_back((int)r);
         }
+        // lanes per item: enough for one sweep (8 / 16 / 32; NB_MAX at least: lane i of the group finishes row element i)
+        auto lanes_of = [](const PcgItem& w) { const int e = w.e1 - w.e0; return e <= 8 ? 8 : e <= 16 ? 16 : 32; };
+        // work items in the order the solver deals them: whole rows, widest groups and most blocks first (then tallest
+        // first), then the chunks of the split rows (kept together: their partial rows are added in item order)
+        {
+          std::vector<int> ord(pitems.size());
+          for (size_t k = 0; k < ord.size(); ++k) ord[k] = (int)k;
+          std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+            const PcgItem &wx = pitems[x], &wy = pitems[y];
+            if ((wx.multi != 0) != (wy.multi != 0)) return wx.multi == 0;
+            if (wx.multi) return false;
+            if (lanes_of(wx) != lanes_of(wy)) return lanes_of(wx) > lanes_of(wy);
+            const int sx = (wx.e1 - wx.e0 + 31) / 32, sy = (wy.e1 - wy.e0 + 31) / 32;
+            if (sx != sy) return sx > sy;
+            return wx.n > wy.n;
+          });
+          std::vector<PcgItem> sorted(pitems.size());
+          for (size_t k = 0; k < ord.size(); ++k) sorted[k] = pitems[ord[k]];
+          pitems.swap(sorted);
+          for (auto& r : prows) { r.item0 = -1; r.nitem = 0; }
+          for (size_t k = 0; k < pitems.size(); ++k) {
+            PcgRow& r = prows[pitems[k].rb];
+            if (r.item0 < 0) r.item0 = (int)k;
+            r.nitem++;
+          }
+        }
+        // packed tables (PcgPass): consecutive items with the same group width share a warp
+        std::vector<PcgPass> passes;
+        std::vector<int> pack_src, pslots;
+        for (size_t k0 = 0; k0 < pitems.size();) {
+          const int G = lanes_of(pitems[k0]);
+          int nit = 0, nsweep = 0, ni = 0, nj = 0;
+          while (nit < 32 / G && k0 + nit < pitems.size() && lanes_of(pitems[k0 + nit]) == G) {
+            const PcgItem& w = pitems[k0 + nit];
+            nsweep = std::max(nsweep, (w.e1 - w.e0 + G - 1) / G);
+            ni = std::max(ni, w.n);
+            for (int e = w.e0; e < w.e1; ++e) nj = std::max(nj, flat[e].n);
+            ++nit;
+          }
+          if ((long long)pack_src.size() + (long long)nsweep * ni * nj * 32 > 0x7fffffffLL) PFAIL("block-sparse solver: packed matrix too large");
+          passes.push_back(PcgPass{(long long)pack_src.size(), (int)pslots.size(), ni, nj, nsweep, (int)k0, nit, G, 0});
+          for (int sw = 0; sw < nsweep; ++sw) {
+            const PcgEntry* le[32];
+            int ln[32];
+            for (int l = 0; l < 32; ++l) {
+              le[l] = nullptr; ln[l] = 0;
+              if (l / G >= nit) continue;
+              const PcgItem& w = pitems[k0 + l / G];
+              const int e = w.e0 + sw * G + l % G;
+              if (e >= w.e1) continue;
+              le[l] = &flat[e]; ln[l] = w.n;
+            }
+            for (int i = 0; i < ni; ++i)
+              for (int j = 0; j < nj; ++j)
+                for (int l = 0; l < 32; ++l) {
+                  long long o = -1;
+                  if (le[l] && i < ln[l] && j < le[l]->n) o = le[l]->off + (le[l]->transposed ? (long long)j * le[l]->ld + i : (long long)i * le[l]->ld + j);
+                  if (o > 0x7fffffffLL) PFAIL("block-sparse solver: block values beyond the packed index range");
+                  pack_src.push_back((int)o);
+                }
+            for (int j = 0; j < nj; ++j)
+              for (int l = 0; l < 32; ++l) pslots.push_back(le[l] && j < le[l]->n ? le[l]->sl[j] : -1);
+          }
+          k0 += nit;
+        }
+        p->n_ppass = (int)passes.size(); p->n_ppacked = (long long)pack_src.size();
+        if (getenv("APB_PCG_DEBUG")) fprintf(stderr, "pcg: %zu rows, %zu items, %zu passes, %zu packed doubles (%lld tight), %zu slots\n", prows.size(), pitems.size(), passes.size(), pack_src.size(), (long long)p->n_bvals, pslots.size());
+        PRC(own_upload(p, passes, &p->d_ppasses));
+        PRC(own_upload(p, pack_src, &p->d_pack_src));
+        PRC(own_upload(p, pslots, &p->d_pslots));
+        PRC(own_alloc(p, (void**)&p->d_packed, sizeof(double) * std::max<size_t>(pack_src.size(), 1)));
         p->n_prows = (int)prows.size(); p->n_pitems = (int)pitems.size();
         p->n_cblocks = (long long)cbs.size();
         PRC(own_upload(p, prows, &p->d_prows));
-        PRC(own_upload(p, flat, &p->d_pentries));
         PRC(own_upload(p, pitems, &p->d_pitems));
         PRC(own_upload(p, own_slot, &p->d_own_slot));
         PRC(own_upload(p, own_off, &p->d_own_off));
@@ -972,14 +1044,14 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         PRC(own_alloc(p, (void**)&p->d_bvals_own, sizeof(double) * ((size_t)p->n_bvals + (size_t)n_par)));
         p->d_bvals = p->d_bvals_own; p->d_diagH = p->d_bvals + p->n_bvals;
         PRC(own_alloc(p, (void**)&p->d_pfac, sizeof(double) * 64 * std::max<size_t>(prows.size(), 1)));
-        PRC(own_alloc(p, (void**)&p->d_pvec, sizeof(double) * 5 * (size_t)n_par));
+        PRC(own_alloc(p, (void**)&p->d_pvec, sizeof(double) * 6 * (size_t)n_par));
         int dev = 0, sms = 148, per_sm = 1;
         PCU(cudaGetDevice(&dev));
         PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
         // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
         const int cap_sm = getenv("APB_PCG_PER_SM") ? atoi(getenv("APB_PCG_PER_SM")) : 2;   // (experiments)
-        const int want = std::max(1, std::min(sms * std::min(per_sm, cap_sm), ceil_div(std::max(p->n_pitems, p->n_prows / 32 + 1), 8)));
+        const int want = std::max(1, std::min(sms * std::min(per_sm, cap_sm), ceil_div(std::max(p->n_ppass, p->n_prows / 32 + 1), 8)));
         p->pcg_grid = want;
         PRC(own_alloc(p, (void**)&p->d_pcg_part, sizeof(double) * 4 * (size_t)want));
         PRC(own_alloc(p, (void**)&p->d_pcg_bar, sizeof(unsigned int)));
@@ -1562,13 +1634,14 @@ extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, con
   if (!p->sparse_ok) return 1;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = (size_t)p->n_par;
-  PcgArgs A{p->d_prows, p->n_prows, p->d_pentries, p->d_pitems, p->n_pitems, p->d_multi_rows, p->n_multi,
-            p->d_own_slot, p->d_own_off, p->d_bvals, p->d_diagH, p->d_pfac, g, x0, h, p->d_pvec, p->d_pvec + P,
-            p->d_pvec + 2 * P, p->d_pvec + 3 * P, p->d_pvec + 4 * P, p->d_qpart, p->d_pcg_part, p->d_pcg_bar,
+  PcgArgs A{p->d_prows, p->n_prows, p->d_ppasses, p->n_ppass, p->d_packed, p->d_pslots, p->d_pitems, p->n_pitems, p->d_multi_rows, p->n_multi,
+            p->d_own_slot, p->d_own_off, p->d_bvals, p->d_diagH, p->d_pfac, g, x0, h, p->d_pvec, p->d_pvec + 2 * P,
+            p->d_pvec + 4 * P, p->d_pvec + 5 * P, p->d_qpart, p->d_pcg_part, p->d_pcg_bar,
             info, p->n_par, max_iter > 0 ? max_iter : 2000, L, tol > 0.0 ? tol : 1e-14};
   void* args[] = {&A};
   CU(cudaMemsetAsync(p->d_pcg_bar, 0, sizeof(unsigned int), st));
   p->pbegin(K_PCG, st);
+  k_pcg_pack<<<296, 256, 0, st>>>(p->d_bvals, p->d_pack_src, p->d_packed, p->n_ppacked);
   CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(256), args, 0, st));
   p->pend(st);
   g_launches++;
@@ -1777,3 +1850,9 @@ extern "C" int apb_comm_destroy(apb_comm_t* c) {
   delete c;
   return 0;
 }
+
+#ifdef PCG_TIMING
+extern "C" int apb_debug_pcg_clk(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_pcg_clk, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -36,12 +36,26 @@ struct PcgRow {      // row block: free parameters [p0, p0+n) of owner `src`
   long long doff;    // offset of its diagonal block (n x n, row-major) in bvals
   int slot0, _pad;   // act_off[src] + p0: where its parameter indices start in act_slot (one dependent load less)
 };
-struct PcgEntry {    // one block contributing to a row block
+struct PcgEntry {    // one block contributing to a row block (host side: the packed tables below are built from these)
   long long off;     // offset of the block in bvals (row-major [i of a][j of b], leading dimension ld)
   int ld;
   int transposed;    // 1: the row block is the block's b side
   int n;             // parameters of the other side
-  int sl[NB_MAX];    // their indices in x (held here: one dependent load less per product)
+  int sl[NB_MAX];    // their indices in x
+};
+// The product walks the matrix in the order the lanes want it: a warp takes 4, 2 or 1 work items at a time (a "pass":
+// 8, 16 or 32 lanes per item, by the number of blocks in the row, so that nearly every row is done in ONE sweep), each
+// lane one block of its item per "sweep", and the values of a sweep are stored element-major, lane-minor -- element
+// (i, j) of all 32 lanes' blocks in 32 consecutive doubles, ni x nj elements (the largest block of the pass; smaller
+// ones are zero-padded), transposition resolved.  Read straight from the tightly packed blocks a
+// lane-per-block product touched 32 different lines per load instruction, and the load/store unit's serialisation of
+// those was the solver's critical path (20 of 33 us per iteration).  k_pcg_pack refreshes the packed copy from the
+// block values before every solve.
+struct PcgPass {     // one warp's share of the product: `nit` work items, g lanes each, `nsweep` sweeps of one block per lane
+  long long voff;    // its values in `packed`: nsweep x (ni x nj x 32)
+  int soff;          // its x indices in `pslots`: nsweep x (nj x 32)
+  int ni, nj, nsweep;
+  int item0, nit, g, _pad;
 };
 struct PcgItem {     // work item (one warp): entries [e0, e1) of row block rb
   int rb, e0, e1;
@@ -51,7 +65,8 @@ struct PcgItem {     // work item (one warp): entries [e0, e1) of row block rb
 
 struct PcgArgs {
   const PcgRow* rows; int n_rows;
-  const PcgEntry* entries;
+  const PcgPass* passes; int n_pass;
+  const double* packed; const int* pslots;
   const PcgItem* items; int n_items;
   const int* multi_rows; int n_multi;   // rows split over several items
   const int* act_slot; const int* act_off;
@@ -61,7 +76,8 @@ struct PcgArgs {
   const double* b;         // right-hand side (P)
   const double* x0;        // starting point (P) or NULL = 0 (the previous lambda-trial's solution is a good one)
   double* x;               // solution (P)
-  double *r, *z, *pa, *pb, *q;   // work vectors (P)
+  double *zp0, *zp1;       // work vectors: (z, p) pairs, double-buffered (2P each, 16-byte aligned)
+  double *r, *q;           // ... residual and A p (P)
   double* qpart;           // n_items x 8: partial rows of split rows
   double* part;            // gridDim x 4: per-CTA shares of the dot products
   unsigned int* barrier;   // arrival counter of pcg_barrier, zero at launch
@@ -70,53 +86,62 @@ struct PcgArgs {
   double L, tol;
 };
 
-// Grid barrier for the (cooperatively launched, hence co-resident) CTAs of k_pcg.  cooperative_groups' grid.sync()
-// invalidates the whole L1 at every barrier, which sends every load of the solver's read-only tables (work items, row
-// blocks, block values: the same ones every iteration) back to L2 -- measured: the phases were chains of ~7 dependent
-// L2 round trips.  Here the vectors that change hands between CTAs are read with ld.cg (L2) and written through, the
-// barrier is a monotonic arrival counter (zeroed before the launch), and the tables stay in L1.
+// Grid barrier for the (cooperatively launched, hence co-resident) CTAs of k_pcg.  cooperative_groups' grid.sync() --
+// and any acquire fence: __threadfence() compiles to MEMBAR + CCTL.IVALL -- invalidates the whole L1 at every barrier,
+// which sends every load of the solver's read-only tables (passes, x indices, the packed matrix: the same ones every
+// iteration, ~130 KB per SM) back to L2; the product then was a chain of L2 round trips (ncu: 18 us of a 25 us
+// iteration).  Here the arrival is a release-ordered reduction (everything this CTA wrote is in L2 before the count
+// moves), the wait is a relaxed poll with NO acquire fence, and every vector that changes hands between CTAs is read with
+// ld.cg (L2) after the block barrier that follows the poll: L1 only ever holds data nobody writes during the kernel
+// (or that only its own thread writes), so it stays valid.
 __device__ __forceinline__ void pcg_barrier(unsigned int* counter, unsigned int& goal) {
   __syncthreads();
   if (threadIdx.x == 0) {
     goal += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
     // (back off between polls: a few hundred CTAs spinning on one L2 line delay the arrivals they are waiting for)
-    while (*(volatile unsigned int*)counter < goal) __nanosleep(PCG_SPIN_NS);
-    __threadfence();
+    unsigned int seen;
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen >= goal) break;
+      __nanosleep(PCG_SPIN_NS);
+    }
   }
   __syncthreads();
 }
 
-// sum of one column of the per-CTA shares, same order in every CTA
-__device__ __forceinline__ double pcg_total(const double* part, int col, int ncta, double* sh) {
-  double v = 0.0;
-  for (int k = threadIdx.x; k < ncta; k += 256) v += __ldcg(part + 4 * k + col);
-  double r = block_sum<256>(v, sh);
-  __shared__ double bc;
-  if (threadIdx.x == 0) bc = r;
+// Sum of NV values over the CTA's 256 threads, result in every thread (same bits: the butterfly's additions commute),
+// two block barriers for all NV.
+template <int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV]) {
+  __shared__ double shn[8 * NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) shn[(threadIdx.x >> 5) * NV + k] = v[k];
+  }
   __syncthreads();
-  r = bc;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += shn[w * NV + k];
+    v[k] = t;
+  }
   __syncthreads();
-  return r;
 }
 
 // two columns of the per-CTA shares in one pass (r.z and r.r are always wanted together)
 __device__ __forceinline__ void pcg_total2(const double* part, int col_a, int col_b, int ncta, double* sh, double& ta, double& tb) {
-  double va = 0.0, vb = 0.0;
+  double v[2] = {0.0, 0.0};
   for (int k = threadIdx.x; k < ncta; k += 256) {
-    va += __ldcg(part + 4 * k + col_a);
-    vb += __ldcg(part + 4 * k + col_b);
+    v[0] += __ldcg(part + 4 * k + col_a);
+    v[1] += __ldcg(part + 4 * k + col_b);
   }
-  __shared__ double bc[2];
-  const double ra = block_sum<256>(va, sh);
-  if (threadIdx.x == 0) bc[0] = ra;
-  const double rb = block_sum<256>(vb, sh);
-  if (threadIdx.x == 0) bc[1] = rb;
-  __syncthreads();
-  ta = bc[0];
-  tb = bc[1];
-  __syncthreads();
+  block_sum_n<2>(v);
+  ta = v[0];
+  tb = v[1];
 }
 
 // z = M^-1 r for the diagonal block of one row block (one thread): L L^T z = r.  Returns r.z of the block.
@@ -141,7 +166,7 @@ __device__ __forceinline__ double pcg_precond(const PcgArgs& A, int rb, const Pc
     double v = i < n ? rv[i] : 0.0;
 #pragma unroll
     for (int k = 0; k < i; ++k) v -= Fr[i * (i + 1) / 2 + k] * y[k];
-    y[i] = v / Fr[i * (i + 1) / 2 + i];
+    y[i] = v * Fr[i * (i + 1) / 2 + i];
   }
   double dot = 0.0;
 #pragma unroll
@@ -149,25 +174,48 @@ __device__ __forceinline__ double pcg_precond(const PcgArgs& A, int rb, const Pc
     double v = y[i];
 #pragma unroll
     for (int k = i + 1; k < NB_MAX; ++k) v -= Fr[k * (k + 1) / 2 + i] * y[k];
-    y[i] = v / Fr[i * (i + 1) / 2 + i];
+    y[i] = v * Fr[i * (i + 1) / 2 + i];
     if (i < n) {
-      z[slr[i]] = y[i];
+      z[2 * slr[i]] = y[i];
       dot = fma(rv[i], y[i], dot);
     }
   }
   return dot;
 }
 
+// packed copy of the block values (see PcgSlice): out[t] = bvals[src[t]], 0 where src[t] < 0
+__global__ void __launch_bounds__(256) k_pcg_pack(const double* __restrict__ bvals, const int* __restrict__ src,
+                                                  double* __restrict__ out, long long n) {
+  for (long long t = blockIdx.x * 256ll + threadIdx.x; t < n; t += gridDim.x * 256ll) {
+    const int o = src[t];
+    out[t] = o >= 0 ? bvals[o] : 0.0;
+  }
+}
+
 #ifndef PCG_MINB
 #define PCG_MINB 2
+#endif
+#ifdef PCG_TIMING   // development builds only: where the time of an iteration goes (globaltimer ns, CTA 0 and the last CTA)
+__device__ unsigned long long g_pcg_clk[2][8];
+__device__ __forceinline__ unsigned long long pcg_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PCG_MARK(k)                                                                     \
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {           \
+    const unsigned long long t_ = pcg_now();                                            \
+    g_pcg_clk[blockIdx.x == 0 ? 0 : 1][k] += t_ - tmark;                                \
+    tmark = t_;                                                                         \
+  }
+#else
+#define PCG_MARK(k)
 #endif
 __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
   unsigned int goal = 0;
   __shared__ double sh[8];
-  __shared__ double bc2;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  const int gwarp = gtid >> 5, nwarp = gsz >> 5;
   const int ncta = gridDim.x;
   const double inv1L = 1.0 / (1.0 + A.L);
 
@@ -200,8 +248,8 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
         M[i][j] = v / d;
       }
     }
-    for (int i = 0; i < row.n; ++i)
-      for (int j = 0; j <= i; ++j) F[i * 8 + j] = M[i][j];
+    for (int i = 0; i < row.n; ++i)   // (the diagonal is stored inverted: the substitutions multiply)
+      for (int j = 0; j <= i; ++j) F[i * 8 + j] = i == j ? 1.0 / M[i][j] : M[i][j];
     const int* sl = A.act_slot + row.slot0;
     double rv[NB_MAX];
     for (int i = 0; i < row.n; ++i) {
@@ -209,13 +257,13 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
       rv[i] = bi;
       A.x[sl[i]] = pre ? A.x0[sl[i]] : 0.0;
       A.r[sl[i]] = bi;
-      A.pa[sl[i]] = 0.0;
+      A.zp0[2 * sl[i] + 1] = 0.0;
       s_bb = fma(bi, bi, s_bb);
     }
     if (pre) {
-      for (int i = 0; i < row.n; ++i) A.z[sl[i]] = A.x0[sl[i]];
+      for (int i = 0; i < row.n; ++i) A.zp0[2 * sl[i]] = A.x0[sl[i]];
     } else {
-      s_rz += pcg_precond(A, rb, row, rv, A.z);
+      s_rz += pcg_precond(A, rb, row, rv, A.zp0);
     }
   }
   {
@@ -227,95 +275,130 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
   pcg_total2(A.part, 1, 2, ncta, sh, rz, bb_);
   const double bb = bb_;
   double rr = bb, beta = 0.0;
-  double* pold = A.pa;
-  double* pnew = A.pb;
+  // (z, p) pairs: the product reads z and the previous direction of a parameter with ONE 16-byte request
+  double* pold = A.zp0;
+  double* pnew = A.zp1;
   int it = 0;
+#ifdef PCG_TIMING
+  unsigned long long tmark = pcg_now();
+#endif
   if (bb > 0.0) {
     for (; it < A.max_iter;) {
-      // ---- phase 1: p = z + beta p_old (on the fly), q = A p, share of p.q.  One warp per work item.
+      // ---- phase 1: p = z + beta p_old (on the fly), q = A p, share of p.q.  A group of lanes per work item.
+      // What the phase costs is its chain of dependent loads (pass -> x indices -> p of the other side -> lane
+      // reduction -> store), a few microseconds however little arithmetic hangs on it: the grid covers all passes at
+      // once (heaviest first, dealt CTA-first so that every SM gets its share), and a pass is one sweep for all but
+      // the rows with more than 32 blocks.
       double s_pq = 0.0;
-      for (int k = gwarp; k < A.n_items; k += nwarp) {
-        const PcgItem w = A.items[k];
-        struct { int n; } row = {w.n};
-        // A lane per block: all blocks of a row (up to 32 per sweep) are fetched at once -- the products are tiny, what
-        // the phase costs is its chain of dependent L2 loads (item -> row -> entry -> values), so that chain is walked
-        // once per sweep, not once per block.  Lane l accumulates its blocks' contribution to all row elements; a
-        // shuffle tree adds the lanes (fixed order).
+      for (int wp = blockIdx.x + gridDim.x * (threadIdx.x >> 5); wp < A.n_pass; wp += gridDim.x * 8) {
+        const PcgPass ps = A.passes[wp];
+        const int G = ps.g, sub = lane / G, gl = lane & (G - 1);
+        const int k = ps.item0 + sub;
+        PcgItem w = {0, 0, 0, 0, 0, 0};
+        if (sub < ps.nit) w = A.items[k];
+        // Lane l accumulates its blocks' contribution to all row elements; a shuffle tree over the group adds the lanes
+        // (fixed order).
         double racc[NB_MAX];
 #pragma unroll
         for (int i = 0; i < NB_MAX; ++i) racc[i] = 0.0;
-        for (int e = w.e0 + lane; e < w.e1; e += 32) {
-          const PcgEntry en = A.entries[e];
-          const double* V = A.bvals + en.off;
+        const double* V = A.packed + ps.voff + lane;
+        const int* SL = A.pslots + ps.soff + lane;
+        for (int sw = 0; sw < ps.nsweep; ++sw) {
+          // (loads in batches, each batch issued before its first use: written load-by-load the compiler kept ONE value
+          //  register and waited out every load's latency in turn)
           double pj[NB_MAX];
+          int sjv[NB_MAX];
+          double2 zp[NB_MAX];
 #pragma unroll
-          for (int j = 0; j < NB_MAX; ++j) {
-            const bool on = j < en.n;
-            const int sj = en.sl[on ? j : 0];
-            pj[j] = on ? fma(beta, __ldcg(pold + sj), __ldcg(A.z + sj)) : 0.0;
-          }
+          for (int j = 0; j < NB_MAX; ++j) sjv[j] = j < ps.nj ? SL[j * 32] : -1;   // (-1: beyond this lane's block, or no block)
 #pragma unroll
-          for (int i = 0; i < NB_MAX; ++i) {
-            if (i < row.n) {
-              double a = 0.0;
+          for (int j = 0; j < NB_MAX; ++j) zp[j] = sjv[j] >= 0 ? __ldcg((const double2*)pold + sjv[j]) : make_double2(0.0, 0.0);
 #pragma unroll
-              for (int j = 0; j < NB_MAX; ++j)
-                if (j < en.n) a = fma(en.transposed ? V[j * en.ld + i] : V[i * en.ld + j], pj[j], a);
+          for (int j = 0; j < NB_MAX; ++j) pj[j] = fma(beta, zp[j].y, zp[j].x);
+#pragma unroll
+          for (int i = 0; i < NB_MAX; i += 2) {
+            if (i < ps.ni) {      // (padding is never fetched: per-lane predicates on the loads)
+              double va[NB_MAX], vb[NB_MAX];
+#pragma unroll
+              for (int j = 0; j < NB_MAX; ++j) {
+                va[j] = (sjv[j] >= 0 && i < w.n) ? V[(i * ps.nj + j) * 32] : 0.0;
+                vb[j] = (sjv[j] >= 0 && i + 1 < w.n) ? V[((i + 1) * ps.nj + j) * 32] : 0.0;
+              }
+              double a = 0.0, b = 0.0;
+#pragma unroll
+              for (int j = 0; j < NB_MAX; ++j) {
+                a = fma(va[j], pj[j], a);
+                b = fma(vb[j], pj[j], b);
+              }
               racc[i] += a;
+              racc[i + 1] += b;
             }
           }
+          V += ps.ni * ps.nj * 32;
+          SL += ps.nj * 32;
         }
+        __syncwarp();
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < NB_MAX; ++i) {
           double v = racc[i];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == i) acc = v;
+          for (int o = 16; o > 0; o >>= 1)
+            if (o < G) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (gl == i) acc = v;
         }
-        if (lane < row.n) {
-          const int sl = A.act_slot[w.slot0 + lane];
+        if (gl < w.n) {
+          const int sl = A.act_slot[w.slot0 + gl];
+          const double2 zp = __ldcg((const double2*)pold + sl);
+          const double pi = fma(beta, zp.y, zp.x);
           double v = acc * inv1L;
           if (w.multi < 2) {   // the row's first (or only) item: the damped diagonal, and it stores p
-            const double pi = fma(beta, __ldcg(pold + sl), __ldcg(A.z + sl));
             const double d = A.diagH[sl];
             v += (d + A.L * (1.0 + d) - d * inv1L) * pi;
-            pnew[sl] = pi;
-            if (!w.multi) {
-              A.q[sl] = v;
-              s_pq = fma(pi, v, s_pq);
-            }
+            pnew[2 * sl + 1] = pi;
           }
-          if (w.multi) A.qpart[(long long)k * 8 + lane] = v;
+          if (!w.multi) A.q[sl] = v;
+          else A.qpart[(long long)k * 8 + gl] = v;
+          s_pq = fma(pi, v, s_pq);   // (a split row's p.q is the sum of its items' p.(partial row))
         }
       }
+      PCG_MARK(0)
       {
         const double t0 = block_sum<256>(s_pq, sh);
         if (threadIdx.x == 0) A.part[4 * blockIdx.x + 0] = t0;
       }
       pcg_barrier(A.barrier, goal);
-      // ---- alpha.  Split rows: every CTA adds their partial rows (same order everywhere), stores q and adds p.q
-      double pq = pcg_total(A.part, 0, ncta, sh);
+      PCG_MARK(1)
+      // ---- alpha.  Split rows: every CTA adds their partial rows (same order everywhere) and stores q; the row's
+      //      owner reads the copy its own CTA wrote.  One fused reduction: p.q and up to three row elements at a time.
+      double pq = 0.0;
       {
-        double extra = 0.0;
-        for (int m = 0; m < A.n_multi; ++m) {
-          const PcgRow row = A.rows[A.multi_rows[m]];
-          const int* sl = A.act_slot + row.slot0;
-          for (int i = 0; i < row.n; ++i) {
-            double v = 0.0;
-            for (int t = threadIdx.x; t < row.nitem; t += 256) v += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
-            const double qi = block_sum<256>(v, sh);
-            if (threadIdx.x == 0) {
-              A.q[sl[i]] = qi;   // every CTA stores the same value; the row's owner reads the copy its own CTA wrote
-              extra = fma(__ldcg(pnew + sl[i]), qi, extra);
-            }
+        int m = 0, i = 0;
+        for (bool first = true; first || m < A.n_multi; first = false) {
+          double v[4] = {0.0, 0.0, 0.0, 0.0};
+          int dst[4] = {-1, -1, -1, -1};
+          int c = 0;
+          if (first) {
+            for (int k = threadIdx.x; k < ncta; k += 256) v[0] += __ldcg(A.part + 4 * k + 0);
+            c = 1;
+          }
+          for (; c < 4 && m < A.n_multi; ++c) {
+            const PcgRow row = A.rows[A.multi_rows[m]];
+            for (int t = threadIdx.x; t < row.nitem; t += 256) v[c] += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
+            dst[c] = A.act_slot[row.slot0 + i];
+            if (++i == row.n) { i = 0; ++m; }
+          }
+          block_sum_n<4>(v);
+          if (first) pq = v[0];
+          if (threadIdx.x == 0) {
+#pragma unroll
+            for (int c2 = 0; c2 < 4; ++c2)
+              if (dst[c2] >= 0) A.q[dst[c2]] = v[c2];
           }
         }
-        if (threadIdx.x == 0) bc2 = extra;
-        __syncthreads();
-        pq += bc2;
         __syncthreads();
       }
+      PCG_MARK(2)
       if (!pre && !(pq > 0.0)) break;
       const double alpha = pre ? 0.0 : rz / pq;
       // ---- phase 2: x += alpha p; r -= alpha q; z = M^-1 r; shares of r.z and r.r
@@ -333,7 +416,7 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
         for (int i = 0; i < NB_MAX; ++i) {
           const bool on = ss[i] >= 0;
           qv[i] = on ? __ldcg(A.q + ss[i]) : 0.0;
-          pv[i] = (on && !pre) ? __ldcg(pnew + ss[i]) : 0.0;
+          pv[i] = (on && !pre) ? __ldcg(pnew + 2 * ss[i] + 1) : 0.0;
           xv[i] = (on && !pre) ? A.x[ss[i]] : 0.0;
           rr0[i] = on ? A.r[ss[i]] : 0.0;
         }
@@ -352,15 +435,18 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
           rv[i] = ri;
           s_rr = fma(ri, ri, s_rr);
         }
-        s_rz2 += pcg_precond(A, rb, row, rv, A.z);
+        s_rz2 += pcg_precond(A, rb, row, rv, pnew);
       }
+      PCG_MARK(3)
       {
         const double t0 = block_sum<256>(s_rz2, sh), t1 = block_sum<256>(s_rr, sh);
         if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
       }
       pcg_barrier(A.barrier, goal);
+      PCG_MARK(4)
       double rz_new;
       pcg_total2(A.part, 1, 2, ncta, sh, rz_new, rr);
+      PCG_MARK(5)
       if (pre) {            // the iteration proper starts here: p = z
         pre = false;
         rz = rz_new;

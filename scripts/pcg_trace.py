@@ -25,3 +25,14 @@ lm._solve = traced
 lm.fit()
 print(json.dumps({"loss": lm.loss_history, "L_history": lm.L_history}))
 for r in trace: print(json.dumps(r))
+try:
+    import ctypes as C
+    from astrophot_b200 import cabi
+    buf = (C.c_ulonglong * 16)()
+    if cabi.lib().apb_debug_pcg_clk(buf) == 0:
+        its = sum(r["its"][0] for r in trace)
+        names = ["phase1", "barrier1", "alpha+split", "phase2", "barrier2", "totals"]
+        for c in range(2):
+            print("cta", "first" if c == 0 else "last", {n: round(buf[8 * c + k] / its / 1e3, 2) for k, n in enumerate(names)}, "us/iteration")
+except AttributeError:
+    pass
