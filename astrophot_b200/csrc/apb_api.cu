@@ -1048,10 +1048,10 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         int dev = 0, sms = 148, per_sm = 1;
         PCU(cudaGetDevice(&dev));
         PCU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, 256, 0));
+        PCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, PCG_NT, 0));
         // enough warps for the work items, never more CTAs than can be co-resident (grid barrier)
-        const int cap_sm = getenv("APB_PCG_PER_SM") ? atoi(getenv("APB_PCG_PER_SM")) : 2;   // (experiments)
-        const int want = std::max(1, std::min(sms * std::min(per_sm, cap_sm), ceil_div(std::max(p->n_ppass, p->n_prows / 32 + 1), 8)));
+        const int cap_sm = PCG_MINB;
+        const int want = std::max(1, std::min(sms * std::min(per_sm, cap_sm), ceil_div(std::max(p->n_ppass, p->n_prows / 32 + 1), PCG_NT / 32)));
         p->pcg_grid = want;
         PRC(own_alloc(p, (void**)&p->d_pcg_part, sizeof(double) * 4 * (size_t)want));
         PRC(own_alloc(p, (void**)&p->d_pcg_bar, sizeof(unsigned int)));
@@ -1642,7 +1642,7 @@ extern "C" int apb_lm_solve_sparse(apb_plan_t* p, const double* g, double L, con
   CU(cudaMemsetAsync(p->d_pcg_bar, 0, sizeof(unsigned int), st));
   p->pbegin(K_PCG, st);
   k_pcg_pack<<<296, 256, 0, st>>>(p->d_bvals, p->d_pack_src, p->d_packed, p->n_ppacked);
-  CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(256), args, 0, st));
+  CU(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(p->pcg_grid), dim3(PCG_NT), args, 0, st));
   p->pend(st);
   g_launches++;
   return 0;

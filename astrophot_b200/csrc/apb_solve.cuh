@@ -26,6 +26,10 @@
 #include "apb_image.cuh"
 
 namespace cg = cooperative_groups;
+#ifndef PCG_NT
+#define PCG_NT 256     // threads per CTA, and CTAs per SM (the grid barrier's cost grows with the number of CTAs)
+#define PCG_MINB 2
+#endif
 #ifndef PCG_SPIN_NS
 #define PCG_SPIN_NS 200
 #endif
@@ -110,11 +114,11 @@ __device__ __forceinline__ void pcg_barrier(unsigned int* counter, unsigned int&
   __syncthreads();
 }
 
-// Sum of NV values over the CTA's 256 threads, result in every thread (same bits: the butterfly's additions commute),
+// Sum of NV values over the CTA's threads, result in every thread (same bits: the butterfly's additions commute),
 // two block barriers for all NV.
 template <int NV>
 __device__ __forceinline__ void block_sum_n(double (&v)[NV]) {
-  __shared__ double shn[8 * NV];
+  __shared__ double shn[PCG_NT / 32 * NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
 #pragma unroll
@@ -126,16 +130,16 @@ __device__ __forceinline__ void block_sum_n(double (&v)[NV]) {
   for (int k = 0; k < NV; ++k) {
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += shn[w * NV + k];
+    for (int w = 0; w < PCG_NT / 32; ++w) t += shn[w * NV + k];
     v[k] = t;
   }
   __syncthreads();
 }
 
 // two columns of the per-CTA shares in one pass (r.z and r.r are always wanted together)
-__device__ __forceinline__ void pcg_total2(const double* part, int col_a, int col_b, int ncta, double* sh, double& ta, double& tb) {
+__device__ __forceinline__ void pcg_total2(const double* part, int col_a, int col_b, int ncta, double& ta, double& tb) {
   double v[2] = {0.0, 0.0};
-  for (int k = threadIdx.x; k < ncta; k += 256) {
+  for (int k = threadIdx.x; k < ncta; k += PCG_NT) {
     v[0] += __ldcg(part + 4 * k + col_a);
     v[1] += __ldcg(part + 4 * k + col_b);
   }
@@ -192,9 +196,6 @@ __global__ void __launch_bounds__(256) k_pcg_pack(const double* __restrict__ bva
   }
 }
 
-#ifndef PCG_MINB
-#define PCG_MINB 2
-#endif
 #ifdef PCG_TIMING   // development builds only: where the time of an iteration goes (globaltimer ns, CTA 0 and the last CTA)
 __device__ unsigned long long g_pcg_clk[2][8];
 __device__ __forceinline__ unsigned long long pcg_now() {
@@ -211,9 +212,8 @@ __device__ __forceinline__ unsigned long long pcg_now() {
 #else
 #define PCG_MARK(k)
 #endif
-__global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
+__global__ void __launch_bounds__(PCG_NT, PCG_MINB) k_pcg(PcgArgs A) {
   unsigned int goal = 0;
-  __shared__ double sh[8];
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
   const int ncta = gridDim.x;
@@ -267,18 +267,21 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
     }
   }
   {
-    const double t0 = block_sum<256>(s_rz, sh), t1 = block_sum<256>(s_bb, sh);
-    if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
+    double v[2] = {s_rz, s_bb};
+    block_sum_n<2>(v);
+    if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = v[0]; A.part[4 * blockIdx.x + 2] = v[1]; }
   }
   pcg_barrier(A.barrier, goal);
   double rz, bb_;
-  pcg_total2(A.part, 1, 2, ncta, sh, rz, bb_);
+  pcg_total2(A.part, 1, 2, ncta, rz, bb_);
   const double bb = bb_;
   double rr = bb, beta = 0.0;
   // (z, p) pairs: the product reads z and the previous direction of a parameter with ONE 16-byte request
   double* pold = A.zp0;
   double* pnew = A.zp1;
   int it = 0;
+  PcgRow mrow0 = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (A.n_multi > 0) mrow0 = A.rows[A.multi_rows[0]];
 #ifdef PCG_TIMING
   unsigned long long tmark = pcg_now();
 #endif
@@ -290,7 +293,13 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
       // once (heaviest first, dealt CTA-first so that every SM gets its share), and a pass is one sweep for all but
       // the rows with more than 32 blocks.
       double s_pq = 0.0;
-      for (int wp = blockIdx.x + gridDim.x * (threadIdx.x >> 5); wp < A.n_pass; wp += gridDim.x * 8) {
+      // (round by round the warps are dealt passes in alternating order: the warp with the heaviest pass of one round
+      //  gets the lightest of the next)
+      for (int rnd = 0;; ++rnd) {
+        const int wic = threadIdx.x >> 5, NW = PCG_NT / 32;
+        if (rnd * NW * (int)gridDim.x >= A.n_pass) break;
+        const int wp = blockIdx.x + gridDim.x * (rnd * NW + ((rnd & 1) ? NW - 1 - wic : wic));
+        if (wp >= A.n_pass) continue;
         const PcgPass ps = A.passes[wp];
         const int G = ps.g, sub = lane / G, gl = lane & (G - 1);
         const int k = ps.item0 + sub;
@@ -305,7 +314,8 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
         const int* SL = A.pslots + ps.soff + lane;
         for (int sw = 0; sw < ps.nsweep; ++sw) {
           // (loads in batches, each batch issued before its first use: written load-by-load the compiler kept ONE value
-          //  register and waited out every load's latency in turn)
+          //  register and waited out every load's latency in turn.  The first two rows of values are requested before
+          //  the directions they multiply have arrived, every further pair of rows under the arithmetic of the previous)
           double pj[NB_MAX];
           int sjv[NB_MAX];
           double2 zp[NB_MAX];
@@ -313,16 +323,22 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
           for (int j = 0; j < NB_MAX; ++j) sjv[j] = j < ps.nj ? SL[j * 32] : -1;   // (-1: beyond this lane's block, or no block)
 #pragma unroll
           for (int j = 0; j < NB_MAX; ++j) zp[j] = sjv[j] >= 0 ? __ldcg((const double2*)pold + sjv[j]) : make_double2(0.0, 0.0);
+          double va[NB_MAX], vb[NB_MAX];
+#pragma unroll
+          for (int j = 0; j < NB_MAX; ++j) {      // (padding is never fetched: per-lane predicates on the loads)
+            va[j] = (sjv[j] >= 0 && 0 < w.n) ? V[j * 32] : 0.0;
+            vb[j] = (sjv[j] >= 0 && 1 < w.n) ? V[(ps.nj + j) * 32] : 0.0;
+          }
 #pragma unroll
           for (int j = 0; j < NB_MAX; ++j) pj[j] = fma(beta, zp[j].y, zp[j].x);
 #pragma unroll
           for (int i = 0; i < NB_MAX; i += 2) {
-            if (i < ps.ni) {      // (padding is never fetched: per-lane predicates on the loads)
-              double va[NB_MAX], vb[NB_MAX];
+            if (i < ps.ni) {
+              double na[NB_MAX], nb[NB_MAX];
 #pragma unroll
               for (int j = 0; j < NB_MAX; ++j) {
-                va[j] = (sjv[j] >= 0 && i < w.n) ? V[(i * ps.nj + j) * 32] : 0.0;
-                vb[j] = (sjv[j] >= 0 && i + 1 < w.n) ? V[((i + 1) * ps.nj + j) * 32] : 0.0;
+                na[j] = (i + 2 < NB_MAX && sjv[j] >= 0 && i + 2 < w.n) ? V[((i + 2) * ps.nj + j) * 32] : 0.0;
+                nb[j] = (i + 3 < NB_MAX && sjv[j] >= 0 && i + 3 < w.n) ? V[((i + 3) * ps.nj + j) * 32] : 0.0;
               }
               double a = 0.0, b = 0.0;
 #pragma unroll
@@ -332,6 +348,8 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
               }
               racc[i] += a;
               racc[i + 1] += b;
+#pragma unroll
+              for (int j = 0; j < NB_MAX; ++j) { va[j] = na[j]; vb[j] = nb[j]; }
             }
           }
           V += ps.ni * ps.nj * 32;
@@ -364,8 +382,9 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
       }
       PCG_MARK(0)
       {
-        const double t0 = block_sum<256>(s_pq, sh);
-        if (threadIdx.x == 0) A.part[4 * blockIdx.x + 0] = t0;
+        double v[1] = {s_pq};
+        block_sum_n<1>(v);
+        if (threadIdx.x == 0) A.part[4 * blockIdx.x + 0] = v[0];
       }
       pcg_barrier(A.barrier, goal);
       PCG_MARK(1)
@@ -379,12 +398,12 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
           int dst[4] = {-1, -1, -1, -1};
           int c = 0;
           if (first) {
-            for (int k = threadIdx.x; k < ncta; k += 256) v[0] += __ldcg(A.part + 4 * k + 0);
+            for (int k = threadIdx.x; k < ncta; k += PCG_NT) v[0] += __ldcg(A.part + 4 * k + 0);
             c = 1;
           }
           for (; c < 4 && m < A.n_multi; ++c) {
-            const PcgRow row = A.rows[A.multi_rows[m]];
-            for (int t = threadIdx.x; t < row.nitem; t += 256) v[c] += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
+            const PcgRow row = m == 0 ? mrow0 : A.rows[A.multi_rows[m]];   // (the first -- usually the only -- one is held in registers)
+            for (int t = threadIdx.x; t < row.nitem; t += PCG_NT) v[c] += __ldcg(A.qpart + (long long)(row.item0 + t) * 8 + i);
             dst[c] = A.act_slot[row.slot0 + i];
             if (++i == row.n) { i = 0; ++m; }
           }
@@ -439,13 +458,14 @@ __global__ void __launch_bounds__(256, PCG_MINB) k_pcg(PcgArgs A) {
       }
       PCG_MARK(3)
       {
-        const double t0 = block_sum<256>(s_rz2, sh), t1 = block_sum<256>(s_rr, sh);
-        if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = t0; A.part[4 * blockIdx.x + 2] = t1; }
+        double v[2] = {s_rz2, s_rr};
+        block_sum_n<2>(v);
+        if (threadIdx.x == 0) { A.part[4 * blockIdx.x + 1] = v[0]; A.part[4 * blockIdx.x + 2] = v[1]; }
       }
       pcg_barrier(A.barrier, goal);
       PCG_MARK(4)
       double rz_new;
-      pcg_total2(A.part, 1, 2, ncta, sh, rz_new, rr);
+      pcg_total2(A.part, 1, 2, ncta, rz_new, rr);
       PCG_MARK(5)
       if (pre) {            // the iteration proper starts here: p = z
         pre = false;
