@@ -128,6 +128,9 @@ struct apb_plan {
   BlockDesc* d_blocks = nullptr; int n_blocks = 0;
   BlockItem* d_vitems = nullptr; int n_vitems = 0;   // diagonal items only (J^T v)
   BlockDesc* d_vblocks = nullptr; int n_vblocks = 0;
+  // fixed-order gather of the block totals into the normal equations (k_block_gather): [0] full build, [1] vector only
+  GatherDst* d_gdst[2] = {nullptr, nullptr}; int* d_gsrc[2] = {nullptr, nullptr}; int n_gdst[2] = {0, 0}, n_gdst_noH[2] = {0, 0};
+  double* d_btot = nullptr; size_t btot_cap = 0;
   int *d_act_slot = nullptr, *d_act_off = nullptr;
   double* d_part = nullptr;
   size_t part_cap = 0;     // work items d_part has room for
@@ -1062,6 +1065,48 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     }
     p->n_items = (int)items.size(); p->n_blocks = (int)blocks.size();
     p->n_vitems = (int)vitems.size(); p->n_vblocks = (int)vblocks.size();
+    // where every value of every block goes (k_block_gather): contributions in block order per target entry
+    for (int which = 0; which < 2; ++which) {
+      const std::vector<BlockDesc>& bl = which ? vblocks : blocks;
+      struct Con { int kind; long long index; int src; };
+      std::vector<Con> cons;
+      for (size_t bi = 0; bi < bl.size(); ++bi) {
+        const BlockDesc& bd = bl[bi];
+        const int* sa = act_slot.data() + act_off[bd.a] + bd.pa0;
+        const int* sb = act_slot.data() + act_off[bd.b] + bd.pb0;
+        for (int i = 0; i < bd.na; ++i) {
+          const int vsrc = (int)(bi * BLK_VALS) + NB_MAX * NB_MAX + i;
+          if (which || bd.diag) cons.push_back(Con{0, sa[i], vsrc});
+          if (which) continue;
+          for (int j = 0; j < bd.nb; ++j) {
+            const int msrc = (int)(bi * BLK_VALS) + i * NB_MAX + j;
+            cons.push_back(Con{3, (long long)sa[i] * n_par + sb[j], msrc});
+            if (!bd.diag) cons.push_back(Con{3, (long long)sb[j] * n_par + sa[i], msrc});
+            if (p->sparse_ok && bd.coff >= 0) {
+              cons.push_back(Con{1, bd.coff + (bd.ctrans ? (long long)j * bd.cld + i : (long long)i * bd.cld + j), msrc});
+              if (bd.diag && i == j) cons.push_back(Con{2, sa[i], msrc});
+            }
+          }
+        }
+      }
+      std::stable_sort(cons.begin(), cons.end(), [](const Con& x, const Con& y) { return x.kind != y.kind ? x.kind < y.kind : x.index < y.index; });
+      std::vector<GatherDst> gd;
+      std::vector<int> gs(cons.size());
+      int noH = 0;
+      for (size_t k = 0; k < cons.size(); ++k) {
+        gs[k] = cons[k].src;
+        if (gd.empty() || gd.back().kind != cons[k].kind || gd.back().index != cons[k].index) {
+          gd.push_back(GatherDst{cons[k].index, cons[k].kind, (int)k, (int)k, 0});
+        }
+        gd.back().s1 = (int)k + 1;
+      }
+      for (const GatherDst& d : gd) noH += d.kind != 3;
+      p->n_gdst[which] = (int)gd.size(); p->n_gdst_noH[which] = noH;
+      PRC(own_upload(p, gd, &p->d_gdst[which]));
+      PRC(own_upload(p, gs, &p->d_gsrc[which]));
+    }
+    p->btot_cap = std::max(blocks.size(), vblocks.size());
+    PRC(own_alloc(p, (void**)&p->d_btot, sizeof(double) * BLK_VALS * std::max<size_t>(p->btot_cap, 1)));
     PRC(own_upload(p, items, &p->d_items));
     PRC(own_upload(p, blocks, &p->d_blocks));
     PRC(own_upload(p, vitems, &p->d_vitems));
@@ -1446,10 +1491,15 @@ extern "C" int apb_normal_eq(apb_plan_t* p, const double* x, int as_rep, double*
                                          -1.0, 0, p->d_part);
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
-    k_block_final<<<dim3(p->n_blocks, BLK_VALS / 8), 256, 0, st>>>(p->d_src, p->d_blocks, p->n_blocks, p->d_act_slot,
-                                                            p->d_act_off, p->d_part, JtWJ, JtWr, P, -1.0, 0,
-                                                            p->sparse_ok ? p->d_bvals : nullptr, p->d_diagH);
+    k_block_final<<<dim3(p->n_blocks, BLK_VALS / 8), 256, 0, st>>>(p->d_blocks, p->d_part, 0, p->d_btot);
     LAUNCH_CHECK();
+    const int nd = JtWJ ? p->n_gdst[0] : p->n_gdst_noH[0];
+    if (nd) {
+      PB(K_BLOCKFIN);
+      k_block_gather<<<ceil_div(nd, 256), 256, 0, st>>>(p->d_gdst[0], nd, p->d_gsrc[0], p->d_btot, JtWr, -1.0,
+                                                        p->sparse_ok ? p->d_bvals : nullptr, p->d_diagH, JtWJ);
+      LAUNCH_CHECK();
+    }
   }
   p->stats.launches = p->launches;
   return 0;
@@ -1488,8 +1538,12 @@ static int geodesic_core(apb_plan* p, apb_plan* pj, const double* xdh, const dou
                                            1.0, 1, part);
     LAUNCH_CHECK();
     PB(K_BLOCKFIN);
-    k_block_final<<<dim3(pj->n_vblocks, BLK_VALS / 8), 256, 0, st>>>(pj->d_src, pj->d_vblocks, pj->n_vblocks, pj->d_act_slot,
-                                                              pj->d_act_off, part, nullptr, rpp, P, 1.0, 1, nullptr, nullptr);
+    double* btot = p->btot_cap >= (size_t)pj->n_vblocks ? p->d_btot : pj->d_btot;
+    k_block_final<<<dim3(pj->n_vblocks, BLK_VALS / 8), 256, 0, st>>>(pj->d_vblocks, part, 1, btot);
+    LAUNCH_CHECK();
+    PB(K_BLOCKFIN);
+    k_block_gather<<<ceil_div(pj->n_gdst[1], 256), 256, 0, st>>>(pj->d_gdst[1], pj->n_gdst[1], pj->d_gsrc[1], btot, rpp, 1.0,
+                                                                 nullptr, nullptr, nullptr);
     LAUNCH_CHECK();
   }
   return 0;

@@ -526,14 +526,12 @@ struct BlockDesc {
 };
 
 // grid (blocks, BLK_VALS/8): one warp per value of a block; its lanes stride over the block's partials
-// (independent loads, 4 in flight per lane) and combine with a fixed shuffle tree (deterministic),
-// then lane 0 adds into H and g.  Entries that belong to a single block are exact; entries shared
-// by several blocks (linked parameters of joint fits) are combined with fp64 atomics.
-__global__ void __launch_bounds__(256) k_block_final(const DevSrc* __restrict__ src, const BlockDesc* __restrict__ blocks,
-                                                     int nblocks, const int* __restrict__ act_slot,
-                                                     const int* __restrict__ act_off, const double* __restrict__ part,
-                                                     double* __restrict__ H, double* __restrict__ g, int P, double gsign,
-                                                     int vec_only, double* __restrict__ bvals, double* __restrict__ diagH) {
+// (independent loads, 4 in flight per lane) and combine with a fixed shuffle tree, then lane 0 stores the value's
+// total in btot[block][value].  Nothing is added into H or g here: an entry of the normal equations may collect
+// several blocks (linked parameters of joint fits, the pieces of a model cut into tiles), and adding them with atomics
+// made joint fits differ in the last bits from run to run.  k_block_gather adds them in a fixed order.
+__global__ void __launch_bounds__(256) k_block_final(const BlockDesc* __restrict__ blocks, const double* __restrict__ part,
+                                                     int vec_only, double* __restrict__ btot) {
   const int bi = blockIdx.x;
   const BlockDesc bd = blocks[bi];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -556,23 +554,30 @@ __global__ void __launch_bounds__(256) k_block_final(const DevSrc* __restrict__ 
   double tot = (t0 + t1) + (t2 + t3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
-  if (lane != 0) return;
-  const int* sa = act_slot + act_off[bd.a] + bd.pa0;
-  const int* sb = act_slot + act_off[bd.b] + bd.pb0;
-  if (j < 0) {
-    atomicAdd(&g[sa[i]], gsign * tot);
-  } else {
-    if (H) {
-      atomicAdd(&H[(long long)sa[i] * P + sb[j]], tot);
-      if (!bd.diag) atomicAdd(&H[(long long)sb[j] * P + sa[i]], tot);
-    }
-    if (bvals && bd.coff >= 0) {
-      // block-sparse copy for the PCG solver (apb_solve.cuh), zeroed before this launch.  One writer per value
-      // (exact) unless a model is cut into tiles: its pieces add into the same owner block.
-      atomicAdd(&bvals[bd.coff + (bd.ctrans ? j * bd.cld + i : i * bd.cld + j)], tot);
-      if (bd.diag && i == j) atomicAdd(&diagH[sa[i]], tot);
-    }
-  }
+  if (lane == 0) btot[(long long)bi * BLK_VALS + v] = tot;
+}
+
+// One thread per entry of the normal equations that any block contributes to: the contributions (indices into btot,
+// listed by the host in block order) are added in that order and the sum is STORED -- every entry has exactly one
+// writer, so J^T W J, J^T W r, the block-sparse copy for the PCG solver and its diagonal are bit-reproducible run to
+// run whatever the sharing of parameters between models.  Targets: 0 vector (g, sign gsign), 1 block-sparse values,
+// 2 diagonal of H, 3 dense H (listed last: the launch stops before them when the caller wants no dense matrix).
+struct GatherDst {
+  long long index;
+  int kind, s0, s1, _pad;
+};
+__global__ void __launch_bounds__(256) k_block_gather(const GatherDst* __restrict__ dst, int ndst, const int* __restrict__ srcs,
+                                                      const double* __restrict__ btot, double* __restrict__ g, double gsign,
+                                                      double* __restrict__ bvals, double* __restrict__ diagH,
+                                                      double* __restrict__ H) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= ndst) return;
+  const GatherDst d = dst[t];
+  double* out = d.kind == 0 ? g : d.kind == 1 ? bvals : d.kind == 2 ? diagH : H;
+  if (!out) return;
+  double v = 0.0;
+  for (int k = d.s0; k < d.s1; ++k) v += btot[srcs[k]];
+  out[d.index] = d.kind == 0 ? gsign * v : v;
 }
 
 // J h per pixel and v = (2/d) ((rh - r)/d - W J h)   (lm.py:401-406); gather by image tile
