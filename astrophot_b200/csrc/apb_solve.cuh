@@ -11,15 +11,15 @@
 // what is left -- overlaps and the sky row -- converges in a few dozen to a few hundred iterations.
 //
 // One launch runs the whole iteration with TWO grid barriers per iteration:
-//   phase 1  q = A p  with  p = z + beta p_old  formed on the fly (the warp that owns a row also stores
+//   phase 1  q = A p  with  p = z + beta p_old  formed on the fly (the lanes that own a row also store
 //            p), and the CTA's share of p.q;
 //   phase 2  alpha from the summed shares;  x += alpha p,  r -= alpha q,  z = M^-1 r  per row block, and
 //            the CTA's shares of r.z and r.r.
 // Dot products are never a pass over the vectors: every CTA writes its share, and after the barrier
 // every CTA adds the shares in the same order, so alpha, beta and the stopping decision are
-// bit-identical in all CTAs without a broadcast.  Rows whose product is split over several warps
-// (the sky row couples to every model) write per-warp partial rows that their owner adds in order:
-// no atomics, run-to-run deterministic.
+// bit-identical in all CTAs without a broadcast.  Rows whose product is split over several work items
+// (the sky row couples to every model) write partial rows that every CTA adds in order:
+// no atomics, run-to-run deterministic.  DESIGN.md section 4 has the measurements behind the layout.
 #pragma once
 #include <cooperative_groups.h>
 #include "apb_internal.cuh"

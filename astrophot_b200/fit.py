@@ -350,8 +350,8 @@ class LM(BaseOptimizer):
             # the curvature ratio |a| / |h| compared with curvature_limit (lm.py:282-306): 1e-8 is plenty
             tol = 1e-8 if loose else self._pcg_tol
             if self.distributed:
-                # every rank solves the same merged system; rank 0's answer is the one all use (the split sky row of
-                # the PCG is summed with atomics, so the ranks' solutions may differ in the last bit)
+                # every rank solves the same merged system (identical bits in: rank-order all-reduce; deterministic
+                # solver); rank 0's answer is still the one all use -- a guard that costs one P-double exchange
                 res = self.plan.solve_sparse(rhs.contiguous(), L, out=self._hs[:P], info=self._hs[P:], tol=tol, x0=x0)
                 if self._peer is not None:
                     if torch.distributed.get_rank(self.group) != 0:

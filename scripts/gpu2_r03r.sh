@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -x -k "two_gpu or peer or nccl or distributed or tile" 2>&1 | tail -3
+bash scripts/gpuN_scale.sh 2 r03r
