@@ -488,7 +488,37 @@ def _remap_psfs(psfs, new_index):
     return out
 
 
-def tile_scene(scene, ny, nx):
+def _balanced_cuts(cost, n):
+    """Cut positions 0 = c_0 < ... < c_n = len(cost) that split the 1-D cost profile into ``n`` runs of (nearly) equal
+    cost; equal lengths where there is no cost to go by."""
+    L = len(cost)
+    total = float(cost.sum())
+    if n <= 1 or total <= 0.0:
+        return [round(k * L / n) for k in range(n + 1)]
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for k in range(1, n):
+        c = int(np.searchsorted(cum, total * k / n))
+        cuts.append(min(max(c, cuts[-1] + 1), L - (n - k)))
+    cuts.append(L)
+    return cuts
+
+
+def _tile_cost(im, srcs):
+    """Per-pixel cost estimate of the sources of one image (H x W): what a tile pays for is, above all, the sub-pixel
+    integration and the convolution of the models it evaluates; point sources and sky cost about a tenth per pixel."""
+    cost = np.zeros((im.H, im.W))
+    for s in srcs:
+        x0, y0, w, h = s.out
+        xa, ya, xb, yb = max(x0, 0), max(y0, 0), min(x0 + w, im.W), min(y0 + h, im.H)
+        if xb <= xa or yb <= ya or (xb - xa) * (yb - ya) > 0.5 * im.H * im.W:
+            continue                    # (a sky: the same everywhere)
+        heavy = s.kind not in (sc.KIND_POINT, sc.KIND_FLAT_SKY) and s.integrate_mode != sc.INTEGRATE_NONE
+        cost[ya:yb, xa:xb] += 1.0 if heavy else 0.1
+    return cost
+
+
+def tile_scene(scene, ny, nx, balance=True):
     """Cut every image of the scene into ``ny`` x ``nx`` tiles (one big image, as in a
     crowded field or a mosaic, partitioned by image tile).  Every tile becomes an image of its own (a
     view of data / weight / mask with the pixel origin moved), and a source is handed to every tile its
@@ -513,9 +543,13 @@ def tile_scene(scene, ny, nx):
             images.append(im)
             origin.append((0, 0, im.W, im.H))
             continue
-        ys = [round(k * im.H / ny) for k in range(ny + 1)]
-        xs = [round(k * im.W / nx) for k in range(nx + 1)]
+        # cuts: rows first, then every strip on its own, so that the tiles carry about the same estimated work
+        # (``balance``; equal areas otherwise).  Where the cuts fall changes no pixel value.
+        ii = len(first_tile) - 1
+        cost = _tile_cost(im, [s for s in scene.sources if s.image == ii]) if balance else np.zeros((im.H, im.W))
+        ys = _balanced_cuts(cost.sum(axis=1), ny)
         for a in range(ny):
+            xs = _balanced_cuts(cost[ys[a]:ys[a + 1]].sum(axis=0), nx)
             for b in range(nx):
                 y0, y1, x0, x1 = ys[a], ys[a + 1], xs[b], xs[b + 1]
                 if y1 <= y0 or x1 <= x0:

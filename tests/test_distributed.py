@@ -86,14 +86,18 @@ def test_tiles_reproduce_the_whole_image(name, tiles):
     x0 = fix["x0"]
     whole = orc.sample(scene, x0)[0]
     parts = orc.sample(tiled, x0)
-    ny, nx = tiles
-    H0, W0 = scene.images[0].H, scene.images[0].W
-    ys = [round(k * H0 / ny) for k in range(ny + 1)]
-    xs = [round(k * W0 / nx) for k in range(nx + 1)]
-    stitched = np.zeros_like(whole)
-    for a in range(ny):
-        for b in range(nx):
-            stitched[ys[a]:ys[a + 1], xs[b]:xs[b + 1]] = parts[a * nx + b]
+    # a tile's origin on the whole image is the shift of its reference pixel (the cuts are cost-balanced, not even)
+    stitched = np.full_like(whole, np.nan)
+    for im, part in zip(tiled.images, parts):
+        x0t, y0t = (np.round(np.asarray(scene.images[0].rij) - np.asarray(im.rij))).astype(int)
+        assert np.all(np.isnan(stitched[y0t:y0t + im.H, x0t:x0t + im.W]))      # every pixel owned once
+        stitched[y0t:y0t + im.H, x0t:x0t + im.W] = part
+    assert not np.any(np.isnan(stitched))
+    even = tile_scene(scene, *tiles, balance=False)
+    assert [(im.H, im.W) for im in even.images] == [
+        (round((a + 1) * scene.images[0].H / tiles[0]) - round(a * scene.images[0].H / tiles[0]),
+         round((b + 1) * scene.images[0].W / tiles[1]) - round(b * scene.images[0].W / tiles[1]))
+        for a in range(tiles[0]) for b in range(tiles[1])]
     assert np.max(np.abs(stitched - whole)) <= 1e-13 * np.max(np.abs(whole))
     H, g, chi2, _ = orc.normal_eq(tiled, x0)
     d = np.sqrt(np.diag(fix["hess0"]))
