@@ -43,7 +43,7 @@ class apb_source_t(C.Structure):
                 ("sampling_mode", C.c_int32), ("quad_init", C.c_int32), ("integrate_mode", C.c_int32),
                 ("quad_level", C.c_int32), ("gridding", C.c_int32), ("max_depth", C.c_int32),
                 ("ref_mode", C.c_int32), ("psf", C.c_int32), ("psf_shift", C.c_int32), ("conv_mode", C.c_int32),
-                ("owner", C.c_int32), ("_pad", C.c_int32),
+                ("owner", C.c_int32), ("upscale", C.c_int32),
                 ("tolerance", C.c_double), ("softening", C.c_double),
                 ("mask", C.c_void_p), ("mask_rect", C.c_int32 * 4)]
 
@@ -239,6 +239,7 @@ class Plan:
             c.ref_mode, c.psf, c.psf_shift = s.ref_mode, s.psf, s.psf_shift
             c.conv_mode = int(getattr(s, "conv_mode", 0))
             c.owner = int(getattr(s, "owner", -1))
+            c.upscale = int(getattr(s, "upscale", 1) or 1)
             c.tolerance, c.softening = s.tolerance, s.softening
             mk = getattr(s, "mask", None)
             if mk is not None:

@@ -45,11 +45,11 @@ static int upload(const std::vector<T>& v, T** out) {
 
 // ---- optional per-kernel timing (CUDA events on the launching stream) ------------------------
 enum KId { K_PREP, K_PSF, K_FIRST, K_MEAN, K_SELECT, K_REFINE, K_REDUCE, K_SCATTER, K_NORM, K_POINT, K_CONV,
-           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_PCG, K_AMP, K_COUNT };
+           K_ASSEMBLE, K_CHI, K_JAC, K_BLOCKS, K_BLOCKFIN, K_GEOV, K_FFTROWS, K_FFTCOLS, K_FFTINV, K_INTEGRATE, K_INTEGRATE_G, K_FIRST_G, K_POOL, K_POOL_G, K_PCG, K_AMP, K_UPSUM, K_COUNT };
 static const char* const kKNames[K_COUNT] = {"k_prep", "k_psf_stamp", "k_first", "k_mean", "k_select", "k_refine",
                                              "k_reduce_level", "k_scatter", "k_normalize", "k_point", "k_conv",
                                              "k_assemble", "k_chi_final", "k_jac_dense", "k_blocks", "k_block_final",
-                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad", "k_pcg", "k_amp"};
+                                             "k_geo_v", "k_fft_rows", "k_fft_cols", "k_fft_rows_inv", "k_integrate", "k_integrate_grad", "k_first_grad", "k_integrate_pool", "k_integrate_pool_grad", "k_pcg", "k_amp", "k_reduce_up"};
 static long long g_launches = 0;
 struct ProfRec { int id; cudaEvent_t a, b; };
 
@@ -96,6 +96,7 @@ struct apb_plan {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int* psf_list = nullptr; int n_psf_list = 0;      // sources needing a shifted PSF stamp
   int* point_list = nullptr; int n_point = 0;
+  int* up_list = nullptr; int n_up = 0;             // sources on a super-sampled grid (k_reduce_up)
   int* norm_list = nullptr; int n_norm = 0;
   int* amp_list = nullptr; int n_amp = 0;     // APB_F_AMP sources
   bool any_threshold = false, all_same_geo = true;
@@ -378,7 +379,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   std::vector<DevSrc>& S = p->h_src;
   S.resize(n_src);
   long long stamp_total = 0, out_total = 0, psfst_total = 0, spec_total = 0;
-  std::vector<int> psf_list, point_list, norm_list, amp_list, act_slot, act_off(n_src + 1, 0);
+  std::vector<int> psf_list, point_list, norm_list, amp_list, up_list, act_slot, act_off(n_src + 1, 0);
   int max_nact = 0;
   std::vector<FftDesc> fdescs;
   std::vector<cpx> twid;
@@ -486,13 +487,22 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     s.psf = a.psf; s.psf_shift = a.psf_shift;
     s.mask = a.mask; s.mask_x0 = a.mask_rect[0]; s.mask_y0 = a.mask_rect[1]; s.mask_w = a.mask_rect[2]; s.mask_h = a.mask_rect[3];
     if (a.mask && (a.mask_rect[2] <= 0 || a.mask_rect[3] <= 0)) PFAIL("source mask with an empty shape");
-    for (int k = 0; k < 4; ++k) s.S[k] = im.S[k];
-    const double det = im.S[0] * im.S[3] - im.S[1] * im.S[2];
+    // super-sampled PSF: the source lives on pixels 1 / up of the image's (window_object.py:233-239: pixelscale / up,
+    // reference_imageij -> (rij + 0.5) up - 0.5); its windows are the image-pixel windows times up
+    const int up = (a.upscale > 1 && a.kind != APB_FLAT_SKY) ? a.upscale : 1;
+    if (up > 16) PFAIL("upscale out of range (1..16)");
+    if (up > 1 && (a.psf < 0 || has_amp || a.kind == APB_PLANE_SKY)) PFAIL("upscale > 1 needs a PSF-convolved source or a point source");
+    int fout[4], ffwd[4], fjac[4];
+    for (int k = 0; k < 4; ++k) { fout[k] = a.out[k] * up; ffwd[k] = a.fwd[k] * up; fjac[k] = a.jac[k] * up; }
+    s.up = up; s.fox = fout[0]; s.foy = fout[1]; s.fow = fout[2]; s.foh = fout[3];
+    for (int k = 0; k < 4; ++k) s.S[k] = up > 1 ? im.S[k] / up : im.S[k];
+    const double det = s.S[0] * s.S[3] - s.S[1] * s.S[2];
     if (det == 0.0) PFAIL("singular pixelscale");
-    s.Sinv[0] = im.S[3] / det; s.Sinv[1] = -im.S[1] / det; s.Sinv[2] = -im.S[2] / det; s.Sinv[3] = im.S[0] / det;
+    s.Sinv[0] = s.S[3] / det; s.Sinv[1] = -s.S[1] / det; s.Sinv[2] = -s.S[2] / det; s.Sinv[3] = s.S[0] / det;
     s.area = fabs(det);
-    s.rij[0] = im.rij[0]; s.rij[1] = im.rij[1]; s.rxy[0] = im.rxy[0]; s.rxy[1] = im.rxy[1];
-    s.bx = s.by = 0; s.out_off = -1; s.psf_off = -1;
+    for (int k = 0; k < 2; ++k) s.rij[k] = up > 1 ? (im.rij[k] + 0.5) * up - 0.5 : im.rij[k];
+    s.rxy[0] = im.rxy[0]; s.rxy[1] = im.rxy[1];
+    s.bx = s.by = 0; s.out_off = -1; s.fine_off = -1; s.psf_off = -1;
     if (a.kind == APB_FLAT_SKY || a.kind == APB_POINT) s.integrate_mode = APB_INTEGRATE_NONE;
     if (a.kind == APB_POINT && a.psf < 0) PFAIL("point source without a PSF");
     if (a.kind == APB_FLAT_SKY) s.psf = -1;
@@ -511,15 +521,18 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
               "(the wider stamp wraps around the padded working image in the reference)");
       if (a.kind != APB_POINT) { s.bx = (s.pw + 2) / 2; s.by = (s.ph + 2) / 2; }  // ceil((1+P)/2), psf_image.py:71-93
       s.psf_off = psfst_total; psfst_total += (3LL + s.n_pp) * s.spw * s.sph;
+      if (up > 1 && psf[s.psf].source >= 0) PFAIL("upscale > 1 with a PSF model as the PSF is not supported");
       s.out_off = out_total; out_total += (long long)(1 + s.n_act) * s.ow * s.oh;
+      s.fine_off = s.out_off;
+      if (up > 1) { s.fine_off = out_total; out_total += (long long)(1 + s.n_act) * s.fow * s.foh; up_list.push_back(i); }
       psf_list.push_back(i);
       if (a.kind == APB_POINT) point_list.push_back(i);
     }
     const bool ring = (a.kind != APB_FLAT_SKY && a.kind != APB_POINT &&
                        (s.sampling_mode == APB_SAMPLE_MIDPOINT || s.sampling_mode == APB_SAMPLE_TRAPEZOID) &&
                        s.integrate_mode == APB_INTEGRATE_THRESHOLD);
-    set_geo(s.geo[0], a.out, a.fwd, s.bx, s.by, ring);
-    set_geo(s.geo[1], a.out, a.jac, s.bx, s.by, ring);
+    set_geo(s.geo[0], fout, ffwd, s.bx, s.by, ring);
+    set_geo(s.geo[1], fout, fjac, s.bx, s.by, ring);
     for (int m = 0; m < 2; ++m) {
       const Geo& g = s.geo[m];
       if (g.ex0 < g.rx0 || g.ey0 < g.ry0 || g.ex0 + g.ew > g.rx0 + g.rw || g.ey0 + g.eh > g.ry0 + g.rh)
@@ -562,7 +575,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
           s.fft_nf = nf; s.fft_nc = nc; s.fft_ld = ldy0 + pad;
           // column-major spectra (apb_fft.cuh): a column is eh / oh / sph / Ny consecutive complex numbers
           s.specA_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.nxh * g.eh;
-          s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.nxh * s.oh;
+          s.specB_off = spec_total; spec_total += (long long)(1 + s.n_act) * s.nxh * s.foh;
           s.specK_off = spec_total; spec_total += (3LL + s.n_pp) * s.nxh * s.sph;
           s.specKT_off = spec_total; spec_total += (3LL + s.n_pp) * s.nxh * Ny;
           p->fft_smem_rows = std::max(p->fft_smem_rows, row_bytes);
@@ -624,8 +637,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
         auto add_job = [&](int in_plane, int kern, int out_plane) {
           const int j = (int)jobs.size();
           jobs.push_back(make_int4(i, in_plane, kern, out_plane));
-          for (int ty = 0; ty < s.oh; ty += CONV_TH)
-            for (int tx = 0; tx < s.ow; tx += CONV_TW) ctiles.push_back(make_int4(j, tx, ty, 0));
+          for (int ty = 0; ty < s.foh; ty += CONV_TH)
+            for (int tx = 0; tx < s.fow; tx += CONV_TW) ctiles.push_back(make_int4(j, tx, ty, 0));
         };
         add_job(0, 0, 0);
         if (gr) {
@@ -703,7 +716,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
       for (const int4& c : conv) {
         jobs.push_back(make_int4(i, c.x, c.y, c.z));
         add_cols(cimg, (int)jobs.size() - 1);
-        add_rows(rinv, c.z, s.oh);
+        add_rows(rinv, c.z, s.foh);
       }
     }
     F.n_rows = (int)rows.size(); F.n_rows_psf = (int)rpsf.size(); F.n_cols_psf = (int)cpsf.size(); F.n_cols_img = (int)cimg.size(); F.n_rows_inv = (int)rinv.size();
@@ -1125,6 +1138,7 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
   { std::vector<apb_psf_t> pv(psf, psf + n_psf); PRC(own_upload(p, pv, &p->d_psf)); }
   PRC(own_upload(p, psf_list, &p->psf_list)); p->n_psf_list = (int)psf_list.size();
   PRC(own_upload(p, point_list, &p->point_list)); p->n_point = (int)point_list.size();
+  PRC(own_upload(p, up_list, &p->up_list)); p->n_up = (int)up_list.size();
   PRC(own_upload(p, norm_list, &p->norm_list)); p->n_norm = (int)norm_list.size();
   PRC(own_upload(p, amp_list, &p->amp_list)); p->n_amp = (int)amp_list.size();
   PRC(own_alloc(p, (void**)&p->d_stamp, sizeof(double) * (size_t)stamp_total));
@@ -1393,6 +1407,12 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
     PB(K_FFTINV);
     k_fft_rows_inv<<<F.n_rows_inv, p->fft_nt_rows, p->fft_smem_rows, st>>>(p->d_src, p->d_fftdesc, p->d_twid, F.rows_inv, p->d_spec,
                                                                 p->d_out);
+    LAUNCH_CHECK();
+  }
+  if (p->n_up) {
+    // super-sampled sources: fine output window -> image pixels (image_object.py:331-376 ``reduce``)
+    PB(K_UPSUM);
+    k_reduce_up<<<dim3(p->n_up, grad ? p->NVp_grad : 1, 4), 256, 0, st>>>(p->d_src, p->up_list, p->d_out, grad);
     LAUNCH_CHECK();
   }
   return 0;

@@ -485,10 +485,11 @@ __global__ void __launch_bounds__(256, 2) k_fft_cols(const DevSrc* __restrict__ 
   }
   __syncthreads();
   const cpx* z = fft_run<true>(r, r == a ? b : a, nc, ld, D, tw);
-  cpx* out = spec + s.specB_off + ((long long)jb.w * nxh + kx0) * s.oh;
-  for (int idx = threadIdx.x; idx < nc * s.oh; idx += blockDim.x) {
-    const int c = idx / s.oh, y = idx - c * s.oh;
-    out[(long long)c * s.oh + y] = z[c * ld + FPAD(y + s.by)];
+  // (foh, fow: the output window on the source's grid -- oh, ow unless the PSF is super-sampled, DevSrc::up)
+  cpx* out = spec + s.specB_off + ((long long)jb.w * nxh + kx0) * s.foh;
+  for (int idx = threadIdx.x; idx < nc * s.foh; idx += blockDim.x) {
+    const int c = idx / s.foh, y = idx - c * s.foh;
+    out[(long long)c * s.foh + y] = z[c * ld + FPAD(y + s.by)];
   }
 }
 
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows_inv(const DevSrc* __restric
   const cpx* tw = twid + D.tw_off;
   cpx* a = fsm;
   cpx* b = a + nf * ld;
-  const cpx* in = spec + s.specB_off + ((long long)wk.y * nxh) * s.oh;
+  const cpx* in = spec + s.specB_off + ((long long)wk.y * nxh) * s.foh;
   // thread (k, f), f fastest: a warp reads runs of 2 nf x 16 bytes of column kk (column-major spectra)
 #pragma unroll 4
   for (int idx = threadIdx.x; idx < nf * N; idx += blockDim.x) {
@@ -519,20 +520,20 @@ __global__ void __launch_bounds__(256, 2) k_fft_rows_inv(const DevSrc* __restric
     const bool second = 2 * f + 1 < wk.w;
     const bool lo = 2 * k <= N;
     const int kk = lo ? k : N - k;
-    const cpx* col = in + (long long)kk * s.oh;
+    const cpx* col = in + (long long)kk * s.foh;
     const cpx x1 = col[r0];
     const cpx x2 = second ? col[r0 + 1] : cpx{0.0, 0.0};
     a[f * ld + FPAD(k)] = lo ? cpx{x1.x - x2.y, x1.y + x2.x} : cpx{x1.x + x2.y, -x1.y + x2.x};
   }
   __syncthreads();
   const cpx* z = fft_run<true>(a, b, nf, ld, D, tw);
-  double* o = outar + s.out_off + (long long)wk.y * s.ow * s.oh;
-  for (int idx = threadIdx.x; idx < nf * s.ow; idx += blockDim.x) {
-    const int f = idx / s.ow, x = idx - f * s.ow;
+  double* o = outar + s.fine_off + (long long)wk.y * s.fow * s.foh;
+  for (int idx = threadIdx.x; idx < nf * s.fow; idx += blockDim.x) {
+    const int f = idx / s.fow, x = idx - f * s.fow;
     const int r0 = wk.z + 2 * f;
     const cpx v = z[f * ld + FPAD(x + s.bx)];
-    o[(long long)r0 * s.ow + x] = v.x;
-    if (2 * f + 1 < wk.w) o[(long long)(r0 + 1) * s.ow + x] = v.y;
+    o[(long long)r0 * s.fow + x] = v.x;
+    if (2 * f + 1 < wk.w) o[(long long)(r0 + 1) * s.fow + x] = v.y;
   }
 }
 #endif  // __CUDACC__

@@ -193,14 +193,15 @@ __global__ void __launch_bounds__(256) k_point(const DevSrc* __restrict__ src, c
   const int si = list[blockIdx.x];
   const DevSrc& s = src[si];
   const DevDyn& d = dyn[si];
-  const int n = s.ow * s.oh;
+  // (the fine output window: the output window itself unless the PSF is super-sampled, DevSrc::up)
+  const int n = s.fow * s.foh;
   const int spw = s.spw, sph = s.sph, ns = spw * sph;
   const double* K0 = psfst + s.psf_off;
   const double F = d.k[0];
-  double* o = outar + s.out_off;
+  double* o = outar + s.fine_off;
   const int x_lo = d.rx - (spw - 1) / 2, y_lo = d.ry - (sph - 1) / 2;
   for (int q = threadIdx.x; q < n; q += 256) {
-    const int x = s.ox + q % s.ow, y = s.oy + q / s.ow;
+    const int x = s.fox + q % s.fow, y = s.foy + q / s.fow;
     const int b = x - x_lo, a = y - y_lo;
     const bool in = a >= 0 && a < sph && b >= 0 && b < spw;
     const int k = a * spw + b;
@@ -276,13 +277,37 @@ __global__ void __launch_bounds__(256) k_conv(const DevSrc* __restrict__ src, co
     }
   }
   const int oy = tl.z + lane;
-  if (oy < s.oh) {
-    double* o = outar + s.out_off + (long long)jb.w * s.ow * s.oh + (long long)oy * s.ow;
+  if (oy < s.foh) {
+    double* o = outar + s.fine_off + (long long)jb.w * s.fow * s.foh + (long long)oy * s.fow;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ox = tl.y + w * 8 + k;
-      if (ox < s.ow) o[ox] = acc[k];
+      if (ox < s.fow) o[ox] = acc[k];
     }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// super-sampled PSFs (model_object.py:348-349, point_source.py:181: ``working_image.reduce(psf_upscale)``): the fine
+// output window of a source (up x up pixels per image pixel) summed into its planes in image pixels.
+// grid: (sources of the list, planes, row slices)
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_reduce_up(const DevSrc* __restrict__ src, const int* __restrict__ list,
+                                                   double* __restrict__ outar, int grad) {
+  const DevSrc& s = src[list[blockIdx.x]];
+  const int pl = blockIdx.y;
+  if (pl > (grad ? s.n_act : 0)) return;
+  const int up = s.up, fow = s.fow, ow = s.ow;
+  const double* f = outar + s.fine_off + (long long)pl * s.fow * s.foh;
+  double* o = outar + s.out_off + (long long)pl * s.ow * s.oh;
+  const int n = s.ow * s.oh;
+  for (int q = blockIdx.z * 256 + threadIdx.x; q < n; q += 256 * gridDim.z) {
+    const int y = q / ow, x = q - y * ow;
+    const double* b = f + (long long)(y * up) * fow + x * up;
+    double acc = 0.0;
+    for (int i = 0; i < up; ++i)
+      for (int j = 0; j < up; ++j) acc += b[(long long)i * fow + j];
+    o[q] = acc;
   }
 }
 

@@ -50,6 +50,12 @@ struct DevSrc {
   long long stamp_off;     // doubles, into the stamp arena; plane p at stamp_off + p*plane_stride
   long long plane_stride;  // >= mw*mh of both modes
   long long out_off;       // PSF sources: offset of cropped planes (ow*oh each) in the out arena; else -1
+  // super-sampled PSF (apb_source_t.upscale = up > 1): S, Sinv, rij, area, geo[], bx, by and the PSF stamps live on the
+  // fine grid (pixels 1 / up of the image's); the convolution (k_point) writes the fine output window (fox, foy, fow, foh
+  // = up x the output window) at fine_off, k_reduce_up block-sums it into the planes at out_off that everything
+  // downstream reads.  up == 1: the fine window is the output window and fine_off == out_off
+  int up, fox, foy, fow, foh;
+  long long fine_off;
   long long psf_off;       // offset of this source's shifted PSF stamps (3 x spw*sph) or -1
   int spw, sph;            // shifted stamp size
   double S[4], Sinv[4], rij[2], rxy[2], area;

@@ -270,6 +270,7 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
 
         # psf
         pidx = -1
+        up = 1
         pmode = comp.psf_mode
         if pmode not in ("none", "full"):
             raise SpecificationConflict(f"unknown psf_mode: {pmode}")
@@ -280,9 +281,15 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             if psf is None:
                 raise SpecificationConflict(f"{comp.name}: psf_mode='full' but no PSF on model or target")
             pwin = psf.window if isinstance(psf, PSF_Image) else psf.target.window
+            # super-sampled PSF (model_object.py:312-315,348-349; point_source.py:147-149,181): the source is sampled on
+            # pixels 1 / up of the image's and block-summed back
             up = int(np.round(float(region.pixel_length) / float(pwin.pixel_length)))
-            if up != 1:
-                raise SpecificationConflict("super-sampled PSFs (psf_upscale > 1) are not implemented yet (SURVEY.md §8f)")
+            if up < 1:
+                raise SpecificationConflict(f"{comp.name}: the PSF's pixels are larger than the image's")
+            if up > 1 and not isinstance(psf, PSF_Image):
+                raise SpecificationConflict("super-sampled PSF *models* (psf_upscale > 1) are not supported by astrophot_b200")
+            if up > 16:
+                raise SpecificationConflict(f"{comp.name}: psf_upscale = {up} > 16")
             if id(psf) not in psf_index:
                 if isinstance(psf, PSF_Image):
                     psfs.append(sc.ScenePSF(data=psf.data.contiguous()))
@@ -323,7 +330,7 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             softening=float(comp.softening), ref_mode=comp._ref_mode, psf=pidx,
             psf_shift=_shift_code(comp.psf_subpixel_shift),
             conv_mode=sc.CONV_DIRECT if comp.psf_convolve_mode == "direct" else sc.CONV_AUTO, name=comp.name,
-            mask=mk, mask_origin=mk_origin)
+            mask=mk, mask_origin=mk_origin, upscale=up)
 
     # ---- sources
     sources = []

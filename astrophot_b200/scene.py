@@ -98,6 +98,8 @@ class SceneSource:
     mask: object = None      # the model's own mask (model_object.py:370-371): 2-D bool array, True = the model contributes
                              # nothing there (value and derivatives); element [0, 0] is image pixel `mask_origin`
     mask_origin: tuple = (0, 0)
+    upscale: int = 1         # super-sampled PSF (model_object.py:312-315,348-349): the source is sampled and convolved on
+                             # pixels 1 / upscale of the image's and block-summed back; windows stay in image pixels
 
     @property
     def n_elem(self):

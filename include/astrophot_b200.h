@@ -114,7 +114,10 @@ typedef struct {
   int32_t owner;     /* index into apb_opts_t.owners of the model this source is a piece of (an image
                         cut into tiles hands every tile its clipped copy of the model); ignored when no
                         owner table is given */
-  int32_t _pad;
+  int32_t upscale;   /* super-sampled PSF (models/model_object.py:312-315,348-349; point_source.py:147-149,181):
+                        the PSF's pixels are 1 / upscale of the image's; the source is sampled, integrated and
+                        convolved (a point source: its PSF dropped) on that finer grid and block-summed back.  `out`,
+                        `fwd`, `jac` stay in image pixels.  Needs a PSF image (apb_psf_t.data); 0 or 1: none */
   double tolerance, softening;
   /* the model's own mask (models/model_object.py:370-371, point_source.py:184-185): device, mask_rect[2] x mask_rect[3]
    * bytes, row-major, element (0, 0) = image pixel (mask_rect[0], mask_rect[1]); where it is non-zero the source

@@ -554,6 +554,26 @@ def _sample_source_unmasked(scene, si, el, mode, want_grad, conv="direct", stats
         I, dI = eval_profile(src, el, X, X, area, want_grad)
         return SourceResult(I, dI)
 
+    up = int(getattr(src, "upscale", 1) or 1)
+    if up > 1:
+        # Super-sampled PSF (model_object.py:312-315,348-349; point_source.py:147-149,181): the working window is
+        # rescaled to the PSF's pixels (window_object.py:233-239: pixelscale / up, reference_imageij -> (rij + 0.5) up - 0.5),
+        # the model is sampled / integrated / convolved (a point source: its PSF dropped) on that grid, and the result is
+        # block-summed back (image_object.py:331-376 ``reduce``).  Here: the same source on a virtual fine image.
+        import dataclasses
+        fine_img = dataclasses.replace(img, H=img.H * up, W=img.W * up, S=S / up,
+                                       rij=(np.asarray(img.rij, dtype=np.float64) + 0.5) * up - 0.5,
+                                       data=None, weight=None, mask=None)
+        fine_src = dataclasses.replace(src, upscale=1, image=len(scene.images), mask=None,
+                                       out=tuple(v * up for v in src.out), fwd=tuple(v * up for v in src.fwd),
+                                       jac=tuple(v * up for v in src.jac))
+        srcs = list(scene.sources)
+        srcs[si] = fine_src
+        scene1 = dataclasses.replace(scene, images=list(scene.images) + [fine_img], sources=srcs)
+        r = _sample_source_unmasked(scene1, si, el, mode, want_grad, conv, stats, vals)
+        red = lambda a: a.reshape(a.shape[:-2] + (oh, up, ow, up)).sum(axis=(-3, -1))
+        return SourceResult(red(r.value), None if r.grad is None else red(r.grad), [(sl, red(pl)) for sl, pl in r.extra])
+
     if src.kind == sc.KIND_POINT:
         return _sample_point(scene, src, img, el, want_grad)
 

@@ -286,6 +286,37 @@ def build(ap, name, data=None):
         models.append(sky)
         g = M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
         return g, {}
+    if name in ("psf_sersic_up2", "psf_sersic_up3_direct"):
+        # super-sampled PSF (model_object.py:313-314,348-349): PSF pixels 1/2 (1/3) of the image's; the model is sampled,
+        # integrated and convolved on the fine grid, then block-summed back
+        up = 2 if name == "psf_sersic_up2" else 3
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 1.8 * up, 6 * up + 1), pixelscale=1.0 / up)
+        tar = _target(ap, (44, 48), data, psf=psf)
+        m = M(name=name, model_type="sersic galaxy model", target=tar, psf_mode="full",
+              psf_convolve_mode="fft" if up == 2 else "direct",
+              parameters={"center": [22.8, 20.3], "q": 0.55, "PA": 2.4, "n": 2.5, "Re": 5.0, "Ie": 1.0})
+        return m, {}
+    if name == "group_up2":
+        # a group on a target with a 2x super-sampled PSF (sheared pixels): galaxy with its own window, a point source,
+        # another cut by the image edge (point_source.py:145-175 with psf_upscale), an unconvolved galaxy and the sky
+        S = np.array([[0.8, 0.06], [-0.04, 0.85]])
+        psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 3.4, 13), pixelscale=S / 2)
+        tar = _target(ap, (60, 64), data, pixelscale=S, origin=[2.0, -1.0], psf=psf)
+        models = [
+            M(name="u_gal", model_type="sersic galaxy model", target=tar, psf_mode="full", window=[[8, 44], [10, 50]],
+              parameters={"center": [22.3, 24.1], "q": 0.6, "PA": 0.7, "n": 1.8, "Re": 4.0, "Ie": 0.9}),
+            M(name="u_pt", model_type="point model", target=tar, window=[[34, 49], [30, 45]],
+              parameters={"center": [35.7, 31.2], "flux": 1.2}),
+            M(name="u_pte", model_type="point model", target=tar, window=[[50, 64], [0, 12]],
+              parameters={"center": [50.1, 2.2], "flux": 1.5}),
+            M(name="u_exp", model_type="exponential galaxy model", target=tar, window=[[30, 64], [36, 60]],
+              parameters={"center": [40.2, 41.5], "q": 0.8, "PA": 2.0, "Re": 3.0, "Ie": 0.6}),
+        ]
+        sky = M(name="u_sky", model_type="flat sky model", target=tar, parameters={"F": -1.2})
+        sky.initialize()
+        models.append(sky)
+        g = M(name="grp_up2", model_type="group model", models=models, target=tar, psf_mode="full")
+        return g, {}
     if name == "moffat_psf_model":
         # a PSF model fitted to a star cut-out held as a PSF_Image (no variance: unit weights)
         ptar = ap.image.PSF_Image(data=np.zeros((25, 25)) if data is None else data[0]["data"], pixelscale=1.0)
@@ -335,13 +366,19 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs",
                  "point_psf_model", "point_psf_model_group", "group_edge", "sersic_modelmask", "psf_sersic_modelmask",
-                 "psf_sersic_lanczos3", "lanczos_group"]
+                 "psf_sersic_lanczos3", "lanczos_group", "psf_sersic_up2", "group_up2"]
+# psf_upscale that is not a power of two: the reference forms 1 / psf_upscale in float32 (model_object.py:313-314 ->
+# window_object.py:233-239), which perturbs the fine pixel scale by 3e-8 and floors the fine window one pixel short, so
+# that the last image row and column of the model stay empty.  astrophot_b200 (and the oracle) use the exact grid; the
+# golden pins the interior at 1e-6.
+ODD_UPSCALE_SCENES = ["psf_sersic_up3_direct"]
 CPU_ONLY_SCENES = []
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
              "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18,
-             "psf_sersic_modelmask": 19, "psf_sersic_lanczos3": 20, "lanczos_group": 21}
+             "psf_sersic_modelmask": 19, "psf_sersic_lanczos3": 20, "lanczos_group": 21,
+             "psf_sersic_up2": 22, "group_up2": 23}
 CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe

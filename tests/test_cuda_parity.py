@@ -179,6 +179,33 @@ def test_sample_vs_oracle_and_reference(name):
     assert st["overflow"] == 0
 
 
+@pytest.mark.parametrize("name,conv", [("psf_sersic_up3_direct", None), ("psf_sersic_up3_direct", "fft"),
+                                       ("psf_sersic_up2", "direct"), ("psf_sersic_up2", "fft"),
+                                       ("group_up2", "direct"), ("group_up2", "fft")])
+def test_supersampled_psf_both_convolutions(name, conv):
+    """Super-sampled PSFs (model_object.py:312-315,348-349; point_source.py:147-149,181): fine-grid sampling and
+    convolution, block-summed back by k_reduce_up, through both convolution kernels, against the oracle (for
+    psf_upscale = 3 the oracle is the only exact checker: scenes.ODD_UPSCALE_SCENES)."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name)
+    scene, info = lower(model)
+    assert max(s.upscale for s in scene.sources) == (3 if "up3" in name else 2)
+    plan = _plan(scene, conv=conv)
+    got = plan.sample(fix["x_val"], as_rep=False)[0].cpu().numpy()
+    want = orc.sample(scene, fix["x_val"], as_rep=False)[0]
+    assert rel_err(got, want) < 1e-10
+    if "up3" in name:
+        assert rel_err(got[:-1, :-1], fix["img0"][:-1, :-1]) < 1e-6
+    else:
+        assert rel_err(got, fix["img0"]) < 1e-10
+    for as_rep, x in ((True, fix["x_rep"]), (False, fix["x_val"])):
+        J = plan.jacobian(x, as_rep=as_rep)[0].cpu().numpy()
+        Jo = orc.jacobian(scene, x, as_rep=as_rep)[0]
+        scale = np.maximum(np.abs(Jo).reshape(-1, Jo.shape[-1]).max(axis=0), 1e-300)
+        assert np.max(np.abs(J - Jo) / scale) < 1e-9
+    assert plan.stats()["overflow"] == 0
+
+
 @pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
 @pytest.mark.parametrize("tag", ["rep", "nat"])
 def test_jacobian_vs_oracle_and_reference(name, tag):
@@ -462,12 +489,12 @@ def test_tiled_plan_equals_whole_image(name, tiles):
     # model image: the tiles stitched together
     img0 = whole.sample(x0, as_rep=True)[0].cpu().numpy()
     parts = [t.cpu().numpy() for t in cut.sample(x0, as_rep=True)]
-    ny, nx = tiles
-    ys = [round(k * img0.shape[0] / ny) for k in range(ny + 1)]
-    xs = [round(k * img0.shape[1] / nx) for k in range(nx + 1)]
-    for a in range(ny):
-        for b in range(nx):
-            assert rel_err(parts[a * nx + b], img0[ys[a]:ys[a + 1], xs[b]:xs[b + 1]]) < 1e-12
+    seen = np.zeros(img0.shape, dtype=int)
+    for im, part in zip(tiled.images, parts):     # (cost-balanced cuts: a tile's origin is the shift of its reference pixel)
+        tx, ty = (np.round(np.asarray(scene.images[0].rij) - np.asarray(im.rij))).astype(int)
+        assert rel_err(part, img0[ty:ty + im.H, tx:tx + im.W]) < 1e-12
+        seen[ty:ty + im.H, tx:tx + im.W] += 1
+    assert np.all(seen == 1)
     # the pieces of a model share its parameters; the sparse matrix is laid out on the owners and still solves
     rng = np.random.default_rng(11)
     for L in (1e-3, 1.0):

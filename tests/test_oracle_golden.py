@@ -29,6 +29,29 @@ def test_sample_matches_reference(name):
             np.testing.assert_allclose(im, ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max() * 1e-6)
 
 
+@pytest.mark.parametrize("name", scenes.ODD_UPSCALE_SCENES)
+def test_odd_upscale_matches_reference_interior(name):
+    """psf_upscale = 3: the reference's float32 1/3 (see scenes.ODD_UPSCALE_SCENES) bounds the agreement."""
+    fix = load_golden(name)
+    model, _ = scenes.build(ap, name)
+    scene, info = lower(model)
+    assert scene.sources[0].upscale == 3
+    im = orc.sample(scene, fix["x_val"], as_rep=False)[0]
+    ref = fix["img0"]
+    assert np.all(ref[-1] == 0) and np.all(ref[:, -1] == 0) and np.all(im[-1] > 0)
+    assert rel_err(im[:-1, :-1], ref[:-1, :-1]) < 1e-6
+    # the oracle's Jacobian against central differences of its own model image
+    x = fix["x_val"]
+    J = orc.jacobian(scene, x, as_rep=False)[0]
+    for k in range(len(x)):
+        h = 1e-6 * max(1.0, abs(x[k]))
+        xp, xm = x.copy(), x.copy()
+        xp[k] += h
+        xm[k] -= h
+        fd = (orc.sample(scene, xp, as_rep=False)[0] - orc.sample(scene, xm, as_rep=False)[0]) / (2 * h)
+        assert np.max(np.abs(J[..., k] - fd)) < 2e-5 * np.max(np.abs(fd)), k
+
+
 @pytest.mark.parametrize("name", scenes.SAMPLE_SCENES + scenes.CPU_ONLY_SCENES)
 @pytest.mark.parametrize("tag", ["rep", "nat"])
 def test_jacobian_matches_reference(name, tag):
