@@ -69,7 +69,7 @@ class apb_kernel_time_t(C.Structure):
 
 
 EXPORTS = ["apb_comm_alloc", "apb_comm_create", "apb_allreduce", "apb_comm_destroy", "apb_lm_trial_spec", "apb_plan_set_image_data", "apb_plan_block_doubles", "apb_plan_bind_blocks", "apb_lm_solve_sparse", "apb_lm_trial", "apb_lm_trial_begin", "apb_lm_trial_end", "apb_fft_length", "apb_plan_reserve", "apb_profile", "apb_profile_read", "apb_launch_count", "apb_bench_peaks", "apb_plan_create", "apb_plan_destroy", "apb_sample", "apb_jacobian", "apb_normal_eq", "apb_geodesic",
-           "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version"]
+           "apb_chi2", "apb_lm_solve", "apb_plan_stats", "apb_last_error", "apb_version", "apb_chol_factor", "apb_chol_solve"]
 
 _lib = None
 
@@ -100,6 +100,8 @@ def load_library(path=None):
     L.apb_geodesic.argtypes = [vp, dp, dp, C.c_double, dp, vp]
     L.apb_chi2.argtypes = [vp, dp, dp, vp]
     L.apb_lm_solve.argtypes = [dp, dp, C.c_double, C.c_int, dp, ip, vp]
+    L.apb_chol_factor.argtypes = [dp, C.c_double, C.c_int, dp, ip, vp]
+    L.apb_chol_solve.argtypes = [dp, dp, C.c_int, dp, vp]
     L.apb_lm_solve_sparse.argtypes = [vp, dp, C.c_double, dp, dp, dp, C.c_double, C.c_int, vp]
     L.apb_plan_set_image_data.argtypes = [vp, C.c_int, dp, dp, dp, vp]
     L.apb_plan_block_doubles.argtypes = [vp]
@@ -513,6 +515,31 @@ def lm_solve(H, g, L, out=None, info=None):
         info = torch.zeros(1, dtype=torch.int32, device="cuda")
     _check(lib().apb_lm_solve(H.data_ptr(), g.data_ptr(), float(L), int(P), out.data_ptr(), info.data_ptr(),
                               _stream()), "apb_lm_solve")
+    return out
+
+
+def chol_factor(H, L, work=None, info=None):
+    """Blocked Cholesky factor of the damped matrix of fit/lm.py:359-371 for systems beyond the single-CTA solver
+    (apb_chol_factor).  Returns (work, info): the factor (P*P + 2 doubles) and a device int (0 = ok)."""
+    _require_cuda()
+    P = H.shape[0]
+    if work is None or work.numel() < P * P + 2:
+        work = torch.empty(P * P + 2, dtype=torch.float64, device=H.device)
+    if info is None:
+        info = torch.zeros(1, dtype=torch.int32, device=H.device)
+    H = H.contiguous()
+    _check(lib().apb_chol_factor(H.data_ptr(), float(L), int(P), work.data_ptr(), info.data_ptr(), _stream()), "apb_chol_factor")
+    return work, info
+
+
+def chol_solve(work, rhs, out=None):
+    """Solve with the factor of ``chol_factor`` (apb_chol_solve)."""
+    _require_cuda()
+    P = rhs.numel()
+    rhs = rhs.contiguous()
+    if out is None:
+        out = torch.empty(P, dtype=torch.float64, device=rhs.device)
+    _check(lib().apb_chol_solve(work.data_ptr(), rhs.data_ptr(), int(P), out.data_ptr(), _stream()), "apb_chol_solve")
     return out
 
 

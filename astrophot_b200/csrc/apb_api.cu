@@ -16,6 +16,7 @@
 #include "apb_fft.cuh"
 #include "apb_solve.cuh"
 #include "apb_comm.cuh"
+#include "apb_chol.cuh"
 
 
 static thread_local std::string g_err;
@@ -491,7 +492,8 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
     // reference_imageij -> (rij + 0.5) up - 0.5); its windows are the image-pixel windows times up
     const int up = (a.upscale > 1 && a.kind != APB_FLAT_SKY) ? a.upscale : 1;
     if (up > 16) PFAIL("upscale out of range (1..16)");
-    if (up > 1 && (a.psf < 0 || has_amp || a.kind == APB_PLANE_SKY)) PFAIL("upscale > 1 needs a PSF-convolved source or a point source");
+    if (up > 1 && ((a.psf < 0 && !has_amp) || a.kind == APB_PLANE_SKY))
+      PFAIL("upscale > 1 needs a PSF-convolved source, a point source, or a point source drawn from a PSF model (APB_F_AMP)");
     int fout[4], ffwd[4], fjac[4];
     for (int k = 0; k < 4; ++k) { fout[k] = a.out[k] * up; ffwd[k] = a.fwd[k] * up; fjac[k] = a.jac[k] * up; }
     s.up = up; s.fox = fout[0]; s.foy = fout[1]; s.fow = fout[2]; s.foh = fout[3];
@@ -521,12 +523,17 @@ extern "C" int apb_plan_create(const apb_source_t* src, int n_src, const apb_ima
               "(the wider stamp wraps around the padded working image in the reference)");
       if (a.kind != APB_POINT) { s.bx = (s.pw + 2) / 2; s.by = (s.ph + 2) / 2; }  // ceil((1+P)/2), psf_image.py:71-93
       s.psf_off = psfst_total; psfst_total += (3LL + s.n_pp) * s.spw * s.sph;
-      if (up > 1 && psf[s.psf].source >= 0) PFAIL("upscale > 1 with a PSF model as the PSF is not supported");
       s.out_off = out_total; out_total += (long long)(1 + s.n_act) * s.ow * s.oh;
       s.fine_off = s.out_off;
       if (up > 1) { s.fine_off = out_total; out_total += (long long)(1 + s.n_act) * s.fow * s.foh; up_list.push_back(i); }
       psf_list.push_back(i);
       if (a.kind == APB_POINT) point_list.push_back(i);
+    }
+    if (up > 1 && s.psf < 0) {
+      // a point source drawn from a super-sampled PSF model (point_source.py:122-143,181): sampled on the fine grid into
+      // its stamp, summed into image-pixel planes of the out arena (fine_off stays -1: k_reduce_up reads the stamp)
+      s.out_off = out_total; out_total += (long long)(1 + s.n_act) * s.ow * s.oh;
+      up_list.push_back(i);
     }
     const bool ring = (a.kind != APB_FLAT_SKY && a.kind != APB_POINT &&
                        (s.sampling_mode == APB_SAMPLE_MIDPOINT || s.sampling_mode == APB_SAMPLE_TRAPEZOID) &&
@@ -1412,7 +1419,7 @@ static int sample_pass(apb_plan* p, const double* x, int as_rep, int mode, int g
   if (p->n_up) {
     // super-sampled sources: fine output window -> image pixels (image_object.py:331-376 ``reduce``)
     PB(K_UPSUM);
-    k_reduce_up<<<dim3(p->n_up, grad ? p->NVp_grad : 1, 4), 256, 0, st>>>(p->d_src, p->up_list, p->d_out, grad);
+    k_reduce_up<<<dim3(p->n_up, grad ? p->NVp_grad : 1, 4), 256, 0, st>>>(p->d_src, p->up_list, mode, p->d_stamp, p->d_out, grad);
     LAUNCH_CHECK();
   }
   return 0;
@@ -1697,6 +1704,39 @@ extern "C" int apb_lm_solve(const double* H, const double* g, double L, int P, d
   if (P <= 0) return 0;
   LmEpi e0{0, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr};
   return lm_solve_launch(H, g, L, P, h, info, e0, (cudaStream_t)stream);
+}
+
+// Dense damped system beyond the single-CTA solver (apb_chol.cuh): factor once per (H, L), solve per right-hand side.
+//   W: device, P*P + 2 doubles (the factor; the tail holds the grid-barrier counter).  info: device int, 0 ok.
+extern "C" int apb_chol_factor(const double* H, double L, int P, double* W, int* info, void* stream) {
+  if (P <= 0) return 0;
+  if (!H || !W || !info) APB_FAIL("apb_chol_factor: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, n_sm = 0, coop = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop || n_sm <= 0) APB_FAIL("apb_chol_factor: the device cannot launch cooperative kernels");
+  unsigned int* bar = (unsigned int*)(W + (size_t)P * P);
+  CU(cudaMemsetAsync(bar, 0, 2 * sizeof(double), st));
+  const int nb = (P + CH_NB - 1) / CH_NB;
+  // (no more CTAs than the widest phase has tiles: the barriers cost by the number of arrivals)
+  const int grid = std::max(1, std::min(n_sm, std::max(nb * (nb - 1) / 2, (int)std::min<long long>((long long)P * P / CH_NT + 1, n_sm))));
+  CholArgs A{H, L, P, W, info, bar};
+  void* args[] = {&A};
+  CU(cudaLaunchCooperativeKernel((void*)k_chol_factor, dim3(grid), dim3(CH_NT), args, 0, st));
+  g_launches++;
+  return 0;
+}
+
+// x = A^-1 rhs with the factor of apb_chol_factor.  rhs, x: device, P (may alias).
+extern "C" int apb_chol_solve(const double* W, const double* rhs, int P, double* x, void* stream) {
+  if (P <= 0) return 0;
+  if (!W || !rhs || !x) APB_FAIL("apb_chol_solve: NULL argument");
+  k_chol_solve<<<1, CH_NT, 0, (cudaStream_t)stream>>>(W, rhs, P, x);
+  CU(cudaGetLastError());
+  g_launches++;
+  return 0;
 }
 
 // Damped solve of the system of the last apb_normal_eq by block-sparse PCG (apb_solve.cuh).

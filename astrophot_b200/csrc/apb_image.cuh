@@ -292,13 +292,24 @@ __global__ void __launch_bounds__(256) k_conv(const DevSrc* __restrict__ src, co
 // output window of a source (up x up pixels per image pixel) summed into its planes in image pixels.
 // grid: (sources of the list, planes, row slices)
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_reduce_up(const DevSrc* __restrict__ src, const int* __restrict__ list,
-                                                   double* __restrict__ outar, int grad) {
+__global__ void __launch_bounds__(256) k_reduce_up(const DevSrc* __restrict__ src, const int* __restrict__ list, int mode,
+                                                   const double* __restrict__ stamp, double* __restrict__ outar, int grad) {
   const DevSrc& s = src[list[blockIdx.x]];
   const int pl = blockIdx.y;
   if (pl > (grad ? s.n_act : 0)) return;
-  const int up = s.up, fow = s.fow, ow = s.ow;
-  const double* f = outar + s.fine_off + (long long)pl * s.fow * s.foh;
+  const int up = s.up, ow = s.ow;
+  // the fine output window: planes of the out arena (convolved sources, point sources), or -- a source without
+  // convolution, i.e. a point source drawn from a PSF model -- the output window inside its stamp
+  const double* f;
+  int fow;
+  if (s.fine_off >= 0) {
+    f = outar + s.fine_off + (long long)pl * s.fow * s.foh;
+    fow = s.fow;
+  } else {
+    const Geo& g = s.geo[mode];
+    f = stamp + s.stamp_off + (long long)pl * s.plane_stride + (long long)(s.foy - g.my0) * g.mw + (s.fox - g.mx0);
+    fow = g.mw;
+  }
   double* o = outar + s.out_off + (long long)pl * s.ow * s.oh;
   const int n = s.ow * s.oh;
   for (int q = blockIdx.z * 256 + threadIdx.x; q < n; q += 256 * gridDim.z) {

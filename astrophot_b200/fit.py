@@ -383,23 +383,25 @@ class LM(BaseOptimizer):
         if self.distributed and not self._hess_reduced:
             self._allreduce(self._H)
             self._hess_reduced = True
-        # otherwise: same damped matrix (lm.py:359-371), library dense solver on the device.  The matrix is
-        # symmetric positive definite for L > 0, so it is Cholesky-factored once per (H, L) and the factor serves
-        # both solves of a lambda-trial (h and the geodesic correction); LU is the fallback.
+        # otherwise: same damped matrix (lm.py:359-371), dense.  It is symmetric positive definite for L > 0, so it is
+        # Cholesky-factored once per (H, L) -- apb_chol_factor, a blocked factorisation in one cooperative kernel -- and
+        # the factor serves both solves of a lambda-trial (h and the geodesic correction).  A matrix the factorisation
+        # rejects (a non-finite or non-positive pivot: the trial is lost anyway) goes through LU like the reference's.
+        from .cabi import chol_factor, chol_solve
         key = (self._hess_version, float(L))
         if self._factor_key != key:
-            A = self.hess / (1.0 + L)
-            d = torch.diagonal(self.hess)
-            A.diagonal().copy_(d + L * (1.0 + d))
-            chol, info = torch.linalg.cholesky_ex(A)
+            self._chol_work, info = chol_factor(self.hess, L, work=getattr(self, "_chol_work", None))
             if int(info.item()) == 0:
-                self._factor = ("chol", chol)
+                self._factor = ("chol", self._chol_work)
             else:
+                A = self.hess / (1.0 + L)
+                d = torch.diagonal(self.hess)
+                A.diagonal().copy_(d + L * (1.0 + d))
                 self._factor = ("lu",) + tuple(torch.linalg.lu_factor(A))
+                del A
             self._factor_key = key
-            del A
         if self._factor[0] == "chol":
-            return torch.cholesky_solve(rhs.reshape(-1, 1), self._factor[1]).reshape(-1)
+            return chol_solve(self._factor[1], rhs)
         return torch.linalg.lu_solve(self._factor[1], self._factor[2], rhs.reshape(-1, 1)).reshape(-1)
 
     @torch.no_grad()

@@ -286,8 +286,6 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
             up = int(np.round(float(region.pixel_length) / float(pwin.pixel_length)))
             if up < 1:
                 raise SpecificationConflict(f"{comp.name}: the PSF's pixels are larger than the image's")
-            if up > 1 and not isinstance(psf, PSF_Image):
-                raise SpecificationConflict("super-sampled PSF *models* (psf_upscale > 1) are not supported by astrophot_b200")
             if up > 16:
                 raise SpecificationConflict(f"{comp.name}: psf_upscale = {up} > 16")
             if id(psf) not in psf_index:
@@ -366,12 +364,15 @@ def lower(model, window=None, for_fit=False, chunk_jacobian=True):
         if not isinstance(pm, PSF_Model) or getattr(pm, "_kind", None) is None:
             raise SpecificationConflict(
                 f"PSF model type '{pm.model_type}' is outside the hot-path scope of astrophot_b200 (SURVEY.md §8f)")
+        # super-sampled PSF model (point_source.py:123-127,181): sampled on pixels 1 / up of the image's, block-summed back
         up = int(np.round(float(region.pixel_length) / float(pm.target.window.pixel_length)))
-        if up != 1:
-            raise SpecificationConflict("super-sampled PSFs (psf_upscale > 1) are not implemented yet (SURVEY.md §8f)")
+        if not 1 <= up <= 16:
+            raise SpecificationConflict(f"{comp.name}: psf_upscale = {up} outside 1..16")
         if getattr(pm, "model_integrated", False) is not False:
             raise SpecificationConflict("model_integrated PSF models are not supported by astrophot_b200")
-        return build_source(pm, ii, region, out, fwd, jac, host=comp)
+        src = build_source(pm, ii, region, out, fwd, jac, host=comp)
+        src.upscale = up
+        return src
 
     for comp in _components(model):
         if isinstance(comp, Component_Model) and comp._kind is None:

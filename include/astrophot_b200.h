@@ -218,6 +218,15 @@ int apb_plan_reserve(apb_plan_t *plan, const int64_t *caps);
  * H: device P*P (not modified), g, h: device P.  info: device int, 0 ok. */
 int apb_lm_solve(const double *H, const double *g, double L, int P, double *h, int *info, void *stream);
 
+/* The same damped system, dense, beyond the single-CTA solver (fit/lm.py:359-371 with a few hundred to a few thousand
+ * parameters some of which are shared between sources: joint multi-band fits, auxiliary PSF models).  The matrix is
+ * symmetric positive definite for L > 0: apb_chol_factor builds it from H and factors it (blocked Cholesky, one persistent
+ * cooperative kernel), apb_chol_solve serves any number of right-hand sides -- the two solves of a lambda-trial
+ * (lm.py:274,283) share one factor.  W: device, P*P + 2 doubles.  info: device int, 0 ok, 1 = a pivot was not positive
+ * (non-finite H): solve another way.  rhs and x may alias. */
+int apb_chol_factor(const double *H, double L, int P, double *W, int *info, void *stream);
+int apb_chol_solve(const double *W, const double *rhs, int P, double *x, void *stream);
+
 /* The same damped system for large parameter counts (crowded fields, fit/lm.py:359-371 with P ~ 1e4):
  * J^T W J of the last apb_normal_eq is kept inside the plan as its list of <= 8x8 source-pair blocks, and the
  * system is solved by block-Jacobi preconditioned conjugate gradients in one persistent cooperative kernel.

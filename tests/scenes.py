@@ -317,6 +317,22 @@ def build(ap, name, data=None):
         models.append(sky)
         g = M(name="grp_up2", model_type="group model", models=models, target=tar, psf_mode="full")
         return g, {}
+    if name == "point_psf_model_up2":
+        # point source drawn from a PSF model whose grid is 2x finer than the image (point_source.py:122-143,181)
+        ptar = ap.image.PSF_Image(data=np.zeros((25, 25)), pixelscale=0.4)
+        pm = M(name="ppu_psf", model_type="moffat psf model", target=ptar, parameters={"n": 2.2, "Rd": 2.0})
+        tar = _target(ap, (36, 40), data, pixelscale=0.8)
+        m = M(name="ppu", model_type="point model", target=tar, psf=pm,
+              parameters={"center": [15.3, 13.9], "flux": 1.2})
+        return m, {}
+    if name == "aux_psf_up2":
+        # galaxy convolved with a PSF *model* sampled on a grid 2x finer than the image; PSF width fitted with the galaxy
+        ptar = ap.image.PSF_Image(data=np.zeros((15, 15)), pixelscale=0.5)
+        pm = M(name="auxu", model_type="gaussian psf model", target=ptar, parameters={"sigma": 1.1})
+        tar = _target(ap, (44, 48), data)
+        m = M(name=name, model_type="sersic galaxy model", target=tar, psf_mode="full", psf=pm,
+              parameters={"center": [23.7, 20.4], "q": 0.6, "PA": 0.8, "n": 2.2, "Re": 5.5, "Ie": 0.9})
+        return m, {}
     if name == "moffat_psf_model":
         # a PSF model fitted to a star cut-out held as a PSF_Image (no variance: unit weights)
         ptar = ap.image.PSF_Image(data=np.zeros((25, 25)) if data is None else data[0]["data"], pixelscale=1.0)
@@ -366,7 +382,7 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
                  "group_nosky", "joint", "moffat_psf_model", "gaussian_psf_model", "crowded", "aux_psf_moffat",
                  "aux_psf_gauss_noshift", "sersic_trapezoid", "group_meanref", "plane_sky_group", "masked_locked_edge", "psf_sheared_novar", "sersic_knobs",
                  "point_psf_model", "point_psf_model_group", "group_edge", "sersic_modelmask", "psf_sersic_modelmask",
-                 "psf_sersic_lanczos3", "lanczos_group", "psf_sersic_up2", "group_up2"]
+                 "psf_sersic_lanczos3", "lanczos_group", "psf_sersic_up2", "group_up2", "point_psf_model_up2", "aux_psf_up2"]
 # psf_upscale that is not a power of two: the reference forms 1 / psf_upscale in float32 (model_object.py:313-314 ->
 # window_object.py:233-239), which perturbs the fine pixel scale by 3e-8 and floors the fine window one pixel short, so
 # that the last image row and column of the model stay empty.  astrophot_b200 (and the oracle) use the exact grid; the
@@ -378,7 +394,7 @@ LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nos
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
              "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18,
              "psf_sersic_modelmask": 19, "psf_sersic_lanczos3": 20, "lanczos_group": 21,
-             "psf_sersic_up2": 22, "group_up2": 23}
+             "psf_sersic_up2": 22, "group_up2": 23, "point_psf_model_up2": 24, "aux_psf_up2": 25}
 CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe

@@ -181,7 +181,8 @@ def test_sample_vs_oracle_and_reference(name):
 
 @pytest.mark.parametrize("name,conv", [("psf_sersic_up3_direct", None), ("psf_sersic_up3_direct", "fft"),
                                        ("psf_sersic_up2", "direct"), ("psf_sersic_up2", "fft"),
-                                       ("group_up2", "direct"), ("group_up2", "fft")])
+                                       ("group_up2", "direct"), ("group_up2", "fft"),
+                                       ("aux_psf_up2", "direct"), ("aux_psf_up2", "fft"), ("point_psf_model_up2", None)])
 def test_supersampled_psf_both_convolutions(name, conv):
     """Super-sampled PSFs (model_object.py:312-315,348-349; point_source.py:147-149,181): fine-grid sampling and
     convolution, block-summed back by k_reduce_up, through both convolution kernels, against the oracle (for
@@ -428,6 +429,41 @@ def test_sparse_pcg_refuses_shared_parameters():
     plan = _plan(scene)
     H, g, _ = plan.normal_eq(fix["x0"], as_rep=True, check=True)
     assert plan.solve_sparse(g, 1.0) is None
+
+
+@pytest.mark.parametrize("P", [1, 31, 32, 33, 160, 333, 1000, 2049])
+def test_dense_cholesky_solver(P):
+    """apb_chol_factor / apb_chol_solve (the dense damped system beyond the single-CTA solver, fit/lm.py:359-371)
+    against a library solve of the same matrix; one factor serves several right-hand sides; a non-finite matrix is
+    reported, not solved."""
+    from astrophot_b200.cabi import chol_factor, chol_solve
+    g = torch.Generator(device="cuda").manual_seed(100 + P)
+    J = torch.randn(2 * P + 7, P, dtype=torch.float64, device="cuda", generator=g) * torch.logspace(-2, 2, P, dtype=torch.float64, device="cuda")
+    H = J.T @ J
+    work = None
+    for L in (1.0, 1e-3, 1e-7):
+        A = H / (1.0 + L)
+        d = torch.diagonal(H)
+        A.diagonal().copy_(d + L * (1.0 + d))
+        work, info = chol_factor(H, L, work=work)
+        assert int(info.item()) == 0
+        Lref = torch.linalg.cholesky(A)
+        F = work[:P * P].reshape(P, P).tril()
+        if L == 1.0:     # (well conditioned: the two factorisations agree far below the matrix's own rounding)
+            assert float((F - Lref).abs().max() / Lref.abs().max()) < 1e-9
+        for k in range(2):
+            rhs = torch.randn(P, dtype=torch.float64, device="cuda", generator=g)
+            x = chol_solve(work, rhs)
+            resid = A @ x - rhs
+            assert float(resid.abs().max()) <= 1e-10 * float((A.abs() @ x.abs()).max())
+            want = torch.cholesky_solve(rhs.reshape(-1, 1), Lref).reshape(-1)
+            assert float((x - want).abs().max()) <= 1e-7 * float(want.abs().max()) * max(1.0, 1e-4 / L)
+            y = rhs.clone()
+            chol_solve(work, y, out=y)       # in place
+            assert torch.equal(x, y)
+    H[P // 2, P // 2] = float("nan")
+    _, info = chol_factor(H, 1.0, work=work)
+    assert int(info.item()) == 1
 
 
 def test_public_api_sample_and_jacobian():
