@@ -423,6 +423,81 @@ def perturb(x_rep, seed, scale=0.05):
 
 
 # ---------------------------------------------------------------------------
+# random scenes with super-sampled PSFs (oracle/fuzz_reference_upscale.py: reference vs oracle; test_cuda_parity: CUDA vs oracle)
+# ---------------------------------------------------------------------------
+def upscale_fuzz_builders(n=12, seed=4242):
+    """[(description, build(ap) -> model)]: groups of PSF-convolved galaxies of mixed families on their own windows, point
+    sources (PSF image, or a PSF model on the finer grid), unconvolved models and a sky on a target whose PSF has pixels
+    1/2 or 1/4 of the image's (model_object.py:312-315,348-349, point_source.py:123-127,147-149,181)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        up = int(rng.choice([2, 4]))
+        sheared = bool(rng.integers(0, 2))
+        S = np.array([[0.8, 0.07], [-0.05, 0.9]]) if sheared else np.eye(2) * float(rng.choice([1.0, 0.5]))
+        H, W = int(rng.integers(40, 60)), int(rng.integers(40, 60))
+        pw = int(rng.choice([5, 7])) * up + 1
+        pw += 1 - pw % 2
+        psf_model_points = bool(rng.integers(0, 2))
+        specs = []
+        for g in range(int(rng.integers(1, 4))):
+            fam = str(rng.choice(["sersic", "exponential", "gaussian", "moffat"]))
+            cx, cy = rng.uniform(8, W - 8), rng.uniform(8, H - 8)
+            half = int(rng.integers(8, 16))
+            win = [[max(0, int(cx) - half), min(W, int(cx) + half)], [max(0, int(cy) - half), min(H, int(cy) + half)]]
+            c = S @ np.array([cx, cy])
+            pars = {"center": [float(c[0]), float(c[1])], "q": float(rng.uniform(0.3, 0.9)), "PA": float(rng.uniform(0, np.pi))}
+            sc_ = float(np.sqrt(abs(np.linalg.det(S))))
+            if fam == "sersic":
+                pars.update(n=float(rng.uniform(0.7, 4.0)), Re=float(rng.uniform(2, 5) * sc_), Ie=float(rng.uniform(-0.5, 1)))
+            elif fam == "exponential":
+                pars.update(Re=float(rng.uniform(2, 5) * sc_), Ie=float(rng.uniform(-0.5, 1)))
+            elif fam == "gaussian":
+                pars.update(sigma=float(rng.uniform(1.5, 3) * sc_), flux=float(rng.uniform(0.5, 2)))
+            else:
+                pars.update(n=float(rng.uniform(1.2, 3.0)), Rd=float(rng.uniform(2, 4) * sc_), I0=float(rng.uniform(-0.5, 1)))
+            kw = dict(sampling_mode=str(rng.choice(["midpoint", "simpsons", "quad:3", "trapezoid"])),
+                      integrate_mode=str(rng.choice(["threshold", "threshold", "none"])),
+                      sampling_tolerance=float(rng.choice([1e-2, 1e-3])), integrate_max_depth=int(rng.choice([2, 3])),
+                      psf_mode=str(rng.choice(["full", "full", "none"])), psf_subpixel_shift=str(rng.choice(["bilinear", "none"])),
+                      psf_convolve_mode=str(rng.choice(["fft", "direct"])))
+            specs.append((f"{fam} galaxy model", win, pars, kw))
+        pts = []
+        for s in range(int(rng.integers(1, 3))):
+            cx, cy = rng.uniform(2, W - 2), rng.uniform(2, H - 2)
+            c = S @ np.array([cx, cy])
+            pts.append(([[max(0, int(cx) - 6), min(W, int(cx) + 7)], [max(0, int(cy) - 6), min(H, int(cy) + 7)]],
+                        {"center": [float(c[0]), float(c[1])], "flux": float(rng.uniform(0.5, 2))},
+                        str(rng.choice(["bilinear", "lanczos:3"]))))
+
+        def build(ap, k=k, up=up, S=S, H=H, W=W, pw=pw, psf_model_points=psf_model_points, specs=specs, pts=pts):
+            psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 0.9 * up + 0.05 * pw, pw), pixelscale=S / up)
+            tar = ap.image.Target_Image(data=np.zeros((H, W)), pixelscale=S, zeropoint=22.5, psf=psf)
+            M = ap.models.AstroPhot_Model
+            models = [M(name=f"u{k}m{i}", model_type=mt, target=tar, window=win, parameters=dict(pars), **kw)
+                      for i, (mt, win, pars, kw) in enumerate(specs)]
+            pm = None
+            if psf_model_points:
+                ptar = ap.image.PSF_Image(data=np.zeros((6 * up + 1, 6 * up + 1)), pixelscale=S / up)
+                pm = M(name=f"u{k}pm", model_type="moffat psf model", target=ptar, normalize_psf=False,
+                       parameters={"n": 2.4, "Rd": 1.6 * float(np.sqrt(abs(np.linalg.det(S)))), "I0": -0.5})
+            for i, (win, pars, shift) in enumerate(pts):
+                if pm is not None and i == 0:
+                    models.append(M(name=f"u{k}p{i}", model_type="point model", target=tar, window=win, parameters=dict(pars), psf=pm))
+                else:
+                    models.append(M(name=f"u{k}p{i}", model_type="point model", target=tar, window=win, parameters=dict(pars),
+                                    psf_subpixel_shift=shift))
+            sky = M(name=f"u{k}sky", model_type="flat sky model", target=tar, parameters={"F": -1.5})
+            sky.initialize()
+            return M(name=f"u{k}", model_type="group model", models=models + [sky], target=tar, psf_mode="full")
+
+        desc = (f"{W}x{H} up={up} sheared={int(sheared)} psf={pw} models={len(specs)}+{len(pts)} "
+                f"psf_model_point={int(psf_model_points)}")
+        out.append((desc, up, build))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # model.initialize(): models built WITHOUT parameter values on noisy data (oracle/make_init_golden.py)
 # ---------------------------------------------------------------------------
 INIT_SCENES = ["init_sersic", "init_sersic_fixed_shape", "init_exponential", "init_gaussian", "init_moffat", "init_spline",

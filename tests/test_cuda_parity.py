@@ -207,6 +207,26 @@ def test_supersampled_psf_both_convolutions(name, conv):
     assert plan.stats()["overflow"] == 0
 
 
+@pytest.mark.parametrize("k", range(8))
+def test_supersampled_psf_random_groups(k):
+    """Random groups on targets with 2x / 4x super-sampled PSFs (scenes.upscale_fuzz_builders; the oracle agrees with the
+    reference on the very same scenes to 2.2e-14, oracle/fuzz_reference_upscale.py): CUDA against the oracle."""
+    desc, up, build = scenes.upscale_fuzz_builders()[k]
+    model = build(ap)
+    scene, _ = lower(model)
+    assert max(s.upscale for s in scene.sources) == up
+    x = model.parameters.vector_values().numpy()
+    plan = _plan(scene)
+    got = plan.sample(x, as_rep=False)[0].cpu().numpy()
+    want = orc.sample(scene, x, as_rep=False)[0]
+    assert rel_err(got, want) < 1e-10, desc
+    J = plan.jacobian(x, as_rep=False)[0].cpu().numpy()
+    Jo = orc.jacobian(scene, x, as_rep=False)[0]
+    scale = np.maximum(np.abs(Jo).reshape(-1, Jo.shape[-1]).max(axis=0), 1e-300)
+    assert np.max(np.abs(J - Jo) / scale) < 1e-9, desc
+    assert plan.stats()["overflow"] == 0
+
+
 @pytest.mark.parametrize("name", scenes.SAMPLE_SCENES)
 @pytest.mark.parametrize("tag", ["rep", "nat"])
 def test_jacobian_vs_oracle_and_reference(name, tag):

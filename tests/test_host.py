@@ -346,3 +346,29 @@ def test_parameter_order_of_every_model_family():
     have = {m.model_type: tuple(m._parameter_order) for m in ap.models.AstroPhot_Model.List_Models(usable=True)
             if m.model_type != "group model"}
     assert have == want
+
+
+def test_supersampled_psf_lowering():
+    """psf_upscale (model_object.py:312-315, point_source.py:123-127,147-149): lowered as `upscale` on the sources that have
+    a PSF, windows left in image pixels; the oracle's fine-grid sampling conserves what the image-pixel sampling gives for
+    a smooth source."""
+    import scenes
+    from astrophot_b200 import scene as sc
+    from astrophot_b200.lowering import lower, tile_scene
+    ap.AP_config.ap_device = "cpu"
+    for desc, up, build in scenes.upscale_fuzz_builders(4):
+        scene, _ = lower(build(ap))
+        for s in scene.sources:
+            has_psf = s.psf >= 0 or bool(s.flags & sc.FLAG_AMP)
+            assert s.upscale == (up if has_psf else 1), (desc, s.name)
+            im = scene.images[s.image]
+            assert s.out[0] >= 0 and s.out[0] + s.out[2] <= im.W and s.out[1] + s.out[3] <= im.H
+        cut = tile_scene(scene, 2, 2)
+        assert {s.upscale for s in cut.sources} == {s.upscale for s in scene.sources}
+    model, _ = scenes.build(ap, "psf_sersic_up2")
+    assert [s.upscale for s in lower(model)[0].sources] == [2]
+    tar = ap.image.Target_Image(data=np.zeros((20, 20)), pixelscale=0.5,
+                                psf=ap.image.PSF_Image(data=np.ones((5, 5)), pixelscale=1.0))
+    m = ap.models.AstroPhot_Model(name="coarse", model_type="point model", target=tar, parameters={"center": [5, 5], "flux": 1})
+    with pytest.raises(ap.errors.SpecificationConflict):
+        lower(m)
