@@ -1721,8 +1721,12 @@ extern "C" int apb_chol_factor(const double* H, double L, int P, double* W, int*
   CU(cudaMemsetAsync(bar, 0, 2 * sizeof(double), st));
   const int nb = (P + CH_NB - 1) / CH_NB;
   // (no more CTAs than the widest phase has tiles: the barriers cost by the number of arrivals)
-  const int grid = std::max(1, std::min(n_sm, std::max(nb * (nb - 1) / 2, (int)std::min<long long>((long long)P * P / CH_NT + 1, n_sm))));
-  CholArgs A{H, L, P, W, info, bar};
+  int grid = std::max(1, std::min(n_sm, std::max(nb * (nb - 1) / 2, (int)std::min<long long>((long long)P * P / CH_NT + 1, n_sm))));
+  // (APB_CHOL_GRID / APB_CHOL_RELAXED: tuning knobs for experiments)
+  if (const char* e = getenv("APB_CHOL_GRID")) grid = std::max(1, std::min(n_sm, atoi(e)));
+  int relaxed = 0;
+  if (const char* e = getenv("APB_CHOL_RELAXED")) relaxed = atoi(e);
+  CholArgs A{H, L, P, W, info, bar, relaxed};
   void* args[] = {&A};
   CU(cudaLaunchCooperativeKernel((void*)k_chol_factor, dim3(grid), dim3(CH_NT), args, 0, st));
   g_launches++;
@@ -1733,7 +1737,7 @@ extern "C" int apb_chol_factor(const double* H, double L, int P, double* W, int*
 extern "C" int apb_chol_solve(const double* W, const double* rhs, int P, double* x, void* stream) {
   if (P <= 0) return 0;
   if (!W || !rhs || !x) APB_FAIL("apb_chol_solve: NULL argument");
-  k_chol_solve<<<1, CH_NT, 0, (cudaStream_t)stream>>>(W, rhs, P, x);
+  k_chol_solve<<<1, CH_SOLVE_NT, 0, (cudaStream_t)stream>>>(W, rhs, P, x);
   CU(cudaGetLastError());
   g_launches++;
   return 0;

@@ -23,20 +23,29 @@ struct CholArgs {
   double* W;           // P x P workspace: the factor (lower triangle, row-major) on return
   int* info;           // 0 ok, 1 a pivot was not positive (not finite)
   unsigned int* bar;   // grid barrier counter, zero at launch
+  int relaxed;         // poll the counter with relaxed loads (everything read across CTAs goes through ld.cg anyway)
 };
 
 // all CTAs resident (cooperative launch).  Release on arrival, acquire on leaving: data written to W by other CTAs before
 // the barrier is read after it (with ld.cg: no line of W may be served from this SM's L1).
-__device__ __forceinline__ void chol_barrier(unsigned int* counter, unsigned int& goal) {
+__device__ __forceinline__ void chol_barrier(unsigned int* counter, unsigned int& goal, int relaxed) {
   __syncthreads();
   if (threadIdx.x == 0) {
     goal += gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
     unsigned int seen;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-      if (seen >= goal) break;
-      __nanosleep(64);
+    if (relaxed) {
+      // (as apb_solve.cuh's pcg_barrier: no acquire, hence no invalidation of L1 -- no line of W is ever served from L1)
+      for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        if (seen >= goal) break;
+      }
+    } else {
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        if (seen >= goal) break;
+        __nanosleep(32);
+      }
     }
   }
   __syncthreads();
@@ -46,6 +55,7 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
   __shared__ double sD[CH_NB][CH_NB + 1];   // diagonal tile -> its factor
   __shared__ double sA[CH_NB][CH_NB + 1];
   __shared__ double sB[CH_NB][CH_NB + 1];
+  __shared__ double sdiag[CH_NB];
   __shared__ int s_bad;
   const int P = A.P, nb = (P + CH_NB - 1) / CH_NB;
   const int tid = threadIdx.x;
@@ -59,7 +69,7 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
     const double hij = A.H[q];
     W[q] = (i == j) ? hij + L * (1.0 + hij) : hij * off;
   }
-  chol_barrier(A.bar, goal);
+  chol_barrier(A.bar, goal, A.relaxed);
   for (int kb = 0; kb < nb; ++kb) {
     const int k0 = kb * CH_NB, kn = min(CH_NB, P - k0);
     // ---- diagonal tile, factored by every CTA for itself (identity beyond the matrix)
@@ -68,23 +78,29 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
       sD[r][c] = (r < kn && c < kn) ? __ldcg(W + (long long)(k0 + r) * P + (k0 + c)) : (r == c ? 1.0 : 0.0);
     }
     __syncthreads();
+    // (one block barrier per column: the trailing entries are updated with the unscaled column, a_rc a_cc / d_c, and the
+    //  columns are scaled by 1 / sqrt(d_c) at the end)
     for (int c = 0; c < kn; ++c) {
-      if (tid == 0) {
-        double d = sD[c][c];
-        if (!(d > 0.0) || !(d < 1.7e308)) { s_bad = 1; d = 1.0; }
-        sD[c][c] = sqrt(d);
-      }
-      __syncthreads();
-      const double dinv = 1.0 / sD[c][c];
-      if (tid > c && tid < kn) sD[tid][c] *= dinv;
-      __syncthreads();
+      const double d = sD[c][c];
+      if (tid == 0 && (!(d > 0.0) || !(d < 1.7e308))) s_bad = 1;
+      const double dinv = 1.0 / d;
       for (int q = tid; q < kn * kn; q += CH_NT) {
         const int r = q / kn, cc = q - r * kn;
-        if (cc > c && r >= cc) sD[r][cc] -= sD[r][c] * sD[cc][c];
+        if (cc > c && r >= cc) sD[r][cc] -= sD[r][c] * sD[cc][c] * dinv;
       }
       __syncthreads();
     }
-    // ---- panel: X L_kk^T = A_ik for the row tiles below, a thread per row
+    if (tid < CH_NB) sdiag[tid] = sqrt(sD[tid][tid]);
+    __syncthreads();
+    for (int q = tid; q < CH_NB * CH_NB; q += CH_NT) {
+      const int r = q / CH_NB, c = q - r * CH_NB;
+      if (r > c) sD[r][c] = sD[r][c] / sdiag[c];
+      else if (r == c) sD[r][c] = sdiag[c];
+    }
+    __syncthreads();
+    // ---- panel: X L_kk^T = A_ik for the row tiles below.  Eight threads per row (four rows per warp): column c of X
+    //      needs the columns before it, x_rc = (a_rc - sum_{m<c} x_rm l_cm) / l_cc -- the eight share the sum, a warp
+    //      barrier per column keeps the row's new entry visible to them
     for (int ib = kb + 1 + blockIdx.x; ib < nb; ib += gridDim.x) {
       const int i0 = ib * CH_NB, in = min(CH_NB, P - i0);
       __syncthreads();
@@ -93,11 +109,16 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
         sA[r][c] = (r < in && c < kn) ? __ldcg(W + (long long)(i0 + r) * P + (k0 + c)) : 0.0;
       }
       __syncthreads();
-      if (tid < in) {
+      {
+        const int r = tid >> 3, sub = tid & 7;
         for (int c = 0; c < kn; ++c) {
-          double v = sA[tid][c];
-          for (int m = 0; m < c; ++m) v -= sA[tid][m] * sD[c][m];
-          sA[tid][c] = v / sD[c][c];
+          double part = 0.0;
+          for (int m = sub; m < c; m += 8) part = fma(sA[r][m], sD[c][m], part);
+          part += __shfl_xor_sync(0xffffffffu, part, 4);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          if (sub == 0) sA[r][c] = (sA[r][c] - part) / sD[c][c];
+          __syncwarp();
         }
       }
       __syncthreads();
@@ -106,7 +127,7 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
         if (r < in && c < kn) W[(long long)(i0 + r) * P + (k0 + c)] = sA[r][c];
       }
     }
-    chol_barrier(A.bar, goal);
+    chol_barrier(A.bar, goal, A.relaxed);
     // (the factored diagonal tile goes back only now: before the barrier a slower CTA may still be loading the tile)
     if (blockIdx.x == 0)
       for (int q = tid; q < kn * kn; q += CH_NT) {
@@ -141,29 +162,40 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
         }
       }
     }
-    chol_barrier(A.bar, goal);
+    chol_barrier(A.bar, goal, A.relaxed);
   }
   if (blockIdx.x == 0 && tid == 0) *A.info = s_bad;
 }
 
-// L y = rhs, L^T x = y with the factor of k_chol_factor (lower triangle of W, row-major).  One CTA of 256 threads.
-// x doubles as the work vector; rhs may alias x.
-__global__ void __launch_bounds__(CH_NT) k_chol_solve(const double* __restrict__ W, const double* rhs, int P, double* x) {
+// L y = rhs, L^T x = y with the factor of k_chol_factor (lower triangle of W, row-major).  One CTA (CH_SOLVE_NT threads:
+// the substitution is a chain of P / 32 dependent steps, each a strip of the factor read once -- what matters is how many
+// loads the one SM keeps in flight).  x doubles as the work vector; rhs may alias x.
+#define CH_SOLVE_NT 1024
+__global__ void __launch_bounds__(CH_SOLVE_NT) k_chol_solve(const double* __restrict__ W, const double* rhs, int P, double* x) {
   __shared__ double sT[CH_NB][CH_NB + 1];
   __shared__ double sy[CH_NB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = (P + CH_NB - 1) / CH_NB;
   for (int kb = 0; kb < nb; ++kb) {
     const int k0 = kb * CH_NB, kn = min(CH_NB, P - k0);
-    for (int r = warp; r < kn; r += CH_NT / 32) {
+    if (warp < kn) {       // a warp per row of the block: rhs_r - sum_{j < k0} L_rj y_j
+      const int r = warp;
       const double* row = W + (long long)(k0 + r) * P;
-      double acc = 0.0;
-      for (int j = lane; j < k0; j += 32) acc = fma(row[j], x[j], acc);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int j = lane;
+      for (; j + 96 < k0; j += 128) {
+        a0 = fma(row[j], x[j], a0);
+        a1 = fma(row[j + 32], x[j + 32], a1);
+        a2 = fma(row[j + 64], x[j + 64], a2);
+        a3 = fma(row[j + 96], x[j + 96], a3);
+      }
+      for (; j < k0; j += 32) a0 = fma(row[j], x[j], a0);
+      double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lane == 0) sy[r] = rhs[k0 + r] - acc;
     }
-    for (int q = tid; q < CH_NB * CH_NB; q += CH_NT) {
+    for (int q = tid; q < CH_NB * CH_NB; q += CH_SOLVE_NT) {
       const int r = q / CH_NB, c = q - r * CH_NB;
       sT[r][c] = (r < kn && c <= r) ? W[(long long)(k0 + r) * P + (k0 + c)] : (r == c ? 1.0 : 0.0);
     }
@@ -181,7 +213,7 @@ __global__ void __launch_bounds__(CH_NT) k_chol_solve(const double* __restrict__
   }
   for (int kb = nb - 1; kb >= 0; --kb) {
     const int k0 = kb * CH_NB, kn = min(CH_NB, P - k0);
-    for (int q = tid; q < CH_NB * CH_NB; q += CH_NT) {
+    for (int q = tid; q < CH_NB * CH_NB; q += CH_SOLVE_NT) {
       const int r = q / CH_NB, c = q - r * CH_NB;
       sT[r][c] = (r < kn && c <= r) ? W[(long long)(k0 + r) * P + (k0 + c)] : (r == c ? 1.0 : 0.0);
     }
@@ -194,13 +226,20 @@ __global__ void __launch_bounds__(CH_NT) k_chol_solve(const double* __restrict__
         else if (lane < c) v -= sT[c][lane] * xc;
       }
       if (lane < kn) x[k0 + lane] = v;
-      if (lane < CH_NB) sy[lane] = lane < kn ? v : 0.0;
+      sy[lane] = lane < kn ? v : 0.0;
     }
     __syncthreads();
-    for (int j = tid; j < k0; j += CH_NT) {
-      double acc = 0.0;
-      for (int r = 0; r < kn; ++r) acc = fma(W[(long long)(k0 + r) * P + j], sy[r], acc);
-      x[j] -= acc;
+    // y_j -= sum_r L_(k0+r, j) x_(k0+r) for the columns before the block: a thread per column, rows read coalesced
+    for (int j = tid; j < k0; j += CH_SOLVE_NT) {
+      const double* col = W + (long long)k0 * P + j;
+      double a0 = 0.0, a1 = 0.0;
+      int r = 0;
+      for (; r + 1 < kn; r += 2) {
+        a0 = fma(col[(long long)r * P], sy[r], a0);
+        a1 = fma(col[(long long)(r + 1) * P], sy[r + 1], a1);
+      }
+      if (r < kn) a0 = fma(col[(long long)r * P], sy[r], a0);
+      x[j] -= a0 + a1;
     }
     __syncthreads();
   }

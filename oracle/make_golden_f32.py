@@ -15,7 +15,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 SCENES = ["c1_sersic", "sersic_sheared", "exponential", "gaussian", "moffat", "spline", "psf_sersic", "group", "crowded",
-          "moffat_psf_model"]
+          "moffat_psf_model", "group_up2", "psf_sersic_up2"]
 
 
 def main(names):

@@ -751,7 +751,7 @@ def test_float32_images_are_accepted_and_returned():
 
 
 F32_SCENES = ["c1_sersic", "sersic_sheared", "exponential", "gaussian", "moffat", "spline", "psf_sersic", "group", "crowded",
-              "moffat_psf_model"]
+              "moffat_psf_model", "group_up2", "psf_sersic_up2"]
 
 
 @pytest.mark.parametrize("name", F32_SCENES)
