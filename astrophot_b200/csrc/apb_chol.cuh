@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
   __shared__ double sD[CH_NB][CH_NB + 1];   // diagonal tile -> its factor
   __shared__ double sA[CH_NB][CH_NB + 1];
   __shared__ double sB[CH_NB][CH_NB + 1];
-  __shared__ double sdiag[CH_NB];
+  __shared__ double sdiag[CH_NB], sdinv[CH_NB];
   __shared__ int s_bad;
   const int P = A.P, nb = (P + CH_NB - 1) / CH_NB;
   const int tid = threadIdx.x;
@@ -80,21 +80,28 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
     __syncthreads();
     // (one block barrier per column: the trailing entries are updated with the unscaled column, a_rc a_cc / d_c, and the
     //  columns are scaled by 1 / sqrt(d_c) at the end)
+    // (a general fp64 division is a chain of ~50 instructions and sat on the critical path of every column: the pivot's
+    //  reciprocal is __drcp_rn, every other division a multiplication by a reciprocal formed once per tile)
     for (int c = 0; c < kn; ++c) {
       const double d = sD[c][c];
       if (tid == 0 && (!(d > 0.0) || !(d < 1.7e308))) s_bad = 1;
-      const double dinv = 1.0 / d;
-      for (int q = tid; q < kn * kn; q += CH_NT) {
-        const int r = q / kn, cc = q - r * kn;
-        if (cc > c && r >= cc) sD[r][cc] -= sD[r][c] * sD[cc][c] * dinv;
+      const double dinv = __drcp_rn(d);
+#pragma unroll
+      for (int q = tid; q < CH_NB * CH_NB; q += CH_NT) {
+        const int r = q >> 5, cc = q & 31;
+        if (cc > c && r >= cc && r < kn) sD[r][cc] -= sD[r][c] * sD[cc][c] * dinv;
       }
       __syncthreads();
     }
-    if (tid < CH_NB) sdiag[tid] = sqrt(sD[tid][tid]);
+    if (tid < CH_NB) {
+      const double sq = sqrt(sD[tid][tid]);
+      sdiag[tid] = sq;
+      sdinv[tid] = 1.0 / sq;
+    }
     __syncthreads();
     for (int q = tid; q < CH_NB * CH_NB; q += CH_NT) {
-      const int r = q / CH_NB, c = q - r * CH_NB;
-      if (r > c) sD[r][c] = sD[r][c] / sdiag[c];
+      const int r = q >> 5, c = q & 31;
+      if (r > c) sD[r][c] = sD[r][c] * sdinv[c];
       else if (r == c) sD[r][c] = sdiag[c];
     }
     __syncthreads();
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
           part += __shfl_xor_sync(0xffffffffu, part, 4);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
           part += __shfl_xor_sync(0xffffffffu, part, 1);
-          if (sub == 0) sA[r][c] = (sA[r][c] - part) / sD[c][c];
+          if (sub == 0) sA[r][c] = (sA[r][c] - part) * sdinv[c];
           __syncwarp();
         }
       }
@@ -151,14 +158,26 @@ __global__ void __launch_bounds__(CH_NT) k_chol_factor(CholArgs A) {
         sB[r][c] = (r < jn && c < kn) ? __ldcg(W + (long long)(j0 + r) * P + (k0 + c)) : 0.0;
       }
       __syncthreads();
-      for (int q = tid; q < CH_NB * CH_NB; q += CH_NT) {
-        const int r = q / CH_NB, c = q - r * CH_NB;      // c = lane: sB rows are 33 doubles apart, no bank conflict
-        if (r < in && c < jn) {
-          double acc = 0.0;
+      {
+        // thread (r0, c): rows r0, r0 + 8, r0 + 16, r0 + 24 of column c = lane (sB rows are 33 doubles apart: no bank
+        // conflict; sA reads are broadcasts); the four old values are on their way while the products are formed
+        const int r0 = tid >> 5, c = tid & 31;
+        double old[4], acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 8 * i;
+          old[i] = (r < in && c < jn) ? __ldcg(W + (long long)(i0 + r) * P + (j0 + c)) : 0.0;
+        }
 #pragma unroll 8
-          for (int k = 0; k < CH_NB; ++k) acc = fma(sA[r][k], sB[c][k], acc);
-          double* w = W + (long long)(i0 + r) * P + (j0 + c);
-          *w = __ldcg(w) - acc;
+        for (int k = 0; k < CH_NB; ++k) {
+          const double b = sB[c][k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fma(sA[r0 + 8 * i][k], b, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 8 * i;
+          if (r < in && c < jn) W[(long long)(i0 + r) * P + (j0 + c)] = old[i] - acc[i];
         }
       }
     }
@@ -202,8 +221,9 @@ __global__ void __launch_bounds__(CH_SOLVE_NT) k_chol_solve(const double* __rest
     __syncthreads();
     if (warp == 0) {
       double v = lane < kn ? sy[lane] : 0.0;
+      const double rinv = 1.0 / sT[lane][lane];      // (identity beyond the matrix)
       for (int c = 0; c < kn; ++c) {
-        const double yc = __shfl_sync(0xffffffffu, v, c) / sT[c][c];
+        const double yc = __shfl_sync(0xffffffffu, v * rinv, c);
         if (lane == c) v = yc;
         else if (lane > c) v -= sT[lane][c] * yc;
       }
@@ -220,8 +240,9 @@ __global__ void __launch_bounds__(CH_SOLVE_NT) k_chol_solve(const double* __rest
     __syncthreads();
     if (warp == 0) {
       double v = lane < kn ? x[k0 + lane] : 0.0;
+      const double rinv = 1.0 / sT[lane][lane];
       for (int c = kn - 1; c >= 0; --c) {
-        const double xc = __shfl_sync(0xffffffffu, v, c) / sT[c][c];
+        const double xc = __shfl_sync(0xffffffffu, v * rinv, c);
         if (lane == c) v = xc;
         else if (lane < c) v -= sT[c][lane] * xc;
       }
