@@ -8,8 +8,10 @@
 // k_chol_factor: one persistent cooperative kernel, right-looking blocked Cholesky on 32 x 32 tiles of a workspace copy
 //   in global memory (it lives in L2: P = 2000 is 32 MB).  Per block column: every CTA factors the diagonal tile itself
 //   in shared memory (cheaper than a third grid barrier), the panel tiles below it are dealt to the CTAs (triangular
-//   solve, a thread per row), grid barrier, the trailing tiles are dealt to the CTAs (rank-32 update), grid barrier.
-// k_chol_solve: forward and backward substitution by one CTA, row-wise (coalesced) reads of the factor.
+//   solve, eight threads per row), grid barrier, the trailing tiles are dealt to the CTAs (rank-32 update), grid barrier.
+//   Measured on B200 (profiles/r02_summary.md section 7): 161 / 871 / 2269 us at P = 200 / 1000 / 2000 -- the latency of a
+//   block column (~25 us), not the barriers, bandwidth or the FP64 pipe.
+// k_chol_solve: forward and backward substitution by one CTA of 1024 threads, row-wise (coalesced) reads of the factor.
 #pragma once
 #include <cuda_runtime.h>
 
