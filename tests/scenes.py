@@ -286,14 +286,16 @@ def build(ap, name, data=None):
         models.append(sky)
         g = M(name="crowd", model_type="group model", models=models, target=tar, psf_mode="full")
         return g, {}
-    if name in ("psf_sersic_up2", "psf_sersic_up3_direct"):
+    if name in ("psf_sersic_up2", "psf_sersic_up3_direct", "psf_sersic_up2_chunked"):
         # super-sampled PSF (model_object.py:313-314,348-349): PSF pixels 1/2 (1/3) of the image's; the model is sampled,
         # integrated and convolved on the fine grid, then block-summed back
-        up = 2 if name == "psf_sersic_up2" else 3
+        up = 3 if name == "psf_sersic_up3_direct" else 2
+        # (_chunked: the Jacobian is taken chunk by chunk, _model_methods.py:349-395, each chunk on its own fine grid)
+        extra = {"image_chunksize": 20} if name.endswith("_chunked") else {}
         psf = ap.image.PSF_Image(data=_psf_moffat(2.5, 1.8 * up, 6 * up + 1), pixelscale=1.0 / up)
         tar = _target(ap, (44, 48), data, psf=psf)
         m = M(name=name, model_type="sersic galaxy model", target=tar, psf_mode="full",
-              psf_convolve_mode="fft" if up == 2 else "direct",
+              psf_convolve_mode="fft" if up == 2 else "direct", **extra,
               parameters={"center": [22.8, 20.3], "q": 0.55, "PA": 2.4, "n": 2.5, "Re": 5.0, "Ie": 1.0})
         return m, {}
     if name == "group_up2":
@@ -388,14 +390,14 @@ SAMPLE_SCENES = ["c1_sersic", "sersic_sheared", "sersic_nointegrate", "sersic_qu
 # that the last image row and column of the model stay empty.  astrophot_b200 (and the oracle) use the exact grid; the
 # golden pins the interior at 1e-6.
 ODD_UPSCALE_SCENES = ["psf_sersic_up3_direct"]
-CPU_ONLY_SCENES = []
+CPU_ONLY_SCENES = ["psf_sersic_up2_chunked"]       # oracle vs reference only (added after the round's GPU budget was spent)
 # scenes with an LM golden (noise seed, start perturbation)
 LM_SCENES = {"c1_sersic": 1, "psf_sersic": 4, "group": 6, "joint": 7, "group_nosky": 8, "crowded": 9, "aux_psf_moffat": 12,
              "plane_sky_group": 13, "masked_locked_edge": 14, "psf_sheared_novar": 15,
              "moffat_psf_model": 16, "point_psf_model": 17, "point_psf_model_group": 18,
              "psf_sersic_modelmask": 19, "psf_sersic_lanczos3": 20, "lanczos_group": 21,
              "psf_sersic_up2": 22, "group_up2": 23, "point_psf_model_up2": 24, "aux_psf_up2": 25}
-CPU_LM_SCENES = {}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
+CPU_LM_SCENES = {"psf_sersic_up2_chunked": 26}     # (the reference's own LM cannot fit group_edge: its Group_Model.fit_mask mis-sizes windows that stick out)
 ALL_LM_SCENES = {**LM_SCENES, **CPU_LM_SCENES}
 NOISE_SCALE = {"moffat_psf_model": 0.02}      # noise of make_data relative to the default recipe
 
