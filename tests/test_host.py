@@ -372,3 +372,41 @@ def test_supersampled_psf_lowering():
     m = ap.models.AstroPhot_Model(name="coarse", model_type="point model", target=tar, parameters={"center": [5, 5], "flux": 1})
     with pytest.raises(ap.errors.SpecificationConflict):
         lower(m)
+
+
+def test_balanced_tile_cuts_partition_the_image():
+    """lowering._balanced_cuts / tile_scene(balance=True): whatever the cost profile, the cuts are strictly increasing, start
+    at 0 and end at the image edge, and the tiles own every pixel once; an empty cost profile gives the even cuts."""
+    from astrophot_b200.lowering import _balanced_cuts, lower, tile_scene
+    import scenes
+    rng = np.random.default_rng(8)
+    for trial in range(200):
+        L = int(rng.integers(4, 300))
+        n = int(rng.integers(1, min(L, 9) + 1))
+        kind = trial % 4
+        cost = (np.zeros(L), rng.uniform(0, 1, L), (rng.uniform(0, 1, L) > 0.97) * rng.uniform(0, 100, L),
+                np.concatenate([np.zeros(L - 1), [5.0]]))[kind]
+        cuts = _balanced_cuts(cost, n)
+        assert cuts[0] == 0 and cuts[-1] == L and len(cuts) == n + 1
+        assert all(b > a for a, b in zip(cuts, cuts[1:])), (trial, cuts)
+        if kind == 0:
+            assert cuts == [round(k * L / n) for k in range(n + 1)]
+        elif kind == 1 and L >= 20 * n:       # a smooth profile: every run within one element of the even share of the cost
+            tot = cost.sum()
+            for a, b in zip(cuts, cuts[1:]):
+                assert abs(cost[a:b].sum() - tot / n) <= 2 * cost.max() + 1e-12
+    ap.AP_config.ap_device = "cpu"
+    model, _ = scenes.build(ap, "crowded")
+    scene, _ = lower(model)
+    im0 = scene.images[0]
+    for ny, nx in ((1, 2), (2, 2), (2, 4), (3, 5)):
+        cut = tile_scene(scene, ny, nx)
+        seen = np.zeros((im0.H, im0.W), dtype=int)
+        for im in cut.images:
+            x0, y0 = (np.round(np.asarray(im0.rij) - np.asarray(im.rij))).astype(int)
+            seen[y0:y0 + im.H, x0:x0 + im.W] += 1
+        assert len(cut.images) == ny * nx and np.all(seen == 1)
+        # every piece of a source sits inside its tile
+        for s in cut.sources:
+            im = cut.images[s.image]
+            assert s.out[0] >= 0 and s.out[1] >= 0 and s.out[0] + s.out[2] <= im.W and s.out[1] + s.out[3] <= im.H
